@@ -1,0 +1,155 @@
+/*
+ * tscd_b200.h -- C-ABI of the B200-native TSCD aggregation stage (libtscd_b200.so).
+ *
+ * The reference (Video-Object-Detection/TSCD) has no FFI: its seam is the nn.Module head chosen in
+ * Exp.get_model() (exps/TSCD_OVIS/ovis_tscd_large.py:106-151).  Each entry point below replaces a
+ * group of eager PyTorch / torchvision / scipy calls inside TSCDHead.forward (yolox/models/tscd_head.py:
+ * 374-733); the reference interface it stands in for is cited next to it.  Python binds these with ctypes
+ * (tscd_b200/_lib.py); INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - no allocation inside: the caller provides outputs and workspaces sized for the worst case;
+ *   - row counts that depend on the data live in device memory (counts / prefix offsets); kernels are
+ *     launched over the worst case and exit early, so the whole stage runs without a host sync and can be
+ *     captured in a CUDA graph;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value: 0 on success, a negative TSCD_ERR_* otherwise (never throws).
+ */
+#ifndef TSCD_B200_H_
+#define TSCD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSCD_OK 0
+#define TSCD_ERR_INVALID_ARG (-1)
+#define TSCD_ERR_UNSUPPORTED (-2)
+#define TSCD_ERR_CAPACITY (-3)
+#define TSCD_ERR_CUDA (-4)
+
+/* element types of boundary / operand tensors */
+#define TSCD_F32 0
+#define TSCD_F16 1
+#define TSCD_BF16 2
+
+#define TSCD_MAX_LEVELS 3
+
+/* Strided view of one per-anchor quantity with `channels` channels over up to 3 FPN levels.
+ * element(frame f, level l, local anchor a, channel c) = ptr[l] + f*frame_stride[l] + a*anchor_stride[l]
+ *                                                        + c*chan_stride[l]            (strides in elements)
+ * Row-major [F,A,ch] tensors use one level; NCHW conv outputs use anchor_stride=1, chan_stride=H*W;
+ * channels_last conv outputs use chan_stride=1, anchor_stride=ch. */
+typedef struct {
+    const void* ptr[TSCD_MAX_LEVELS];
+    int64_t frame_stride[TSCD_MAX_LEVELS];
+    int64_t anchor_stride[TSCD_MAX_LEVELS];
+    int64_t chan_stride[TSCD_MAX_LEVELS];
+} tscd_view;
+
+/* Anchor geometry: level-major, row-major within a level (tscd_head.py:374-376, 755-766). */
+typedef struct {
+    int32_t num_levels;
+    int32_t level_h[TSCD_MAX_LEVELS];
+    int32_t level_w[TSCD_MAX_LEVELS];
+    int32_t level_stride[TSCD_MAX_LEVELS]; /* 8,16,32 */
+    int32_t level_start[TSCD_MAX_LEVELS + 1]; /* anchor offset of each level; [num_levels] = A */
+} tscd_anchors;
+
+/* ---- K1: decode + score + select -------------------------------------------------------------------
+ * Replaces: sigmoid/concat (tscd_head.py:357-359), decode_outputs (:755-770), the cxcywh->xyxy step,
+ * class max, thresholding and torch.topk of TSCDHead.postprocess_widx (:1561-1624, mode B) and of
+ * postpro_woclass (post_process.py:476-508, mode A).
+ * Emits, per frame, a candidate list (anchor id, xyxy box, score = obj*class_conf, class id):
+ *   mode A: the top-`pre_k` anchors by objectness, descending (ties: lower anchor id first);
+ *   mode B: anchors with score >= conf_thresh subject to minimal/maximal limits, ascending anchor id. */
+typedef struct {
+    int32_t mode;          /* 0 = A (postpro_woclass), 1 = B (postprocess_widx) */
+    int32_t num_frames;    /* total frames in the batch (clips * frames per clip) */
+    int32_t num_classes;
+    int32_t head_dtype;    /* TSCD_F32 / TSCD_F16 */
+    int32_t apply_sigmoid; /* 1: obj/cls are raw logits (seam S1); 0: already sigmoid-ed (S2/S3) */
+    int32_t apply_decode;  /* 1: reg is (dx,dy,dw,dh) (S1/S2); 0: already decoded cxcywh (S3) */
+    int32_t pre_k;         /* mode A: P */
+    float conf_thresh;     /* mode B: 0.001 */
+    int32_t minimal_limit; /* mode B */
+    int32_t maximal_limit; /* mode B */
+    int32_t cand_cap;      /* capacity (per frame) of the candidate arrays */
+    tscd_anchors anchors;
+    tscd_view reg, obj, cls; /* 4, 1 and C channels */
+    /* outputs [num_frames, cand_cap] (SoA) + [num_frames] */
+    int32_t* cand_idx;
+    float* cand_box; /* [.,.,4] */
+    float* cand_score;
+    int32_t* cand_cls;
+    int32_t* cand_count;
+} tscd_select_args;
+int tscd_select(const tscd_select_args* args, void* stream);
+
+/* ---- K2: class-aware batched NMS ---------------------------------------------------------------------
+ * Replaces torchvision.ops.batched_nms (coordinate trick + nms) at tscd_head.py:1630,
+ * post_process.py:58,73,510.  One CTA per frame; keep lists are positions into the candidate arrays in
+ * descending-score order (stable: ties keep the lower position first), truncated to max_keep.
+ * n per frame must be <= 4096 (TSCD_ERR_CAPACITY is reported through `status`). */
+typedef struct {
+    int32_t num_frames;
+    int32_t cand_cap;     /* row pitch of the candidate arrays */
+    int32_t max_keep;     /* pitch of keep[]; mode A passes K (first K survivors) */
+    float iou_thresh;
+    const float* box;     /* [F,cap,4] */
+    const float* score;   /* [F,cap] */
+    const int32_t* cls;   /* [F,cap] */
+    const int32_t* count; /* [F] */
+    int32_t* keep;        /* [F,max_keep] */
+    int32_t* keep_count;  /* [F] */
+    int32_t* status;      /* [1] device flag: set to TSCD_ERR_CAPACITY if any frame exceeded the cap */
+} tscd_nms_args;
+int tscd_nms(const tscd_nms_args* args, void* stream);
+
+/* ---- K3: rows + feature gather into the clip bank -------------------------------------------------------
+ * Replaces the row build (tscd_head.py:1581-1582, 1670-1684) and find_feature_score (:976-1006).
+ * For every kept proposal writes the reference row [x1,y1,x2,y2,obj,class_conf,class_pred,cls*C] (fp32),
+ * its anchor id, and gathers the three 256-channel feature rows into the packed bank (row order: frames in
+ * input order, proposals in selection order; offsets = exclusive prefix sum of the per-frame counts). */
+typedef struct {
+    int32_t num_frames;
+    int32_t num_classes;
+    int32_t head_dtype, apply_sigmoid, apply_decode;
+    int32_t cand_cap;
+    int32_t max_keep;       /* pitch of keep / rows / idx */
+    int32_t use_keep;       /* 0: kept = candidates[0:count] (no pre-NMS) */
+    int32_t feat_dim;       /* D (256) */
+    int32_t feat_dtype;     /* dtype of the feature planes */
+    int32_t bank_dtype;     /* TSCD_F16 / TSCD_BF16 / TSCD_F32 */
+    tscd_anchors anchors;
+    tscd_view reg, obj, cls;
+    tscd_view feat_cls, feat_reg, feat_edge; /* D channels each */
+    const int32_t* cand_idx;
+    const int32_t* cand_count;
+    const int32_t* keep;
+    const int32_t* keep_count;
+    /* outputs */
+    int32_t* sel_count;     /* [F] */
+    int32_t* row_off;       /* [F+1] exclusive prefix of sel_count */
+    int32_t* sel_idx;       /* [F,max_keep] anchor ids */
+    float* sel_rows;        /* [F,max_keep,7+C] */
+    void* bank_cls;         /* [cap_rows, D] */
+    void* bank_reg;
+    void* bank_edge;
+    float* bank_score;      /* [cap_rows] class_conf (cls_scores) */
+    float* bank_fg;         /* [cap_rows] objectness (fg_scores) */
+    float* bank_box;        /* [cap_rows,4] */
+} tscd_gather_args;
+int tscd_gather(const tscd_gather_args* args, void* stream);
+
+/* Library / build information (also proves the .so was loaded). */
+const char* tscd_version(void);
+int tscd_device_ok(void); /* 1 if the current device is compute capability 10.x */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSCD_B200_H_ */

@@ -1,0 +1,201 @@
+"""GPU parity: K1 select, K2 NMS, K3 gather through the C-ABI vs the oracle and the reference goldens.
+Integer results (selected anchor ids, NMS keep order, bank row order) must be bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import GOLDEN, unpack_list
+
+pytestmark = pytest.mark.gpu
+
+
+def _stage_mods():
+    from tscd_b200 import ops, selection
+    return ops, selection
+
+
+def _run(decoded_or_head, hw, C, cfg_kw, apply_decode, feats=None, feat_layout="rowmajor", bank_dtype=torch.float32):
+    ops, selection = _stage_mods()
+    an = ops.AnchorSpec(hw)
+    t = decoded_or_head.cuda()
+    head = ops.HeadViews.from_fused(t, an, apply_sigmoid=False, apply_decode=apply_decode)
+    Fn, A = t.shape[0], t.shape[1]
+    if feats is None:
+        g = torch.Generator().manual_seed(1)
+        feats = [torch.randn(Fn, A, 32, generator=g) for _ in range(3)]
+    D = feats[0].shape[2]
+    dev_feats = [f.cuda().contiguous() for f in feats]
+    if feat_layout == "rowmajor":
+        views = tuple(ops.view_rowmajor(f, an) for f in dev_feats)
+    else:
+        per_level = []
+        for f in dev_feats:
+            lv, s = [], 0
+            for (h, w) in hw:
+                x = f[:, s:s + h * w].reshape(Fn, h, w, D).permute(0, 3, 1, 2)   # logical NCHW
+                x = x.contiguous() if feat_layout == "nchw" else x.contiguous(memory_format=torch.channels_last)
+                lv.append(x)
+                s += h * w
+            per_level.append(lv)
+        views = tuple(ops.view_levels(lv) for lv in per_level)
+        dev_feats = per_level
+    cfg = selection.SelectionConfig(**cfg_kw)
+    sel = selection.select_and_gather(head, views, feats[0].dtype, D, cfg, bank_dtype=bank_dtype)
+    torch.cuda.synchronize()
+    assert int(sel["status"].item()) == 0 if sel["status"] is not None else True
+    rows, idxs = selection.to_lists(sel)
+    return sel, rows, idxs, feats
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLDEN, "select.npz"))
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("b_min50_max500", dict(mode="B", minimal_limit=50, maximal_limit=500, use_pre_nms=False)),
+    ("b_max100", dict(mode="B", minimal_limit=0, maximal_limit=100, use_pre_nms=False)),
+    ("b_prenms", dict(mode="B", minimal_limit=0, maximal_limit=0, use_pre_nms=True)),
+    ("b_min700_prenms", dict(mode="B", minimal_limit=700, maximal_limit=0, use_pre_nms=True)),
+    ("a_750_30", dict(mode="A", pre_k=750, top_k=30)),
+])
+def test_selection_matches_reference_golden(gold, name, kw):
+    hw = [tuple(x) for x in gold["hw"].tolist()]
+    C = int(gold["C"])
+    sel, rows, idxs, feats = _run(torch.from_numpy(gold["decoded"]), hw, C, dict(nms_thresh=0.75, **kw), apply_decode=False)
+    g_rows, g_idx = unpack_list(gold, name + ".rows"), unpack_list(gold, name + ".idx")
+    row_off = sel["row_off"].cpu().tolist()
+    for f in range(len(g_idx)):
+        assert idxs[f].cpu().tolist() == g_idx[f].tolist(), f"frame {f}"
+        assert np.array_equal(rows[f].cpu().numpy(), g_rows[f]), f"rows frame {f}"
+        # bank rows: features of the kept anchors, in selection order (fp32 bank -> exact copies)
+        want = feats[0][f, torch.from_numpy(g_idx[f])]
+        got = sel["bank_cls"][row_off[f]:row_off[f + 1]].cpu()
+        assert torch.equal(got, want)
+        assert torch.equal(sel["bank_score"][row_off[f]:row_off[f + 1]].cpu(), torch.from_numpy(g_rows[f][:, 5]))
+        assert torch.equal(sel["bank_fg"][row_off[f]:row_off[f + 1]].cpu(), torch.from_numpy(g_rows[f][:, 4]))
+        assert torch.equal(sel["bank_box"][row_off[f]:row_off[f + 1]].cpu(), torch.from_numpy(g_rows[f][:, :4]))
+
+
+@pytest.mark.parametrize("mode", ["A", "B"])
+@pytest.mark.parametrize("clustered", [False, True])
+def test_selection_full_size_vs_oracle(mode, clustered):
+    """BASELINE config shape: 32 frames x 6804 anchors (576x576), 25 classes, seam S3 (decoded, fp32)."""
+    hw = [(72, 72), (36, 36), (18, 18)]
+    C = 25
+    head, _ = oracle.synth_head_outputs(32, hw, C, dim=8, seed=2024, clustered=clustered,
+                                        obj_mean=(-3.0 if mode == "A" else -7.0))
+    decoded = oracle.decode_outputs(head, hw, [8, 16, 32])
+    if mode == "A":
+        kw = dict(mode="A", pre_k=750, top_k=30, nms_thresh=0.75)
+        o_rows, o_idx = oracle.select_mode_a(decoded, C, nms_thre=0.75, pre_k=750, top_k=30)
+    else:
+        kw = dict(mode="B", minimal_limit=50, maximal_limit=500, use_pre_nms=False, nms_thresh=0.75)
+        o_rows, o_idx = oracle.select_mode_b(decoded, C, nms_thre=0.75, minimal_limit=50, maximal_limit=500,
+                                             use_pre_nms=False)
+    sel, rows, idxs, _ = _run(decoded, hw, C, kw, apply_decode=False)
+    for f in range(32):
+        assert idxs[f].cpu().tolist() == o_idx[f].tolist(), f"frame {f}"
+        assert torch.equal(rows[f].cpu(), o_rows[f])
+
+
+def test_selection_seam_s2_decode_in_kernel():
+    """Seam S2: the kernel decodes (exp) itself; ids must still match, boxes to 1e-6 relative."""
+    hw = [(72, 72), (36, 36), (18, 18)]
+    C = 25
+    head, _ = oracle.synth_head_outputs(8, hw, C, dim=8, seed=7, clustered=True)
+    decoded = oracle.decode_outputs(head, hw, [8, 16, 32])
+    o_rows, o_idx = oracle.select_mode_a(decoded, C, nms_thre=0.75, pre_k=750, top_k=30)
+    sel, rows, idxs, _ = _run(head, hw, C, dict(mode="A", pre_k=750, top_k=30, nms_thresh=0.75), apply_decode=True)
+    for f in range(8):
+        assert idxs[f].cpu().tolist() == o_idx[f].tolist()
+        torch.testing.assert_close(rows[f].cpu(), o_rows[f], rtol=2e-6, atol=1e-4)
+
+
+def test_nms_kernel_vs_oracle_ties_and_negative_coords():
+    ops, _ = _stage_mods()
+    g = torch.Generator().manual_seed(3)
+    Fn, cap = 24, 1500
+    box = torch.zeros(Fn, cap, 4)
+    score = torch.zeros(Fn, cap)
+    cls = torch.zeros(Fn, cap, dtype=torch.int32)
+    count = torch.zeros(Fn, dtype=torch.int32)
+    for f in range(Fn):
+        n = [0, 1, 2, 31, 32, 33, 64, 65, 100, 257][f] if f < 10 else int(torch.randint(100, cap + 1, (1,), generator=g))
+        ctr = torch.rand(max(n // 10, 1), 2, generator=g) * 400 - 60
+        c = ctr[torch.randint(0, ctr.shape[0], (n,), generator=g)] + torch.randn(n, 2, generator=g) * 3
+        wh = torch.rand(n, 2, generator=g) * 40 + 10
+        box[f, :n] = torch.cat([c - wh / 2, c + wh / 2], 1)
+        s = torch.rand(n, generator=g)
+        if n > 4:
+            s[torch.randint(0, n, (n // 5,), generator=g)] = 0.25     # exact ties
+        score[f, :n] = s
+        cls[f, :n] = torch.randint(0, 4, (n,), generator=g).int()
+        count[f] = n
+    for thr in (0.5, 0.75):
+        keep, kc, status = ops.nms(box.cuda(), score.cuda(), cls.cuda(), count.cuda(), thr)
+        torch.cuda.synchronize()
+        assert int(status.item()) == 0
+        for f in range(Fn):
+            n = int(count[f])
+            want = oracle.batched_nms(box[f, :n], score[f, :n], cls[f, :n].float(), thr).tolist()
+            got = keep[f, :int(kc[f])].cpu().tolist()
+            assert got == want, f"thr {thr} frame {f} n {n}"
+    # max_keep truncation == prefix of the full keep list
+    keep30, kc30, _ = ops.nms(box.cuda(), score.cuda(), cls.cuda(), count.cuda(), 0.75, max_keep=30)
+    keep, kc, _ = ops.nms(box.cuda(), score.cuda(), cls.cuda(), count.cuda(), 0.75)
+    for f in range(Fn):
+        k = min(30, int(kc[f]))
+        assert int(kc30[f]) == k
+        assert keep30[f, :k].tolist() == keep[f, :k].tolist()
+
+
+def test_nms_capacity_is_reported():
+    ops, _ = _stage_mods()
+    cap = 5000
+    box = torch.rand(1, cap, 4).cuda()
+    box[..., 2:] += box[..., :2]
+    keep, kc, status = ops.nms(box, torch.rand(1, cap).cuda(), torch.zeros(1, cap, dtype=torch.int32).cuda(),
+                               torch.tensor([cap], dtype=torch.int32).cuda(), 0.5)
+    torch.cuda.synchronize()
+    assert int(status.item()) == -3
+
+
+@pytest.mark.parametrize("layout", ["rowmajor", "nchw", "channels_last"])
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16])
+def test_gather_layouts_and_dtypes(layout, dt):
+    hw = [(16, 16), (8, 8), (4, 4)]
+    C = 5
+    head, feats = oracle.synth_head_outputs(6, hw, C, dim=256, seed=5, obj_mean=-6.0)
+    decoded = oracle.decode_outputs(head, hw, [8, 16, 32])
+    feats = [f.to(dt) for f in feats]
+    o_rows, o_idx = oracle.select_mode_b(decoded, C, minimal_limit=12, maximal_limit=40, use_pre_nms=False)
+    sel, rows, idxs, _ = _run(decoded, hw, C, dict(mode="B", minimal_limit=12, maximal_limit=40, use_pre_nms=False),
+                              apply_decode=False, feats=feats, feat_layout=layout, bank_dtype=torch.float16)
+    off = sel["row_off"].cpu().tolist()
+    for f in range(6):
+        assert idxs[f].cpu().tolist() == o_idx[f].tolist()
+        for p, name in enumerate(("bank_cls", "bank_reg", "bank_edge")):
+            want = feats[p][f, o_idx[f]].to(torch.float16)
+            assert torch.equal(sel[name][off[f]:off[f + 1]].cpu(), want), (f, name)
+    assert off[-1] == sum(len(i) for i in o_idx)
+
+
+def test_empty_frames_and_small_anchor_sets():
+    """mode B with no limit: frames whose scores are all below 0.001 select nothing (reference returns None)."""
+    hw = [(4, 4), (2, 2), (1, 1)]
+    C = 3
+    head, _ = oracle.synth_head_outputs(3, hw, C, dim=8, seed=2, obj_mean=[-30.0, -2.0, -30.0])
+    decoded = oracle.decode_outputs(head, hw, [8, 16, 32])
+    o_rows, o_idx = oracle.select_mode_b(decoded, C, use_pre_nms=True)
+    sel, rows, idxs, _ = _run(decoded, hw, C, dict(mode="B", use_pre_nms=True), apply_decode=False)
+    assert rows[0] is None and rows[2] is None and o_rows[0] is None
+    assert idxs[1].cpu().tolist() == o_idx[1].tolist()
+    # mode A with fewer anchors than pre_k
+    o_rows, o_idx = oracle.select_mode_a(decoded, C, pre_k=750, top_k=30)
+    sel, rows, idxs, _ = _run(decoded, hw, C, dict(mode="A", pre_k=750, top_k=30), apply_decode=False)
+    for f in range(3):
+        assert idxs[f].cpu().tolist() == o_idx[f].tolist()

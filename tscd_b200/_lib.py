@@ -1,0 +1,84 @@
+"""ctypes binding of libtscd_b200.so (the C-ABI declared in include/tscd_b200.h).
+
+There is deliberately no fallback: if the CUDA library is missing or a call fails, a RuntimeError is
+raised.  Nothing here imports ``oracle``.
+"""
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+TSCD_F32, TSCD_F16, TSCD_BF16 = 0, 1, 2
+MAX_LEVELS = 3
+_ERR = {-1: "invalid argument", -2: "unsupported configuration", -3: "capacity exceeded", -4: "CUDA error"}
+
+
+class View(C.Structure):
+    _fields_ = [("ptr", C.c_void_p * MAX_LEVELS), ("frame_stride", C.c_int64 * MAX_LEVELS),
+                ("anchor_stride", C.c_int64 * MAX_LEVELS), ("chan_stride", C.c_int64 * MAX_LEVELS)]
+
+
+class Anchors(C.Structure):
+    _fields_ = [("num_levels", C.c_int32), ("level_h", C.c_int32 * MAX_LEVELS), ("level_w", C.c_int32 * MAX_LEVELS),
+                ("level_stride", C.c_int32 * MAX_LEVELS), ("level_start", C.c_int32 * (MAX_LEVELS + 1))]
+
+
+class SelectArgs(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("num_frames", C.c_int32), ("num_classes", C.c_int32), ("head_dtype", C.c_int32),
+                ("apply_sigmoid", C.c_int32), ("apply_decode", C.c_int32), ("pre_k", C.c_int32),
+                ("conf_thresh", C.c_float), ("minimal_limit", C.c_int32), ("maximal_limit", C.c_int32),
+                ("cand_cap", C.c_int32), ("anchors", Anchors), ("reg", View), ("obj", View), ("cls", View),
+                ("cand_idx", C.c_void_p), ("cand_box", C.c_void_p), ("cand_score", C.c_void_p),
+                ("cand_cls", C.c_void_p), ("cand_count", C.c_void_p)]
+
+
+class NmsArgs(C.Structure):
+    _fields_ = [("num_frames", C.c_int32), ("cand_cap", C.c_int32), ("max_keep", C.c_int32), ("iou_thresh", C.c_float),
+                ("box", C.c_void_p), ("score", C.c_void_p), ("cls", C.c_void_p), ("count", C.c_void_p),
+                ("keep", C.c_void_p), ("keep_count", C.c_void_p), ("status", C.c_void_p)]
+
+
+class GatherArgs(C.Structure):
+    _fields_ = [("num_frames", C.c_int32), ("num_classes", C.c_int32), ("head_dtype", C.c_int32),
+                ("apply_sigmoid", C.c_int32), ("apply_decode", C.c_int32), ("cand_cap", C.c_int32),
+                ("max_keep", C.c_int32), ("use_keep", C.c_int32), ("feat_dim", C.c_int32), ("feat_dtype", C.c_int32),
+                ("bank_dtype", C.c_int32), ("anchors", Anchors), ("reg", View), ("obj", View), ("cls", View),
+                ("feat_cls", View), ("feat_reg", View), ("feat_edge", View),
+                ("cand_idx", C.c_void_p), ("cand_count", C.c_void_p), ("keep", C.c_void_p), ("keep_count", C.c_void_p),
+                ("sel_count", C.c_void_p), ("row_off", C.c_void_p), ("sel_idx", C.c_void_p), ("sel_rows", C.c_void_p),
+                ("bank_cls", C.c_void_p), ("bank_reg", C.c_void_p), ("bank_edge", C.c_void_p),
+                ("bank_score", C.c_void_p), ("bank_fg", C.c_void_p), ("bank_box", C.c_void_p)]
+
+
+_lib = None
+
+# every symbol include/tscd_b200.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("tscd_version", C.c_char_p, []),
+    ("tscd_device_ok", C.c_int, []),
+    ("tscd_select", C.c_int, [C.POINTER(SelectArgs), C.c_void_p]),
+    ("tscd_nms", C.c_int, [C.POINTER(NmsArgs), C.c_void_p]),
+    ("tscd_gather", C.c_int, [C.POINTER(GatherArgs), C.c_void_p]),
+]
+
+
+def lib():
+    """Load the shared library (once).  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -m tscd_b200.build` (or __graft_entry__.build()). "
+                "tscd_b200 has no CPU or PyTorch fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {_ERR.get(rc, rc)} (code {rc})")

@@ -1,0 +1,12 @@
+// Library identification entry points of libtscd_b200.so.
+#include "common.cuh"
+
+extern "C" const char* tscd_version(void) { return "tscd_b200 0.1 (sm_100a)"; }
+
+extern "C" int tscd_device_ok(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10 ? 1 : 0;
+}

@@ -1,0 +1,159 @@
+// K3: per-frame counts -> bank offsets, reference rows for the kept proposals, and the gather of their
+// classification / regression / edge feature rows into the packed clip bank.
+//
+// Reference: row build tscd_head.py:1581-1582 (+1670-1684), find_feature_score tscd_head.py:976-1006.
+// One warp per kept proposal: lanes read the class scores (warp arg-max, first maximum wins like
+// torch.max), lane 0 decodes the box, then the warp copies the three D-channel feature rows with 16-byte
+// vector loads when the plane is channel-contiguous (channels_last conv outputs), falling back to strided
+// element loads for NCHW planes.
+#include "common.cuh"
+
+namespace tscd {
+
+__global__ void count_scan_kernel(int num_frames, int use_keep, int max_keep, const int32_t* cand_count,
+                                  const int32_t* keep_count, int32_t* sel_count, int32_t* row_off) {
+    __shared__ int scratch[40];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < num_frames; base += blockDim.x) {
+        int f = base + threadIdx.x;
+        int c = 0;
+        if (f < num_frames) {
+            c = use_keep ? keep_count[f] : cand_count[f];
+            c = min(c, max_keep);
+            sel_count[f] = c;
+        }
+        int tot;
+        int ex = block_excl_scan(c, scratch, &tot);
+        int carry = carry_s;
+        if (f < num_frames) row_off[f] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) row_off[num_frames] = carry_s;
+}
+
+__device__ __forceinline__ float ld_any(const void* base, int dtype, int64_t idx) {
+    if (dtype == TSCD_F32) return __ldg(reinterpret_cast<const float*>(base) + idx);
+    if (dtype == TSCD_F16) return __half2float(__ldg(reinterpret_cast<const __half*>(base) + idx));
+    return __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(base) + idx));
+}
+
+template <typename TF, typename TB>
+__device__ __forceinline__ void copy_feature_row(const tscd_view& v, int level, int frame, int local, int D, TB* dst,
+                                                 int lane) {
+    const TF* src = reinterpret_cast<const TF*>(v.ptr[level]) + (int64_t)frame * v.frame_stride[level] +
+                    (int64_t)local * v.anchor_stride[level];
+    const int64_t cs = v.chan_stride[level];
+    constexpr int VEC = 16 / sizeof(TF);
+    if (cs == 1 && (D % VEC) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+        for (int c0 = lane * VEC; c0 < D; c0 += 32 * VEC) {
+            uint4 raw = __ldg(reinterpret_cast<const uint4*>(src + c0));
+            const TF* e = reinterpret_cast<const TF*>(&raw);
+            if (sizeof(TF) == sizeof(TB) && ((reinterpret_cast<uintptr_t>(dst + c0) & 15) == 0)) {
+                // same width: convert in registers, one 16-byte store
+                uint4 out;
+                TB* o = reinterpret_cast<TB*>(&out);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) o[k] = cvt_from_float<TB>(ldf_reg(e[k]));
+                *reinterpret_cast<uint4*>(dst + c0) = out;
+            } else {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) dst[c0 + k] = cvt_from_float<TB>(ldf_reg(e[k]));
+            }
+        }
+    } else {
+        for (int c = lane; c < D; c += 32) dst[c] = cvt_from_float<TB>(ldf(src + c * cs));
+    }
+}
+
+template <typename TF, typename TB>
+__global__ void __launch_bounds__(256) rows_gather_kernel(const tscd_gather_args args) {
+    const int frame = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int n = args.sel_count[frame];
+    const int row0 = args.row_off[frame];
+    const int C = args.num_classes;
+    const int W = 7 + C;
+    const tscd_anchors& an = args.anchors;
+    const int hd = args.head_dtype;
+    for (int j = wid + blockIdx.y * nw; j < n; j += nw * gridDim.y) {
+        const int pos = args.use_keep ? args.keep[(int64_t)frame * args.max_keep + j] : j;
+        const int a = args.cand_idx[(int64_t)frame * args.cand_cap + pos];
+        AnchorPos p = anchor_pos(an, a);
+        float* row = args.sel_rows + ((int64_t)frame * args.max_keep + j) * W;
+        // class scores + arg-max (first maximum)
+        const int64_t cbase = (int64_t)frame * args.cls.frame_stride[p.level] + (int64_t)p.local * args.cls.anchor_stride[p.level];
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int c = lane; c < C; c += 32) {
+            float v = ld_any(args.cls.ptr[p.level], hd, cbase + c * args.cls.chan_stride[p.level]);
+            if (args.apply_sigmoid) v = sigmoidf_ref(v);
+            row[7 + c] = v;
+            if (v > best) { best = v; bi = c; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) {
+            float obj = ld_any(args.obj.ptr[p.level], hd,
+                               (int64_t)frame * args.obj.frame_stride[p.level] + (int64_t)p.local * args.obj.anchor_stride[p.level]);
+            if (args.apply_sigmoid) obj = sigmoidf_ref(obj);
+            float4 box = (hd == TSCD_F32) ? anchor_box<float>(args.reg, p, frame, args.apply_decode != 0)
+                                          : anchor_box<__half>(args.reg, p, frame, args.apply_decode != 0);
+            row[0] = box.x; row[1] = box.y; row[2] = box.z; row[3] = box.w;
+            row[4] = obj; row[5] = best; row[6] = (float)bi;
+            args.sel_idx[(int64_t)frame * args.max_keep + j] = a;
+            const int r = row0 + j;
+            args.bank_score[r] = best;
+            args.bank_fg[r] = obj;
+            reinterpret_cast<float4*>(args.bank_box)[r] = box;
+        }
+        const int64_t r = (int64_t)(row0 + j) * args.feat_dim;
+        copy_feature_row<TF, TB>(args.feat_cls, p.level, frame, p.local, args.feat_dim, reinterpret_cast<TB*>(args.bank_cls) + r, lane);
+        copy_feature_row<TF, TB>(args.feat_reg, p.level, frame, p.local, args.feat_dim, reinterpret_cast<TB*>(args.bank_reg) + r, lane);
+        copy_feature_row<TF, TB>(args.feat_edge, p.level, frame, p.local, args.feat_dim, reinterpret_cast<TB*>(args.bank_edge) + r, lane);
+    }
+}
+
+template <typename TF>
+static int launch_gather_tb(const tscd_gather_args* a, dim3 grid, cudaStream_t st) {
+    switch (a->bank_dtype) {
+        case TSCD_F32: rows_gather_kernel<TF, float><<<grid, 256, 0, st>>>(*a); break;
+        case TSCD_F16: rows_gather_kernel<TF, __half><<<grid, 256, 0, st>>>(*a); break;
+        case TSCD_BF16: rows_gather_kernel<TF, __nv_bfloat16><<<grid, 256, 0, st>>>(*a); break;
+        default: return TSCD_ERR_UNSUPPORTED;
+    }
+    return TSCD_OK;
+}
+
+}  // namespace tscd
+
+extern "C" int tscd_gather(const tscd_gather_args* a, void* stream) {
+    using namespace tscd;
+    if (!a || a->num_frames < 0 || a->num_classes <= 0 || a->max_keep <= 0 || a->feat_dim <= 0) return TSCD_ERR_INVALID_ARG;
+    if (a->head_dtype != TSCD_F32 && a->head_dtype != TSCD_F16) return TSCD_ERR_UNSUPPORTED;
+    if (a->num_frames == 0) return TSCD_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    count_scan_kernel<<<1, 1024, 0, st>>>(a->num_frames, a->use_keep, a->max_keep, a->cand_count, a->keep_count,
+                                          a->sel_count, a->row_off);
+    TSCD_CUDA_CHECK_LAUNCH();
+    int ysplit = a->max_keep > 64 ? (a->max_keep + 63) / 64 : 1;
+    if (ysplit > 8) ysplit = 8;
+    dim3 grid(a->num_frames, ysplit);
+    int rc;
+    switch (a->feat_dtype) {
+        case TSCD_F32: rc = launch_gather_tb<float>(a, grid, st); break;
+        case TSCD_F16: rc = launch_gather_tb<__half>(a, grid, st); break;
+        case TSCD_BF16: rc = launch_gather_tb<__nv_bfloat16>(a, grid, st); break;
+        default: return TSCD_ERR_UNSUPPORTED;
+    }
+    if (rc != TSCD_OK) return rc;
+    TSCD_CUDA_CHECK_LAUNCH();
+    return TSCD_OK;
+}

@@ -1,0 +1,193 @@
+// K2: class-aware batched NMS, one CTA per frame, bit-exact with torchvision's coordinate-trick path.
+//
+// Reference: torchvision.ops.batched_nms as called at yolox/models/tscd_head.py:1630 and
+// yolox/models/post_process.py:58,73,510  (boxes.py `_batched_nms_coordinate_trick`):
+//     offsets = class_id * (boxes.max() + 1);  keep = nms(boxes + offsets[:,None], scores, thr)
+// nms = stable descending sort by score, greedy suppression where  inter/(Sa+Sb-inter) > thr.
+// All arithmetic uses explicit round-to-nearest single-precision ops (no FMA contraction) so every IoU
+// decision matches the CPU kernel; the comparison against `thr` is done in double like the CPU kernel.
+//
+// Algorithm (lazy greedy, no N^2 bitmask): candidates are sorted in shared memory (bitonic, 64-bit
+// composite keys = score bits | inverted position, which reproduces the stable order).  They are then
+// processed in chunks of 32: all threads build the 32x32 intra-chunk IoU bitmask, one warp resolves the
+// chunk serially from the bitmask (ballot/shuffle), then all threads apply the chunk's survivors to every
+// later candidate.  Work is O(kept * N) instead of O(N^2) and stops as soon as max_keep boxes are kept
+// (mode A only needs the first K=30 survivors of 750).
+#include "common.cuh"
+
+namespace tscd {
+
+constexpr int kNmsThreads = 256;
+constexpr int kNmsCap = 4096;
+
+__device__ __forceinline__ bool iou_gt(const float4& a, float sa, const float4& b, float sb, double thr) {
+    float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+    float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+    float inter = __fmul_rn(w, h);
+    float uni = __fsub_rn(__fadd_rn(sa, sb), inter);
+    float ovr = __fdiv_rn(inter, uni);
+    return (double)ovr > thr;
+}
+
+__device__ void bitonic_sort_desc64(unsigned long long* a, int n64) {
+    for (int k = 2; k <= n64; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n64; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long x = a[i], y = a[ixj];
+                    bool desc = ((i & k) == 0);
+                    if (desc ? (x < y) : (x > y)) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kNmsThreads) nms_kernel(const tscd_nms_args args, int smem_cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int frame = blockIdx.x;
+    int n = args.count[frame];
+    if (n > smem_cap) {
+        if (threadIdx.x == 0) { atomicMin(args.status, TSCD_ERR_CAPACITY); args.keep_count[frame] = 0; }
+        return;
+    }
+    if (n <= 0) {
+        if (threadIdx.x == 0) args.keep_count[frame] = 0;
+        return;
+    }
+    int n64 = 1;
+    while (n64 < n) n64 <<= 1;
+
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem_raw);      // [n64]
+    float4* sbox = reinterpret_cast<float4*>(skey + smem_cap);                        // [n] sorted, offset boxes
+    float* sarea = reinterpret_cast<float*>(sbox + smem_cap);                         // [n]
+    unsigned char* dead = reinterpret_cast<unsigned char*>(sarea + smem_cap);         // [n]
+    __shared__ unsigned int cmask[32];
+    __shared__ float red[kNmsThreads / 32];
+    __shared__ int s_kept_bits, s_nkept;
+    __shared__ int s_chunk_kept[32];
+
+    const int64_t base = (int64_t)frame * args.cand_cap;
+    const float* gscore = args.score + base;
+    const float4* gbox = reinterpret_cast<const float4*>(args.box) + base;
+    const int32_t* gcls = args.cls + base;
+
+    // ---- sort keys + max coordinate -----------------------------------------------------------------
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < n64; i += blockDim.x) {
+        unsigned long long v = 0ull;
+        if (i < n) {
+            v = ((unsigned long long)f2ord(gscore[i]) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+            float4 b = gbox[i];
+            mx = fmaxf(mx, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
+        }
+        skey[i] = v;
+    }
+    mx = warp_maxf(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < kNmsThreads / 32; ++w) mx = fmaxf(mx, red[w]);
+    const float off_unit = __fadd_rn(mx, 1.f);  // boxes.max() + 1
+
+    bitonic_sort_desc64(skey, n64);
+
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        int pos = (int)(0xffffffffu - (uint32_t)(skey[r] & 0xffffffffull));
+        float4 b = gbox[pos];
+        float off = __fmul_rn((float)gcls[pos], off_unit);
+        b.x = __fadd_rn(b.x, off); b.y = __fadd_rn(b.y, off);
+        b.z = __fadd_rn(b.z, off); b.w = __fadd_rn(b.w, off);
+        sbox[r] = b;
+        sarea[r] = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+        dead[r] = 0;
+    }
+    if (threadIdx.x == 0) s_nkept = 0;
+    __syncthreads();
+
+    const double thr = (double)args.iou_thresh;
+    const int max_keep = args.max_keep;
+    int32_t* keep = args.keep + (int64_t)frame * max_keep;
+
+    for (int c0 = 0; c0 < n; c0 += 32) {
+        const int cn = min(32, n - c0);
+        // (1) intra-chunk bitmask: bit j of cmask[l] set if earlier lane j suppresses lane l
+        if (threadIdx.x < 32) cmask[threadIdx.x] = 0u;
+        __syncthreads();
+        for (int pr = threadIdx.x; pr < 32 * 32; pr += blockDim.x) {
+            int l = pr >> 5, j = pr & 31;
+            if (j < l && l < cn) {
+                if (iou_gt(sbox[c0 + j], sarea[c0 + j], sbox[c0 + l], sarea[c0 + l], thr)) atomicOr(&cmask[l], 1u << j);
+            }
+        }
+        __syncthreads();
+        // (2) serial resolve by warp 0
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            bool alive = (lane < cn) && !dead[c0 + lane];
+            unsigned alive_bits = __ballot_sync(0xffffffffu, alive);
+            unsigned my = cmask[lane];
+            unsigned kept = 0u;
+#pragma unroll
+            for (int l = 0; l < 32; ++l) {
+                unsigned m = __shfl_sync(0xffffffffu, my, l);
+                if (((alive_bits >> l) & 1u) && !(m & kept)) kept |= 1u << l;
+            }
+            int nk = s_nkept;
+            __syncwarp();
+            // truncate to max_keep
+            int rank = __popc(kept & ((1u << lane) - 1u));
+            bool mine = (kept >> lane) & 1u;
+            if (mine && nk + rank < max_keep) {
+                keep[nk + rank] = (int)(0xffffffffu - (uint32_t)(skey[c0 + lane] & 0xffffffffull));
+                s_chunk_kept[rank] = c0 + lane;
+            }
+            if (lane == 0) {
+                int add = min(__popc(kept), max_keep - nk);
+                s_kept_bits = add;  // number of newly kept boxes to apply
+                s_nkept = nk + add;
+            }
+        }
+        __syncthreads();
+        const int n_new = s_kept_bits;
+        if (s_nkept >= max_keep) break;
+        // (3) apply this chunk's survivors to all later candidates
+        if (n_new > 0) {
+            for (int j = c0 + 32 + threadIdx.x; j < n; j += blockDim.x) {
+                if (dead[j]) continue;
+                float4 bj = sbox[j];
+                float sj = sarea[j];
+                bool d = false;
+                for (int k = 0; k < n_new && !d; ++k) {
+                    int i = s_chunk_kept[k];
+                    d = iou_gt(sbox[i], sarea[i], bj, sj, thr);
+                }
+                if (d) dead[j] = 1;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) args.keep_count[frame] = s_nkept;
+}
+
+}  // namespace tscd
+
+extern "C" int tscd_nms(const tscd_nms_args* a, void* stream) {
+    using namespace tscd;
+    if (!a || a->num_frames < 0 || a->cand_cap <= 0 || a->max_keep <= 0) return TSCD_ERR_INVALID_ARG;
+    if (a->num_frames == 0) return TSCD_OK;
+    int cap = a->cand_cap < kNmsCap ? a->cand_cap : kNmsCap;
+    int cap64 = 1;
+    while (cap64 < cap) cap64 <<= 1;   // sort buffer must hold the padded power of two
+    size_t smem = (size_t)cap64 * (8 + 16 + 4 + 1) + 16;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return TSCD_ERR_CUDA;
+    nms_kernel<<<a->num_frames, kNmsThreads, smem, st>>>(*a, cap64);
+    TSCD_CUDA_CHECK_LAUNCH();
+    return TSCD_OK;
+}

@@ -1,0 +1,239 @@
+// K1: fused decode + score + per-frame proposal selection (modes A and B).
+//
+// Reference semantics: TSCDHead.postprocess_widx (yolox/models/tscd_head.py:1546-1693) and
+// postpro_woclass (yolox/models/post_process.py:464-521); see include/tscd_b200.h.
+//
+// One CTA per frame.  Pass 1 streams the frame's objectness / class planes once from HBM and keeps one
+// 32-bit order-preserving key per anchor in shared memory (A*4 B; 27 KB at A=6804).  Pass 2 is a block
+// radix select (4 x 8-bit digits) for the k-th largest key with the documented tie-break (equal keys:
+// lower anchor id first), a stable compaction, and for mode A a bitonic sort of the P survivors.  Only the
+// survivors' regression / class rows are touched again (L2 hits).
+#include "common.cuh"
+
+namespace tscd {
+
+constexpr int kSelThreads = 256;
+
+struct SelSmem {
+    int hist[256];
+    int scan[40];
+    int misc[8];
+};
+
+// k-th largest key among keys[0..n) (k >= 1, k <= n).  Returns the threshold key T and the number of
+// elements equal to T that belong to the top-k (r_eq); elements > T number k - r_eq.
+__device__ void radix_select_kth(const uint32_t* keys, int n, int k, SelSmem* s, uint32_t* T_out, int* req_out) {
+    uint32_t prefix = 0, mask = 0;
+    int remaining = k;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s->hist[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            uint32_t u = keys[i];
+            if ((u & mask) == prefix) atomicAdd(&s->hist[(u >> shift) & 255], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            // warp 0: lane l owns digits [8l, 8l+8); suffix sums from the top digit down
+            const int lane = threadIdx.x;
+            int loc[8], tot = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { loc[j] = s->hist[255 - (lane * 8 + j)]; tot += loc[j]; }
+            int inc = warp_incl_scan(tot, lane);
+            int before = inc - tot;  // count of keys in strictly higher digit groups
+            if (before < remaining && remaining <= inc) {
+                int cum = before;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (cum < remaining && remaining <= cum + loc[j]) {
+                        s->misc[0] = 255 - (lane * 8 + j);
+                        s->misc[1] = remaining - cum;
+                    }
+                    cum += loc[j];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= (uint32_t)s->misc[0] << shift;
+        mask |= 255u << shift;
+        remaining = s->misc[1];
+        __syncthreads();
+    }
+    *T_out = prefix;
+    *req_out = remaining;
+}
+
+// Descending bitonic sort of n64 (power of two) 64-bit keys in shared memory.
+__device__ void bitonic_sort_desc(unsigned long long* a, int n64) {
+    for (int k = 2; k <= n64; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n64; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long x = a[i], y = a[ixj];
+                    bool desc = ((i & k) == 0);
+                    if (desc ? (x < y) : (x > y)) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kSelThreads) select_kernel(const tscd_select_args args) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int frame = blockIdx.x;
+    const tscd_anchors& an = args.anchors;
+    const int A = an.level_start[an.num_levels];
+    const int C = args.num_classes;
+    const bool sig = args.apply_sigmoid != 0;
+
+    uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw);                     // [A]
+    int* sel = reinterpret_cast<int*>(keys + ((A + 3) & ~3));                   // [A] selected anchor ids
+    unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(sel + ((A + 3) & ~3));  // [pow2(pre_k)]
+    __shared__ SelSmem s;
+
+    // ---- pass 1: one key per anchor -------------------------------------------------------------------
+    int n_ge = 0;  // mode B: anchors with score >= conf_thresh
+    for (int a = threadIdx.x; a < A; a += blockDim.x) {
+        AnchorPos p = anchor_pos(an, a);
+        float obj = ldf(view_ptr<T>(args.obj, p.level, frame, p.local));
+        if (sig) obj = sigmoidf_ref(obj);
+        float key = obj;
+        if (args.mode == 1) {
+            const T* c = view_ptr<T>(args.cls, p.level, frame, p.local);
+            const int64_t cs = args.cls.chan_stride[p.level];
+            float best = ldf(c);
+            for (int k = 1; k < C; ++k) best = fmaxf(best, ldf(c + k * cs));
+            if (sig) best = sigmoidf_ref(best);  // sigmoid is monotone: max first, one exp per anchor
+            key = __fmul_rn(obj, best);          // tscd_head.py:1591  obj * class_conf
+            n_ge += (key >= args.conf_thresh) ? 1 : 0;
+        }
+        keys[a] = f2ord(key);
+    }
+    __syncthreads();
+
+    // ---- how many to take --------------------------------------------------------------------------
+    int take_k = 0;  // 0 = plain threshold mask (mode B, no limit triggered)
+    if (args.mode == 0) {
+        take_k = min(args.pre_k, A);
+    } else {
+        int tot;
+        block_excl_scan(n_ge, s.scan, &tot);
+        int cnt = tot;
+        if (args.minimal_limit != 0 && cnt < args.minimal_limit) {  // :1594-1599 (top-min is a superset of the mask)
+            take_k = min(args.minimal_limit, A);
+            cnt = take_k;
+        }
+        if (args.maximal_limit != 0 && cnt > args.maximal_limit) {  // :1600-1607
+            take_k = min(args.maximal_limit, A);
+        }
+    }
+
+    uint32_t Tk = f2ord(args.conf_thresh);
+    int r_eq = 0x7fffffff;  // threshold mode: every key == Tk is taken
+    if (take_k > 0) radix_select_kth(keys, A, take_k, &s, &Tk, &r_eq);
+
+    // ---- stable compaction in ascending anchor order ---------------------------------------------------
+    const int chunk = (A + blockDim.x - 1) / blockDim.x;
+    const int lo = min(threadIdx.x * chunk, A), hi = min(lo + chunk, A);
+    int n_gt = 0, n_eq = 0;
+    for (int a = lo; a < hi; ++a) {
+        uint32_t u = keys[a];
+        n_gt += (u > Tk);
+        n_eq += (u == Tk);
+    }
+    int tot_eq, tot_gt;
+    int eq_before = block_excl_scan(n_eq, s.scan, &tot_eq);
+    int take_eq = max(0, min(n_eq, r_eq - eq_before));  // lowest anchor ids among the ties
+    int out_before = block_excl_scan(n_gt + take_eq, s.scan, &tot_gt);
+    const int n_sel_raw = tot_gt;
+    {
+        int o = out_before, e = eq_before;
+        for (int a = lo; a < hi; ++a) {
+            uint32_t u = keys[a];
+            bool t = (u > Tk);
+            if (u == Tk) { t = (e < r_eq); ++e; }
+            if (t) { if (o < args.cand_cap) sel[o] = a; ++o; }
+        }
+    }
+    __syncthreads();
+    const int n_sel = min(n_sel_raw, args.cand_cap);
+
+    // ---- mode A: order by objectness, descending, ties lower anchor id first ---------------------------
+    if (args.mode == 0) {
+        int n64 = 1;
+        while (n64 < n_sel) n64 <<= 1;
+        for (int i = threadIdx.x; i < n64; i += blockDim.x) {
+            unsigned long long v = 0ull;
+            if (i < n_sel) {
+                int a = sel[i];
+                v = ((unsigned long long)keys[a] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)a);
+            }
+            sortbuf[i] = v;
+        }
+        __syncthreads();
+        bitonic_sort_desc(sortbuf, n64);
+        for (int i = threadIdx.x; i < n_sel; i += blockDim.x)
+            sel[i] = (int)(0xffffffffu - (uint32_t)(sortbuf[i] & 0xffffffffull));
+        __syncthreads();
+    }
+
+    // ---- candidate records -----------------------------------------------------------------------------
+    const int64_t base = (int64_t)frame * args.cand_cap;
+    for (int i = threadIdx.x; i < n_sel; i += blockDim.x) {
+        const int a = sel[i];
+        AnchorPos p = anchor_pos(an, a);
+        float obj = ldf(view_ptr<T>(args.obj, p.level, frame, p.local));
+        if (sig) obj = sigmoidf_ref(obj);
+        const T* c = view_ptr<T>(args.cls, p.level, frame, p.local);
+        const int64_t cs = args.cls.chan_stride[p.level];
+        float best = ldf(c);
+        int bi = 0;
+        for (int k = 1; k < C; ++k) {
+            float v = ldf(c + k * cs);
+            if (v > best) { best = v; bi = k; }  // first maximum wins (torch.max)
+        }
+        if (sig) best = sigmoidf_ref(best);
+        float4 box = anchor_box<T>(args.reg, p, frame, args.apply_decode != 0);
+        args.cand_idx[base + i] = a;
+        reinterpret_cast<float4*>(args.cand_box)[base + i] = box;
+        args.cand_score[base + i] = __fmul_rn(obj, best);
+        args.cand_cls[base + i] = bi;
+    }
+    if (threadIdx.x == 0) args.cand_count[frame] = n_sel;
+}
+
+}  // namespace tscd
+
+extern "C" int tscd_select(const tscd_select_args* a, void* stream) {
+    using namespace tscd;
+    if (!a || a->num_frames < 0 || a->num_classes <= 0 || a->cand_cap <= 0) return TSCD_ERR_INVALID_ARG;
+    if (a->anchors.num_levels < 1 || a->anchors.num_levels > TSCD_MAX_LEVELS) return TSCD_ERR_INVALID_ARG;
+    if (a->mode != 0 && a->mode != 1) return TSCD_ERR_INVALID_ARG;
+    if (a->mode == 0 && a->pre_k <= 0) return TSCD_ERR_INVALID_ARG;
+    if (a->num_frames == 0) return TSCD_OK;
+    const int A = a->anchors.level_start[a->anchors.num_levels];
+    if (A <= 0) return TSCD_ERR_INVALID_ARG;
+    int n64 = 1;
+    if (a->mode == 0) while (n64 < (a->pre_k < A ? a->pre_k : A)) n64 <<= 1;
+    size_t smem = (size_t)((A + 3) & ~3) * 8 + (size_t)n64 * 8;
+    if (smem > 200 * 1024) return TSCD_ERR_CAPACITY;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    if (a->head_dtype == TSCD_F32) {
+        e = cudaFuncSetAttribute(select_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return TSCD_ERR_CUDA;
+        select_kernel<float><<<a->num_frames, kSelThreads, smem, st>>>(*a);
+    } else if (a->head_dtype == TSCD_F16) {
+        e = cudaFuncSetAttribute(select_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return TSCD_ERR_CUDA;
+        select_kernel<__half><<<a->num_frames, kSelThreads, smem, st>>>(*a);
+    } else {
+        return TSCD_ERR_UNSUPPORTED;
+    }
+    TSCD_CUDA_CHECK_LAUNCH();
+    return TSCD_OK;
+}

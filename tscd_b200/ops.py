@@ -1,0 +1,173 @@
+"""Thin Python wrappers: torch tensors in, C-ABI calls (raw pointers) out.  PyTorch is used for device
+memory and streams only."""
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: L.TSCD_F32, torch.float16: L.TSCD_F16, torch.bfloat16: L.TSCD_BF16}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+@dataclass
+class AnchorSpec:
+    """Level-major, row-major anchor geometry (tscd_head.py:374-376, 755-766)."""
+    hw: Sequence[Sequence[int]]
+    strides: Sequence[int] = (8, 16, 32)
+
+    @property
+    def num_anchors(self):
+        return sum(h * w for h, w in self.hw)
+
+    def to_c(self) -> L.Anchors:
+        a = L.Anchors()
+        a.num_levels = len(self.hw)
+        start = 0
+        for i, ((h, w), s) in enumerate(zip(self.hw, self.strides)):
+            a.level_h[i], a.level_w[i], a.level_stride[i], a.level_start[i] = h, w, s, start
+            start += h * w
+        a.level_start[len(self.hw)] = start
+        return a
+
+
+def view_rowmajor(t: torch.Tensor, anchors: AnchorSpec, col: int = 0) -> L.View:
+    """View of columns [col, col+ch) of a contiguous [F, A, W] tensor."""
+    assert t.is_contiguous() and t.dim() == 3
+    Fn, A, W = t.shape
+    v = L.View()
+    es = t.element_size()
+    start = 0
+    for i, (h, w) in enumerate(anchors.hw):
+        v.ptr[i] = t.data_ptr() + (start * W + col) * es
+        v.frame_stride[i], v.anchor_stride[i], v.chan_stride[i] = A * W, W, 1
+        start += h * w
+    return v
+
+
+def view_levels(ts: List[torch.Tensor]) -> L.View:
+    """View of per-level conv outputs [F, ch, H, W] in NCHW or channels_last memory format."""
+    v = L.View()
+    for i, t in enumerate(ts):
+        assert t.dim() == 4
+        Fn, ch, H, W = t.shape
+        sF, sC, sH, sW = t.stride()
+        assert sH == W * sW, "rows of a level must be dense in the anchor dimension"
+        v.ptr[i] = t.data_ptr()
+        v.frame_stride[i], v.anchor_stride[i], v.chan_stride[i] = sF, sW, sC
+    return v
+
+
+@dataclass
+class HeadViews:
+    anchors: AnchorSpec
+    reg: L.View
+    obj: L.View
+    cls: L.View
+    dtype: torch.dtype
+    num_frames: int
+    num_classes: int
+    apply_sigmoid: bool
+    apply_decode: bool
+    _keep: tuple = ()  # keeps the tensors alive
+
+    @staticmethod
+    def from_fused(t: torch.Tensor, anchors: AnchorSpec, apply_sigmoid: bool, apply_decode: bool):
+        """[F, A, 5+C] tensor: seam S2 (sigmoid applied, not decoded) or S3 (decoded cxcywh)."""
+        t = t.contiguous()
+        return HeadViews(anchors, view_rowmajor(t, anchors, 0), view_rowmajor(t, anchors, 4),
+                         view_rowmajor(t, anchors, 5), t.dtype, t.shape[0], t.shape[2] - 5, apply_sigmoid,
+                         apply_decode, (t,))
+
+    @staticmethod
+    def from_levels(reg: List[torch.Tensor], obj: List[torch.Tensor], cls: List[torch.Tensor], anchors: AnchorSpec):
+        """Seam S1: raw per-level conv outputs (logits), sigmoid + decode fused into the kernels."""
+        return HeadViews(anchors, view_levels(reg), view_levels(obj), view_levels(cls), cls[0].dtype,
+                         cls[0].shape[0], cls[0].shape[1], True, True, (tuple(reg), tuple(obj), tuple(cls)))
+
+
+def select(head: HeadViews, mode: str, pre_k: int = 750, conf_thresh: float = 0.001, minimal_limit: int = 0,
+           maximal_limit: int = 0, cand_cap: Optional[int] = None):
+    """K1.  Returns dict(idx,box,score,cls,count) of device tensors [F,cap(,4)] / [F]."""
+    dev = torch.device("cuda")
+    Fn, A = head.num_frames, head.anchors.num_anchors
+    if cand_cap is None:
+        cand_cap = min(pre_k, A) if mode == "A" else (maximal_limit if maximal_limit else A)
+        if mode == "B" and minimal_limit:
+            cand_cap = max(cand_cap, min(minimal_limit, A))
+    out = dict(idx=torch.empty(Fn, cand_cap, dtype=torch.int32, device=dev),
+               box=torch.empty(Fn, cand_cap, 4, dtype=torch.float32, device=dev),
+               score=torch.empty(Fn, cand_cap, dtype=torch.float32, device=dev),
+               cls=torch.empty(Fn, cand_cap, dtype=torch.int32, device=dev),
+               count=torch.empty(Fn, dtype=torch.int32, device=dev), cap=cand_cap)
+    a = L.SelectArgs()
+    a.mode = 0 if mode == "A" else 1
+    a.num_frames, a.num_classes, a.head_dtype = Fn, head.num_classes, _DT[head.dtype]
+    a.apply_sigmoid, a.apply_decode = int(head.apply_sigmoid), int(head.apply_decode)
+    a.pre_k, a.conf_thresh = pre_k, conf_thresh
+    a.minimal_limit, a.maximal_limit, a.cand_cap = minimal_limit, maximal_limit, cand_cap
+    a.anchors, a.reg, a.obj, a.cls = head.anchors.to_c(), head.reg, head.obj, head.cls
+    a.cand_idx, a.cand_box, a.cand_score = _p(out["idx"]), _p(out["box"]), _p(out["score"])
+    a.cand_cls, a.cand_count = _p(out["cls"]), _p(out["count"])
+    L.check(L.lib().tscd_select(C.byref(a), _stream()), "tscd_select")
+    return out
+
+
+def nms(box: torch.Tensor, score: torch.Tensor, cls: torch.Tensor, count: torch.Tensor, iou_thresh: float,
+        max_keep: Optional[int] = None, status: Optional[torch.Tensor] = None):
+    """K2.  box [F,cap,4] f32, score [F,cap] f32, cls [F,cap] i32, count [F] i32 -> (keep [F,max_keep], keep_count [F])."""
+    Fn, cap = score.shape
+    max_keep = cap if max_keep is None else max_keep
+    keep = torch.empty(Fn, max_keep, dtype=torch.int32, device=score.device)
+    keep_count = torch.empty(Fn, dtype=torch.int32, device=score.device)
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=score.device)
+    a = L.NmsArgs()
+    a.num_frames, a.cand_cap, a.max_keep, a.iou_thresh = Fn, cap, max_keep, iou_thresh
+    a.box, a.score, a.cls, a.count = _p(box), _p(score), _p(cls), _p(count)
+    a.keep, a.keep_count, a.status = _p(keep), _p(keep_count), _p(status)
+    L.check(L.lib().tscd_nms(C.byref(a), _stream()), "tscd_nms")
+    return keep, keep_count, status
+
+
+def gather(head: HeadViews, feats, feat_dtype: torch.dtype, feat_dim: int, cand, keep=None, keep_count=None,
+           max_keep: Optional[int] = None, bank_dtype: torch.dtype = torch.float16, bank_rows: Optional[int] = None):
+    """K3.  feats = (view_cls, view_reg, view_edge).  Returns dict with sel_count,row_off,sel_idx,sel_rows,bank_*."""
+    dev = torch.device("cuda")
+    Fn, Cn = head.num_frames, head.num_classes
+    use_keep = keep is not None
+    max_keep = (keep.shape[1] if use_keep else cand["cap"]) if max_keep is None else max_keep
+    rows_cap = Fn * max_keep if bank_rows is None else bank_rows
+    out = dict(sel_count=torch.empty(Fn, dtype=torch.int32, device=dev),
+               row_off=torch.empty(Fn + 1, dtype=torch.int32, device=dev),
+               sel_idx=torch.empty(Fn, max_keep, dtype=torch.int32, device=dev),
+               sel_rows=torch.empty(Fn, max_keep, 7 + Cn, dtype=torch.float32, device=dev),
+               bank_cls=torch.zeros(rows_cap, feat_dim, dtype=bank_dtype, device=dev),
+               bank_reg=torch.zeros(rows_cap, feat_dim, dtype=bank_dtype, device=dev),
+               bank_edge=torch.zeros(rows_cap, feat_dim, dtype=bank_dtype, device=dev),
+               bank_score=torch.zeros(rows_cap, dtype=torch.float32, device=dev),
+               bank_fg=torch.zeros(rows_cap, dtype=torch.float32, device=dev),
+               bank_box=torch.zeros(rows_cap, 4, dtype=torch.float32, device=dev), max_keep=max_keep)
+    a = L.GatherArgs()
+    a.num_frames, a.num_classes, a.head_dtype = Fn, Cn, _DT[head.dtype]
+    a.apply_sigmoid, a.apply_decode = int(head.apply_sigmoid), int(head.apply_decode)
+    a.cand_cap, a.max_keep, a.use_keep = cand["cap"], max_keep, int(use_keep)
+    a.feat_dim, a.feat_dtype, a.bank_dtype = feat_dim, _DT[feat_dtype], _DT[bank_dtype]
+    a.anchors, a.reg, a.obj, a.cls = head.anchors.to_c(), head.reg, head.obj, head.cls
+    a.feat_cls, a.feat_reg, a.feat_edge = feats
+    a.cand_idx, a.cand_count = _p(cand["idx"]), _p(cand["count"])
+    a.keep, a.keep_count = _p(keep), _p(keep_count)
+    for k in ("sel_count", "row_off", "sel_idx", "sel_rows", "bank_cls", "bank_reg", "bank_edge", "bank_score",
+              "bank_fg", "bank_box"):
+        setattr(a, k, _p(out[k]))
+    L.check(L.lib().tscd_gather(C.byref(a), _stream()), "tscd_gather")
+    return out
