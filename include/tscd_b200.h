@@ -145,6 +145,28 @@ typedef struct {
 } tscd_gather_args;
 int tscd_gather(const tscd_gather_args* args, void* stream);
 
+/* ---- Linear layer (tcgen05 GEMM) --------------------------------------------------------------------------
+ * y[M,N] = x[M,K] * w[N,K]^T + bias.  Replaces every F.linear on the path (post_trans.py:613-618,687-689,
+ * 1159-1161; tscd_matching.py:37-39,165-167,756; tscd_head.py:507,515-520).  x / w are fp16 or bf16 with K
+ * contiguous (row pitches ldx / ldw in elements, multiples of 8; pointers 16-byte aligned); accumulation is
+ * fp32 in tensor memory.  M is the row CAPACITY; if m_dev is non-null only the first min(M, *m_dev) rows are
+ * computed (data-dependent row counts stay on the device).  Either or both outputs may be given. */
+typedef struct {
+    int32_t M, N, K;
+    int32_t dtype;        /* TSCD_F16 / TSCD_BF16 operand type (also the type of out16) */
+    const void* x;
+    int64_t ldx;
+    const void* w;
+    int64_t ldw;
+    const float* bias;    /* [N] or NULL */
+    const int32_t* m_dev; /* device row count or NULL */
+    void* out16;          /* [M, ld16] or NULL */
+    int32_t ld16;
+    float* out32;         /* [M, ld32] or NULL */
+    int32_t ld32;
+} tscd_linear_args;
+int tscd_linear(const tscd_linear_args* args, void* stream);
+
 /* Library / build information (also proves the .so was loaded). */
 const char* tscd_version(void);
 int tscd_device_ok(void); /* 1 if the current device is compute capability 10.x */

@@ -25,8 +25,8 @@ def test_struct_sizes_match_header():
     import subprocess
     import tempfile
     from tscd_b200 import _lib
-    src = '#include <stdio.h>\n#include "tscd_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",' \
-          'sizeof(tscd_view),sizeof(tscd_anchors),sizeof(tscd_select_args),sizeof(tscd_nms_args),sizeof(tscd_gather_args));return 0;}'
+    src = '#include <stdio.h>\n#include "tscd_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",' \
+          'sizeof(tscd_view),sizeof(tscd_anchors),sizeof(tscd_select_args),sizeof(tscd_nms_args),sizeof(tscd_gather_args),sizeof(tscd_linear_args));return 0;}'
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "p.c")
         open(c, "w").write(src)
@@ -34,5 +34,5 @@ def test_struct_sizes_match_header():
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     import ctypes
-    mine = [ctypes.sizeof(x) for x in (_lib.View, _lib.Anchors, _lib.SelectArgs, _lib.NmsArgs, _lib.GatherArgs)]
+    mine = [ctypes.sizeof(x) for x in (_lib.View, _lib.Anchors, _lib.SelectArgs, _lib.NmsArgs, _lib.GatherArgs, _lib.LinearArgs)]
     assert sizes == mine

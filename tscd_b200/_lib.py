@@ -50,6 +50,13 @@ class GatherArgs(C.Structure):
                 ("bank_score", C.c_void_p), ("bank_fg", C.c_void_p), ("bank_box", C.c_void_p)]
 
 
+class LinearArgs(C.Structure):
+    _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("dtype", C.c_int32),
+                ("x", C.c_void_p), ("ldx", C.c_int64), ("w", C.c_void_p), ("ldw", C.c_int64),
+                ("bias", C.c_void_p), ("m_dev", C.c_void_p), ("out16", C.c_void_p), ("ld16", C.c_int32),
+                ("out32", C.c_void_p), ("ld32", C.c_int32)]
+
+
 _lib = None
 
 # every symbol include/tscd_b200.h declares: (name, restype, argtypes)
@@ -59,6 +66,7 @@ SYMBOLS = [
     ("tscd_select", C.c_int, [C.POINTER(SelectArgs), C.c_void_p]),
     ("tscd_nms", C.c_int, [C.POINTER(NmsArgs), C.c_void_p]),
     ("tscd_gather", C.c_int, [C.POINTER(GatherArgs), C.c_void_p]),
+    ("tscd_linear", C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
 ]
 
 

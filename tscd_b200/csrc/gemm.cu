@@ -1,0 +1,237 @@
+// Linear layers of the aggregation stage as a hand-written tcgen05 GEMM:
+//     C[M,N] = A[M,K] * W[N,K]^T (+ bias[N]),  A/W fp16 or bf16 (K contiguous), fp32 accumulation in TMEM.
+//
+// Replaces the F.linear / cuBLAS calls at yolox/models/post_trans.py:613-618,687-689,1159-1161,
+// yolox/models/tscd_matching.py:37-39,165-167,756 and yolox/models/tscd_head.py:507,515-520.
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0     TMA producer: cp.async.bulk.tensor 2D loads of the A (128x64) and W (BNx64) k-blocks into a
+//              3-stage shared-memory ring (128-byte swizzle), completion on "full" mbarriers;
+//   warp 1     allocates TMEM and issues tcgen05.mma (one elected thread, 4 x K=16 per k-block), releasing
+//              ring slots with tcgen05.commit on "empty" mbarriers and signalling the epilogue at the end;
+//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns per instruction; thread == output row), bias,
+//              conversion and direct 64/128-byte row-segment stores to global memory.
+// The row count may live in device memory (`m_dev`): CTAs whose rows are all beyond it exit immediately,
+// which is how the ragged, data-dependent proposal counts are handled without a host sync.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace tscd {
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmBK = 64;
+constexpr int kGemmStages = 3;
+constexpr int kGemmThreads = 192;
+
+struct GemmParams {
+    int M, N, K;
+    const int* m_dev;     // optional device row count (min(M, *m_dev) rows are valid)
+    const float* bias;    // optional [N]
+    void* out16;          // optional 16-bit output (same type as the operands), pitch ld16 elements
+    float* out32;         // optional fp32 output, pitch ld32 elements
+    int ld16, ld32;
+    int is_bf16;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                const __grid_constant__ CUtensorMap tmap_w,
+                                                                const GemmParams p) {
+    using namespace tc;
+    const int m0 = blockIdx.y * kGemmBM;
+    const int n0 = blockIdx.x * BN;
+    int M = p.M;
+    if (p.m_dev) M = min(M, __ldg(p.m_dev));
+    if (m0 >= M) return;  // uniform over the CTA, before any barrier / TMEM state exists
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // 1024-byte alignment is required by the 128-byte swizzle
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kABytes = kGemmBM * kGemmBK * 2;
+    constexpr int kWBytes = BN * kGemmBK * 2;
+    unsigned char* sA = smem;
+    unsigned char* sW = smem + kGemmStages * kABytes;
+    __shared__ __align__(8) uint64_t full_bar[kGemmStages];
+    __shared__ __align__(8) uint64_t empty_bar[kGemmStages];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_kb = (p.K + kGemmBK - 1) / kGemmBK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_w);
+        for (int s = 0; s < kGemmStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<BN>(&tmem_base_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kGemmStages;
+                const uint32_t ph = (kb / kGemmStages) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], kABytes + kWBytes);
+                tma_load_2d(sA + s * kABytes, &tmap_a, &full_bar[s], kb * kGemmBK, m0);
+                tma_load_2d(sW + s * kWBytes, &tmap_w, &full_bar[s], kb * kGemmBK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_f16(p.is_bf16, kGemmBM, BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kGemmStages;
+                const uint32_t ph = (kb / kGemmStages) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + s * kABytes));
+                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sW + s * kWBytes));
+#pragma unroll
+                for (int k = 0; k < kGemmBK / 16; ++k) {
+                    // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
+                    umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(&tmem_full_bar);
+        }
+    } else {
+        // epilogue warps 2..5 own TMEM lane quadrant (warp % 4)
+        const int q = warp & 3;
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        const int row = m0 + q * 32 + lane;
+        const bool row_ok = row < M;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tmem_ld_wait();
+            const int col0 = n0 + c0;
+            if (!row_ok || col0 >= p.N) continue;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                v[j] = __uint_as_float(r[j]);
+                if (p.bias && col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+            }
+            const bool full = (col0 + 32 <= p.N);
+            if (p.out32) {
+                float* o = p.out32 + (int64_t)row * p.ld32 + col0;
+                if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+                    for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = v[j];
+                }
+            }
+            if (p.out16) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (p.is_bf16) {
+                        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                        pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                    } else {
+                        __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                        pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                }
+                uint16_t* o = reinterpret_cast<uint16_t*>(p.out16) + (int64_t)row * p.ld16 + col0;
+                if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(o + 2 * j) = make_uint4(pk[j], pk[j + 1], pk[j + 2], pk[j + 3]);
+                } else {
+                    const uint16_t* h = reinterpret_cast<const uint16_t*>(pk);
+                    for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = h[j];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<BN>(tmem_base);
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+        if (q != cudaDriverEntryPointSuccess) return nullptr;
+        fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// 2-D K-major operand [rows, K] with row pitch ld (elements); box = 64 (K) x box_rows, 128-byte swizzle.
+int make_tmap_kmajor(CUtensorMap* m, const void* ptr, int is_bf16, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return TSCD_ERR_CUDA;
+    if ((ld * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return TSCD_ERR_INVALID_ARG;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)(ld * 2)};
+    cuuint32_t box[2] = {(cuuint32_t)kGemmBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                     const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? TSCD_OK : TSCD_ERR_CUDA;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
+    constexpr size_t smem = (size_t)kGemmStages * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return TSCD_ERR_CUDA;
+        attr_set = true;
+    }
+    dim3 grid((p.N + BN - 1) / BN, (p.M + kGemmBM - 1) / kGemmBM);
+    gemm_tn_kernel<BN><<<grid, kGemmThreads, smem, st>>>(ta, tw, p);
+    return cudaGetLastError() == cudaSuccess ? TSCD_OK : TSCD_ERR_CUDA;
+}
+
+}  // namespace tscd
+
+extern "C" int tscd_linear(const tscd_linear_args* a, void* stream) {
+    using namespace tscd;
+    if (!a || a->M <= 0 || a->N <= 0 || a->K <= 0 || !a->x || !a->w) return TSCD_ERR_INVALID_ARG;
+    if (a->dtype != TSCD_F16 && a->dtype != TSCD_BF16) return TSCD_ERR_UNSUPPORTED;
+    if (!a->out16 && !a->out32) return TSCD_ERR_INVALID_ARG;
+    const int is_bf16 = a->dtype == TSCD_BF16;
+    const int BN = a->N <= 64 ? 64 : 128;
+    CUtensorMap ta, tw;
+    int rc = make_tmap_kmajor(&ta, a->x, is_bf16, a->M, a->K, a->ldx, kGemmBM);
+    if (rc != TSCD_OK) return rc;
+    rc = make_tmap_kmajor(&tw, a->w, is_bf16, a->N, a->K, a->ldw, BN);
+    if (rc != TSCD_OK) return rc;
+    GemmParams p;
+    p.M = a->M; p.N = a->N; p.K = a->K;
+    p.m_dev = a->m_dev; p.bias = a->bias;
+    p.out16 = a->out16; p.out32 = a->out32;
+    p.ld16 = a->ld16; p.ld32 = a->ld32;
+    p.is_bf16 = is_bf16;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return BN == 64 ? launch_gemm<64>(ta, tw, p, st) : launch_gemm<128>(ta, tw, p, st);
+}

@@ -171,3 +171,28 @@ def gather(head: HeadViews, feats, feat_dtype: torch.dtype, feat_dim: int, cand,
         setattr(a, k, _p(out[k]))
     L.check(L.lib().tscd_gather(C.byref(a), _stream()), "tscd_gather")
     return out
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, m_dev: Optional[torch.Tensor] = None,
+           out16: Optional[torch.Tensor] = None, out32: Optional[torch.Tensor] = None, want16=True, want32=False):
+    """y = x @ w.T + bias on the tcgen05 GEMM.  x [M,K] (row pitch may exceed K), w [N,K]; both fp16 or bf16.
+    Outputs may be column slices of wider buffers (stride(0) is the pitch)."""
+    assert x.dtype == w.dtype and x.dtype in (torch.float16, torch.bfloat16)
+    assert x.stride(1) == 1 and w.stride(1) == 1
+    M, K = x.shape
+    N = w.shape[0]
+    if out16 is None and want16:
+        out16 = torch.empty(M, N, dtype=x.dtype, device=x.device)
+    if out32 is None and want32:
+        out32 = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    a = L.LinearArgs()
+    a.M, a.N, a.K, a.dtype = M, N, K, _DT[x.dtype]
+    a.x, a.ldx, a.w, a.ldw = _p(x), x.stride(0), _p(w), w.stride(0)
+    a.bias = _p(bias)
+    a.m_dev = _p(m_dev)
+    a.out16, a.ld16 = _p(out16), (0 if out16 is None else out16.stride(0))
+    a.out32, a.ld32 = _p(out32), (0 if out32 is None else out32.stride(0))
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous()
+    L.check(L.lib().tscd_linear(C.byref(a), _stream()), "tscd_linear")
+    return out16, out32
