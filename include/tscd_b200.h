@@ -167,6 +167,75 @@ typedef struct {
 } tscd_linear_args;
 int tscd_linear(const tscd_linear_args* args, void* stream);
 
+/* ---- K4: cross-frame attention aggregation (tcgen05) -----------------------------------------------------
+ * Replaces Attention_mca_g2l.forward (post_trans.py:601-714, called once per local frame by
+ * MCA_tscd_g2l_reg.forward :1127-1162) and Attention_msa.forward (:734-826).
+ *
+ * The bank of a clip is [local rows | global rows]; a query (local row of frame f) attends to the rows of its
+ * own frame and to all global rows ("no inter-frame mixing"); with self_attn=1 every row attends to every row
+ * of its clip (gen-1 MSA).  Three entry points:
+ *   tscd_attn_prep    per-head L2 normalisation of q,k,v (no epsilon, post_trans.py:623-628), folding of
+ *                     25 * cls_score[key] into k_cls and 25 into k_reg (:658-660), the transposed value
+ *                     matrices V^T per clip, and the copy of the query rows' raw v (x_ori, :680,684);
+ *   tscd_attn_pv      softmax(QK^T) of both branches, attn = (attn_cls + attn_reg)/2, attn @ v_cls and
+ *                     attn @ v_reg (:672-685), plus the per-row softmax statistics;
+ *   tscd_attn_round2  the `ave` round (:692-712): head-mean raw-v cosine masks (> sim_thresh, > conf_sim_thresh),
+ *                     softmax of the head-mean attention restricted to the mask and renormalised, times V.
+ * Rows: `row_off` [B*F+1] bank offsets per frame; queries of clip b are bank rows
+ * [row_off[b*F], row_off[b*F+L]); their packed output index is lrow_off[b*L] + (row - row_off[b*F]). */
+typedef struct {
+    int32_t B, F, L;          /* clips, frames per clip, local frames per clip */
+    int32_t self_attn;        /* 1: every row is a query and every key of the clip is visible (MSA) */
+    int32_t dtype;            /* TSCD_F16 / TSCD_BF16 */
+    int32_t row_cap;          /* rows of the [.,256] operand arrays */
+    int32_t nk_pitch;         /* columns (keys) of each V^T row; multiple of 128 */
+    const int32_t* row_off;   /* [B*F+1] */
+    const int32_t* lrow_off;  /* [B*L+1] (== row_off when self_attn) */
+} tscd_attn_layout;
+
+typedef struct {
+    tscd_attn_layout lay;
+    float scale;              /* 25 */
+    const void* qkv_cls;      /* [row_cap, ld_qkv]: q | k | v (256 columns each) of the cls branch */
+    const void* qkv_reg;
+    int32_t ld_qkv;
+    const float* key_score;   /* [row_cap] cls_score of every bank row (bank_score) */
+    void *qn_cls, *kn_cls, *vn_cls, *qn_reg, *kn_reg, *vn_reg; /* [row_cap,256] outputs */
+    void *vt_cls, *vt_reg;    /* [B*256, nk_pitch] outputs: V^T per clip (un-normalised v) */
+    void* xori_cls;           /* [loc_cap, ld_xori] raw v of the query rows (x_ori), or NULL */
+    void* xori_reg;
+    int32_t ld_xori;
+    int32_t* row_frame;       /* [row_cap] frame index (within its clip) of every bank row */
+} tscd_attn_prep_args;
+int tscd_attn_prep(const tscd_attn_prep_args* args, void* stream);
+
+typedef struct {
+    tscd_attn_layout lay;
+    const void *qn_cls, *kn_cls, *qn_reg, *kn_reg;
+    const void *vt_cls, *vt_reg;
+    const int32_t* row_frame;
+    int32_t need_reg;         /* 0: skip attn @ v_reg (TSCD `agg` discards it, tscd_head.py:480) */
+    void* x_cls;              /* [loc_cap, ld_x] attn @ v_cls, heads concatenated */
+    void* x_reg;
+    int32_t ld_x;
+    float* stats;             /* [loc_cap,16]: row max (cls h0-3, reg h0-3), row sum (cls h0-3, reg h0-3) */
+} tscd_attn_pv_args;
+int tscd_attn_pv(const tscd_attn_pv_args* args, void* stream);
+
+typedef struct {
+    tscd_attn_layout lay;
+    const void *qn_cls, *kn_cls, *qn_reg, *kn_reg, *vn_cls, *vn_reg;
+    const void* vt;           /* [B*256, nk_pitch] value matrix (transposed) to aggregate */
+    const int32_t* row_frame;
+    const float* stats;
+    int32_t use_obj_mask;     /* 0: weights = sim_mask (cls output); 1: sim_mask * obj_mask (reg output) */
+    float sim_thresh;         /* 0.75 */
+    float conf_sim_thresh;    /* 0.99 */
+    void* out;                /* [loc_cap, ld_out] 256 columns */
+    int32_t ld_out;
+} tscd_attn_round2_args;
+int tscd_attn_round2(const tscd_attn_round2_args* args, void* stream);
+
 /* Library / build information (also proves the .so was loaded). */
 const char* tscd_version(void);
 int tscd_device_ok(void); /* 1 if the current device is compute capability 10.x */

@@ -57,6 +57,34 @@ class LinearArgs(C.Structure):
                 ("out32", C.c_void_p), ("ld32", C.c_int32)]
 
 
+class AttnLayout(C.Structure):
+    _fields_ = [("B", C.c_int32), ("F", C.c_int32), ("L", C.c_int32), ("self_attn", C.c_int32), ("dtype", C.c_int32),
+                ("row_cap", C.c_int32), ("nk_pitch", C.c_int32), ("row_off", C.c_void_p), ("lrow_off", C.c_void_p)]
+
+
+class AttnPrepArgs(C.Structure):
+    _fields_ = [("lay", AttnLayout), ("scale", C.c_float), ("qkv_cls", C.c_void_p), ("qkv_reg", C.c_void_p),
+                ("ld_qkv", C.c_int32), ("key_score", C.c_void_p),
+                ("qn_cls", C.c_void_p), ("kn_cls", C.c_void_p), ("vn_cls", C.c_void_p),
+                ("qn_reg", C.c_void_p), ("kn_reg", C.c_void_p), ("vn_reg", C.c_void_p),
+                ("vt_cls", C.c_void_p), ("vt_reg", C.c_void_p), ("xori_cls", C.c_void_p), ("xori_reg", C.c_void_p),
+                ("ld_xori", C.c_int32), ("row_frame", C.c_void_p)]
+
+
+class AttnPvArgs(C.Structure):
+    _fields_ = [("lay", AttnLayout), ("qn_cls", C.c_void_p), ("kn_cls", C.c_void_p), ("qn_reg", C.c_void_p),
+                ("kn_reg", C.c_void_p), ("vt_cls", C.c_void_p), ("vt_reg", C.c_void_p), ("row_frame", C.c_void_p),
+                ("need_reg", C.c_int32), ("x_cls", C.c_void_p), ("x_reg", C.c_void_p), ("ld_x", C.c_int32),
+                ("stats", C.c_void_p)]
+
+
+class AttnRound2Args(C.Structure):
+    _fields_ = [("lay", AttnLayout), ("qn_cls", C.c_void_p), ("kn_cls", C.c_void_p), ("qn_reg", C.c_void_p),
+                ("kn_reg", C.c_void_p), ("vn_cls", C.c_void_p), ("vn_reg", C.c_void_p), ("vt", C.c_void_p),
+                ("row_frame", C.c_void_p), ("stats", C.c_void_p), ("use_obj_mask", C.c_int32),
+                ("sim_thresh", C.c_float), ("conf_sim_thresh", C.c_float), ("out", C.c_void_p), ("ld_out", C.c_int32)]
+
+
 _lib = None
 
 # every symbol include/tscd_b200.h declares: (name, restype, argtypes)
@@ -67,6 +95,9 @@ SYMBOLS = [
     ("tscd_nms", C.c_int, [C.POINTER(NmsArgs), C.c_void_p]),
     ("tscd_gather", C.c_int, [C.POINTER(GatherArgs), C.c_void_p]),
     ("tscd_linear", C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
+    ("tscd_attn_prep", C.c_int, [C.POINTER(AttnPrepArgs), C.c_void_p]),
+    ("tscd_attn_pv", C.c_int, [C.POINTER(AttnPvArgs), C.c_void_p]),
+    ("tscd_attn_round2", C.c_int, [C.POINTER(AttnRound2Args), C.c_void_p]),
 ]
 
 

@@ -1,0 +1,74 @@
+"""Host orchestration of the MCA (global->local cross-attention) aggregation modules.
+
+Reference: MCA_tscd_g2l_reg.forward (post_trans.py:1127-1162) + Attention_mca_g2l.forward (:601-714), used
+twice by TSCDHead (`agg`, `agg_iou`; tscd_head.py:104,113,480,491).  Differences in *how*, not *what*:
+the q/kv projections of both modules run as one GEMM per branch over the whole bank (the reference
+re-projects the global bank once per local frame and module), and the per-local-frame loop is one masked
+attention launch."""
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+
+
+class MCAWeights:
+    """16-bit device copies of one module's weights, q/kv fused as [Wq; Wkv] per branch."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, dtype=torch.float16, device="cuda"):
+        def w(name):
+            return sd[prefix + name].detach().to(device=device, dtype=dtype).contiguous()
+
+        def b(name):
+            return sd[prefix + name].detach().to(device=device, dtype=torch.float32).contiguous()
+
+        self.qkv_cls = torch.cat([w("mca.q_cls_local.weight"), w("mca.kv_cls.weight")], 0).contiguous()   # [768,256]
+        self.qkv_reg = torch.cat([w("mca.q_reg_local.weight"), w("mca.kv_reg.weight")], 0).contiguous()
+        self.lin_w, self.lin_b = w("mca.linear.weight"), b("mca.linear.bias")
+        self.has_reg = (prefix + "mca.linear_reg.weight") in sd
+        if self.has_reg:
+            self.linreg_w, self.linreg_b = w("mca.linear_reg.weight"), b("mca.linear_reg.bias")
+            self.obj_w, self.obj_b = w("linear_obj.weight"), b("linear_obj.bias")
+        self.out_w, self.out_b = w("linear.weight"), b("linear.bias")
+
+
+def make_layout(sel_count: torch.Tensor, B: int, F: int, L: int, row_cap: int, loc_cap: int, nk_pitch: int,
+                dtype=torch.float16, row_off: Optional[torch.Tensor] = None) -> ops.AttnLayoutT:
+    """Device-side prefix offsets from per-frame counts (torch ops on the current stream; no sync)."""
+    cnt = sel_count.view(B, F).to(torch.int32)
+    if row_off is None:
+        row_off = torch.zeros(B * F + 1, dtype=torch.int32, device=sel_count.device)
+        row_off[1:] = torch.cumsum(cnt.reshape(-1), 0)
+    lrow_off = torch.zeros(B * L + 1, dtype=torch.int32, device=sel_count.device)
+    lrow_off[1:] = torch.cumsum(cnt[:, :L].reshape(-1), 0)
+    return ops.AttnLayoutT(B, F, L, row_off, lrow_off, row_cap, loc_cap, nk_pitch, dtype)
+
+
+def mca_forward(lay: ops.AttnLayoutT, w: MCAWeights, bank_cls, bank_reg, bank_score, n_rows_dev, n_loc_dev,
+                need_reg=True, sim_thresh=0.75, conf_sim_thresh=0.99, debug=None):
+    """One MCA module.  bank_* [row_cap,256] 16-bit, bank_score [row_cap] fp32; n_rows_dev / n_loc_dev are int32
+    device scalars (total bank rows / total local rows).  Returns (trans_cls [loc_cap,1024], trans_obj or None)."""
+    dev, dt = bank_cls.device, lay.dtype
+    qkv_c, _ = ops.linear(bank_cls, w.qkv_cls, m_dev=n_rows_dev)
+    qkv_r, _ = ops.linear(bank_reg, w.qkv_reg, m_dev=n_rows_dev)
+    tmp_c = torch.zeros(lay.loc_cap, 512, dtype=dt, device=dev)      # [attn@v | x_ori]
+    tmp_r = torch.zeros(lay.loc_cap, 512, dtype=dt, device=dev)
+    bufs = ops.attn_prep(lay, qkv_c, qkv_r, bank_score, xori_cls=tmp_c[:, 256:], xori_reg=tmp_r[:, 256:])
+    stats = torch.zeros(lay.loc_cap, 16, dtype=torch.float32, device=dev)
+    ops.attn_pv(lay, bufs, tmp_c[:, :256], tmp_r[:, :256], stats, need_reg=need_reg)
+    cat_c = torch.zeros(lay.loc_cap, 768, dtype=dt, device=dev)      # [round2 @ V | linear(x)]
+    ops.linear(tmp_c, w.lin_w, w.lin_b, m_dev=n_loc_dev, out16=cat_c[:, 256:], want16=False)
+    ops.attn_round2(lay, bufs, bufs["vt_cls"], stats, cat_c[:, :256], use_obj_mask=False, sim_thresh=sim_thresh,
+                    conf_sim_thresh=conf_sim_thresh)
+    trans_cls16, trans_cls32 = ops.linear(cat_c, w.out_w, w.out_b, m_dev=n_loc_dev, want16=True, want32=True)
+    trans_obj16 = trans_obj32 = None
+    cat_r = None
+    if need_reg:
+        cat_r = torch.zeros(lay.loc_cap, 768, dtype=dt, device=dev)
+        ops.linear(tmp_r, w.linreg_w, w.linreg_b, m_dev=n_loc_dev, out16=cat_r[:, 256:], want16=False)
+        ops.attn_round2(lay, bufs, bufs["vt_reg"], stats, cat_r[:, :256], use_obj_mask=True, sim_thresh=sim_thresh,
+                        conf_sim_thresh=conf_sim_thresh)
+        trans_obj16, trans_obj32 = ops.linear(cat_r, w.obj_w, w.obj_b, m_dev=n_loc_dev, want16=True, want32=True)
+    if debug is not None:
+        debug.update(qkv_c=qkv_c, qkv_r=qkv_r, bufs=bufs, tmp_c=tmp_c, tmp_r=tmp_r, stats=stats, cat_c=cat_c, cat_r=cat_r)
+    return (trans_cls16, trans_cls32), (trans_obj16, trans_obj32)

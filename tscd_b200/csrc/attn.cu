@@ -1,0 +1,708 @@
+// K4: cross-frame attention aggregation on tcgen05 tensor cores (see include/tscd_b200.h for semantics).
+//
+// Reference: Attention_mca_g2l.forward (yolox/models/post_trans.py:601-714) / Attention_msa.forward (:734-826).
+//
+// Layout of the work: one CTA per (clip, 128-query tile).  Queries of a clip are its local rows; keys are
+// all rows of the clip with a per-(query,key) visibility mask (own frame or global frame), which is how the
+// reference's per-local-frame loop (post_trans.py:1143-1151) collapses into one masked attention problem
+// and the global K/V projections are computed once instead of once per local frame.
+//
+// Every matrix product runs on the 5th-gen tensor cores (tcgen05.mma, fp32 accumulators in TMEM):
+//   S_cls/S_reg = Qn Kn^T per head (K-major operands straight from TMA, 128-byte swizzle),
+//   attn @ V     with the probabilities written to shared memory by the softmax warps as a swizzled K-major
+//                A operand and V^T tiles as the B operand,
+//   the head-mean raw-v cosine similarity as ONE K=256 product of the per-head-normalised rows,
+//   the round-2 weights @ V.
+// Softmax statistics are exact two-pass (row max, then exp/sum) so fp16 probabilities never underflow.
+// The CTA runs its phases in lock step (TMA -> MMA -> softmax warps); concurrency comes from the other
+// clips' CTAs.  Warps 0-3 own the 128 TMEM lanes (thread == query row); warp 4 issues TMA and MMA.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace tscd {
+
+int make_tmap_kmajor(CUtensorMap* m, const void* ptr, int is_bf16, int64_t rows, int64_t K, int64_t ld, int box_rows);
+
+constexpr int kAttnThreads = 160;
+constexpr float kLog2e = 1.4426950408889634f;
+
+// -------------------------------------------------------------------------------------------------------
+// prep: normalise / scale / transpose
+// -------------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float2 ld2(const T* p);
+template <> __device__ __forceinline__ float2 ld2<__half>(const __half* p) { return __half22float2(*reinterpret_cast<const __half2*>(p)); }
+template <> __device__ __forceinline__ float2 ld2<__nv_bfloat16>(const __nv_bfloat16* p) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+template <typename T>
+__device__ __forceinline__ void st2(T* p, float a, float b);
+template <> __device__ __forceinline__ void st2<__half>(__half* p, float a, float b) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(a, b); }
+template <> __device__ __forceinline__ void st2<__nv_bfloat16>(__nv_bfloat16* p, float a, float b) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+
+constexpr int kPrepPitch = 72;  // 64 keys + 8 padding (bank spread) per channel row of the transpose tile
+
+template <typename T>
+__global__ void __launch_bounds__(256) attn_prep_kernel(const tscd_attn_prep_args a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    T* tile_c = reinterpret_cast<T*>(smem_raw);        // [256][kPrepPitch]
+    T* tile_r = tile_c + 256 * kPrepPitch;
+    const tscd_attn_layout& lay = a.lay;
+    const int b = blockIdx.y, k0 = blockIdx.x * 64;
+    const int s0 = lay.row_off[b * lay.F];
+    const int n_clip = lay.row_off[(b + 1) * lay.F] - s0;
+    const int n_loc = lay.self_attn ? n_clip : (lay.row_off[b * lay.F + lay.L] - s0);
+    const int n_pad = min((n_clip + 127) & ~127, lay.nk_pitch);
+    if (k0 >= n_pad) return;
+    const int lbase = lay.lrow_off[b * lay.L];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int i = 0; i < 8; ++i) {
+        const int r = k0 + warp * 8 + i;       // key index within the clip
+        const int row = s0 + r;                // bank row
+        const bool valid = r < n_clip;
+        if (valid && lane == 0) {
+            int f = 0;
+            while (f + 1 < lay.F && lay.row_off[b * lay.F + f + 1] <= row) ++f;
+            a.row_frame[row] = f;
+        }
+        const float kscale_c = valid ? a.scale * __ldg(a.key_score + row) : 0.f;
+#pragma unroll
+        for (int br = 0; br < 2; ++br) {
+            const T* src = reinterpret_cast<const T*>(br == 0 ? a.qkv_cls : a.qkv_reg) + (int64_t)row * a.ld_qkv;
+            T* qn = reinterpret_cast<T*>(br == 0 ? a.qn_cls : a.qn_reg) + (int64_t)row * 256;
+            T* kn = reinterpret_cast<T*>(br == 0 ? a.kn_cls : a.kn_reg) + (int64_t)row * 256;
+            T* vn = reinterpret_cast<T*>(br == 0 ? a.vn_cls : a.vn_reg) + (int64_t)row * 256;
+            T* tile = br == 0 ? tile_c : tile_r;
+            T* xori = reinterpret_cast<T*>(br == 0 ? a.xori_cls : a.xori_reg);
+            const float ks = br == 0 ? kscale_c : a.scale;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const int c = h * 64 + lane * 2;
+                float2 q = make_float2(0.f, 0.f), k = q, v = q;
+                if (valid) { q = ld2<T>(src + c); k = ld2<T>(src + 256 + c); v = ld2<T>(src + 512 + c); }
+                float sq = warp_sumf(q.x * q.x + q.y * q.y);
+                float sk = warp_sumf(k.x * k.x + k.y * k.y);
+                float sv = warp_sumf(v.x * v.x + v.y * v.y);
+                if (valid) {
+                    const float nq = sqrtf(sq), nk = sqrtf(sk), nv = sqrtf(sv);
+                    st2<T>(qn + c, q.x / nq, q.y / nq);
+                    st2<T>(kn + c, k.x / nk * ks, k.y / nk * ks);
+                    st2<T>(vn + c, v.x / nv, v.y / nv);
+                    if (xori && r < n_loc) st2<T>(xori + (int64_t)(lbase + r) * a.ld_xori + c, v.x, v.y);
+                }
+                tile[(c) * kPrepPitch + (r - k0)] = cvt_from_float<T>(v.x);
+                tile[(c + 1) * kPrepPitch + (r - k0)] = cvt_from_float<T>(v.y);
+            }
+        }
+    }
+    __syncthreads();
+    // transposed store: channel c -> 64 consecutive keys (128 bytes)
+    for (int c = warp; c < 256; c += 8) {
+#pragma unroll
+        for (int br = 0; br < 2; ++br) {
+            const T* tile = br == 0 ? tile_c : tile_r;
+            T* vt = reinterpret_cast<T*>(br == 0 ? a.vt_cls : a.vt_reg) + ((int64_t)b * 256 + c) * lay.nk_pitch + k0;
+            *reinterpret_cast<uint32_t*>(vt + 2 * lane) = *reinterpret_cast<const uint32_t*>(tile + c * kPrepPitch + 2 * lane);
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------
+// shared pieces of the two tensor-core kernels
+// -------------------------------------------------------------------------------------------------------
+struct ClipInfo {
+    int s0, n_clip, n_loc, lbase, q0;
+};
+__device__ __forceinline__ ClipInfo clip_info(const tscd_attn_layout& lay, int b, int qtile) {
+    ClipInfo c;
+    c.s0 = lay.row_off[b * lay.F];
+    c.n_clip = min(lay.row_off[(b + 1) * lay.F] - c.s0, lay.nk_pitch);
+    c.n_loc = lay.self_attn ? c.n_clip : (lay.row_off[b * lay.F + lay.L] - c.s0);
+    c.lbase = lay.lrow_off[b * lay.L];
+    c.q0 = qtile * 128;
+    return c;
+}
+
+// 16-byte chunk `chunk` (8 x 16-bit) of row `row` inside a [rows x 64] K-major tile with 128-byte swizzle
+__device__ __forceinline__ uint32_t sw128_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    if (BF16) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    } else {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+}
+
+struct PvTmaps {
+    CUtensorMap qc, kc, qr, kr, vtc, vtr;
+};
+
+// -------------------------------------------------------------------------------------------------------
+// attn_pv: row max (pass A), exp/sum + P@V (pass B)
+// -------------------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void __launch_bounds__(kAttnThreads, 1) attn_pv_kernel(const __grid_constant__ PvTmaps tm, const tscd_attn_pv_args a) {
+    using namespace tc;
+    const tscd_attn_layout& lay = a.lay;
+    const int b = blockIdx.y;
+    const ClipInfo ci = clip_info(lay, b, blockIdx.x);
+    if (ci.q0 >= ci.n_loc) return;
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* sQc = smem;                 // 16 KB
+    unsigned char* sQr = smem + 16384;         // 16 KB
+    unsigned char* sK = smem + 32768;          // 64 KB (pass A: Kc 32K | Kr 32K; pass B: Kc 16K | Kr 16K | Vtc 16K | Vtr 16K)
+    unsigned char* sP = smem + 98304;          // 64 KB (Pc 32K | Pr 32K)
+    __shared__ __align__(8) uint64_t bar_tma, bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float s_stats[128][17];
+    __shared__ int s_kf[256];
+
+    const int warp = threadIdx.x >> 5;
+    const bool ctrl = (threadIdx.x == 128);
+    if (ctrl) {
+        tma_prefetch_desc(&tm.qc); tma_prefetch_desc(&tm.kc); tma_prefetch_desc(&tm.qr); tma_prefetch_desc(&tm.kr);
+        tma_prefetch_desc(&tm.vtc); tma_prefetch_desc(&tm.vtr);
+        mbar_init(&bar_tma, 1);
+        mbar_init(&bar_mma, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc<512>(&tmem_base_s);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    uint32_t ph_tma = 0, ph_mma = 0;
+
+    const int row = threadIdx.x;  // query row within the tile (epilogue threads only)
+    const bool is_epi = warp < 4;
+    const int q = ci.q0 + row;
+    const bool q_ok = is_epi && q < ci.n_loc;
+    int qf = -2;
+    if (q_ok && !lay.self_attn) qf = a.row_frame[ci.s0 + q];
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    const int L = lay.L;
+    const bool self_attn = lay.self_attn != 0;
+
+    const uint32_t idesc256 = make_idesc_f16(BF16, 128, 256);
+    const uint32_t idesc128 = make_idesc_f16(BF16, 128, 128);
+    const uint32_t idesc64 = make_idesc_f16(BF16, 128, 64);
+
+    // ================= pass A: row maxima =================
+    for (int h = 0; h < 4; ++h) {
+        float mc = -INFINITY, mr = -INFINITY;
+        for (int g = 0; g * 256 < ci.n_clip; ++g) {
+            const int kbase = g * 256;
+            if (ctrl) {
+                const uint32_t bytes = (g == 0 ? 2 * 16384 : 0) + 4 * 16384;
+                mbar_expect_tx(&bar_tma, bytes);
+                if (g == 0) {
+                    tma_load_2d(sQc, &tm.qc, &bar_tma, h * 64, ci.s0 + ci.q0);
+                    tma_load_2d(sQr, &tm.qr, &bar_tma, h * 64, ci.s0 + ci.q0);
+                }
+                tma_load_2d(sK, &tm.kc, &bar_tma, h * 64, ci.s0 + kbase);
+                tma_load_2d(sK + 16384, &tm.kc, &bar_tma, h * 64, ci.s0 + kbase + 128);
+                tma_load_2d(sK + 32768, &tm.kr, &bar_tma, h * 64, ci.s0 + kbase);
+                tma_load_2d(sK + 49152, &tm.kr, &bar_tma, h * 64, ci.s0 + kbase + 128);
+            }
+            if (is_epi) {
+                for (int j = row; j < 256; j += 128) {
+                    const int k = kbase + j;
+                    s_kf[j] = (k < ci.n_clip) ? (self_attn ? 0 : a.row_frame[ci.s0 + k]) : -1;
+                }
+            }
+            mbar_wait(&bar_tma, ph_tma); ph_tma ^= 1;
+            if (ctrl) {
+                tc_fence_after();
+                const uint64_t dqc = make_smem_desc_sw128(smem_u32(sQc)), dqr = make_smem_desc_sw128(smem_u32(sQr));
+                const uint64_t dkc = make_smem_desc_sw128(smem_u32(sK)), dkr = make_smem_desc_sw128(smem_u32(sK + 32768));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(tmem + 0, dqc + 2 * k, dkc + 2 * k, idesc256, k ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(tmem + 256, dqr + 2 * k, dkr + 2 * k, idesc256, k ? 1u : 0u);
+                umma_commit(&bar_mma);
+            }
+            __syncthreads();  // s_kf visible
+            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
+            tc_fence_after();
+            if (is_epi) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < 256; c0 += 32) {
+                    uint32_t rc[32], rr[32];
+                    tmem_ld_32x32(lane_base + c0, rc);
+                    tmem_ld_32x32(lane_base + 256 + c0, rr);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int kf = s_kf[c0 + j];
+                        const bool ok = kf >= 0 && (self_attn || kf >= L || kf == qf);
+                        if (ok) { mc = fmaxf(mc, __uint_as_float(rc[j])); mr = fmaxf(mr, __uint_as_float(rr[j])); }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncthreads();
+        }
+        if (is_epi) { s_stats[row][h] = mc; s_stats[row][4 + h] = mr; }
+    }
+
+    // ================= pass B: exp / row sums / P @ V =================
+    unsigned char* sKc = sK;
+    unsigned char* sKr = sK + 16384;
+    unsigned char* sVtc = sK + 32768;
+    unsigned char* sVtr = sK + 49152;
+    unsigned char* sPc = sP;
+    unsigned char* sPr = sP + 32768;
+    for (int h = 0; h < 4; ++h) {
+        const float mc = is_epi ? s_stats[row][h] * kLog2e : 0.f;
+        const float mr = is_epi ? s_stats[row][4 + h] * kLog2e : 0.f;
+        float lc = 0.f, lr = 0.f;
+        for (int g = 0; g * 128 < ci.n_clip; ++g) {
+            const int kbase = g * 128;
+            if (ctrl) {
+                const uint32_t bytes = (g == 0 ? 2 * 16384 : 0) + 2 * 16384 + 2 * 8192 + (a.need_reg ? 2 * 8192 : 0);
+                mbar_expect_tx(&bar_tma, bytes);
+                if (g == 0) {
+                    tma_load_2d(sQc, &tm.qc, &bar_tma, h * 64, ci.s0 + ci.q0);
+                    tma_load_2d(sQr, &tm.qr, &bar_tma, h * 64, ci.s0 + ci.q0);
+                }
+                tma_load_2d(sKc, &tm.kc, &bar_tma, h * 64, ci.s0 + kbase);
+                tma_load_2d(sKr, &tm.kr, &bar_tma, h * 64, ci.s0 + kbase);
+                tma_load_2d(sVtc, &tm.vtc, &bar_tma, kbase, b * 256 + h * 64);
+                tma_load_2d(sVtc + 8192, &tm.vtc, &bar_tma, kbase + 64, b * 256 + h * 64);
+                if (a.need_reg) {
+                    tma_load_2d(sVtr, &tm.vtr, &bar_tma, kbase, b * 256 + h * 64);
+                    tma_load_2d(sVtr + 8192, &tm.vtr, &bar_tma, kbase + 64, b * 256 + h * 64);
+                }
+            }
+            if (is_epi) {
+                const int k = kbase + row;
+                s_kf[row] = (k < ci.n_clip) ? (self_attn ? 0 : a.row_frame[ci.s0 + k]) : -1;
+            }
+            mbar_wait(&bar_tma, ph_tma); ph_tma ^= 1;
+            if (ctrl) {
+                tc_fence_after();
+                const uint64_t dqc = make_smem_desc_sw128(smem_u32(sQc)), dqr = make_smem_desc_sw128(smem_u32(sQr));
+                const uint64_t dkc = make_smem_desc_sw128(smem_u32(sKc)), dkr = make_smem_desc_sw128(smem_u32(sKr));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(tmem + 0, dqc + 2 * k, dkc + 2 * k, idesc128, k ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(tmem + 128, dqr + 2 * k, dkr + 2 * k, idesc128, k ? 1u : 0u);
+                umma_commit(&bar_mma);
+            }
+            __syncthreads();
+            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
+            tc_fence_after();
+            if (is_epi) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    uint32_t rc[32], rr[32];
+                    tmem_ld_32x32(lane_base + c0, rc);
+                    tmem_ld_32x32(lane_base + 128 + c0, rr);
+                    tmem_ld_wait();
+                    float ec[32], er[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int kf = s_kf[c0 + j];
+                        const bool ok = kf >= 0 && (self_attn || kf >= L || kf == qf);
+                        ec[j] = ok ? exp2f(fmaf(__uint_as_float(rc[j]), kLog2e, -mc)) : 0.f;
+                        er[j] = ok ? exp2f(fmaf(__uint_as_float(rr[j]), kLog2e, -mr)) : 0.f;
+                        lc += ec[j];
+                        lr += er[j];
+                    }
+                    const int atom = c0 >> 6;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const int chunk = ((c0 & 63) >> 3) + cc;
+                        const uint32_t off = (uint32_t)atom * 16384u + sw128_off(row, chunk);
+                        *reinterpret_cast<uint4*>(sPc + off) =
+                            make_uint4(pack2<BF16>(ec[cc * 8], ec[cc * 8 + 1]), pack2<BF16>(ec[cc * 8 + 2], ec[cc * 8 + 3]),
+                                       pack2<BF16>(ec[cc * 8 + 4], ec[cc * 8 + 5]), pack2<BF16>(ec[cc * 8 + 6], ec[cc * 8 + 7]));
+                        *reinterpret_cast<uint4*>(sPr + off) =
+                            make_uint4(pack2<BF16>(er[cc * 8], er[cc * 8 + 1]), pack2<BF16>(er[cc * 8 + 2], er[cc * 8 + 3]),
+                                       pack2<BF16>(er[cc * 8 + 4], er[cc * 8 + 5]), pack2<BF16>(er[cc * 8 + 6], er[cc * 8 + 7]));
+                    }
+                }
+                fence_proxy_async();
+            }
+            tc_fence_before();
+            __syncthreads();
+            if (ctrl) {
+                tc_fence_after();
+                const uint32_t first = (g == 0) ? 0u : 1u;
+#pragma unroll
+                for (int at = 0; at < 2; ++at) {
+                    const uint64_t dpc = make_smem_desc_sw128(smem_u32(sPc + at * 16384));
+                    const uint64_t dpr = make_smem_desc_sw128(smem_u32(sPr + at * 16384));
+                    const uint64_t dvc = make_smem_desc_sw128(smem_u32(sVtc + at * 8192));
+                    const uint64_t dvr = make_smem_desc_sw128(smem_u32(sVtr + at * 8192));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t acc = (at | k) ? 1u : first;
+                        umma_f16(tmem + 256, dpc + 2 * k, dvc + 2 * k, idesc64, acc);   // O_cc
+                        umma_f16(tmem + 320, dpr + 2 * k, dvc + 2 * k, idesc64, acc);   // O_rc
+                        if (a.need_reg) {
+                            umma_f16(tmem + 384, dpc + 2 * k, dvr + 2 * k, idesc64, acc);  // O_cr
+                            umma_f16(tmem + 448, dpr + 2 * k, dvr + 2 * k, idesc64, acc);  // O_rr
+                        }
+                    }
+                }
+                umma_commit(&bar_mma);
+            }
+            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
+            tc_fence_after();
+        }
+        // head epilogue: x = (O_c / l_c + O_r / l_r) / 2
+        if (is_epi) {
+            s_stats[row][8 + h] = lc;
+            s_stats[row][12 + h] = lr;
+            const float ic = 0.5f / lc, ir = 0.5f / lr;
+            for (int br = 0; br < (a.need_reg ? 2 : 1); ++br) {
+                uint16_t* dst = reinterpret_cast<uint16_t*>(br == 0 ? a.x_cls : a.x_reg);
+#pragma unroll 1
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t oc[32], orr[32];
+                    tmem_ld_32x32(lane_base + 256 + br * 128 + c0, oc);
+                    tmem_ld_32x32(lane_base + 320 + br * 128 + c0, orr);
+                    tmem_ld_wait();
+                    if (q_ok) {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            pk[j] = pack2<BF16>(__uint_as_float(oc[2 * j]) * ic + __uint_as_float(orr[2 * j]) * ir,
+                                                __uint_as_float(oc[2 * j + 1]) * ic + __uint_as_float(orr[2 * j + 1]) * ir);
+                        uint4* o = reinterpret_cast<uint4*>(dst + (int64_t)(ci.lbase + q) * a.ld_x + h * 64 + c0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    if (q_ok) {
+        float* st = a.stats + (int64_t)(ci.lbase + q) * 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) st[j] = s_stats[row][j];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------
+// attn_round2: masks from head-mean raw-v cosine, exp(head-mean attention), renormalise, @ V
+// -------------------------------------------------------------------------------------------------------
+struct R2Tmaps {
+    CUtensorMap q128c, q128r, k64c, k64r, vn128c, vn128r, vn64c, vn64r, vt;
+};
+
+template <bool BF16>
+__global__ void __launch_bounds__(kAttnThreads, 1) attn_round2_kernel(const __grid_constant__ R2Tmaps tm,
+                                                                       const tscd_attn_round2_args a) {
+    using namespace tc;
+    const tscd_attn_layout& lay = a.lay;
+    const int b = blockIdx.y;
+    const ClipInfo ci = clip_info(lay, b, blockIdx.x);
+    if (ci.q0 >= ci.n_loc) return;
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* sA = smem;                  // 64 KB: Vn(query) 4 atoms x 16K   | S phase: Qc 16K, Qr 16K, Kc 8K, Kr 8K
+    unsigned char* sB = smem + 65536;          // 32 KB: Vn(keys) 4 atoms x 8K
+    unsigned char* sW = smem + 98304;          // 16 KB: weights [128 x 64]
+    unsigned char* sVt = smem + 114688;        // 32 KB: V^T tile [256 x 64 keys] (4 boxes x 8K)
+    __shared__ __align__(8) uint64_t bar_tma, bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int s_kf[64];
+
+    const int warp = threadIdx.x >> 5;
+    const bool ctrl = (threadIdx.x == 128);
+    if (ctrl) {
+        tma_prefetch_desc(&tm.q128c); tma_prefetch_desc(&tm.q128r); tma_prefetch_desc(&tm.k64c); tma_prefetch_desc(&tm.k64r);
+        tma_prefetch_desc(&tm.vn128c); tma_prefetch_desc(&tm.vn128r); tma_prefetch_desc(&tm.vn64c); tma_prefetch_desc(&tm.vn64r);
+        tma_prefetch_desc(&tm.vt);
+        mbar_init(&bar_tma, 1);
+        mbar_init(&bar_mma, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc<512>(&tmem_base_s);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    uint32_t ph_tma = 0, ph_mma = 0;
+
+    const int row = threadIdx.x;
+    const bool is_epi = warp < 4;
+    const int q = ci.q0 + row;
+    const bool q_ok = is_epi && q < ci.n_loc;
+    int qf = -2;
+    if (q_ok && !lay.self_attn) qf = a.row_frame[ci.s0 + q];
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    const int L = lay.L;
+    const bool self_attn = lay.self_attn != 0;
+    const bool use_obj = a.use_obj_mask != 0;
+
+    float mc[4], mr[4], ilc[4], ilr[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) { mc[h] = mr[h] = 0.f; ilc[h] = ilr[h] = 0.f; }
+    if (q_ok) {
+        const float* st = a.stats + (int64_t)(ci.lbase + q) * 16;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            mc[h] = st[h] * kLog2e; mr[h] = st[4 + h] * kLog2e;
+            ilc[h] = 0.5f / st[8 + h]; ilr[h] = 0.5f / st[12 + h];
+        }
+    }
+    const uint32_t idesc64 = make_idesc_f16(BF16, 128, 64);
+    const uint32_t idesc256 = make_idesc_f16(BF16, 128, 256);
+    float den = 0.f;
+
+    for (int kt = 0; kt * 64 < ci.n_clip; ++kt) {
+        const int kbase = kt * 64;
+        // ---- raw-v cosine (head mean = one K=256 product / 4) ----
+        for (int br = 0; br < (use_obj ? 2 : 1); ++br) {
+            if (ctrl) {
+                mbar_expect_tx(&bar_tma, 4 * 16384 + 4 * 8192);
+#pragma unroll
+                for (int at = 0; at < 4; ++at) {
+                    tma_load_2d(sA + at * 16384, br == 0 ? &tm.vn128c : &tm.vn128r, &bar_tma, at * 64, ci.s0 + ci.q0);
+                    tma_load_2d(sB + at * 8192, br == 0 ? &tm.vn64c : &tm.vn64r, &bar_tma, at * 64, ci.s0 + kbase);
+                }
+            }
+            mbar_wait(&bar_tma, ph_tma); ph_tma ^= 1;
+            if (ctrl) {
+                tc_fence_after();
+#pragma unroll
+                for (int at = 0; at < 4; ++at) {
+                    const uint64_t da = make_smem_desc_sw128(smem_u32(sA + at * 16384));
+                    const uint64_t db = make_smem_desc_sw128(smem_u32(sB + at * 8192));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem + 384 + br * 64, da + 2 * k, db + 2 * k, idesc64, (at | k) ? 1u : 0u);
+                }
+                umma_commit(&bar_mma);
+            }
+            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
+            tc_fence_after();
+        }
+        if (is_epi && row < 64) {
+            const int k = kbase + row;
+            s_kf[row] = (k < ci.n_clip) ? (self_attn ? 0 : a.row_frame[ci.s0 + k]) : -1;
+        }
+        // ---- head-mean attention ----
+        float as[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) as[j] = 0.f;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            if (ctrl) {
+                mbar_expect_tx(&bar_tma, 2 * 16384 + 2 * 8192);
+                tma_load_2d(sA, &tm.q128c, &bar_tma, h * 64, ci.s0 + ci.q0);
+                tma_load_2d(sA + 16384, &tm.q128r, &bar_tma, h * 64, ci.s0 + ci.q0);
+                tma_load_2d(sA + 32768, &tm.k64c, &bar_tma, h * 64, ci.s0 + kbase);
+                tma_load_2d(sA + 40960, &tm.k64r, &bar_tma, h * 64, ci.s0 + kbase);
+            }
+            mbar_wait(&bar_tma, ph_tma); ph_tma ^= 1;
+            if (ctrl) {
+                tc_fence_after();
+                const uint64_t dqc = make_smem_desc_sw128(smem_u32(sA)), dqr = make_smem_desc_sw128(smem_u32(sA + 16384));
+                const uint64_t dkc = make_smem_desc_sw128(smem_u32(sA + 32768)), dkr = make_smem_desc_sw128(smem_u32(sA + 40960));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(tmem + 256, dqc + 2 * k, dkc + 2 * k, idesc64, k ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(tmem + 320, dqr + 2 * k, dkr + 2 * k, idesc64, k ? 1u : 0u);
+                umma_commit(&bar_mma);
+            }
+            __syncthreads();  // s_kf visible (first head) / keeps the phases aligned
+            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
+            tc_fence_after();
+            if (is_epi) {
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t rc[32], rr[32];
+                    tmem_ld_32x32(lane_base + 256 + c0, rc);
+                    tmem_ld_32x32(lane_base + 320 + c0, rr);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float ec = exp2f(fmaf(__uint_as_float(rc[j]), kLog2e, -mc[h]));
+                        const float er = exp2f(fmaf(__uint_as_float(rr[j]), kLog2e, -mr[h]));
+                        as[c0 + j] += ec * ilc[h] + er * ilr[h];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncthreads();
+        }
+        // ---- weights ----
+        if (is_epi) {
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t rc[32], rr[32];
+                tmem_ld_32x32(lane_base + 384 + c0, rc);
+                if (use_obj) tmem_ld_32x32(lane_base + 448 + c0, rr);
+                tmem_ld_wait();
+                float w[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int kf = s_kf[c0 + j];
+                    bool ok = kf >= 0 && (self_attn || kf >= L || kf == qf);
+                    ok = ok && (__uint_as_float(rc[j]) * 0.25f > a.sim_thresh);
+                    if (use_obj) ok = ok && (__uint_as_float(rr[j]) * 0.25f > a.conf_sim_thresh);
+                    w[j] = ok ? exp2f(as[c0 + j] * (0.25f * kLog2e)) : 0.f;
+                    den += w[j];
+                }
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int chunk = (c0 >> 3) + cc;
+                    *reinterpret_cast<uint4*>(sW + sw128_off(row, chunk)) =
+                        make_uint4(pack2<BF16>(w[cc * 8], w[cc * 8 + 1]), pack2<BF16>(w[cc * 8 + 2], w[cc * 8 + 3]),
+                                   pack2<BF16>(w[cc * 8 + 4], w[cc * 8 + 5]), pack2<BF16>(w[cc * 8 + 6], w[cc * 8 + 7]));
+                }
+            }
+            fence_proxy_async();
+        }
+        if (ctrl) {
+            mbar_expect_tx(&bar_tma, 4 * 8192);
+#pragma unroll
+            for (int at = 0; at < 4; ++at) tma_load_2d(sVt + at * 8192, &tm.vt, &bar_tma, kbase, b * 256 + at * 64);
+        }
+        tc_fence_before();
+        __syncthreads();
+        mbar_wait(&bar_tma, ph_tma); ph_tma ^= 1;
+        if (ctrl) {
+            tc_fence_after();
+            const uint64_t dw = make_smem_desc_sw128(smem_u32(sW));
+            const uint64_t dv = make_smem_desc_sw128(smem_u32(sVt));   // 256 rows x 64 keys: four 8 KB boxes are contiguous
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tmem + 0, dw + 2 * k, dv + 2 * k, idesc256, (kt | k) ? 1u : 0u);
+            umma_commit(&bar_mma);
+        }
+        mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
+        tc_fence_after();
+    }
+    // ---- U / den ----
+    if (is_epi) {
+        const float inv = 1.f / den;
+        uint16_t* dst = reinterpret_cast<uint16_t*>(a.out);
+#pragma unroll 1
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+            uint32_t u[32];
+            tmem_ld_32x32(lane_base + c0, u);
+            tmem_ld_wait();
+            if (q_ok) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) pk[j] = pack2<BF16>(__uint_as_float(u[2 * j]) * inv, __uint_as_float(u[2 * j + 1]) * inv);
+                uint4* o = reinterpret_cast<uint4*>(dst + (int64_t)(ci.lbase + q) * a.ld_out + c0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem);
+    }
+}
+
+static bool layout_ok(const tscd_attn_layout& l) {
+    return l.B > 0 && l.F > 0 && l.L > 0 && l.L <= l.F && l.row_cap > 0 && l.nk_pitch > 0 && (l.nk_pitch % 128) == 0 &&
+           l.row_off && l.lrow_off && (l.dtype == TSCD_F16 || l.dtype == TSCD_BF16);
+}
+
+}  // namespace tscd
+
+extern "C" int tscd_attn_prep(const tscd_attn_prep_args* a, void* stream) {
+    using namespace tscd;
+    if (!a || !layout_ok(a->lay)) return TSCD_ERR_INVALID_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    dim3 grid(a->lay.nk_pitch / 64, a->lay.B);
+    const size_t smem = 2 * 256 * kPrepPitch * 2;
+    if (a->lay.dtype == TSCD_F16) {
+        if (cudaFuncSetAttribute(attn_prep_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
+        attn_prep_kernel<__half><<<grid, 256, smem, st>>>(*a);
+    } else {
+        if (cudaFuncSetAttribute(attn_prep_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
+        attn_prep_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(*a);
+    }
+    TSCD_CUDA_CHECK_LAUNCH();
+    return TSCD_OK;
+}
+
+extern "C" int tscd_attn_pv(const tscd_attn_pv_args* a, void* stream) {
+    using namespace tscd;
+    if (!a || !layout_ok(a->lay)) return TSCD_ERR_INVALID_ARG;
+    const tscd_attn_layout& l = a->lay;
+    const int bf = l.dtype == TSCD_BF16;
+    PvTmaps tm;
+    int rc = 0;
+    rc |= make_tmap_kmajor(&tm.qc, a->qn_cls, bf, l.row_cap, 256, 256, 128);
+    rc |= make_tmap_kmajor(&tm.kc, a->kn_cls, bf, l.row_cap, 256, 256, 128);
+    rc |= make_tmap_kmajor(&tm.qr, a->qn_reg, bf, l.row_cap, 256, 256, 128);
+    rc |= make_tmap_kmajor(&tm.kr, a->kn_reg, bf, l.row_cap, 256, 256, 128);
+    rc |= make_tmap_kmajor(&tm.vtc, a->vt_cls, bf, (int64_t)l.B * 256, l.nk_pitch, l.nk_pitch, 64);
+    rc |= make_tmap_kmajor(&tm.vtr, a->vt_reg, bf, (int64_t)l.B * 256, l.nk_pitch, l.nk_pitch, 64);
+    if (rc) return TSCD_ERR_CUDA;
+    const size_t smem = 160 * 1024 + 1024;
+    const int max_q = l.self_attn ? l.nk_pitch : l.nk_pitch;  // query tiles are bounded by the clip size
+    dim3 grid((max_q + 127) / 128, l.B);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (bf) {
+        if (cudaFuncSetAttribute(attn_pv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
+        attn_pv_kernel<true><<<grid, kAttnThreads, smem, st>>>(tm, *a);
+    } else {
+        if (cudaFuncSetAttribute(attn_pv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
+        attn_pv_kernel<false><<<grid, kAttnThreads, smem, st>>>(tm, *a);
+    }
+    TSCD_CUDA_CHECK_LAUNCH();
+    return TSCD_OK;
+}
+
+extern "C" int tscd_attn_round2(const tscd_attn_round2_args* a, void* stream) {
+    using namespace tscd;
+    if (!a || !layout_ok(a->lay)) return TSCD_ERR_INVALID_ARG;
+    const tscd_attn_layout& l = a->lay;
+    const int bf = l.dtype == TSCD_BF16;
+    R2Tmaps tm;
+    int rc = 0;
+    rc |= make_tmap_kmajor(&tm.q128c, a->qn_cls, bf, l.row_cap, 256, 256, 128);
+    rc |= make_tmap_kmajor(&tm.q128r, a->qn_reg, bf, l.row_cap, 256, 256, 128);
+    rc |= make_tmap_kmajor(&tm.k64c, a->kn_cls, bf, l.row_cap, 256, 256, 64);
+    rc |= make_tmap_kmajor(&tm.k64r, a->kn_reg, bf, l.row_cap, 256, 256, 64);
+    rc |= make_tmap_kmajor(&tm.vn128c, a->vn_cls, bf, l.row_cap, 256, 256, 128);
+    rc |= make_tmap_kmajor(&tm.vn128r, a->vn_reg, bf, l.row_cap, 256, 256, 128);
+    rc |= make_tmap_kmajor(&tm.vn64c, a->vn_cls, bf, l.row_cap, 256, 256, 64);
+    rc |= make_tmap_kmajor(&tm.vn64r, a->vn_reg, bf, l.row_cap, 256, 256, 64);
+    rc |= make_tmap_kmajor(&tm.vt, a->vt, bf, (int64_t)l.B * 256, l.nk_pitch, l.nk_pitch, 64);
+    if (rc) return TSCD_ERR_CUDA;
+    const size_t smem = 144 * 1024 + 1024;
+    dim3 grid((l.nk_pitch + 127) / 128, l.B);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (bf) {
+        if (cudaFuncSetAttribute(attn_round2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
+        attn_round2_kernel<true><<<grid, kAttnThreads, smem, st>>>(tm, *a);
+    } else {
+        if (cudaFuncSetAttribute(attn_round2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
+        attn_round2_kernel<false><<<grid, kAttnThreads, smem, st>>>(tm, *a);
+    }
+    TSCD_CUDA_CHECK_LAUNCH();
+    return TSCD_OK;
+}

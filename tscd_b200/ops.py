@@ -196,3 +196,69 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         assert bias.dtype == torch.float32 and bias.is_contiguous()
     L.check(L.lib().tscd_linear(C.byref(a), _stream()), "tscd_linear")
     return out16, out32
+
+
+# ----------------------------------------------------------------------------------------------- K4 attention
+@dataclass
+class AttnLayoutT:
+    """Batch layout shared by the attention kernels (device offsets, no host sync)."""
+    B: int
+    F: int
+    L: int
+    row_off: torch.Tensor      # int32 [B*F+1]
+    lrow_off: torch.Tensor     # int32 [B*L+1]
+    row_cap: int
+    loc_cap: int
+    nk_pitch: int
+    dtype: torch.dtype
+    self_attn: bool = False
+
+    def to_c(self) -> L.AttnLayout:
+        a = L.AttnLayout()
+        a.B, a.F, a.L, a.self_attn, a.dtype = self.B, self.F, self.L, int(self.self_attn), _DT[self.dtype]
+        a.row_cap, a.nk_pitch = self.row_cap, self.nk_pitch
+        a.row_off, a.lrow_off = _p(self.row_off), _p(self.lrow_off)
+        return a
+
+
+def attn_prep(lay: AttnLayoutT, qkv_cls, qkv_reg, key_score, xori_cls=None, xori_reg=None, scale=25.0, bufs=None):
+    """Normalise / scale / transpose.  qkv_* are [row_cap, >=768] views (q|k|v).  Returns dict of operand buffers."""
+    dev, dt = qkv_cls.device, lay.dtype
+    if bufs is None:
+        bufs = {}
+        for n in ("qn_cls", "kn_cls", "vn_cls", "qn_reg", "kn_reg", "vn_reg"):
+            bufs[n] = torch.zeros(lay.row_cap, 256, dtype=dt, device=dev)
+        for n in ("vt_cls", "vt_reg"):
+            bufs[n] = torch.zeros(lay.B * 256, lay.nk_pitch, dtype=dt, device=dev)
+        bufs["row_frame"] = torch.zeros(lay.row_cap, dtype=torch.int32, device=dev)
+    a = L.AttnPrepArgs()
+    a.lay, a.scale = lay.to_c(), scale
+    assert qkv_cls.stride(1) == 1 and qkv_cls.stride(0) == qkv_reg.stride(0)
+    a.qkv_cls, a.qkv_reg, a.ld_qkv, a.key_score = _p(qkv_cls), _p(qkv_reg), qkv_cls.stride(0), _p(key_score)
+    for n in ("qn_cls", "kn_cls", "vn_cls", "qn_reg", "kn_reg", "vn_reg", "vt_cls", "vt_reg", "row_frame"):
+        setattr(a, n, _p(bufs[n]))
+    a.xori_cls, a.xori_reg = _p(xori_cls), _p(xori_reg)
+    a.ld_xori = 0 if xori_cls is None else xori_cls.stride(0)
+    L.check(L.lib().tscd_attn_prep(C.byref(a), _stream()), "tscd_attn_prep")
+    return bufs
+
+
+def attn_pv(lay: AttnLayoutT, bufs, x_cls, x_reg, stats, need_reg=True):
+    a = L.AttnPvArgs()
+    a.lay = lay.to_c()
+    for n in ("qn_cls", "kn_cls", "qn_reg", "kn_reg", "vt_cls", "vt_reg", "row_frame"):
+        setattr(a, n, _p(bufs[n]))
+    a.need_reg = int(need_reg)
+    a.x_cls, a.x_reg, a.ld_x, a.stats = _p(x_cls), _p(x_reg), x_cls.stride(0), _p(stats)
+    L.check(L.lib().tscd_attn_pv(C.byref(a), _stream()), "tscd_attn_pv")
+
+
+def attn_round2(lay: AttnLayoutT, bufs, vt, stats, out, use_obj_mask, sim_thresh=0.75, conf_sim_thresh=0.99):
+    a = L.AttnRound2Args()
+    a.lay = lay.to_c()
+    for n in ("qn_cls", "kn_cls", "qn_reg", "kn_reg", "vn_cls", "vn_reg", "row_frame"):
+        setattr(a, n, _p(bufs[n]))
+    a.vt, a.stats, a.use_obj_mask = _p(vt), _p(stats), int(use_obj_mask)
+    a.sim_thresh, a.conf_sim_thresh = sim_thresh, conf_sim_thresh
+    a.out, a.ld_out = _p(out), out.stride(0)
+    L.check(L.lib().tscd_attn_round2(C.byref(a), _stream()), "tscd_attn_round2")
