@@ -236,6 +236,143 @@ typedef struct {
 } tscd_attn_round2_args;
 int tscd_attn_round2(const tscd_attn_round2_args* args, void* stream);
 
+/* ---- K5: CAFM (AwarePositionRegMatcher) -------------------------------------------------------------------
+ * Replaces AwarePositionRegMatcher.forward (tscd_matching.py:722-888) with its ReferringCrossAttentionLayer
+ * (:566-589), SEModule (:278-283), PositionMHAttention (:31-60), double_match_embds (:912-937) and the scipy
+ * Hungarian solve (:935) -- here a device-side shortest-augmenting-path LSAP in fp64 with SciPy's tie rules.
+ * The key / value projections (k_reg, v_reg) and the time-embedding Linear run as tscd_linear GEMMs before.
+ *   tscd_cafm_prep   gathers the local rows' raw reg / edge features, builds the key-side input
+ *                    SE(feat, edge) + time_embedding[frame], and the (|x| + 1e-6) norms used by the matching cost;
+ *   tscd_cafm_chain  one CTA per clip walks its local frames in order: cost -> LSAP -> permutation ->
+ *                    query = W_q (SE(prev_out, prev_edge) + prev_time) -> 8-head cosine attention over the
+ *                    CURRENT frame only (no inter-frame mixing) -> LayerNorm(identity + attn) -> decoder_norm.
+ * State (last frame's outputs / embeddings, tscd_matching.py:708-715) lives in caller-owned buffers so that
+ * consecutive clips of one video can be chained with resume=1. */
+typedef struct {
+    int32_t B, F, L, D;          /* D = 256; embed dim of the matching features = 4*D */
+    int32_t bank_dtype;          /* dtype of bank_reg / bank_edge and of the 16-bit outputs */
+    const int32_t* row_off;      /* [B*F+1] */
+    const int32_t* lrow_off;     /* [B*L+1] */
+    const void* bank_reg;        /* [row_cap, D] */
+    const void* bank_edge;
+    const float* time_emb;       /* [B*L, D] output of absolute_position_embedding */
+    const float* se_w1;          /* [32,2]  CA.fc.0.weight */
+    const float* se_w2;          /* [2,32]  CA.fc.2.weight */
+    const float* emb_reg;        /* [loc_cap, 4D] agg_iou reg output (matching only) */
+    const float* emb_cls;        /* [loc_cap, 4D] agg_iou cls output (matching only) */
+    float* feat;                 /* out [loc_cap, D] raw reg features of the local rows */
+    float* edge;                 /* out [loc_cap, D] */
+    void* feat16;                /* out [loc_cap, D] 16-bit copy (value projection input) */
+    void* kin16;                 /* out [loc_cap, D] 16-bit key-side input SE(feat,edge)+time */
+    float* kin;                  /* out [loc_cap, D] fp32 copy (first-frame query input) */
+    float* norm_reg;             /* out [loc_cap] |emb_reg| + 1e-6 */
+    float* norm_cls;             /* out [loc_cap] */
+} tscd_cafm_prep_args;
+int tscd_cafm_prep(const tscd_cafm_prep_args* args, void* stream);
+
+typedef struct {
+    int32_t B, F, L, D, kmax;    /* kmax: capacity (rows per frame) of the state / scratch buffers, <= 512 */
+    int32_t out_dtype;
+    const int32_t* row_off;
+    const int32_t* lrow_off;
+    const int32_t* resume;       /* [B] 1: continue from the state buffers (tscd_matching.py:779) */
+    const float* feat;           /* [loc_cap, D] */
+    const float* edge;
+    const float* kin;            /* [loc_cap, D] */
+    const float* kproj;          /* [loc_cap, D] k_reg(kin)  */
+    const float* vproj;          /* [loc_cap, D] v_reg(feat) */
+    const float* time_emb;       /* [B*L, D] */
+    const float* emb_reg;        /* [loc_cap, 4D] */
+    const float* emb_cls;
+    const float* norm_reg;
+    const float* norm_cls;
+    const float* wq_t;           /* [D(in), D(out)] q_reg.weight transposed, fp32 */
+    const float* se_w1;
+    const float* se_w2;
+    const float* ln_w;           /* layer norm of the cross-attention layer */
+    const float* ln_b;
+    const float* dec_w;          /* decoder_norm */
+    const float* dec_b;
+    /* state, caller-owned, persists across calls */
+    int32_t* st_n;               /* [B] rows held (0 = no memory) */
+    float* st_out;               /* [B,kmax,D] */
+    float* st_edge;              /* [B,kmax,D] */
+    float* st_reg;               /* [B,kmax,4D] */
+    float* st_cls;               /* [B,kmax,4D] */
+    float* st_nreg;              /* [B,kmax] */
+    float* st_ncls;              /* [B,kmax] */
+    float* st_time;              /* [B,D] */
+    /* scratch */
+    float* sc_qin;               /* [B,kmax,D] */
+    float* sc_q;                 /* [B,kmax,D] */
+    float* sc_k;                 /* [B,kmax,D] */
+    float* sc_cost;              /* [B,kmax,kmax] */
+    /* outputs */
+    void* out16;                 /* [loc_cap, D] CAFM output after decoder_norm, original row order */
+    float* out32;                /* [loc_cap, D] same in fp32 (may be NULL) */
+    int32_t* perm;               /* [loc_cap] matched column of every output row (debug / tests; may be NULL) */
+    int32_t* status;
+} tscd_cafm_chain_args;
+int tscd_cafm_chain(const tscd_cafm_chain_args* args, void* stream);
+
+/* ---- TaskAligned attention + LayerNorms ---------------------------------------------------------------------
+ * tscd_frame_attention: MHAttention.forward (tscd_matching.py:159-181) for every local frame at once:
+ * per frame and head, softmax(q^ k^T) v with L2-normalised q,k (no scale), queries/keys/values all from the
+ * SAME frame.  q/k/v are fp32 GEMM outputs (projections done by tscd_linear).
+ * tscd_residual_ln2: y = LN_b(LN_a(x + r))  -- CrossAttentionLayer.forward_post's norm followed by the
+ * decoder_norm of TaskAligned (tscd_matching.py:421-433, 1133-1137). */
+typedef struct {
+    int32_t num_frames;          /* B*L local frames */
+    int32_t heads, head_dim;
+    const int32_t* lrow_off;     /* [num_frames+1] */
+    const float* q; int32_t ldq;
+    const float* k; int32_t ldk;
+    const float* v; int32_t ldv;
+    float* out; int32_t ldo;     /* [loc_cap, heads*head_dim] */
+} tscd_frame_attention_args;
+int tscd_frame_attention(const tscd_frame_attention_args* args, void* stream);
+
+typedef struct {
+    int32_t rows_cap, dim;
+    const int32_t* n_rows;       /* device row count */
+    const float* x; const float* r;
+    const float *w_a, *b_a, *w_b, *b_b;
+    int32_t out_dtype;
+    void* out16; float* out32;
+} tscd_residual_ln2_args;
+int tscd_residual_ln2(const tscd_residual_ln2_args* args, void* stream);
+
+/* ---- final per-class expansion (post_process.py:9-85) ---------------------------------------------------------
+ * tscd_final_expand builds, per local frame, the two candidate lists the reference feeds to batched_nms:
+ *   refined: one row per (proposal, class) with sigmoid(cls) >= thr and sigmoid(obj)*sigmoid(cls) >= thr, in
+ *            row-major (proposal, class) order; box = decode_reg_preds5(deltas, still box) (tscd_head.py:914-949);
+ *   still:   the unrefined rows with obj*class_conf >= thr.
+ * tscd_final_rows assembles [x1,y1,x2,y2,obj,cls_score,cls_id] rows in NMS keep order. */
+typedef struct {
+    int32_t B, F, L, num_classes, max_keep;
+    float conf_thre;             /* 0.001 */
+    float xform_clip;            /* log(736/32) */
+    const int32_t* sel_count;    /* [B*F] */
+    const float* sel_rows;       /* [B*F, max_keep, 7+C] */
+    const int32_t* lrow_off;     /* [B*L+1] */
+    const float* cls_logits; int32_t ld_cls;   /* [loc_cap, >=C] */
+    const float* obj_logits; int32_t ld_obj;   /* [loc_cap, >=1] */
+    const float* reg_deltas; int32_t ld_reg;   /* [loc_cap, >=4] */
+    /* refined candidates, capacity per frame = max_keep * num_classes */
+    float* r_box; float* r_score; int32_t* r_cls; float* r_obj; float* r_cscore; int32_t* r_count;
+    /* still-detector candidates, capacity per frame = max_keep */
+    float* o_box; float* o_score; int32_t* o_cls; float* o_obj; float* o_cscore; int32_t* o_count;
+} tscd_final_expand_args;
+int tscd_final_expand(const tscd_final_expand_args* args, void* stream);
+
+typedef struct {
+    int32_t num_frames, cand_cap, keep_cap;
+    const float* box; const float* obj; const float* cscore; const int32_t* cls;
+    const int32_t* keep; const int32_t* keep_count;
+    float* rows;                 /* [num_frames, keep_cap, 7] */
+} tscd_final_rows_args;
+int tscd_final_rows(const tscd_final_rows_args* args, void* stream);
+
 /* Library / build information (also proves the .so was loaded). */
 const char* tscd_version(void);
 int tscd_device_ok(void); /* 1 if the current device is compute capability 10.x */

@@ -22,17 +22,23 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_header():
     """ctypes mirrors must have the C layout (compile a tiny probe with gcc)."""
+    import ctypes
     import subprocess
     import tempfile
     from tscd_b200 import _lib
-    src = '#include <stdio.h>\n#include "tscd_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",' \
-          'sizeof(tscd_view),sizeof(tscd_anchors),sizeof(tscd_select_args),sizeof(tscd_nms_args),sizeof(tscd_gather_args),sizeof(tscd_linear_args));return 0;}'
+    pairs = [("tscd_view", _lib.View), ("tscd_anchors", _lib.Anchors), ("tscd_select_args", _lib.SelectArgs),
+             ("tscd_nms_args", _lib.NmsArgs), ("tscd_gather_args", _lib.GatherArgs), ("tscd_linear_args", _lib.LinearArgs),
+             ("tscd_attn_layout", _lib.AttnLayout), ("tscd_attn_prep_args", _lib.AttnPrepArgs),
+             ("tscd_attn_pv_args", _lib.AttnPvArgs), ("tscd_attn_round2_args", _lib.AttnRound2Args),
+             ("tscd_cafm_prep_args", _lib.CafmPrepArgs), ("tscd_cafm_chain_args", _lib.CafmChainArgs),
+             ("tscd_frame_attention_args", _lib.FrameAttentionArgs), ("tscd_residual_ln2_args", _lib.ResidualLn2Args),
+             ("tscd_final_expand_args", _lib.FinalExpandArgs), ("tscd_final_rows_args", _lib.FinalRowsArgs)]
+    body = "".join(f'printf("%zu\\n", sizeof({c}));' for c, _ in pairs)
+    src = '#include <stdio.h>\n#include "tscd_b200.h"\nint main(){' + body + 'return 0;}'
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "p.c")
         open(c, "w").write(src)
         exe = os.path.join(d, "p")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
-    import ctypes
-    mine = [ctypes.sizeof(x) for x in (_lib.View, _lib.Anchors, _lib.SelectArgs, _lib.NmsArgs, _lib.GatherArgs, _lib.LinearArgs)]
-    assert sizes == mine
+    assert sizes == [ctypes.sizeof(t) for _, t in pairs]

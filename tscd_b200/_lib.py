@@ -85,6 +85,43 @@ class AttnRound2Args(C.Structure):
                 ("sim_thresh", C.c_float), ("conf_sim_thresh", C.c_float), ("out", C.c_void_p), ("ld_out", C.c_int32)]
 
 
+def _fields(spec):
+    """'name:type' list -> ctypes fields; types: i=int32, f=float, p=pointer."""
+    m = {"i": C.c_int32, "f": C.c_float, "p": C.c_void_p}
+    return [(x.split(":")[0], m[x.split(":")[1]]) for x in spec.split()]
+
+
+class CafmPrepArgs(C.Structure):
+    _fields_ = _fields("B:i F:i L:i D:i bank_dtype:i row_off:p lrow_off:p bank_reg:p bank_edge:p time_emb:p se_w1:p "
+                       "se_w2:p emb_reg:p emb_cls:p feat:p edge:p feat16:p kin16:p kin:p norm_reg:p norm_cls:p")
+
+
+class CafmChainArgs(C.Structure):
+    _fields_ = _fields("B:i F:i L:i D:i kmax:i out_dtype:i row_off:p lrow_off:p resume:p feat:p edge:p kin:p kproj:p "
+                       "vproj:p time_emb:p emb_reg:p emb_cls:p norm_reg:p norm_cls:p wq_t:p se_w1:p se_w2:p ln_w:p "
+                       "ln_b:p dec_w:p dec_b:p st_n:p st_out:p st_edge:p st_reg:p st_cls:p st_nreg:p st_ncls:p "
+                       "st_time:p sc_qin:p sc_q:p sc_k:p sc_cost:p out16:p out32:p perm:p status:p")
+
+
+class FrameAttentionArgs(C.Structure):
+    _fields_ = _fields("num_frames:i heads:i head_dim:i lrow_off:p q:p ldq:i k:p ldk:i v:p ldv:i out:p ldo:i")
+
+
+class ResidualLn2Args(C.Structure):
+    _fields_ = _fields("rows_cap:i dim:i n_rows:p x:p r:p w_a:p b_a:p w_b:p b_b:p out_dtype:i out16:p out32:p")
+
+
+class FinalExpandArgs(C.Structure):
+    _fields_ = _fields("B:i F:i L:i num_classes:i max_keep:i conf_thre:f xform_clip:f sel_count:p sel_rows:p lrow_off:p "
+                       "cls_logits:p ld_cls:i obj_logits:p ld_obj:i reg_deltas:p ld_reg:i "
+                       "r_box:p r_score:p r_cls:p r_obj:p r_cscore:p r_count:p "
+                       "o_box:p o_score:p o_cls:p o_obj:p o_cscore:p o_count:p")
+
+
+class FinalRowsArgs(C.Structure):
+    _fields_ = _fields("num_frames:i cand_cap:i keep_cap:i box:p obj:p cscore:p cls:p keep:p keep_count:p rows:p")
+
+
 _lib = None
 
 # every symbol include/tscd_b200.h declares: (name, restype, argtypes)
@@ -98,6 +135,12 @@ SYMBOLS = [
     ("tscd_attn_prep", C.c_int, [C.POINTER(AttnPrepArgs), C.c_void_p]),
     ("tscd_attn_pv", C.c_int, [C.POINTER(AttnPvArgs), C.c_void_p]),
     ("tscd_attn_round2", C.c_int, [C.POINTER(AttnRound2Args), C.c_void_p]),
+    ("tscd_cafm_prep", C.c_int, [C.POINTER(CafmPrepArgs), C.c_void_p]),
+    ("tscd_cafm_chain", C.c_int, [C.POINTER(CafmChainArgs), C.c_void_p]),
+    ("tscd_frame_attention", C.c_int, [C.POINTER(FrameAttentionArgs), C.c_void_p]),
+    ("tscd_residual_ln2", C.c_int, [C.POINTER(ResidualLn2Args), C.c_void_p]),
+    ("tscd_final_expand", C.c_int, [C.POINTER(FinalExpandArgs), C.c_void_p]),
+    ("tscd_final_rows", C.c_int, [C.POINTER(FinalRowsArgs), C.c_void_p]),
 ]
 
 

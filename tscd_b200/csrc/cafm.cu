@@ -1,0 +1,409 @@
+// K5: CAFM -- spatiotemporal context-aware feature matching (AwarePositionRegMatcher).
+//
+// Reference: yolox/models/tscd_matching.py:639-937 (forward :722-888, double_match_embds :912-937,
+// ReferringCrossAttentionLayer.forward_post :566-589, SEModule :278-283, PositionMHAttention :31-60) and
+// scipy.optimize.linear_sum_assignment (called at :935).
+//
+// The recurrence over local frames is inherently sequential (frame i's queries are frame i-1's outputs), so
+// one CTA owns one clip and walks its frames; clips run in parallel on different SMs.  Everything that does
+// not depend on the recurrence (value / key projections, SE gate of the key side, time embedding, norms) is
+// computed up front by batched kernels (tscd_cafm_prep + tscd_linear).  Inside the chain:
+//   cost      32x32 tiles of (prev, cur) pairs, 128-dim slabs of the 2x1024-dim embeddings staged in shared
+//             memory, fp32:  1 - (cos_reg + cos_cls)/2  with the reference's (|x| + 1e-6) norms, NaN -> 0;
+//   LSAP      shortest augmenting path in fp64 by one warp, SciPy's scan order and tie rules (among equal
+//             minima prefer a column that is a new sink; `remaining` filled in reverse, swap-with-last);
+//   attention 8 heads x 32, cosine (L2-normalised q,k, no scale), keys/values = the CURRENT frame only;
+//   output    LayerNorm(identity + attn), scattered back to the original row order, then decoder_norm.
+#include "common.cuh"
+
+namespace tscd {
+
+constexpr int kChainThreads = 512;
+constexpr int kChainMax = 512;
+
+__device__ __forceinline__ float se_gate(float a, float b, const float* w1, const float* w2) {
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        float h = fmaxf(0.f, fmaf(w1[2 * j + 1], b, w1[2 * j] * a));
+        o0 = fmaf(w2[j], h, o0);
+        o1 = fmaf(w2[32 + j], h, o1);
+    }
+    const float s0 = 1.f / (1.f + expf(-o0)), s1 = 1.f / (1.f + expf(-o1));
+    return a * s0 + b * s1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cafm_prep_kernel(const tscd_cafm_prep_args a) {
+    __shared__ float w1[64], w2[64];
+    if (threadIdx.x < 64) { w1[threadIdx.x] = a.se_w1[threadIdx.x]; w2[threadIdx.x] = a.se_w2[threadIdx.x]; }
+    __syncthreads();
+    const int lf = blockIdx.x;  // local frame index b*L + f
+    const int b = lf / a.L, f = lf - b * a.L;
+    const int r0 = a.row_off[b * a.F + f];
+    const int n = a.row_off[b * a.F + f + 1] - r0;
+    const int l0 = a.lrow_off[lf];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D = a.D, E = 4 * a.D;
+    for (int j = warp; j < n; j += 8) {
+        const T* fr = reinterpret_cast<const T*>(a.bank_reg) + (int64_t)(r0 + j) * D;
+        const T* er = reinterpret_cast<const T*>(a.bank_edge) + (int64_t)(r0 + j) * D;
+        const int64_t o = (int64_t)(l0 + j) * D;
+        for (int c = lane; c < D; c += 32) {
+            const float x = ldf(fr + c), e = ldf(er + c);
+            const float k = se_gate(x, e, w1, w2) + a.time_emb[(int64_t)lf * D + c];
+            a.feat[o + c] = x;
+            a.edge[o + c] = e;
+            a.kin[o + c] = k;
+            reinterpret_cast<T*>(a.feat16)[o + c] = cvt_from_float<T>(x);
+            reinterpret_cast<T*>(a.kin16)[o + c] = cvt_from_float<T>(k);
+        }
+        float sr = 0.f, sc = 0.f;
+        const float* pr = a.emb_reg + (int64_t)(l0 + j) * E;
+        const float* pc = a.emb_cls + (int64_t)(l0 + j) * E;
+        for (int c = lane; c < E; c += 32) { sr = fmaf(pr[c], pr[c], sr); sc = fmaf(pc[c], pc[c], sc); }
+        sr = warp_sumf(sr); sc = warp_sumf(sc);
+        if (lane == 0) { a.norm_reg[l0 + j] = sqrtf(sr) + 1e-6f; a.norm_cls[l0 + j] = sqrtf(sc) + 1e-6f; }
+    }
+}
+
+struct ChainSmem {
+    double u[kChainMax], v[kChainMax], spc[kChainMax];
+    int path[kChainMax], col4row[kChainMax], row4col[kChainMax], remaining[kChainMax];
+    int perm[kChainMax], prow[kChainMax];
+    unsigned char SR[kChainMax], SC[kChainMax];
+    float w1[64], w2[64];
+    float tileA[32][129], tileB[32][129];
+    float pbuf[kChainThreads / 32][kChainMax];
+};
+
+// Rectangular LSAP by warp 0.  C is the [n_prev x n_cur] cost (row-major, fp32).  Solves the problem with
+// rows = the smaller side exactly like scipy (transposing when n_cur < n_prev).  Results in s.col4row / s.row4col.
+__device__ void lap_warp(const float* C, int n_prev, int n_cur, ChainSmem& s, int lane) {
+    const bool tr = n_cur < n_prev;
+    const int nr = tr ? n_cur : n_prev, nc = tr ? n_prev : n_cur;
+    for (int j = lane; j < nc; j += 32) { s.v[j] = 0.0; s.row4col[j] = -1; s.path[j] = -1; }
+    for (int i = lane; i < nr; i += 32) { s.u[i] = 0.0; s.col4row[i] = -1; }
+    __syncwarp();
+    for (int cur = 0; cur < nr; ++cur) {
+        for (int it = lane; it < nc; it += 32) { s.remaining[it] = nc - it - 1; s.spc[it] = INFINITY; s.SC[it] = 0; }
+        for (int i = lane; i < nr; i += 32) s.SR[i] = 0;
+        __syncwarp();
+        double min_val = 0.0;
+        int i = cur, num_rem = nc, sink = -1;
+        while (sink == -1) {
+            if (lane == 0) s.SR[i] = 1;
+            const double ui = s.u[i];
+            double best = INFINITY;
+            int best_it = -1;
+            int best_sink = 0;
+            for (int it = lane; it < num_rem; it += 32) {
+                const int j = s.remaining[it];
+                const double c = (double)(tr ? C[(int64_t)j * n_cur + i] : C[(int64_t)i * n_cur + j]);
+                const double r = min_val + c - ui - s.v[j];
+                if (r < s.spc[j]) { s.path[j] = i; s.spc[j] = r; }
+                const double sj = s.spc[j];
+                const int snk = s.row4col[j] == -1;
+                if (sj < best || (sj == best && snk)) { best = sj; best_it = it; best_sink = snk; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oit = __shfl_xor_sync(0xffffffffu, best_it, o);
+                const int os = __shfl_xor_sync(0xffffffffu, best_sink, o);
+                bool take = false;
+                if (oit >= 0) {
+                    if (best_it < 0 || ob < best) take = true;
+                    else if (ob == best) {
+                        if (os && !best_sink) take = true;
+                        else if (os && best_sink) take = oit > best_it;      // last sink among the ties
+                        else if (!os && !best_sink) take = oit < best_it;    // otherwise the first tie
+                    }
+                }
+                if (take) { best = ob; best_it = oit; best_sink = os; }
+            }
+            min_val = best;
+            if (best_it < 0 || best == INFINITY) { sink = -2; break; }   // infeasible (cannot happen: finite costs)
+            const int j = s.remaining[best_it];
+            if (s.row4col[j] == -1) sink = j; else i = s.row4col[j];
+            __syncwarp();
+            if (lane == 0) { s.SC[j] = 1; s.remaining[best_it] = s.remaining[num_rem - 1]; }
+            --num_rem;
+            __syncwarp();
+        }
+        if (sink < 0) break;
+        if (lane == 0) s.u[cur] += min_val;
+        for (int r = lane; r < nr; r += 32)
+            if (s.SR[r] && r != cur) s.u[r] += min_val - s.spc[s.col4row[r]];
+        for (int j = lane; j < nc; j += 32)
+            if (s.SC[j]) s.v[j] -= min_val - s.spc[j];
+        __syncwarp();
+        if (lane == 0) {
+            int j = sink;
+            for (;;) {
+                const int r = s.path[j];
+                s.row4col[j] = r;
+                const int t = s.col4row[r];
+                s.col4row[r] = j;
+                j = t;
+                if (r == cur) break;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void layer_norm_row(const float* x, const float* w, const float* b, float* y, int D, int lane) {
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) s += x[c];
+    const float mean = warp_sumf(s) / D;
+    float v = 0.f;
+    for (int c = lane; c < D; c += 32) { const float d = x[c] - mean; v = fmaf(d, d, v); }
+    const float rstd = rsqrtf(warp_sumf(v) / D + 1e-5f);
+    for (int c = lane; c < D; c += 32) y[c] = (x[c] - mean) * rstd * w[c] + b[c];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd_cafm_chain_args a) {
+    extern __shared__ __align__(16) unsigned char chain_smem[];
+    ChainSmem& s = *reinterpret_cast<ChainSmem*>(chain_smem);
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int D = a.D, E = 4 * a.D, KM = a.kmax;
+    constexpr int NW = kChainThreads / 32;
+    if (tid < 64) { s.w1[tid] = a.se_w1[tid]; s.w2[tid] = a.se_w2[tid]; }
+
+    float* st_out = a.st_out + (int64_t)b * KM * D;
+    float* st_edge = a.st_edge + (int64_t)b * KM * D;
+    float* st_reg = a.st_reg + (int64_t)b * KM * E;
+    float* st_cls = a.st_cls + (int64_t)b * KM * E;
+    float* st_nreg = a.st_nreg + (int64_t)b * KM;
+    float* st_ncls = a.st_ncls + (int64_t)b * KM;
+    float* st_time = a.st_time + (int64_t)b * D;
+    float* qin = a.sc_qin + (int64_t)b * KM * D;
+    float* qv = a.sc_q + (int64_t)b * KM * D;
+    float* kh = a.sc_k + (int64_t)b * KM * D;
+    float* cost = a.sc_cost + (int64_t)b * KM * KM;
+
+    const bool resume = a.resume ? (a.resume[b] != 0) : false;
+    int n_prev = resume ? a.st_n[b] : 0;   // 0 = no memory
+    __syncthreads();
+
+    for (int f = 0; f < a.L; ++f) {
+        const int lf = b * a.L + f;
+        const int l0 = a.lrow_off[lf];
+        const int n = a.lrow_off[lf + 1] - l0;
+        if (n == 0) {
+            if (f == 0 && !resume) n_prev = 0;      // tscd_matching.py:762-771
+            continue;
+        }
+        if (n > KM || n > kChainMax) {
+            if (tid == 0) atomicMin(a.status, TSCD_ERR_CAPACITY);
+            continue;
+        }
+        const bool first = (f == 0 && !resume) || n_prev == 0;
+        const int np = first ? n : n_prev;           // rows on the "reference" side of the matching
+        const float* Rc = a.emb_reg + (int64_t)l0 * E;
+        const float* Cc = a.emb_cls + (int64_t)l0 * E;
+        const float* Rp = first ? Rc : st_reg;
+        const float* Cp = first ? Cc : st_cls;
+        const float* nRc = a.norm_reg + l0;
+        const float* nCc = a.norm_cls + l0;
+        const float* nRp = first ? nRc : st_nreg;
+        const float* nCp = first ? nCc : st_ncls;
+
+        // ---- matching cost [np x n] ------------------------------------------------------------------
+        for (int rb = 0; rb < np; rb += 32) {
+            for (int cb = 0; cb < n; cb += 32) {
+                float accR[2] = {0.f, 0.f}, accC[2] = {0.f, 0.f};
+                const int pr = tid >> 5;            // pairs (pr, lane) and (pr + 16, lane)
+                for (int which = 0; which < 2; ++which) {
+                    const float* P = which == 0 ? Rp : Cp;
+                    const float* Q = which == 0 ? Rc : Cc;
+                    for (int d0 = 0; d0 < E; d0 += 128) {
+                        __syncthreads();
+                        for (int t = tid; t < 32 * 128; t += kChainThreads) {
+                            const int rr = t >> 7, dd = t & 127;
+                            s.tileA[rr][dd] = (rb + rr < np) ? P[(int64_t)(rb + rr) * E + d0 + dd] : 0.f;
+                            s.tileB[rr][dd] = (cb + rr < n) ? Q[(int64_t)(cb + rr) * E + d0 + dd] : 0.f;
+                        }
+                        __syncthreads();
+                        float x0 = 0.f, x1 = 0.f;
+#pragma unroll 8
+                        for (int dd = 0; dd < 128; ++dd) {
+                            const float q = s.tileB[lane][dd];
+                            x0 = fmaf(s.tileA[pr][dd], q, x0);
+                            x1 = fmaf(s.tileA[pr + 16][dd], q, x1);
+                        }
+                        if (which == 0) { accR[0] += x0; accR[1] += x1; } else { accC[0] += x0; accC[1] += x1; }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int r = rb + pr + 16 * k, c = cb + lane;
+                    if (r < np && c < n) {
+                        const float cr = accR[k] / (nRp[r] * nRc[c]);
+                        const float cc = accC[k] / (nCp[r] * nCc[c]);
+                        float v = 1.f - (cr + cc) / 2.f;
+                        if (v != v) v = 0.f;
+                        cost[(int64_t)r * n + c] = v;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- assignment -----------------------------------------------------------------------------
+        if (warp == 0) {
+            lap_warp(cost, np, n, s, lane);
+            __syncwarp();
+            if (lane == 0) {
+                if (np <= n) {
+                    for (int r = 0; r < np; ++r) { s.perm[r] = s.col4row[r]; s.prow[r] = r; }
+                    int t = np;
+                    for (int c = 0; c < n && t < n; ++c)
+                        if (s.row4col[c] == -1) { s.perm[t] = c; s.prow[t] = -1 - c; ++t; }
+                } else {
+                    int t = 0;
+                    for (int j = 0; j < np; ++j)
+                        if (s.row4col[j] >= 0) { s.perm[t] = s.row4col[j]; s.prow[t] = j; ++t; }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- query input ----------------------------------------------------------------------------
+        const float* featc = a.feat + (int64_t)l0 * D;
+        const float* edgec = a.edge + (int64_t)l0 * D;
+        const float* kinc = a.kin + (int64_t)l0 * D;
+        for (int t = tid; t < n * D; t += kChainThreads) {
+            const int r = t / D, c = t - r * D;
+            float v;
+            if (first) {
+                v = kinc[(int64_t)r * D + c];                  // SE(feat, edge) + time of this frame
+            } else {
+                const int p = s.prow[r];
+                const float tg = p >= 0 ? st_out[(int64_t)p * D + c] : featc[(int64_t)(-1 - p) * D + c];
+                const float ed = p >= 0 ? st_edge[(int64_t)p * D + c] : edgec[(int64_t)(-1 - p) * D + c];
+                v = se_gate(tg, ed, s.w1, s.w2) + st_time[c];
+            }
+            qin[t] = v;
+        }
+        __syncthreads();
+        // ---- q = W_q qin  (thread = output channel, 4 rows at a time) --------------------------------
+        {
+            const int c = tid % D, g = tid / D, ng = kChainThreads / D;
+            for (int r0 = g * 4; r0 < n; r0 += ng * 4) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int k = 0; k < D; ++k) {
+                    const float w = __ldg(a.wq_t + (int64_t)k * D + c);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (r0 + i < n) acc[i] = fmaf(qin[(int64_t)(r0 + i) * D + k], w, acc[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (r0 + i < n) qv[(int64_t)(r0 + i) * D + c] = acc[i];
+            }
+        }
+        __syncthreads();
+        // ---- per-head L2 normalisation of q and k (8 heads x 32) --------------------------------------
+        const float* kp = a.kproj + (int64_t)l0 * D;
+        const float* vp = a.vproj + (int64_t)l0 * D;
+        for (int t = warp; t < n * 8 * 2; t += NW) {
+            const int which = t & 1, rh = t >> 1, r = rh >> 3, h = rh & 7;
+            const float x = which == 0 ? qv[(int64_t)r * D + h * 32 + lane] : kp[(int64_t)r * D + h * 32 + lane];
+            const float nn = sqrtf(warp_sumf(x * x));
+            if (which == 0) qv[(int64_t)r * D + h * 32 + lane] = x / nn; else kh[(int64_t)r * D + h * 32 + lane] = x / nn;
+        }
+        __syncthreads();
+        // ---- attention over the current frame; LayerNorm(identity + attn) ----------------------------
+        // qin is reused as the pre-norm output buffer [n, D]
+        for (int t = warp; t < n * 8; t += NW) {
+            const int r = t >> 3, h = t & 7;
+            const float ql = qv[(int64_t)r * D + h * 32 + lane];
+            float qreg[32];
+#pragma unroll
+            for (int d = 0; d < 32; ++d) qreg[d] = __shfl_sync(0xffffffffu, ql, d);
+            float* p = s.pbuf[warp];
+            float mx = -INFINITY;
+            for (int j = lane; j < n; j += 32) {
+                const float* kr = kh + (int64_t)j * D + h * 32;
+                float sc = 0.f;
+#pragma unroll
+                for (int d = 0; d < 32; ++d) sc = fmaf(qreg[d], kr[d], sc);
+                p[j] = sc;
+                mx = fmaxf(mx, sc);
+            }
+            mx = warp_maxf(mx);
+            __syncwarp();
+            float sum = 0.f;
+            for (int j = lane; j < n; j += 32) { const float e = expf(p[j] - mx); p[j] = e; sum += e; }
+            sum = warp_sumf(sum);
+            __syncwarp();
+            float acc = 0.f;
+            for (int j = 0; j < n; ++j) acc = fmaf(p[j], vp[(int64_t)j * D + h * 32 + lane], acc);
+            const int idr = first ? r : s.perm[r];
+            qin[(int64_t)r * D + h * 32 + lane] = featc[(int64_t)idr * D + h * 32 + lane] + acc / sum;
+            __syncwarp();
+        }
+        __syncthreads();
+        // ---- norms, state update, scatter to the original order --------------------------------------
+        for (int r = warp; r < n; r += NW) {
+            layer_norm_row(qin + (int64_t)r * D, a.ln_w, a.ln_b, st_out + (int64_t)r * D, D, lane);   // new last_outputs
+            __syncwarp();
+            const int dst = l0 + s.perm[r];
+            float* tmp = qv + (int64_t)r * D;    // q no longer needed
+            layer_norm_row(st_out + (int64_t)r * D, a.dec_w, a.dec_b, tmp, D, lane);
+            __syncwarp();
+            for (int c = lane; c < D; c += 32) {
+                reinterpret_cast<T*>(a.out16)[(int64_t)dst * D + c] = cvt_from_float<T>(tmp[c]);
+                if (a.out32) a.out32[(int64_t)dst * D + c] = tmp[c];
+            }
+            if (a.perm && lane == 0) a.perm[l0 + r] = s.perm[r];
+            const int src = first ? r : s.perm[r];   // order in which this frame is remembered
+            for (int c = lane; c < D; c += 32) st_edge[(int64_t)r * D + c] = edgec[(int64_t)src * D + c];
+            if (lane == 0) { st_nreg[r] = nRc[src]; st_ncls[r] = nCc[src]; }
+        }
+        __syncthreads();   // cost reads of st_reg / st_cls for this frame are complete
+        for (int t = tid; t < n * (E / 4); t += kChainThreads) {
+            const int r = t / (E / 4), c4 = t - r * (E / 4);
+            const int src = first ? r : s.perm[r];
+            reinterpret_cast<float4*>(st_reg)[(int64_t)r * (E / 4) + c4] = reinterpret_cast<const float4*>(Rc)[(int64_t)src * (E / 4) + c4];
+            reinterpret_cast<float4*>(st_cls)[(int64_t)r * (E / 4) + c4] = reinterpret_cast<const float4*>(Cc)[(int64_t)src * (E / 4) + c4];
+        }
+        for (int c = tid; c < D; c += kChainThreads) st_time[c] = a.time_emb[(int64_t)lf * D + c];
+        n_prev = n;
+        __syncthreads();
+    }
+    if (tid == 0) a.st_n[b] = n_prev;
+}
+
+}  // namespace tscd
+
+extern "C" int tscd_cafm_prep(const tscd_cafm_prep_args* a, void* stream) {
+    using namespace tscd;
+    if (!a || a->B <= 0 || a->L <= 0 || a->D <= 0 || (a->D % 32) != 0) return TSCD_ERR_INVALID_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (a->bank_dtype == TSCD_F16) cafm_prep_kernel<__half><<<a->B * a->L, 256, 0, st>>>(*a);
+    else if (a->bank_dtype == TSCD_BF16) cafm_prep_kernel<__nv_bfloat16><<<a->B * a->L, 256, 0, st>>>(*a);
+    else return TSCD_ERR_UNSUPPORTED;
+    TSCD_CUDA_CHECK_LAUNCH();
+    return TSCD_OK;
+}
+
+extern "C" int tscd_cafm_chain(const tscd_cafm_chain_args* a, void* stream) {
+    using namespace tscd;
+    if (!a || a->B <= 0 || a->L <= 0 || a->D != 256 || a->kmax <= 0 || a->kmax > kChainMax) return TSCD_ERR_INVALID_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t smem = sizeof(ChainSmem);
+    if (a->out_dtype == TSCD_F16) {
+        if (cudaFuncSetAttribute(cafm_chain_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
+        cafm_chain_kernel<__half><<<a->B, kChainThreads, smem, st>>>(*a);
+    } else if (a->out_dtype == TSCD_BF16) {
+        if (cudaFuncSetAttribute(cafm_chain_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
+        cafm_chain_kernel<__nv_bfloat16><<<a->B, kChainThreads, smem, st>>>(*a);
+    } else {
+        return TSCD_ERR_UNSUPPORTED;
+    }
+    TSCD_CUDA_CHECK_LAUNCH();
+    return TSCD_OK;
+}

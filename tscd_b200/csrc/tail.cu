@@ -1,0 +1,240 @@
+// Tail of the stage: TaskAligned cosine attention per frame, the two LayerNorms, and the final per-class
+// expansion feeding the last class-aware NMS.
+//
+// Reference: TaskAligned.forward / CrossAttentionLayer.forward_post / MHAttention.forward
+// (yolox/models/tscd_matching.py:1107-1139, 421-433, 159-181), decode_reg_preds5 (yolox/models/tscd_head.py:
+// 914-949) and postprocess (yolox/models/post_process.py:9-85).
+#include "common.cuh"
+
+namespace tscd {
+
+// ---------------------------------------------------------------------------------------------- frame attention
+// One CTA per (local frame, head).  Keys/values stream through shared memory in chunks of 64 with an online
+// softmax; each warp owns query rows, lanes own keys (scores) then output dims (weighted sum).
+constexpr int kFaChunk = 64;
+
+__global__ void __launch_bounds__(256) frame_attention_kernel(const tscd_frame_attention_args a) {
+    extern __shared__ __align__(16) float fa_smem[];
+    const int hd = a.head_dim;           // multiple of 32, <= 128
+    const int pitch = hd + 1;
+    float* sK = fa_smem;                  // [64][hd+1] normalised keys
+    float* sV = sK + kFaChunk * pitch;    // [64][hd]
+    float* sQ = sV + kFaChunk * hd;       // [8 warps][hd] normalised query rows
+    const int lf = blockIdx.x, h = blockIdx.y;
+    const int l0 = a.lrow_off[lf], n = a.lrow_off[lf + 1] - l0;
+    if (n <= 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nd = hd / 32;               // output dims per lane (<= 4)
+    float* myq = sQ + warp * hd;
+
+    for (int rb = 0; rb < n; rb += 8) {   // 8 query rows per pass (one per warp)
+        const int r = rb + warp;
+        const bool r_ok = r < n;
+        float qs = 0.f;
+        if (r_ok) {
+            for (int d = lane; d < hd; d += 32) { const float x = a.q[(int64_t)(l0 + r) * a.ldq + h * hd + d]; myq[d] = x; qs = fmaf(x, x, qs); }
+        }
+        qs = warp_sumf(qs);
+        if (r_ok) { const float inv = 1.f / sqrtf(qs); for (int d = lane; d < hd; d += 32) myq[d] *= inv; }
+        float m = -INFINITY, l = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k0 = 0; k0 < n; k0 += kFaChunk) {
+            const int kc = min(kFaChunk, n - k0);
+            __syncthreads();
+            for (int j = warp; j < kc; j += 8) {   // stage + normalise keys, copy values
+                const float* kr = a.k + (int64_t)(l0 + k0 + j) * a.ldk + h * hd;
+                const float* vr = a.v + (int64_t)(l0 + k0 + j) * a.ldv + h * hd;
+                float ks = 0.f;
+                for (int d = lane; d < hd; d += 32) { const float x = kr[d]; sK[j * pitch + d] = x; ks = fmaf(x, x, ks); sV[j * hd + d] = vr[d]; }
+                ks = warp_sumf(ks);
+                const float inv = 1.f / sqrtf(ks);
+                for (int d = lane; d < hd; d += 32) sK[j * pitch + d] *= inv;
+            }
+            __syncthreads();
+            if (r_ok) {
+                float s0 = -INFINITY, s1 = -INFINITY;
+                if (lane < kc) { s0 = 0.f; for (int d = 0; d < hd; ++d) s0 = fmaf(myq[d], sK[lane * pitch + d], s0); }
+                if (lane + 32 < kc) { s1 = 0.f; for (int d = 0; d < hd; ++d) s1 = fmaf(myq[d], sK[(lane + 32) * pitch + d], s1); }
+                const float mn = fmaxf(m, warp_maxf(fmaxf(s0, s1)));
+                const float corr = expf(m - mn);
+                const float p0 = (lane < kc) ? expf(s0 - mn) : 0.f;
+                const float p1 = (lane + 32 < kc) ? expf(s1 - mn) : 0.f;
+                l = l * corr + warp_sumf(p0 + p1);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) acc[t] *= corr;
+                for (int j = 0; j < kc; ++j) {
+                    const float pj = __shfl_sync(0xffffffffu, j < 32 ? p0 : p1, j & 31);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (t < nd) acc[t] = fmaf(pj, sV[j * hd + lane + 32 * t], acc[t]);
+                }
+                m = mn;
+            }
+        }
+        if (r_ok) {
+            const float inv = 1.f / l;
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (t < nd) a.out[(int64_t)(l0 + r) * a.ldo + h * hd + lane + 32 * t] = acc[t] * inv;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- LN(LN(x + r))
+template <typename T>
+__global__ void __launch_bounds__(256) residual_ln2_kernel(const tscd_residual_ln2_args a) {
+    extern __shared__ __align__(16) float ln_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = min(a.rows_cap, a.n_rows ? __ldg(a.n_rows) : a.rows_cap);
+    const int D = a.dim;
+    float* buf = ln_smem + warp * D;
+    for (int r = blockIdx.x * 8 + warp; r < n; r += gridDim.x * 8) {
+        float s = 0.f;
+        for (int c = lane; c < D; c += 32) { const float x = a.x[(int64_t)r * D + c] + a.r[(int64_t)r * D + c]; buf[c] = x; s += x; }
+        float mean = warp_sumf(s) / D, v = 0.f;
+        for (int c = lane; c < D; c += 32) { const float d = buf[c] - mean; v = fmaf(d, d, v); }
+        float rstd = rsqrtf(warp_sumf(v) / D + 1e-5f);
+        s = 0.f;
+        for (int c = lane; c < D; c += 32) { const float y = (buf[c] - mean) * rstd * a.w_a[c] + a.b_a[c]; buf[c] = y; s += y; }
+        mean = warp_sumf(s) / D; v = 0.f;
+        for (int c = lane; c < D; c += 32) { const float d = buf[c] - mean; v = fmaf(d, d, v); }
+        rstd = rsqrtf(warp_sumf(v) / D + 1e-5f);
+        for (int c = lane; c < D; c += 32) {
+            const float y = (buf[c] - mean) * rstd * a.w_b[c] + a.b_b[c];
+            if (a.out16) reinterpret_cast<T*>(a.out16)[(int64_t)r * D + c] = cvt_from_float<T>(y);
+            if (a.out32) a.out32[(int64_t)r * D + c] = y;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- final expansion
+__global__ void __launch_bounds__(256) final_expand_kernel(const tscd_final_expand_args a) {
+    __shared__ int scan[40];
+    const int lf = blockIdx.x;
+    const int b = lf / a.L, f = lf - b * a.L;
+    const int fi = b * a.F + f;
+    const int n = min(a.sel_count[fi], a.max_keep);
+    const int l0 = a.lrow_off[lf];
+    const int C = a.num_classes, W = 7 + C;
+    const float* rows = a.sel_rows + (int64_t)fi * a.max_keep * W;
+    const int64_t rbase = (int64_t)lf * a.max_keep * C, obase = (int64_t)lf * a.max_keep;
+    const float thr = a.conf_thre;
+
+    // ---- refined candidates: flattened (proposal, class) space, stable compaction ----
+    const int total = n * C;
+    const int chunk = (total + blockDim.x - 1) / blockDim.x;
+    const int lo = min((int)threadIdx.x * chunk, total), hi = min(lo + chunk, total);
+    int cnt = 0;
+    for (int t = lo; t < hi; ++t) {
+        const int p = t / C, c = t - p * C;
+        const float cs = sigmoidf_ref(a.cls_logits[(int64_t)(l0 + p) * a.ld_cls + c]);
+        const float ob = sigmoidf_ref(a.obj_logits[(int64_t)(l0 + p) * a.ld_obj]);
+        cnt += (cs >= thr && __fmul_rn(ob, cs) >= thr) ? 1 : 0;
+    }
+    int tot;
+    int o = block_excl_scan(cnt, scan, &tot);
+    for (int t = lo; t < hi; ++t) {
+        const int p = t / C, c = t - p * C;
+        const float cs = sigmoidf_ref(a.cls_logits[(int64_t)(l0 + p) * a.ld_cls + c]);
+        const float ob = sigmoidf_ref(a.obj_logits[(int64_t)(l0 + p) * a.ld_obj]);
+        if (cs >= thr && __fmul_rn(ob, cs) >= thr) {
+            // decode_reg_preds5 (tscd_head.py:914-949), deltas w.r.t. the still-detector box
+            const float* r = rows + (int64_t)p * W;
+            const float* d = a.reg_deltas + (int64_t)(l0 + p) * a.ld_reg;
+            const float w = __fsub_rn(r[2], r[0]), h = __fsub_rn(r[3], r[1]);
+            const float cx = __fadd_rn(r[0], __fmul_rn(0.5f, w)), cy = __fadd_rn(r[1], __fmul_rn(0.5f, h));
+            const float dw = fminf(d[2], a.xform_clip), dh = fminf(d[3], a.xform_clip);
+            const float pcx = __fadd_rn(__fmul_rn(d[0], w), cx), pcy = __fadd_rn(__fmul_rn(d[1], h), cy);
+            const float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), h);
+            float4 box = make_float4(__fsub_rn(pcx, __fmul_rn(0.5f, pw)), __fsub_rn(pcy, __fmul_rn(0.5f, ph)),
+                                     __fadd_rn(pcx, __fmul_rn(0.5f, pw)), __fadd_rn(pcy, __fmul_rn(0.5f, ph)));
+            reinterpret_cast<float4*>(a.r_box)[rbase + o] = box;
+            a.r_score[rbase + o] = __fmul_rn(ob, cs);
+            a.r_cls[rbase + o] = c;
+            a.r_obj[rbase + o] = ob;
+            a.r_cscore[rbase + o] = cs;
+            ++o;
+        }
+    }
+    if (threadIdx.x == 0) a.r_count[lf] = tot;
+
+    // ---- still-detector candidates ----
+    const int chunk2 = (n + blockDim.x - 1) / blockDim.x;
+    const int lo2 = min((int)threadIdx.x * chunk2, n), hi2 = min(lo2 + chunk2, n);
+    cnt = 0;
+    for (int p = lo2; p < hi2; ++p) {
+        const float* r = rows + (int64_t)p * W;
+        cnt += (__fmul_rn(r[4], r[5]) >= thr) ? 1 : 0;
+    }
+    o = block_excl_scan(cnt, scan, &tot);
+    for (int p = lo2; p < hi2; ++p) {
+        const float* r = rows + (int64_t)p * W;
+        if (__fmul_rn(r[4], r[5]) >= thr) {
+            reinterpret_cast<float4*>(a.o_box)[obase + o] = make_float4(r[0], r[1], r[2], r[3]);
+            a.o_score[obase + o] = __fmul_rn(r[4], r[5]);
+            a.o_cls[obase + o] = (int)r[6];
+            a.o_obj[obase + o] = r[4];
+            a.o_cscore[obase + o] = r[5];
+            ++o;
+        }
+    }
+    if (threadIdx.x == 0) a.o_count[lf] = tot;
+}
+
+__global__ void final_rows_kernel(const tscd_final_rows_args a) {
+    const int fr = blockIdx.x;
+    const int n = min(a.keep_count[fr], a.keep_cap);
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const int pos = a.keep[(int64_t)fr * a.keep_cap + j];
+        const int64_t s = (int64_t)fr * a.cand_cap + pos;
+        float* o = a.rows + ((int64_t)fr * a.keep_cap + j) * 7;
+        const float4 bx = reinterpret_cast<const float4*>(a.box)[s];
+        o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+        o[4] = a.obj[s]; o[5] = a.cscore[s]; o[6] = (float)a.cls[s];
+    }
+}
+
+}  // namespace tscd
+
+extern "C" int tscd_frame_attention(const tscd_frame_attention_args* a, void* stream) {
+    using namespace tscd;
+    if (!a || a->num_frames <= 0 || a->heads <= 0 || a->head_dim <= 0 || a->head_dim % 32 || a->head_dim > 128) return TSCD_ERR_INVALID_ARG;
+    const size_t smem = (size_t)(kFaChunk * (a->head_dim + 1) + kFaChunk * a->head_dim + 8 * a->head_dim) * sizeof(float);
+    if (cudaFuncSetAttribute(frame_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
+    frame_attention_kernel<<<dim3(a->num_frames, a->heads), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+    TSCD_CUDA_CHECK_LAUNCH();
+    return TSCD_OK;
+}
+
+extern "C" int tscd_residual_ln2(const tscd_residual_ln2_args* a, void* stream) {
+    using namespace tscd;
+    if (!a || a->rows_cap <= 0 || a->dim <= 0 || a->dim > 4096) return TSCD_ERR_INVALID_ARG;
+    const size_t smem = (size_t)8 * a->dim * sizeof(float);
+    int grid = (a->rows_cap + 7) / 8;
+    if (grid > 148 * 8) grid = 148 * 8;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (a->out_dtype == TSCD_BF16) {
+        if (cudaFuncSetAttribute(residual_ln2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
+        residual_ln2_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(*a);
+    } else {
+        if (cudaFuncSetAttribute(residual_ln2_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
+        residual_ln2_kernel<__half><<<grid, 256, smem, st>>>(*a);
+    }
+    TSCD_CUDA_CHECK_LAUNCH();
+    return TSCD_OK;
+}
+
+extern "C" int tscd_final_expand(const tscd_final_expand_args* a, void* stream) {
+    using namespace tscd;
+    if (!a || a->B <= 0 || a->L <= 0 || a->num_classes <= 0 || a->max_keep <= 0) return TSCD_ERR_INVALID_ARG;
+    final_expand_kernel<<<a->B * a->L, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+    TSCD_CUDA_CHECK_LAUNCH();
+    return TSCD_OK;
+}
+
+extern "C" int tscd_final_rows(const tscd_final_rows_args* a, void* stream) {
+    using namespace tscd;
+    if (!a || a->num_frames <= 0) return TSCD_ERR_INVALID_ARG;
+    final_rows_kernel<<<a->num_frames, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+    TSCD_CUDA_CHECK_LAUNCH();
+    return TSCD_OK;
+}

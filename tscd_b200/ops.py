@@ -262,3 +262,18 @@ def attn_round2(lay: AttnLayoutT, bufs, vt, stats, out, use_obj_mask, sim_thresh
     a.sim_thresh, a.conf_sim_thresh = sim_thresh, conf_sim_thresh
     a.out, a.ld_out = _p(out), out.stride(0)
     L.check(L.lib().tscd_attn_round2(C.byref(a), _stream()), "tscd_attn_round2")
+
+
+# ----------------------------------------------------------------------------------------------- generic call helper
+def call(name: str, struct_cls, **kw):
+    """Fill a ctypes argument struct from keyword arguments (tensors -> data_ptr) and call the C-ABI entry point."""
+    a = struct_cls()
+    for k, v in kw.items():
+        if isinstance(v, torch.Tensor) or v is None:
+            v = _p(v)
+        elif isinstance(v, torch.dtype):
+            v = _DT[v]
+        setattr(a, k, v)
+    missing = {f[0] for f in struct_cls._fields_} - set(kw)
+    assert not missing, f"{name}: missing {missing}"
+    L.check(getattr(L.lib(), name)(C.byref(a), _stream()), name)

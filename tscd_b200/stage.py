@@ -1,0 +1,226 @@
+"""The TSCD aggregation stage as one host-side object: everything in TSCDHead.forward after the decoupled-head
+convolutions (yolox/models/tscd_head.py:374-733), for a BATCH of clips, on hand-written sm_100a kernels.
+
+Host code is plumbing only (buffer allocation through torch, C-ABI calls on the current stream).  All
+data-dependent sizes stay on the device until the single read-back that turns the padded detection tensors
+into the reference's `list[Tensor[n,7] | None]` containers.  There is no CPU / PyTorch fallback: if
+libtscd_b200.so is missing `tscd_b200._lib.lib()` raises.
+"""
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib as L
+from . import aggregate, ops, selection
+
+
+def _r128(x: int) -> int:
+    return (x + 127) // 128 * 128
+
+
+@dataclass
+class StageConfig:
+    num_classes: int
+    selection: selection.SelectionConfig = field(default_factory=selection.SelectionConfig)
+    dim: int = 256                    # int(256 * width); the kernels are specialised for 256 (TSCD-L)
+    heads: int = 4
+    sim_thresh: float = 0.75          # TSCDHead ctor `sim_thresh`
+    conf_sim_thresh: float = 0.99     # kwargs['conf_sim_thresh'] (post_trans.py:693)
+    final_nms_thresh: float = 0.5     # forward(..., nms_thresh=0.5)
+    final_conf_thresh: float = 0.001  # post_process.py:10 default (not overridable in the reference)
+    dtype: torch.dtype = torch.float16  # tensor-core operand type (fp16 = the reference's eval dtype; bf16 also supported)
+
+
+class StageWeights:
+    """Device copies of the aggregation-stage parameters (reference state_dict key names)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], cfg: StageConfig, device="cuda"):
+        dt = cfg.dtype
+
+        def w16(name):
+            return sd[name].detach().to(device=device, dtype=dt).contiguous()
+
+        def f32(name):
+            return sd[name].detach().to(device=device, dtype=torch.float32).contiguous()
+
+        self.agg = aggregate.MCAWeights(sd, "agg.", dt, device)
+        self.agg_iou = aggregate.MCAWeights(sd, "agg_iou.", dt, device)
+        m = "local_reg_matcher."
+        lay = m + "transformer_aware_cross_attention_layers.0."
+        self.ape_w, self.ape_b = w16(m + "absolute_position_embedding.weight"), f32(m + "absolute_position_embedding.bias")
+        self.cafm_wk = w16(lay + "multihead_attn.k_reg.weight")
+        self.cafm_wv = w16(lay + "multihead_attn.v_reg.weight")
+        self.cafm_wq_t = f32(lay + "multihead_attn.q_reg.weight").t().contiguous()     # [in, out]
+        self.se_w1, self.se_w2 = f32(lay + "CA.fc.0.weight"), f32(lay + "CA.fc.2.weight")
+        self.cafm_ln_w, self.cafm_ln_b = f32(lay + "norm.weight"), f32(lay + "norm.bias")
+        self.cafm_dec_w, self.cafm_dec_b = f32(m + "decoder_norm.weight"), f32(m + "decoder_norm.bias")
+        self.fc_w, self.fc_b = w16("fc_reg_matcher.weight"), f32("fc_reg_matcher.bias")
+        t = "task_aligned.transformer_cross_attention_layers.0."
+        self.ta_wq = w16(t + "multihead_attn.q_reg.weight")
+        self.ta_wkv = torch.cat([w16(t + "multihead_attn.k_reg.weight"), w16(t + "multihead_attn.v_reg.weight")], 0).contiguous()
+        self.ta_ln_w, self.ta_ln_b = f32(t + "norm.weight"), f32(t + "norm.bias")
+        self.ta_dec_w, self.ta_dec_b = f32("task_aligned.decoder_norm.weight"), f32("task_aligned.decoder_norm.bias")
+        self.cls_w, self.cls_b = w16("cls_pred.weight"), f32("cls_pred.bias")
+        self.obj_w, self.obj_b = w16("matcher_obj_pred.weight"), f32("matcher_obj_pred.bias")
+        self.reg_w, self.reg_b = w16("matcher_reg_pred.weight"), f32("matcher_reg_pred.bias")
+
+
+class CAFMState:
+    """Caller-owned CAFM memory (tscd_matching.py:708-715) for `slots` concurrent video streams."""
+
+    def __init__(self, slots: int, kmax: int, dim: int = 256, device="cuda"):
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)  # noqa: E731
+        self.slots, self.kmax = slots, kmax
+        self.n = torch.zeros(slots, dtype=torch.int32, device=device)
+        self.out, self.edge = z(slots, kmax, dim), z(slots, kmax, dim)
+        self.reg, self.cls = z(slots, kmax, 4 * dim), z(slots, kmax, 4 * dim)
+        self.nreg, self.ncls, self.time = z(slots, kmax), z(slots, kmax), z(slots, dim)
+
+
+class AggregationStage:
+    """forward(): head outputs + feature planes of B clips x F frames -> refined detections of the B x L local frames."""
+
+    def __init__(self, cfg: StageConfig, state_dict: Dict[str, torch.Tensor], device="cuda"):
+        if cfg.dim != 256 or cfg.heads != 4:
+            raise RuntimeError("tscd_b200 kernels are specialised for TSCD-L (dim 256, 4 heads)")
+        L.lib()  # fail loudly if the CUDA library is missing
+        self.cfg = cfg
+        self.w = StageWeights(state_dict, cfg, device)
+        self.device = device
+
+    # ------------------------------------------------------------------------------------------------------
+    def forward(self, head: ops.HeadViews, feats, feat_dtype, time_embedding: torch.Tensor, B: int, F: int, Lf: int,
+                state: Optional[CAFMState] = None, resume: Optional[torch.Tensor] = None, trace: Optional[dict] = None):
+        cfg, w, dev, dt = self.cfg, self.w, self.device, self.cfg.dtype
+        C = cfg.num_classes
+        D = cfg.dim
+        assert head.num_frames == B * F and 1 <= Lf <= F
+        A = head.anchors.num_anchors
+        kmax = cfg.selection.max_keep(A)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+
+        # ---- K1-K3: selection + bank ------------------------------------------------------------------
+        sel = selection.select_and_gather(head, feats, feat_dtype, D, cfg.selection, bank_dtype=dt, status=status)
+        # operand arrays are read in 128-row TMA boxes: pad the banks
+        row_cap = _r128(B * F * kmax) + 128
+        loc_cap = _r128(B * Lf * kmax)
+        nk_pitch = _r128(F * kmax)
+
+        def pad_rows(t, rows):
+            if t.shape[0] >= rows:
+                return t
+            p = torch.zeros(rows, *t.shape[1:], dtype=t.dtype, device=dev)
+            p[:t.shape[0]] = t
+            return p
+
+        bank_cls, bank_reg, bank_edge = (pad_rows(sel[k], row_cap) for k in ("bank_cls", "bank_reg", "bank_edge"))
+        bank_score = pad_rows(sel["bank_score"], row_cap)
+        lay = aggregate.make_layout(sel["sel_count"], B, F, Lf, row_cap, loc_cap, nk_pitch, dt, row_off=sel["row_off"])
+        n_rows_dev, n_loc_dev = lay.row_off[-1:], lay.lrow_off[-1:]
+
+        # ---- K4: agg (cls refinement) and agg_iou (reg / obj refinement) ---------------------------------
+        (agg_cls16, agg_cls32), _ = aggregate.mca_forward(lay, w.agg, bank_cls, bank_reg, bank_score, n_rows_dev, n_loc_dev,
+                                                          need_reg=False, sim_thresh=cfg.sim_thresh,
+                                                          conf_sim_thresh=cfg.conf_sim_thresh)
+        (iou_cls16, iou_cls32), (iou_reg16, iou_reg32) = aggregate.mca_forward(
+            lay, w.agg_iou, bank_cls, bank_reg, bank_score, n_rows_dev, n_loc_dev, need_reg=True,
+            sim_thresh=cfg.sim_thresh, conf_sim_thresh=cfg.conf_sim_thresh)
+
+        # ---- K5: CAFM --------------------------------------------------------------------------------
+        te16 = time_embedding.to(device=dev, dtype=dt).contiguous()
+        assert te16.shape == (B * Lf, 256)
+        _, te32 = ops.linear(te16, w.ape_w, w.ape_b, want16=False, want32=True)
+        f32z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
+        feat, edge, kin = f32z(loc_cap, D), f32z(loc_cap, D), f32z(loc_cap, D)
+        feat16 = torch.zeros(loc_cap, D, dtype=dt, device=dev)
+        kin16 = torch.zeros(loc_cap, D, dtype=dt, device=dev)
+        norm_reg, norm_cls = f32z(loc_cap), f32z(loc_cap)
+        ops.call("tscd_cafm_prep", L.CafmPrepArgs, B=B, F=F, L=Lf, D=D, bank_dtype=dt, row_off=lay.row_off,
+                 lrow_off=lay.lrow_off, bank_reg=bank_reg, bank_edge=bank_edge, time_emb=te32, se_w1=w.se_w1,
+                 se_w2=w.se_w2, emb_reg=iou_reg32, emb_cls=iou_cls32, feat=feat, edge=edge, feat16=feat16,
+                 kin16=kin16, kin=kin, norm_reg=norm_reg, norm_cls=norm_cls)
+        _, kproj = ops.linear(kin16, w.cafm_wk, m_dev=n_loc_dev, want16=False, want32=True)
+        _, vproj = ops.linear(feat16, w.cafm_wv, m_dev=n_loc_dev, want16=False, want32=True)
+        if state is None:
+            state = CAFMState(B, kmax, D, dev)
+        assert state.slots == B and state.kmax == kmax
+        if resume is None:
+            resume = torch.zeros(B, dtype=torch.int32, device=dev)
+        cafm16 = torch.zeros(loc_cap, D, dtype=dt, device=dev)
+        cafm32 = f32z(loc_cap, D) if trace is not None else None
+        perm = torch.zeros(loc_cap, dtype=torch.int32, device=dev) if trace is not None else None
+        ops.call("tscd_cafm_chain", L.CafmChainArgs, B=B, F=F, L=Lf, D=D, kmax=kmax, out_dtype=dt, row_off=lay.row_off,
+                 lrow_off=lay.lrow_off, resume=resume, feat=feat, edge=edge, kin=kin, kproj=kproj, vproj=vproj,
+                 time_emb=te32, emb_reg=iou_reg32, emb_cls=iou_cls32, norm_reg=norm_reg, norm_cls=norm_cls,
+                 wq_t=w.cafm_wq_t, se_w1=w.se_w1, se_w2=w.se_w2, ln_w=w.cafm_ln_w, ln_b=w.cafm_ln_b,
+                 dec_w=w.cafm_dec_w, dec_b=w.cafm_dec_b, st_n=state.n, st_out=state.out, st_edge=state.edge,
+                 st_reg=state.reg, st_cls=state.cls, st_nreg=state.nreg, st_ncls=state.ncls, st_time=state.time,
+                 sc_qin=f32z(B, kmax, D), sc_q=f32z(B, kmax, D), sc_k=f32z(B, kmax, D), sc_cost=f32z(B, kmax, kmax),
+                 out16=cafm16, out32=cafm32, perm=perm, status=status)
+
+        # ---- fc_reg_matcher, TaskAligned, prediction heads ---------------------------------------------
+        matched16, matched32 = ops.linear(cafm16, w.fc_w, w.fc_b, m_dev=n_loc_dev, want16=True, want32=trace is not None)
+        _, reg_deltas = ops.linear(matched16, w.reg_w, w.reg_b, m_dev=n_loc_dev, want16=False, want32=True)
+        _, ta_q = ops.linear(iou_reg16, w.ta_wq, m_dev=n_loc_dev, want16=False, want32=True)
+        _, ta_kv = ops.linear(matched16, w.ta_wkv, m_dev=n_loc_dev, want16=False, want32=True)
+        att = f32z(loc_cap, 4 * D)
+        ops.call("tscd_frame_attention", L.FrameAttentionArgs, num_frames=B * Lf, heads=8, head_dim=(4 * D) // 8,
+                 lrow_off=lay.lrow_off, q=ta_q, ldq=ta_q.stride(0), k=ta_kv, ldk=ta_kv.stride(0),
+                 v=ta_kv[:, 4 * D:], ldv=ta_kv.stride(0), out=att, ldo=att.stride(0))
+        objref16 = torch.zeros(loc_cap, 4 * D, dtype=dt, device=dev)
+        objref32 = f32z(loc_cap, 4 * D) if trace is not None else None
+        ops.call("tscd_residual_ln2", L.ResidualLn2Args, rows_cap=loc_cap, dim=4 * D, n_rows=n_loc_dev, x=iou_reg32, r=att,
+                 w_a=w.ta_ln_w, b_a=w.ta_ln_b, w_b=w.ta_dec_w, b_b=w.ta_dec_b, out_dtype=dt, out16=objref16, out32=objref32)
+        _, obj_logits = ops.linear(objref16, w.obj_w, w.obj_b, m_dev=n_loc_dev, want16=False, want32=True)
+        _, cls_logits = ops.linear(agg_cls16, w.cls_w, w.cls_b, m_dev=n_loc_dev, want16=False, want32=True)
+
+        # ---- final per-class expansion + NMS ---------------------------------------------------------------
+        nlf = B * Lf
+        rcap, ocap = kmax * C, kmax
+        i32 = lambda *s: torch.zeros(*s, dtype=torch.int32, device=dev)  # noqa: E731
+        r = dict(box=f32z(nlf, rcap, 4), score=f32z(nlf, rcap), cls=i32(nlf, rcap), obj=f32z(nlf, rcap),
+                 cscore=f32z(nlf, rcap), count=i32(nlf))
+        o = dict(box=f32z(nlf, ocap, 4), score=f32z(nlf, ocap), cls=i32(nlf, ocap), obj=f32z(nlf, ocap),
+                 cscore=f32z(nlf, ocap), count=i32(nlf))
+        ops.call("tscd_final_expand", L.FinalExpandArgs, B=B, F=F, L=Lf, num_classes=C, max_keep=kmax,
+                 conf_thre=cfg.final_conf_thresh, xform_clip=math.log(736.0 / 32), sel_count=sel["sel_count"],
+                 sel_rows=sel["sel_rows"], lrow_off=lay.lrow_off, cls_logits=cls_logits, ld_cls=cls_logits.stride(0),
+                 obj_logits=obj_logits, ld_obj=obj_logits.stride(0), reg_deltas=reg_deltas, ld_reg=reg_deltas.stride(0),
+                 r_box=r["box"], r_score=r["score"], r_cls=r["cls"], r_obj=r["obj"], r_cscore=r["cscore"], r_count=r["count"],
+                 o_box=o["box"], o_score=o["score"], o_cls=o["cls"], o_obj=o["obj"], o_cscore=o["cscore"], o_count=o["count"])
+        out = {}
+        for name, c, cap in (("det", r, rcap), ("ori", o, ocap)):
+            keep, kc, _ = ops.nms(c["box"], c["score"], c["cls"], c["count"], cfg.final_nms_thresh, max_keep=cap, status=status)
+            rows = f32z(nlf, cap, 7)
+            ops.call("tscd_final_rows", L.FinalRowsArgs, num_frames=nlf, cand_cap=cap, keep_cap=cap, box=c["box"],
+                     obj=c["obj"], cscore=c["cscore"], cls=c["cls"], keep=keep, keep_count=kc, rows=rows)
+            out[name + "_rows"], out[name + "_count"], out[name + "_cand"] = rows, kc, c["count"]
+        out.update(status=status, sel=sel, layout=lay, state=state)
+        if trace is not None:
+            trace.update(agg_cls=agg_cls32, iou_cls=iou_cls32, iou_reg=iou_reg32, cafm=cafm32, perm=perm, matched=matched32,
+                         obj_ref=objref32, cls_logits=cls_logits, obj_logits=obj_logits, reg_deltas=reg_deltas,
+                         time_emb=te32, kproj=kproj, vproj=vproj, kin=kin, att=att)
+        return out
+
+    # ------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def to_lists(out, B: int, Lf: int):
+        """One device->host read; returns (result, result_ori) with the reference's container types
+        (post_process.py:12-13,85): per local frame a fresh Tensor[n,7] or None."""
+        st = int(out["status"].item())
+        if st != 0:
+            raise RuntimeError(f"tscd_b200 stage reported error {st} (capacity exceeded: per-frame NMS candidates > 4096 "
+                               "or proposals > configured maximum)")
+        det_n, ori_n = out["det_count"].cpu().tolist(), out["ori_count"].cpu().tolist()
+        det_c = out["det_cand"].cpu().tolist()
+        result, result_ori = [], []
+        for i in range(B * Lf):
+            if det_c[i] == 0:                      # post_process.py:54-55: `continue` skips both outputs
+                result.append(None)
+                result_ori.append(None)
+                continue
+            result.append(out["det_rows"][i, :det_n[i]].clone())
+            result_ori.append(out["ori_rows"][i, :ori_n[i]].clone())
+        return result, result_ori
