@@ -13,7 +13,9 @@ from typing import Dict, List, Optional
 import torch
 
 from . import _lib as L
-from . import aggregate, ops, selection
+from . import aggregate, ops
+from . import selection as _selection
+from .selection import SelectionConfig
 
 
 def _r128(x: int) -> int:
@@ -23,7 +25,7 @@ def _r128(x: int) -> int:
 @dataclass
 class StageConfig:
     num_classes: int
-    selection: selection.SelectionConfig = field(default_factory=selection.SelectionConfig)
+    selection: SelectionConfig = field(default_factory=SelectionConfig)
     dim: int = 256                    # int(256 * width); the kernels are specialised for 256 (TSCD-L)
     heads: int = 4
     sim_thresh: float = 0.75          # TSCDHead ctor `sim_thresh`
@@ -102,7 +104,7 @@ class AggregationStage:
         status = torch.zeros(1, dtype=torch.int32, device=dev)
 
         # ---- K1-K3: selection + bank ------------------------------------------------------------------
-        sel = selection.select_and_gather(head, feats, feat_dtype, D, cfg.selection, bank_dtype=dt, status=status)
+        sel = _selection.select_and_gather(head, feats, feat_dtype, D, cfg.selection, bank_dtype=dt, status=status)
         # operand arrays are read in 128-row TMA boxes: pad the banks
         row_cap = _r128(B * F * kmax) + 128
         loc_cap = _r128(B * Lf * kmax)
