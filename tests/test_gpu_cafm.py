@@ -1,0 +1,70 @@
+"""GPU parity of K5 (CAFM) in isolation: the chain kernel gets the ORACLE's fp32 matching embeddings, so the
+cost matrices agree to fp32 rounding and the device LSAP must reproduce scipy's assignment exactly, for ragged
+frames (n_prev <, ==, > n_cur, empty frames) and with resume across calls."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("counts_calls", [
+    [[[18, 18, 24], [30, 12, 30]], [[16, 29, 17], [5, 40, 0]]],       # two clips, two consecutive calls
+    [[[0, 9, 33], [1, 1, 2]]],                                            # empty first frame, tiny frames
+])
+def test_cafm_chain_exact_assignments(counts_calls):
+    from tscd_b200 import aggregate, ops, selection, stage
+    dtype, D, C = torch.float16, 256, 5
+    sd = oracle.init_stage_weights(C, dim=D, seed=23)
+    sd16 = {k: (v.to(dtype).float() if v.dim() == 2 and "CA.fc" not in k else v.clone()) for k, v in sd.items()}
+    cfg = stage.StageConfig(num_classes=C, selection=selection.SelectionConfig(mode="B", maximal_limit=40), dtype=dtype)
+    st = stage.AggregationStage(cfg, sd)
+    B, Lf = len(counts_calls[0]), len(counts_calls[0][0])
+    F = Lf + 1
+    kmax = 40
+    state = stage.CAFMState(B, kmax, D)
+    o_state = [None] * B
+    g = torch.Generator().manual_seed(4)
+    for call, counts in enumerate(counts_calls):
+        per_frame = []
+        for b in range(B):
+            per_frame += counts[b] + [3]                                 # one global frame per clip (unused by CAFM)
+        N = sum(per_frame)
+        row_cap = ((N + 127) // 128 + 1) * 128
+        loc_total = sum(sum(c) for c in counts)
+        loc_cap = max(128, ((loc_total + 127) // 128) * 128)
+        cnt = torch.tensor(per_frame, dtype=torch.int32).cuda()
+        lay = aggregate.make_layout(cnt, B, F, Lf, row_cap, loc_cap, 128 * ((F * kmax + 127) // 128), dtype)
+        feat = torch.randn(N, D, generator=g).to(dtype)
+        edge = torch.randn(N, D, generator=g).to(dtype)
+        base = torch.randn(12, 4 * D, generator=g)                      # shared objects -> meaningful matching
+        emb_r = torch.zeros(loc_cap, 4 * D)
+        emb_c = torch.zeros(loc_cap, 4 * D)
+        emb_r[:loc_total] = base[torch.randint(0, 12, (loc_total,), generator=g)] + 0.5 * torch.randn(loc_total, 4 * D, generator=g)
+        emb_c[:loc_total] = base[torch.randint(0, 12, (loc_total,), generator=g)] + 0.5 * torch.randn(loc_total, 4 * D, generator=g)
+        te = torch.cat([oracle.timing_signal_1d(torch.arange(call * Lf, (call + 1) * Lf), 256) for _ in range(B)], 0)
+        bank_reg = torch.zeros(row_cap, D, dtype=dtype).cuda(); bank_reg[:N] = feat.cuda()
+        bank_edge = torch.zeros(row_cap, D, dtype=dtype).cuda(); bank_edge[:N] = edge.cuda()
+        status = torch.zeros(1, dtype=torch.int32).cuda()
+        resume = torch.full((B,), int(call > 0), dtype=torch.int32).cuda()
+        c16, c32, perm, _ = st.run_cafm(lay, bank_reg, bank_edge, emb_r.cuda(), emb_c.cuda(), te, kmax, state, resume, status,
+                                        want_debug=True)
+        torch.cuda.synchronize()
+        assert int(status.item()) == 0
+        off = np.concatenate([[0], np.cumsum(per_frame)])
+        lpos = 0
+        for b in range(B):
+            rows = np.concatenate([np.arange(off[b * F + f], off[b * F + f + 1]) for f in range(Lf)]).astype(np.int64)
+            nl = len(rows)
+            dbg = {}
+            want, o_state[b] = oracle.aware_position_reg_matcher(
+                sd16, "local_reg_matcher.", feat[rows].float(), emb_r[lpos:lpos + nl], emb_c[lpos:lpos + nl], edge[rows].float(),
+                counts[b], te.to(dtype).float()[b * Lf:(b + 1) * Lf], resume=(call > 0), state=o_state[b], debug=dbg)
+            o_perm = np.concatenate(dbg["perm"]) if "perm" in dbg else np.zeros(0, dtype=np.int64)
+            assert perm[lpos:lpos + nl].cpu().numpy().tolist() == o_perm.tolist(), f"call {call} clip {b}"
+            if want is not None:
+                err = float((c32[lpos:lpos + nl].cpu() - want).abs().max() / want.abs().max())
+                assert err < 2e-3, f"call {call} clip {b}: {err}"
+            lpos += nl

@@ -131,36 +131,13 @@ class AggregationStage:
             sim_thresh=cfg.sim_thresh, conf_sim_thresh=cfg.conf_sim_thresh)
 
         # ---- K5: CAFM --------------------------------------------------------------------------------
-        te16 = time_embedding.to(device=dev, dtype=dt).contiguous()
-        assert te16.shape == (B * Lf, 256)
-        _, te32 = ops.linear(te16, w.ape_w, w.ape_b, want16=False, want32=True)
-        f32z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
-        feat, edge, kin = f32z(loc_cap, D), f32z(loc_cap, D), f32z(loc_cap, D)
-        feat16 = torch.zeros(loc_cap, D, dtype=dt, device=dev)
-        kin16 = torch.zeros(loc_cap, D, dtype=dt, device=dev)
-        norm_reg, norm_cls = f32z(loc_cap), f32z(loc_cap)
-        ops.call("tscd_cafm_prep", L.CafmPrepArgs, B=B, F=F, L=Lf, D=D, bank_dtype=dt, row_off=lay.row_off,
-                 lrow_off=lay.lrow_off, bank_reg=bank_reg, bank_edge=bank_edge, time_emb=te32, se_w1=w.se_w1,
-                 se_w2=w.se_w2, emb_reg=iou_reg32, emb_cls=iou_cls32, feat=feat, edge=edge, feat16=feat16,
-                 kin16=kin16, kin=kin, norm_reg=norm_reg, norm_cls=norm_cls)
-        _, kproj = ops.linear(kin16, w.cafm_wk, m_dev=n_loc_dev, want16=False, want32=True)
-        _, vproj = ops.linear(feat16, w.cafm_wv, m_dev=n_loc_dev, want16=False, want32=True)
         if state is None:
             state = CAFMState(B, kmax, D, dev)
-        assert state.slots == B and state.kmax == kmax
         if resume is None:
             resume = torch.zeros(B, dtype=torch.int32, device=dev)
-        cafm16 = torch.zeros(loc_cap, D, dtype=dt, device=dev)
-        cafm32 = f32z(loc_cap, D) if trace is not None else None
-        perm = torch.zeros(loc_cap, dtype=torch.int32, device=dev) if trace is not None else None
-        ops.call("tscd_cafm_chain", L.CafmChainArgs, B=B, F=F, L=Lf, D=D, kmax=kmax, out_dtype=dt, row_off=lay.row_off,
-                 lrow_off=lay.lrow_off, resume=resume, feat=feat, edge=edge, kin=kin, kproj=kproj, vproj=vproj,
-                 time_emb=te32, emb_reg=iou_reg32, emb_cls=iou_cls32, norm_reg=norm_reg, norm_cls=norm_cls,
-                 wq_t=w.cafm_wq_t, se_w1=w.se_w1, se_w2=w.se_w2, ln_w=w.cafm_ln_w, ln_b=w.cafm_ln_b,
-                 dec_w=w.cafm_dec_w, dec_b=w.cafm_dec_b, st_n=state.n, st_out=state.out, st_edge=state.edge,
-                 st_reg=state.reg, st_cls=state.cls, st_nreg=state.nreg, st_ncls=state.ncls, st_time=state.time,
-                 sc_qin=f32z(B, kmax, D), sc_q=f32z(B, kmax, D), sc_k=f32z(B, kmax, D), sc_cost=f32z(B, kmax, kmax),
-                 out16=cafm16, out32=cafm32, perm=perm, status=status)
+        cafm16, cafm32, perm, te32 = self.run_cafm(lay, bank_reg, bank_edge, iou_reg32, iou_cls32, time_embedding, kmax,
+                                                   state, resume, status, want_debug=trace is not None)
+        f32z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
 
         # ---- fc_reg_matcher, TaskAligned, prediction heads ---------------------------------------------
         matched16, matched32 = ops.linear(cafm16, w.fc_w, w.fc_b, m_dev=n_loc_dev, want16=True, want32=trace is not None)
@@ -203,8 +180,44 @@ class AggregationStage:
         if trace is not None:
             trace.update(agg_cls=agg_cls32, iou_cls=iou_cls32, iou_reg=iou_reg32, cafm=cafm32, perm=perm, matched=matched32,
                          obj_ref=objref32, cls_logits=cls_logits, obj_logits=obj_logits, reg_deltas=reg_deltas,
-                         time_emb=te32, kproj=kproj, vproj=vproj, kin=kin, att=att)
+                         time_emb=te32, att=att)
         return out
+
+    # ------------------------------------------------------------------------------------------------------
+    def run_cafm(self, lay: ops.AttnLayoutT, bank_reg, bank_edge, emb_reg32, emb_cls32, time_embedding, kmax: int,
+                 state: CAFMState, resume: torch.Tensor, status: torch.Tensor, want_debug=False):
+        """CAFM (AwarePositionRegMatcher.forward, tscd_matching.py:722-888) for all clips of the batch.
+        emb_reg32 / emb_cls32 [loc_cap,1024] are the agg_iou outputs used for matching only."""
+        w, dev, dt, D = self.w, self.device, self.cfg.dtype, self.cfg.dim
+        B, F, Lf, loc_cap = lay.B, lay.F, lay.L, lay.loc_cap
+        n_loc_dev = lay.lrow_off[-1:]
+        te16 = time_embedding.to(device=dev, dtype=dt).contiguous()
+        assert te16.shape == (B * Lf, 256)
+        assert state.slots == B and state.kmax == kmax
+        _, te32 = ops.linear(te16, w.ape_w, w.ape_b, want16=False, want32=True)
+        f32z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
+        feat, edge, kin = f32z(loc_cap, D), f32z(loc_cap, D), f32z(loc_cap, D)
+        feat16 = torch.zeros(loc_cap, D, dtype=dt, device=dev)
+        kin16 = torch.zeros(loc_cap, D, dtype=dt, device=dev)
+        norm_reg, norm_cls = f32z(loc_cap), f32z(loc_cap)
+        ops.call("tscd_cafm_prep", L.CafmPrepArgs, B=B, F=F, L=Lf, D=D, bank_dtype=dt, row_off=lay.row_off,
+                 lrow_off=lay.lrow_off, bank_reg=bank_reg, bank_edge=bank_edge, time_emb=te32, se_w1=w.se_w1,
+                 se_w2=w.se_w2, emb_reg=emb_reg32, emb_cls=emb_cls32, feat=feat, edge=edge, feat16=feat16,
+                 kin16=kin16, kin=kin, norm_reg=norm_reg, norm_cls=norm_cls)
+        _, kproj = ops.linear(kin16, w.cafm_wk, m_dev=n_loc_dev, want16=False, want32=True)
+        _, vproj = ops.linear(feat16, w.cafm_wv, m_dev=n_loc_dev, want16=False, want32=True)
+        cafm16 = torch.zeros(loc_cap, D, dtype=dt, device=dev)
+        cafm32 = f32z(loc_cap, D) if want_debug else None
+        perm = torch.zeros(loc_cap, dtype=torch.int32, device=dev) if want_debug else None
+        ops.call("tscd_cafm_chain", L.CafmChainArgs, B=B, F=F, L=Lf, D=D, kmax=kmax, out_dtype=dt, row_off=lay.row_off,
+                 lrow_off=lay.lrow_off, resume=resume, feat=feat, edge=edge, kin=kin, kproj=kproj, vproj=vproj,
+                 time_emb=te32, emb_reg=emb_reg32, emb_cls=emb_cls32, norm_reg=norm_reg, norm_cls=norm_cls,
+                 wq_t=w.cafm_wq_t, se_w1=w.se_w1, se_w2=w.se_w2, ln_w=w.cafm_ln_w, ln_b=w.cafm_ln_b,
+                 dec_w=w.cafm_dec_w, dec_b=w.cafm_dec_b, st_n=state.n, st_out=state.out, st_edge=state.edge,
+                 st_reg=state.reg, st_cls=state.cls, st_nreg=state.nreg, st_ncls=state.ncls, st_time=state.time,
+                 sc_qin=f32z(B, kmax, D), sc_q=f32z(B, kmax, D), sc_k=f32z(B, kmax, D), sc_cost=f32z(B, kmax, kmax),
+                 out16=cafm16, out32=cafm32, perm=perm, status=status)
+        return cafm16, cafm32, perm, te32
 
     # ------------------------------------------------------------------------------------------------------
     @staticmethod
