@@ -161,6 +161,37 @@ def lib():
     return _lib
 
 
+# kernels launched per C-ABI call (for the bench's `gpu_launches` claim)
+KERNELS_PER_CALL = {"tscd_gather": 2}
+launch_count = 0
+# optional per-entry-point CUDA-event timing: {"names": set or None (= all), "events": {name: [(start, end), ...]}}
+profile = None
+
+
 def check(rc, what):
+    global launch_count
     if rc != 0:
         raise RuntimeError(f"{what} failed: {_ERR.get(rc, rc)} (code {rc})")
+    launch_count += KERNELS_PER_CALL.get(what, 1)
+
+
+class timed:
+    """Context manager: brackets one C-ABI call with CUDA events on the current stream when profiling is on."""
+
+    def __init__(self, name):
+        self.name = name
+        self.on = profile is not None and (profile["names"] is None or name in profile["names"])
+
+    def __enter__(self):
+        if self.on:
+            import torch
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.e.record()
+            profile["events"].setdefault(self.name, []).append((self.s, self.e))
+        return False

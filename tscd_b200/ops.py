@@ -118,7 +118,8 @@ def select(head: HeadViews, mode: str, pre_k: int = 750, conf_thresh: float = 0.
     a.anchors, a.reg, a.obj, a.cls = head.anchors.to_c(), head.reg, head.obj, head.cls
     a.cand_idx, a.cand_box, a.cand_score = _p(out["idx"]), _p(out["box"]), _p(out["score"])
     a.cand_cls, a.cand_count = _p(out["cls"]), _p(out["count"])
-    L.check(L.lib().tscd_select(C.byref(a), _stream()), "tscd_select")
+    with L.timed("tscd_select"):
+        L.check(L.lib().tscd_select(C.byref(a), _stream()), "tscd_select")
     return out
 
 
@@ -135,7 +136,8 @@ def nms(box: torch.Tensor, score: torch.Tensor, cls: torch.Tensor, count: torch.
     a.num_frames, a.cand_cap, a.max_keep, a.iou_thresh = Fn, cap, max_keep, iou_thresh
     a.box, a.score, a.cls, a.count = _p(box), _p(score), _p(cls), _p(count)
     a.keep, a.keep_count, a.status = _p(keep), _p(keep_count), _p(status)
-    L.check(L.lib().tscd_nms(C.byref(a), _stream()), "tscd_nms")
+    with L.timed("tscd_nms"):
+        L.check(L.lib().tscd_nms(C.byref(a), _stream()), "tscd_nms")
     return keep, keep_count, status
 
 
@@ -169,7 +171,8 @@ def gather(head: HeadViews, feats, feat_dtype: torch.dtype, feat_dim: int, cand,
     for k in ("sel_count", "row_off", "sel_idx", "sel_rows", "bank_cls", "bank_reg", "bank_edge", "bank_score",
               "bank_fg", "bank_box"):
         setattr(a, k, _p(out[k]))
-    L.check(L.lib().tscd_gather(C.byref(a), _stream()), "tscd_gather")
+    with L.timed("tscd_gather"):
+        L.check(L.lib().tscd_gather(C.byref(a), _stream()), "tscd_gather")
     return out
 
 
@@ -194,7 +197,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     a.out32, a.ld32 = _p(out32), (0 if out32 is None else out32.stride(0))
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous()
-    L.check(L.lib().tscd_linear(C.byref(a), _stream()), "tscd_linear")
+    with L.timed("tscd_linear"):
+        L.check(L.lib().tscd_linear(C.byref(a), _stream()), "tscd_linear")
     return out16, out32
 
 
@@ -239,7 +243,8 @@ def attn_prep(lay: AttnLayoutT, qkv_cls, qkv_reg, key_score, xori_cls=None, xori
         setattr(a, n, _p(bufs[n]))
     a.xori_cls, a.xori_reg = _p(xori_cls), _p(xori_reg)
     a.ld_xori = 0 if xori_cls is None else xori_cls.stride(0)
-    L.check(L.lib().tscd_attn_prep(C.byref(a), _stream()), "tscd_attn_prep")
+    with L.timed("tscd_attn_prep"):
+        L.check(L.lib().tscd_attn_prep(C.byref(a), _stream()), "tscd_attn_prep")
     return bufs
 
 
@@ -250,7 +255,8 @@ def attn_pv(lay: AttnLayoutT, bufs, x_cls, x_reg, stats, need_reg=True):
         setattr(a, n, _p(bufs[n]))
     a.need_reg = int(need_reg)
     a.x_cls, a.x_reg, a.ld_x, a.stats = _p(x_cls), _p(x_reg), x_cls.stride(0), _p(stats)
-    L.check(L.lib().tscd_attn_pv(C.byref(a), _stream()), "tscd_attn_pv")
+    with L.timed("tscd_attn_pv"):
+        L.check(L.lib().tscd_attn_pv(C.byref(a), _stream()), "tscd_attn_pv")
 
 
 def attn_round2(lay: AttnLayoutT, bufs, vt, stats, out, use_obj_mask, sim_thresh=0.75, conf_sim_thresh=0.99):
@@ -261,7 +267,8 @@ def attn_round2(lay: AttnLayoutT, bufs, vt, stats, out, use_obj_mask, sim_thresh
     a.vt, a.stats, a.use_obj_mask = _p(vt), _p(stats), int(use_obj_mask)
     a.sim_thresh, a.conf_sim_thresh = sim_thresh, conf_sim_thresh
     a.out, a.ld_out = _p(out), out.stride(0)
-    L.check(L.lib().tscd_attn_round2(C.byref(a), _stream()), "tscd_attn_round2")
+    with L.timed("tscd_attn_round2"):
+        L.check(L.lib().tscd_attn_round2(C.byref(a), _stream()), "tscd_attn_round2")
 
 
 # ----------------------------------------------------------------------------------------------- generic call helper
@@ -276,4 +283,5 @@ def call(name: str, struct_cls, **kw):
         setattr(a, k, v)
     missing = {f[0] for f in struct_cls._fields_} - set(kw)
     assert not missing, f"{name}: missing {missing}"
-    L.check(getattr(L.lib(), name)(C.byref(a), _stream()), name)
+    with L.timed(name):
+        L.check(getattr(L.lib(), name)(C.byref(a), _stream()), name)
