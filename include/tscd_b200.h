@@ -375,6 +375,7 @@ int tscd_final_rows(const tscd_final_rows_args* args, void* stream);
 
 /* Library / build information (also proves the .so was loaded). */
 const char* tscd_version(void);
+const char* tscd_last_cuda_error(void); /* text of the last CUDA runtime error seen by a TSCD_ERR_CUDA return */
 int tscd_device_ok(void); /* 1 if the current device is compute capability 10.x */
 
 #ifdef __cplusplus

@@ -128,6 +128,7 @@ _lib = None
 SYMBOLS = [
     ("tscd_version", C.c_char_p, []),
     ("tscd_device_ok", C.c_int, []),
+    ("tscd_last_cuda_error", C.c_char_p, []),
     ("tscd_select", C.c_int, [C.POINTER(SelectArgs), C.c_void_p]),
     ("tscd_nms", C.c_int, [C.POINTER(NmsArgs), C.c_void_p]),
     ("tscd_gather", C.c_int, [C.POINTER(GatherArgs), C.c_void_p]),
@@ -162,6 +163,7 @@ def lib():
 
 
 # kernels launched per C-ABI call (for the bench's `gpu_launches` claim)
+_DEBUG_SYNC = os.environ.get("TSCD_DEBUG_SYNC", "0") == "1"
 KERNELS_PER_CALL = {"tscd_gather": 2}
 launch_count = 0
 # optional per-entry-point CUDA-event timing: {"names": set or None (= all), "events": {name: [(start, end), ...]}}
@@ -171,8 +173,15 @@ profile = None
 def check(rc, what):
     global launch_count
     if rc != 0:
-        raise RuntimeError(f"{what} failed: {_ERR.get(rc, rc)} (code {rc})")
+        detail = lib().tscd_last_cuda_error().decode() if rc == -4 else ""
+        raise RuntimeError(f"{what} failed: {_ERR.get(rc, rc)} (code {rc}) {detail}")
     launch_count += KERNELS_PER_CALL.get(what, 1)
+    if _DEBUG_SYNC:                      # TSCD_DEBUG_SYNC=1: localise asynchronous kernel faults
+        import torch
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:           # noqa: BLE001
+            raise RuntimeError(f"{what}: asynchronous CUDA failure: {e}") from e
 
 
 class timed:

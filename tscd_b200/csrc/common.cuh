@@ -7,10 +7,14 @@
 
 #include "../../include/tscd_b200.h"
 
+extern "C" void tscd_set_last_cuda_error(int code, const char* where);
 #define TSCD_CUDA_CHECK_LAUNCH()                                   \
     do {                                                           \
         cudaError_t e__ = cudaGetLastError();                      \
-        if (e__ != cudaSuccess) return TSCD_ERR_CUDA;              \
+        if (e__ != cudaSuccess) {                                  \
+            tscd_set_last_cuda_error((int)e__, __FILE__);          \
+            return TSCD_ERR_CUDA;                                  \
+        }                                                          \
     } while (0)
 
 namespace tscd {
