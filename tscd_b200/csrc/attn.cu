@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_pv_kernel(const __grid_c
                     s_kf[j] = (k < ci.n_clip) ? (self_attn ? 0 : a.row_frame[ci.s0 + k]) : -1;
                 }
             }
-            mbar_wait(&bar_tma, ph_tma); ph_tma ^= 1;
+            mbar_wait(&bar_tma, ph_tma, 201); ph_tma ^= 1; __syncthreads();
             if (ctrl) {
                 tc_fence_after();
                 const uint64_t dqc = make_smem_desc_sw128(smem_u32(sQc)), dqr = make_smem_desc_sw128(smem_u32(sQr));
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_pv_kernel(const __grid_c
                 umma_commit(&bar_mma);
             }
             __syncthreads();  // s_kf visible
-            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
+            mbar_wait(&bar_mma, ph_mma, 202); ph_mma ^= 1; __syncthreads();
             tc_fence_after();
             if (is_epi) {
 #pragma unroll 1
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_pv_kernel(const __grid_c
                 const int k = kbase + row;
                 s_kf[row] = (k < ci.n_clip) ? (self_attn ? 0 : a.row_frame[ci.s0 + k]) : -1;
             }
-            mbar_wait(&bar_tma, ph_tma); ph_tma ^= 1;
+            mbar_wait(&bar_tma, ph_tma, 203); ph_tma ^= 1; __syncthreads();
             if (ctrl) {
                 tc_fence_after();
                 const uint64_t dqc = make_smem_desc_sw128(smem_u32(sQc)), dqr = make_smem_desc_sw128(smem_u32(sQr));
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_pv_kernel(const __grid_c
                 umma_commit(&bar_mma);
             }
             __syncthreads();
-            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
+            mbar_wait(&bar_mma, ph_mma, 204); ph_mma ^= 1; __syncthreads();
             tc_fence_after();
             if (is_epi) {
 #pragma unroll 1
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_pv_kernel(const __grid_c
                 }
                 umma_commit(&bar_mma);
             }
-            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
+            mbar_wait(&bar_mma, ph_mma, 205); ph_mma ^= 1; __syncthreads();
             tc_fence_after();
         }
         // head epilogue: x = (O_c / l_c + O_r / l_r) / 2
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_round2_kernel(const __gr
                     tma_load_2d(sB + at * 8192, br == 0 ? &tm.vn64c : &tm.vn64r, &bar_tma, at * 64, ci.s0 + kbase);
                 }
             }
-            mbar_wait(&bar_tma, ph_tma); ph_tma ^= 1;
+            mbar_wait(&bar_tma, ph_tma, 206); ph_tma ^= 1; __syncthreads();
             if (ctrl) {
                 tc_fence_after();
 #pragma unroll
@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_round2_kernel(const __gr
                 }
                 umma_commit(&bar_mma);
             }
-            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
+            mbar_wait(&bar_mma, ph_mma, 207); ph_mma ^= 1; __syncthreads();
             tc_fence_after();
         }
         if (is_epi && row < 64) {
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_round2_kernel(const __gr
                 tma_load_2d(sA + 32768, &tm.k64c, &bar_tma, h * 64, ci.s0 + kbase);
                 tma_load_2d(sA + 40960, &tm.k64r, &bar_tma, h * 64, ci.s0 + kbase);
             }
-            mbar_wait(&bar_tma, ph_tma); ph_tma ^= 1;
+            mbar_wait(&bar_tma, ph_tma, 208); ph_tma ^= 1; __syncthreads();
             if (ctrl) {
                 tc_fence_after();
                 const uint64_t dqc = make_smem_desc_sw128(smem_u32(sA)), dqr = make_smem_desc_sw128(smem_u32(sA + 16384));
@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_round2_kernel(const __gr
                 umma_commit(&bar_mma);
             }
             __syncthreads();  // s_kf visible (first head) / keeps the phases aligned
-            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
+            mbar_wait(&bar_mma, ph_mma, 209); ph_mma ^= 1; __syncthreads();
             tc_fence_after();
             if (is_epi) {
 #pragma unroll
@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_round2_kernel(const __gr
         }
         tc_fence_before();
         __syncthreads();
-        mbar_wait(&bar_tma, ph_tma); ph_tma ^= 1;
+        mbar_wait(&bar_tma, ph_tma, 210); ph_tma ^= 1; __syncthreads();
         if (ctrl) {
             tc_fence_after();
             const uint64_t dw = make_smem_desc_sw128(smem_u32(sW));
@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_round2_kernel(const __gr
             for (int k = 0; k < 4; ++k) umma_f16(tmem + 0, dw + 2 * k, dv + 2 * k, idesc256, (kt | k) ? 1u : 0u);
             umma_commit(&bar_mma);
         }
-        mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
+        mbar_wait(&bar_mma, ph_mma, 211); ph_mma ^= 1; __syncthreads();
         tc_fence_after();
     }
     // ---- U / den ----

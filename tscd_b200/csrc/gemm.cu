@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % kGemmStages;
                 const uint32_t ph = (kb / kGemmStages) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_wait(&empty_bar[s], ph ^ 1, 100 + s);
                 mbar_expect_tx(&full_bar[s], kABytes + kWBytes);
                 tma_load_2d(sA + s * kABytes, &tmap_a, &full_bar[s], kb * kGemmBK, m0);
                 tma_load_2d(sW + s * kWBytes, &tmap_w, &full_bar[s], kb * kGemmBK, n0);
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % kGemmStages;
                 const uint32_t ph = (kb / kGemmStages) & 1;
-                mbar_wait(&full_bar[s], ph);
+                mbar_wait(&full_bar[s], ph, 110 + s);
                 tc_fence_after();
                 const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + s * kABytes));
                 const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sW + s * kWBytes));
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
     } else {
         // epilogue warps 2..5 own TMEM lane quadrant (warp % 4)
         const int q = warp & 3;
-        mbar_wait(&tmem_full_bar, 0);
+        mbar_wait(&tmem_full_bar, 0, 120);
         tc_fence_after();
         const int row = m0 + q * 32 + lane;
         const bool row_ok = row < M;

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace tscd {
 namespace tc {
@@ -33,10 +34,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
-// Bounded wait: a protocol bug traps instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded wait: a protocol bug reports where it is stuck and traps instead of hanging the GPU.
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
+    return t;
+}
+static __device__ __noinline__ void mbar_timeout(int tag, uint32_t parity) {
+    printf("tscd_b200: mbarrier wait timed out (tag %d, parity %u, block %d,%d,%d, thread %d)\n", tag, parity, blockIdx.x,
+           blockIdx.y, blockIdx.z, threadIdx.x);
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
     const uint32_t addr = smem_u32(bar);
-    for (uint32_t it = 0; it < (1u << 26); ++it) {
+    uint64_t t0 = 0;
+    for (uint32_t it = 0;; ++it) {
         uint32_t done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -46,8 +58,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) return;
+        if ((it & 1023u) == 1023u) {
+            const uint64_t now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) mbar_timeout(tag, parity);   // 2 s
+        }
     }
-    __trap();
 }
 
 // ---- TMA --------------------------------------------------------------------------------------------
