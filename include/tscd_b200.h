@@ -236,6 +236,19 @@ typedef struct {
 } tscd_attn_round2_args;
 int tscd_attn_round2(const tscd_attn_round2_args* args, void* stream);
 
+/* Per-clip transpose of a 16-bit row-major matrix x[row_cap, width] (width multiple of 256) into
+ * xt[(b*width + c), key] (pitch nk_pitch), key = row - row_off[b*F]; pad keys are zero-filled up to the next
+ * multiple of 128.  Used by the gen-1 MSA, whose round 2 aggregates linear1's OUTPUT (MSA_yolov.find_similar_round2,
+ * post_trans.py:1238-1254) rather than the raw values. */
+typedef struct {
+    tscd_attn_layout lay;
+    int32_t width;
+    const void* x;
+    int32_t ld_x;
+    void* xt;
+} tscd_transpose_args;
+int tscd_transpose_clip(const tscd_transpose_args* args, void* stream);
+
 /* ---- K5: CAFM (AwarePositionRegMatcher) -------------------------------------------------------------------
  * Replaces AwarePositionRegMatcher.forward (tscd_matching.py:722-888) with its ReferringCrossAttentionLayer
  * (:566-589), SEModule (:278-283), PositionMHAttention (:31-60), double_match_embds (:912-937) and the scipy

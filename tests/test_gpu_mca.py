@@ -71,3 +71,36 @@ def test_mca_module_vs_oracle(clustered, dtype):
         assert _rel(o32[lpos:lpos + nl], to) < 1e-2, f"clip {b} obj"
         assert _rel(c16[lpos:lpos + nl], tc) < 1e-2
         lpos += nl
+
+
+def test_msa_yolov_self_attention_vs_oracle():
+    """Gen-1 MSA (north_star item 4): self-attention over all proposals of each clip, both softmax branches,
+    cosine masks, round 2 on linear1's output, linear2."""
+    from tscd_b200 import aggregate, ops
+    dtype = torch.float16
+    B, F = 2, 4
+    g = torch.Generator().manual_seed(21)
+    counts = [30, 30, 17, 30, 30, 30, 30, 9]
+    xc, xr, score = _make_case(B, F, F, counts, 9, True)
+    xc, xr = xc.to(dtype).float(), xr.to(dtype).float()
+    sd = oracle.init_stage_weights(25, dim=256, seed=5, gen1=True)
+    sd16 = {k: v.to(dtype).float() if v.dim() == 2 else v for k, v in sd.items()}
+    N = sum(counts)
+    row_cap = ((N + 127) // 128 + 1) * 128
+    cnt = torch.tensor(counts, dtype=torch.int32).cuda()
+    lay = aggregate.make_layout(cnt, B, F, F, row_cap, row_cap, 128, dtype)
+    lay.self_attn = True
+    lay.lrow_off = lay.row_off
+    bank_c = torch.zeros(row_cap, 256, dtype=dtype).cuda(); bank_c[:N] = xc.to(dtype).cuda()
+    bank_r = torch.zeros(row_cap, 256, dtype=dtype).cuda(); bank_r[:N] = xr.to(dtype).cuda()
+    bscore = torch.zeros(row_cap).cuda(); bscore[:N] = score.cuda()
+    n_dev = torch.tensor([N], dtype=torch.int32).cuda()
+    w = aggregate.MSAWeights(sd, "trans.", dtype)
+    o16, o32 = aggregate.msa_forward(lay, w, bank_c, bank_r, bscore, n_dev)
+    torch.cuda.synchronize()
+    off = 0
+    for b in range(B):
+        n = sum(counts[b * F:(b + 1) * F])
+        want, _ = oracle.msa_yolov(sd16, "trans.", xc[off:off + n].unsqueeze(0), xr[off:off + n].unsqueeze(0), score[off:off + n])
+        assert _rel(o32[off:off + n], want) < 1e-2, f"clip {b}"
+        off += n

@@ -199,3 +199,46 @@ def test_empty_frames_and_small_anchor_sets():
     sel, rows, idxs, _ = _run(decoded, hw, C, dict(mode="A", pre_k=750, top_k=30), apply_decode=False)
     for f in range(3):
         assert idxs[f].cpu().tolist() == o_idx[f].tolist()
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16])
+@pytest.mark.parametrize("mode", ["A", "B"])
+def test_selection_seam_s1_raw_level_outputs(dt, mode):
+    """Production seam S1: raw per-level NCHW logits; sigmoid + decode fused into the kernels.  The oracle gets
+    sigmoid/exp from torch-CPU, so a 1-ulp difference may swap exact near-ties: require >= 99.5 % identical ids."""
+    ops, selection = _stage_mods()
+    hw = [(72, 72), (36, 36), (18, 18)]
+    C, Fn = 25, 4
+    g = torch.Generator().manual_seed(31)
+    reg, obj, cls, fused = [], [], [], []
+    for (h, w) in hw:
+        xy = torch.rand(Fn, 2, h, w, generator=g) * 2 - 0.5
+        wh = torch.randn(Fn, 2, h, w, generator=g) * 0.7 + 1.0
+        r = torch.cat([xy, wh], 1).to(dt)
+        o = (torch.randn(Fn, 1, h, w, generator=g) * 2 - (3 if mode == "A" else 7)).to(dt)
+        c = (torch.randn(Fn, C, h, w, generator=g) * 2 - 3).to(dt)
+        reg.append(r); obj.append(o); cls.append(c)
+        fused.append(torch.cat([r.float(), o.float().sigmoid(), c.float().sigmoid()], 1).flatten(2))
+    head_out = torch.cat(fused, 2).permute(0, 2, 1).contiguous()            # tscd_head.py:374-376
+    decoded = oracle.decode_outputs(head_out, hw, [8, 16, 32])
+    if mode == "A":
+        o_rows, o_idx = oracle.select_mode_a(decoded, C, pre_k=750, top_k=30)
+        cfg = selection.SelectionConfig(mode="A", pre_k=750, top_k=30)
+    else:
+        o_rows, o_idx = oracle.select_mode_b(decoded, C, minimal_limit=50, maximal_limit=500, use_pre_nms=False)
+        cfg = selection.SelectionConfig(mode="B", minimal_limit=50, maximal_limit=500, use_pre_nms=False)
+    an = ops.AnchorSpec(hw)
+    head = ops.HeadViews.from_levels([t.cuda() for t in reg], [t.cuda() for t in obj], [t.cuda() for t in cls], an)
+    feats = [[torch.randn(Fn, 32, h, w).cuda() for (h, w) in hw] for _ in range(3)]
+    sel = selection.select_and_gather(head, tuple(ops.view_levels(f) for f in feats), torch.float32, 32, cfg,
+                                      bank_dtype=torch.float32)
+    torch.cuda.synchronize()
+    rows, idxs = selection.to_lists(sel)
+    same = tot = 0
+    for f in range(Fn):
+        got, want = idxs[f].cpu().tolist(), o_idx[f].tolist()
+        tot += len(want)
+        same += len(set(got) & set(want))
+        if got == want:
+            torch.testing.assert_close(rows[f].cpu(), o_rows[f], rtol=1e-5, atol=1e-4)
+    assert same / tot >= 0.995, (same, tot)

@@ -85,6 +85,10 @@ class AttnRound2Args(C.Structure):
                 ("sim_thresh", C.c_float), ("conf_sim_thresh", C.c_float), ("out", C.c_void_p), ("ld_out", C.c_int32)]
 
 
+class TransposeArgs(C.Structure):
+    _fields_ = [("lay", AttnLayout), ("width", C.c_int32), ("x", C.c_void_p), ("ld_x", C.c_int32), ("xt", C.c_void_p)]
+
+
 def _fields(spec):
     """'name:type' list -> ctypes fields; types: i=int32, f=float, p=pointer."""
     m = {"i": C.c_int32, "f": C.c_float, "p": C.c_void_p}
@@ -136,6 +140,7 @@ SYMBOLS = [
     ("tscd_attn_prep", C.c_int, [C.POINTER(AttnPrepArgs), C.c_void_p]),
     ("tscd_attn_pv", C.c_int, [C.POINTER(AttnPvArgs), C.c_void_p]),
     ("tscd_attn_round2", C.c_int, [C.POINTER(AttnRound2Args), C.c_void_p]),
+    ("tscd_transpose_clip", C.c_int, [C.POINTER(TransposeArgs), C.c_void_p]),
     ("tscd_cafm_prep", C.c_int, [C.POINTER(CafmPrepArgs), C.c_void_p]),
     ("tscd_cafm_chain", C.c_int, [C.POINTER(CafmChainArgs), C.c_void_p]),
     ("tscd_frame_attention", C.c_int, [C.POINTER(FrameAttentionArgs), C.c_void_p]),

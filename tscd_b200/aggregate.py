@@ -72,3 +72,41 @@ def mca_forward(lay: ops.AttnLayoutT, w: MCAWeights, bank_cls, bank_reg, bank_sc
     if debug is not None:
         debug.update(qkv_c=qkv_c, qkv_r=qkv_r, bufs=bufs, tmp_c=tmp_c, tmp_r=tmp_r, stats=stats, cat_c=cat_c, cat_r=cat_r)
     return (trans_cls16, trans_cls32), (trans_obj16, trans_obj32)
+
+
+# ----------------------------------------------------------------------------------------------- gen-1 MSA
+class MSAWeights:
+    """MSA_yolov parameters (post_trans.py:1227-1236): msa.qkv_cls / msa.qkv_reg, linear1, linear2."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, dtype=torch.float16, device="cuda"):
+        w = lambda n: sd[prefix + n].detach().to(device=device, dtype=dtype).contiguous()          # noqa: E731
+        b = lambda n: sd[prefix + n].detach().to(device=device, dtype=torch.float32).contiguous()  # noqa: E731
+        self.qkv_cls, self.qkv_reg = w("msa.qkv_cls.weight"), w("msa.qkv_reg.weight")               # [768,256]: q|k|v
+        self.l1_w, self.l1_b = w("linear1.weight"), b("linear1.bias")
+        self.l2_w, self.l2_b = w("linear2.weight"), b("linear2.bias")
+
+
+def msa_forward(lay: ops.AttnLayoutT, w: MSAWeights, bank_cls, bank_reg, bank_score, n_rows_dev,
+                sim_thresh=0.75, conf_sim_thresh=0.99):
+    """MSA_yolov.forward (post_trans.py:1256-1269; gen-1 self-attention over ALL proposals of a clip, reconf off).
+    `lay` must be a self-attention layout (L == F, lrow_off is row_off).  Returns (out16, out32) [row_cap, 1024]."""
+    assert lay.self_attn and lay.L == lay.F
+    dev, dt, cap = bank_cls.device, lay.dtype, lay.row_cap
+    qkv_c, _ = ops.linear(bank_cls, w.qkv_cls, m_dev=n_rows_dev)
+    qkv_r, _ = ops.linear(bank_reg, w.qkv_reg, m_dev=n_rows_dev)
+    tmp_c = torch.zeros(cap, 512, dtype=dt, device=dev)                  # [attn@v | v]
+    tmp_r = torch.zeros(cap, 512, dtype=dt, device=dev)
+    bufs = ops.attn_prep(lay, qkv_c, qkv_r, bank_score, xori_cls=tmp_c[:, 256:], xori_reg=tmp_r[:, 256:])
+    stats = torch.zeros(cap, 16, dtype=torch.float32, device=dev)
+    ops.attn_pv(lay, bufs, tmp_c[:, :256], tmp_r[:, :256], stats, need_reg=False)
+    cat = torch.zeros(cap, 1024, dtype=dt, device=dev)                   # [round2 @ tc | tc]
+    ops.linear(tmp_c, w.l1_w, w.l1_b, m_dev=n_rows_dev, out16=cat[:, 512:], want16=False)
+    tct = torch.zeros(lay.B * 512, lay.nk_pitch, dtype=dt, device=dev)
+    ops.call("tscd_transpose_clip", ops.L.TransposeArgs, lay=lay.to_c(), width=512, x=cat[:, 512:], ld_x=cat.stride(0), xt=tct)
+    # round 2 aggregates linear1's output, 256 columns per launch; V^T rows of clip b start at b*512 (+256)
+    for half in range(2):
+        vt = tct.view(lay.B, 512, lay.nk_pitch)[:, half * 256:(half + 1) * 256]
+        vt = vt.contiguous().view(lay.B * 256, lay.nk_pitch)
+        ops.attn_round2(lay, bufs, vt, stats, cat[:, half * 256:(half + 1) * 256], use_obj_mask=False,
+                        sim_thresh=sim_thresh, conf_sim_thresh=conf_sim_thresh)
+    return ops.linear(cat, w.l2_w, w.l2_b, m_dev=n_rows_dev, want16=True, want32=True)

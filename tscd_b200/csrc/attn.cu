@@ -112,6 +112,28 @@ __global__ void __launch_bounds__(256) attn_prep_kernel(const tscd_attn_prep_arg
     }
 }
 
+// per-clip transpose (64 keys x 64 channels tiles through shared memory)
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_clip_kernel(const tscd_transpose_args a) {
+    __shared__ T tile[64][66];
+    const tscd_attn_layout& lay = a.lay;
+    const int b = blockIdx.z, k0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    const int s0 = lay.row_off[b * lay.F];
+    const int n_clip = lay.row_off[(b + 1) * lay.F] - s0;
+    const int n_pad = min((n_clip + 127) & ~127, lay.nk_pitch);
+    if (k0 >= n_pad) return;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    for (int r = ty; r < 64; r += 4) {
+        const int key = k0 + r;
+        T v = cvt_from_float<T>(0.f);
+        if (key < n_clip) v = reinterpret_cast<const T*>(a.x)[(int64_t)(s0 + key) * a.ld_x + c0 + tx];
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int c = ty; c < 64; c += 4)
+        reinterpret_cast<T*>(a.xt)[((int64_t)b * a.width + c0 + c) * lay.nk_pitch + k0 + tx] = tile[tx][c];
+}
+
 // -------------------------------------------------------------------------------------------------------
 // shared pieces of the two tensor-core kernels
 // -------------------------------------------------------------------------------------------------------
@@ -643,6 +665,17 @@ extern "C" int tscd_attn_prep(const tscd_attn_prep_args* a, void* stream) {
         if (cudaFuncSetAttribute(attn_prep_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
         attn_prep_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(*a);
     }
+    TSCD_CUDA_CHECK_LAUNCH();
+    return TSCD_OK;
+}
+
+extern "C" int tscd_transpose_clip(const tscd_transpose_args* a, void* stream) {
+    using namespace tscd;
+    if (!a || !layout_ok(a->lay) || a->width <= 0 || (a->width % 64) != 0) return TSCD_ERR_INVALID_ARG;
+    dim3 grid(a->lay.nk_pitch / 64, a->width / 64, a->lay.B);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (a->lay.dtype == TSCD_F16) transpose_clip_kernel<__half><<<grid, 256, 0, st>>>(*a);
+    else transpose_clip_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(*a);
     TSCD_CUDA_CHECK_LAUNCH();
     return TSCD_OK;
 }

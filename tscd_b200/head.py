@@ -1,0 +1,89 @@
+"""Drop-in head for the reference's own tools: `TSCDHeadB200` keeps TSCDHead's constructor, parameter names
+(strict `load_state_dict` of reference checkpoints works) and forward signature / return types,
+reuses the reference's conv towers unchanged (PyTorch/cuDNN, out of scope) and replaces ONLY the inference
+tail (yolox/models/tscd_head.py:374-733) by the sm_100a kernels of this package.
+
+The reference package (`yolox`) is not vendored: the class is created on demand by `make_head_class()` when
+`yolox.models.tscd_head.TSCDHead` is importable (i.e. inside a reference checkout), see INTEGRATION.md.
+Training mode and configurations the kernels do not cover raise loudly; there is no silent fallback."""
+from typing import List
+
+import torch
+
+from . import ops
+from .selection import SelectionConfig
+from .stage import AggregationStage, CAFMState, StageConfig
+from .weights import timing_signal_1d  # noqa: F401  (re-exported for callers that build time embeddings)
+
+_CONV_PREFIXES = ("stems", "cls_convs", "reg_convs", "edge_enhance", "cls_preds", "reg_preds", "obj_preds")
+
+
+def stage_config_from_head(head) -> StageConfig:
+    """Translate TSCDHead's ctor arguments / kwargs into a StageConfig; reject what is unsupported."""
+    kw = head.kwargs
+    if kw.get("agg_type", "localagg") != "mca" or not kw.get("decouple_reg", False) or not kw.get("reconf", False) \
+            or not kw.get("ota_mode", False):
+        raise RuntimeError("TSCDHeadB200 supports the TSCD configuration only: agg_type='mca', decouple_reg, reconf, ota_mode")
+    if kw.get("local_mask", False) or head.use_mask or not head.ave:
+        raise RuntimeError("TSCDHeadB200: local_mask / use_mask / ave=False are not implemented (not used by the TSCD exps)")
+    sel = SelectionConfig(mode="B", nms_thresh=head.nms_thresh, conf_thresh=0.001,
+                          minimal_limit=kw.get("minimal_limit", 0), maximal_limit=kw.get("maximal_limit", 0),
+                          use_pre_nms=kw.get("use_pre_nms", True))
+    return StageConfig(num_classes=head.num_classes, selection=sel, dim=head.width, heads=4, sim_thresh=head.sim_thresh,
+                       conf_sim_thresh=kw.get("conf_sim_thresh", 0.99))
+
+
+def make_head_class():
+    """Returns class TSCDHeadB200(TSCDHead).  Requires the reference's `yolox` package on sys.path."""
+    from yolox.models.tscd_head import TSCDHead  # reference checkout
+
+    class TSCDHeadB200(TSCDHead):
+        def __init__(self, *args, **kwargs):
+            super().__init__(*args, **kwargs)
+            self._b200_stage = None
+            self._b200_state = None
+
+        def _stage(self):
+            if self._b200_stage is None:
+                sd = {k: v for k, v in self.state_dict().items() if not k.startswith(_CONV_PREFIXES)}
+                self._b200_stage = AggregationStage(stage_config_from_head(self), sd, device=next(self.parameters()).device)
+            return self._b200_stage
+
+        def load_state_dict(self, *a, **k):
+            self._b200_stage = None          # weights changed: rebuild the 16-bit device copies lazily
+            return super().load_state_dict(*a, **k)
+
+        def forward(self, xin, labels=None, imgs=None, time_embedding=None, nms_thresh=0.5, lframe=0, gframe=32,
+                    resume=False):
+            if self.training:
+                raise RuntimeError("TSCDHeadB200 is inference-only (the training branches are out of scope)")
+            if imgs.shape[0] == 1:
+                return super().forward(xin, labels, imgs, time_embedding, nms_thresh, lframe, gframe, resume)
+            # ---- conv towers: the reference's own modules, channels_last so an anchor's 256 channels are contiguous ----
+            reg_o, obj_o, cls_o, f_cls, f_reg, f_edge = [], [], [], [], [], []
+            for k, x in enumerate(xin):
+                x = self.stems[k](x.contiguous(memory_format=torch.channels_last))
+                reg_feat, cls_feat = self.reg_convs[k](x), self.cls_convs[k](x)
+                vid_cls = self.cls_convs2[k](x) if self.kwargs.get("vid_cls", True) else cls_feat
+                vid_reg = self.reg_convs2[k](x) if self.kwargs.get("vid_reg", True) else reg_feat
+                reg_o.append(self.reg_preds[k](reg_feat)); obj_o.append(self.obj_preds[k](reg_feat))
+                cls_o.append(self.cls_preds[k](cls_feat))
+                f_cls.append(vid_cls); f_reg.append(vid_reg); f_edge.append(self.edge_enhance_reg[k](vid_reg))
+            hw = [tuple(t.shape[-2:]) for t in cls_o]
+            an = ops.AnchorSpec(hw, tuple(self.strides))
+            head = ops.HeadViews.from_levels(reg_o, obj_o, cls_o, an)
+            feats = tuple(ops.view_levels(f) for f in (f_cls, f_reg, f_edge))
+            st = self._stage()
+            st.cfg.final_nms_thresh = nms_thresh
+            F = imgs.shape[0]
+            kmax = st.cfg.selection.max_keep(an.num_anchors)
+            if self._b200_state is None or self._b200_state.kmax != kmax:
+                self._b200_state = CAFMState(1, kmax, st.cfg.dim, imgs.device)
+            res = torch.tensor([int(bool(resume))], dtype=torch.int32, device=imgs.device)
+            out = st.forward(head, feats, f_cls[0].dtype, time_embedding[:lframe].float(), 1, F, lframe,
+                             state=self._b200_state, resume=res)
+            result, result_ori = st.to_lists(out, 1, lframe)
+            dt = xin[0].dtype
+            return ([None if r is None else r.to(dt) for r in result], [None if r is None else r.to(dt) for r in result_ori])
+
+    return TSCDHeadB200

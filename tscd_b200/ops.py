@@ -276,7 +276,9 @@ def call(name: str, struct_cls, **kw):
     """Fill a ctypes argument struct from keyword arguments (tensors -> data_ptr) and call the C-ABI entry point."""
     a = struct_cls()
     for k, v in kw.items():
-        if isinstance(v, torch.Tensor) or v is None:
+        if isinstance(v, C.Structure):
+            pass
+        elif isinstance(v, torch.Tensor) or v is None:
             v = _p(v)
         elif isinstance(v, torch.dtype):
             v = _DT[v]
