@@ -20,6 +20,7 @@ namespace tscd {
 
 constexpr int kChainThreads = 512;
 constexpr int kChainMax = 512;
+constexpr int kCostSmem = 64 * 64;
 
 __device__ __forceinline__ float se_gate(float a, float b, const float* w1, const float* w2) {
     float o0 = 0.f, o1 = 0.f;
@@ -75,6 +76,7 @@ struct ChainSmem {
     float w1[64], w2[64];
     float tileA[32][129], tileB[32][129];
     float pbuf[kChainThreads / 32][kChainMax];
+    float cost_s[kCostSmem];          // matching cost kept on chip when n_prev * n_cur fits (the common case)
 };
 
 // Rectangular LSAP by warp 0.  C is the [n_prev x n_cur] cost (row-major, fp32).  Solves the problem with
@@ -94,34 +96,26 @@ __device__ void lap_warp(const float* C, int n_prev, int n_cur, ChainSmem& s, in
         while (sink == -1) {
             if (lane == 0) s.SR[i] = 1;
             const double ui = s.u[i];
+            // candidate key: (value, tb) ascending; tb encodes SciPy's tie rule -- among equal minima a column that is a
+            // new sink wins and the LAST such sink in scan order is taken, otherwise the FIRST minimum
             double best = INFINITY;
-            int best_it = -1;
-            int best_sink = 0;
+            unsigned best_tb = 0xffffffffu;
             for (int it = lane; it < num_rem; it += 32) {
                 const int j = s.remaining[it];
                 const double c = (double)(tr ? C[(int64_t)j * n_cur + i] : C[(int64_t)i * n_cur + j]);
                 const double r = min_val + c - ui - s.v[j];
                 if (r < s.spc[j]) { s.path[j] = i; s.spc[j] = r; }
                 const double sj = s.spc[j];
-                const int snk = s.row4col[j] == -1;
-                if (sj < best || (sj == best && snk)) { best = sj; best_it = it; best_sink = snk; }
+                const unsigned tb = (s.row4col[j] == -1) ? (unsigned)(kChainMax - 1 - it) : (0x10000u | (unsigned)it);
+                if (sj < best || (sj == best && tb < best_tb)) { best = sj; best_tb = tb; }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oit = __shfl_xor_sync(0xffffffffu, best_it, o);
-                const int os = __shfl_xor_sync(0xffffffffu, best_sink, o);
-                bool take = false;
-                if (oit >= 0) {
-                    if (best_it < 0 || ob < best) take = true;
-                    else if (ob == best) {
-                        if (os && !best_sink) take = true;
-                        else if (os && best_sink) take = oit > best_it;      // last sink among the ties
-                        else if (!os && !best_sink) take = oit < best_it;    // otherwise the first tie
-                    }
-                }
-                if (take) { best = ob; best_it = oit; best_sink = os; }
+                const unsigned otb = __shfl_xor_sync(0xffffffffu, best_tb, o);
+                if (ob < best || (ob == best && otb < best_tb)) { best = ob; best_tb = otb; }
             }
+            const int best_it = (best_tb == 0xffffffffu) ? -1 : ((best_tb & 0x10000u) ? (int)(best_tb & 0xffffu) : kChainMax - 1 - (int)best_tb);
             min_val = best;
             if (best_it < 0 || best == INFINITY) { sink = -2; break; }   // infeasible (cannot happen: finite costs)
             const int j = s.remaining[best_it];
@@ -212,6 +206,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
         const float* nRp = first ? nRc : st_nreg;
         const float* nCp = first ? nCc : st_ncls;
 
+        float* costm = (np * n <= kCostSmem) ? s.cost_s : cost;
         // ---- matching cost [np x n] ------------------------------------------------------------------
         for (int rb = 0; rb < np; rb += 32) {
             for (int cb = 0; cb < n; cb += 32) {
@@ -246,7 +241,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
                         const float cc = accC[k] / (nCp[r] * nCc[c]);
                         float v = 1.f - (cr + cc) / 2.f;
                         if (v != v) v = 0.f;
-                        cost[(int64_t)r * n + c] = v;
+                        costm[(int64_t)r * n + c] = v;
                     }
                 }
             }
@@ -254,7 +249,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
         __syncthreads();
         // ---- assignment -----------------------------------------------------------------------------
         if (warp == 0) {
-            lap_warp(cost, np, n, s, lane);
+            lap_warp(costm, np, n, s, lane);
             __syncwarp();
             if (lane == 0) {
                 if (np <= n) {
@@ -288,19 +283,22 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
             qin[t] = v;
         }
         __syncthreads();
-        // ---- q = W_q qin  (thread = output channel, 4 rows at a time) --------------------------------
+        // ---- q = W_q qin  (thread = output channel; each half of the CTA owns every other block of 16 rows,
+        //      so W_q^T is streamed from L2 once per 16 rows with coalesced loads) ------------------------
         {
             const int c = tid % D, g = tid / D, ng = kChainThreads / D;
-            for (int r0 = g * 4; r0 < n; r0 += ng * 4) {
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int r0 = g * 16; r0 < n; r0 += ng * 16) {
+                float acc[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll 4
                 for (int k = 0; k < D; ++k) {
                     const float w = __ldg(a.wq_t + (int64_t)k * D + c);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (r0 + i < n) acc[i] = fmaf(qin[(int64_t)(r0 + i) * D + k], w, acc[i]);
+                    for (int i = 0; i < 16; ++i) acc[i] = fmaf(qin[(int64_t)min(r0 + i, n - 1) * D + k], w, acc[i]);
                 }
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 16; ++i)
                     if (r0 + i < n) qv[(int64_t)(r0 + i) * D + c] = acc[i];
             }
         }
