@@ -283,6 +283,21 @@ typedef struct {
 } tscd_cafm_prep_args;
 int tscd_cafm_prep(const tscd_cafm_prep_args* args, void* stream);
 
+/* Matching costs of every local frame against its reference frame (the previous non-empty local frame in its
+ * ORIGINAL row order, the carried-over state when the clip resumes, or itself for a first frame), for all clips
+ * at once: cost[lf][r][c] = 1 - (cos_reg + cos_cls)/2 (tscd_matching.py:912-929), pitch kmax.  The chain kernel
+ * only re-indexes rows by the previous frame's assignment. */
+typedef struct {
+    int32_t B, L, D, kmax;
+    const int32_t* lrow_off;
+    const int32_t* resume;
+    const int32_t* st_n;
+    const float* emb_reg; const float* emb_cls; const float* norm_reg; const float* norm_cls;
+    const float* st_reg; const float* st_cls; const float* st_nreg; const float* st_ncls;
+    float* cost;                 /* [B*L, kmax, kmax] */
+} tscd_cafm_cost_args;
+int tscd_cafm_cost(const tscd_cafm_cost_args* args, void* stream);
+
 typedef struct {
     int32_t B, F, L, D, kmax;    /* kmax: capacity (rows per frame) of the state / scratch buffers, <= 512 */
     int32_t out_dtype;
@@ -320,6 +335,7 @@ typedef struct {
     float* sc_q;                 /* [B,kmax,D] */
     float* sc_k;                 /* [B,kmax,D] */
     float* sc_cost;              /* [B,kmax,kmax] */
+    const float* cost_full;      /* [B*L,kmax,kmax] from tscd_cafm_cost */
     /* outputs */
     void* out16;                 /* [loc_cap, D] CAFM output after decoder_norm, original row order */
     float* out32;                /* [loc_cap, D] same in fp32 (may be NULL) */

@@ -68,16 +68,89 @@ __global__ void __launch_bounds__(256) cafm_prep_kernel(const tscd_cafm_prep_arg
     }
 }
 
+constexpr int kSmall = 32;   // frames with <= kSmall proposals keep their whole working set in shared memory
+
 struct ChainSmem {
     double u[kChainMax], v[kChainMax], spc[kChainMax];
     int path[kChainMax], col4row[kChainMax], row4col[kChainMax], remaining[kChainMax];
-    int perm[kChainMax], prow[kChainMax];
+    int perm[kChainMax], prow[kChainMax], ord_prev[kChainMax];
     unsigned char SR[kChainMax], SC[kChainMax];
     float w1[64], w2[64];
-    float tileA[32][129], tileB[32][129];
     float pbuf[kChainThreads / 32][kChainMax];
     float cost_s[kCostSmem];          // matching cost kept on chip when n_prev * n_cur fits (the common case)
+    float x0[kSmall * 256];           // query input, then pre-norm output
+    float x1[kSmall * 256];           // q, then scratch for the decoder norm
+    float xk[kSmall * 256];           // normalised keys
+    float xv[kSmall * 256];           // values
 };
+
+// ---------------------------------------------------------------------------------------------- matching costs
+// One CTA per (local frame, 32x32 tile): 128-dim slabs of the two 1024-dim embeddings staged in shared memory.
+__global__ void __launch_bounds__(256) cafm_cost_kernel(const tscd_cafm_cost_args a) {
+    __shared__ float tileA[32][129], tileB[32][129];
+    const int lf = blockIdx.x, b = lf / a.L, f = lf - b * a.L;
+    const int l0 = a.lrow_off[lf], n = a.lrow_off[lf + 1] - l0;
+    if (n <= 0) return;
+    const int E = 4 * a.D, KM = a.kmax;
+    // reference side: previous non-empty local frame, else the carried state (resume), else the frame itself
+    const float *Rp = nullptr, *Cp = nullptr, *nRp = nullptr, *nCp = nullptr;
+    int np = 0;
+    for (int p = f - 1; p >= 0 && np == 0; --p) {
+        const int pl0 = a.lrow_off[b * a.L + p], pn = a.lrow_off[b * a.L + p + 1] - pl0;
+        if (pn > 0) { np = pn; Rp = a.emb_reg + (int64_t)pl0 * E; Cp = a.emb_cls + (int64_t)pl0 * E; nRp = a.norm_reg + pl0; nCp = a.norm_cls + pl0; }
+    }
+    if (np == 0) {
+        const int sn = (a.resume && a.resume[b]) ? a.st_n[b] : 0;
+        if (sn > 0) {
+            np = sn;
+            Rp = a.st_reg + (int64_t)b * KM * E; Cp = a.st_cls + (int64_t)b * KM * E;
+            nRp = a.st_nreg + (int64_t)b * KM; nCp = a.st_ncls + (int64_t)b * KM;
+        } else {
+            np = n;
+            Rp = a.emb_reg + (int64_t)l0 * E; Cp = a.emb_cls + (int64_t)l0 * E; nRp = a.norm_reg + l0; nCp = a.norm_cls + l0;
+        }
+    }
+    const int rb = blockIdx.y * 32, cb = blockIdx.z * 32;
+    if (rb >= np || cb >= n || np > KM || n > KM) return;
+    const float* Rc = a.emb_reg + (int64_t)l0 * E;
+    const float* Cc = a.emb_cls + (int64_t)l0 * E;
+    const int lane = threadIdx.x & 31, pr = threadIdx.x >> 5;   // pairs (pr + 8k, lane), k = 0..3
+    float accR[4] = {0.f, 0.f, 0.f, 0.f}, accC[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int which = 0; which < 2; ++which) {
+        const float* P = which == 0 ? Rp : Cp;
+        const float* Q = which == 0 ? Rc : Cc;
+        for (int d0 = 0; d0 < E; d0 += 128) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < 32 * 128; t += 256) {
+                const int rr = t >> 7, dd = t & 127;
+                tileA[rr][dd] = (rb + rr < np) ? P[(int64_t)(rb + rr) * E + d0 + dd] : 0.f;
+                tileB[rr][dd] = (cb + rr < n) ? Q[(int64_t)(cb + rr) * E + d0 + dd] : 0.f;
+            }
+            __syncthreads();
+            float x[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+            for (int dd = 0; dd < 128; ++dd) {
+                const float q = tileB[lane][dd];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) x[k] = fmaf(tileA[pr + 8 * k][dd], q, x[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { if (which == 0) accR[k] += x[k]; else accC[k] += x[k]; }
+        }
+    }
+    float* out = a.cost + (int64_t)lf * KM * KM;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = rb + pr + 8 * k, c = cb + lane;
+        if (r < np && c < n) {
+            const float cr = accR[k] / (nRp[r] * a.norm_reg[l0 + c]);
+            const float cc = accC[k] / (nCp[r] * a.norm_cls[l0 + c]);
+            float v = 1.f - (cr + cc) / 2.f;
+            if (v != v) v = 0.f;                    // tscd_matching.py:930 NaN -> 0
+            out[(int64_t)r * KM + c] = v;
+        }
+    }
+}
 
 // Rectangular LSAP by warp 0.  C is the [n_prev x n_cur] cost (row-major, fp32).  Solves the problem with
 // rows = the smaller side exactly like scipy (transposing when n_cur < n_prev).  Results in s.col4row / s.row4col.
@@ -169,18 +242,16 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
 
     float* st_out = a.st_out + (int64_t)b * KM * D;
     float* st_edge = a.st_edge + (int64_t)b * KM * D;
-    float* st_reg = a.st_reg + (int64_t)b * KM * E;
-    float* st_cls = a.st_cls + (int64_t)b * KM * E;
-    float* st_nreg = a.st_nreg + (int64_t)b * KM;
-    float* st_ncls = a.st_ncls + (int64_t)b * KM;
     float* st_time = a.st_time + (int64_t)b * D;
-    float* qin = a.sc_qin + (int64_t)b * KM * D;
-    float* qv = a.sc_q + (int64_t)b * KM * D;
-    float* kh = a.sc_k + (int64_t)b * KM * D;
-    float* cost = a.sc_cost + (int64_t)b * KM * KM;
+    float* g_qin = a.sc_qin + (int64_t)b * KM * D;
+    float* g_q = a.sc_q + (int64_t)b * KM * D;
+    float* g_k = a.sc_k + (int64_t)b * KM * D;
+    float* g_cost = a.sc_cost + (int64_t)b * KM * KM;
 
     const bool resume = a.resume ? (a.resume[b] != 0) : false;
     int n_prev = resume ? a.st_n[b] : 0;   // 0 = no memory
+    for (int r = tid; r < kChainMax; r += kChainThreads) s.ord_prev[r] = r;   // carried state is already in matched order
+    int last_l0 = -1;
     __syncthreads();
 
     for (int f = 0; f < a.L; ++f) {
@@ -191,60 +262,32 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
             if (f == 0 && !resume) n_prev = 0;      // tscd_matching.py:762-771
             continue;
         }
-        if (n > KM || n > kChainMax) {
+        if (n > KM || n > kChainMax || n_prev > KM) {
             if (tid == 0) atomicMin(a.status, TSCD_ERR_CAPACITY);
             continue;
         }
         const bool first = (f == 0 && !resume) || n_prev == 0;
-        const int np = first ? n : n_prev;           // rows on the "reference" side of the matching
-        const float* Rc = a.emb_reg + (int64_t)l0 * E;
-        const float* Cc = a.emb_cls + (int64_t)l0 * E;
-        const float* Rp = first ? Rc : st_reg;
-        const float* Cp = first ? Cc : st_cls;
-        const float* nRc = a.norm_reg + l0;
-        const float* nCc = a.norm_cls + l0;
-        const float* nRp = first ? nRc : st_nreg;
-        const float* nCp = first ? nCc : st_ncls;
+        const int np = first ? n : n_prev;           // rows on the reference side of the matching
+        const bool small = n <= kSmall;
+        float* qin = small ? s.x0 : g_qin;
+        float* qv = small ? s.x1 : g_q;
+        float* kh = small ? s.xk : g_k;
+        const float* featc = a.feat + (int64_t)l0 * D;
+        const float* edgec = a.edge + (int64_t)l0 * D;
+        const float* kinc = a.kin + (int64_t)l0 * D;
+        const float* kp = a.kproj + (int64_t)l0 * D;
+        const float* vg = a.vproj + (int64_t)l0 * D;
+        const float* vp = small ? s.xv : vg;
 
-        float* costm = (np * n <= kCostSmem) ? s.cost_s : cost;
-        // ---- matching cost [np x n] ------------------------------------------------------------------
-        for (int rb = 0; rb < np; rb += 32) {
-            for (int cb = 0; cb < n; cb += 32) {
-                float accR[2] = {0.f, 0.f}, accC[2] = {0.f, 0.f};
-                const int pr = tid >> 5;            // pairs (pr, lane) and (pr + 16, lane)
-                for (int which = 0; which < 2; ++which) {
-                    const float* P = which == 0 ? Rp : Cp;
-                    const float* Q = which == 0 ? Rc : Cc;
-                    for (int d0 = 0; d0 < E; d0 += 128) {
-                        __syncthreads();
-                        for (int t = tid; t < 32 * 128; t += kChainThreads) {
-                            const int rr = t >> 7, dd = t & 127;
-                            s.tileA[rr][dd] = (rb + rr < np) ? P[(int64_t)(rb + rr) * E + d0 + dd] : 0.f;
-                            s.tileB[rr][dd] = (cb + rr < n) ? Q[(int64_t)(cb + rr) * E + d0 + dd] : 0.f;
-                        }
-                        __syncthreads();
-                        float x0 = 0.f, x1 = 0.f;
-#pragma unroll 8
-                        for (int dd = 0; dd < 128; ++dd) {
-                            const float q = s.tileB[lane][dd];
-                            x0 = fmaf(s.tileA[pr][dd], q, x0);
-                            x1 = fmaf(s.tileA[pr + 16][dd], q, x1);
-                        }
-                        if (which == 0) { accR[0] += x0; accR[1] += x1; } else { accC[0] += x0; accC[1] += x1; }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int r = rb + pr + 16 * k, c = cb + lane;
-                    if (r < np && c < n) {
-                        const float cr = accR[k] / (nRp[r] * nRc[c]);
-                        const float cc = accC[k] / (nCp[r] * nCc[c]);
-                        float v = 1.f - (cr + cc) / 2.f;
-                        if (v != v) v = 0.f;
-                        costm[(int64_t)r * n + c] = v;
-                    }
-                }
+        // ---- matching cost: rows of the precomputed [prev(original order) x cur] table, re-indexed ------
+        float* costm = (np * n <= kCostSmem) ? s.cost_s : g_cost;
+        {
+            const float* src = a.cost_full + (int64_t)lf * KM * KM;
+            for (int t = tid; t < np * n; t += kChainThreads) {
+                const int r = t / n, c = t - r * n;
+                costm[t] = src[(int64_t)(first ? r : s.ord_prev[r]) * KM + c];
             }
+            if (small) for (int t = tid; t < n * D; t += kChainThreads) s.xv[t] = vg[t];
         }
         __syncthreads();
         // ---- assignment -----------------------------------------------------------------------------
@@ -266,9 +309,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
         }
         __syncthreads();
         // ---- query input ----------------------------------------------------------------------------
-        const float* featc = a.feat + (int64_t)l0 * D;
-        const float* edgec = a.edge + (int64_t)l0 * D;
-        const float* kinc = a.kin + (int64_t)l0 * D;
         for (int t = tid; t < n * D; t += kChainThreads) {
             const int r = t / D, c = t - r * D;
             float v;
@@ -304,8 +344,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
         }
         __syncthreads();
         // ---- per-head L2 normalisation of q and k (8 heads x 32) --------------------------------------
-        const float* kp = a.kproj + (int64_t)l0 * D;
-        const float* vp = a.vproj + (int64_t)l0 * D;
         for (int t = warp; t < n * 8 * 2; t += NW) {
             const int which = t & 1, rh = t >> 1, r = rh >> 3, h = rh & 7;
             const float x = which == 0 ? qv[(int64_t)r * D + h * 32 + lane] : kp[(int64_t)r * D + h * 32 + lane];
@@ -313,21 +351,20 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
             if (which == 0) qv[(int64_t)r * D + h * 32 + lane] = x / nn; else kh[(int64_t)r * D + h * 32 + lane] = x / nn;
         }
         __syncthreads();
-        // ---- attention over the current frame; LayerNorm(identity + attn) ----------------------------
-        // qin is reused as the pre-norm output buffer [n, D]
+        // ---- attention over the current frame; qin is reused as the pre-norm output buffer [n, D] ----
         for (int t = warp; t < n * 8; t += NW) {
             const int r = t >> 3, h = t & 7;
-            const float ql = qv[(int64_t)r * D + h * 32 + lane];
-            float qreg[32];
-#pragma unroll
-            for (int d = 0; d < 32; ++d) qreg[d] = __shfl_sync(0xffffffffu, ql, d);
+            const float* qs = qv + (int64_t)r * D + h * 32;
             float* p = s.pbuf[warp];
             float mx = -INFINITY;
             for (int j = lane; j < n; j += 32) {
                 const float* kr = kh + (int64_t)j * D + h * 32;
                 float sc = 0.f;
 #pragma unroll
-                for (int d = 0; d < 32; ++d) sc = fmaf(qreg[d], kr[d], sc);
+                for (int d = 0; d < 32; ++d) {       // rotated index: lanes hit distinct banks when q / k live in shared memory
+                    const int dd = (d + lane) & 31;
+                    sc = fmaf(qs[dd], kr[dd], sc);
+                }
                 p[j] = sc;
                 mx = fmaxf(mx, sc);
             }
@@ -359,18 +396,30 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
             if (a.perm && lane == 0) a.perm[l0 + r] = s.perm[r];
             const int src = first ? r : s.perm[r];   // order in which this frame is remembered
             for (int c = lane; c < D; c += 32) st_edge[(int64_t)r * D + c] = edgec[(int64_t)src * D + c];
-            if (lane == 0) { st_nreg[r] = nRc[src]; st_ncls[r] = nCc[src]; }
         }
-        __syncthreads();   // cost reads of st_reg / st_cls for this frame are complete
-        for (int t = tid; t < n * (E / 4); t += kChainThreads) {
+        for (int c = tid; c < D; c += kChainThreads) st_time[c] = a.time_emb[(int64_t)lf * D + c];
+        __syncthreads();
+        for (int r = tid; r < n; r += kChainThreads) s.ord_prev[r] = first ? r : s.perm[r];
+        n_prev = n;
+        last_l0 = l0;
+        __syncthreads();
+    }
+    // ---- carry the last frame's matching embeddings (in matched order) to the next call ----------------
+    if (last_l0 >= 0) {
+        float* st_reg = a.st_reg + (int64_t)b * KM * E;
+        float* st_cls = a.st_cls + (int64_t)b * KM * E;
+        const float* Rc = a.emb_reg + (int64_t)last_l0 * E;
+        const float* Cc = a.emb_cls + (int64_t)last_l0 * E;
+        for (int t = tid; t < n_prev * (E / 4); t += kChainThreads) {
             const int r = t / (E / 4), c4 = t - r * (E / 4);
-            const int src = first ? r : s.perm[r];
+            const int src = s.ord_prev[r];
             reinterpret_cast<float4*>(st_reg)[(int64_t)r * (E / 4) + c4] = reinterpret_cast<const float4*>(Rc)[(int64_t)src * (E / 4) + c4];
             reinterpret_cast<float4*>(st_cls)[(int64_t)r * (E / 4) + c4] = reinterpret_cast<const float4*>(Cc)[(int64_t)src * (E / 4) + c4];
         }
-        for (int c = tid; c < D; c += kChainThreads) st_time[c] = a.time_emb[(int64_t)lf * D + c];
-        n_prev = n;
-        __syncthreads();
+        for (int r = tid; r < n_prev; r += kChainThreads) {
+            a.st_nreg[(int64_t)b * KM + r] = a.norm_reg[last_l0 + s.ord_prev[r]];
+            a.st_ncls[(int64_t)b * KM + r] = a.norm_cls[last_l0 + s.ord_prev[r]];
+        }
     }
     if (tid == 0) a.st_n[b] = n_prev;
 }
@@ -384,6 +433,15 @@ extern "C" int tscd_cafm_prep(const tscd_cafm_prep_args* a, void* stream) {
     if (a->bank_dtype == TSCD_F16) cafm_prep_kernel<__half><<<a->B * a->L, 256, 0, st>>>(*a);
     else if (a->bank_dtype == TSCD_BF16) cafm_prep_kernel<__nv_bfloat16><<<a->B * a->L, 256, 0, st>>>(*a);
     else return TSCD_ERR_UNSUPPORTED;
+    TSCD_CUDA_CHECK_LAUNCH();
+    return TSCD_OK;
+}
+
+extern "C" int tscd_cafm_cost(const tscd_cafm_cost_args* a, void* stream) {
+    using namespace tscd;
+    if (!a || a->B <= 0 || a->L <= 0 || a->D != 256 || a->kmax <= 0 || a->kmax > kChainMax) return TSCD_ERR_INVALID_ARG;
+    const int tiles = (a->kmax + 31) / 32;
+    cafm_cost_kernel<<<dim3(a->B * a->L, tiles, tiles), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
     TSCD_CUDA_CHECK_LAUNCH();
     return TSCD_OK;
 }
