@@ -295,8 +295,23 @@ typedef struct {
     const float* emb_reg; const float* emb_cls; const float* norm_reg; const float* norm_cls;
     const float* st_reg; const float* st_cls; const float* st_nreg; const float* st_ncls;
     float* cost;                 /* [B*L, kmax, kmax] */
+    int32_t* ref_n;              /* [B*L] rows on the reference side of every frame's matching (0 for empty frames) */
 } tscd_cafm_cost_args;
 int tscd_cafm_cost(const tscd_cafm_cost_args* args, void* stream);
+
+/* Rectangular LSAP of every frame's cost table in parallel (one warp per frame; scipy.optimize.
+ * linear_sum_assignment semantics, fp64).  The assignment of a frame does not depend on the order in which the
+ * previous frame remembers its rows, so all frames are solved before the sequential chain, which only re-indexes:
+ * lap_col[lf][r] = matched column of reference row r (-1: none), lap_row[lf][c] = matched reference row of column c. */
+typedef struct {
+    int32_t num_frames, kmax;
+    const int32_t* lrow_off;
+    const int32_t* ref_n;
+    const float* cost;
+    int32_t* lap_col;            /* [B*L, kmax] */
+    int32_t* lap_row;            /* [B*L, kmax] */
+} tscd_cafm_lap_args;
+int tscd_cafm_lap(const tscd_cafm_lap_args* args, void* stream);
 
 typedef struct {
     int32_t B, F, L, D, kmax;    /* kmax: capacity (rows per frame) of the state / scratch buffers, <= 512 */
@@ -334,8 +349,9 @@ typedef struct {
     float* sc_qin;               /* [B,kmax,D] */
     float* sc_q;                 /* [B,kmax,D] */
     float* sc_k;                 /* [B,kmax,D] */
-    float* sc_cost;              /* [B,kmax,kmax] */
-    const float* cost_full;      /* [B*L,kmax,kmax] from tscd_cafm_cost */
+    const int32_t* ref_n;        /* [B*L] from tscd_cafm_cost */
+    const int32_t* lap_col;      /* [B*L,kmax] from tscd_cafm_lap */
+    const int32_t* lap_row;      /* [B*L,kmax] */
     /* outputs */
     void* out16;                 /* [loc_cap, D] CAFM output after decoder_norm, original row order */
     float* out32;                /* [loc_cap, D] same in fp32 (may be NULL) */

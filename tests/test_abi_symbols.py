@@ -30,7 +30,7 @@ def test_struct_sizes_match_header():
              ("tscd_nms_args", _lib.NmsArgs), ("tscd_gather_args", _lib.GatherArgs), ("tscd_linear_args", _lib.LinearArgs),
              ("tscd_attn_layout", _lib.AttnLayout), ("tscd_attn_prep_args", _lib.AttnPrepArgs),
              ("tscd_attn_pv_args", _lib.AttnPvArgs), ("tscd_attn_round2_args", _lib.AttnRound2Args),
-             ("tscd_transpose_args", _lib.TransposeArgs), ("tscd_cafm_prep_args", _lib.CafmPrepArgs), ("tscd_cafm_chain_args", _lib.CafmChainArgs), ("tscd_cafm_cost_args", _lib.CafmCostArgs),
+             ("tscd_transpose_args", _lib.TransposeArgs), ("tscd_cafm_prep_args", _lib.CafmPrepArgs), ("tscd_cafm_chain_args", _lib.CafmChainArgs), ("tscd_cafm_cost_args", _lib.CafmCostArgs), ("tscd_cafm_lap_args", _lib.CafmLapArgs),
              ("tscd_frame_attention_args", _lib.FrameAttentionArgs), ("tscd_residual_ln2_args", _lib.ResidualLn2Args),
              ("tscd_final_expand_args", _lib.FinalExpandArgs), ("tscd_final_rows_args", _lib.FinalRowsArgs)]
     body = "".join(f'printf("%zu\\n", sizeof({c}));' for c, _ in pairs)

@@ -104,12 +104,16 @@ class CafmChainArgs(C.Structure):
     _fields_ = _fields("B:i F:i L:i D:i kmax:i out_dtype:i row_off:p lrow_off:p resume:p feat:p edge:p kin:p kproj:p "
                        "vproj:p time_emb:p emb_reg:p emb_cls:p norm_reg:p norm_cls:p wq_t:p se_w1:p se_w2:p ln_w:p "
                        "ln_b:p dec_w:p dec_b:p st_n:p st_out:p st_edge:p st_reg:p st_cls:p st_nreg:p st_ncls:p "
-                       "st_time:p sc_qin:p sc_q:p sc_k:p sc_cost:p cost_full:p out16:p out32:p perm:p status:p")
+                       "st_time:p sc_qin:p sc_q:p sc_k:p ref_n:p lap_col:p lap_row:p out16:p out32:p perm:p status:p")
 
 
 class CafmCostArgs(C.Structure):
     _fields_ = _fields("B:i L:i D:i kmax:i lrow_off:p resume:p st_n:p emb_reg:p emb_cls:p norm_reg:p norm_cls:p "
-                       "st_reg:p st_cls:p st_nreg:p st_ncls:p cost:p")
+                       "st_reg:p st_cls:p st_nreg:p st_ncls:p cost:p ref_n:p")
+
+
+class CafmLapArgs(C.Structure):
+    _fields_ = _fields("num_frames:i kmax:i lrow_off:p ref_n:p cost:p lap_col:p lap_row:p")
 
 
 class FrameAttentionArgs(C.Structure):
@@ -148,6 +152,7 @@ SYMBOLS = [
     ("tscd_transpose_clip", C.c_int, [C.POINTER(TransposeArgs), C.c_void_p]),
     ("tscd_cafm_prep", C.c_int, [C.POINTER(CafmPrepArgs), C.c_void_p]),
     ("tscd_cafm_cost", C.c_int, [C.POINTER(CafmCostArgs), C.c_void_p]),
+    ("tscd_cafm_lap", C.c_int, [C.POINTER(CafmLapArgs), C.c_void_p]),
     ("tscd_cafm_chain", C.c_int, [C.POINTER(CafmChainArgs), C.c_void_p]),
     ("tscd_frame_attention", C.c_int, [C.POINTER(FrameAttentionArgs), C.c_void_p]),
     ("tscd_residual_ln2", C.c_int, [C.POINTER(ResidualLn2Args), C.c_void_p]),

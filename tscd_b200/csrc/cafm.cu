@@ -70,14 +70,17 @@ __global__ void __launch_bounds__(256) cafm_prep_kernel(const tscd_cafm_prep_arg
 
 constexpr int kSmall = 32;   // frames with <= kSmall proposals keep their whole working set in shared memory
 
-struct ChainSmem {
+struct LapSmem {
     double u[kChainMax], v[kChainMax], spc[kChainMax];
     int path[kChainMax], col4row[kChainMax], row4col[kChainMax], remaining[kChainMax];
-    int perm[kChainMax], prow[kChainMax], ord_prev[kChainMax];
     unsigned char SR[kChainMax], SC[kChainMax];
+    float cost_s[kCostSmem];          // cost table kept on chip when n_ref * n_cur fits (the common case)
+};
+
+struct ChainSmem {
+    int perm[kChainMax], prow[kChainMax], ord_prev[kChainMax];
     float w1[64], w2[64];
     float pbuf[kChainThreads / 32][kChainMax];
-    float cost_s[kCostSmem];          // matching cost kept on chip when n_prev * n_cur fits (the common case)
     float x0[kSmall * 256];           // query input, then pre-norm output
     float x1[kSmall * 256];           // q, then scratch for the decoder norm
     float xk[kSmall * 256];           // normalised keys
@@ -90,7 +93,10 @@ __global__ void __launch_bounds__(256) cafm_cost_kernel(const tscd_cafm_cost_arg
     __shared__ float tileA[32][129], tileB[32][129];
     const int lf = blockIdx.x, b = lf / a.L, f = lf - b * a.L;
     const int l0 = a.lrow_off[lf], n = a.lrow_off[lf + 1] - l0;
-    if (n <= 0) return;
+    if (n <= 0) {
+        if (a.ref_n && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) a.ref_n[lf] = 0;
+        return;
+    }
     const int E = 4 * a.D, KM = a.kmax;
     // reference side: previous non-empty local frame, else the carried state (resume), else the frame itself
     const float *Rp = nullptr, *Cp = nullptr, *nRp = nullptr, *nCp = nullptr;
@@ -110,6 +116,7 @@ __global__ void __launch_bounds__(256) cafm_cost_kernel(const tscd_cafm_cost_arg
             Rp = a.emb_reg + (int64_t)l0 * E; Cp = a.emb_cls + (int64_t)l0 * E; nRp = a.norm_reg + l0; nCp = a.norm_cls + l0;
         }
     }
+    if (a.ref_n && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) a.ref_n[lf] = (np > KM || n > KM) ? 0 : np;
     const int rb = blockIdx.y * 32, cb = blockIdx.z * 32;
     if (rb >= np || cb >= n || np > KM || n > KM) return;
     const float* Rc = a.emb_reg + (int64_t)l0 * E;
@@ -154,7 +161,7 @@ __global__ void __launch_bounds__(256) cafm_cost_kernel(const tscd_cafm_cost_arg
 
 // Rectangular LSAP by warp 0.  C is the [n_prev x n_cur] cost (row-major, fp32).  Solves the problem with
 // rows = the smaller side exactly like scipy (transposing when n_cur < n_prev).  Results in s.col4row / s.row4col.
-__device__ void lap_warp(const float* C, int n_prev, int n_cur, ChainSmem& s, int lane) {
+__device__ void lap_warp(const float* C, int ldc, int n_prev, int n_cur, LapSmem& s, int lane) {
     const bool tr = n_cur < n_prev;
     const int nr = tr ? n_cur : n_prev, nc = tr ? n_prev : n_cur;
     for (int j = lane; j < nc; j += 32) { s.v[j] = 0.0; s.row4col[j] = -1; s.path[j] = -1; }
@@ -175,7 +182,7 @@ __device__ void lap_warp(const float* C, int n_prev, int n_cur, ChainSmem& s, in
             unsigned best_tb = 0xffffffffu;
             for (int it = lane; it < num_rem; it += 32) {
                 const int j = s.remaining[it];
-                const double c = (double)(tr ? C[(int64_t)j * n_cur + i] : C[(int64_t)i * n_cur + j]);
+                const double c = (double)(tr ? C[(int64_t)j * ldc + i] : C[(int64_t)i * ldc + j]);
                 const double r = min_val + c - ui - s.v[j];
                 if (r < s.spc[j]) { s.path[j] = i; s.spc[j] = r; }
                 const double sj = s.spc[j];
@@ -220,6 +227,36 @@ __device__ void lap_warp(const float* C, int n_prev, int n_cur, ChainSmem& s, in
     }
 }
 
+__global__ void __launch_bounds__(32) cafm_lap_kernel(const tscd_cafm_lap_args a) {
+    extern __shared__ __align__(16) unsigned char lap_smem[];
+    LapSmem& s = *reinterpret_cast<LapSmem*>(lap_smem);
+    const int lf = blockIdx.x, lane = threadIdx.x;
+    const int n = a.lrow_off[lf + 1] - a.lrow_off[lf];
+    const int np = a.ref_n[lf];
+    if (n <= 0 || np <= 0) return;
+    const int KM = a.kmax;
+    const float* C = a.cost + (int64_t)lf * KM * KM;
+    int ldc = KM;
+    if (np * n <= kCostSmem) {                       // stage the table on chip: every Dijkstra step reads one row / column
+        for (int t = lane; t < np * n; t += 32) { const int r = t / n, c = t - r * n; s.cost_s[t] = C[(int64_t)r * KM + c]; }
+        __syncwarp();
+        C = s.cost_s;
+        ldc = n;
+    }
+    lap_warp(C, ldc, np, n, s, lane);
+    __syncwarp();
+    const bool tr = n < np;       // lap_warp solves with rows = the smaller side
+    int32_t* col = a.lap_col + (int64_t)lf * KM;
+    int32_t* row = a.lap_row + (int64_t)lf * KM;
+    if (!tr) {
+        for (int r = lane; r < np; r += 32) col[r] = s.col4row[r];
+        for (int c = lane; c < n; c += 32) row[c] = s.row4col[c];
+    } else {                      // transposed problem: its rows are the current columns
+        for (int r = lane; r < np; r += 32) col[r] = s.row4col[r];
+        for (int c = lane; c < n; c += 32) row[c] = s.col4row[c];
+    }
+}
+
 __device__ __forceinline__ void layer_norm_row(const float* x, const float* w, const float* b, float* y, int D, int lane) {
     float s = 0.f;
     for (int c = lane; c < D; c += 32) s += x[c];
@@ -246,7 +283,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
     float* g_qin = a.sc_qin + (int64_t)b * KM * D;
     float* g_q = a.sc_q + (int64_t)b * KM * D;
     float* g_k = a.sc_k + (int64_t)b * KM * D;
-    float* g_cost = a.sc_cost + (int64_t)b * KM * KM;
 
     const bool resume = a.resume ? (a.resume[b] != 0) : false;
     int n_prev = resume ? a.st_n[b] : 0;   // 0 = no memory
@@ -267,7 +303,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
             continue;
         }
         const bool first = (f == 0 && !resume) || n_prev == 0;
-        const int np = first ? n : n_prev;           // rows on the reference side of the matching
+        const int np = first ? n : n_prev;           // rows on the reference side of the matching (== ref_n[lf])
         const bool small = n <= kSmall;
         float* qin = small ? s.x0 : g_qin;
         float* qv = small ? s.x1 : g_q;
@@ -279,31 +315,22 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
         const float* vg = a.vproj + (int64_t)l0 * D;
         const float* vp = small ? s.xv : vg;
 
-        // ---- matching cost: rows of the precomputed [prev(original order) x cur] table, re-indexed ------
-        float* costm = (np * n <= kCostSmem) ? s.cost_s : g_cost;
-        {
-            const float* src = a.cost_full + (int64_t)lf * KM * KM;
-            for (int t = tid; t < np * n; t += kChainThreads) {
-                const int r = t / n, c = t - r * n;
-                costm[t] = src[(int64_t)(first ? r : s.ord_prev[r]) * KM + c];
-            }
-            if (small) for (int t = tid; t < n * D; t += kChainThreads) s.xv[t] = vg[t];
-        }
-        __syncthreads();
-        // ---- assignment -----------------------------------------------------------------------------
-        if (warp == 0) {
-            lap_warp(costm, np, n, s, lane);
-            __syncwarp();
-            if (lane == 0) {
-                if (np <= n) {
-                    for (int r = 0; r < np; ++r) { s.perm[r] = s.col4row[r]; s.prow[r] = r; }
-                    int t = np;
-                    for (int c = 0; c < n && t < n; ++c)
-                        if (s.row4col[c] == -1) { s.perm[t] = c; s.prow[t] = -1 - c; ++t; }
-                } else {
-                    int t = 0;
-                    for (int j = 0; j < np; ++j)
-                        if (s.row4col[j] >= 0) { s.perm[t] = s.row4col[j]; s.prow[t] = j; ++t; }
+        // ---- assignment: re-index the frame's (order-independent) LSAP solution by how the reference frame
+        //      remembers its rows (tscd_matching.py:813-844) ---------------------------------------------
+        if (small) for (int t = tid; t < n * D; t += kChainThreads) s.xv[t] = vg[t];
+        if (tid == 0) {
+            const int32_t* colo = a.lap_col + (int64_t)lf * KM;
+            const int32_t* rowo = a.lap_row + (int64_t)lf * KM;
+            if (np <= n) {
+                for (int r = 0; r < np; ++r) { s.perm[r] = colo[first ? r : s.ord_prev[r]]; s.prow[r] = r; }
+                int t = np;
+                for (int c = 0; c < n && t < n; ++c)
+                    if (rowo[c] == -1) { s.perm[t] = c; s.prow[t] = -1 - c; ++t; }
+            } else {
+                int t = 0;
+                for (int r = 0; r < np && t < n; ++r) {
+                    const int c = colo[s.ord_prev[r]];
+                    if (c >= 0) { s.perm[t] = c; s.prow[t] = r; ++t; }
                 }
             }
         }
@@ -442,6 +469,16 @@ extern "C" int tscd_cafm_cost(const tscd_cafm_cost_args* a, void* stream) {
     if (!a || a->B <= 0 || a->L <= 0 || a->D != 256 || a->kmax <= 0 || a->kmax > kChainMax) return TSCD_ERR_INVALID_ARG;
     const int tiles = (a->kmax + 31) / 32;
     cafm_cost_kernel<<<dim3(a->B * a->L, tiles, tiles), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+    TSCD_CUDA_CHECK_LAUNCH();
+    return TSCD_OK;
+}
+
+extern "C" int tscd_cafm_lap(const tscd_cafm_lap_args* a, void* stream) {
+    using namespace tscd;
+    if (!a || a->num_frames <= 0 || a->kmax <= 0 || a->kmax > kChainMax) return TSCD_ERR_INVALID_ARG;
+    const size_t smem = sizeof(LapSmem);
+    if (cudaFuncSetAttribute(cafm_lap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
+    cafm_lap_kernel<<<a->num_frames, 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
     TSCD_CUDA_CHECK_LAUNCH();
     return TSCD_OK;
 }

@@ -210,16 +210,21 @@ class AggregationStage:
         cafm32 = f32z(loc_cap, D) if want_debug else None
         perm = torch.zeros(loc_cap, dtype=torch.int32, device=dev) if want_debug else None
         cost_full = f32z(B * Lf, kmax, kmax)
+        ref_n = torch.zeros(B * Lf, dtype=torch.int32, device=dev)
         ops.call("tscd_cafm_cost", L.CafmCostArgs, B=B, L=Lf, D=D, kmax=kmax, lrow_off=lay.lrow_off, resume=resume,
                  st_n=state.n, emb_reg=emb_reg32, emb_cls=emb_cls32, norm_reg=norm_reg, norm_cls=norm_cls,
-                 st_reg=state.reg, st_cls=state.cls, st_nreg=state.nreg, st_ncls=state.ncls, cost=cost_full)
+                 st_reg=state.reg, st_cls=state.cls, st_nreg=state.nreg, st_ncls=state.ncls, cost=cost_full, ref_n=ref_n)
+        lap_col = torch.full((B * Lf, kmax), -1, dtype=torch.int32, device=dev)
+        lap_row = torch.full((B * Lf, kmax), -1, dtype=torch.int32, device=dev)
+        ops.call("tscd_cafm_lap", L.CafmLapArgs, num_frames=B * Lf, kmax=kmax, lrow_off=lay.lrow_off, ref_n=ref_n, cost=cost_full,
+                 lap_col=lap_col, lap_row=lap_row)
         ops.call("tscd_cafm_chain", L.CafmChainArgs, B=B, F=F, L=Lf, D=D, kmax=kmax, out_dtype=dt, row_off=lay.row_off,
                  lrow_off=lay.lrow_off, resume=resume, feat=feat, edge=edge, kin=kin, kproj=kproj, vproj=vproj,
                  time_emb=te32, emb_reg=emb_reg32, emb_cls=emb_cls32, norm_reg=norm_reg, norm_cls=norm_cls,
                  wq_t=w.cafm_wq_t, se_w1=w.se_w1, se_w2=w.se_w2, ln_w=w.cafm_ln_w, ln_b=w.cafm_ln_b,
                  dec_w=w.cafm_dec_w, dec_b=w.cafm_dec_b, st_n=state.n, st_out=state.out, st_edge=state.edge,
                  st_reg=state.reg, st_cls=state.cls, st_nreg=state.nreg, st_ncls=state.ncls, st_time=state.time,
-                 sc_qin=f32z(B, kmax, D), sc_q=f32z(B, kmax, D), sc_k=f32z(B, kmax, D), sc_cost=f32z(B, kmax, kmax), cost_full=cost_full,
+                 sc_qin=f32z(B, kmax, D), sc_q=f32z(B, kmax, D), sc_k=f32z(B, kmax, D), ref_n=ref_n, lap_col=lap_col, lap_row=lap_row,
                  out16=cafm16, out32=cafm32, perm=perm, status=status)
         return cafm16, cafm32, perm, te32
 
