@@ -23,6 +23,9 @@ constexpr int kNmsCap = 4096;
 __device__ __forceinline__ bool iou_gt(const float4& a, float sa, const float4& b, float sb, double thr) {
     float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
     float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    // disjoint boxes (every pair of different classes after the coordinate-trick offset): inter = 0, and
+    // 0/u > thr is false for thr >= 0 (0/0 = NaN compares false too) -- skip the division
+    if (!(xx2 > xx1) || !(yy2 > yy1)) return false;
     float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
     float inter = __fmul_rn(w, h);
     float uni = __fsub_rn(__fadd_rn(sa, sb), inter);
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const tscd_nms_args ar
 
 extern "C" int tscd_nms(const tscd_nms_args* a, void* stream) {
     using namespace tscd;
-    if (!a || a->num_frames < 0 || a->cand_cap <= 0 || a->max_keep <= 0) return TSCD_ERR_INVALID_ARG;
+    if (!a || a->num_frames < 0 || a->cand_cap <= 0 || a->max_keep <= 0 || !(a->iou_thresh >= 0.f)) return TSCD_ERR_INVALID_ARG;
     if (a->num_frames == 0) return TSCD_OK;
     int cap = a->cand_cap < kNmsCap ? a->cand_cap : kNmsCap;
     int cap64 = 1;
