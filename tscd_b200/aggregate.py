@@ -51,12 +51,12 @@ def mca_forward(lay: ops.AttnLayoutT, w: MCAWeights, bank_cls, bank_reg, bank_sc
     dev, dt = bank_cls.device, lay.dtype
     qkv_c, _ = ops.linear(bank_cls, w.qkv_cls, m_dev=n_rows_dev)
     qkv_r, _ = ops.linear(bank_reg, w.qkv_reg, m_dev=n_rows_dev)
-    tmp_c = torch.zeros(lay.loc_cap, 512, dtype=dt, device=dev)      # [attn@v | x_ori]
-    tmp_r = torch.zeros(lay.loc_cap, 512, dtype=dt, device=dev)
+    tmp_c = torch.empty(lay.loc_cap, 512, dtype=dt, device=dev)      # [attn@v | x_ori]
+    tmp_r = torch.empty(lay.loc_cap, 512, dtype=dt, device=dev)
     bufs = ops.attn_prep(lay, qkv_c, qkv_r, bank_score, xori_cls=tmp_c[:, 256:], xori_reg=tmp_r[:, 256:])
-    stats = torch.zeros(lay.loc_cap, 16, dtype=torch.float32, device=dev)
+    stats = torch.empty(lay.loc_cap, 16, dtype=torch.float32, device=dev)
     ops.attn_pv(lay, bufs, tmp_c[:, :256], tmp_r[:, :256], stats, need_reg=need_reg)
-    cat_c = torch.zeros(lay.loc_cap, 768, dtype=dt, device=dev)      # [round2 @ V | linear(x)]
+    cat_c = torch.empty(lay.loc_cap, 768, dtype=dt, device=dev)      # [round2 @ V | linear(x)]
     ops.linear(tmp_c, w.lin_w, w.lin_b, m_dev=n_loc_dev, out16=cat_c[:, 256:], want16=False)
     ops.attn_round2(lay, bufs, bufs["vt_cls"], stats, cat_c[:, :256], use_obj_mask=False, sim_thresh=sim_thresh,
                     conf_sim_thresh=conf_sim_thresh)
@@ -64,7 +64,7 @@ def mca_forward(lay: ops.AttnLayoutT, w: MCAWeights, bank_cls, bank_reg, bank_sc
     trans_obj16 = trans_obj32 = None
     cat_r = None
     if need_reg:
-        cat_r = torch.zeros(lay.loc_cap, 768, dtype=dt, device=dev)
+        cat_r = torch.empty(lay.loc_cap, 768, dtype=dt, device=dev)
         ops.linear(tmp_r, w.linreg_w, w.linreg_b, m_dev=n_loc_dev, out16=cat_r[:, 256:], want16=False)
         ops.attn_round2(lay, bufs, bufs["vt_reg"], stats, cat_r[:, :256], use_obj_mask=True, sim_thresh=sim_thresh,
                         conf_sim_thresh=conf_sim_thresh)
@@ -94,14 +94,14 @@ def msa_forward(lay: ops.AttnLayoutT, w: MSAWeights, bank_cls, bank_reg, bank_sc
     dev, dt, cap = bank_cls.device, lay.dtype, lay.row_cap
     qkv_c, _ = ops.linear(bank_cls, w.qkv_cls, m_dev=n_rows_dev)
     qkv_r, _ = ops.linear(bank_reg, w.qkv_reg, m_dev=n_rows_dev)
-    tmp_c = torch.zeros(cap, 512, dtype=dt, device=dev)                  # [attn@v | v]
-    tmp_r = torch.zeros(cap, 512, dtype=dt, device=dev)
+    tmp_c = torch.empty(cap, 512, dtype=dt, device=dev)                  # [attn@v | v]
+    tmp_r = torch.empty(cap, 512, dtype=dt, device=dev)
     bufs = ops.attn_prep(lay, qkv_c, qkv_r, bank_score, xori_cls=tmp_c[:, 256:], xori_reg=tmp_r[:, 256:])
-    stats = torch.zeros(cap, 16, dtype=torch.float32, device=dev)
+    stats = torch.empty(cap, 16, dtype=torch.float32, device=dev)
     ops.attn_pv(lay, bufs, tmp_c[:, :256], tmp_r[:, :256], stats, need_reg=False)
-    cat = torch.zeros(cap, 1024, dtype=dt, device=dev)                   # [round2 @ tc | tc]
+    cat = torch.empty(cap, 1024, dtype=dt, device=dev)                   # [round2 @ tc | tc]
     ops.linear(tmp_c, w.l1_w, w.l1_b, m_dev=n_rows_dev, out16=cat[:, 512:], want16=False)
-    tct = torch.zeros(lay.B * 512, lay.nk_pitch, dtype=dt, device=dev)
+    tct = torch.empty(lay.B * 512, lay.nk_pitch, dtype=dt, device=dev)
     ops.call("tscd_transpose_clip", ops.L.TransposeArgs, lay=lay.to_c(), width=512, x=cat[:, 512:], ld_x=cat.stride(0), xt=tct)
     # round 2 aggregates linear1's output, 256 columns per launch; V^T rows of clip b start at b*512 (+256)
     for half in range(2):

@@ -82,7 +82,7 @@ __device__ void bitonic_sort_desc(unsigned long long* a, int n64) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kSelThreads) select_kernel(const tscd_select_args args) {
+__global__ void __launch_bounds__(kSelThreads) select_kernel(const tscd_select_args args, int sort_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int frame = blockIdx.x;
     const tscd_anchors& an = args.anchors;
@@ -90,28 +90,86 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const tscd_select_a
     const int C = args.num_classes;
     const bool sig = args.apply_sigmoid != 0;
 
-    uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw);                     // [A]
-    int* sel = reinterpret_cast<int*>(keys + ((A + 3) & ~3));                   // [A] selected anchor ids
-    unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(sel + ((A + 3) & ~3));  // [pow2(pre_k)]
+    const int A4 = (A + 3) & ~3;
+    uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw);                     // [A] order-preserving selection key
+    float* conf_s = reinterpret_cast<float*>(keys + A4);                        // [A] class max (mode A: pre-sigmoid)
+    int* sel = reinterpret_cast<int*>(conf_s + A4);                             // [A] selected anchor ids
+    unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(sel + A4);  // [pow2(pre_k)]
+    unsigned char* cls_s = reinterpret_cast<unsigned char*>(sortbuf + sort_cap); // [A] class arg-max
     __shared__ SelSmem s;
 
-    // ---- pass 1: one key per anchor -------------------------------------------------------------------
+    // ---- pass 1: stream objectness + class planes once; key / class max / arg-max per anchor ----------
+    // Planar layouts (anchor stride 1: NCHW conv outputs) are read with 16-byte vector loads, V anchors per
+    // thread, all C+1 planes of the group in flight; other layouts take the per-anchor path.
     int n_ge = 0;  // mode B: anchors with score >= conf_thresh
-    for (int a = threadIdx.x; a < A; a += blockDim.x) {
-        AnchorPos p = anchor_pos(an, a);
-        float obj = ldf(view_ptr<T>(args.obj, p.level, frame, p.local));
-        if (sig) obj = sigmoidf_ref(obj);
-        float key = obj;
-        if (args.mode == 1) {
-            const T* c = view_ptr<T>(args.cls, p.level, frame, p.local);
-            const int64_t cs = args.cls.chan_stride[p.level];
-            float best = ldf(c);
-            for (int k = 1; k < C; ++k) best = fmaxf(best, ldf(c + k * cs));
-            if (sig) best = sigmoidf_ref(best);  // sigmoid is monotone: max first, one exp per anchor
-            key = __fmul_rn(obj, best);          // tscd_head.py:1591  obj * class_conf
-            n_ge += (key >= args.conf_thresh) ? 1 : 0;
+    const bool modeB = args.mode == 1;
+    for (int l = 0; l < an.num_levels; ++l) {
+        const int a_lo = an.level_start[l], nl = an.level_start[l + 1] - a_lo;
+        constexpr int VMAX = 16 / sizeof(T);
+        const T* op = reinterpret_cast<const T*>(args.obj.ptr[l]) + (int64_t)frame * args.obj.frame_stride[l];
+        const T* cp = reinterpret_cast<const T*>(args.cls.ptr[l]) + (int64_t)frame * args.cls.frame_stride[l];
+        const int64_t ccs = args.cls.chan_stride[l];
+        const bool planar = args.obj.anchor_stride[l] == 1 && args.cls.anchor_stride[l] == 1 &&
+                            ((reinterpret_cast<uintptr_t>(op) | reinterpret_cast<uintptr_t>(cp)) & 15) == 0 &&
+                            (ccs % VMAX) == 0 && (args.obj.frame_stride[l] % VMAX) == 0 && (args.cls.frame_stride[l] % VMAX) == 0;
+        const int nvec = planar ? nl / VMAX : 0;
+        for (int g = threadIdx.x; g < nvec; g += blockDim.x) {
+            const int a0 = g * VMAX;
+            float ob[VMAX], best[VMAX];
+            int bi[VMAX];
+            {
+                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(op + a0));
+                const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+                for (int v = 0; v < VMAX; ++v) { ob[v] = ldf_reg(e[v]); best[v] = -INFINITY; bi[v] = 0; }
+            }
+#pragma unroll 5
+            for (int c = 0; c < C; ++c) {
+                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(cp + (int64_t)c * ccs + a0));
+                const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+                for (int v = 0; v < VMAX; ++v) {
+                    const float x = ldf_reg(e[v]);
+                    if (x > best[v]) { best[v] = x; bi[v] = c; }     // first maximum wins (torch.max)
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < VMAX; ++v) {
+                const int a = a_lo + a0 + v;
+                float o = ob[v], b = best[v];
+                if (sig) o = sigmoidf_ref(o);
+                float key = o;
+                if (modeB) {
+                    if (sig) b = sigmoidf_ref(b);
+                    key = __fmul_rn(o, b);                            // tscd_head.py:1591  obj * class_conf
+                    n_ge += (key >= args.conf_thresh) ? 1 : 0;
+                }
+                keys[a] = f2ord(key);
+                conf_s[a] = b;
+                cls_s[a] = (unsigned char)bi[v];
+            }
         }
-        keys[a] = f2ord(key);
+        for (int i = nvec * VMAX + threadIdx.x; i < nl; i += blockDim.x) {      // tail / non-planar layouts
+            const int a = a_lo + i;
+            float o = ldf(op + (int64_t)i * args.obj.anchor_stride[l]);
+            const T* c = cp + (int64_t)i * args.cls.anchor_stride[l];
+            float b = ldf(c);
+            int bidx = 0;
+            for (int k = 1; k < C; ++k) {
+                const float x = ldf(c + k * ccs);
+                if (x > b) { b = x; bidx = k; }
+            }
+            if (sig) o = sigmoidf_ref(o);
+            float key = o;
+            if (modeB) {
+                if (sig) b = sigmoidf_ref(b);
+                key = __fmul_rn(o, b);
+                n_ge += (key >= args.conf_thresh) ? 1 : 0;
+            }
+            keys[a] = f2ord(key);
+            conf_s[a] = b;
+            cls_s[a] = (unsigned char)bidx;
+        }
     }
     __syncthreads();
 
@@ -181,27 +239,24 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const tscd_select_a
         __syncthreads();
     }
 
-    // ---- candidate records -----------------------------------------------------------------------------
+    // ---- candidate records: only the regression rows of the survivors are touched again ------------------
     const int64_t base = (int64_t)frame * args.cand_cap;
     for (int i = threadIdx.x; i < n_sel; i += blockDim.x) {
         const int a = sel[i];
         AnchorPos p = anchor_pos(an, a);
-        float obj = ldf(view_ptr<T>(args.obj, p.level, frame, p.local));
-        if (sig) obj = sigmoidf_ref(obj);
-        const T* c = view_ptr<T>(args.cls, p.level, frame, p.local);
-        const int64_t cs = args.cls.chan_stride[p.level];
-        float best = ldf(c);
-        int bi = 0;
-        for (int k = 1; k < C; ++k) {
-            float v = ldf(c + k * cs);
-            if (v > best) { best = v; bi = k; }  // first maximum wins (torch.max)
+        float score;
+        if (modeB) {
+            score = ord2f(keys[a]);
+        } else {
+            float conf = conf_s[a];
+            if (sig) conf = sigmoidf_ref(conf);
+            score = __fmul_rn(ord2f(keys[a]), conf);                  // post_process.py:512  obj * class_conf
         }
-        if (sig) best = sigmoidf_ref(best);
         float4 box = anchor_box<T>(args.reg, p, frame, args.apply_decode != 0);
         args.cand_idx[base + i] = a;
         reinterpret_cast<float4*>(args.cand_box)[base + i] = box;
-        args.cand_score[base + i] = __fmul_rn(obj, best);
-        args.cand_cls[base + i] = bi;
+        args.cand_score[base + i] = score;
+        args.cand_cls[base + i] = (int)cls_s[a];
     }
     if (threadIdx.x == 0) args.cand_count[frame] = n_sel;
 }
@@ -219,18 +274,19 @@ extern "C" int tscd_select(const tscd_select_args* a, void* stream) {
     if (A <= 0) return TSCD_ERR_INVALID_ARG;
     int n64 = 1;
     if (a->mode == 0) while (n64 < (a->pre_k < A ? a->pre_k : A)) n64 <<= 1;
-    size_t smem = (size_t)((A + 3) & ~3) * 8 + (size_t)n64 * 8;
+    if (a->num_classes > 255) return TSCD_ERR_UNSUPPORTED;
+    size_t smem = (size_t)((A + 3) & ~3) * 12 + (size_t)n64 * 8 + (size_t)((A + 15) & ~15);
     if (smem > 200 * 1024) return TSCD_ERR_CAPACITY;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     cudaError_t e;
     if (a->head_dtype == TSCD_F32) {
         e = cudaFuncSetAttribute(select_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return TSCD_ERR_CUDA;
-        select_kernel<float><<<a->num_frames, kSelThreads, smem, st>>>(*a);
+        select_kernel<float><<<a->num_frames, kSelThreads, smem, st>>>(*a, n64);
     } else if (a->head_dtype == TSCD_F16) {
         e = cudaFuncSetAttribute(select_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return TSCD_ERR_CUDA;
-        select_kernel<__half><<<a->num_frames, kSelThreads, smem, st>>>(*a);
+        select_kernel<__half><<<a->num_frames, kSelThreads, smem, st>>>(*a, n64);
     } else {
         return TSCD_ERR_UNSUPPORTED;
     }

@@ -153,12 +153,13 @@ def gather(head: HeadViews, feats, feat_dtype: torch.dtype, feat_dim: int, cand,
                row_off=torch.empty(Fn + 1, dtype=torch.int32, device=dev),
                sel_idx=torch.empty(Fn, max_keep, dtype=torch.int32, device=dev),
                sel_rows=torch.empty(Fn, max_keep, 7 + Cn, dtype=torch.float32, device=dev),
-               bank_cls=torch.zeros(rows_cap, feat_dim, dtype=bank_dtype, device=dev),
-               bank_reg=torch.zeros(rows_cap, feat_dim, dtype=bank_dtype, device=dev),
-               bank_edge=torch.zeros(rows_cap, feat_dim, dtype=bank_dtype, device=dev),
-               bank_score=torch.zeros(rows_cap, dtype=torch.float32, device=dev),
-               bank_fg=torch.zeros(rows_cap, dtype=torch.float32, device=dev),
-               bank_box=torch.zeros(rows_cap, 4, dtype=torch.float32, device=dev), max_keep=max_keep)
+               # rows past the packed count are never consumed (every kernel is bounded by the device-side counts)
+               bank_cls=torch.empty(rows_cap, feat_dim, dtype=bank_dtype, device=dev),
+               bank_reg=torch.empty(rows_cap, feat_dim, dtype=bank_dtype, device=dev),
+               bank_edge=torch.empty(rows_cap, feat_dim, dtype=bank_dtype, device=dev),
+               bank_score=torch.empty(rows_cap, dtype=torch.float32, device=dev),
+               bank_fg=torch.empty(rows_cap, dtype=torch.float32, device=dev),
+               bank_box=torch.empty(rows_cap, 4, dtype=torch.float32, device=dev), max_keep=max_keep)
     a = L.GatherArgs()
     a.num_frames, a.num_classes, a.head_dtype = Fn, Cn, _DT[head.dtype]
     a.apply_sigmoid, a.apply_decode = int(head.apply_sigmoid), int(head.apply_decode)
@@ -230,11 +231,13 @@ def attn_prep(lay: AttnLayoutT, qkv_cls, qkv_reg, key_score, xori_cls=None, xori
     dev, dt = qkv_cls.device, lay.dtype
     if bufs is None:
         bufs = {}
+        # no zero fill: invalid keys are masked by select (never multiplied) and the prep kernel itself zero-fills
+        # the V^T padding that the P@V / W@V products read
         for n in ("qn_cls", "kn_cls", "vn_cls", "qn_reg", "kn_reg", "vn_reg"):
-            bufs[n] = torch.zeros(lay.row_cap, 256, dtype=dt, device=dev)
+            bufs[n] = torch.empty(lay.row_cap, 256, dtype=dt, device=dev)
         for n in ("vt_cls", "vt_reg"):
-            bufs[n] = torch.zeros(lay.B * 256, lay.nk_pitch, dtype=dt, device=dev)
-        bufs["row_frame"] = torch.zeros(lay.row_cap, dtype=torch.int32, device=dev)
+            bufs[n] = torch.empty(lay.B * 256, lay.nk_pitch, dtype=dt, device=dev)
+        bufs["row_frame"] = torch.empty(lay.row_cap, dtype=torch.int32, device=dev)
     a = L.AttnPrepArgs()
     a.lay, a.scale = lay.to_c(), scale
     assert qkv_cls.stride(1) == 1 and qkv_cls.stride(0) == qkv_reg.stride(0)

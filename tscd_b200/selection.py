@@ -32,7 +32,7 @@ class SelectionConfig:
 
 
 def select_and_gather(head: ops.HeadViews, feats, feat_dtype, feat_dim, cfg: SelectionConfig,
-                      bank_dtype=torch.float16, status: Optional[torch.Tensor] = None):
+                      bank_dtype=torch.float16, status: Optional[torch.Tensor] = None, bank_rows: Optional[int] = None):
     """Runs K1 (+K2) + K3.  Returns the dict of ops.gather plus the candidate dict under 'cand'."""
     cand = ops.select(head, cfg.mode, pre_k=cfg.pre_k, conf_thresh=cfg.conf_thresh,
                       minimal_limit=cfg.minimal_limit, maximal_limit=cfg.maximal_limit)
@@ -42,7 +42,7 @@ def select_and_gather(head: ops.HeadViews, feats, feat_dtype, feat_dim, cfg: Sel
         keep, keep_count, status = ops.nms(cand["box"], cand["score"], cand["cls"], cand["count"], cfg.nms_thresh,
                                            max_keep=max_keep, status=status)
     out = ops.gather(head, feats, feat_dtype, feat_dim, cand, keep, keep_count, max_keep=max_keep,
-                     bank_dtype=bank_dtype)
+                     bank_dtype=bank_dtype, bank_rows=bank_rows)
     out["cand"] = cand
     out["status"] = status
     return out

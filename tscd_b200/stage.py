@@ -91,6 +91,12 @@ class AggregationStage:
         self.cfg = cfg
         self.w = StageWeights(state_dict, cfg, device)
         self.device = device
+        self._side = None
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
 
     # ------------------------------------------------------------------------------------------------------
     def forward(self, head: ops.HeadViews, feats, feat_dtype, time_embedding: torch.Tensor, B: int, F: int, Lf: int,
@@ -103,32 +109,36 @@ class AggregationStage:
         kmax = cfg.selection.max_keep(A)
         status = torch.zeros(1, dtype=torch.int32, device=dev)
 
-        # ---- K1-K3: selection + bank ------------------------------------------------------------------
-        sel = _selection.select_and_gather(head, feats, feat_dtype, D, cfg.selection, bank_dtype=dt, status=status)
-        # operand arrays are read in 128-row TMA boxes: pad the banks
+        # ---- K1-K3: selection + bank (operand arrays are read in 128-row TMA boxes: capacity padded) ------
         row_cap = _r128(B * F * kmax) + 128
         loc_cap = _r128(B * Lf * kmax)
         nk_pitch = _r128(F * kmax)
-
-        def pad_rows(t, rows):
-            if t.shape[0] >= rows:
-                return t
-            p = torch.zeros(rows, *t.shape[1:], dtype=t.dtype, device=dev)
-            p[:t.shape[0]] = t
-            return p
-
-        bank_cls, bank_reg, bank_edge = (pad_rows(sel[k], row_cap) for k in ("bank_cls", "bank_reg", "bank_edge"))
-        bank_score = pad_rows(sel["bank_score"], row_cap)
+        sel = _selection.select_and_gather(head, feats, feat_dtype, D, cfg.selection, bank_dtype=dt, status=status,
+                                           bank_rows=row_cap)
+        bank_cls, bank_reg, bank_edge, bank_score = sel["bank_cls"], sel["bank_reg"], sel["bank_edge"], sel["bank_score"]
         lay = aggregate.make_layout(sel["sel_count"], B, F, Lf, row_cap, loc_cap, nk_pitch, dt, row_off=sel["row_off"])
         n_rows_dev, n_loc_dev = lay.row_off[-1:], lay.lrow_off[-1:]
 
-        # ---- K4: agg (cls refinement) and agg_iou (reg / obj refinement) ---------------------------------
-        (agg_cls16, agg_cls32), _ = aggregate.mca_forward(lay, w.agg, bank_cls, bank_reg, bank_score, n_rows_dev, n_loc_dev,
-                                                          need_reg=False, sim_thresh=cfg.sim_thresh,
-                                                          conf_sim_thresh=cfg.conf_sim_thresh)
+        # ---- K4: agg_iou (reg / obj refinement, feeds the CAFM recurrence) on the main stream; agg (cls refinement)
+        #      + cls_pred on a side stream that starts when the recurrence does: the chain occupies one SM per clip,
+        #      the independent classification branch fills the rest of the GPU --------------------------------
+        main = torch.cuda.current_stream()
+        side = self._side_stream()
         (iou_cls16, iou_cls32), (iou_reg16, iou_reg32) = aggregate.mca_forward(
             lay, w.agg_iou, bank_cls, bank_reg, bank_score, n_rows_dev, n_loc_dev, need_reg=True,
             sim_thresh=cfg.sim_thresh, conf_sim_thresh=cfg.conf_sim_thresh)
+        ev_fork = torch.cuda.Event()
+        ev_fork.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ev_fork)
+            (agg_cls16, agg_cls32), _ = aggregate.mca_forward(lay, w.agg, bank_cls, bank_reg, bank_score, n_rows_dev,
+                                                              n_loc_dev, need_reg=False, sim_thresh=cfg.sim_thresh,
+                                                              conf_sim_thresh=cfg.conf_sim_thresh)
+            _, cls_logits = ops.linear(agg_cls16, w.cls_w, w.cls_b, m_dev=n_loc_dev, want16=False, want32=True)
+            ev_join = torch.cuda.Event()
+            ev_join.record(side)
+        for t in (cls_logits, agg_cls32):
+            t.record_stream(main)
 
         # ---- K5: CAFM --------------------------------------------------------------------------------
         if state is None:
@@ -137,7 +147,7 @@ class AggregationStage:
             resume = torch.zeros(B, dtype=torch.int32, device=dev)
         cafm16, cafm32, perm, te32 = self.run_cafm(lay, bank_reg, bank_edge, iou_reg32, iou_cls32, time_embedding, kmax,
                                                    state, resume, status, want_debug=trace is not None)
-        f32z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
+        f32z = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731  (fully written before read)
 
         # ---- fc_reg_matcher, TaskAligned, prediction heads ---------------------------------------------
         matched16, matched32 = ops.linear(cafm16, w.fc_w, w.fc_b, m_dev=n_loc_dev, want16=True, want32=trace is not None)
@@ -148,17 +158,17 @@ class AggregationStage:
         ops.call("tscd_frame_attention", L.FrameAttentionArgs, num_frames=B * Lf, heads=8, head_dim=(4 * D) // 8,
                  lrow_off=lay.lrow_off, q=ta_q, ldq=ta_q.stride(0), k=ta_kv, ldk=ta_kv.stride(0),
                  v=ta_kv[:, 4 * D:], ldv=ta_kv.stride(0), out=att, ldo=att.stride(0))
-        objref16 = torch.zeros(loc_cap, 4 * D, dtype=dt, device=dev)
+        objref16 = torch.empty(loc_cap, 4 * D, dtype=dt, device=dev)
         objref32 = f32z(loc_cap, 4 * D) if trace is not None else None
         ops.call("tscd_residual_ln2", L.ResidualLn2Args, rows_cap=loc_cap, dim=4 * D, n_rows=n_loc_dev, x=iou_reg32, r=att,
                  w_a=w.ta_ln_w, b_a=w.ta_ln_b, w_b=w.ta_dec_w, b_b=w.ta_dec_b, out_dtype=dt, out16=objref16, out32=objref32)
         _, obj_logits = ops.linear(objref16, w.obj_w, w.obj_b, m_dev=n_loc_dev, want16=False, want32=True)
-        _, cls_logits = ops.linear(agg_cls16, w.cls_w, w.cls_b, m_dev=n_loc_dev, want16=False, want32=True)
+        main.wait_event(ev_join)                 # classification branch joins here
 
         # ---- final per-class expansion + NMS ---------------------------------------------------------------
         nlf = B * Lf
         rcap, ocap = kmax * C, kmax
-        i32 = lambda *s: torch.zeros(*s, dtype=torch.int32, device=dev)  # noqa: E731
+        i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)  # noqa: E731
         r = dict(box=f32z(nlf, rcap, 4), score=f32z(nlf, rcap), cls=i32(nlf, rcap), obj=f32z(nlf, rcap),
                  cscore=f32z(nlf, rcap), count=i32(nlf))
         o = dict(box=f32z(nlf, ocap, 4), score=f32z(nlf, ocap), cls=i32(nlf, ocap), obj=f32z(nlf, ocap),
@@ -195,10 +205,10 @@ class AggregationStage:
         assert te16.shape == (B * Lf, 256)
         assert state.slots == B and state.kmax == kmax
         _, te32 = ops.linear(te16, w.ape_w, w.ape_b, want16=False, want32=True)
-        f32z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
+        f32z = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731  (fully written before read)
         feat, edge, kin = f32z(loc_cap, D), f32z(loc_cap, D), f32z(loc_cap, D)
-        feat16 = torch.zeros(loc_cap, D, dtype=dt, device=dev)
-        kin16 = torch.zeros(loc_cap, D, dtype=dt, device=dev)
+        feat16 = torch.empty(loc_cap, D, dtype=dt, device=dev)
+        kin16 = torch.empty(loc_cap, D, dtype=dt, device=dev)
         norm_reg, norm_cls = f32z(loc_cap), f32z(loc_cap)
         ops.call("tscd_cafm_prep", L.CafmPrepArgs, B=B, F=F, L=Lf, D=D, bank_dtype=dt, row_off=lay.row_off,
                  lrow_off=lay.lrow_off, bank_reg=bank_reg, bank_edge=bank_edge, time_emb=te32, se_w1=w.se_w1,
@@ -206,16 +216,16 @@ class AggregationStage:
                  kin16=kin16, kin=kin, norm_reg=norm_reg, norm_cls=norm_cls)
         _, kproj = ops.linear(kin16, w.cafm_wk, m_dev=n_loc_dev, want16=False, want32=True)
         _, vproj = ops.linear(feat16, w.cafm_wv, m_dev=n_loc_dev, want16=False, want32=True)
-        cafm16 = torch.zeros(loc_cap, D, dtype=dt, device=dev)
+        cafm16 = torch.empty(loc_cap, D, dtype=dt, device=dev)
         cafm32 = f32z(loc_cap, D) if want_debug else None
-        perm = torch.zeros(loc_cap, dtype=torch.int32, device=dev) if want_debug else None
+        perm = torch.empty(loc_cap, dtype=torch.int32, device=dev) if want_debug else None
         cost_full = f32z(B * Lf, kmax, kmax)
-        ref_n = torch.zeros(B * Lf, dtype=torch.int32, device=dev)
+        ref_n = torch.empty(B * Lf, dtype=torch.int32, device=dev)
         ops.call("tscd_cafm_cost", L.CafmCostArgs, B=B, L=Lf, D=D, kmax=kmax, lrow_off=lay.lrow_off, resume=resume,
                  st_n=state.n, emb_reg=emb_reg32, emb_cls=emb_cls32, norm_reg=norm_reg, norm_cls=norm_cls,
                  st_reg=state.reg, st_cls=state.cls, st_nreg=state.nreg, st_ncls=state.ncls, cost=cost_full, ref_n=ref_n)
-        lap_col = torch.full((B * Lf, kmax), -1, dtype=torch.int32, device=dev)
-        lap_row = torch.full((B * Lf, kmax), -1, dtype=torch.int32, device=dev)
+        lap_col = torch.empty(B * Lf, kmax, dtype=torch.int32, device=dev)
+        lap_row = torch.empty(B * Lf, kmax, dtype=torch.int32, device=dev)
         ops.call("tscd_cafm_lap", L.CafmLapArgs, num_frames=B * Lf, kmax=kmax, lrow_off=lay.lrow_off, ref_n=ref_n, cost=cost_full,
                  lap_col=lap_col, lap_row=lap_row)
         ops.call("tscd_cafm_chain", L.CafmChainArgs, B=B, F=F, L=Lf, D=D, kmax=kmax, out_dtype=dt, row_off=lay.row_off,
