@@ -111,10 +111,25 @@ class AggregationStage:
 
         # ---- K1-K3: selection + bank (operand arrays are read in 128-row TMA boxes: capacity padded) ------
         row_cap = _r128(B * F * kmax) + 128
-        loc_cap = _r128(B * Lf * kmax)
-        nk_pitch = _r128(F * kmax)
         sel = _selection.select_and_gather(head, feats, feat_dtype, D, cfg.selection, bank_dtype=dt, status=status,
                                            bank_rows=row_cap)
+        return self.forward_from_bank(sel, B, F, Lf, kmax, time_embedding, state=state, resume=resume, trace=trace,
+                                      status=status)
+
+    # ------------------------------------------------------------------------------------------------------
+    def forward_from_bank(self, sel, B: int, F: int, Lf: int, kmax: int, time_embedding, state=None, resume=None,
+                          trace=None, status=None, before_cafm=None, after_cafm=None):
+        """Everything after K1-K3.  `sel` holds the packed clip bank (bank_cls/reg/edge/score with >= _r128(B*F*kmax)+128
+        rows), sel_count [B*F], row_off [B*F+1] and sel_rows [B*F,kmax,7+C] (only local frames' rows are read).
+        `before_cafm(state)` / `after_cafm(state)` let a caller hand the CAFM memory from rank to rank."""
+        cfg, w, dev, dt = self.cfg, self.w, self.device, self.cfg.dtype
+        C, D = cfg.num_classes, cfg.dim
+        if status is None:
+            status = torch.zeros(1, dtype=torch.int32, device=dev)
+        row_cap = sel["bank_cls"].shape[0]
+        assert row_cap >= _r128(B * F * kmax) + 128
+        loc_cap = _r128(B * Lf * kmax)
+        nk_pitch = _r128(F * kmax)
         bank_cls, bank_reg, bank_edge, bank_score = sel["bank_cls"], sel["bank_reg"], sel["bank_edge"], sel["bank_score"]
         lay = aggregate.make_layout(sel["sel_count"], B, F, Lf, row_cap, loc_cap, nk_pitch, dt, row_off=sel["row_off"])
         n_rows_dev, n_loc_dev = lay.row_off[-1:], lay.lrow_off[-1:]
@@ -145,8 +160,12 @@ class AggregationStage:
             state = CAFMState(B, kmax, D, dev)
         if resume is None:
             resume = torch.zeros(B, dtype=torch.int32, device=dev)
+        if before_cafm is not None:
+            before_cafm(state)
         cafm16, cafm32, perm, te32 = self.run_cafm(lay, bank_reg, bank_edge, iou_reg32, iou_cls32, time_embedding, kmax,
                                                    state, resume, status, want_debug=trace is not None)
+        if after_cafm is not None:
+            after_cafm(state)
         f32z = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731  (fully written before read)
 
         # ---- fc_reg_matcher, TaskAligned, prediction heads ---------------------------------------------
