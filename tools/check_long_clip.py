@@ -17,8 +17,9 @@ sys.path.insert(0, ROOT)
 
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
-    dev = torch.device("cuda")
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     from tscd_b200 import ops, parallel, selection, stage, weights
     C, D = 25, 256
@@ -39,7 +40,7 @@ def main():
     kmax = cfg.selection.max_keep(A)
 
     def run_sel(frames):
-        h = ops.HeadViews.from_fused(head[frames].cuda(), an, apply_sigmoid=True if False else False, apply_decode=True)
+        h = ops.HeadViews.from_fused(head[frames].cuda(), an, apply_sigmoid=False, apply_decode=True)
         fv = [f[frames].cuda().contiguous() for f in feats]
         views = tuple(ops.view_rowmajor(f, an) for f in fv)
         rows_cap = ((len(frames) * kmax + 127) // 128) * 128 + 128
