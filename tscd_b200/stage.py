@@ -117,6 +117,31 @@ class AggregationStage:
                                       status=status)
 
     # ------------------------------------------------------------------------------------------------------
+    def capture(self, head: ops.HeadViews, feats, feat_dtype, time_embedding: torch.Tensor, B: int, F: int, Lf: int,
+                state: Optional["CAFMState"] = None, resume: Optional[torch.Tensor] = None, warmup: int = 2):
+        """Capture one forward() over FIXED input buffers into a CUDA graph (the stage has no host sync, so the whole
+        launch sequence -- ~130 kernels on two streams -- replays from one cudaGraphLaunch).  Returns (graph, out):
+        refill the input tensors in place, call graph.replay(), read `out` (same dict forward() returns)."""
+        A = head.anchors.num_anchors
+        kmax = self.cfg.selection.max_keep(A)
+        if state is None:
+            state = CAFMState(B, kmax, self.cfg.dim, self.device)
+        if resume is None:
+            resume = torch.zeros(B, dtype=torch.int32, device=self.device)
+        te = time_embedding.to(self.device)
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):                     # warm-up on a side stream (lazy module loading, attribute setting)
+            for _ in range(warmup):
+                self.forward(head, feats, feat_dtype, te, B, F, Lf, state=state, resume=resume)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.forward(head, feats, feat_dtype, te, B, F, Lf, state=state, resume=resume)
+        return graph, out
+
+    # ------------------------------------------------------------------------------------------------------
     def forward_from_bank(self, sel, B: int, F: int, Lf: int, kmax: int, time_embedding, state=None, resume=None,
                           trace=None, status=None, before_cafm=None, after_cafm=None):
         """Everything after K1-K3.  `sel` holds the packed clip bank (bank_cls/reg/edge/score with >= _r128(B*F*kmax)+128
@@ -152,8 +177,9 @@ class AggregationStage:
             _, cls_logits = ops.linear(agg_cls16, w.cls_w, w.cls_b, m_dev=n_loc_dev, want16=False, want32=True)
             ev_join = torch.cuda.Event()
             ev_join.record(side)
-        for t in (cls_logits, agg_cls32):
-            t.record_stream(main)
+        if not torch.cuda.is_current_stream_capturing():
+            for t in (cls_logits, agg_cls32):
+                t.record_stream(main)
 
         # ---- K5: CAFM --------------------------------------------------------------------------------
         if state is None:
