@@ -35,19 +35,24 @@ struct GemmParams {
     int is_bf16;
 };
 
+// Persistent, warp-specialised: every CTA walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...  (n fastest, so
+// CTAs running at the same time share their A rows in L2).  Two TMEM accumulator stages let the epilogue of tile i
+// overlap the TMA/MMA main loop of tile i+1; the smem ring keeps filling across tile boundaries.
+constexpr int kAccStages = 2;
+
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                 const __grid_constant__ CUtensorMap tmap_w,
                                                                 const GemmParams p) {
     using namespace tc;
-    const int m0 = blockIdx.y * kGemmBM;
-    const int n0 = blockIdx.x * BN;
     int M = p.M;
     if (p.m_dev) M = min(M, __ldg(p.m_dev));
-    if (m0 >= M) return;  // uniform over the CTA, before any barrier / TMEM state exists
+    const int tiles_n = (p.N + BN - 1) / BN;
+    const int tiles_m = (M + kGemmBM - 1) / kGemmBM;      // only tiles with valid rows exist
+    const int num_tiles = tiles_m * tiles_n;
+    if ((int)blockIdx.x >= num_tiles) return;             // uniform over the CTA, before any barrier / TMEM state exists
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // 1024-byte alignment is required by the 128-byte swizzle
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kABytes = kGemmBM * kGemmBK * 2;
     constexpr int kWBytes = BN * kGemmBK * 2;
@@ -55,7 +60,8 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
     unsigned char* sW = smem + kGemmStages * kABytes;
     __shared__ __align__(8) uint64_t full_bar[kGemmStages];
     __shared__ __align__(8) uint64_t empty_bar[kGemmStages];
-    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ __align__(8) uint64_t tmem_full_bar[kAccStages];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[kAccStages];
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5;
@@ -66,10 +72,10 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_w);
         for (int s = 0; s < kGemmStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&tmem_full_bar, 1);
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<BN>(&tmem_base_smem);
+    if (warp == 1) tmem_alloc<kAccStages * BN>(&tmem_base_smem);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -77,92 +83,114 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kGemmStages;
-                const uint32_t ph = (kb / kGemmStages) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1, 100 + s);
-                mbar_expect_tx(&full_bar[s], kABytes + kWBytes);
-                tma_load_2d(sA + s * kABytes, &tmap_a, &full_bar[s], kb * kGemmBK, m0);
-                tma_load_2d(sW + s * kWBytes, &tmap_w, &full_bar[s], kb * kGemmBK, n0);
+            uint32_t it = 0;   // running k-block counter across tiles -> ring stage / phase
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int m0 = (t / tiles_n) * kGemmBM, n0 = (t % tiles_n) * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % kGemmStages;
+                    const uint32_t ph = (it / kGemmStages) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1, 100 + s);
+                    mbar_expect_tx(&full_bar[s], kABytes + kWBytes);
+                    tma_load_2d(sA + s * kABytes, &tmap_a, &full_bar[s], kb * kGemmBK, m0);
+                    tma_load_2d(sW + s * kWBytes, &tmap_w, &full_bar[s], kb * kGemmBK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc_f16(p.is_bf16, kGemmBM, BN);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kGemmStages;
-                const uint32_t ph = (kb / kGemmStages) & 1;
-                mbar_wait(&full_bar[s], ph, 110 + s);
+            uint32_t it = 0, ti = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+                const int acc = ti % kAccStages;
+                const uint32_t aph = (ti / kAccStages) & 1;
+                mbar_wait(&tmem_empty_bar[acc], aph ^ 1, 130 + acc);     // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + s * kABytes));
-                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sW + s * kWBytes));
+                const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % kGemmStages;
+                    const uint32_t ph = (it / kGemmStages) & 1;
+                    mbar_wait(&full_bar[s], ph, 110 + s);
+                    tc_fence_after();
+                    const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + s * kABytes));
+                    const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sW + s * kWBytes));
 #pragma unroll
-                for (int k = 0; k < kGemmBK / 16; ++k) {
-                    // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
-                    umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < kGemmBK / 16; ++k) {
+                        // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
+                        umma_f16(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[s]);
                 }
-                umma_commit(&empty_bar[s]);
+                umma_commit(&tmem_full_bar[acc]);
             }
-            umma_commit(&tmem_full_bar);
         }
     } else {
         // epilogue warps 2..5 own TMEM lane quadrant (warp % 4)
         const int q = warp & 3;
-        mbar_wait(&tmem_full_bar, 0, 120);
-        tc_fence_after();
-        const int row = m0 + q * 32 + lane;
-        const bool row_ok = row < M;
+        uint32_t ti = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+            const int m0 = (t / tiles_n) * kGemmBM, n0 = (t % tiles_n) * BN;
+            const int acc = ti % kAccStages;
+            const uint32_t aph = (ti / kAccStages) & 1;
+            mbar_wait(&tmem_full_bar[acc], aph, 120 + acc);
+            tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < M;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            tmem_ld_wait();
-            const int col0 = n0 + c0;
-            if (!row_ok || col0 >= p.N) continue;
-            float v[32];
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+                tmem_ld_wait();
+                const int col0 = n0 + c0;
+                if (!row_ok || col0 >= p.N) continue;
+                float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                v[j] = __uint_as_float(r[j]);
-                if (p.bias && col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
-            }
-            const bool full = (col0 + 32 <= p.N);
-            if (p.out32) {
-                float* o = p.out32 + (int64_t)row * p.ld32 + col0;
-                if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-                    for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = v[j];
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = __uint_as_float(r[j]);
+                    if (p.bias && col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
                 }
-            }
-            if (p.out16) {
-                uint32_t pk[16];
+                const bool full = (col0 + 32 <= p.N);
+                if (p.out32) {
+                    float* o = p.out32 + (int64_t)row * p.ld32 + col0;
+                    if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    if (p.is_bf16) {
-                        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                        pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     } else {
-                        __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-                        pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                        for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = v[j];
                     }
                 }
-                uint16_t* o = reinterpret_cast<uint16_t*>(p.out16) + (int64_t)row * p.ld16 + col0;
-                if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                if (p.out16) {
+                    uint32_t pk[16];
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(o + 2 * j) = make_uint4(pk[j], pk[j + 1], pk[j + 2], pk[j + 3]);
-                } else {
-                    const uint16_t* h = reinterpret_cast<const uint16_t*>(pk);
-                    for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = h[j];
+                    for (int j = 0; j < 16; ++j) {
+                        if (p.is_bf16) {
+                            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                            pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                        } else {
+                            __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                            pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                    }
+                    uint16_t* o = reinterpret_cast<uint16_t*>(p.out16) + (int64_t)row * p.ld16 + col0;
+                    if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(o + 2 * j) = make_uint4(pk[j], pk[j + 1], pk[j + 2], pk[j + 3]);
+                    } else {
+                        const uint16_t* h = reinterpret_cast<const uint16_t*>(pk);
+                        for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = h[j];
+                    }
                 }
             }
+            // this warp has read its quadrant of the accumulator: release it to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<BN>(tmem_base);
+        tmem_dealloc<kAccStages * BN>(tmem_base);
     }
 }
 
@@ -207,7 +235,14 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmP
             return TSCD_ERR_CUDA;
         attr_set = true;
     }
-    dim3 grid((p.N + BN - 1) / BN, (p.M + kGemmBM - 1) / kGemmBM);
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int tiles = ((p.N + BN - 1) / BN) * ((p.M + kGemmBM - 1) / kGemmBM);
+    const int grid = tiles < 2 * num_sms ? tiles : 2 * num_sms;      // two resident CTAs per SM (97 KB smem, 2 x 2*BN TMEM columns)
     gemm_tn_kernel<BN><<<grid, kGemmThreads, smem, st>>>(ta, tw, p);
     return cudaGetLastError() == cudaSuccess ? TSCD_OK : TSCD_ERR_CUDA;
 }
