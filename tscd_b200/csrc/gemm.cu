@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
     constexpr int kWBytes = BN * kGemmBK * 2;
     unsigned char* sA = smem;
     unsigned char* sW = smem + kGemmStages * kABytes;
+    unsigned char* sStage = sW + kGemmStages * kWBytes;      // 4 epilogue warps x (32 rows x 64 B)
     __shared__ __align__(8) uint64_t full_bar[kGemmStages];
     __shared__ __align__(8) uint64_t empty_bar[kGemmStages];
     __shared__ __align__(8) uint64_t tmem_full_bar[kAccStages];
@@ -126,6 +127,9 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
     } else {
         // epilogue warps 2..5 own TMEM lane quadrant (warp % 4)
         const int q = warp & 3;
+        unsigned char* stg = sStage + q * 2048;
+        const bool al16 = p.out16 && (p.ld16 % 8) == 0 && (reinterpret_cast<uintptr_t>(p.out16) & 15) == 0;
+        const bool al32 = p.out32 && (p.ld32 % 4) == 0 && (reinterpret_cast<uintptr_t>(p.out32) & 15) == 0;
         uint32_t ti = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
             const int m0 = (t / tiles_n) * kGemmBM, n0 = (t % tiles_n) * BN;
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
                 tmem_ld_wait();
                 const int col0 = n0 + c0;
-                if (!row_ok || col0 >= p.N) continue;
+                if (col0 >= p.N) continue;
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -149,15 +153,9 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
                     if (p.bias && col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
                 }
                 const bool full = (col0 + 32 <= p.N);
-                if (p.out32) {
-                    float* o = p.out32 + (int64_t)row * p.ld32 + col0;
-                    if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
-                        for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = v[j];
-                    }
-                }
+                const int row_base = m0 + q * 32;
+                // Full chunks go through a per-warp 32 x 64-byte staging tile so that every store instruction writes
+                // 8 rows x 64 contiguous bytes (whole 32-byte sectors) instead of 32 scattered 16-byte pieces.
                 if (p.out16) {
                     uint32_t pk[16];
 #pragma unroll
@@ -170,13 +168,48 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
                             pk[j] = *reinterpret_cast<uint32_t*>(&h);
                         }
                     }
-                    uint16_t* o = reinterpret_cast<uint16_t*>(p.out16) + (int64_t)row * p.ld16 + col0;
-                    if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                    uint16_t* obase = reinterpret_cast<uint16_t*>(p.out16);
+                    if (full && al16) {
+                        __syncwarp();
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(o + 2 * j) = make_uint4(pk[j], pk[j + 1], pk[j + 2], pk[j + 3]);
-                    } else {
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        __syncwarp();
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int rr = 8 * k + (lane >> 2), ch = lane & 3;
+                            const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+                            if (row_base + rr < M)
+                                *reinterpret_cast<uint4*>(obase + (int64_t)(row_base + rr) * p.ld16 + col0 + ch * 8) = val;
+                        }
+                    } else if (row_ok) {
                         const uint16_t* h = reinterpret_cast<const uint16_t*>(pk);
+                        uint16_t* o = obase + (int64_t)row * p.ld16 + col0;
                         for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = h[j];
+                    }
+                }
+                if (p.out32) {
+                    if (full && al32) {
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            __syncwarp();
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<float4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                                    make_float4(v[hh * 16 + 4 * j], v[hh * 16 + 4 * j + 1], v[hh * 16 + 4 * j + 2], v[hh * 16 + 4 * j + 3]);
+                            __syncwarp();
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int rr = 8 * k + (lane >> 2), ch = lane & 3;
+                                const float4 val = *reinterpret_cast<const float4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+                                if (row_base + rr < M)
+                                    *reinterpret_cast<float4*>(p.out32 + (int64_t)(row_base + rr) * p.ld32 + col0 + hh * 16 + ch * 4) = val;
+                            }
+                        }
+                    } else if (row_ok) {
+                        float* o = p.out32 + (int64_t)row * p.ld32 + col0;
+                        for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = v[j];
                     }
                 }
             }
@@ -228,7 +261,7 @@ int make_tmap_kmajor(CUtensorMap* m, const void* ptr, int is_bf16, int64_t rows,
 
 template <int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
-    constexpr size_t smem = (size_t)kGemmStages * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + 1024;
+    constexpr size_t smem = (size_t)kGemmStages * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + 4 * 2048 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
