@@ -23,7 +23,7 @@ namespace tscd {
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
 constexpr int kGemmStages = 3;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps
 
 struct GemmParams {
     int M, N, K;
@@ -40,7 +40,7 @@ struct GemmParams {
 // overlap the TMA/MMA main loop of tile i+1; the smem ring keeps filling across tile boundaries.
 constexpr int kAccStages = 2;
 
-template <int BN>
+template <int BN, bool BF16>
 __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                 const __grid_constant__ CUtensorMap tmap_w,
                                                                 const GemmParams p) {
@@ -52,18 +52,21 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
     const int num_tiles = tiles_m * tiles_n;
     if ((int)blockIdx.x >= num_tiles) return;             // uniform over the CTA, before any barrier / TMEM state exists
 
+    // No static shared memory in this kernel: the dynamic window then starts at the CTA's shared base, which honours
+    // the 1024-byte alignment the 128-byte swizzle needs (no over-allocation -> two CTAs fit in 227 KB).
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* smem = smem_raw;
     constexpr int kABytes = kGemmBM * kGemmBK * 2;
     constexpr int kWBytes = BN * kGemmBK * 2;
     unsigned char* sA = smem;
     unsigned char* sW = smem + kGemmStages * kABytes;
-    unsigned char* sStage = sW + kGemmStages * kWBytes;      // 4 epilogue warps x (32 rows x 64 B)
-    __shared__ __align__(8) uint64_t full_bar[kGemmStages];
-    __shared__ __align__(8) uint64_t empty_bar[kGemmStages];
-    __shared__ __align__(8) uint64_t tmem_full_bar[kAccStages];
-    __shared__ __align__(8) uint64_t tmem_empty_bar[kAccStages];
-    __shared__ uint32_t tmem_base_smem;
+    unsigned char* sStage = sW + kGemmStages * kWBytes;      // 8 epilogue warps x (32 rows x 64 B)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + 8 * 2048);
+    uint64_t* empty_bar = full_bar + kGemmStages;
+    uint64_t* tmem_full_bar = empty_bar + kGemmStages;
+    uint64_t* tmem_empty_bar = tmem_full_bar + kAccStages;
+    uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(tmem_empty_bar + kAccStages);
+    if ((smem_u32(smem) & 1023u) != 0) __trap();             // alignment contract violated
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_w);
         for (int s = 0; s < kGemmStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 8); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<kAccStages * BN>(&tmem_base_smem);
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_f16(p.is_bf16, kGemmBM, BN);
+            const uint32_t idesc = make_idesc_f16(BF16, kGemmBM, BN);
             uint32_t it = 0, ti = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
                 const int acc = ti % kAccStages;
@@ -125,9 +128,12 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
             }
         }
     } else {
-        // epilogue warps 2..5 own TMEM lane quadrant (warp % 4)
+        // 8 epilogue warps: warp % 4 selects the TMEM lane quadrant (hardware rule), (warp - 2) / 4 the column half.
+        // TMEM loads are software-pipelined: chunk c+1 is in flight while chunk c is converted and stored.
         const int q = warp & 3;
-        unsigned char* stg = sStage + q * 2048;
+        const int half = (warp - 2) >> 2;
+        constexpr int kChunks = BN / 64;                    // 32-column chunks per warp (half of the tile's columns)
+        unsigned char* stg = sStage + (warp - 2) * 2048;
         const bool al16 = p.out16 && (p.ld16 % 8) == 0 && (reinterpret_cast<uintptr_t>(p.out16) & 15) == 0;
         const bool al32 = p.out32 && (p.ld32 % 4) == 0 && (reinterpret_cast<uintptr_t>(p.out32) & 15) == 0;
         uint32_t ti = 0;
@@ -137,83 +143,90 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
             const uint32_t aph = (ti / kAccStages) & 1;
             mbar_wait(&tmem_full_bar[acc], aph, 120 + acc);
             tc_fence_after();
-            const int row = m0 + q * 32 + lane;
+            const int row_base = m0 + q * 32;
+            const int row = row_base + lane;
             const bool row_ok = row < M;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
-                tmem_ld_wait();
-                const int col0 = n0 + c0;
-                if (col0 >= p.N) continue;
-                float v[32];
+            const uint32_t tsrc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
+            uint32_t rbuf[2][32];
+            tmem_ld_32x32(tsrc, rbuf[0]);
+            tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    v[j] = __uint_as_float(r[j]);
-                    if (p.bias && col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
-                }
-                const bool full = (col0 + 32 <= p.N);
-                const int row_base = m0 + q * 32;
-                // Full chunks go through a per-warp 32 x 64-byte staging tile so that every store instruction writes
-                // 8 rows x 64 contiguous bytes (whole 32-byte sectors) instead of 32 scattered 16-byte pieces.
-                if (p.out16) {
-                    uint32_t pk[16];
+            for (int c = 0; c < kChunks; ++c) {
+                if (c + 1 < kChunks) tmem_ld_32x32(tsrc + (uint32_t)((c + 1) * 32), rbuf[(c + 1) & 1]);
+                const uint32_t* r = rbuf[c & 1];
+                const int col0 = n0 + half * (BN / 2) + c * 32;
+                if (col0 < p.N) {
+                    float v[32];
+                    if (p.bias) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (p.is_bf16) {
-                            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                            pk[j] = *reinterpret_cast<uint32_t*>(&h);
-                        } else {
-                            __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-                            pk[j] = *reinterpret_cast<uint32_t*>(&h);
-                        }
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + ((col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                     }
-                    uint16_t* obase = reinterpret_cast<uint16_t*>(p.out16);
-                    if (full && al16) {
-                        __syncwarp();
+                    const bool full = (col0 + 32 <= p.N);
+                    // Full chunks go through a per-warp 32 x 64-byte staging tile so that every store instruction
+                    // writes 8 rows x 64 contiguous bytes (whole sectors) instead of 32 scattered 16-byte pieces.
+                    if (p.out16) {
+                        uint32_t pk[16];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
-                                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                        __syncwarp();
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int rr = 8 * k + (lane >> 2), ch = lane & 3;
-                            const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
-                            if (row_base + rr < M)
-                                *reinterpret_cast<uint4*>(obase + (int64_t)(row_base + rr) * p.ld16 + col0 + ch * 8) = val;
+                        for (int j = 0; j < 16; ++j) {
+                            if (BF16) {
+                                __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                            } else {
+                                __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                            }
                         }
-                    } else if (row_ok) {
-                        const uint16_t* h = reinterpret_cast<const uint16_t*>(pk);
-                        uint16_t* o = obase + (int64_t)row * p.ld16 + col0;
-                        for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = h[j];
-                    }
-                }
-                if (p.out32) {
-                    if (full && al32) {
-#pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
+                        uint16_t* obase = reinterpret_cast<uint16_t*>(p.out16);
+                        if (full && al16) {
                             __syncwarp();
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
-                                *reinterpret_cast<float4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
-                                    make_float4(v[hh * 16 + 4 * j], v[hh * 16 + 4 * j + 1], v[hh * 16 + 4 * j + 2], v[hh * 16 + 4 * j + 3]);
+                                *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                                    make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
                             __syncwarp();
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const int rr = 8 * k + (lane >> 2), ch = lane & 3;
-                                const float4 val = *reinterpret_cast<const float4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+                                const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
                                 if (row_base + rr < M)
-                                    *reinterpret_cast<float4*>(p.out32 + (int64_t)(row_base + rr) * p.ld32 + col0 + hh * 16 + ch * 4) = val;
+                                    *reinterpret_cast<uint4*>(obase + (int64_t)(row_base + rr) * p.ld16 + col0 + ch * 8) = val;
                             }
+                        } else if (row_ok) {
+                            const uint16_t* h = reinterpret_cast<const uint16_t*>(pk);
+                            uint16_t* o = obase + (int64_t)row * p.ld16 + col0;
+                            for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = h[j];
                         }
-                    } else if (row_ok) {
-                        float* o = p.out32 + (int64_t)row * p.ld32 + col0;
-                        for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = v[j];
+                    }
+                    if (p.out32) {
+                        if (full && al32) {
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                __syncwarp();
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    *reinterpret_cast<float4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                                        make_float4(v[hh * 16 + 4 * j], v[hh * 16 + 4 * j + 1], v[hh * 16 + 4 * j + 2], v[hh * 16 + 4 * j + 3]);
+                                __syncwarp();
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const int rr = 8 * k + (lane >> 2), ch = lane & 3;
+                                    const float4 val = *reinterpret_cast<const float4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+                                    if (row_base + rr < M)
+                                        *reinterpret_cast<float4*>(p.out32 + (int64_t)(row_base + rr) * p.ld32 + col0 + hh * 16 + ch * 4) = val;
+                                }
+                            }
+                        } else if (row_ok) {
+                            float* o = p.out32 + (int64_t)row * p.ld32 + col0;
+                            for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = v[j];
+                        }
                     }
                 }
+                if (c + 1 < kChunks) tmem_ld_wait();
             }
-            // this warp has read its quadrant of the accumulator: release it to the MMA warp
+            // this warp has read its part of the accumulator: release it to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -259,12 +272,12 @@ int make_tmap_kmajor(CUtensorMap* m, const void* ptr, int is_bf16, int64_t rows,
     return r == CUDA_SUCCESS ? TSCD_OK : TSCD_ERR_CUDA;
 }
 
-template <int BN>
+template <int BN, bool BF16>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
-    constexpr size_t smem = (size_t)kGemmStages * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + 4 * 2048 + 1024;
+    constexpr size_t smem = (size_t)kGemmStages * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + 8 * 2048 + 128;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(gemm_tn_kernel<BN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return TSCD_ERR_CUDA;
         attr_set = true;
     }
@@ -276,7 +289,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmP
     }
     const int tiles = ((p.N + BN - 1) / BN) * ((p.M + kGemmBM - 1) / kGemmBM);
     const int grid = tiles < 2 * num_sms ? tiles : 2 * num_sms;      // two resident CTAs per SM (97 KB smem, 2 x 2*BN TMEM columns)
-    gemm_tn_kernel<BN><<<grid, kGemmThreads, smem, st>>>(ta, tw, p);
+    gemm_tn_kernel<BN, BF16><<<grid, kGemmThreads, smem, st>>>(ta, tw, p);
     return cudaGetLastError() == cudaSuccess ? TSCD_OK : TSCD_ERR_CUDA;
 }
 
@@ -301,5 +314,6 @@ extern "C" int tscd_linear(const tscd_linear_args* a, void* stream) {
     p.ld16 = a->ld16; p.ld32 = a->ld32;
     p.is_bf16 = is_bf16;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    return BN == 64 ? launch_gemm<64>(ta, tw, p, st) : launch_gemm<128>(ta, tw, p, st);
+    if (is_bf16) return BN == 64 ? launch_gemm<64, true>(ta, tw, p, st) : launch_gemm<128, true>(ta, tw, p, st);
+    return BN == 64 ? launch_gemm<64, false>(ta, tw, p, st) : launch_gemm<128, false>(ta, tw, p, st);
 }
