@@ -90,7 +90,7 @@ struct ChainSmem {
 // ---------------------------------------------------------------------------------------------- matching costs
 // One CTA per (local frame, 32x32 tile): 128-dim slabs of the two 1024-dim embeddings staged in shared memory.
 __global__ void __launch_bounds__(256) cafm_cost_kernel(const tscd_cafm_cost_args a) {
-    __shared__ float tileA[32][129], tileB[32][129];
+    __shared__ __align__(16) float tileA[32][132], tileB[32][132];   // 4-float skew: float4 row reads are conflict-free
     const int lf = blockIdx.x, b = lf / a.L, f = lf - b * a.L;
     const int l0 = a.lrow_off[lf], n = a.lrow_off[lf + 1] - l0;
     if (n <= 0) {
@@ -135,11 +135,15 @@ __global__ void __launch_bounds__(256) cafm_cost_kernel(const tscd_cafm_cost_arg
             }
             __syncthreads();
             float x[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
-            for (int dd = 0; dd < 128; ++dd) {
-                const float q = tileB[lane][dd];
+            const float4* qrow = reinterpret_cast<const float4*>(tileB[lane]);
+#pragma unroll 4
+            for (int d4 = 0; d4 < 32; ++d4) {
+                const float4 q = qrow[d4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) x[k] = fmaf(tileA[pr + 8 * k][dd], q, x[k]);
+                for (int k = 0; k < 4; ++k) {
+                    const float4 p4 = reinterpret_cast<const float4*>(tileA[pr + 8 * k])[d4];   // broadcast
+                    x[k] = fmaf(p4.x, q.x, fmaf(p4.y, q.y, fmaf(p4.z, q.z, fmaf(p4.w, q.w, x[k]))));
+                }
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) { if (which == 0) accR[k] += x[k]; else accC[k] += x[k]; }

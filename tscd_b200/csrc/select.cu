@@ -29,9 +29,18 @@ __device__ void radix_select_kth(const uint32_t* keys, int n, int k, SelSmem* s,
         const int shift = 24 - 8 * pass;
         for (int i = threadIdx.x; i < 256; i += blockDim.x) s->hist[i] = 0;
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            uint32_t u = keys[i];
-            if ((u & mask) == prefix) atomicAdd(&s->hist[(u >> shift) & 255], 1);
+        // warp-aggregated histogram: sigmoid scores share a few exponent digits, so plain shared-memory atomics
+        // serialise on one bin; lanes with the same digit elect a leader that adds the group's population once
+        for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+            const int i = i0 + threadIdx.x;
+            const uint32_t u = i < n ? keys[i] : 0u;
+            const bool in = i < n && (u & mask) == prefix;
+            const unsigned act = __ballot_sync(0xffffffffu, in);
+            if (in) {
+                const uint32_t d = (u >> shift) & 255;
+                const unsigned peers = __match_any_sync(act, d);
+                if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s->hist[d], __popc(peers));
+            }
         }
         __syncthreads();
         if (threadIdx.x < 32) {

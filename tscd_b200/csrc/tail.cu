@@ -9,15 +9,16 @@
 namespace tscd {
 
 // ---------------------------------------------------------------------------------------------- frame attention
-// One CTA per (local frame, head).  Keys/values stream through shared memory in chunks of 64 with an online
-// softmax; each warp owns query rows, lanes own keys (scores) then output dims (weighted sum).
+// One CTA per (local frame, head).  Keys/values stream through shared memory in chunks of 64 (one chunk for the
+// usual <= 64 proposals per frame) with an online softmax; each warp owns query rows, lanes own keys (scores) then
+// output dims (weighted sum).  All shared-memory traffic is 128-bit: the kernel is shared-memory-bandwidth bound.
 constexpr int kFaChunk = 64;
 
-__global__ void __launch_bounds__(256) frame_attention_kernel(const tscd_frame_attention_args a) {
+__global__ void __launch_bounds__(256, 2) frame_attention_kernel(const tscd_frame_attention_args a) {
     extern __shared__ __align__(16) float fa_smem[];
     const int hd = a.head_dim;           // multiple of 32, <= 128
-    const int pitch = hd + 1;
-    float* sK = fa_smem;                  // [64][hd+1] normalised keys
+    const int pitch = hd + 4;            // rows stay 16-byte aligned; 4-float skew keeps float4 row reads conflict-free
+    float* sK = fa_smem;                  // [64][hd+4] normalised keys
     float* sV = sK + kFaChunk * pitch;    // [64][hd]
     float* sQ = sV + kFaChunk * hd;       // [8 warps][hd] normalised query rows
     const int lf = blockIdx.x, h = blockIdx.y;
@@ -26,6 +27,24 @@ __global__ void __launch_bounds__(256) frame_attention_kernel(const tscd_frame_a
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nd = hd / 32;               // output dims per lane (<= 4)
     float* myq = sQ + warp * hd;
+    const bool single = n <= kFaChunk;    // keys / values staged once for all query rows
+
+    auto stage = [&](int k0, int kc) {
+        for (int j = warp; j < kc; j += 8) {   // stage + normalise keys, copy values
+            const float* kr = a.k + (int64_t)(l0 + k0 + j) * a.ldk + h * hd;
+            const float* vr = a.v + (int64_t)(l0 + k0 + j) * a.ldv + h * hd;
+            float kv[4], ks = 0.f;
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (t < nd) { kv[t] = kr[lane + 32 * t]; ks = fmaf(kv[t], kv[t], ks); sV[j * hd + lane + 32 * t] = vr[lane + 32 * t]; }
+            ks = warp_sumf(ks);
+            const float inv = 1.f / sqrtf(ks);
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (t < nd) sK[j * pitch + lane + 32 * t] = kv[t] * inv;
+        }
+    };
+    if (single) { stage(0, n); __syncthreads(); }
 
     for (int rb = 0; rb < n; rb += 8) {   // 8 query rows per pass (one per warp)
         const int r = rb + warp;
@@ -36,24 +55,31 @@ __global__ void __launch_bounds__(256) frame_attention_kernel(const tscd_frame_a
         }
         qs = warp_sumf(qs);
         if (r_ok) { const float inv = 1.f / sqrtf(qs); for (int d = lane; d < hd; d += 32) myq[d] *= inv; }
+        __syncwarp();
         float m = -INFINITY, l = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
         for (int k0 = 0; k0 < n; k0 += kFaChunk) {
             const int kc = min(kFaChunk, n - k0);
-            __syncthreads();
-            for (int j = warp; j < kc; j += 8) {   // stage + normalise keys, copy values
-                const float* kr = a.k + (int64_t)(l0 + k0 + j) * a.ldk + h * hd;
-                const float* vr = a.v + (int64_t)(l0 + k0 + j) * a.ldv + h * hd;
-                float ks = 0.f;
-                for (int d = lane; d < hd; d += 32) { const float x = kr[d]; sK[j * pitch + d] = x; ks = fmaf(x, x, ks); sV[j * hd + d] = vr[d]; }
-                ks = warp_sumf(ks);
-                const float inv = 1.f / sqrtf(ks);
-                for (int d = lane; d < hd; d += 32) sK[j * pitch + d] *= inv;
+            if (!single) {
+                __syncthreads();
+                stage(k0, kc);
+                __syncthreads();
             }
-            __syncthreads();
             if (r_ok) {
-                float s0 = -INFINITY, s1 = -INFINITY;
-                if (lane < kc) { s0 = 0.f; for (int d = 0; d < hd; ++d) s0 = fmaf(myq[d], sK[lane * pitch + d], s0); }
-                if (lane + 32 < kc) { s1 = 0.f; for (int d = 0; d < hd; ++d) s1 = fmaf(myq[d], sK[(lane + 32) * pitch + d], s1); }
+                float s0 = 0.f, s1 = 0.f;
+                const float4* q4 = reinterpret_cast<const float4*>(myq);
+                const float4* ka = reinterpret_cast<const float4*>(sK + min(lane, kc - 1) * pitch);
+                const float4* kb = reinterpret_cast<const float4*>(sK + min(lane + 32, kc - 1) * pitch);
+                const bool two = kc > 32;
+                for (int d = 0; d < hd / 4; ++d) {
+                    const float4 qq = q4[d], x = ka[d];
+                    s0 = fmaf(qq.x, x.x, fmaf(qq.y, x.y, fmaf(qq.z, x.z, fmaf(qq.w, x.w, s0))));
+                    if (two) {
+                        const float4 y = kb[d];
+                        s1 = fmaf(qq.x, y.x, fmaf(qq.y, y.y, fmaf(qq.z, y.z, fmaf(qq.w, y.w, s1))));
+                    }
+                }
+                if (lane >= kc) s0 = -INFINITY;
+                if (lane + 32 >= kc) s1 = -INFINITY;
                 const float mn = fmaxf(m, warp_maxf(fmaxf(s0, s1)));
                 const float corr = expf(m - mn);
                 const float p0 = (lane < kc) ? expf(s0 - mn) : 0.f;
@@ -76,6 +102,7 @@ __global__ void __launch_bounds__(256) frame_attention_kernel(const tscd_frame_a
             for (int t = 0; t < 4; ++t)
                 if (t < nd) a.out[(int64_t)(l0 + r) * a.ldo + h * hd + lane + 32 * t] = acc[t] * inv;
         }
+        __syncwarp();
     }
 }
 
@@ -198,7 +225,7 @@ __global__ void final_rows_kernel(const tscd_final_rows_args a) {
 extern "C" int tscd_frame_attention(const tscd_frame_attention_args* a, void* stream) {
     using namespace tscd;
     if (!a || a->num_frames <= 0 || a->heads <= 0 || a->head_dim <= 0 || a->head_dim % 32 || a->head_dim > 128) return TSCD_ERR_INVALID_ARG;
-    const size_t smem = (size_t)(kFaChunk * (a->head_dim + 1) + kFaChunk * a->head_dim + 8 * a->head_dim) * sizeof(float);
+    const size_t smem = (size_t)(kFaChunk * (a->head_dim + 4) + kFaChunk * a->head_dim + 8 * a->head_dim) * sizeof(float);
     if (cudaFuncSetAttribute(frame_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
     frame_attention_kernel<<<dim3(a->num_frames, a->heads), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
     TSCD_CUDA_CHECK_LAUNCH();
