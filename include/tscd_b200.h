@@ -418,6 +418,10 @@ typedef struct {
 } tscd_final_rows_args;
 int tscd_final_rows(const tscd_final_rows_args* args, void* stream);
 
+/* Debug aid: cycles block 0 of the last tscd_cafm_chain launches spent per phase
+ * (0 assignment re-index, 1 query input, 2 q projection, 3 normalise, 4 attention, 5 norms/state, 6 state carry). */
+int tscd_debug_chain_clocks(long long* host_out8, int reset);
+
 /* Library / build information (also proves the .so was loaded). */
 const char* tscd_version(void);
 const char* tscd_last_cuda_error(void); /* text of the last CUDA runtime error seen by a TSCD_ERR_CUDA return */

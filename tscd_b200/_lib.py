@@ -153,6 +153,7 @@ SYMBOLS = [
     ("tscd_cafm_prep", C.c_int, [C.POINTER(CafmPrepArgs), C.c_void_p]),
     ("tscd_cafm_cost", C.c_int, [C.POINTER(CafmCostArgs), C.c_void_p]),
     ("tscd_cafm_lap", C.c_int, [C.POINTER(CafmLapArgs), C.c_void_p]),
+    ("tscd_debug_chain_clocks", C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
     ("tscd_cafm_chain", C.c_int, [C.POINTER(CafmChainArgs), C.c_void_p]),
     ("tscd_frame_attention", C.c_int, [C.POINTER(FrameAttentionArgs), C.c_void_p]),
     ("tscd_residual_ln2", C.c_int, [C.POINTER(ResidualLn2Args), C.c_void_p]),

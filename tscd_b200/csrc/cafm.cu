@@ -271,6 +271,13 @@ __device__ __forceinline__ void layer_norm_row(const float* x, const float* w, c
     for (int c = lane; c < D; c += 32) y[c] = (x[c] - mean) * rstd * w[c] + b[c];
 }
 
+// per-phase cycle counters of block 0 (debug aid, read with tscd_debug_chain_clocks)
+__device__ long long g_chain_clk[8];
+#define CHAIN_TICK(i)                                                                     \
+    do {                                                                                  \
+        if (blockIdx.x == 0 && threadIdx.x == 0) { const long long now__ = clock64(); g_chain_clk[i] += now__ - tick__; tick__ = now__; } \
+    } while (0)
+
 template <typename T>
 __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd_cafm_chain_args a) {
     extern __shared__ __align__(16) unsigned char chain_smem[];
@@ -293,6 +300,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
     for (int r = tid; r < kChainMax; r += kChainThreads) s.ord_prev[r] = r;   // carried state is already in matched order
     int last_l0 = -1;
     __syncthreads();
+    long long tick__ = clock64();
 
     for (int f = 0; f < a.L; ++f) {
         const int lf = b * a.L + f;
@@ -339,6 +347,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
             }
         }
         __syncthreads();
+        CHAIN_TICK(0);
         // ---- query input ----------------------------------------------------------------------------
         for (int t = tid; t < n * D; t += kChainThreads) {
             const int r = t / D, c = t - r * D;
@@ -354,6 +363,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
             qin[t] = v;
         }
         __syncthreads();
+        CHAIN_TICK(1);
         // ---- q = W_q qin  (thread = output channel; each half of the CTA owns every other block of 16 rows,
         //      so W_q^T is streamed from L2 once per 16 rows with coalesced loads) ------------------------
         {
@@ -374,6 +384,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
             }
         }
         __syncthreads();
+        CHAIN_TICK(2);
         // ---- per-head L2 normalisation of q and k (8 heads x 32) --------------------------------------
         for (int t = warp; t < n * 8 * 2; t += NW) {
             const int which = t & 1, rh = t >> 1, r = rh >> 3, h = rh & 7;
@@ -382,6 +393,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
             if (which == 0) qv[(int64_t)r * D + h * 32 + lane] = x / nn; else kh[(int64_t)r * D + h * 32 + lane] = x / nn;
         }
         __syncthreads();
+        CHAIN_TICK(3);
         // ---- attention over the current frame; qin is reused as the pre-norm output buffer [n, D] ----
         for (int t = warp; t < n * 8; t += NW) {
             const int r = t >> 3, h = t & 7;
@@ -412,6 +424,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
             __syncwarp();
         }
         __syncthreads();
+        CHAIN_TICK(4);
         // ---- norms, state update, scatter to the original order --------------------------------------
         for (int r = warp; r < n; r += NW) {
             layer_norm_row(qin + (int64_t)r * D, a.ln_w, a.ln_b, st_out + (int64_t)r * D, D, lane);   // new last_outputs
@@ -434,6 +447,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
         n_prev = n;
         last_l0 = l0;
         __syncthreads();
+        CHAIN_TICK(5);
     }
     // ---- carry the last frame's matching embeddings (in matched order) to the next call ----------------
     if (last_l0 >= 0) {
@@ -453,6 +467,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
         }
     }
     if (tid == 0) a.st_n[b] = n_prev;
+    __syncthreads();
+    CHAIN_TICK(6);
 }
 
 }  // namespace tscd
@@ -484,6 +500,16 @@ extern "C" int tscd_cafm_lap(const tscd_cafm_lap_args* a, void* stream) {
     if (cudaFuncSetAttribute(cafm_lap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
     cafm_lap_kernel<<<a->num_frames, 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
     TSCD_CUDA_CHECK_LAUNCH();
+    return TSCD_OK;
+}
+
+extern "C" int tscd_debug_chain_clocks(long long* out, int reset) {
+    using namespace tscd;
+    if (cudaMemcpyFromSymbol(out, g_chain_clk, sizeof(long long) * 8) != cudaSuccess) return TSCD_ERR_CUDA;
+    if (reset) {
+        long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (cudaMemcpyToSymbol(g_chain_clk, z, sizeof(z)) != cudaSuccess) return TSCD_ERR_CUDA;
+    }
     return TSCD_OK;
 }
 

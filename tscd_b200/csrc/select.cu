@@ -12,7 +12,7 @@
 
 namespace tscd {
 
-constexpr int kSelThreads = 256;
+constexpr int kSelThreads = 512;
 
 struct SelSmem {
     int hist[256];
@@ -102,8 +102,9 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const tscd_select_a
     const int A4 = (A + 3) & ~3;
     uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw);                     // [A] order-preserving selection key
     float* conf_s = reinterpret_cast<float*>(keys + A4);                        // [A] class max (mode A: pre-sigmoid)
-    int* sel = reinterpret_cast<int*>(conf_s + A4);                             // [A] selected anchor ids
-    unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(sel + A4);  // [pow2(pre_k)]
+    const int S4 = (min(A, args.cand_cap) + 3) & ~3;
+    int* sel = reinterpret_cast<int*>(conf_s + A4);                             // [min(A, cand_cap)] selected anchor ids
+    unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(sel + S4 + (S4 & 1 ? 1 : 0));  // [pow2(pre_k)], 8-byte aligned
     unsigned char* cls_s = reinterpret_cast<unsigned char*>(sortbuf + sort_cap); // [A] class arg-max
     __shared__ SelSmem s;
 
@@ -284,7 +285,8 @@ extern "C" int tscd_select(const tscd_select_args* a, void* stream) {
     int n64 = 1;
     if (a->mode == 0) while (n64 < (a->pre_k < A ? a->pre_k : A)) n64 <<= 1;
     if (a->num_classes > 255) return TSCD_ERR_UNSUPPORTED;
-    size_t smem = (size_t)((A + 3) & ~3) * 12 + (size_t)n64 * 8 + (size_t)((A + 15) & ~15);
+    const int selcap = ((A < a->cand_cap ? A : a->cand_cap) + 3) & ~3;
+    size_t smem = (size_t)((A + 3) & ~3) * 8 + (size_t)selcap * 4 + 8 + (size_t)n64 * 8 + (size_t)((A + 15) & ~15);
     if (smem > 200 * 1024) return TSCD_ERR_CAPACITY;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     cudaError_t e;
