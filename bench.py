@@ -170,7 +170,18 @@ def algorithmic_work(name, counts, B, need_reg_calls):
         return "hbm", B * F * (6804 * 2 + PRE_K * (5 + C) * 2 + PRE_K * 28)
     if name == "tscd_gather":
         return "hbm", B * F * (2 * TOP_K * 3 * D * 2 + TOP_K * (7 + C) * 4)
+    if name == "tscd_linear":         # sum over the step's GEMMs of 2*M_valid*N*K, mean per launch
+        return "tensor", sum(2.0 * m * N * K for (m, N, K) in LINEAR_SHAPES) / max(1, len(LINEAR_SHAPES))
+    if name == "tscd_cafm_chain":     # SURVEY 8(d) K5, the part inside the recurrence: q projection + cosine attention
+        fl = 0.0
+        for b in range(B):
+            for n in counts[b * F:b * F + LF]:
+                fl += 2.0 * n * D * D + 4.0 * n * n * D
+        return "tensor", fl
     return "tensor", None
+
+
+LINEAR_SHAPES = []
 
 
 def main():
@@ -179,8 +190,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--clips", type=int, default=16, help="clips per GPU per step")
-    ap.add_argument("--e2e-clips", type=int, default=2)
+    ap.add_argument("--clips", type=int, default=64, help="clips per GPU per step (BASELINE.json configs[4]: 64 clips x 32 frames)")
+    ap.add_argument("--e2e-clips", type=int, default=32)
+    ap.add_argument("--e2e-chunk", type=int, default=8, help="clips per pipelined chunk of the host-buffer path")
     ap.add_argument("--cpu-clips", type=int, default=40, help="clips timed for cpu_baseline (rank 0, N=1)")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
@@ -221,6 +233,8 @@ def main():
         out = step()
     torch.cuda.synchronize()
     per_kernel = {k: sum(s.elapsed_time(e) for s, e in v) for k, v in L.profile["events"].items()}
+    for (M, N, K, md) in L.profile.get("linear", []):
+        LINEAR_SHAPES.append((M if md is None else min(M, int(md.item())), N, K))
     calls = {k: len(v) for k, v in L.profile["events"].items()}
     top = max(per_kernel, key=per_kernel.get)
     counts = out["sel"]["sel_count"].cpu().tolist()
@@ -282,28 +296,35 @@ def main():
         ms = float(t.item())
     value = world * B * F * args.steps / (ms / 1e3)
 
-    # ---- e2e: host (pinned) inputs -> detections on the host ----
+    # ---- e2e: host (pinned) inputs -> detections on the host, through AggregationStage.forward_host ----
+    # Every step: H2D of the head logits (copy stream, chunk-pipelined with compute), zero-copy gather of the kept
+    # proposals' feature rows out of the pinned feature planes, one D2H of the padded detections per chunk.
     Be = args.e2e_clips
-    cfg_e = stage.StageConfig(num_classes=C, selection=cfg.selection)
-    host = synth_s1(Be, torch.device("cpu"), seed=99 + rank, pin=True)
+    inp_mib = nbytes(inp) / 2**20
+    launch_mode = "cuda_graph" if graph is not None else "eager"
+    del graph, out, inp, head, feats
+    torch.cuda.empty_cache()
+    dev_src = synth_s1(Be, dev, seed=99 + rank)
+    host = {k: [torch.empty(t.shape, dtype=t.dtype, pin_memory=True,
+                                memory_format=torch.channels_last if k.startswith("f_") else torch.contiguous_format).copy_(t) for t in v]
+        for k, v in dev_src.items()}
+    for k, v in host.items():
+        for t, d in zip(v, dev_src[k]):
+            assert t.stride() == d.stride() and t.is_pinned()
+    del dev_src
+    torch.cuda.empty_cache()
     te_e = torch.cat([weights.timing_signal_1d(torch.arange(LF), 256)] * Be, 0).pin_memory()
-    h2d = nbytes(host) + te_e.numel() * 4
 
     def e2e_step():
-        d = {k: [t.to(dev, non_blocking=True) for t in v] for k, v in host.items()}
-        hd, ft = views_of(d, ops)
-        o = st.forward(hd, ft, torch.float16, te_e.to(dev, non_blocking=True), Be, F, LF)
-        res, res_ori = st.to_lists(o, Be, LF)                       # D2H + sync
-        host_res = [None if r is None else r.cpu() for r in res + res_ori]
-        return sum(0 if r is None else r.numel() * 4 for r in host_res) + 3 * Be * LF * 4 + 4
+        return st.forward_host(host, HW, te_e, Be, F, LF, chunk_clips=args.e2e_chunk)
 
     for _ in range(2):
-        d2h = e2e_step()
+        res, res_ori, h2d, d2h = e2e_step()
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(e2e_steps):
-        d2h = e2e_step()
+        res, res_ori, h2d, d2h = e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -311,6 +332,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_val = world * Be * F * e2e_steps / e2e_s
+    host_resident = nbytes(host)
 
     if rank != 0:
         return
@@ -330,12 +352,15 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "clips_per_gpu_per_step": B, "seam": "S1 raw per-level conv outputs (NCHW fp16 logits, channels_last fp16 features)",
-                       "l2": f"inputs per step ({nbytes(inp) / 2**20:.0f} MiB/GPU) exceed the 126 MB L2; no flush needed",
+                       "l2": f"inputs per step ({inp_mib:.0f} MiB/GPU) exceed the 126 MB L2; no flush needed",
                        "parallelism": f"clip-parallel x{world}, no collective"},
-            "clocks": clk, "gpu_launches": launches, "launch_mode": "cuda_graph" if graph is not None else "eager",
+            "clocks": clk, "gpu_launches": launches, "launch_mode": launch_mode,
             "host_ms_per_eager_step": host_ms,
             "e2e": {"value": e2e_val, "unit": "clip-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "clips_per_gpu_per_step": Be, "steps": e2e_steps},
+                    "clips_per_gpu_per_step": Be, "chunk_clips": args.e2e_chunk, "steps": e2e_steps,
+                    "host_resident_input_bytes_per_step": host_resident,
+                    "note": "inputs are pinned HOST tensors; head logits are copied H2D, the 256-ch feature planes are read in place "
+                            "(zero-copy gather of the kept rows); h2d counts both"},
             "roofline": roof}
     if world == 1:
         fps, dt, thr = cpu_stage_sample(args.cpu_clips)

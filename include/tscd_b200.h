@@ -322,8 +322,15 @@ typedef struct {
     const float* feat;           /* [loc_cap, D] */
     const float* edge;
     const float* kin;            /* [loc_cap, D] */
-    const float* kproj;          /* [loc_cap, D] k_reg(kin)  */
-    const float* vproj;          /* [loc_cap, D] v_reg(feat) */
+    const float* kproj;          /* [loc_cap, D] k_reg(kin)  (generic path) */
+    const float* vproj;          /* [loc_cap, D] v_reg(feat) (generic path) */
+    /* fast path (kmax <= 32): set all five and the chain runs entirely out of shared memory on mma.sync tensor-core
+     * tiles; feat / edge / kin / kproj / vproj / wq_t / sc_* are then unused and may be NULL */
+    const void* kproj16;         /* [loc_cap, D] k_reg(kin), 16-bit (out_dtype) */
+    const void* vproj16;         /* [loc_cap, D] v_reg(feat), 16-bit */
+    const void* wq16;            /* [D(out), D(in)] q_reg.weight, 16-bit */
+    const void* bank_reg;        /* [row_cap, D] packed clip bank (16-bit, out_dtype): identity / unmatched-row features */
+    const void* bank_edge;       /* [row_cap, D] */
     const float* time_emb;       /* [B*L, D] */
     const float* emb_reg;        /* [loc_cap, 4D] */
     const float* emb_cls;

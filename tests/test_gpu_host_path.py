@@ -1,0 +1,80 @@
+"""The host-buffer entry (AggregationStage.forward_host: pinned host boundary tensors, H2D of the head logits on a copy
+stream, zero-copy gather of the kept proposals' feature rows, chunk-pipelined, one D2H per chunk) must return exactly
+what forward() returns for the same tensors resident on the device -- same kernels, same inputs, bit-identical."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+F, LF, C, D = 8, 3, 7, 256
+HW = [(24, 24), (12, 12), (6, 6)]
+
+
+def _synth(B, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    n = B * F
+    out = dict(reg=[], obj=[], cls=[], f_cls=[], f_reg=[], f_edge=[])
+    for (h, w) in HW:
+        xy = torch.rand(n, 2, h, w, generator=g, device="cuda") * 2 - 0.5
+        wh = torch.randn(n, 2, h, w, generator=g, device="cuda") * 0.7 + 1.0
+        out["reg"].append(torch.cat([xy, wh], 1).half())
+        out["obj"].append((torch.randn(n, 1, h, w, generator=g, device="cuda") * 2 - 3).half())
+        out["cls"].append((torch.randn(n, C, h, w, generator=g, device="cuda") * 2 - 3).half())
+        for k in ("f_cls", "f_reg", "f_edge"):
+            out[k].append(torch.randn(n, D, h, w, generator=g, device="cuda").half().contiguous(memory_format=torch.channels_last))
+    return out
+
+
+@pytest.mark.parametrize("B,chunk", [(5, 2), (4, 4)])
+def test_forward_host_equals_forward(B, chunk):
+    from tscd_b200 import ops, selection, stage, weights
+    cfg = stage.StageConfig(num_classes=C, selection=selection.SelectionConfig(mode="A", pre_k=200, top_k=12, nms_thresh=0.75))
+    st = stage.AggregationStage(cfg, weights.random_state_dict(C, D, seed=5))
+    dev = _synth(B, 31)
+    host = {k: [torch.empty(t.shape, dtype=t.dtype, pin_memory=True,
+                                memory_format=torch.channels_last if k.startswith("f_") else torch.contiguous_format).copy_(t) for t in v]
+        for k, v in dev.items()}
+    te = torch.cat([weights.timing_signal_1d(torch.arange(LF), 256)] * B, 0)
+
+    an = ops.AnchorSpec(HW)
+    head = ops.HeadViews.from_levels(dev["reg"], dev["obj"], dev["cls"], an)
+    feats = tuple(ops.view_levels(dev[k]) for k in ("f_cls", "f_reg", "f_edge"))
+    want = []
+    # reference run chunk by chunk (the CAFM state is per forward() call, clips are independent)
+    for c0 in range(0, B, chunk):
+        nc = min(chunk, B - c0)
+        f0, f1 = c0 * F, (c0 + nc) * F
+        h = ops.HeadViews.from_levels([t[f0:f1] for t in dev["reg"]], [t[f0:f1] for t in dev["obj"]], [t[f0:f1] for t in dev["cls"]], an)
+        fv = tuple(ops.view_levels([t[f0:f1] for t in dev[k]]) for k in ("f_cls", "f_reg", "f_edge"))
+        out = st.forward(h, fv, torch.float16, te[c0 * LF:(c0 + nc) * LF], nc, F, LF)
+        r, o = st.to_lists(out, nc, LF)
+        want += list(zip(r, o))
+    del head, feats
+
+    for _ in range(2):       # twice: staging buffers are reused across calls
+        res, res_ori, h2d, d2h = st.forward_host(host, HW, te.pin_memory(), B, F, LF, chunk_clips=chunk)
+        assert len(res) == B * LF and len(res_ori) == B * LF
+        n_det = 0
+        for (wr, wo), gr, go in zip(want, res, res_ori):
+            assert (wr is None) == (gr is None)
+            if wr is None:
+                continue
+            assert gr.device.type == "cpu" and go.device.type == "cpu"
+            assert torch.equal(gr, wr.cpu()) and torch.equal(go, wo.cpu())
+            n_det += len(gr)
+        assert n_det > 0
+        head_bytes = sum(t.numel() * t.element_size() for k in ("reg", "obj", "cls") for t in host[k])
+        feat_bytes = sum(t.numel() * t.element_size() for k in ("f_cls", "f_reg", "f_edge") for t in host[k])
+        assert head_bytes < h2d < head_bytes + feat_bytes // 4      # only the kept rows of the feature planes crossed PCIe
+        assert d2h > 0
+
+
+def test_forward_host_rejects_pageable_memory():
+    from tscd_b200 import selection, stage, weights
+    cfg = stage.StageConfig(num_classes=C, selection=selection.SelectionConfig(mode="A", pre_k=200, top_k=12))
+    st = stage.AggregationStage(cfg, weights.random_state_dict(C, D, seed=5))
+    dev = _synth(1, 3)
+    host = {k: [t.cpu() for t in v] for k, v in dev.items()}
+    te = weights.timing_signal_1d(torch.arange(LF), 256)
+    with pytest.raises(RuntimeError):
+        st.forward_host(host, HW, te, 1, F, LF)

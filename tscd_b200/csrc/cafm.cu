@@ -471,6 +471,457 @@ __global__ void __launch_bounds__(kChainThreads, 1) cafm_chain_kernel(const tscd
     CHAIN_TICK(6);
 }
 
+
+// ================================================================================================================
+// Fast chain for frames of at most 32 proposals (kmax <= 32: the mode-A / BASELINE configuration, K = 30).
+//
+// One CTA (16 warps) per clip.  The whole per-frame working set lives in shared memory and the two small matrix
+// products of every step run on the tensor cores with warp-level mma.sync (m16n8k16, 16-bit operands, fp32
+// accumulation) -- a 30-row problem is latency-bound, far below the 128-row tcgen05 tile:
+//   * W_q (256x256) is held in REGISTERS for the whole chain: warp w owns output channels [16w, 16w+16), i.e. the
+//     B fragments of 2 n-tiles x 16 k-steps = 64 registers per thread, loaded once per clip;
+//   * k_reg / v_reg projections, raw features, edge features, time embedding and the frame's LSAP solution of frame
+//     i+1 are prefetched with cp.async into the second half of a double buffer while frame i is computed;
+//   * q is kept un-normalised (16-bit) with its per-(row, head) squared norms; the cosine of the attention is
+//     S * (1/|q_r|) * (1/|k_j|), applied to the fp32 accumulators;  softmax in registers;  P feeds the P.V product
+//     straight from the accumulator layout (no shared-memory round trip);
+//   * LayerNorm(identity + attn) is written in place as the next frame's `last_outputs`.
+// ================================================================================================================
+constexpr int kFR = 32;        // rows per frame (capacity of the fast path)
+constexpr int kFS = 264;       // padded row pitch (16-bit elements) of the ldmatrix operands: 528 B -> conflict-free
+constexpr int kFastThreads = 512;
+
+template <typename T>
+struct FastBuf {
+    T k[kFR * kFS];
+    T v[kFR * kFS];
+    T feat[kFR * 256];
+    T edge[kFR * 256];
+    float time[256];
+    int col[kFR], row[kFR];
+};
+
+template <typename T>
+struct FastSmem {
+    FastBuf<T> buf[2];
+    T qin[kFR * kFS];
+    T q[kFR * kFS];
+    float x[kFR * 256];          // pre-norm output of the current frame, then (in place) last_outputs
+    float qss[kFR][16];          // squared norm partials of q: [row][warp]; head h = warps 2h, 2h+1
+    float ln[4][256];            // ln_w, ln_b, dec_w, dec_b
+    float4 se[32];               // (w1[j][0], w1[j][1], w2[0][j], w2[1][j])
+    int perm[kFR], prow[kFR], ord_prev[kFR], frames[64];
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+template <typename T> __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
+template <> __device__ __forceinline__ void mma16816<__half>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <> __device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// SE gate of 8 (a, b) pairs at once: the 32 hidden units' weights are read once per 8 elements (one LDS.128 each).
+__device__ __forceinline__ void se_gate8(const float (&a)[8], const float (&b)[8], const float4* se, float (&out)[8]) {
+    float o0[8], o1[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { o0[e] = 0.f; o1[e] = 0.f; }
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+        const float4 w = se[j];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float h = fmaxf(0.f, fmaf(w.y, b[e], w.x * a[e]));
+            o0[e] = fmaf(w.z, h, o0[e]);
+            o1[e] = fmaf(w.w, h, o1[e]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float s0 = 1.f / (1.f + expf(-o0[e])), s1 = 1.f / (1.f + expf(-o1[e]));
+        out[e] = a[e] * s0 + b[e] * s1;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]) {      // 8 consecutive 16-bit values, 16-byte aligned
+    const uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = ldf_reg(e[i]);
+}
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+template <typename T>
+__device__ __forceinline__ void fast_prefetch(const tscd_cafm_chain_args& a, FastBuf<T>& dst, int b, int f, int tid) {
+    const int lf = b * a.L + f;
+    const int l0 = a.lrow_off[lf], n = a.lrow_off[lf + 1] - l0;
+    const int r0 = a.row_off[b * a.F + f];
+    const T* kp = reinterpret_cast<const T*>(a.kproj16) + (int64_t)l0 * 256;
+    const T* vp = reinterpret_cast<const T*>(a.vproj16) + (int64_t)l0 * 256;
+    const T* fp = reinterpret_cast<const T*>(a.bank_reg) + (int64_t)r0 * 256;
+    const T* ep = reinterpret_cast<const T*>(a.bank_edge) + (int64_t)r0 * 256;
+    for (int i = tid; i < n * 32; i += kFastThreads) {
+        const int r = i >> 5, c = (i & 31) * 8;
+        cp_async16(&dst.k[r * kFS + c], kp + r * 256 + c);
+        cp_async16(&dst.v[r * kFS + c], vp + r * 256 + c);
+        cp_async16(&dst.feat[r * 256 + c], fp + r * 256 + c);
+        cp_async16(&dst.edge[r * 256 + c], ep + r * 256 + c);
+    }
+    for (int i = n * 32 + tid; i < kFR * 32; i += kFastThreads) {          // padding rows: keys are masked, values must be finite
+        const int r = i >> 5, c = (i & 31) * 8;
+        *reinterpret_cast<uint4*>(&dst.k[r * kFS + c]) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(&dst.v[r * kFS + c]) = make_uint4(0, 0, 0, 0);
+    }
+    if (tid < 64) cp_async16(&dst.time[tid * 4], a.time_emb + (int64_t)lf * 256 + tid * 4);
+    if (tid >= 64 && tid < 64 + kFR) {
+        const int i = tid - 64;
+        if (i < a.kmax) {
+            cp_async4(&dst.col[i], a.lap_col + (int64_t)lf * a.kmax + i);
+            cp_async4(&dst.row[i], a.lap_row + (int64_t)lf * a.kmax + i);
+        }
+    }
+    cp_async_commit();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kFastThreads, 1) cafm_chain_fast_kernel(const tscd_cafm_chain_args a) {
+    extern __shared__ __align__(16) unsigned char chain_smem[];
+    FastSmem<T>& s = *reinterpret_cast<FastSmem<T>*>(chain_smem);
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int KM = a.kmax, E = 4 * 256;
+
+    // ---- one-time setup: weights, list of non-empty frames, carried state --------------------------------
+    if (tid < 32) s.se[tid] = make_float4(a.se_w1[2 * tid], a.se_w1[2 * tid + 1], a.se_w2[tid], a.se_w2[32 + tid]);
+    for (int c = tid; c < 256; c += kFastThreads) {
+        s.ln[0][c] = a.ln_w[c]; s.ln[1][c] = a.ln_b[c]; s.ln[2][c] = a.dec_w[c]; s.ln[3][c] = a.dec_b[c];
+    }
+    const bool resume = a.resume ? (a.resume[b] != 0) : false;
+    int n_prev = resume ? a.st_n[b] : 0;
+    bool bad = n_prev > kFR;
+    int m = 0;                                   // number of non-empty frames (uniform: every thread scans the offsets)
+    for (int f = 0; f < a.L; ++f) {
+        const int n = a.lrow_off[b * a.L + f + 1] - a.lrow_off[b * a.L + f];
+        if (n > kFR || n > KM) bad = true;
+        if (n > 0) { if (tid == 0 && m < 64) s.frames[m] = f; ++m; }
+    }
+    if (bad || a.L > 64) {
+        if (tid == 0) atomicMin(a.status, TSCD_ERR_CAPACITY);
+        return;
+    }
+    // W_q fragments: warp w owns output channels [16w, 16w+16); B[k][n] = W[n][k] -> thread (g, t4) holds
+    // W[n0 + g][k0 + 2*t4 .. +1] and W[n0 + g][k0 + 8 + 2*t4 .. +1]
+    uint32_t wq[2][16][2];
+    {
+        const T* W = reinterpret_cast<const T*>(a.wq16);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int ks = 0; ks < 16; ++ks) {
+                const T* p = W + (int64_t)(warp * 16 + nt * 8 + g) * 256 + ks * 16 + 2 * t4;
+                wq[nt][ks][0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+                wq[nt][ks][1] = __ldg(reinterpret_cast<const uint32_t*>(p + 8));
+            }
+    }
+    if (tid < kFR) s.ord_prev[tid] = tid;        // carried state is already in matched order
+    __syncthreads();                             // s.frames visible
+    if (m > 0) fast_prefetch<T>(a, s.buf[0], b, s.frames[0], tid);
+    if (n_prev > 0) {                            // resume: last_outputs -> x, last edge / time -> the "previous" buffer
+        const float* so = a.st_out + (int64_t)b * KM * 256;
+        const float* se = a.st_edge + (int64_t)b * KM * 256;
+        for (int i = tid; i < n_prev * 256; i += kFastThreads) {
+            s.x[i] = so[i];
+            s.buf[1].edge[i] = cvt_from_float<T>(se[i]);          // exact: edge features are 16-bit bank values
+        }
+        for (int c = tid; c < 256; c += kFastThreads) s.buf[1].time[c] = a.st_time[(int64_t)b * 256 + c];
+    }
+    int slot = 0, last_l0 = -1;
+
+    for (int fi = 0; fi < m; ++fi) {
+        const int f = s.frames[fi];
+        const int lf = b * a.L + f;
+        const int l0 = a.lrow_off[lf], n = a.lrow_off[lf + 1] - l0;
+        FastBuf<T>& cur = s.buf[slot];
+        FastBuf<T>& prv = s.buf[slot ^ 1];
+        const bool first = (f == 0 && !resume) || n_prev == 0;
+        const int np = first ? n : n_prev;
+        cp_async_wait_all();
+        __syncthreads();                                          // cur is loaded; previous frame's writes are visible
+
+        // ---- assignment: re-index the frame's LSAP solution by how the reference frame remembers its rows ----
+        if (warp == 0) {
+            if (np <= n) {
+                if (lane < np) {
+                    s.perm[lane] = cur.col[first ? lane : s.ord_prev[lane]];
+                    s.prow[lane] = first ? (-1 - lane) : lane;
+                }
+                const bool un = lane < n && cur.row[lane] == -1;
+                const unsigned bal = __ballot_sync(0xffffffffu, un);
+                const int pos = np + __popc(bal & ((1u << lane) - 1u));
+                if (un && pos < n) { s.perm[pos] = lane; s.prow[pos] = -1 - lane; }
+            } else {
+                const int c = lane < np ? cur.col[s.ord_prev[lane]] : -1;
+                const bool mt = c >= 0;
+                const unsigned bal = __ballot_sync(0xffffffffu, mt);
+                const int pos = __popc(bal & ((1u << lane) - 1u));
+                if (mt && pos < n) { s.perm[pos] = c; s.prow[pos] = lane; }
+            }
+        }
+        __syncthreads();
+
+        // ---- query input  SE(tgt, query_edge) + query_pos  (tscd_matching.py:566-575), 16-bit A operand ------------
+        {
+            const float* tm = first ? cur.time : prv.time;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                const int r = (tid >> 5) + pass * 16, c0 = (tid & 31) * 8;
+                uint4 packed = make_uint4(0, 0, 0, 0);
+                if (r < n) {
+                    const int p = s.prow[r];
+                    float ta[8], ed[8], o[8];
+                    if (p >= 0) { load8(&s.x[p * 256 + c0], ta); load8(&prv.edge[s.ord_prev[p] * 256 + c0], ed); }
+                    else        { load8(&cur.feat[(-1 - p) * 256 + c0], ta); load8(&cur.edge[(-1 - p) * 256 + c0], ed); }
+                    se_gate8(ta, ed, s.se, o);
+                    float tv[8];
+                    load8(&tm[c0], tv);
+                    packed.x = pack2<T>(o[0] + tv[0], o[1] + tv[1]); packed.y = pack2<T>(o[2] + tv[2], o[3] + tv[3]);
+                    packed.z = pack2<T>(o[4] + tv[4], o[5] + tv[5]); packed.w = pack2<T>(o[6] + tv[6], o[7] + tv[7]);
+                }
+                *reinterpret_cast<uint4*>(&s.qin[r * kFS + c0]) = packed;
+            }
+        }
+        __syncthreads();
+        // the previous frame's buffer is free now: prefetch the next non-empty frame into it
+        if (fi + 1 < m) fast_prefetch<T>(a, prv, b, s.frames[fi + 1], tid);
+
+        // ---- q = W_q qin on the tensor cores; un-normalised q (16-bit) + per-(row, warp) squared norms ------------
+        {
+            const int mts = n > 16 ? 2 : 1;
+#pragma unroll 1
+            for (int mt = 0; mt < mts; ++mt) {
+                float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                const T* arow = &s.qin[(mt * 16 + (lane & 15)) * kFS + (lane >> 4) * 8];
+#pragma unroll
+                for (int ks = 0; ks < 16; ++ks) {
+                    uint32_t af[4];
+                    ldsm_x4(af, arow + ks * 16);
+                    mma16816<T>(acc[0], af, wq[0][ks][0], wq[0][ks][1]);
+                    mma16816<T>(acc[1], af, wq[1][ks][0], wq[1][ks][1]);
+                }
+                float ss0 = 0.f, ss1 = 0.f;
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    const int col = warp * 16 + nt * 8 + 2 * t4;
+                    *reinterpret_cast<uint32_t*>(&s.q[(mt * 16 + g) * kFS + col]) = pack2<T>(acc[nt][0], acc[nt][1]);
+                    *reinterpret_cast<uint32_t*>(&s.q[(mt * 16 + g + 8) * kFS + col]) = pack2<T>(acc[nt][2], acc[nt][3]);
+                    ss0 = fmaf(acc[nt][0], acc[nt][0], fmaf(acc[nt][1], acc[nt][1], ss0));
+                    ss1 = fmaf(acc[nt][2], acc[nt][2], fmaf(acc[nt][3], acc[nt][3], ss1));
+                }
+                ss0 += __shfl_xor_sync(0xffffffffu, ss0, 1); ss0 += __shfl_xor_sync(0xffffffffu, ss0, 2);
+                ss1 += __shfl_xor_sync(0xffffffffu, ss1, 1); ss1 += __shfl_xor_sync(0xffffffffu, ss1, 2);
+                if (t4 == 0) { s.qss[mt * 16 + g][warp] = ss0; s.qss[mt * 16 + g + 8][warp] = ss1; }
+            }
+        }
+        __syncthreads();
+
+        // ---- 8-head cosine attention over the CURRENT frame only: warp = (head, 16-row tile) -------------------
+        {
+            const int h = warp >> 1, mt = warp & 1;
+            if (mt * 16 < n) {
+                // 1 / |k_j| of this head, lane = key
+                float invk;
+                {
+                    float ssk = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float kv[8];
+                        load8(&cur.k[lane * kFS + h * 32 + c * 8], kv);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) ssk = fmaf(kv[i], kv[i], ssk);
+                    }
+                    invk = 1.f / sqrtf(ssk);
+                }
+                uint32_t qa[2][4];
+                const T* qrow = &s.q[(mt * 16 + (lane & 15)) * kFS + h * 32 + (lane >> 4) * 8];
+                ldsm_x4(qa[0], qrow);
+                ldsm_x4(qa[1], qrow + 16);
+                float sc[4][4];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    uint32_t kb[4];
+                    ldsm_x4(kb, &cur.k[(nt * 8 + (lane & 7)) * kFS + h * 32 + (lane >> 3) * 8]);
+                    sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+                    mma16816<T>(sc[nt], qa[0], kb[0], kb[1]);
+                    mma16816<T>(sc[nt], qa[1], kb[2], kb[3]);
+                }
+                const int R0 = mt * 16 + g, R1 = R0 + 8;
+                const float iq0 = 1.f / sqrtf(s.qss[R0][2 * h] + s.qss[R0][2 * h + 1]);
+                const float iq1 = 1.f / sqrtf(s.qss[R1][2 * h] + s.qss[R1][2 * h + 1]);
+                float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int j0 = nt * 8 + 2 * t4;
+                    const float ik0 = __shfl_sync(0xffffffffu, invk, j0), ik1 = __shfl_sync(0xffffffffu, invk, j0 + 1);
+                    sc[nt][0] = j0 < n ? sc[nt][0] * iq0 * ik0 : -INFINITY;
+                    sc[nt][1] = j0 + 1 < n ? sc[nt][1] * iq0 * ik1 : -INFINITY;
+                    sc[nt][2] = j0 < n ? sc[nt][2] * iq1 * ik0 : -INFINITY;
+                    sc[nt][3] = j0 + 1 < n ? sc[nt][3] * iq1 * ik1 : -INFINITY;
+                    mx0 = fmaxf(mx0, fmaxf(sc[nt][0], sc[nt][1]));
+                    mx1 = fmaxf(mx1, fmaxf(sc[nt][2], sc[nt][3]));
+                }
+                mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+                mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+                float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    sc[nt][0] = expf(sc[nt][0] - mx0); sc[nt][1] = expf(sc[nt][1] - mx0);
+                    sc[nt][2] = expf(sc[nt][2] - mx1); sc[nt][3] = expf(sc[nt][3] - mx1);
+                    sum0 += sc[nt][0] + sc[nt][1];
+                    sum1 += sc[nt][2] + sc[nt][3];
+                }
+                sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+                sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+                const float is0 = 1.f / sum0, is1 = 1.f / sum1;
+                float o[4][4];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    uint32_t pa[4];
+                    pa[0] = pack2<T>(sc[2 * ks][0] * is0, sc[2 * ks][1] * is0);
+                    pa[1] = pack2<T>(sc[2 * ks][2] * is1, sc[2 * ks][3] * is1);
+                    pa[2] = pack2<T>(sc[2 * ks + 1][0] * is0, sc[2 * ks + 1][1] * is0);
+                    pa[3] = pack2<T>(sc[2 * ks + 1][2] * is1, sc[2 * ks + 1][3] * is1);
+#pragma unroll
+                    for (int ntp = 0; ntp < 2; ++ntp) {
+                        uint32_t vb[4];
+                        ldsm_x4_trans(vb, &cur.v[(ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kFS + h * 32 + ntp * 16 + (lane >> 4) * 8]);
+                        mma16816<T>(o[2 * ntp], pa, vb[0], vb[1]);
+                        mma16816<T>(o[2 * ntp + 1], pa, vb[2], vb[3]);
+                    }
+                }
+                // identity + attention -> pre-norm output (tscd_matching.py:585-586)
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int R = half ? R1 : R0;
+                    if (R < n) {
+                        const int idr = first ? R : s.perm[R];
+#pragma unroll
+                        for (int nt = 0; nt < 4; ++nt) {
+                            const int col = h * 32 + nt * 8 + 2 * t4;
+                            const float i0 = ldf_reg(cur.feat[idr * 256 + col]), i1 = ldf_reg(cur.feat[idr * 256 + col + 1]);
+                            *reinterpret_cast<float2*>(&s.x[R * 256 + col]) = make_float2(i0 + o[nt][2 * half], i1 + o[nt][2 * half + 1]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- LayerNorm (new last_outputs, in place) + decoder_norm -> output in the original row order ------------
+        for (int r = warp; r < n; r += 16) {
+            float v[8], y[8], z[8];
+            load8(&s.x[r * 256 + lane * 8], v);
+            float sm = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sm += v[i];
+            float mean = warp_sumf(sm) / 256.f, var = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; var = fmaf(d, d, var); }
+            float rstd = rsqrtf(warp_sumf(var) / 256.f + 1e-5f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[i] = (v[i] - mean) * rstd * s.ln[0][lane * 8 + i] + s.ln[1][lane * 8 + i];
+            *reinterpret_cast<float4*>(&s.x[r * 256 + lane * 8]) = make_float4(y[0], y[1], y[2], y[3]);
+            *reinterpret_cast<float4*>(&s.x[r * 256 + lane * 8 + 4]) = make_float4(y[4], y[5], y[6], y[7]);
+            sm = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sm += y[i];
+            mean = warp_sumf(sm) / 256.f; var = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float d = y[i] - mean; var = fmaf(d, d, var); }
+            rstd = rsqrtf(warp_sumf(var) / 256.f + 1e-5f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z[i] = (y[i] - mean) * rstd * s.ln[2][lane * 8 + i] + s.ln[3][lane * 8 + i];
+            const int64_t dst = (int64_t)(l0 + s.perm[r]) * 256 + lane * 8;
+            uint4 pk;
+            pk.x = pack2<T>(z[0], z[1]); pk.y = pack2<T>(z[2], z[3]); pk.z = pack2<T>(z[4], z[5]); pk.w = pack2<T>(z[6], z[7]);
+            *reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.out16) + dst) = pk;
+            if (a.out32) {
+                *reinterpret_cast<float4*>(a.out32 + dst) = make_float4(z[0], z[1], z[2], z[3]);
+                *reinterpret_cast<float4*>(a.out32 + dst + 4) = make_float4(z[4], z[5], z[6], z[7]);
+            }
+            if (a.perm && lane == 0) a.perm[l0 + r] = s.perm[r];
+        }
+        __syncthreads();
+        if (tid < n) s.ord_prev[tid] = first ? tid : s.perm[tid];   // order in which this frame is remembered
+        n_prev = n;
+        last_l0 = l0;
+        slot ^= 1;
+    }
+    __syncthreads();
+
+    // ---- write the memory back (tscd_matching.py:876-878) for the next call ------------------------------------
+    if (last_l0 >= 0) {
+        const FastBuf<T>& lastb = s.buf[slot ^ 1];
+        float* so = a.st_out + (int64_t)b * KM * 256;
+        float* se = a.st_edge + (int64_t)b * KM * 256;
+        for (int i = tid; i < n_prev * 256; i += kFastThreads) {
+            const int r = i >> 8, c = i & 255;
+            so[i] = s.x[i];
+            se[i] = ldf_reg(lastb.edge[s.ord_prev[r] * 256 + c]);
+        }
+        for (int c = tid; c < 256; c += kFastThreads) a.st_time[(int64_t)b * 256 + c] = lastb.time[c];
+        float* st_reg = a.st_reg + (int64_t)b * KM * E;
+        float* st_cls = a.st_cls + (int64_t)b * KM * E;
+        const float* Rc = a.emb_reg + (int64_t)last_l0 * E;
+        const float* Cc = a.emb_cls + (int64_t)last_l0 * E;
+        for (int i = tid; i < n_prev * (E / 4); i += kFastThreads) {
+            const int r = i / (E / 4), c4 = i - r * (E / 4);
+            const int src = s.ord_prev[r];
+            reinterpret_cast<float4*>(st_reg)[(int64_t)r * (E / 4) + c4] = reinterpret_cast<const float4*>(Rc)[(int64_t)src * (E / 4) + c4];
+            reinterpret_cast<float4*>(st_cls)[(int64_t)r * (E / 4) + c4] = reinterpret_cast<const float4*>(Cc)[(int64_t)src * (E / 4) + c4];
+        }
+        for (int r = tid; r < n_prev; r += kFastThreads) {
+            a.st_nreg[(int64_t)b * KM + r] = a.norm_reg[last_l0 + s.ord_prev[r]];
+            a.st_ncls[(int64_t)b * KM + r] = a.norm_cls[last_l0 + s.ord_prev[r]];
+        }
+    }
+    if (tid == 0) a.st_n[b] = n_prev;
+}
+
 }  // namespace tscd
 
 extern "C" int tscd_cafm_prep(const tscd_cafm_prep_args* a, void* stream) {
@@ -517,6 +968,22 @@ extern "C" int tscd_cafm_chain(const tscd_cafm_chain_args* a, void* stream) {
     using namespace tscd;
     if (!a || a->B <= 0 || a->L <= 0 || a->D != 256 || a->kmax <= 0 || a->kmax > kChainMax) return TSCD_ERR_INVALID_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (a->kproj16 && a->vproj16 && a->wq16) {            // fast path: every frame holds <= 32 proposals (kmax <= 32)
+        if (a->kmax > kFR || a->L > 64 || !a->bank_reg || !a->bank_edge) return TSCD_ERR_INVALID_ARG;
+        if (a->out_dtype == TSCD_F16) {
+            const size_t sm = sizeof(FastSmem<__half>);
+            if (cudaFuncSetAttribute(cafm_chain_fast_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return TSCD_ERR_CUDA;
+            cafm_chain_fast_kernel<__half><<<a->B, kFastThreads, sm, st>>>(*a);
+        } else if (a->out_dtype == TSCD_BF16) {
+            const size_t sm = sizeof(FastSmem<__nv_bfloat16>);
+            if (cudaFuncSetAttribute(cafm_chain_fast_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return TSCD_ERR_CUDA;
+            cafm_chain_fast_kernel<__nv_bfloat16><<<a->B, kFastThreads, sm, st>>>(*a);
+        } else {
+            return TSCD_ERR_UNSUPPORTED;
+        }
+        TSCD_CUDA_CHECK_LAUNCH();
+        return TSCD_OK;
+    }
     const size_t smem = sizeof(ChainSmem);
     if (a->out_dtype == TSCD_F16) {
         if (cudaFuncSetAttribute(cafm_chain_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;

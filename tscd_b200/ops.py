@@ -198,6 +198,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     a.out32, a.ld32 = _p(out32), (0 if out32 is None else out32.stride(0))
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous()
+    if L.profile is not None:
+        L.profile.setdefault("linear", []).append((M, N, K, m_dev))
     with L.timed("tscd_linear"):
         L.check(L.lib().tscd_linear(C.byref(a), _stream()), "tscd_linear")
     return out16, out32

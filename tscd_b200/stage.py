@@ -117,6 +117,105 @@ class AggregationStage:
                                       status=status)
 
     # ------------------------------------------------------------------------------------------------------
+    def forward_host(self, host: dict, hw, time_embedding: torch.Tensor, B: int, F: int, Lf: int, chunk_clips: int = 8,
+                     strides=(8, 16, 32)):
+        """The stage for callers whose boundary tensors live in (pinned) HOST memory -> detections on the host.
+
+        `host` = dict(reg, obj, cls, f_cls, f_reg, f_edge) of per-level lists of pinned CPU tensors (seam S1 layouts:
+        [B*F, ch, H, W], NCHW or channels_last).  Only what the kernels actually consume crosses PCIe:
+          * the head logits (reg/obj/cls planes, ~0.4 MB per frame) are copied host->device on a copy stream, one
+            chunk of clips ahead of the compute stream;
+          * the 256-channel feature planes (10.4 MB per frame) are NOT copied: K3 gathers the kept proposals' rows
+            straight out of the pinned host tensors (UVA zero-copy, 3 x 512 B per kept proposal), exactly the rows
+            find_feature_score (tscd_head.py:976-1006) indexes;
+          * detections come back as two padded tensors + counts in ONE device->host copy per chunk.
+        Returns (result, result_ori, h2d_bytes, d2h_bytes) with host tensors in the reference's list layout."""
+        dev = self.device
+        for k in ("reg", "obj", "cls", "f_cls", "f_reg", "f_edge"):
+            for t in host[k]:
+                if t.device.type != "cpu" or not t.is_pinned():
+                    raise RuntimeError(f"forward_host: host['{k}'] must be pinned CPU tensors (cudaHostAlloc) so the GPU can "
+                                       "read them in place; there is no pageable-memory / CPU path")
+        an = ops.AnchorSpec(hw, strides)
+        feat_dtype = host["f_cls"][0].dtype
+        main = torch.cuda.current_stream()
+        if getattr(self, "_copy", None) is None:
+            self._copy = torch.cuda.Stream(device=dev)
+        cp = self._copy
+        key = (B, F, tuple(tuple(x) for x in hw), host["cls"][0].shape[1], host["cls"][0].dtype)
+        if getattr(self, "_stage_key", None) != key:           # device staging for the head logits, reused across calls
+            self._stage_buf = {k: [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in host[k]] for k in ("reg", "obj", "cls")}
+            self._stage_key = key
+        dbuf = self._stage_buf
+        te = time_embedding
+        cp.wait_stream(main)                                   # previous call's kernels are done with the staging buffers
+        chunks = [(c0, min(chunk_clips, B - c0)) for c0 in range(0, B, chunk_clips)]
+        events, h2d = [], 0
+        with torch.cuda.stream(cp):
+            te_dev = te.to(dev, non_blocking=True)
+            h2d += te.numel() * te.element_size()
+            for (c0, nc) in chunks:
+                f0, f1 = c0 * F, (c0 + nc) * F
+                for k in ("reg", "obj", "cls"):
+                    for l, t in enumerate(host[k]):
+                        dbuf[k][l][f0:f1].copy_(t[f0:f1], non_blocking=True)
+                        h2d += (f1 - f0) * t[0].numel() * t.element_size()
+                ev = torch.cuda.Event()
+                ev.record(cp)
+                events.append(ev)
+        pend = []
+        for (c0, nc), ev in zip(chunks, events):
+            f0, f1 = c0 * F, (c0 + nc) * F
+            main.wait_event(ev)
+            head = ops.HeadViews.from_levels([t[f0:f1] for t in dbuf["reg"]], [t[f0:f1] for t in dbuf["obj"]],
+                                             [t[f0:f1] for t in dbuf["cls"]], an)
+            feats = tuple(ops.view_levels([t[f0:f1] for t in host[k]]) for k in ("f_cls", "f_reg", "f_edge"))
+            out = self.forward(head, feats, feat_dtype, te_dev[c0 * Lf:(c0 + nc) * Lf], nc, F, Lf)
+            pend.append((nc, self._pack_to_host(out)))
+        torch.cuda.current_stream().synchronize()
+        result, result_ori, d2h = [], [], 0
+        for nc, pk in pend:
+            r, o, nb = self._unpack_host(pk, nc * Lf)
+            result += r
+            result_ori += o
+            d2h += nb
+        h2d += sum(int(x) for _, pk in pend for x in pk["gathered_bytes"])
+        return result, result_ori, h2d, d2h
+
+    @staticmethod
+    def _pack_to_host(out):
+        """Asynchronous D2H of the padded detections + counts + status (one pinned buffer each)."""
+        pk = {}
+        for k in ("det_rows", "ori_rows", "det_count", "ori_count", "det_cand", "status"):
+            h = torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True)
+            h.copy_(out[k], non_blocking=True)
+            pk[k] = h
+        cnt = torch.empty(out["sel"]["sel_count"].shape, dtype=torch.int32, pin_memory=True)
+        cnt.copy_(out["sel"]["sel_count"], non_blocking=True)
+        pk["sel_count"] = cnt
+        pk["gathered_bytes"] = []
+        pk["_row_bytes"] = 3 * out["sel"]["bank_cls"].shape[1] * 2
+        return pk
+
+    @staticmethod
+    def _unpack_host(pk, nlf):
+        st = int(pk["status"][0])
+        if st != 0:
+            raise RuntimeError(f"tscd_b200 stage reported error {st} (capacity exceeded)")
+        pk["gathered_bytes"].append(int(pk["sel_count"].sum()) * pk["_row_bytes"])   # zero-copy reads of the feature rows
+        det_n, ori_n, det_c = pk["det_count"].tolist(), pk["ori_count"].tolist(), pk["det_cand"].tolist()
+        result, result_ori = [], []
+        for i in range(nlf):
+            if det_c[i] == 0:
+                result.append(None)
+                result_ori.append(None)
+                continue
+            result.append(pk["det_rows"][i, :det_n[i]])
+            result_ori.append(pk["ori_rows"][i, :ori_n[i]])
+        nb = sum(pk[k].numel() * pk[k].element_size() for k in ("det_rows", "ori_rows", "det_count", "ori_count", "det_cand", "status", "sel_count"))
+        return result, result_ori, nb
+
+    # ------------------------------------------------------------------------------------------------------
     def capture(self, head: ops.HeadViews, feats, feat_dtype, time_embedding: torch.Tensor, B: int, F: int, Lf: int,
                 state: Optional["CAFMState"] = None, resume: Optional[torch.Tensor] = None, warmup: int = 2):
         """Capture one forward() over FIXED input buffers into a CUDA graph (the stage has no host sync, so the whole
