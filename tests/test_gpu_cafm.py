@@ -10,11 +10,14 @@ import oracle
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("counts_calls", [
-    [[[18, 18, 24], [30, 12, 30]], [[16, 29, 17], [5, 40, 0]]],       # two clips, two consecutive calls
-    [[[0, 9, 33], [1, 1, 2]]],                                            # empty first frame, tiny frames
+@pytest.mark.parametrize("counts_calls,kmax", [
+    ([[[18, 18, 24], [30, 12, 30]], [[16, 29, 17], [5, 40, 0]]], 40),   # two clips, two consecutive calls (generic chain)
+    ([[[0, 9, 33], [1, 1, 2]]], 40),                                      # empty first frame, tiny frames
+    # kmax <= 32: the shared-memory / mma.sync chain (16-bit tensor-core operands inside the recurrence)
+    ([[[18, 18, 24], [30, 12, 30]], [[16, 29, 17], [5, 32, 0]]], 32),
+    ([[[0, 9, 31, 0, 16, 17], [1, 1, 2, 32, 32, 3]], [[0, 0, 0, 0, 0, 0], [7, 0, 30, 30, 0, 1]], [[4, 4, 4, 4, 4, 4], [0, 3, 0, 3, 0, 3]]], 32),
 ])
-def test_cafm_chain_exact_assignments(counts_calls):
+def test_cafm_chain_exact_assignments(counts_calls, kmax):
     from tscd_b200 import aggregate, ops, selection, stage
     dtype, D, C = torch.float16, 256, 5
     sd = oracle.init_stage_weights(C, dim=D, seed=23)
@@ -23,7 +26,6 @@ def test_cafm_chain_exact_assignments(counts_calls):
     st = stage.AggregationStage(cfg, sd)
     B, Lf = len(counts_calls[0]), len(counts_calls[0][0])
     F = Lf + 1
-    kmax = 40
     state = stage.CAFMState(B, kmax, D)
     o_state = [None] * B
     g = torch.Generator().manual_seed(4)
@@ -66,5 +68,5 @@ def test_cafm_chain_exact_assignments(counts_calls):
             assert perm[lpos:lpos + nl].cpu().numpy().tolist() == o_perm.tolist(), f"call {call} clip {b}"
             if want is not None:
                 err = float((c32[lpos:lpos + nl].cpu() - want).abs().max() / want.abs().max())
-                assert err < 2e-3, f"call {call} clip {b}: {err}"
+                assert err < (4e-3 if kmax <= 32 else 2e-3), f"call {call} clip {b}: {err}"
             lpos += nl

@@ -34,10 +34,59 @@ __device__ __forceinline__ float se_gate(float a, float b, const float* w1, cons
     return a * s0 + b * s1;
 }
 
+// SE gate of 8 (a, b) pairs at once: the 32 hidden units' weights are read once per 8 elements (one LDS.128 each).
+__device__ __forceinline__ void se_gate8(const float (&a)[8], const float (&b)[8], const float4* se, float (&out)[8]) {
+    float o0[8], o1[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { o0[e] = 0.f; o1[e] = 0.f; }
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+        const float4 w = se[j];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float h = fmaxf(0.f, fmaf(w.y, b[e], w.x * a[e]));
+            o0[e] = fmaf(w.z, h, o0[e]);
+            o1[e] = fmaf(w.w, h, o1[e]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float s0 = 1.f / (1.f + expf(-o0[e])), s1 = 1.f / (1.f + expf(-o1[e]));
+        out[e] = a[e] * s0 + b[e] * s1;
+    }
+}
+
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]) {      // 8 consecutive 16-bit values, 16-byte aligned
+    const uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = ldf_reg(e[i]);
+}
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// One warp per local row: lane owns 8 consecutive channels (16-byte loads / stores), the SE gate is register-blocked
+// over them; then the warp reduces the two 1024-dim matching-embedding norms of the row.  grid = (local frames, ysplit).
 template <typename T>
 __global__ void __launch_bounds__(256) cafm_prep_kernel(const tscd_cafm_prep_args a) {
-    __shared__ float w1[64], w2[64];
-    if (threadIdx.x < 64) { w1[threadIdx.x] = a.se_w1[threadIdx.x]; w2[threadIdx.x] = a.se_w2[threadIdx.x]; }
+    __shared__ float4 se[32];
+    if (threadIdx.x < 32) se[threadIdx.x] = make_float4(a.se_w1[2 * threadIdx.x], a.se_w1[2 * threadIdx.x + 1], a.se_w2[threadIdx.x], a.se_w2[32 + threadIdx.x]);
     __syncthreads();
     const int lf = blockIdx.x;  // local frame index b*L + f
     const int b = lf / a.L, f = lf - b * a.L;
@@ -45,24 +94,35 @@ __global__ void __launch_bounds__(256) cafm_prep_kernel(const tscd_cafm_prep_arg
     const int n = a.row_off[b * a.F + f + 1] - r0;
     const int l0 = a.lrow_off[lf];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int D = a.D, E = 4 * a.D;
-    for (int j = warp; j < n; j += 8) {
+    const int D = a.D, E = 4 * a.D;         // D == 256 (checked on the host)
+    for (int j = warp + 8 * blockIdx.y; j < n; j += 8 * gridDim.y) {
         const T* fr = reinterpret_cast<const T*>(a.bank_reg) + (int64_t)(r0 + j) * D;
         const T* er = reinterpret_cast<const T*>(a.bank_edge) + (int64_t)(r0 + j) * D;
-        const int64_t o = (int64_t)(l0 + j) * D;
-        for (int c = lane; c < D; c += 32) {
-            const float x = ldf(fr + c), e = ldf(er + c);
-            const float k = se_gate(x, e, w1, w2) + a.time_emb[(int64_t)lf * D + c];
-            a.feat[o + c] = x;
-            a.edge[o + c] = e;
-            a.kin[o + c] = k;
-            reinterpret_cast<T*>(a.feat16)[o + c] = cvt_from_float<T>(x);
-            reinterpret_cast<T*>(a.kin16)[o + c] = cvt_from_float<T>(k);
-        }
+        const int64_t o = (int64_t)(l0 + j) * D + lane * 8;
+        float x[8], e[8], k[8], tm[8];
+        const uint4 xraw = __ldg(reinterpret_cast<const uint4*>(fr + lane * 8));
+        load8(reinterpret_cast<const T*>(&xraw), x);
+        load8(er + lane * 8, e);
+        load8(a.time_emb + (int64_t)lf * D + lane * 8, tm);
+        se_gate8(x, e, se, k);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) k[i] += tm[i];
+        if (a.feat) store8(a.feat + o, x);
+        if (a.edge) store8(a.edge + o, e);
+        if (a.kin) store8(a.kin + o, k);
+        *reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.feat16) + o) = xraw;
+        uint4 kp;
+        kp.x = pack2<T>(k[0], k[1]); kp.y = pack2<T>(k[2], k[3]); kp.z = pack2<T>(k[4], k[5]); kp.w = pack2<T>(k[6], k[7]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.kin16) + o) = kp;
         float sr = 0.f, sc = 0.f;
-        const float* pr = a.emb_reg + (int64_t)(l0 + j) * E;
-        const float* pc = a.emb_cls + (int64_t)(l0 + j) * E;
-        for (int c = lane; c < E; c += 32) { sr = fmaf(pr[c], pr[c], sr); sc = fmaf(pc[c], pc[c], sc); }
+        const float4* pr = reinterpret_cast<const float4*>(a.emb_reg + (int64_t)(l0 + j) * E);
+        const float4* pc = reinterpret_cast<const float4*>(a.emb_cls + (int64_t)(l0 + j) * E);
+#pragma unroll 4
+        for (int c = lane; c < E / 4; c += 32) {
+            const float4 u = pr[c], w = pc[c];
+            sr = fmaf(u.x, u.x, fmaf(u.y, u.y, fmaf(u.z, u.z, fmaf(u.w, u.w, sr))));
+            sc = fmaf(w.x, w.x, fmaf(w.y, w.y, fmaf(w.z, w.z, fmaf(w.w, w.w, sc))));
+        }
         sr = warp_sumf(sr); sc = warp_sumf(sc);
         if (lane == 0) { a.norm_reg[l0 + j] = sqrtf(sr) + 1e-6f; a.norm_cls[l0 + j] = sqrtf(sc) + 1e-6f; }
     }
@@ -539,50 +599,6 @@ template <> __device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&d)[4
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
-template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-
-// SE gate of 8 (a, b) pairs at once: the 32 hidden units' weights are read once per 8 elements (one LDS.128 each).
-__device__ __forceinline__ void se_gate8(const float (&a)[8], const float (&b)[8], const float4* se, float (&out)[8]) {
-    float o0[8], o1[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { o0[e] = 0.f; o1[e] = 0.f; }
-#pragma unroll 4
-    for (int j = 0; j < 32; ++j) {
-        const float4 w = se[j];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float h = fmaxf(0.f, fmaf(w.y, b[e], w.x * a[e]));
-            o0[e] = fmaf(w.z, h, o0[e]);
-            o1[e] = fmaf(w.w, h, o1[e]);
-        }
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const float s0 = 1.f / (1.f + expf(-o0[e])), s1 = 1.f / (1.f + expf(-o1[e]));
-        out[e] = a[e] * s0 + b[e] * s1;
-    }
-}
-
-template <typename T>
-__device__ __forceinline__ void load8(const T* p, float (&v)[8]) {      // 8 consecutive 16-bit values, 16-byte aligned
-    const uint4 raw = *reinterpret_cast<const uint4*>(p);
-    const T* e = reinterpret_cast<const T*>(&raw);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = ldf_reg(e[i]);
-}
-__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
-    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-
 template <typename T>
 __device__ __forceinline__ void fast_prefetch(const tscd_cafm_chain_args& a, FastBuf<T>& dst, int b, int f, int tid) {
     const int lf = b * a.L + f;
@@ -928,8 +944,10 @@ extern "C" int tscd_cafm_prep(const tscd_cafm_prep_args* a, void* stream) {
     using namespace tscd;
     if (!a || a->B <= 0 || a->L <= 0 || a->D <= 0 || (a->D % 32) != 0) return TSCD_ERR_INVALID_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (a->bank_dtype == TSCD_F16) cafm_prep_kernel<__half><<<a->B * a->L, 256, 0, st>>>(*a);
-    else if (a->bank_dtype == TSCD_BF16) cafm_prep_kernel<__nv_bfloat16><<<a->B * a->L, 256, 0, st>>>(*a);
+    if (a->D != 256) return TSCD_ERR_UNSUPPORTED;
+    const dim3 grid(a->B * a->L, 4);
+    if (a->bank_dtype == TSCD_F16) cafm_prep_kernel<__half><<<grid, 256, 0, st>>>(*a);
+    else if (a->bank_dtype == TSCD_BF16) cafm_prep_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(*a);
     else return TSCD_ERR_UNSUPPORTED;
     TSCD_CUDA_CHECK_LAUNCH();
     return TSCD_OK;

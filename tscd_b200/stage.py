@@ -54,7 +54,8 @@ class StageWeights:
         self.ape_w, self.ape_b = w16(m + "absolute_position_embedding.weight"), f32(m + "absolute_position_embedding.bias")
         self.cafm_wk = w16(lay + "multihead_attn.k_reg.weight")
         self.cafm_wv = w16(lay + "multihead_attn.v_reg.weight")
-        self.cafm_wq_t = f32(lay + "multihead_attn.q_reg.weight").t().contiguous()     # [in, out]
+        self.cafm_wq_t = f32(lay + "multihead_attn.q_reg.weight").t().contiguous()     # [in, out] (generic chain)
+        self.cafm_wq16 = w16(lay + "multihead_attn.q_reg.weight")                       # [out, in] (fast chain, kmax <= 32)
         self.se_w1, self.se_w2 = f32(lay + "CA.fc.0.weight"), f32(lay + "CA.fc.2.weight")
         self.cafm_ln_w, self.cafm_ln_b = f32(lay + "norm.weight"), f32(lay + "norm.bias")
         self.cafm_dec_w, self.cafm_dec_b = f32(m + "decoder_norm.weight"), f32(m + "decoder_norm.bias")
@@ -350,7 +351,10 @@ class AggregationStage:
         assert state.slots == B and state.kmax == kmax
         _, te32 = ops.linear(te16, w.ape_w, w.ape_b, want16=False, want32=True)
         f32z = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731  (fully written before read)
-        feat, edge, kin = f32z(loc_cap, D), f32z(loc_cap, D), f32z(loc_cap, D)
+        fast = kmax <= 32            # every frame's working set fits the shared-memory / mma.sync chain (csrc/cafm.cu)
+        feat = edge = kin = None
+        if not fast:
+            feat, edge, kin = f32z(loc_cap, D), f32z(loc_cap, D), f32z(loc_cap, D)
         feat16 = torch.empty(loc_cap, D, dtype=dt, device=dev)
         kin16 = torch.empty(loc_cap, D, dtype=dt, device=dev)
         norm_reg, norm_cls = f32z(loc_cap), f32z(loc_cap)
@@ -358,8 +362,8 @@ class AggregationStage:
                  lrow_off=lay.lrow_off, bank_reg=bank_reg, bank_edge=bank_edge, time_emb=te32, se_w1=w.se_w1,
                  se_w2=w.se_w2, emb_reg=emb_reg32, emb_cls=emb_cls32, feat=feat, edge=edge, feat16=feat16,
                  kin16=kin16, kin=kin, norm_reg=norm_reg, norm_cls=norm_cls)
-        _, kproj = ops.linear(kin16, w.cafm_wk, m_dev=n_loc_dev, want16=False, want32=True)
-        _, vproj = ops.linear(feat16, w.cafm_wv, m_dev=n_loc_dev, want16=False, want32=True)
+        kproj16, kproj = ops.linear(kin16, w.cafm_wk, m_dev=n_loc_dev, want16=fast, want32=not fast)
+        vproj16, vproj = ops.linear(feat16, w.cafm_wv, m_dev=n_loc_dev, want16=fast, want32=not fast)
         cafm16 = torch.empty(loc_cap, D, dtype=dt, device=dev)
         cafm32 = f32z(loc_cap, D) if want_debug else None
         perm = torch.empty(loc_cap, dtype=torch.int32, device=dev) if want_debug else None
@@ -374,11 +378,13 @@ class AggregationStage:
                  lap_col=lap_col, lap_row=lap_row)
         ops.call("tscd_cafm_chain", L.CafmChainArgs, B=B, F=F, L=Lf, D=D, kmax=kmax, out_dtype=dt, row_off=lay.row_off,
                  lrow_off=lay.lrow_off, resume=resume, feat=feat, edge=edge, kin=kin, kproj=kproj, vproj=vproj,
-                 time_emb=te32, emb_reg=emb_reg32, emb_cls=emb_cls32, norm_reg=norm_reg, norm_cls=norm_cls,
+                 kproj16=kproj16, vproj16=vproj16, wq16=w.cafm_wq16 if fast else None,
+                 bank_reg=bank_reg if fast else None, bank_edge=bank_edge if fast else None, time_emb=te32, emb_reg=emb_reg32, emb_cls=emb_cls32, norm_reg=norm_reg, norm_cls=norm_cls,
                  wq_t=w.cafm_wq_t, se_w1=w.se_w1, se_w2=w.se_w2, ln_w=w.cafm_ln_w, ln_b=w.cafm_ln_b,
                  dec_w=w.cafm_dec_w, dec_b=w.cafm_dec_b, st_n=state.n, st_out=state.out, st_edge=state.edge,
                  st_reg=state.reg, st_cls=state.cls, st_nreg=state.nreg, st_ncls=state.ncls, st_time=state.time,
-                 sc_qin=f32z(B, kmax, D), sc_q=f32z(B, kmax, D), sc_k=f32z(B, kmax, D), ref_n=ref_n, lap_col=lap_col, lap_row=lap_row,
+                 sc_qin=None if fast else f32z(B, kmax, D), sc_q=None if fast else f32z(B, kmax, D),
+                 sc_k=None if fast else f32z(B, kmax, D), ref_n=ref_n, lap_col=lap_col, lap_row=lap_row,
                  out16=cafm16, out32=cafm32, perm=perm, status=status)
         return cafm16, cafm32, perm, te32
 
