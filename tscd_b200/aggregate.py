@@ -45,9 +45,10 @@ def make_layout(sel_count: torch.Tensor, B: int, F: int, L: int, row_cap: int, l
 
 
 def mca_forward(lay: ops.AttnLayoutT, w: MCAWeights, bank_cls, bank_reg, bank_score, n_rows_dev, n_loc_dev,
-                need_reg=True, sim_thresh=0.75, conf_sim_thresh=0.99, debug=None):
+                need_reg=True, sim_thresh=0.75, conf_sim_thresh=0.99, debug=None, cls_out=(True, True), obj_out=(True, True)):
     """One MCA module.  bank_* [row_cap,256] 16-bit, bank_score [row_cap] fp32; n_rows_dev / n_loc_dev are int32
-    device scalars (total bank rows / total local rows).  Returns (trans_cls [loc_cap,1024], trans_obj or None)."""
+    device scalars (total bank rows / total local rows).  Returns (trans_cls [loc_cap,1024], trans_obj or None), each a
+    (16-bit, fp32) pair; cls_out / obj_out = (want16, want32) select which copies the output GEMMs write."""
     dev, dt = bank_cls.device, lay.dtype
     qkv_c, _ = ops.linear(bank_cls, w.qkv_cls, m_dev=n_rows_dev)
     qkv_r, _ = ops.linear(bank_reg, w.qkv_reg, m_dev=n_rows_dev)
@@ -60,7 +61,7 @@ def mca_forward(lay: ops.AttnLayoutT, w: MCAWeights, bank_cls, bank_reg, bank_sc
     ops.linear(tmp_c, w.lin_w, w.lin_b, m_dev=n_loc_dev, out16=cat_c[:, 256:], want16=False)
     ops.attn_round2(lay, bufs, bufs["vt_cls"], stats, cat_c[:, :256], use_obj_mask=False, sim_thresh=sim_thresh,
                     conf_sim_thresh=conf_sim_thresh)
-    trans_cls16, trans_cls32 = ops.linear(cat_c, w.out_w, w.out_b, m_dev=n_loc_dev, want16=True, want32=True)
+    trans_cls16, trans_cls32 = ops.linear(cat_c, w.out_w, w.out_b, m_dev=n_loc_dev, want16=cls_out[0], want32=cls_out[1])
     trans_obj16 = trans_obj32 = None
     cat_r = None
     if need_reg:
@@ -68,7 +69,7 @@ def mca_forward(lay: ops.AttnLayoutT, w: MCAWeights, bank_cls, bank_reg, bank_sc
         ops.linear(tmp_r, w.linreg_w, w.linreg_b, m_dev=n_loc_dev, out16=cat_r[:, 256:], want16=False)
         ops.attn_round2(lay, bufs, bufs["vt_reg"], stats, cat_r[:, :256], use_obj_mask=True, sim_thresh=sim_thresh,
                         conf_sim_thresh=conf_sim_thresh)
-        trans_obj16, trans_obj32 = ops.linear(cat_r, w.obj_w, w.obj_b, m_dev=n_loc_dev, want16=True, want32=True)
+        trans_obj16, trans_obj32 = ops.linear(cat_r, w.obj_w, w.obj_b, m_dev=n_loc_dev, want16=obj_out[0], want32=obj_out[1])
     if debug is not None:
         debug.update(qkv_c=qkv_c, qkv_r=qkv_r, bufs=bufs, tmp_c=tmp_c, tmp_r=tmp_r, stats=stats, cat_c=cat_c, cat_r=cat_r)
     return (trans_cls16, trans_cls32), (trans_obj16, trans_obj32)

@@ -165,8 +165,10 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
                         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                     }
                     const bool full = (col0 + 32 <= p.N);
-                    // Full chunks go through a per-warp 32 x 64-byte staging tile so that every store instruction
-                    // writes 8 rows x 64 contiguous bytes (whole sectors) instead of 32 scattered 16-byte pieces.
+                    // Every chunk goes through a per-warp 32 x 64-byte staging tile (16-byte pieces XOR-swizzled by
+                    // row) so that a store instruction writes 8 rows x 64 contiguous bytes (whole sectors) instead of
+                    // 32 scattered 16-byte pieces.  Register arrays are only ever indexed statically (no local memory);
+                    // the ragged / unaligned edge reads single elements back from the staging tile.
                     if (p.out16) {
                         uint32_t pk[16];
 #pragma unroll
@@ -180,13 +182,13 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
                             }
                         }
                         uint16_t* obase = reinterpret_cast<uint16_t*>(p.out16);
-                        if (full && al16) {
-                            __syncwarp();
+                        __syncwarp();
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
-                                    make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                            __syncwarp();
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        __syncwarp();
+                        if (full && al16) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const int rr = 8 * k + (lane >> 2), ch = lane & 3;
@@ -195,21 +197,22 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
                                     *reinterpret_cast<uint4*>(obase + (int64_t)(row_base + rr) * p.ld16 + col0 + ch * 8) = val;
                             }
                         } else if (row_ok) {
-                            const uint16_t* h = reinterpret_cast<const uint16_t*>(pk);
                             uint16_t* o = obase + (int64_t)row * p.ld16 + col0;
-                            for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = h[j];
+                            const int nc = min(32, p.N - col0);
+                            for (int j = 0; j < nc; ++j)
+                                o[j] = *reinterpret_cast<const uint16_t*>(stg + lane * 64 + (((j >> 3) ^ ((lane >> 1) & 3)) << 4) + (j & 7) * 2);
                         }
                     }
                     if (p.out32) {
-                        if (full && al32) {
 #pragma unroll
-                            for (int hh = 0; hh < 2; ++hh) {
-                                __syncwarp();
+                        for (int hh = 0; hh < 2; ++hh) {
+                            __syncwarp();
 #pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    *reinterpret_cast<float4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
-                                        make_float4(v[hh * 16 + 4 * j], v[hh * 16 + 4 * j + 1], v[hh * 16 + 4 * j + 2], v[hh * 16 + 4 * j + 3]);
-                                __syncwarp();
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<float4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                                    make_float4(v[hh * 16 + 4 * j], v[hh * 16 + 4 * j + 1], v[hh * 16 + 4 * j + 2], v[hh * 16 + 4 * j + 3]);
+                            __syncwarp();
+                            if (full && al32) {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
                                     const int rr = 8 * k + (lane >> 2), ch = lane & 3;
@@ -217,10 +220,12 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
                                     if (row_base + rr < M)
                                         *reinterpret_cast<float4*>(p.out32 + (int64_t)(row_base + rr) * p.ld32 + col0 + hh * 16 + ch * 4) = val;
                                 }
+                            } else if (row_ok) {
+                                float* o = p.out32 + (int64_t)row * p.ld32 + col0 + hh * 16;
+                                const int nc = min(16, p.N - col0 - hh * 16);
+                                for (int j = 0; j < nc; ++j)
+                                    o[j] = *reinterpret_cast<const float*>(stg + lane * 64 + (((j >> 2) ^ ((lane >> 1) & 3)) << 4) + (j & 3) * 4);
                             }
-                        } else if (row_ok) {
-                            float* o = p.out32 + (int64_t)row * p.ld32 + col0;
-                            for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = v[j];
                         }
                     }
                 }

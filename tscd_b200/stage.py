@@ -266,20 +266,22 @@ class AggregationStage:
         side = self._side_stream()
         (iou_cls16, iou_cls32), (iou_reg16, iou_reg32) = aggregate.mca_forward(
             lay, w.agg_iou, bank_cls, bank_reg, bank_score, n_rows_dev, n_loc_dev, need_reg=True,
-            sim_thresh=cfg.sim_thresh, conf_sim_thresh=cfg.conf_sim_thresh)
+            sim_thresh=cfg.sim_thresh, conf_sim_thresh=cfg.conf_sim_thresh, cls_out=(False, True))   # cls: matching only (fp32)
         ev_fork = torch.cuda.Event()
         ev_fork.record(main)
         with torch.cuda.stream(side):
             side.wait_event(ev_fork)
             (agg_cls16, agg_cls32), _ = aggregate.mca_forward(lay, w.agg, bank_cls, bank_reg, bank_score, n_rows_dev,
                                                               n_loc_dev, need_reg=False, sim_thresh=cfg.sim_thresh,
-                                                              conf_sim_thresh=cfg.conf_sim_thresh)
+                                                              conf_sim_thresh=cfg.conf_sim_thresh,
+                                                              cls_out=(True, trace is not None))
             _, cls_logits = ops.linear(agg_cls16, w.cls_w, w.cls_b, m_dev=n_loc_dev, want16=False, want32=True)
             ev_join = torch.cuda.Event()
             ev_join.record(side)
         if not torch.cuda.is_current_stream_capturing():
             for t in (cls_logits, agg_cls32):
-                t.record_stream(main)
+                if t is not None:
+                    t.record_stream(main)
 
         # ---- K5: CAFM --------------------------------------------------------------------------------
         if state is None:
