@@ -165,14 +165,35 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }
 
 struct PvTmaps {
-    CUtensorMap qc, kc, qr, kr, vtc, vtr;
+    CUtensorMap qc, kc, qr, kr, k64c, k64r, vtc, vtr;
 };
 
 // -------------------------------------------------------------------------------------------------------
-// attn_pv: row max (pass A), exp/sum + P@V (pass B)
+// attn_pv: row max (pass A), exp/sum + P@V (pass B) -- warp-specialised, mbarrier-pipelined
+//
+//   warp 4 (one thread)  TMA producer: Q tiles (double-buffered per head) and a 3-stage ring of key tiles
+//                        (pass A: Kc|Kr of 128 keys; pass B: Kc|Kr|Vc^T|Vr^T of 64 keys), 32 KB per stage;
+//   warp 5 (one thread)  tcgen05.mma issuer: S = Q K^T of tile g+1 is issued before P(g) @ V(g), into one of two
+//                        TMEM score buffers, so the tensor pipe works while the softmax warps are busy;
+//   warps 0-3            softmax: thread == query row == TMEM lane; tcgen05.ld, visibility mask from the row's own
+//                        frame range (no shared-memory side table), exp2, fp16/bf16 probabilities written as the
+//                        swizzled K-major A operand of the P@V products (two P buffers).
+//   TMEM: pass A  2 x (S_cls 128 | S_reg 128);   pass B  2 x (S_cls 64 | S_reg 64) | O_cc O_rc O_cr O_rr (64 each).
 // -------------------------------------------------------------------------------------------------------
+constexpr int kPvThreads = 192;
+constexpr int kPvStages = 3;
+
+struct PvBars {
+    uint64_t kv_full[kPvStages], kv_empty[kPvStages];
+    uint64_t q_full[2], q_empty[2];
+    uint64_t s_full[2], s_empty[2];
+    uint64_t p_full[2], p_empty[2];
+    uint64_t o_full, o_empty;
+    uint32_t tmem_base;
+};
+
 template <bool BF16>
-__global__ void __launch_bounds__(kAttnThreads, 1) attn_pv_kernel(const __grid_constant__ PvTmaps tm, const tscd_attn_pv_args a) {
+__global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_constant__ PvTmaps tm, const tscd_attn_pv_args a) {
     using namespace tc;
     const tscd_attn_layout& lay = a.lay;
     const int b = blockIdx.y;
@@ -181,172 +202,251 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_pv_kernel(const __grid_c
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    unsigned char* sQc = smem;                 // 16 KB
-    unsigned char* sQr = smem + 16384;         // 16 KB
-    unsigned char* sK = smem + 32768;          // 64 KB (pass A: Kc 32K | Kr 32K; pass B: Kc 16K | Kr 16K | Vtc 16K | Vtr 16K)
-    unsigned char* sP = smem + 98304;          // 64 KB (Pc 32K | Pr 32K)
-    __shared__ __align__(8) uint64_t bar_tma, bar_mma;
-    __shared__ uint32_t tmem_base_s;
-    __shared__ float s_stats[128][17];
-    __shared__ int s_kf[256];
+    unsigned char* sQ = smem;                            // 2 x (Qc 16K | Qr 16K)
+    unsigned char* sKV = smem + 65536;                   // 3 x 32K
+    unsigned char* sP = smem + 65536 + kPvStages * 32768;  // 2 x (Pc 16K | Pr 16K)
+    PvBars& bars = *reinterpret_cast<PvBars*>(sP + 65536);
 
-    const int warp = threadIdx.x >> 5;
-    const bool ctrl = (threadIdx.x == 128);
-    if (ctrl) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 128) {
         tma_prefetch_desc(&tm.qc); tma_prefetch_desc(&tm.kc); tma_prefetch_desc(&tm.qr); tma_prefetch_desc(&tm.kr);
-        tma_prefetch_desc(&tm.vtc); tma_prefetch_desc(&tm.vtr);
-        mbar_init(&bar_tma, 1);
-        mbar_init(&bar_mma, 1);
+        tma_prefetch_desc(&tm.k64c); tma_prefetch_desc(&tm.k64r); tma_prefetch_desc(&tm.vtc); tma_prefetch_desc(&tm.vtr);
+        for (int i = 0; i < kPvStages; ++i) { mbar_init(&bars.kv_full[i], 1); mbar_init(&bars.kv_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars.q_full[i], 1); mbar_init(&bars.q_empty[i], 1);
+            mbar_init(&bars.s_full[i], 1); mbar_init(&bars.s_empty[i], 4);
+            mbar_init(&bars.p_full[i], 4); mbar_init(&bars.p_empty[i], 1);
+        }
+        mbar_init(&bars.o_full, 1); mbar_init(&bars.o_empty, 4);
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc<512>(&tmem_base_s);
+    if (warp == 5) tmem_alloc<512>(&bars.tmem_base);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = tmem_base_s;
-    uint32_t ph_tma = 0, ph_mma = 0;
+    const uint32_t tmem = bars.tmem_base;
 
-    const int row = threadIdx.x;  // query row within the tile (epilogue threads only)
-    const bool is_epi = warp < 4;
+    const int GA = (ci.n_clip + 127) / 128;       // key tiles of pass A
+    const int GB = (ci.n_clip + 63) / 64;         // key tiles of pass B
+    const bool need_reg = a.need_reg != 0;
+
+    // softmax-thread state
+    const int row = threadIdx.x;
+    const bool is_sm = warp < 4;
     const int q = ci.q0 + row;
-    const bool q_ok = is_epi && q < ci.n_loc;
-    int qf = -2;
-    if (q_ok && !lay.self_attn) qf = a.row_frame[ci.s0 + q];
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-    const int L = lay.L;
+    const bool q_ok = is_sm && q < ci.n_loc;
     const bool self_attn = lay.self_attn != 0;
-
-    const uint32_t idesc256 = make_idesc_f16(BF16, 128, 256);
-    const uint32_t idesc128 = make_idesc_f16(BF16, 128, 128);
-    const uint32_t idesc64 = make_idesc_f16(BF16, 128, 64);
-
-    // ================= pass A: row maxima =================
-    for (int h = 0; h < 4; ++h) {
-        float mc = -INFINITY, mr = -INFINITY;
-        for (int g = 0; g * 256 < ci.n_clip; ++g) {
-            const int kbase = g * 256;
-            if (ctrl) {
-                const uint32_t bytes = (g == 0 ? 2 * 16384 : 0) + 4 * 16384;
-                mbar_expect_tx(&bar_tma, bytes);
-                if (g == 0) {
-                    tma_load_2d(sQc, &tm.qc, &bar_tma, h * 64, ci.s0 + ci.q0);
-                    tma_load_2d(sQr, &tm.qr, &bar_tma, h * 64, ci.s0 + ci.q0);
-                }
-                tma_load_2d(sK, &tm.kc, &bar_tma, h * 64, ci.s0 + kbase);
-                tma_load_2d(sK + 16384, &tm.kc, &bar_tma, h * 64, ci.s0 + kbase + 128);
-                tma_load_2d(sK + 32768, &tm.kr, &bar_tma, h * 64, ci.s0 + kbase);
-                tma_load_2d(sK + 49152, &tm.kr, &bar_tma, h * 64, ci.s0 + kbase + 128);
-            }
-            if (is_epi) {
-                for (int j = row; j < 256; j += 128) {
-                    const int k = kbase + j;
-                    s_kf[j] = (k < ci.n_clip) ? (self_attn ? 0 : a.row_frame[ci.s0 + k]) : -1;
-                }
-            }
-            mbar_wait(&bar_tma, ph_tma, 201); ph_tma ^= 1; __syncthreads();
-            if (ctrl) {
-                tc_fence_after();
-                const uint64_t dqc = make_smem_desc_sw128(smem_u32(sQc)), dqr = make_smem_desc_sw128(smem_u32(sQr));
-                const uint64_t dkc = make_smem_desc_sw128(smem_u32(sK)), dkr = make_smem_desc_sw128(smem_u32(sK + 32768));
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16(tmem + 0, dqc + 2 * k, dkc + 2 * k, idesc256, k ? 1u : 0u);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16(tmem + 256, dqr + 2 * k, dkr + 2 * k, idesc256, k ? 1u : 0u);
-                umma_commit(&bar_mma);
-            }
-            __syncthreads();  // s_kf visible
-            mbar_wait(&bar_mma, ph_mma, 202); ph_mma ^= 1; __syncthreads();
-            tc_fence_after();
-            if (is_epi) {
-#pragma unroll 1
-                for (int c0 = 0; c0 < 256; c0 += 32) {
-                    uint32_t rc[32], rr[32];
-                    tmem_ld_32x32(lane_base + c0, rc);
-                    tmem_ld_32x32(lane_base + 256 + c0, rr);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int kf = s_kf[c0 + j];
-                        const bool ok = kf >= 0 && (self_attn || kf >= L || kf == qf);
-                        if (ok) { mc = fmaxf(mc, __uint_as_float(rc[j])); mr = fmaxf(mr, __uint_as_float(rr[j])); }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncthreads();
-        }
-        if (is_epi) { s_stats[row][h] = mc; s_stats[row][4 + h] = mr; }
+    int lo = 0, hi = 0;                            // own frame's key range (clip-local); empty for padding rows
+    if (q_ok && !self_attn) {
+        const int qf = a.row_frame[ci.s0 + q];
+        lo = lay.row_off[b * lay.F + qf] - ci.s0;
+        hi = lay.row_off[b * lay.F + qf + 1] - ci.s0;
     }
+    const int n_glob0 = self_attn ? 0 : ci.n_loc;  // keys >= n_glob0 are visible to every query
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    float mxc[4], mxr[4];
 
-    // ================= pass B: exp / row sums / P @ V =================
-    unsigned char* sKc = sK;
-    unsigned char* sKr = sK + 16384;
-    unsigned char* sVtc = sK + 32768;
-    unsigned char* sVtr = sK + 49152;
-    unsigned char* sPc = sP;
-    unsigned char* sPr = sP + 32768;
-    for (int h = 0; h < 4; ++h) {
-        const float mc = is_epi ? s_stats[row][h] * kLog2e : 0.f;
-        const float mr = is_epi ? s_stats[row][4 + h] * kLog2e : 0.f;
-        float lc = 0.f, lr = 0.f;
-        for (int g = 0; g * 128 < ci.n_clip; ++g) {
-            const int kbase = g * 128;
-            if (ctrl) {
-                const uint32_t bytes = (g == 0 ? 2 * 16384 : 0) + 2 * 16384 + 2 * 8192 + (a.need_reg ? 2 * 8192 : 0);
-                mbar_expect_tx(&bar_tma, bytes);
-                if (g == 0) {
-                    tma_load_2d(sQc, &tm.qc, &bar_tma, h * 64, ci.s0 + ci.q0);
-                    tma_load_2d(sQr, &tm.qr, &bar_tma, h * 64, ci.s0 + ci.q0);
-                }
-                tma_load_2d(sKc, &tm.kc, &bar_tma, h * 64, ci.s0 + kbase);
-                tma_load_2d(sKr, &tm.kr, &bar_tma, h * 64, ci.s0 + kbase);
-                tma_load_2d(sVtc, &tm.vtc, &bar_tma, kbase, b * 256 + h * 64);
-                tma_load_2d(sVtc + 8192, &tm.vtc, &bar_tma, kbase + 64, b * 256 + h * 64);
-                if (a.need_reg) {
-                    tma_load_2d(sVtr, &tm.vtr, &bar_tma, kbase, b * 256 + h * 64);
-                    tma_load_2d(sVtr + 8192, &tm.vtr, &bar_tma, kbase + 64, b * 256 + h * 64);
+    // ======================================= pass A: row maxima =======================================
+    if (warp == 4) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int h = 0; h < 4; ++h) {
+                const int qb = h & 1, uq = h >> 1;
+                mbar_wait(&bars.q_empty[qb], (uq & 1) ^ 1, 300);
+                mbar_expect_tx(&bars.q_full[qb], 32768);
+                tma_load_2d(sQ + qb * 32768, &tm.qc, &bars.q_full[qb], h * 64, ci.s0 + ci.q0);
+                tma_load_2d(sQ + qb * 32768 + 16384, &tm.qr, &bars.q_full[qb], h * 64, ci.s0 + ci.q0);
+                for (int g = 0; g < GA; ++g, ++it) {
+                    const int st = it % kPvStages;
+                    mbar_wait(&bars.kv_empty[st], ((it / kPvStages) & 1) ^ 1, 301);
+                    mbar_expect_tx(&bars.kv_full[st], 32768);
+                    tma_load_2d(sKV + st * 32768, &tm.kc, &bars.kv_full[st], h * 64, ci.s0 + g * 128);
+                    tma_load_2d(sKV + st * 32768 + 16384, &tm.kr, &bars.kv_full[st], h * 64, ci.s0 + g * 128);
                 }
             }
-            if (is_epi) {
-                const int k = kbase + row;
-                s_kf[row] = (k < ci.n_clip) ? (self_attn ? 0 : a.row_frame[ci.s0 + k]) : -1;
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            const uint32_t idesc128 = make_idesc_f16(BF16, 128, 128);
+            uint32_t it = 0;
+            for (int h = 0; h < 4; ++h) {
+                const int qb = h & 1, uq = h >> 1;
+                mbar_wait(&bars.q_full[qb], uq & 1, 310);
+                const uint64_t dqc = make_smem_desc_sw128(smem_u32(sQ + qb * 32768));
+                const uint64_t dqr = make_smem_desc_sw128(smem_u32(sQ + qb * 32768 + 16384));
+                for (int g = 0; g < GA; ++g, ++it) {
+                    const int st = it % kPvStages, sb = it & 1;
+                    mbar_wait(&bars.kv_full[st], (it / kPvStages) & 1, 311);
+                    mbar_wait(&bars.s_empty[sb], ((it >> 1) & 1) ^ 1, 312);
+                    tc_fence_after();
+                    const uint64_t dkc = make_smem_desc_sw128(smem_u32(sKV + st * 32768));
+                    const uint64_t dkr = make_smem_desc_sw128(smem_u32(sKV + st * 32768 + 16384));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem + sb * 256, dqc + 2 * k, dkc + 2 * k, idesc128, k ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem + sb * 256 + 128, dqr + 2 * k, dkr + 2 * k, idesc128, k ? 1u : 0u);
+                    umma_commit(&bars.kv_empty[st]);
+                    umma_commit(&bars.s_full[sb]);
+                }
+                umma_commit(&bars.q_empty[qb]);
             }
-            mbar_wait(&bar_tma, ph_tma, 203); ph_tma ^= 1; __syncthreads();
-            if (ctrl) {
+        }
+    } else {
+        uint32_t it = 0;
+        for (int h = 0; h < 4; ++h) {
+            float mc = -INFINITY, mr = -INFINITY;
+            for (int g = 0; g < GA; ++g, ++it) {
+                const int sb = it & 1, kbase = g * 128;
+                mbar_wait(&bars.s_full[sb], (it >> 1) & 1, 320);
                 tc_fence_after();
-                const uint64_t dqc = make_smem_desc_sw128(smem_u32(sQc)), dqr = make_smem_desc_sw128(smem_u32(sQr));
-                const uint64_t dkc = make_smem_desc_sw128(smem_u32(sKc)), dkr = make_smem_desc_sw128(smem_u32(sKr));
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16(tmem + 0, dqc + 2 * k, dkc + 2 * k, idesc128, k ? 1u : 0u);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16(tmem + 128, dqr + 2 * k, dkr + 2 * k, idesc128, k ? 1u : 0u);
-                umma_commit(&bar_mma);
-            }
-            __syncthreads();
-            mbar_wait(&bar_mma, ph_mma, 204); ph_mma ^= 1; __syncthreads();
-            tc_fence_after();
-            if (is_epi) {
+                const bool all_vis = kbase >= n_glob0 && kbase + 128 <= ci.n_clip;
 #pragma unroll 1
                 for (int c0 = 0; c0 < 128; c0 += 32) {
                     uint32_t rc[32], rr[32];
-                    tmem_ld_32x32(lane_base + c0, rc);
-                    tmem_ld_32x32(lane_base + 128 + c0, rr);
+                    tmem_ld_32x32(lane_base + sb * 256 + c0, rc);
+                    tmem_ld_32x32(lane_base + sb * 256 + 128 + c0, rr);
+                    tmem_ld_wait();
+                    if (all_vis) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { mc = fmaxf(mc, __uint_as_float(rc[j])); mr = fmaxf(mr, __uint_as_float(rr[j])); }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int k = kbase + c0 + j;
+                            const bool ok = k < ci.n_clip && (k >= n_glob0 || (k >= lo && k < hi));
+                            if (ok) { mc = fmaxf(mc, __uint_as_float(rc[j])); mr = fmaxf(mr, __uint_as_float(rr[j])); }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars.s_empty[sb]);
+            }
+            mxc[h] = mc; mxr[h] = mr;
+        }
+    }
+    __syncthreads();      // every pass-A score tile has been consumed: TMEM is re-partitioned for pass B
+
+    // ============================== pass B: exp / row sums / P @ V ================================
+    const uint32_t itA = 4u * (uint32_t)GA;       // barrier use counters continue across the passes
+    if (warp == 4) {
+        if (lane == 0) {
+            uint32_t it = itA;
+            for (int h = 0; h < 4; ++h) {
+                const int qb = h & 1, uq = 2 + (h >> 1);
+                mbar_wait(&bars.q_empty[qb], (uq & 1) ^ 1, 330);
+                mbar_expect_tx(&bars.q_full[qb], 32768);
+                tma_load_2d(sQ + qb * 32768, &tm.qc, &bars.q_full[qb], h * 64, ci.s0 + ci.q0);
+                tma_load_2d(sQ + qb * 32768 + 16384, &tm.qr, &bars.q_full[qb], h * 64, ci.s0 + ci.q0);
+                for (int g = 0; g < GB; ++g, ++it) {
+                    const int st = it % kPvStages;
+                    unsigned char* base = sKV + st * 32768;
+                    mbar_wait(&bars.kv_empty[st], ((it / kPvStages) & 1) ^ 1, 331);
+                    mbar_expect_tx(&bars.kv_full[st], need_reg ? 32768 : 24576);
+                    tma_load_2d(base, &tm.k64c, &bars.kv_full[st], h * 64, ci.s0 + g * 64);
+                    tma_load_2d(base + 8192, &tm.k64r, &bars.kv_full[st], h * 64, ci.s0 + g * 64);
+                    tma_load_2d(base + 16384, &tm.vtc, &bars.kv_full[st], g * 64, b * 256 + h * 64);
+                    if (need_reg) tma_load_2d(base + 24576, &tm.vtr, &bars.kv_full[st], g * 64, b * 256 + h * 64);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            const uint32_t idesc64 = make_idesc_f16(BF16, 128, 64);
+            uint32_t it = itA;          // key-tile counter (ring stage / score buffer of tile `it`)
+            uint32_t ip = 0;            // P@V counter (tile whose probabilities are consumed next)
+            for (int h = 0; h < 4; ++h) {
+                const int qb = h & 1, uq = 2 + (h >> 1);
+                mbar_wait(&bars.q_full[qb], uq & 1, 340);
+                const uint64_t dqc = make_smem_desc_sw128(smem_u32(sQ + qb * 32768));
+                const uint64_t dqr = make_smem_desc_sw128(smem_u32(sQ + qb * 32768 + 16384));
+                for (int g = 0; g <= GB; ++g) {
+                    if (g < GB) {       // scores of tile g
+                        const int st = it % kPvStages, sb = it & 1;
+                        mbar_wait(&bars.kv_full[st], (it / kPvStages) & 1, 341);
+                        mbar_wait(&bars.s_empty[sb], ((it >> 1) & 1) ^ 1, 342);
+                        tc_fence_after();
+                        const uint64_t dkc = make_smem_desc_sw128(smem_u32(sKV + st * 32768));
+                        const uint64_t dkr = make_smem_desc_sw128(smem_u32(sKV + st * 32768 + 8192));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_f16(tmem + sb * 128, dqc + 2 * k, dkc + 2 * k, idesc64, k ? 1u : 0u);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_f16(tmem + sb * 128 + 64, dqr + 2 * k, dkr + 2 * k, idesc64, k ? 1u : 0u);
+                        umma_commit(&bars.s_full[sb]);
+                        ++it;
+                    }
+                    if (g >= 1) {       // P @ V of tile g-1
+                        const uint32_t itp = itA + ip;                 // global index of that tile
+                        const int st = itp % kPvStages, pb = ip & 1;
+                        mbar_wait(&bars.p_full[pb], (ip >> 1) & 1, 343);
+                        if (g == 1 && h > 0) mbar_wait(&bars.o_empty, (h - 1) & 1, 344);   // previous head's O has been read
+                        tc_fence_after();
+                        const uint64_t dpc = make_smem_desc_sw128(smem_u32(sP + pb * 32768));
+                        const uint64_t dpr = make_smem_desc_sw128(smem_u32(sP + pb * 32768 + 16384));
+                        const uint64_t dvc = make_smem_desc_sw128(smem_u32(sKV + st * 32768 + 16384));
+                        const uint64_t dvr = make_smem_desc_sw128(smem_u32(sKV + st * 32768 + 24576));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t acc = (g > 1 || k) ? 1u : 0u;
+                            umma_f16(tmem + 256, dpc + 2 * k, dvc + 2 * k, idesc64, acc);   // O_cc
+                            umma_f16(tmem + 320, dpr + 2 * k, dvc + 2 * k, idesc64, acc);   // O_rc
+                            if (need_reg) {
+                                umma_f16(tmem + 384, dpc + 2 * k, dvr + 2 * k, idesc64, acc);  // O_cr
+                                umma_f16(tmem + 448, dpr + 2 * k, dvr + 2 * k, idesc64, acc);  // O_rr
+                            }
+                        }
+                        umma_commit(&bars.kv_empty[st]);
+                        umma_commit(&bars.p_empty[pb]);
+                        ++ip;
+                    }
+                }
+                umma_commit(&bars.o_full);
+                umma_commit(&bars.q_empty[qb]);
+            }
+        }
+    } else {
+        uint32_t it = itA, ip = 0;
+        float lsum_c[4], lsum_r[4];
+        for (int h = 0; h < 4; ++h) {
+            const float mc = mxc[h] * kLog2e, mr = mxr[h] * kLog2e;
+            float lc = 0.f, lr = 0.f;
+            for (int g = 0; g < GB; ++g, ++it, ++ip) {
+                const int sb = it & 1, pb = ip & 1, kbase = g * 64;
+                mbar_wait(&bars.s_full[sb], (it >> 1) & 1, 350);
+                mbar_wait(&bars.p_empty[pb], ((ip >> 1) & 1) ^ 1, 351);
+                tc_fence_after();
+                unsigned char* sPc = sP + pb * 32768;
+                unsigned char* sPr = sPc + 16384;
+                const bool all_vis = kbase >= n_glob0 && kbase + 64 <= ci.n_clip;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t rc[32], rr[32];
+                    tmem_ld_32x32(lane_base + sb * 128 + c0, rc);
+                    tmem_ld_32x32(lane_base + sb * 128 + 64 + c0, rr);
                     tmem_ld_wait();
                     float ec[32], er[32];
+                    if (all_vis) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int kf = s_kf[c0 + j];
-                        const bool ok = kf >= 0 && (self_attn || kf >= L || kf == qf);
-                        ec[j] = ok ? exp2f(fmaf(__uint_as_float(rc[j]), kLog2e, -mc)) : 0.f;
-                        er[j] = ok ? exp2f(fmaf(__uint_as_float(rr[j]), kLog2e, -mr)) : 0.f;
-                        lc += ec[j];
-                        lr += er[j];
+                        for (int j = 0; j < 32; ++j) {
+                            ec[j] = exp2f(fmaf(__uint_as_float(rc[j]), kLog2e, -mc));
+                            er[j] = exp2f(fmaf(__uint_as_float(rr[j]), kLog2e, -mr));
+                            lc += ec[j];
+                            lr += er[j];
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int k = kbase + c0 + j;
+                            const bool ok = k < ci.n_clip && (k >= n_glob0 || (k >= lo && k < hi));
+                            ec[j] = ok ? exp2f(fmaf(__uint_as_float(rc[j]), kLog2e, -mc)) : 0.f;
+                            er[j] = ok ? exp2f(fmaf(__uint_as_float(rr[j]), kLog2e, -mr)) : 0.f;
+                            lc += ec[j];
+                            lr += er[j];
+                        }
                     }
-                    const int atom = c0 >> 6;
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) {
-                        const int chunk = ((c0 & 63) >> 3) + cc;
-                        const uint32_t off = (uint32_t)atom * 16384u + sw128_off(row, chunk);
+                        const uint32_t off = sw128_off(row, (c0 >> 3) + cc);
                         *reinterpret_cast<uint4*>(sPc + off) =
                             make_uint4(pack2<BF16>(ec[cc * 8], ec[cc * 8 + 1]), pack2<BF16>(ec[cc * 8 + 2], ec[cc * 8 + 3]),
                                        pack2<BF16>(ec[cc * 8 + 4], ec[cc * 8 + 5]), pack2<BF16>(ec[cc * 8 + 6], ec[cc * 8 + 7]));
@@ -356,40 +456,16 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_pv_kernel(const __grid_c
                     }
                 }
                 fence_proxy_async();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&bars.s_empty[sb]); mbar_arrive(&bars.p_full[pb]); }
             }
-            tc_fence_before();
-            __syncthreads();
-            if (ctrl) {
-                tc_fence_after();
-                const uint32_t first = (g == 0) ? 0u : 1u;
-#pragma unroll
-                for (int at = 0; at < 2; ++at) {
-                    const uint64_t dpc = make_smem_desc_sw128(smem_u32(sPc + at * 16384));
-                    const uint64_t dpr = make_smem_desc_sw128(smem_u32(sPr + at * 16384));
-                    const uint64_t dvc = make_smem_desc_sw128(smem_u32(sVtc + at * 8192));
-                    const uint64_t dvr = make_smem_desc_sw128(smem_u32(sVtr + at * 8192));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t acc = (at | k) ? 1u : first;
-                        umma_f16(tmem + 256, dpc + 2 * k, dvc + 2 * k, idesc64, acc);   // O_cc
-                        umma_f16(tmem + 320, dpr + 2 * k, dvc + 2 * k, idesc64, acc);   // O_rc
-                        if (a.need_reg) {
-                            umma_f16(tmem + 384, dpc + 2 * k, dvr + 2 * k, idesc64, acc);  // O_cr
-                            umma_f16(tmem + 448, dpr + 2 * k, dvr + 2 * k, idesc64, acc);  // O_rr
-                        }
-                    }
-                }
-                umma_commit(&bar_mma);
-            }
-            mbar_wait(&bar_mma, ph_mma, 205); ph_mma ^= 1; __syncthreads();
+            lsum_c[h] = lc; lsum_r[h] = lr;
+            // head epilogue: x = (O_c / l_c + O_r / l_r) / 2
+            mbar_wait(&bars.o_full, h & 1, 352);
             tc_fence_after();
-        }
-        // head epilogue: x = (O_c / l_c + O_r / l_r) / 2
-        if (is_epi) {
-            s_stats[row][8 + h] = lc;
-            s_stats[row][12 + h] = lr;
             const float ic = 0.5f / lc, ir = 0.5f / lr;
-            for (int br = 0; br < (a.need_reg ? 2 : 1); ++br) {
+            for (int br = 0; br < (need_reg ? 2 : 1); ++br) {
                 uint16_t* dst = reinterpret_cast<uint16_t*>(br == 0 ? a.x_cls : a.x_reg);
 #pragma unroll 1
                 for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -409,18 +485,21 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_pv_kernel(const __grid_c
                     }
                 }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars.o_empty);
         }
-        tc_fence_before();
-        __syncthreads();
-    }
-    if (q_ok) {
-        float* st = a.stats + (int64_t)(ci.lbase + q) * 16;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) st[j] = s_stats[row][j];
+        if (q_ok) {
+            float4* st = reinterpret_cast<float4*>(a.stats + (int64_t)(ci.lbase + q) * 16);
+            st[0] = make_float4(mxc[0], mxc[1], mxc[2], mxc[3]);
+            st[1] = make_float4(mxr[0], mxr[1], mxr[2], mxr[3]);
+            st[2] = make_float4(lsum_c[0], lsum_c[1], lsum_c[2], lsum_c[3]);
+            st[3] = make_float4(lsum_r[0], lsum_r[1], lsum_r[2], lsum_r[3]);
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 5) {
         tc_fence_after();
         tmem_dealloc<512>(tmem);
     }
@@ -691,19 +770,20 @@ extern "C" int tscd_attn_pv(const tscd_attn_pv_args* a, void* stream) {
     rc |= make_tmap_kmajor(&tm.kc, a->kn_cls, bf, l.row_cap, 256, 256, 128);
     rc |= make_tmap_kmajor(&tm.qr, a->qn_reg, bf, l.row_cap, 256, 256, 128);
     rc |= make_tmap_kmajor(&tm.kr, a->kn_reg, bf, l.row_cap, 256, 256, 128);
+    rc |= make_tmap_kmajor(&tm.k64c, a->kn_cls, bf, l.row_cap, 256, 256, 64);
+    rc |= make_tmap_kmajor(&tm.k64r, a->kn_reg, bf, l.row_cap, 256, 256, 64);
     rc |= make_tmap_kmajor(&tm.vtc, a->vt_cls, bf, (int64_t)l.B * 256, l.nk_pitch, l.nk_pitch, 64);
     rc |= make_tmap_kmajor(&tm.vtr, a->vt_reg, bf, (int64_t)l.B * 256, l.nk_pitch, l.nk_pitch, 64);
     if (rc) return TSCD_ERR_CUDA;
-    const size_t smem = 160 * 1024 + 1024;
-    const int max_q = l.self_attn ? l.nk_pitch : l.nk_pitch;  // query tiles are bounded by the clip size
-    dim3 grid((max_q + 127) / 128, l.B);
+    const size_t smem = 65536 + kPvStages * 32768 + 65536 + sizeof(PvBars) + 1024;
+    dim3 grid((l.nk_pitch + 127) / 128, l.B);      // query tiles are bounded by the clip size; empty tiles exit at once
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (bf) {
         if (cudaFuncSetAttribute(attn_pv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
-        attn_pv_kernel<true><<<grid, kAttnThreads, smem, st>>>(tm, *a);
+        attn_pv_kernel<true><<<grid, kPvThreads, smem, st>>>(tm, *a);
     } else {
         if (cudaFuncSetAttribute(attn_pv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
-        attn_pv_kernel<false><<<grid, kAttnThreads, smem, st>>>(tm, *a);
+        attn_pv_kernel<false><<<grid, kPvThreads, smem, st>>>(tm, *a);
     }
     TSCD_CUDA_CHECK_LAUNCH();
     return TSCD_OK;
