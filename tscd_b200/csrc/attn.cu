@@ -180,7 +180,7 @@ struct PvTmaps {
 //                        swizzled K-major A operand of the P@V products (two P buffers).
 //   TMEM: pass A  2 x (S_cls 128 | S_reg 128);   pass B  2 x (S_cls 64 | S_reg 64) | O_cc O_rc O_cr O_rr (64 each).
 // -------------------------------------------------------------------------------------------------------
-constexpr int kPvThreads = 192;
+constexpr int kPvThreads = 320;     // 8 softmax warps (2 per scheduler), TMA warp, MMA warp
 constexpr int kPvStages = 3;
 
 struct PvBars {
@@ -190,7 +190,15 @@ struct PvBars {
     uint64_t p_full[2], p_empty[2];
     uint64_t o_full, o_empty;
     uint32_t tmem_base;
+    float xch[2][128][2];      // partial row sums exchanged between the two column halves of a row (cls, reg)
 };
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
 template <bool BF16>
 __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_constant__ PvTmaps tm, const tscd_attn_pv_args a) {
@@ -201,26 +209,27 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
     if (ci.q0 >= ci.n_loc) return;
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* smem = smem_raw;                      // no static shared memory: the window starts 1024-byte aligned
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     unsigned char* sQ = smem;                            // 2 x (Qc 16K | Qr 16K)
     unsigned char* sKV = smem + 65536;                   // 3 x 32K
     unsigned char* sP = smem + 65536 + kPvStages * 32768;  // 2 x (Pc 16K | Pr 16K)
     PvBars& bars = *reinterpret_cast<PvBars*>(sP + 65536);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 128) {
+    if (threadIdx.x == 256) {
         tma_prefetch_desc(&tm.qc); tma_prefetch_desc(&tm.kc); tma_prefetch_desc(&tm.qr); tma_prefetch_desc(&tm.kr);
         tma_prefetch_desc(&tm.k64c); tma_prefetch_desc(&tm.k64r); tma_prefetch_desc(&tm.vtc); tma_prefetch_desc(&tm.vtr);
         for (int i = 0; i < kPvStages; ++i) { mbar_init(&bars.kv_full[i], 1); mbar_init(&bars.kv_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars.q_full[i], 1); mbar_init(&bars.q_empty[i], 1);
-            mbar_init(&bars.s_full[i], 1); mbar_init(&bars.s_empty[i], 4);
-            mbar_init(&bars.p_full[i], 4); mbar_init(&bars.p_empty[i], 1);
+            mbar_init(&bars.s_full[i], 1); mbar_init(&bars.s_empty[i], 8);
+            mbar_init(&bars.p_full[i], 8); mbar_init(&bars.p_empty[i], 1);
         }
-        mbar_init(&bars.o_full, 1); mbar_init(&bars.o_empty, 4);
+        mbar_init(&bars.o_full, 1); mbar_init(&bars.o_empty, 8);
         fence_barrier_init();
     }
-    if (warp == 5) tmem_alloc<512>(&bars.tmem_base);
+    if (warp == 9) tmem_alloc<512>(&bars.tmem_base);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -231,8 +240,9 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
     const bool need_reg = a.need_reg != 0;
 
     // softmax-thread state
-    const int row = threadIdx.x;
-    const bool is_sm = warp < 4;
+    const int row = threadIdx.x & 127;
+    const int half = (threadIdx.x >> 7) & 1;     // softmax warps 0-3 own the lower column half of every tile, 4-7 the upper
+    const bool is_sm = warp < 8;
     const int q = ci.q0 + row;
     const bool q_ok = is_sm && q < ci.n_loc;
     const bool self_attn = lay.self_attn != 0;
@@ -243,11 +253,11 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
         hi = lay.row_off[b * lay.F + qf + 1] - ci.s0;
     }
     const int n_glob0 = self_attn ? 0 : ci.n_loc;  // keys >= n_glob0 are visible to every query
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float mxc[4], mxr[4];
 
     // ======================================= pass A: row maxima =======================================
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             uint32_t it = 0;
             for (int h = 0; h < 4; ++h) {
@@ -265,7 +275,7 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         if (lane == 0) {
             const uint32_t idesc128 = make_idesc_f16(BF16, 128, 128);
             uint32_t it = 0;
@@ -301,35 +311,51 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                 tc_fence_after();
                 const bool all_vis = kbase >= n_glob0 && kbase + 128 <= ci.n_clip;
 #pragma unroll 1
-                for (int c0 = 0; c0 < 128; c0 += 32) {
+                for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
                     uint32_t rc[32], rr[32];
                     tmem_ld_32x32(lane_base + sb * 256 + c0, rc);
                     tmem_ld_32x32(lane_base + sb * 256 + 128 + c0, rr);
                     tmem_ld_wait();
+                    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
                     if (all_vis) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) { mc = fmaxf(mc, __uint_as_float(rc[j])); mr = fmaxf(mr, __uint_as_float(rr[j])); }
+                        for (int j = 0; j < 32; j += 2) {
+                            m0 = fmaxf(m0, __uint_as_float(rc[j])); m1 = fmaxf(m1, __uint_as_float(rc[j + 1]));
+                            m2 = fmaxf(m2, __uint_as_float(rr[j])); m3 = fmaxf(m3, __uint_as_float(rr[j + 1]));
+                        }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int k = kbase + c0 + j;
                             const bool ok = k < ci.n_clip && (k >= n_glob0 || (k >= lo && k < hi));
-                            if (ok) { mc = fmaxf(mc, __uint_as_float(rc[j])); mr = fmaxf(mr, __uint_as_float(rr[j])); }
+                            if (ok) { m0 = fmaxf(m0, __uint_as_float(rc[j])); m2 = fmaxf(m2, __uint_as_float(rr[j])); }
                         }
                     }
+                    mc = fmaxf(mc, fmaxf(m0, m1)); mr = fmaxf(mr, fmaxf(m2, m3));
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars.s_empty[sb]);
             }
-            mxc[h] = mc; mxr[h] = mr;
+            reinterpret_cast<float*>(sP)[(half * 128 + row) * 8 + h] = mc;      // sP is idle during pass A
+            reinterpret_cast<float*>(sP)[(half * 128 + row) * 8 + 4 + h] = mr;
         }
     }
     __syncthreads();      // every pass-A score tile has been consumed: TMEM is re-partitioned for pass B
+    if (is_sm) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const float* x0 = reinterpret_cast<const float*>(sP) + row * 8;
+            const float* x1 = x0 + 128 * 8;
+            mxc[h] = fmaxf(x0[h], x1[h]);
+            mxr[h] = fmaxf(x0[4 + h], x1[4 + h]);
+        }
+        softmax_bar_sync();  // both halves have read the maxima before xch is reused for the row sums
+    }
 
     // ============================== pass B: exp / row sums / P @ V ================================
     const uint32_t itA = 4u * (uint32_t)GA;       // barrier use counters continue across the passes
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             uint32_t it = itA;
             for (int h = 0; h < 4; ++h) {
@@ -350,7 +376,7 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         if (lane == 0) {
             const uint32_t idesc64 = make_idesc_f16(BF16, 128, 64);
             uint32_t it = itA;          // key-tile counter (ring stage / score buffer of tile `it`)
@@ -418,32 +444,34 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                 unsigned char* sPc = sP + pb * 32768;
                 unsigned char* sPr = sPc + 16384;
                 const bool all_vis = kbase >= n_glob0 && kbase + 64 <= ci.n_clip;
-#pragma unroll 1
-                for (int c0 = 0; c0 < 64; c0 += 32) {
+                {
+                    const int c0 = half * 32;
                     uint32_t rc[32], rr[32];
                     tmem_ld_32x32(lane_base + sb * 128 + c0, rc);
                     tmem_ld_32x32(lane_base + sb * 128 + 64 + c0, rr);
                     tmem_ld_wait();
                     float ec[32], er[32];
+                    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
                     if (all_vis) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            ec[j] = exp2f(fmaf(__uint_as_float(rc[j]), kLog2e, -mc));
-                            er[j] = exp2f(fmaf(__uint_as_float(rr[j]), kLog2e, -mr));
-                            lc += ec[j];
-                            lr += er[j];
+                        for (int j = 0; j < 32; j += 2) {
+                            ec[j] = ex2_approx(fmaf(__uint_as_float(rc[j]), kLog2e, -mc));
+                            ec[j + 1] = ex2_approx(fmaf(__uint_as_float(rc[j + 1]), kLog2e, -mc));
+                            er[j] = ex2_approx(fmaf(__uint_as_float(rr[j]), kLog2e, -mr));
+                            er[j + 1] = ex2_approx(fmaf(__uint_as_float(rr[j + 1]), kLog2e, -mr));
+                            l0 += ec[j]; l1 += ec[j + 1]; l2 += er[j]; l3 += er[j + 1];
                         }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int k = kbase + c0 + j;
                             const bool ok = k < ci.n_clip && (k >= n_glob0 || (k >= lo && k < hi));
-                            ec[j] = ok ? exp2f(fmaf(__uint_as_float(rc[j]), kLog2e, -mc)) : 0.f;
-                            er[j] = ok ? exp2f(fmaf(__uint_as_float(rr[j]), kLog2e, -mr)) : 0.f;
-                            lc += ec[j];
-                            lr += er[j];
+                            ec[j] = ok ? ex2_approx(fmaf(__uint_as_float(rc[j]), kLog2e, -mc)) : 0.f;
+                            er[j] = ok ? ex2_approx(fmaf(__uint_as_float(rr[j]), kLog2e, -mr)) : 0.f;
+                            l0 += ec[j]; l2 += er[j];
                         }
                     }
+                    lc += l0 + l1; lr += l2 + l3;
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) {
                         const uint32_t off = sw128_off(row, (c0 >> 3) + cc);
@@ -460,36 +488,39 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&bars.s_empty[sb]); mbar_arrive(&bars.p_full[pb]); }
             }
+            // the row's two column halves exchange their partial sums
+            bars.xch[half][row][0] = lc; bars.xch[half][row][1] = lr;
+            softmax_bar_sync();
+            lc += bars.xch[half ^ 1][row][0]; lr += bars.xch[half ^ 1][row][1];
+            softmax_bar_sync();
             lsum_c[h] = lc; lsum_r[h] = lr;
-            // head epilogue: x = (O_c / l_c + O_r / l_r) / 2
+            // head epilogue: x = (O_c / l_c + O_r / l_r) / 2; each half drains 32 of the head's 64 output columns
             mbar_wait(&bars.o_full, h & 1, 352);
             tc_fence_after();
             const float ic = 0.5f / lc, ir = 0.5f / lr;
             for (int br = 0; br < (need_reg ? 2 : 1); ++br) {
                 uint16_t* dst = reinterpret_cast<uint16_t*>(br == 0 ? a.x_cls : a.x_reg);
-#pragma unroll 1
-                for (int c0 = 0; c0 < 64; c0 += 32) {
-                    uint32_t oc[32], orr[32];
-                    tmem_ld_32x32(lane_base + 256 + br * 128 + c0, oc);
-                    tmem_ld_32x32(lane_base + 320 + br * 128 + c0, orr);
-                    tmem_ld_wait();
-                    if (q_ok) {
-                        uint32_t pk[16];
+                const int c0 = half * 32;
+                uint32_t oc[32], orr[32];
+                tmem_ld_32x32(lane_base + 256 + br * 128 + c0, oc);
+                tmem_ld_32x32(lane_base + 320 + br * 128 + c0, orr);
+                tmem_ld_wait();
+                if (q_ok) {
+                    uint32_t pk[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            pk[j] = pack2<BF16>(__uint_as_float(oc[2 * j]) * ic + __uint_as_float(orr[2 * j]) * ir,
-                                                __uint_as_float(oc[2 * j + 1]) * ic + __uint_as_float(orr[2 * j + 1]) * ir);
-                        uint4* o = reinterpret_cast<uint4*>(dst + (int64_t)(ci.lbase + q) * a.ld_x + h * 64 + c0);
+                    for (int j = 0; j < 16; ++j)
+                        pk[j] = pack2<BF16>(__uint_as_float(oc[2 * j]) * ic + __uint_as_float(orr[2 * j]) * ir,
+                                            __uint_as_float(oc[2 * j + 1]) * ic + __uint_as_float(orr[2 * j + 1]) * ir);
+                    uint4* o = reinterpret_cast<uint4*>(dst + (int64_t)(ci.lbase + q) * a.ld_x + h * 64 + c0);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                    }
+                    for (int j = 0; j < 4; ++j) o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars.o_empty);
         }
-        if (q_ok) {
+        if (q_ok && half == 0) {
             float4* st = reinterpret_cast<float4*>(a.stats + (int64_t)(ci.lbase + q) * 16);
             st[0] = make_float4(mxc[0], mxc[1], mxc[2], mxc[3]);
             st[1] = make_float4(mxr[0], mxr[1], mxr[2], mxr[3]);
@@ -499,7 +530,7 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == 9) {
         tc_fence_after();
         tmem_dealloc<512>(tmem);
     }
@@ -775,7 +806,7 @@ extern "C" int tscd_attn_pv(const tscd_attn_pv_args* a, void* stream) {
     rc |= make_tmap_kmajor(&tm.vtc, a->vt_cls, bf, (int64_t)l.B * 256, l.nk_pitch, l.nk_pitch, 64);
     rc |= make_tmap_kmajor(&tm.vtr, a->vt_reg, bf, (int64_t)l.B * 256, l.nk_pitch, l.nk_pitch, 64);
     if (rc) return TSCD_ERR_CUDA;
-    const size_t smem = 65536 + kPvStages * 32768 + 65536 + sizeof(PvBars) + 1024;
+    const size_t smem = 65536 + kPvStages * 32768 + 65536 + sizeof(PvBars);
     dim3 grid((l.nk_pitch + 127) / 128, l.B);      // query tiles are bounded by the clip size; empty tiles exit at once
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (bf) {
