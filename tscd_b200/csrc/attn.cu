@@ -543,9 +543,33 @@ struct R2Tmaps {
     CUtensorMap q128c, q128r, k64c, k64r, vn128c, vn128r, vn64c, vn64r, vt;
 };
 
+// Warp-specialised like attn_pv.  All operands stream through ONE ring of 24 KB stages in a fixed order that the
+// TMA warp produces and the MMA warp consumes:
+//   per key tile kt (64 keys):  S units (h0c h0r h1c h1r) | raw-v atoms of tile kt+1 (cls x4 [, reg x4]) |
+//                               S units (h2c h2r h3c h3r) | V^T halves of tile kt-1 (2 x 128 dims)
+//   stage formats:  S unit  = Q head slice [128x64] 16K + K head slice [64x64] 8K
+//                   raw atom = Vn(query) [128x64] 16K + Vn(keys) [64x64] 8K          (one of the four 64-dim atoms)
+//                   V^T half = [128 dims x 64 keys] 16K
+// TMEM: U 256 | R_cls 64 | R_reg 64 | two score units of 64 columns.  The 8 softmax warps read the raw-v
+// similarities of a tile first (mask bits -> registers), then the 8 score units (head-sum of the normalised
+// attention, exact statistics from attn_pv), then write the round-2 weights as the A operand of W @ V^T.
+constexpr int kR2Threads = 320;
+constexpr int kR2Stages = 6;
+constexpr int kR2StageBytes = 24576;
+
+struct R2Bars {
+    uint64_t full[kR2Stages], empty[kR2Stages];
+    uint64_t r_full, r_empty;
+    uint64_t s_full[2], s_empty[2];
+    uint64_t w_full[2], w_empty[2];
+    uint64_t u_full;
+    uint32_t tmem_base;
+    float xch[2][128];
+};
+
 template <bool BF16>
-__global__ void __launch_bounds__(kAttnThreads, 1) attn_round2_kernel(const __grid_constant__ R2Tmaps tm,
-                                                                       const tscd_attn_round2_args a) {
+__global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid_constant__ R2Tmaps tm,
+                                                                     const tscd_attn_round2_args a) {
     using namespace tc;
     const tscd_attn_layout& lay = a.lay;
     const int b = blockIdx.y;
@@ -553,195 +577,252 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_round2_kernel(const __gr
     if (ci.q0 >= ci.n_loc) return;
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    unsigned char* sA = smem;                  // 64 KB: Vn(query) 4 atoms x 16K   | S phase: Qc 16K, Qr 16K, Kc 8K, Kr 8K
-    unsigned char* sB = smem + 65536;          // 32 KB: Vn(keys) 4 atoms x 8K
-    unsigned char* sW = smem + 98304;          // 16 KB: weights [128 x 64]
-    unsigned char* sVt = smem + 114688;        // 32 KB: V^T tile [256 x 64 keys] (4 boxes x 8K)
-    __shared__ __align__(8) uint64_t bar_tma, bar_mma;
-    __shared__ uint32_t tmem_base_s;
-    __shared__ int s_kf[64];
+    unsigned char* smem = smem_raw;                       // no static shared memory: the window starts 1024-byte aligned
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    unsigned char* sRing = smem;                          // 6 x 24K
+    unsigned char* sW = smem + kR2Stages * kR2StageBytes; // 2 x 16K weights [128 x 64 keys]
+    R2Bars& bars = *reinterpret_cast<R2Bars*>(sW + 32768);
 
-    const int warp = threadIdx.x >> 5;
-    const bool ctrl = (threadIdx.x == 128);
-    if (ctrl) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 256) {
         tma_prefetch_desc(&tm.q128c); tma_prefetch_desc(&tm.q128r); tma_prefetch_desc(&tm.k64c); tma_prefetch_desc(&tm.k64r);
         tma_prefetch_desc(&tm.vn128c); tma_prefetch_desc(&tm.vn128r); tma_prefetch_desc(&tm.vn64c); tma_prefetch_desc(&tm.vn64r);
         tma_prefetch_desc(&tm.vt);
-        mbar_init(&bar_tma, 1);
-        mbar_init(&bar_mma, 1);
+        for (int i = 0; i < kR2Stages; ++i) { mbar_init(&bars.full[i], 1); mbar_init(&bars.empty[i], 1); }
+        mbar_init(&bars.r_full, 1); mbar_init(&bars.r_empty, 8);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars.s_full[i], 1); mbar_init(&bars.s_empty[i], 8);
+            mbar_init(&bars.w_full[i], 8); mbar_init(&bars.w_empty[i], 1);
+        }
+        mbar_init(&bars.u_full, 1);
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc<512>(&tmem_base_s);
+    if (warp == 9) tmem_alloc<512>(&bars.tmem_base);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = tmem_base_s;
-    uint32_t ph_tma = 0, ph_mma = 0;
-
-    const int row = threadIdx.x;
-    const bool is_epi = warp < 4;
-    const int q = ci.q0 + row;
-    const bool q_ok = is_epi && q < ci.n_loc;
-    int qf = -2;
-    if (q_ok && !lay.self_attn) qf = a.row_frame[ci.s0 + q];
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-    const int L = lay.L;
-    const bool self_attn = lay.self_attn != 0;
+    const uint32_t tmem = bars.tmem_base;
+    const int KT = (ci.n_clip + 63) / 64;
     const bool use_obj = a.use_obj_mask != 0;
+    const int n_atoms = use_obj ? 8 : 4;
 
-    float mc[4], mr[4], ilc[4], ilr[4];
-#pragma unroll
-    for (int h = 0; h < 4; ++h) { mc[h] = mr[h] = 0.f; ilc[h] = ilr[h] = 0.f; }
-    if (q_ok) {
-        const float* st = a.stats + (int64_t)(ci.lbase + q) * 16;
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            mc[h] = st[h] * kLog2e; mr[h] = st[4 + h] * kLog2e;
-            ilc[h] = 0.5f / st[8 + h]; ilr[h] = 0.5f / st[12 + h];
-        }
-    }
-    const uint32_t idesc64 = make_idesc_f16(BF16, 128, 64);
-    const uint32_t idesc256 = make_idesc_f16(BF16, 128, 256);
-    float den = 0.f;
-
-    for (int kt = 0; kt * 64 < ci.n_clip; ++kt) {
-        const int kbase = kt * 64;
-        // ---- raw-v cosine (head mean = one K=256 product / 4) ----
-        for (int br = 0; br < (use_obj ? 2 : 1); ++br) {
-            if (ctrl) {
-                mbar_expect_tx(&bar_tma, 4 * 16384 + 4 * 8192);
-#pragma unroll
-                for (int at = 0; at < 4; ++at) {
-                    tma_load_2d(sA + at * 16384, br == 0 ? &tm.vn128c : &tm.vn128r, &bar_tma, at * 64, ci.s0 + ci.q0);
-                    tma_load_2d(sB + at * 8192, br == 0 ? &tm.vn64c : &tm.vn64r, &bar_tma, at * 64, ci.s0 + kbase);
+    if (warp == 8) {
+        // ------------------------------------------------ TMA producer ------------------------------------------------
+        if (lane == 0) {
+            uint32_t it = 0;
+            auto acquire = [&](uint32_t bytes) -> unsigned char* {
+                const int st = it % kR2Stages;
+                mbar_wait(&bars.empty[st], ((it / kR2Stages) & 1) ^ 1, 400);
+                mbar_expect_tx(&bars.full[st], bytes);
+                return sRing + st * kR2StageBytes;
+            };
+            auto load_raw = [&](int kt) {
+                for (int x = 0; x < n_atoms; ++x, ++it) {
+                    const int br = x >> 2, at = x & 3;
+                    unsigned char* d = acquire(24576);
+                    uint64_t* fb = &bars.full[it % kR2Stages];
+                    tma_load_2d(d, br == 0 ? &tm.vn128c : &tm.vn128r, fb, at * 64, ci.s0 + ci.q0);
+                    tma_load_2d(d + 16384, br == 0 ? &tm.vn64c : &tm.vn64r, fb, at * 64, ci.s0 + kt * 64);
                 }
-            }
-            mbar_wait(&bar_tma, ph_tma, 206); ph_tma ^= 1; __syncthreads();
-            if (ctrl) {
-                tc_fence_after();
-#pragma unroll
-                for (int at = 0; at < 4; ++at) {
-                    const uint64_t da = make_smem_desc_sw128(smem_u32(sA + at * 16384));
-                    const uint64_t db = make_smem_desc_sw128(smem_u32(sB + at * 8192));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(tmem + 384 + br * 64, da + 2 * k, db + 2 * k, idesc64, (at | k) ? 1u : 0u);
+            };
+            auto load_units = [&](int kt, int u0) {
+                for (int u = u0; u < u0 + 4; ++u, ++it) {
+                    const int h = u >> 1, br = u & 1;
+                    unsigned char* d = acquire(24576);
+                    uint64_t* fb = &bars.full[it % kR2Stages];
+                    tma_load_2d(d, br == 0 ? &tm.q128c : &tm.q128r, fb, h * 64, ci.s0 + ci.q0);
+                    tma_load_2d(d + 16384, br == 0 ? &tm.k64c : &tm.k64r, fb, h * 64, ci.s0 + kt * 64);
                 }
-                umma_commit(&bar_mma);
+            };
+            auto load_vt = [&](int kt) {
+                for (int hf = 0; hf < 2; ++hf, ++it) {
+                    unsigned char* d = acquire(16384);
+                    uint64_t* fb = &bars.full[it % kR2Stages];
+                    tma_load_2d(d, &tm.vt, fb, kt * 64, b * 256 + hf * 128);
+                    tma_load_2d(d + 8192, &tm.vt, fb, kt * 64, b * 256 + hf * 128 + 64);
+                }
+            };
+            load_raw(0);
+            for (int kt = 0; kt < KT; ++kt) {
+                load_units(kt, 0);
+                if (kt + 1 < KT) load_raw(kt + 1);
+                load_units(kt, 4);
+                if (kt >= 1) load_vt(kt - 1);
             }
-            mbar_wait(&bar_mma, ph_mma, 207); ph_mma ^= 1; __syncthreads();
-            tc_fence_after();
+            load_vt(KT - 1);
         }
-        if (is_epi && row < 64) {
-            const int k = kbase + row;
-            s_kf[row] = (k < ci.n_clip) ? (self_attn ? 0 : a.row_frame[ci.s0 + k]) : -1;
-        }
-        // ---- head-mean attention ----
-        float as[64];
-#pragma unroll
-        for (int j = 0; j < 64; ++j) as[j] = 0.f;
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            if (ctrl) {
-                mbar_expect_tx(&bar_tma, 2 * 16384 + 2 * 8192);
-                tma_load_2d(sA, &tm.q128c, &bar_tma, h * 64, ci.s0 + ci.q0);
-                tma_load_2d(sA + 16384, &tm.q128r, &bar_tma, h * 64, ci.s0 + ci.q0);
-                tma_load_2d(sA + 32768, &tm.k64c, &bar_tma, h * 64, ci.s0 + kbase);
-                tma_load_2d(sA + 40960, &tm.k64r, &bar_tma, h * 64, ci.s0 + kbase);
-            }
-            mbar_wait(&bar_tma, ph_tma, 208); ph_tma ^= 1; __syncthreads();
-            if (ctrl) {
+    } else if (warp == 9) {
+        // ------------------------------------------------ MMA issuer ------------------------------------------------
+        if (lane == 0) {
+            const uint32_t idesc64 = make_idesc_f16(BF16, 128, 64);
+            const uint32_t idesc128 = make_idesc_f16(BF16, 128, 128);
+            uint32_t it = 0, iu = 0;     // ring stage counter, score-unit counter
+            auto wait_stage = [&]() -> unsigned char* {
+                const int st = it % kR2Stages;
+                mbar_wait(&bars.full[st], (it / kR2Stages) & 1, 410);
                 tc_fence_after();
-                const uint64_t dqc = make_smem_desc_sw128(smem_u32(sA)), dqr = make_smem_desc_sw128(smem_u32(sA + 16384));
-                const uint64_t dkc = make_smem_desc_sw128(smem_u32(sA + 32768)), dkr = make_smem_desc_sw128(smem_u32(sA + 40960));
+                return sRing + st * kR2StageBytes;
+            };
+            auto raw = [&](int kt) {          // raw-v similarities of tile kt (K = 256 as four 64-dim atoms per branch)
+                mbar_wait(&bars.r_empty, (kt & 1) ^ 1, 411);
+                tc_fence_after();
+                for (int x = 0; x < n_atoms; ++x, ++it) {
+                    const int br = x >> 2, at = x & 3;
+                    unsigned char* d = wait_stage();
+                    const uint64_t da = make_smem_desc_sw128(smem_u32(d)), db = make_smem_desc_sw128(smem_u32(d + 16384));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16(tmem + 256, dqc + 2 * k, dkc + 2 * k, idesc64, k ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem + 256 + br * 64, da + 2 * k, db + 2 * k, idesc64, (at | k) ? 1u : 0u);
+                    umma_commit(&bars.empty[it % kR2Stages]);
+                }
+                umma_commit(&bars.r_full);
+            };
+            auto units = [&](int u0) {
+                for (int u = u0; u < u0 + 4; ++u, ++it, ++iu) {
+                    const int su = iu & 1;
+                    mbar_wait(&bars.s_empty[su], ((iu >> 1) & 1) ^ 1, 412);
+                    unsigned char* d = wait_stage();
+                    const uint64_t dq = make_smem_desc_sw128(smem_u32(d)), dk = make_smem_desc_sw128(smem_u32(d + 16384));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16(tmem + 320, dqr + 2 * k, dkr + 2 * k, idesc64, k ? 1u : 0u);
-                umma_commit(&bar_mma);
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem + 384 + su * 64, dq + 2 * k, dk + 2 * k, idesc64, k ? 1u : 0u);
+                    umma_commit(&bars.empty[it % kR2Stages]);
+                    umma_commit(&bars.s_full[su]);
+                }
+            };
+            auto wv = [&](int kt) {           // U += W(kt) @ V^T(kt), two 128-dim halves
+                const int wb = kt & 1;
+                mbar_wait(&bars.w_full[wb], (kt >> 1) & 1, 413);
+                tc_fence_after();
+                const uint64_t dw = make_smem_desc_sw128(smem_u32(sW + wb * 16384));
+                for (int hf = 0; hf < 2; ++hf, ++it) {
+                    unsigned char* d = wait_stage();
+                    const uint64_t dv = make_smem_desc_sw128(smem_u32(d));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem + hf * 128, dw + 2 * k, dv + 2 * k, idesc128, (kt | k) ? 1u : 0u);
+                    umma_commit(&bars.empty[it % kR2Stages]);
+                }
+                umma_commit(&bars.w_empty[wb]);
+            };
+            raw(0);
+            for (int kt = 0; kt < KT; ++kt) {
+                units(0);
+                if (kt + 1 < KT) raw(kt + 1);
+                units(4);
+                if (kt >= 1) wv(kt - 1);
             }
-            __syncthreads();  // s_kf visible (first head) / keeps the phases aligned
-            mbar_wait(&bar_mma, ph_mma, 209); ph_mma ^= 1; __syncthreads();
+            wv(KT - 1);
+            umma_commit(&bars.u_full);
+        }
+    } else {
+        // ------------------------------------------------ softmax / weight warps ------------------------------------------------
+        const int row = threadIdx.x & 127;
+        const int half = (threadIdx.x >> 7) & 1;
+        const int q = ci.q0 + row;
+        const bool q_ok = q < ci.n_loc;
+        const bool self_attn = lay.self_attn != 0;
+        int lo = 0, hi = 0;
+        if (q_ok && !self_attn) {
+            const int qf = a.row_frame[ci.s0 + q];
+            lo = lay.row_off[b * lay.F + qf] - ci.s0;
+            hi = lay.row_off[b * lay.F + qf + 1] - ci.s0;
+        }
+        const int n_glob0 = self_attn ? 0 : ci.n_loc;
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        float mcl[8], il[8];       // per unit u = 2*h + br: row max * log2e, 0.5 / row sum
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { mcl[u] = 0.f; il[u] = 0.f; }
+        if (q_ok) {
+            const float* st = a.stats + (int64_t)(ci.lbase + q) * 16;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                mcl[2 * h] = st[h] * kLog2e; mcl[2 * h + 1] = st[4 + h] * kLog2e;
+                il[2 * h] = 0.5f / st[8 + h]; il[2 * h + 1] = 0.5f / st[12 + h];
+            }
+        }
+        const int c0 = half * 32;
+        float den = 0.f;
+        uint32_t iu = 0;
+        for (int kt = 0; kt < KT; ++kt) {
+            const int kbase = kt * 64;
+            // ---- mask bits of this tile: visibility, head-mean raw-v cosine thresholds ----
+            uint32_t bits = 0;
+            mbar_wait(&bars.r_full, kt & 1, 420);
             tc_fence_after();
-            if (is_epi) {
+            {
+                uint32_t rc[32], rr[32];
+                tmem_ld_32x32(lane_base + 256 + c0, rc);
+                if (use_obj) tmem_ld_32x32(lane_base + 320 + c0, rr);
+                tmem_ld_wait();
 #pragma unroll
-                for (int c0 = 0; c0 < 64; c0 += 32) {
-                    uint32_t rc[32], rr[32];
-                    tmem_ld_32x32(lane_base + 256 + c0, rc);
-                    tmem_ld_32x32(lane_base + 320 + c0, rr);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float ec = exp2f(fmaf(__uint_as_float(rc[j]), kLog2e, -mc[h]));
-                        const float er = exp2f(fmaf(__uint_as_float(rr[j]), kLog2e, -mr[h]));
-                        as[c0 + j] += ec * ilc[h] + er * ilr[h];
-                    }
+                for (int j = 0; j < 32; ++j) {
+                    const int k = kbase + c0 + j;
+                    bool ok = k < ci.n_clip && (k >= n_glob0 || (k >= lo && k < hi));
+                    ok = ok && (__uint_as_float(rc[j]) * 0.25f > a.sim_thresh);
+                    if (use_obj) ok = ok && (__uint_as_float(rr[j]) * 0.25f > a.conf_sim_thresh);
+                    bits |= ok ? (1u << j) : 0u;
                 }
             }
             tc_fence_before();
-            __syncthreads();
-        }
-        // ---- weights ----
-        if (is_epi) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars.r_empty);
+            // ---- head-sum of the normalised attention over the 8 (head, branch) score units ----
+            float as[32];
 #pragma unroll
-            for (int c0 = 0; c0 < 64; c0 += 32) {
-                uint32_t rc[32], rr[32];
-                tmem_ld_32x32(lane_base + 384 + c0, rc);
-                if (use_obj) tmem_ld_32x32(lane_base + 448 + c0, rr);
+            for (int j = 0; j < 32; ++j) as[j] = 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u, ++iu) {
+                const int su = iu & 1;
+                mbar_wait(&bars.s_full[su], (iu >> 1) & 1, 421);
+                tc_fence_after();
+                uint32_t r[32];
+                tmem_ld_32x32(lane_base + 384 + su * 64 + c0, r);
                 tmem_ld_wait();
-                float w[32];
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars.s_empty[su]);      // the unit is in registers: release it before the math
+                const float m = mcl[u], sc = il[u];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int kf = s_kf[c0 + j];
-                    bool ok = kf >= 0 && (self_attn || kf >= L || kf == qf);
-                    ok = ok && (__uint_as_float(rc[j]) * 0.25f > a.sim_thresh);
-                    if (use_obj) ok = ok && (__uint_as_float(rr[j]) * 0.25f > a.conf_sim_thresh);
-                    w[j] = ok ? exp2f(as[c0 + j] * (0.25f * kLog2e)) : 0.f;
-                    den += w[j];
-                }
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    const int chunk = (c0 >> 3) + cc;
-                    *reinterpret_cast<uint4*>(sW + sw128_off(row, chunk)) =
-                        make_uint4(pack2<BF16>(w[cc * 8], w[cc * 8 + 1]), pack2<BF16>(w[cc * 8 + 2], w[cc * 8 + 3]),
-                                   pack2<BF16>(w[cc * 8 + 4], w[cc * 8 + 5]), pack2<BF16>(w[cc * 8 + 6], w[cc * 8 + 7]));
-                }
+                for (int j = 0; j < 32; ++j) as[j] = fmaf(ex2_approx(fmaf(__uint_as_float(r[j]), kLog2e, -m)), sc, as[j]);
             }
+            // ---- weights: mask * exp(mean attention) ----
+            float w[32];
+            float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                w[j] = ((bits >> j) & 1u) ? ex2_approx(as[j] * (0.25f * kLog2e)) : 0.f;
+                w[j + 1] = ((bits >> (j + 1)) & 1u) ? ex2_approx(as[j + 1] * (0.25f * kLog2e)) : 0.f;
+                d0 += w[j]; d1 += w[j + 1];
+            }
+            den += d0 + d1;
+            const int wb = kt & 1;
+            mbar_wait(&bars.w_empty[wb], ((kt >> 1) & 1) ^ 1, 422);
+            unsigned char* sWb = sW + wb * 16384;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+                *reinterpret_cast<uint4*>(sWb + sw128_off(row, (c0 >> 3) + cc)) =
+                    make_uint4(pack2<BF16>(w[cc * 8], w[cc * 8 + 1]), pack2<BF16>(w[cc * 8 + 2], w[cc * 8 + 3]),
+                               pack2<BF16>(w[cc * 8 + 4], w[cc * 8 + 5]), pack2<BF16>(w[cc * 8 + 6], w[cc * 8 + 7]));
             fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars.w_full[wb]);
         }
-        if (ctrl) {
-            mbar_expect_tx(&bar_tma, 4 * 8192);
-#pragma unroll
-            for (int at = 0; at < 4; ++at) tma_load_2d(sVt + at * 8192, &tm.vt, &bar_tma, kbase, b * 256 + at * 64);
-        }
-        tc_fence_before();
-        __syncthreads();
-        mbar_wait(&bar_tma, ph_tma, 210); ph_tma ^= 1; __syncthreads();
-        if (ctrl) {
-            tc_fence_after();
-            const uint64_t dw = make_smem_desc_sw128(smem_u32(sW));
-            const uint64_t dv = make_smem_desc_sw128(smem_u32(sVt));   // 256 rows x 64 keys: four 8 KB boxes are contiguous
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(tmem + 0, dw + 2 * k, dv + 2 * k, idesc256, (kt | k) ? 1u : 0u);
-            umma_commit(&bar_mma);
-        }
-        mbar_wait(&bar_mma, ph_mma, 211); ph_mma ^= 1; __syncthreads();
+        // ---- U / den: each column half of a row drains 128 of the 256 output columns ----
+        bars.xch[half][row] = den;
+        softmax_bar_sync();
+        den += bars.xch[half ^ 1][row];
+        mbar_wait(&bars.u_full, 0, 423);
         tc_fence_after();
-    }
-    // ---- U / den ----
-    if (is_epi) {
         const float inv = 1.f / den;
         uint16_t* dst = reinterpret_cast<uint16_t*>(a.out);
 #pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 32) {
+        for (int cb = half * 128; cb < half * 128 + 128; cb += 32) {
             uint32_t u[32];
-            tmem_ld_32x32(lane_base + c0, u);
+            tmem_ld_32x32(lane_base + cb, u);
             tmem_ld_wait();
             if (q_ok) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) pk[j] = pack2<BF16>(__uint_as_float(u[2 * j]) * inv, __uint_as_float(u[2 * j + 1]) * inv);
-                uint4* o = reinterpret_cast<uint4*>(dst + (int64_t)(ci.lbase + q) * a.ld_out + c0);
+                uint4* o = reinterpret_cast<uint4*>(dst + (int64_t)(ci.lbase + q) * a.ld_out + cb);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
             }
@@ -749,7 +830,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_round2_kernel(const __gr
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 9) {
         tc_fence_after();
         tmem_dealloc<512>(tmem);
     }
@@ -837,15 +918,15 @@ extern "C" int tscd_attn_round2(const tscd_attn_round2_args* a, void* stream) {
     rc |= make_tmap_kmajor(&tm.vn64r, a->vn_reg, bf, l.row_cap, 256, 256, 64);
     rc |= make_tmap_kmajor(&tm.vt, a->vt, bf, (int64_t)l.B * 256, l.nk_pitch, l.nk_pitch, 64);
     if (rc) return TSCD_ERR_CUDA;
-    const size_t smem = 144 * 1024 + 1024;
+    const size_t smem = kR2Stages * kR2StageBytes + 32768 + sizeof(R2Bars);
     dim3 grid((l.nk_pitch + 127) / 128, l.B);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (bf) {
         if (cudaFuncSetAttribute(attn_round2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
-        attn_round2_kernel<true><<<grid, kAttnThreads, smem, st>>>(tm, *a);
+        attn_round2_kernel<true><<<grid, kR2Threads, smem, st>>>(tm, *a);
     } else {
         if (cudaFuncSetAttribute(attn_round2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
-        attn_round2_kernel<false><<<grid, kAttnThreads, smem, st>>>(tm, *a);
+        attn_round2_kernel<false><<<grid, kR2Threads, smem, st>>>(tm, *a);
     }
     TSCD_CUDA_CHECK_LAUNCH();
     return TSCD_OK;
