@@ -44,13 +44,41 @@ template <> __device__ __forceinline__ void st2<__nv_bfloat16>(__nv_bfloat16* p,
     *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
 }
 
-constexpr int kPrepPitch = 72;  // 64 keys + 8 padding (bank spread) per channel row of the transpose tile
+constexpr int kPrepRowPitch = 264;  // 16-bit elements per staged v row: 256 + 8 padding (rows stay 16-byte aligned)
 
 template <typename T>
+__device__ __forceinline__ void unpack8(const uint4& raw, float (&v)[8]) {
+    const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = ldf_reg(e[i]);
+}
+template <typename T>
+__device__ __forceinline__ uint4 pack8(const float (&v)[8], float scale) {
+    uint4 o;
+    T* e = reinterpret_cast<T*>(&o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = cvt_from_float<T>(v[i] * scale);
+    return o;
+}
+// sum of squares over the 8 lanes that share a head (lane owns 8 of the head's 64 channels)
+__device__ __forceinline__ float head_sumsq(const float (&v)[8]) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(v[i], v[i], s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    return s;
+}
+
+// One CTA per (64 keys, clip); one warp per bank row, lane = 8 consecutive channels (16-byte loads / stores), all four
+// heads of a row normalised at once (8 lanes per head).  The un-normalised v rows are staged in shared memory and
+// written out transposed (V^T: 64 consecutive keys = 128 bytes per channel row).
+template <typename T>
 __global__ void __launch_bounds__(256) attn_prep_kernel(const tscd_attn_prep_args a) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    T* tile_c = reinterpret_cast<T*>(smem_raw);        // [256][kPrepPitch]
-    T* tile_r = tile_c + 256 * kPrepPitch;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* tile_c = reinterpret_cast<T*>(smem_raw);        // [64 keys][kPrepRowPitch]
+    T* tile_r = tile_c + 64 * kPrepRowPitch;
     const tscd_attn_layout& lay = a.lay;
     const int b = blockIdx.y, k0 = blockIdx.x * 64;
     const int s0 = lay.row_off[b * lay.F];
@@ -60,54 +88,62 @@ __global__ void __launch_bounds__(256) attn_prep_kernel(const tscd_attn_prep_arg
     if (k0 >= n_pad) return;
     const int lbase = lay.lrow_off[b * lay.L];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = lane * 8;
 
+#pragma unroll 2
     for (int i = 0; i < 8; ++i) {
-        const int r = k0 + warp * 8 + i;       // key index within the clip
+        const int r = k0 + warp + 8 * i;       // key index within the clip
         const int row = s0 + r;                // bank row
         const bool valid = r < n_clip;
-        if (valid && lane == 0) {
-            int f = 0;
-            while (f + 1 < lay.F && lay.row_off[b * lay.F + f + 1] <= row) ++f;
-            a.row_frame[row] = f;
+        if (valid) {                           // frame of the row: lanes test one frame each
+            for (int f0 = 0; f0 < lay.F; f0 += 32) {
+                const int f = f0 + lane;
+                const bool in = f < lay.F && lay.row_off[b * lay.F + f] <= row && row < lay.row_off[b * lay.F + f + 1];
+                const unsigned bal = __ballot_sync(0xffffffffu, in);
+                if (bal) { if (lane == 0) a.row_frame[row] = f0 + __ffs(bal) - 1; break; }
+            }
         }
         const float kscale_c = valid ? a.scale * __ldg(a.key_score + row) : 0.f;
 #pragma unroll
         for (int br = 0; br < 2; ++br) {
-            const T* src = reinterpret_cast<const T*>(br == 0 ? a.qkv_cls : a.qkv_reg) + (int64_t)row * a.ld_qkv;
-            T* qn = reinterpret_cast<T*>(br == 0 ? a.qn_cls : a.qn_reg) + (int64_t)row * 256;
-            T* kn = reinterpret_cast<T*>(br == 0 ? a.kn_cls : a.kn_reg) + (int64_t)row * 256;
-            T* vn = reinterpret_cast<T*>(br == 0 ? a.vn_cls : a.vn_reg) + (int64_t)row * 256;
-            T* tile = br == 0 ? tile_c : tile_r;
-            T* xori = reinterpret_cast<T*>(br == 0 ? a.xori_cls : a.xori_reg);
-            const float ks = br == 0 ? kscale_c : a.scale;
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                const int c = h * 64 + lane * 2;
-                float2 q = make_float2(0.f, 0.f), k = q, v = q;
-                if (valid) { q = ld2<T>(src + c); k = ld2<T>(src + 256 + c); v = ld2<T>(src + 512 + c); }
-                float sq = warp_sumf(q.x * q.x + q.y * q.y);
-                float sk = warp_sumf(k.x * k.x + k.y * k.y);
-                float sv = warp_sumf(v.x * v.x + v.y * v.y);
-                if (valid) {
-                    const float nq = sqrtf(sq), nk = sqrtf(sk), nv = sqrtf(sv);
-                    st2<T>(qn + c, q.x / nq, q.y / nq);
-                    st2<T>(kn + c, k.x / nk * ks, k.y / nk * ks);
-                    st2<T>(vn + c, v.x / nv, v.y / nv);
-                    if (xori && r < n_loc) st2<T>(xori + (int64_t)(lbase + r) * a.ld_xori + c, v.x, v.y);
-                }
-                tile[(c) * kPrepPitch + (r - k0)] = cvt_from_float<T>(v.x);
-                tile[(c + 1) * kPrepPitch + (r - k0)] = cvt_from_float<T>(v.y);
+            const T* src = reinterpret_cast<const T*>(br == 0 ? a.qkv_cls : a.qkv_reg) + (int64_t)row * a.ld_qkv + c;
+            T* tile = (br == 0 ? tile_c : tile_r) + (r - k0) * kPrepRowPitch + c;
+            if (!valid) {                       // padding keys: V^T columns must be finite (they are multiplied by zero weights)
+                *reinterpret_cast<uint4*>(tile) = make_uint4(0, 0, 0, 0);
+                continue;
             }
+            const bool is_query = r < n_loc;                   // q of the global rows is never read
+            const uint4 kraw = __ldg(reinterpret_cast<const uint4*>(src + 256));
+            const uint4 vraw = __ldg(reinterpret_cast<const uint4*>(src + 512));
+            float k[8], v[8];
+            unpack8<T>(kraw, k); unpack8<T>(vraw, v);
+            const float ik = (br == 0 ? kscale_c : a.scale) / sqrtf(head_sumsq(k)), iv = 1.f / sqrtf(head_sumsq(v));
+            T* kn = reinterpret_cast<T*>(br == 0 ? a.kn_cls : a.kn_reg) + (int64_t)row * 256 + c;
+            T* vn = reinterpret_cast<T*>(br == 0 ? a.vn_cls : a.vn_reg) + (int64_t)row * 256 + c;
+            *reinterpret_cast<uint4*>(kn) = pack8<T>(k, ik);
+            *reinterpret_cast<uint4*>(vn) = pack8<T>(v, iv);
+            if (is_query) {                                    // uniform over the warp
+                const uint4 qraw = __ldg(reinterpret_cast<const uint4*>(src));
+                float q[8];
+                unpack8<T>(qraw, q);
+                const float iq = 1.f / sqrtf(head_sumsq(q));
+                T* qn = reinterpret_cast<T*>(br == 0 ? a.qn_cls : a.qn_reg) + (int64_t)row * 256 + c;
+                *reinterpret_cast<uint4*>(qn) = pack8<T>(q, iq);
+            }
+            T* xori = reinterpret_cast<T*>(br == 0 ? a.xori_cls : a.xori_reg);
+            if (xori && r < n_loc) *reinterpret_cast<uint4*>(xori + (int64_t)(lbase + r) * a.ld_xori + c) = vraw;
+            *reinterpret_cast<uint4*>(tile) = vraw;
         }
     }
     __syncthreads();
-    // transposed store: channel c -> 64 consecutive keys (128 bytes)
-    for (int c = warp; c < 256; c += 8) {
+    // transposed store: channel ch -> 64 consecutive keys (128 bytes); lane = two consecutive keys
+    for (int ch = warp; ch < 256; ch += 8) {
 #pragma unroll
         for (int br = 0; br < 2; ++br) {
-            const T* tile = br == 0 ? tile_c : tile_r;
-            T* vt = reinterpret_cast<T*>(br == 0 ? a.vt_cls : a.vt_reg) + ((int64_t)b * 256 + c) * lay.nk_pitch + k0;
-            *reinterpret_cast<uint32_t*>(vt + 2 * lane) = *reinterpret_cast<const uint32_t*>(tile + c * kPrepPitch + 2 * lane);
+            const uint16_t* tile = reinterpret_cast<const uint16_t*>(br == 0 ? tile_c : tile_r);
+            const uint32_t lo = tile[(2 * lane) * kPrepRowPitch + ch], hi = tile[(2 * lane + 1) * kPrepRowPitch + ch];
+            T* vt = reinterpret_cast<T*>(br == 0 ? a.vt_cls : a.vt_reg) + ((int64_t)b * 256 + ch) * lay.nk_pitch + k0;
+            *reinterpret_cast<uint32_t*>(vt + 2 * lane) = lo | (hi << 16);
         }
     }
 }
@@ -848,7 +884,7 @@ extern "C" int tscd_attn_prep(const tscd_attn_prep_args* a, void* stream) {
     if (!a || !layout_ok(a->lay)) return TSCD_ERR_INVALID_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     dim3 grid(a->lay.nk_pitch / 64, a->lay.B);
-    const size_t smem = 2 * 256 * kPrepPitch * 2;
+    const size_t smem = 2 * 64 * kPrepRowPitch * 2;
     if (a->lay.dtype == TSCD_F16) {
         if (cudaFuncSetAttribute(attn_prep_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
         attn_prep_kernel<__half><<<grid, 256, smem, st>>>(*a);
