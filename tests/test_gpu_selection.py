@@ -153,6 +153,43 @@ def test_nms_kernel_vs_oracle_ties_and_negative_coords():
         assert keep30[f, :k].tolist() == keep[f, :k].tolist()
 
 
+def test_nms_matrix_path_vs_oracle():
+    """cand_cap <= 768 with max_keep >= cap/4 takes the suppression-matrix kernel (the final per-class NMS of the stage):
+    ragged counts around the 32-box word boundaries, clustered boxes (long suppression chains), exact score ties, negative
+    coordinates (cross-class interaction through the coordinate trick), and max_keep truncation."""
+    ops, _ = _stage_mods()
+    g = torch.Generator().manual_seed(11)
+    sizes = [0, 1, 2, 31, 32, 33, 63, 64, 65, 255, 256, 257, 500, 700, 750, 767, 768] + [int(x) for x in torch.randint(40, 769, (15,), generator=g)]
+    Fn, cap = len(sizes), 768
+    box = torch.zeros(Fn, cap, 4)
+    score = torch.zeros(Fn, cap)
+    cls = torch.zeros(Fn, cap, dtype=torch.int32)
+    count = torch.tensor(sizes, dtype=torch.int32)
+    for f, n in enumerate(sizes):
+        ctr = torch.rand(max(n // 12, 1), 2, generator=g) * 300 - 80
+        c = ctr[torch.randint(0, ctr.shape[0], (n,), generator=g)] + torch.randn(n, 2, generator=g) * 2
+        wh = torch.rand(n, 2, generator=g) * 10 + 30
+        box[f, :n] = torch.cat([c - wh / 2, c + wh / 2], 1)
+        sc = torch.rand(n, generator=g)
+        if n > 4:
+            sc[torch.randint(0, n, (n // 5,), generator=g)] = 0.5
+        score[f, :n] = sc
+        cls[f, :n] = torch.randint(0, 3 if f % 2 else 25, (n,), generator=g).int()
+    for thr in (0.5, 0.75):
+        keep, kc, status = ops.nms(box.cuda(), score.cuda(), cls.cuda(), count.cuda(), thr)           # max_keep = cap -> matrix kernel
+        keep_q, kc_q, _ = ops.nms(box.cuda(), score.cuda(), cls.cuda(), count.cuda(), thr, max_keep=cap // 4)   # truncated, still matrix
+        torch.cuda.synchronize()
+        assert int(status.item()) == 0
+        n_supp = 0
+        for f, n in enumerate(sizes):
+            want = oracle.batched_nms(box[f, :n], score[f, :n], cls[f, :n].float(), thr).tolist()
+            assert keep[f, :int(kc[f])].cpu().tolist() == want, f"thr {thr} frame {f} n {n}"
+            k = min(cap // 4, len(want))
+            assert int(kc_q[f]) == k and keep_q[f, :k].cpu().tolist() == want[:k], f"truncated: thr {thr} frame {f} n {n}"
+            n_supp += n - len(want)
+        assert n_supp > 1000         # the case really exercises suppression
+
+
 def test_nms_capacity_is_reported():
     ops, _ = _stage_mods()
     cap = 5000

@@ -95,6 +95,77 @@ __device__ __forceinline__ int block_excl_scan(int v, int* scratch, int* total) 
     return res;
 }
 
+// ---- block-wide bitonic sort, descending, 64-bit keys ---------------------------------------------------
+// E keys per thread in registers (element index = tid * E + r, E * blockDim.x keys in total, both powers of two).
+// Compare-exchange distances below E stay inside the thread, distances below 32 * E go through warp shuffles, only
+// the remaining ones use shared memory and a CTA barrier (10 of the 55 steps for 1024 keys on 512 threads).
+// `smem` must hold E * blockDim.x keys.  All threads must call.
+template <int E>
+__device__ __forceinline__ void bitonic_sort_regs_desc(unsigned long long (&v)[E], unsigned long long* smem) {
+    const int tid = threadIdx.x;
+    const int N = E * (int)blockDim.x;
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j < E) {
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    if ((r & j) == 0 && r + j < E) {
+                        const bool desc = (((tid * E + r) & k) == 0);
+                        const unsigned long long x = v[r], y = v[r + j < E ? r + j : r];
+                        const bool sw = desc ? (x < y) : (x > y);
+                        v[r] = sw ? y : x;
+                        v[r + j < E ? r + j : r] = sw ? x : y;
+                    }
+                }
+            } else if (j < 32 * E) {
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const int idx = tid * E + r;
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[r], j / E);
+                    const bool keep_max = (((idx & j) == 0) == ((idx & k) == 0));
+                    v[r] = keep_max ? (v[r] > o ? v[r] : o) : (v[r] < o ? v[r] : o);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < E; ++r) smem[tid * E + r] = v[r];
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const int idx = tid * E + r;
+                    const unsigned long long o = smem[idx ^ j];
+                    const bool keep_max = (((idx & j) == 0) == ((idx & k) == 0));
+                    v[r] = keep_max ? (v[r] > o ? v[r] : o) : (v[r] < o ? v[r] : o);
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// Sort the first `n` (<= cap) keys of smem_keys[0..cap) descending in place; cap = E * blockDim.x exactly.
+// Entries at or beyond n are treated as 0 (they sort last).  Ends with the sorted keys visible to the whole CTA.
+template <int E>
+__device__ __forceinline__ void block_sort_desc64(unsigned long long* smem_keys, int n) {
+    unsigned long long v[E];
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < E; ++r) { const int i = tid * E + r; v[r] = i < n ? smem_keys[i] : 0ull; }
+    __syncthreads();
+    bitonic_sort_regs_desc<E>(v, smem_keys);
+#pragma unroll
+    for (int r = 0; r < E; ++r) smem_keys[tid * E + r] = v[r];
+    __syncthreads();
+}
+// run-time dispatch on cap / blockDim.x (a power of two between 1 and 16)
+__device__ __forceinline__ void block_sort_desc64_dyn(unsigned long long* smem_keys, int n, int cap) {
+    const int e = cap / (int)blockDim.x;
+    if (e <= 1) block_sort_desc64<1>(smem_keys, n);
+    else if (e == 2) block_sort_desc64<2>(smem_keys, n);
+    else if (e == 4) block_sort_desc64<4>(smem_keys, n);
+    else if (e == 8) block_sort_desc64<8>(smem_keys, n);
+    else block_sort_desc64<16>(smem_keys, n);
+}
+
 // ---- anchor geometry ----------------------------------------------------------------------------------
 struct AnchorPos {
     int level;

@@ -33,22 +33,6 @@ __device__ __forceinline__ bool iou_gt(const float4& a, float sa, const float4& 
     return (double)ovr > thr;
 }
 
-__device__ void bitonic_sort_desc64(unsigned long long* a, int n64) {
-    for (int k = 2; k <= n64; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n64; i += blockDim.x) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    unsigned long long x = a[i], y = a[ixj];
-                    bool desc = ((i & k) == 0);
-                    if (desc ? (x < y) : (x > y)) { a[i] = y; a[ixj] = x; }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
 __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const tscd_nms_args args, int smem_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int frame = blockIdx.x;
@@ -97,7 +81,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const tscd_nms_args ar
     for (int w = 1; w < kNmsThreads / 32; ++w) mx = fmaxf(mx, red[w]);
     const float off_unit = __fadd_rn(mx, 1.f);  // boxes.max() + 1
 
-    bitonic_sort_desc64(skey, n64);
+    block_sort_desc64_dyn(skey, n, smem_cap);
 
     for (int r = threadIdx.x; r < n; r += blockDim.x) {
         int pos = (int)(0xffffffffu - (uint32_t)(skey[r] & 0xffffffffull));
@@ -177,6 +161,135 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const tscd_nms_args ar
     if (threadIdx.x == 0) args.keep_count[frame] = s_nkept;
 }
 
+// -------------------------------------------------------------------------------------------------------------
+// Suppression-matrix variant for frames that keep most of their candidates (the final per-class NMS keeps up to all
+// n <= 768 boxes, so the lazy kernel's O(kept * N) apply phase degenerates to N^2 with a barrier-heavy chunk loop).
+// Same sort, same offset boxes, same IoU predicate; then
+//   (1) all threads build the upper-triangular bit matrix  M[i][w] bit b = box i suppresses box 32w+b (> i),
+//   (2) one warp walks the sorted boxes 32 at a time: the diagonal block resolves the word with shuffles, the rows of
+//       the newly kept boxes are OR-ed into the per-lane `removed` words.
+// -------------------------------------------------------------------------------------------------------------
+constexpr int kNmsMatThreads = 512;
+constexpr int kNmsMatCap = 768;      // 768 x 24 words = 72 KB
+
+__global__ void __launch_bounds__(kNmsMatThreads) nms_matrix_kernel(const tscd_nms_args args, int smem_cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int frame = blockIdx.x;
+    int n = args.count[frame];
+    if (n > smem_cap || n > kNmsMatCap) {
+        if (threadIdx.x == 0) { atomicMin(args.status, TSCD_ERR_CAPACITY); args.keep_count[frame] = 0; }
+        return;
+    }
+    if (n <= 0) {
+        if (threadIdx.x == 0) args.keep_count[frame] = 0;
+        return;
+    }
+    int n64 = 1;
+    while (n64 < n) n64 <<= 1;
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem_raw);      // [n64]
+    float4* sbox = reinterpret_cast<float4*>(skey + smem_cap);                        // [n] sorted, offset boxes
+    float* sarea = reinterpret_cast<float*>(sbox + smem_cap);                         // [n]
+    uint32_t* smask = reinterpret_cast<uint32_t*>(sarea + smem_cap);                  // [n][W]
+    __shared__ float red[kNmsMatThreads / 32];
+
+    const int64_t base = (int64_t)frame * args.cand_cap;
+    const float* gscore = args.score + base;
+    const float4* gbox = reinterpret_cast<const float4*>(args.box) + base;
+    const int32_t* gcls = args.cls + base;
+
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < n64; i += blockDim.x) {
+        unsigned long long v = 0ull;
+        if (i < n) {
+            v = ((unsigned long long)f2ord(gscore[i]) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+            float4 b = gbox[i];
+            mx = fmaxf(mx, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
+        }
+        skey[i] = v;
+    }
+    mx = warp_maxf(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < kNmsMatThreads / 32; ++w) mx = fmaxf(mx, red[w]);
+    const float off_unit = __fadd_rn(mx, 1.f);  // boxes.max() + 1
+
+    block_sort_desc64_dyn(skey, n, smem_cap);
+
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        int pos = (int)(0xffffffffu - (uint32_t)(skey[r] & 0xffffffffull));
+        float4 b = gbox[pos];
+        float off = __fmul_rn((float)gcls[pos], off_unit);
+        b.x = __fadd_rn(b.x, off); b.y = __fadd_rn(b.y, off);
+        b.z = __fadd_rn(b.z, off); b.w = __fadd_rn(b.w, off);
+        sbox[r] = b;
+        sarea[r] = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+    }
+    __syncthreads();
+
+    const double thr = (double)args.iou_thresh;
+    const int W = (n + 31) >> 5;
+    // (1) suppression matrix; rows are dealt in a snake order so that long and short rows alternate per thread
+    const int T = blockDim.x;
+    for (int k = 0;; ++k) {
+        const int i = (k & 1) ? (T * (k + 1) - 1 - (int)threadIdx.x) : (T * k + (int)threadIdx.x);
+        if (T * k >= n) break;
+        if (i >= n) continue;
+        const float4 bi = sbox[i];
+        const float si = sarea[i];
+        for (int w = i >> 5; w < W; ++w) {
+            uint32_t bits = 0u;
+            const int j0 = w << 5;
+            const int jlo = max(i + 1, j0), jhi = min(n, j0 + 32);
+            for (int j = jlo; j < jhi; ++j) {
+                const float4 bj = sbox[j];
+                // cheap x-extent rejection first: boxes of different classes sit (max+1) apart after the offset
+                if (fminf(bi.z, bj.z) > fmaxf(bi.x, bj.x)) {
+                    if (iou_gt(bi, si, bj, sarea[j], thr)) bits |= 1u << (j - j0);
+                }
+            }
+            smask[i * W + w] = bits;
+        }
+    }
+    __syncthreads();
+
+    // (2) resolve, 32 sorted boxes per step
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const int max_keep = args.max_keep;
+        int32_t* keep = args.keep + (int64_t)frame * max_keep;
+        uint32_t removed = 0u;           // lane w < W: suppressed flags of boxes [32w, 32w+32)
+        int nk = 0;
+        for (int w = 0; w < W && nk < max_keep; ++w) {
+            const int i = (w << 5) + lane;
+            const uint32_t rem_w = __shfl_sync(0xffffffffu, removed, w);
+            const uint32_t diag = i < n ? smask[i * W + w] : 0u;          // boxes of this word that box i suppresses
+            uint32_t alive = ~rem_w;
+            if (n - (w << 5) < 32) alive &= (1u << (n - (w << 5))) - 1u;
+            uint32_t kept = 0u;
+#pragma unroll
+            for (int l = 0; l < 32; ++l) {
+                const uint32_t dl = __shfl_sync(0xffffffffu, diag, l);
+                if ((alive >> l) & 1u) { kept |= 1u << l; alive &= ~dl; }
+            }
+            // truncate to max_keep, emit, and apply the kept rows to the later words
+            const int room = max_keep - nk;
+            const int rank = __popc(kept & ((1u << lane) - 1u));
+            const bool mine = ((kept >> lane) & 1u) && rank < room;
+            if (mine) keep[nk + rank] = (int)(0xffffffffu - (uint32_t)(skey[i] & 0xffffffffull));
+            uint32_t kk = kept;
+            while (kk) {
+                const int l = __ffs(kk) - 1;
+                kk &= kk - 1;
+                if (lane > w && lane < W) removed |= smask[((w << 5) + l) * W + lane];
+            }
+            nk += min(__popc(kept), room);
+        }
+        if (lane == 0) args.keep_count[frame] = nk;
+    }
+}
+
 }  // namespace tscd
 
 extern "C" int tscd_nms(const tscd_nms_args* a, void* stream) {
@@ -186,8 +299,18 @@ extern "C" int tscd_nms(const tscd_nms_args* a, void* stream) {
     int cap = a->cand_cap < kNmsCap ? a->cand_cap : kNmsCap;
     int cap64 = 1;
     while (cap64 < cap) cap64 <<= 1;   // sort buffer must hold the padded power of two
+    if (cap64 < kNmsMatThreads) cap64 = kNmsMatThreads;   // ... and E * blockDim.x keys of the block sort (either kernel)
     size_t smem = (size_t)cap64 * (8 + 16 + 4 + 1) + 16;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (cap <= kNmsMatCap && (int64_t)a->max_keep * 4 >= cap) {
+        // most candidates survive: suppression-matrix kernel
+        const size_t smem_m = (size_t)cap64 * (8 + 16 + 4) + (size_t)cap * ((cap + 31) / 32) * 4 + 16;
+        if (cudaFuncSetAttribute(nms_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m) != cudaSuccess)
+            return TSCD_ERR_CUDA;
+        nms_matrix_kernel<<<a->num_frames, kNmsMatThreads, smem_m, st>>>(*a, cap64);
+        TSCD_CUDA_CHECK_LAUNCH();
+        return TSCD_OK;
+    }
     if (cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return TSCD_ERR_CUDA;
     nms_kernel<<<a->num_frames, kNmsThreads, smem, st>>>(*a, cap64);

@@ -29,18 +29,22 @@ __device__ void radix_select_kth(const uint32_t* keys, int n, int k, SelSmem* s,
         const int shift = 24 - 8 * pass;
         for (int i = threadIdx.x; i < 256; i += blockDim.x) s->hist[i] = 0;
         __syncthreads();
-        // warp-aggregated histogram: sigmoid scores share a few exponent digits, so plain shared-memory atomics
-        // serialise on one bin; lanes with the same digit elect a leader that adds the group's population once
+        // histogram of the digit among the keys that still match the prefix.  Sigmoid scores share a few exponent
+        // digits, so a plain shared-memory atomic per key would serialise on one bin in the first pass: the lanes
+        // that agree with the first active lane's digit are counted with one ballot (leader adds the population),
+        // the others (few, spread over many bins in the later passes) add themselves.
         for (int i0 = 0; i0 < n; i0 += blockDim.x) {
             const int i = i0 + threadIdx.x;
             const uint32_t u = i < n ? keys[i] : 0u;
             const bool in = i < n && (u & mask) == prefix;
             const unsigned act = __ballot_sync(0xffffffffu, in);
-            if (in) {
-                const uint32_t d = (u >> shift) & 255;
-                const unsigned peers = __match_any_sync(act, d);
-                if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s->hist[d], __popc(peers));
-            }
+            if (act == 0u) continue;
+            const uint32_t d = (u >> shift) & 255;
+            const int first = __ffs(act) - 1;
+            const uint32_t d0 = __shfl_sync(0xffffffffu, d, first);
+            const unsigned same = __ballot_sync(0xffffffffu, in && d == d0);
+            if ((int)(threadIdx.x & 31) == first) atomicAdd(&s->hist[d0], __popc(same));
+            else if (in && d != d0) atomicAdd(&s->hist[d], 1);
         }
         __syncthreads();
         if (threadIdx.x < 32) {
@@ -73,25 +77,8 @@ __device__ void radix_select_kth(const uint32_t* keys, int n, int k, SelSmem* s,
     *req_out = remaining;
 }
 
-// Descending bitonic sort of n64 (power of two) 64-bit keys in shared memory.
-__device__ void bitonic_sort_desc(unsigned long long* a, int n64) {
-    for (int k = 2; k <= n64; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n64; i += blockDim.x) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    unsigned long long x = a[i], y = a[ixj];
-                    bool desc = ((i & k) == 0);
-                    if (desc ? (x < y) : (x > y)) { a[i] = y; a[ixj] = x; }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
 template <typename T>
-__global__ void __launch_bounds__(kSelThreads) select_kernel(const tscd_select_args args, int sort_cap) {
+__global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const tscd_select_args args, int sort_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int frame = blockIdx.x;
     const tscd_anchors& an = args.anchors;
@@ -113,52 +100,83 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const tscd_select_a
     // thread, all C+1 planes of the group in flight; other layouts take the per-anchor path.
     int n_ge = 0;  // mode B: anchors with score >= conf_thresh
     const bool modeB = args.mode == 1;
+    constexpr int VMAX = 16 / sizeof(T);
+    // vector groups of all levels share one index space, so the small levels do not cost extra latency rounds
+    int nvec_l[TSCD_MAX_LEVELS], goff[TSCD_MAX_LEVELS + 1];
+    goff[0] = 0;
+#pragma unroll
+    for (int l = 0; l < TSCD_MAX_LEVELS; ++l) {
+        nvec_l[l] = 0;
+        if (l < an.num_levels) {
+            const int nl = an.level_start[l + 1] - an.level_start[l];
+            const T* op = reinterpret_cast<const T*>(args.obj.ptr[l]) + (int64_t)frame * args.obj.frame_stride[l];
+            const T* cp = reinterpret_cast<const T*>(args.cls.ptr[l]) + (int64_t)frame * args.cls.frame_stride[l];
+            const bool planar = args.obj.anchor_stride[l] == 1 && args.cls.anchor_stride[l] == 1 &&
+                                ((reinterpret_cast<uintptr_t>(op) | reinterpret_cast<uintptr_t>(cp)) & 15) == 0 &&
+                                (args.cls.chan_stride[l] % VMAX) == 0 && (args.obj.frame_stride[l] % VMAX) == 0 &&
+                                (args.cls.frame_stride[l] % VMAX) == 0;
+            nvec_l[l] = planar ? nl / VMAX : 0;
+        }
+        goff[l + 1] = goff[l] + nvec_l[l];
+    }
+    for (int g = threadIdx.x; g < goff[TSCD_MAX_LEVELS]; g += blockDim.x) {
+        static_assert(TSCD_MAX_LEVELS == 3, "level lookup below is written for three FPN levels");
+        const int l = (g >= goff[1] ? 1 : 0) + (g >= goff[2] ? 1 : 0);
+        const int a_lo = l == 0 ? an.level_start[0] : (l == 1 ? an.level_start[1] : an.level_start[2]);
+        const int a0 = (g - (l == 0 ? 0 : (l == 1 ? goff[1] : goff[2]))) * VMAX;
+        const T* op = reinterpret_cast<const T*>(args.obj.ptr[l]) + (int64_t)frame * args.obj.frame_stride[l] + a0;
+        const T* cp = reinterpret_cast<const T*>(args.cls.ptr[l]) + (int64_t)frame * args.cls.frame_stride[l] + a0;
+        const int64_t ccs = args.cls.chan_stride[l];
+        float ob[VMAX], best[VMAX];
+        int bi[VMAX];
+        const uint4 oraw = __ldg(reinterpret_cast<const uint4*>(op));
+#pragma unroll
+        for (int v = 0; v < VMAX; ++v) { best[v] = -INFINITY; bi[v] = 0; }
+        // class planes in batches of 8 independent 16-byte loads (128 B in flight per thread)
+        for (int c0 = 0; c0 < C; c0 += 8) {
+            uint4 raw[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (c0 + u < C) raw[u] = __ldg(reinterpret_cast<const uint4*>(cp + (int64_t)(c0 + u) * ccs));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (c0 + u < C) {
+                    const T* e = reinterpret_cast<const T*>(&raw[u]);
+#pragma unroll
+                    for (int v = 0; v < VMAX; ++v) {
+                        const float x = ldf_reg(e[v]);
+                        if (x > best[v]) { best[v] = x; bi[v] = c0 + u; }     // first maximum wins (torch.max)
+                    }
+                }
+            }
+        }
+        {
+            const T* e = reinterpret_cast<const T*>(&oraw);
+#pragma unroll
+            for (int v = 0; v < VMAX; ++v) ob[v] = ldf_reg(e[v]);
+        }
+#pragma unroll
+        for (int v = 0; v < VMAX; ++v) {
+            const int a = a_lo + a0 + v;
+            float o = ob[v], b = best[v];
+            if (sig) o = sigmoidf_ref(o);
+            float key = o;
+            if (modeB) {
+                if (sig) b = sigmoidf_ref(b);
+                key = __fmul_rn(o, b);                            // tscd_head.py:1591  obj * class_conf
+                n_ge += (key >= args.conf_thresh) ? 1 : 0;
+            }
+            keys[a] = f2ord(key);
+            conf_s[a] = b;
+            cls_s[a] = (unsigned char)bi[v];
+        }
+    }
     for (int l = 0; l < an.num_levels; ++l) {
         const int a_lo = an.level_start[l], nl = an.level_start[l + 1] - a_lo;
-        constexpr int VMAX = 16 / sizeof(T);
         const T* op = reinterpret_cast<const T*>(args.obj.ptr[l]) + (int64_t)frame * args.obj.frame_stride[l];
         const T* cp = reinterpret_cast<const T*>(args.cls.ptr[l]) + (int64_t)frame * args.cls.frame_stride[l];
         const int64_t ccs = args.cls.chan_stride[l];
-        const bool planar = args.obj.anchor_stride[l] == 1 && args.cls.anchor_stride[l] == 1 &&
-                            ((reinterpret_cast<uintptr_t>(op) | reinterpret_cast<uintptr_t>(cp)) & 15) == 0 &&
-                            (ccs % VMAX) == 0 && (args.obj.frame_stride[l] % VMAX) == 0 && (args.cls.frame_stride[l] % VMAX) == 0;
-        const int nvec = planar ? nl / VMAX : 0;
-        for (int g = threadIdx.x; g < nvec; g += blockDim.x) {
-            const int a0 = g * VMAX;
-            float ob[VMAX], best[VMAX];
-            int bi[VMAX];
-            {
-                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(op + a0));
-                const T* e = reinterpret_cast<const T*>(&raw);
-#pragma unroll
-                for (int v = 0; v < VMAX; ++v) { ob[v] = ldf_reg(e[v]); best[v] = -INFINITY; bi[v] = 0; }
-            }
-#pragma unroll 5
-            for (int c = 0; c < C; ++c) {
-                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(cp + (int64_t)c * ccs + a0));
-                const T* e = reinterpret_cast<const T*>(&raw);
-#pragma unroll
-                for (int v = 0; v < VMAX; ++v) {
-                    const float x = ldf_reg(e[v]);
-                    if (x > best[v]) { best[v] = x; bi[v] = c; }     // first maximum wins (torch.max)
-                }
-            }
-#pragma unroll
-            for (int v = 0; v < VMAX; ++v) {
-                const int a = a_lo + a0 + v;
-                float o = ob[v], b = best[v];
-                if (sig) o = sigmoidf_ref(o);
-                float key = o;
-                if (modeB) {
-                    if (sig) b = sigmoidf_ref(b);
-                    key = __fmul_rn(o, b);                            // tscd_head.py:1591  obj * class_conf
-                    n_ge += (key >= args.conf_thresh) ? 1 : 0;
-                }
-                keys[a] = f2ord(key);
-                conf_s[a] = b;
-                cls_s[a] = (unsigned char)bi[v];
-            }
-        }
+        const int nvec = nvec_l[l];
         for (int i = nvec * VMAX + threadIdx.x; i < nl; i += blockDim.x) {      // tail / non-planar layouts
             const int a = a_lo + i;
             float o = ldf(op + (int64_t)i * args.obj.anchor_stride[l]);
@@ -232,18 +250,12 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const tscd_select_a
 
     // ---- mode A: order by objectness, descending, ties lower anchor id first ---------------------------
     if (args.mode == 0) {
-        int n64 = 1;
-        while (n64 < n_sel) n64 <<= 1;
-        for (int i = threadIdx.x; i < n64; i += blockDim.x) {
-            unsigned long long v = 0ull;
-            if (i < n_sel) {
-                int a = sel[i];
-                v = ((unsigned long long)keys[a] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)a);
-            }
-            sortbuf[i] = v;
+        for (int i = threadIdx.x; i < n_sel; i += blockDim.x) {
+            const int a = sel[i];
+            sortbuf[i] = ((unsigned long long)keys[a] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)a);
         }
         __syncthreads();
-        bitonic_sort_desc(sortbuf, n64);
+        block_sort_desc64_dyn(sortbuf, n_sel, sort_cap);      // registers + shuffles; shared memory only for distances >= 32 * E
         for (int i = threadIdx.x; i < n_sel; i += blockDim.x)
             sel[i] = (int)(0xffffffffu - (uint32_t)(sortbuf[i] & 0xffffffffull));
         __syncthreads();
@@ -284,6 +296,8 @@ extern "C" int tscd_select(const tscd_select_args* a, void* stream) {
     if (A <= 0) return TSCD_ERR_INVALID_ARG;
     int n64 = 1;
     if (a->mode == 0) while (n64 < (a->pre_k < A ? a->pre_k : A)) n64 <<= 1;
+    if (n64 < kSelThreads) n64 = kSelThreads;            // the block sort works on E * blockDim.x keys
+    if (n64 > 16 * kSelThreads) return TSCD_ERR_CAPACITY;
     if (a->num_classes > 255) return TSCD_ERR_UNSUPPORTED;
     const int selcap = ((A < a->cand_cap ? A : a->cand_cap) + 3) & ~3;
     size_t smem = (size_t)((A + 3) & ~3) * 8 + (size_t)selcap * 4 + 8 + (size_t)n64 * 8 + (size_t)((A + 15) & ~15);
