@@ -175,20 +175,26 @@ def test_nms_matrix_path_vs_oracle():
             sc[torch.randint(0, n, (n // 5,), generator=g)] = 0.5
         score[f, :n] = sc
         cls[f, :n] = torch.randint(0, 3 if f % 2 else 25, (n,), generator=g).int()
-    for thr in (0.5, 0.75):
-        keep, kc, status = ops.nms(box.cuda(), score.cuda(), cls.cuda(), count.cuda(), thr)           # max_keep = cap -> matrix kernel
-        keep_q, kc_q, _ = ops.nms(box.cuda(), score.cuda(), cls.cuda(), count.cuda(), thr, max_keep=cap // 4)   # truncated, still matrix
-        torch.cuda.synchronize()
-        assert int(status.item()) == 0
-        n_supp = 0
-        for f, n in enumerate(sizes):
-            want = oracle.batched_nms(box[f, :n], score[f, :n], cls[f, :n].float(), thr).tolist()
-            assert keep[f, :int(kc[f])].cpu().tolist() == want, f"thr {thr} frame {f} n {n}"
-            k = min(cap // 4, len(want))
-            assert int(kc_q[f]) == k and keep_q[f, :k].cpu().tolist() == want[:k], f"truncated: thr {thr} frame {f} n {n}"
-            n_supp += n - len(want)
-        assert n_supp > 1000         # the case really exercises suppression
-
+    # shift 0: negative coordinates -> class bands overlap -> general (matrix) algorithm;
+    # shift 100: all coordinates positive -> frames with <= 96 boxes per class take the exact per-class fast path
+    for shift in (0.0, 100.0):
+        bx = box + shift
+        for thr in (0.5, 0.75):
+            keep, kc, status = ops.nms(bx.cuda(), score.cuda(), cls.cuda(), count.cuda(), thr)           # max_keep = cap -> matrix kernel
+            keep_q, kc_q, _ = ops.nms(bx.cuda(), score.cuda(), cls.cuda(), count.cuda(), thr, max_keep=cap // 4)   # truncated, still matrix
+            keep_l, kc_l, _ = ops.nms(bx.cuda(), score.cuda(), cls.cuda(), count.cuda(), thr, max_keep=30)         # lazy kernel (+ fast path)
+            torch.cuda.synchronize()
+            assert int(status.item()) == 0
+            n_supp = 0
+            for f, n in enumerate(sizes):
+                want = oracle.batched_nms(bx[f, :n], score[f, :n], cls[f, :n].float(), thr).tolist()
+                assert keep[f, :int(kc[f])].cpu().tolist() == want, f"shift {shift} thr {thr} frame {f} n {n}"
+                k = min(cap // 4, len(want))
+                assert int(kc_q[f]) == k and keep_q[f, :k].cpu().tolist() == want[:k], f"truncated: shift {shift} thr {thr} frame {f} n {n}"
+                k = min(30, len(want))
+                assert int(kc_l[f]) == k and keep_l[f, :k].cpu().tolist() == want[:k], f"top-30: shift {shift} thr {thr} frame {f} n {n}"
+                n_supp += n - len(want)
+            assert n_supp > 1000         # the case really exercises suppression
 
 def test_nms_capacity_is_reported():
     ops, _ = _stage_mods()

@@ -33,6 +33,205 @@ __device__ __forceinline__ bool iou_gt(const float4& a, float sa, const float4& 
     return (double)ovr > thr;
 }
 
+
+// -------------------------------------------------------------------------------------------------------------
+// Per-class fast path, shared by both kernels.  After the coordinate-trick offset, boxes of different classes can
+// only interact if the x-extents of their classes overlap (negative coordinates).  When no cross-class pair exceeds
+// the IoU threshold -- the normal case -- greedy NMS decomposes EXACTLY into independent per-class problems: one warp per class walks
+// the class's boxes in score order (lanes test the later members), all classes in parallel, and the keep list is
+// the score-ordered compaction of the per-box flags.  Same offset boxes, same IoU predicate as the general paths.
+// Returns false (nothing written) when the frame does not qualify: class ids outside [0, 256), a class with more
+// than kClsMaxMembers boxes, or a cross-class pair above the IoU threshold; the caller then runs its general algorithm.
+// -------------------------------------------------------------------------------------------------------------
+constexpr int kClsMaxMembers = 96;
+
+struct ClsScratch {          // carved from dynamic shared memory by the caller
+    unsigned short* list;    // [n] sorted indices grouped by class (score order inside a class)
+    unsigned char* flag;     // [n] 1 = kept
+    unsigned char* scls;     // [n] class of sorted box r
+    int* off;                // [257] class offsets into list
+    float* lo;               // [256] min x1 of the class's offset boxes
+    float* hi;               // [256] max x2
+    int* misc;               // [4]
+    unsigned char* ids;      // [256] non-empty class ids, ascending
+};
+__host__ __device__ inline size_t cls_scratch_bytes(int cap) { return (size_t)cap * 4 + 257 * 4 + 512 * 4 + 16 + 16 + 256; }
+__device__ inline ClsScratch carve_cls_scratch(unsigned char* p, int cap) {
+    ClsScratch c;
+    c.off = reinterpret_cast<int*>(p); p += 257 * 4 + 12;
+    c.lo = reinterpret_cast<float*>(p); p += 256 * 4;
+    c.hi = reinterpret_cast<float*>(p); p += 256 * 4;
+    c.misc = reinterpret_cast<int*>(p); p += 16;
+    c.ids = p; p += 256;
+    c.list = reinterpret_cast<unsigned short*>(p); p += (size_t)cap * 2;
+    c.flag = p; p += cap;
+    c.scls = p;
+    return c;
+}
+
+// skey: sorted keys (low 32 bits = inverted original position); sbox/sarea: sorted offset boxes.
+__device__ bool nms_per_class(const tscd_nms_args& args, int frame, int n, const unsigned long long* skey, const float4* sbox,
+                              const float* sarea, const int32_t* gcls, ClsScratch sc) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    if (tid == 0) { sc.misc[0] = 0; sc.misc[1] = 0; }
+    for (int c = tid; c < 257; c += blockDim.x) sc.off[c] = 0;
+    __syncthreads();
+    // class of every sorted box, class histogram
+    int bad = 0;
+    for (int r = tid; r < n; r += blockDim.x) {
+        const int pos = (int)(0xffffffffu - (uint32_t)(skey[r] & 0xffffffffull));
+        const int c = gcls[pos];
+        if (c < 0 || c > 255) { bad = 1; continue; }
+        sc.scls[r] = (unsigned char)c;
+        atomicAdd(&sc.off[c + 1], 1);
+    }
+    if (bad) sc.misc[0] = 1;
+    __syncthreads();
+    if (sc.misc[0]) return false;
+    if (warp == 0) {                       // exclusive prefix over the 256 class counts (8 per lane), size check
+        int loc[8], tot = 0, big = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { loc[j] = sc.off[1 + lane * 8 + j]; tot += loc[j]; big |= loc[j] > kClsMaxMembers; }
+        int inc = warp_incl_scan(tot, lane);
+        int run = inc - tot;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { run += loc[j]; sc.off[1 + lane * 8 + j] = run; }
+        __syncwarp();
+        if (__any_sync(0xffffffffu, big) && lane == 0) sc.misc[0] = 1;
+        // compact list of the non-empty classes (ascending ids), kept in sc.ids
+        int ncl = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = j * 32 + lane;
+            const bool ne = sc.off[c + 1] - sc.off[c] > 0;      // prefix values of the lower classes are final: same warp, in order
+            __syncwarp();
+            const unsigned bal = __ballot_sync(0xffffffffu, ne);
+            if (ne) sc.ids[ncl + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)c;
+            ncl += __popc(bal);
+        }
+        if (lane == 0) sc.misc[2] = ncl;
+    }
+    __syncthreads();
+    if (sc.misc[0]) return false;
+    const int ncl = sc.misc[2];
+    // class lists in score order + class x-bands: warp per class, ballot compaction over the sorted boxes
+    for (int ci = warp; ci < ncl; ci += nw) {
+        const int c = sc.ids[ci];
+        const int o0 = sc.off[c], cnt = sc.off[c + 1] - o0;
+        int filled = 0;
+        float lo = INFINITY, hi = -INFINITY;
+        for (int r0 = 0; r0 < n && filled < cnt; r0 += 32) {
+            const int r = r0 + lane;
+            const bool m = r < n && sc.scls[r] == c;
+            const unsigned bal = __ballot_sync(0xffffffffu, m);
+            if (m) {
+                sc.list[o0 + filled + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)r;
+                lo = fminf(lo, sbox[r].x); hi = fmaxf(hi, sbox[r].z);
+            }
+            filled += __popc(bal);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+        if (lane == 0) { sc.lo[c] = lo; sc.hi[c] = hi; }
+    }
+    __syncthreads();
+    // Classes whose x-bands overlap (negative coordinates near the image border) may interact.  The decomposition stays
+    // exact as long as no CROSS-class pair actually exceeds the IoU threshold: test exactly those pairs (warp per class,
+    // lanes over the member pairs of every overlapping later class); a single hit sends the frame to the general path.
+    {
+        const double thr_x = (double)args.iou_thresh;
+        for (int ci = warp; ci < ncl; ci += nw) {
+            const int c = sc.ids[ci];
+            const int oc = sc.off[c], nc = sc.off[c + 1] - oc;
+            const float l = sc.lo[c], h = sc.hi[c];
+            for (int di = ci + 1; di < ncl; ++di) {
+                const int d = sc.ids[di];
+                if (!(fminf(h, sc.hi[d]) > fmaxf(l, sc.lo[d]))) continue;
+                const int od = sc.off[d], nd = sc.off[d + 1] - od;
+                bool hit = false;
+                for (int ii = 0; ii < nc; ++ii) {              // lanes over the members of d, one member of c at a time
+                    const int i = sc.list[oc + ii];
+                    const float4 bi = sbox[i];
+                    if (!(bi.z > sc.lo[d])) continue;           // box i does not reach into the band of class d (d > c: further right)
+                    const float si = sarea[i];
+                    for (int jj = lane; jj < nd; jj += 32) {
+                        const int j = sc.list[od + jj];
+                        hit = hit || iou_gt(bi, si, sbox[j], sarea[j], thr_x);
+                    }
+                }
+                if (__any_sync(0xffffffffu, hit)) { if (lane == 0) sc.misc[0] = 1; }
+            }
+        }
+    }
+    __syncthreads();
+    if (sc.misc[0]) return false;
+
+    // per-class greedy: lane j owns members j, j+32, j+64 (<= kClsMaxMembers); the class leader walks the score order
+    const double thr = (double)args.iou_thresh;
+    for (int ci = warp; ci < ncl; ci += nw) {
+        const int c = sc.ids[ci];
+        const int o0 = sc.off[c], cnt = sc.off[c + 1] - o0;
+        constexpr int S = kClsMaxMembers / 32;
+        float4 b[S];
+        float ar[S];
+        unsigned dead = 0;
+#pragma unroll
+        for (int q = 0; q < S; ++q) {
+            const int k = q * 32 + lane;
+            if (k < cnt) { const int r = sc.list[o0 + k]; b[q] = sbox[r]; ar[q] = sarea[r]; }
+            else { b[q] = make_float4(0.f, 0.f, 0.f, 0.f); ar[q] = 0.f; dead |= 1u << q; }
+        }
+        for (int k = 0; k < cnt; ++k) {
+            const int q0 = k >> 5, l0 = k & 31;
+            // is member k still alive?  (owner lane l0, slot q0)
+            const unsigned dk = __shfl_sync(0xffffffffu, dead, l0);
+            if ((dk >> q0) & 1u) continue;
+            float4 bk;
+            float ak;
+            {
+                const float4 src = q0 == 0 ? b[0] : (q0 == 1 ? b[1] : b[S - 1]);
+                const float sa = q0 == 0 ? ar[0] : (q0 == 1 ? ar[1] : ar[S - 1]);
+                bk.x = __shfl_sync(0xffffffffu, src.x, l0); bk.y = __shfl_sync(0xffffffffu, src.y, l0);
+                bk.z = __shfl_sync(0xffffffffu, src.z, l0); bk.w = __shfl_sync(0xffffffffu, src.w, l0);
+                ak = __shfl_sync(0xffffffffu, sa, l0);
+            }
+#pragma unroll
+            for (int q = 0; q < S; ++q) {
+                const int m = q * 32 + lane;
+                if (m > k && m < cnt && !((dead >> q) & 1u) && iou_gt(bk, ak, b[q], ar[q], thr)) dead |= 1u << q;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < S; ++q) {
+            const int k = q * 32 + lane;
+            if (k < cnt) sc.flag[sc.list[o0 + k]] = ((dead >> q) & 1u) ? 0 : 1;
+        }
+    }
+    __syncthreads();
+    // score-ordered compaction of the kept boxes, truncated to max_keep
+    {
+        const int max_keep = args.max_keep;
+        int32_t* keep = args.keep + (int64_t)frame * max_keep;
+        int* carry = &sc.misc[1];
+        int* scan = sc.off;              // class offsets are no longer needed: reuse as scan scratch (>= 33 ints)
+        __syncthreads();
+        for (int r0 = 0; r0 < n; r0 += blockDim.x) {
+            const int r = r0 + tid;
+            const int f = (r < n && sc.flag[r]) ? 1 : 0;
+            int tot;
+            const int ex = block_excl_scan(f, scan, &tot);
+            const int base = *carry;
+            if (f && base + ex < max_keep) keep[base + ex] = (int)(0xffffffffu - (uint32_t)(skey[r] & 0xffffffffull));
+            __syncthreads();
+            if (tid == 0) *carry = base + tot;
+            __syncthreads();
+            if (*carry >= max_keep) break;
+        }
+        if (tid == 0) args.keep_count[frame] = min(*carry, max_keep);
+    }
+    return true;
+}
+
 __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const tscd_nms_args args, int smem_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int frame = blockIdx.x;
@@ -227,6 +426,9 @@ __global__ void __launch_bounds__(kNmsMatThreads) nms_matrix_kernel(const tscd_n
         sarea[r] = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
     }
     __syncthreads();
+    // the suppression-matrix area doubles as scratch of the per-class fast path
+    if (nms_per_class(args, frame, n, skey, sbox, sarea, gcls, carve_cls_scratch(reinterpret_cast<unsigned char*>(smask), smem_cap)))
+        return;
 
     const double thr = (double)args.iou_thresh;
     const int W = (n + 31) >> 5;
@@ -302,9 +504,12 @@ extern "C" int tscd_nms(const tscd_nms_args* a, void* stream) {
     if (cap64 < kNmsMatThreads) cap64 = kNmsMatThreads;   // ... and E * blockDim.x keys of the block sort (either kernel)
     size_t smem = (size_t)cap64 * (8 + 16 + 4 + 1) + 16;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (cap <= kNmsMatCap && (int64_t)a->max_keep * 4 >= cap) {
-        // most candidates survive: suppression-matrix kernel
-        const size_t smem_m = (size_t)cap64 * (8 + 16 + 4) + (size_t)cap * ((cap + 31) / 32) * 4 + 16;
+    if (cap > 64 && cap <= kNmsMatCap && (int64_t)a->max_keep * 4 >= cap) {
+        // most candidates survive: per-class decomposition / suppression-matrix kernel (the lazy kernel stops early and wins
+        // when only the first few survivors are wanted, and for tiny frames)
+        size_t smem_m = (size_t)cap * ((cap + 31) / 32) * 4;
+        if (smem_m < cls_scratch_bytes(cap64)) smem_m = cls_scratch_bytes(cap64);
+        smem_m += (size_t)cap64 * (8 + 16 + 4) + 16;
         if (cudaFuncSetAttribute(nms_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m) != cudaSuccess)
             return TSCD_ERR_CUDA;
         nms_matrix_kernel<<<a->num_frames, kNmsMatThreads, smem_m, st>>>(*a, cap64);
