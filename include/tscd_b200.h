@@ -370,17 +370,19 @@ int tscd_cafm_chain(const tscd_cafm_chain_args* args, void* stream);
 /* ---- TaskAligned attention + LayerNorms ---------------------------------------------------------------------
  * tscd_frame_attention: MHAttention.forward (tscd_matching.py:159-181) for every local frame at once:
  * per frame and head, softmax(q^ k^T) v with L2-normalised q,k (no scale), queries/keys/values all from the
- * SAME frame.  q/k/v are fp32 GEMM outputs (projections done by tscd_linear).
+ * SAME frame.  q/k/v are the GEMM outputs of the projections (tscd_linear): fp32 for the generic kernel, 16-bit for the
+ * mma.sync tensor-core kernel used when every frame holds <= 32 proposals.
  * tscd_residual_ln2: y = LN_b(LN_a(x + r))  -- CrossAttentionLayer.forward_post's norm followed by the
  * decoder_norm of TaskAligned (tscd_matching.py:421-433, 1133-1137). */
 typedef struct {
     int32_t num_frames;          /* B*L local frames */
     int32_t heads, head_dim;
+    int32_t in_dtype;            /* TSCD_F32: generic kernel; TSCD_F16 / TSCD_BF16: tensor-core kernel (frames <= 32 rows, head_dim 128) */
     const int32_t* lrow_off;     /* [num_frames+1] */
-    const float* q; int32_t ldq;
-    const float* k; int32_t ldk;
-    const float* v; int32_t ldv;
-    float* out; int32_t ldo;     /* [loc_cap, heads*head_dim] */
+    const void* q; int32_t ldq;  /* row pitches in elements */
+    const void* k; int32_t ldk;
+    const void* v; int32_t ldv;
+    float* out; int32_t ldo;     /* [loc_cap, heads*head_dim] fp32 */
 } tscd_frame_attention_args;
 int tscd_frame_attention(const tscd_frame_attention_args* args, void* stream);
 

@@ -117,7 +117,7 @@ class CafmLapArgs(C.Structure):
 
 
 class FrameAttentionArgs(C.Structure):
-    _fields_ = _fields("num_frames:i heads:i head_dim:i lrow_off:p q:p ldq:i k:p ldk:i v:p ldv:i out:p ldo:i")
+    _fields_ = _fields("num_frames:i heads:i head_dim:i in_dtype:i lrow_off:p q:p ldq:i k:p ldk:i v:p ldv:i out:p ldo:i")
 
 
 class ResidualLn2Args(C.Structure):

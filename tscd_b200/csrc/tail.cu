@@ -5,6 +5,7 @@
 // (yolox/models/tscd_matching.py:1107-1139, 421-433, 159-181), decode_reg_preds5 (yolox/models/tscd_head.py:
 // 914-949) and postprocess (yolox/models/post_process.py:9-85).
 #include "common.cuh"
+#include "mma.cuh"
 
 namespace tscd {
 
@@ -31,8 +32,8 @@ __global__ void __launch_bounds__(256, 2) frame_attention_kernel(const tscd_fram
 
     auto stage = [&](int k0, int kc) {
         for (int j = warp; j < kc; j += 8) {   // stage + normalise keys, copy values
-            const float* kr = a.k + (int64_t)(l0 + k0 + j) * a.ldk + h * hd;
-            const float* vr = a.v + (int64_t)(l0 + k0 + j) * a.ldv + h * hd;
+            const float* kr = reinterpret_cast<const float*>(a.k) + (int64_t)(l0 + k0 + j) * a.ldk + h * hd;
+            const float* vr = reinterpret_cast<const float*>(a.v) + (int64_t)(l0 + k0 + j) * a.ldv + h * hd;
             float kv[4], ks = 0.f;
 #pragma unroll
             for (int t = 0; t < 4; ++t)
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(256, 2) frame_attention_kernel(const tscd_fram
         const bool r_ok = r < n;
         float qs = 0.f;
         if (r_ok) {
-            for (int d = lane; d < hd; d += 32) { const float x = a.q[(int64_t)(l0 + r) * a.ldq + h * hd + d]; myq[d] = x; qs = fmaf(x, x, qs); }
+            for (int d = lane; d < hd; d += 32) { const float x = reinterpret_cast<const float*>(a.q)[(int64_t)(l0 + r) * a.ldq + h * hd + d]; myq[d] = x; qs = fmaf(x, x, qs); }
         }
         qs = warp_sumf(qs);
         if (r_ok) { const float inv = 1.f / sqrtf(qs); for (int d = lane; d < hd; d += 32) myq[d] *= inv; }
@@ -103,6 +104,140 @@ __global__ void __launch_bounds__(256, 2) frame_attention_kernel(const tscd_fram
                 if (t < nd) a.out[(int64_t)(l0 + r) * a.ldo + h * hd + lane + 32 * t] = acc[t] * inv;
         }
         __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- frame attention, tensor cores
+// Frames of at most 32 proposals, head_dim 128, 16-bit q/k/v (the GEMM's 16-bit outputs).  One CTA per (frame, half of the
+// heads): the frame's q, k, v head slices are staged with cp.async, warp = (head, 16-row tile).  S = q k^T on mma.sync
+// (8 k-steps), cosine by scaling the fp32 scores with 1/|q_r| and 1/|k_j|, softmax in registers, P fed to P @ v straight
+// from the accumulator layout.  Output fp32 (it feeds the residual LayerNorm).
+constexpr int kFa16Pitch = 136;     // 16-bit elements per staged row: 128 + 8 (272 B -> ldmatrix conflict-free)
+constexpr int kFa16Heads = 4;       // heads per CTA
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2) frame_attention16_kernel(const tscd_frame_attention_args a) {
+    extern __shared__ __align__(16) unsigned char fa16_smem[];
+    T* sQ = reinterpret_cast<T*>(fa16_smem);                        // [4 heads][32][136]
+    T* sK = sQ + kFa16Heads * 32 * kFa16Pitch;
+    T* sV = sK + kFa16Heads * 32 * kFa16Pitch;
+    float* sQn = reinterpret_cast<float*>(sV + kFa16Heads * 32 * kFa16Pitch);   // [4][32] 1/|q|
+    float* sKn = sQn + kFa16Heads * 32;
+    const int lf = blockIdx.x, h0 = blockIdx.y * kFa16Heads;
+    const int l0 = a.lrow_off[lf], n = a.lrow_off[lf + 1] - l0;
+    if (n <= 0) return;
+    if (n > 32) __trap();                     // host contract: this variant is only launched for kmax <= 32
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const T* q = reinterpret_cast<const T*>(a.q);
+    const T* k = reinterpret_cast<const T*>(a.k);
+    const T* v = reinterpret_cast<const T*>(a.v);
+    // stage: 3 matrices x 4 heads x n rows x 16 chunks of 16 bytes
+    for (int i = tid; i < 3 * kFa16Heads * 32 * 16; i += 256) {
+        const int ch = i & 15, r = (i >> 4) & 31, hh = (i >> 9) & 3, m = i >> 11;
+        T* dst = (m == 0 ? sQ : (m == 1 ? sK : sV)) + (hh * 32 + r) * kFa16Pitch + ch * 8;
+        if (r < n) {
+            const T* src = (m == 0 ? q + (int64_t)(l0 + r) * a.ldq : (m == 1 ? k + (int64_t)(l0 + r) * a.ldk : v + (int64_t)(l0 + r) * a.ldv)) +
+                           (h0 + hh) * 128 + ch * 8;
+            cp_async16(dst, src);
+        } else {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);     // padding rows: finite (keys masked, values x 0)
+        }
+    }
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+    // 1 / |q_r|, 1 / |k_j| per head: one thread per (matrix, head, row)
+    {
+        const int r = tid & 31, hh = (tid >> 5) & 3, m = tid >> 7;
+        const T* row = (m == 0 ? sQ : sK) + (hh * 32 + r) * kFa16Pitch;
+        float ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            float x[8];
+            load8(row + c * 8, x);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ss = fmaf(x[i], x[i], ss);
+        }
+        (m == 0 ? sQn : sKn)[hh * 32 + r] = 1.f / sqrtf(ss);
+    }
+    __syncthreads();
+    const int hh = warp >> 1, mt = warp & 1;
+    if (mt * 16 >= n) return;
+    const T* Qh = sQ + hh * 32 * kFa16Pitch;
+    const T* Kh = sK + hh * 32 * kFa16Pitch;
+    const T* Vh = sV + hh * 32 * kFa16Pitch;
+    float sc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+        uint32_t qa[4];
+        ldsm_x4(qa, Qh + (mt * 16 + (lane & 15)) * kFa16Pitch + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+        for (int ntp = 0; ntp < 2; ++ntp) {       // two key n-tiles per ldmatrix.x4: (keys 16ntp..+7, k lo/hi), (keys +8.., k lo/hi)
+            uint32_t kb[4];
+            ldsm_x4(kb, Kh + (ntp * 16 + (lane & 7) + ((lane >> 4) & 1) * 8) * kFa16Pitch + ks * 16 + ((lane >> 3) & 1) * 8);
+            mma16816<T>(sc[2 * ntp], qa, kb[0], kb[1]);
+            mma16816<T>(sc[2 * ntp + 1], qa, kb[2], kb[3]);
+        }
+    }
+    const int R0 = mt * 16 + g, R1 = R0 + 8;
+    const float iq0 = sQn[hh * 32 + R0], iq1 = sQn[hh * 32 + R1];
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const int j0 = nt * 8 + 2 * t4;
+        const float ik0 = sKn[hh * 32 + j0], ik1 = sKn[hh * 32 + j0 + 1];
+        sc[nt][0] = j0 < n ? sc[nt][0] * iq0 * ik0 : -INFINITY;
+        sc[nt][1] = j0 + 1 < n ? sc[nt][1] * iq0 * ik1 : -INFINITY;
+        sc[nt][2] = j0 < n ? sc[nt][2] * iq1 * ik0 : -INFINITY;
+        sc[nt][3] = j0 + 1 < n ? sc[nt][3] * iq1 * ik1 : -INFINITY;
+        mx0 = fmaxf(mx0, fmaxf(sc[nt][0], sc[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(sc[nt][2], sc[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        sc[nt][0] = expf(sc[nt][0] - mx0); sc[nt][1] = expf(sc[nt][1] - mx0);
+        sc[nt][2] = expf(sc[nt][2] - mx1); sc[nt][3] = expf(sc[nt][3] - mx1);
+        sum0 += sc[nt][0] + sc[nt][1];
+        sum1 += sc[nt][2] + sc[nt][3];
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    const float is0 = 1.f / sum0, is1 = 1.f / sum1;
+    uint32_t pa[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        pa[ks][0] = pack2<T>(sc[2 * ks][0] * is0, sc[2 * ks][1] * is0);
+        pa[ks][1] = pack2<T>(sc[2 * ks][2] * is1, sc[2 * ks][3] * is1);
+        pa[ks][2] = pack2<T>(sc[2 * ks + 1][0] * is0, sc[2 * ks + 1][1] * is0);
+        pa[ks][3] = pack2<T>(sc[2 * ks + 1][2] * is1, sc[2 * ks + 1][3] * is1);
+    }
+    float* out0 = a.out + (int64_t)(l0 + R0) * a.ldo + (h0 + hh) * 128;
+    float* out1 = a.out + (int64_t)(l0 + R1) * a.ldo + (h0 + hh) * 128;
+#pragma unroll
+    for (int ntp = 0; ntp < 8; ++ntp) {           // 16 output dims per iteration
+        float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            uint32_t vb[4];
+            ldsm_x4_trans(vb, Vh + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kFa16Pitch + ntp * 16 + (lane >> 4) * 8);
+            mma16816<T>(o0, pa[ks], vb[0], vb[1]);
+            mma16816<T>(o1, pa[ks], vb[2], vb[3]);
+        }
+        const int col = ntp * 16 + 2 * t4;
+        if (R0 < n) {
+            *reinterpret_cast<float2*>(out0 + col) = make_float2(o0[0], o0[1]);
+            *reinterpret_cast<float2*>(out0 + col + 8) = make_float2(o1[0], o1[1]);
+        }
+        if (R1 < n) {
+            *reinterpret_cast<float2*>(out1 + col) = make_float2(o0[2], o0[3]);
+            *reinterpret_cast<float2*>(out1 + col + 8) = make_float2(o1[2], o1[3]);
+        }
     }
 }
 
@@ -225,9 +360,26 @@ __global__ void final_rows_kernel(const tscd_final_rows_args a) {
 extern "C" int tscd_frame_attention(const tscd_frame_attention_args* a, void* stream) {
     using namespace tscd;
     if (!a || a->num_frames <= 0 || a->heads <= 0 || a->head_dim <= 0 || a->head_dim % 32 || a->head_dim > 128) return TSCD_ERR_INVALID_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (a->in_dtype == TSCD_F16 || a->in_dtype == TSCD_BF16) {
+        // tensor-core variant: 16-bit q/k/v, frames of <= 32 rows (caller guarantees kmax <= 32), head_dim 128
+        if (a->head_dim != 128 || (a->heads % kFa16Heads) != 0 || (a->ldq % 8) || (a->ldk % 8) || (a->ldv % 8)) return TSCD_ERR_UNSUPPORTED;
+        const size_t sm = (size_t)3 * kFa16Heads * 32 * kFa16Pitch * 2 + 2 * kFa16Heads * 32 * sizeof(float);
+        const dim3 grid(a->num_frames, a->heads / kFa16Heads);
+        if (a->in_dtype == TSCD_F16) {
+            if (cudaFuncSetAttribute(frame_attention16_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return TSCD_ERR_CUDA;
+            frame_attention16_kernel<__half><<<grid, 256, sm, st>>>(*a);
+        } else {
+            if (cudaFuncSetAttribute(frame_attention16_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return TSCD_ERR_CUDA;
+            frame_attention16_kernel<__nv_bfloat16><<<grid, 256, sm, st>>>(*a);
+        }
+        TSCD_CUDA_CHECK_LAUNCH();
+        return TSCD_OK;
+    }
+    if (a->in_dtype != TSCD_F32) return TSCD_ERR_UNSUPPORTED;
     const size_t smem = (size_t)(kFaChunk * (a->head_dim + 4) + kFaChunk * a->head_dim + 8 * a->head_dim) * sizeof(float);
     if (cudaFuncSetAttribute(frame_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
-    frame_attention_kernel<<<dim3(a->num_frames, a->heads), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+    frame_attention_kernel<<<dim3(a->num_frames, a->heads), 256, smem, st>>>(*a);
     TSCD_CUDA_CHECK_LAUNCH();
     return TSCD_OK;
 }

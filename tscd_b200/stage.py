@@ -299,12 +299,14 @@ class AggregationStage:
         # ---- fc_reg_matcher, TaskAligned, prediction heads ---------------------------------------------
         matched16, matched32 = ops.linear(cafm16, w.fc_w, w.fc_b, m_dev=n_loc_dev, want16=True, want32=trace is not None)
         _, reg_deltas = ops.linear(matched16, w.reg_w, w.reg_b, m_dev=n_loc_dev, want16=False, want32=True)
-        _, ta_q = ops.linear(iou_reg16, w.ta_wq, m_dev=n_loc_dev, want16=False, want32=True)
-        _, ta_kv = ops.linear(matched16, w.ta_wkv, m_dev=n_loc_dev, want16=False, want32=True)
+        fast_ta = kmax <= 32          # 16-bit q/k/v + mma.sync attention (csrc/tail.cu frame_attention16_kernel)
+        ta_q16, ta_q = ops.linear(iou_reg16, w.ta_wq, m_dev=n_loc_dev, want16=fast_ta, want32=not fast_ta)
+        ta_kv16, ta_kv = ops.linear(matched16, w.ta_wkv, m_dev=n_loc_dev, want16=fast_ta, want32=not fast_ta)
+        tq, tkv = (ta_q16, ta_kv16) if fast_ta else (ta_q, ta_kv)
         att = f32z(loc_cap, 4 * D)
         ops.call("tscd_frame_attention", L.FrameAttentionArgs, num_frames=B * Lf, heads=8, head_dim=(4 * D) // 8,
-                 lrow_off=lay.lrow_off, q=ta_q, ldq=ta_q.stride(0), k=ta_kv, ldk=ta_kv.stride(0),
-                 v=ta_kv[:, 4 * D:], ldv=ta_kv.stride(0), out=att, ldo=att.stride(0))
+                 in_dtype=dt if fast_ta else torch.float32, lrow_off=lay.lrow_off, q=tq, ldq=tq.stride(0), k=tkv, ldk=tkv.stride(0),
+                 v=tkv[:, 4 * D:], ldv=tkv.stride(0), out=att, ldo=att.stride(0))
         objref16 = torch.empty(loc_cap, 4 * D, dtype=dt, device=dev)
         objref32 = f32z(loc_cap, 4 * D) if trace is not None else None
         ops.call("tscd_residual_ln2", L.ResidualLn2Args, rows_cap=loc_cap, dim=4 * D, n_rows=n_loc_dev, x=iou_reg32, r=att,
