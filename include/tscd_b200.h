@@ -86,6 +86,11 @@ typedef struct {
     float* cand_score;
     int32_t* cand_cls;
     int32_t* cand_count;
+    /* optional workspace (mode A): with both set and anchor-contiguous class planes, the class max / arg-max of every
+     * anchor is computed by a separate streaming kernel and read back for the survivors only */
+    void* ws_conf;           /* [num_frames, ws_pitch] head_dtype */
+    unsigned char* ws_cls;   /* [num_frames, ws_pitch] */
+    int32_t ws_pitch;        /* >= A, multiple of 16 */
 } tscd_select_args;
 int tscd_select(const tscd_select_args* args, void* stream);
 

@@ -29,7 +29,8 @@ class SelectArgs(C.Structure):
                 ("conf_thresh", C.c_float), ("minimal_limit", C.c_int32), ("maximal_limit", C.c_int32),
                 ("cand_cap", C.c_int32), ("anchors", Anchors), ("reg", View), ("obj", View), ("cls", View),
                 ("cand_idx", C.c_void_p), ("cand_box", C.c_void_p), ("cand_score", C.c_void_p),
-                ("cand_cls", C.c_void_p), ("cand_count", C.c_void_p)]
+                ("cand_cls", C.c_void_p), ("cand_count", C.c_void_p),
+                ("ws_conf", C.c_void_p), ("ws_cls", C.c_void_p), ("ws_pitch", C.c_int32)]
 
 
 class NmsArgs(C.Structure):

@@ -22,11 +22,13 @@ struct SelSmem {
 
 // k-th largest key among keys[0..n) (k >= 1, k <= n).  Returns the threshold key T and the number of
 // elements equal to T that belong to the top-k (r_eq); elements > T number k - r_eq.
-__device__ void radix_select_kth(const uint32_t* keys, int n, int k, SelSmem* s, uint32_t* T_out, int* req_out) {
+template <typename KT>
+__device__ void radix_select_kth(const KT* keys, int n, int k, SelSmem* s, uint32_t* T_out, int* req_out) {
     uint32_t prefix = 0, mask = 0;
     int remaining = k;
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
+    constexpr int kPasses = (int)sizeof(KT);       // 8-bit digits, most significant first
+    for (int pass = 0; pass < kPasses; ++pass) {
+        const int shift = 8 * (kPasses - 1 - pass);
         for (int i = threadIdx.x; i < 256; i += blockDim.x) s->hist[i] = 0;
         __syncthreads();
         // histogram of the digit among the keys that still match the prefix.  Sigmoid scores share a few exponent
@@ -35,7 +37,7 @@ __device__ void radix_select_kth(const uint32_t* keys, int n, int k, SelSmem* s,
         // the others (few, spread over many bins in the later passes) add themselves.
         for (int i0 = 0; i0 < n; i0 += blockDim.x) {
             const int i = i0 + threadIdx.x;
-            const uint32_t u = i < n ? keys[i] : 0u;
+            const uint32_t u = i < n ? (uint32_t)keys[i] : 0u;
             const bool in = i < n && (u & mask) == prefix;
             const unsigned act = __ballot_sync(0xffffffffu, in);
             if (act == 0u) continue;
@@ -77,8 +79,85 @@ __device__ void radix_select_kth(const uint32_t* keys, int n, int k, SelSmem* s,
     *req_out = remaining;
 }
 
+// Class max / arg-max of every anchor as its own streaming kernel (mode A, planar head layouts): thread = 8 anchors x all
+// class planes, 8 independent 16-byte loads in flight per batch, thousands of small CTAs -> the class planes (83 % of the
+// stage's mandatory HBM bytes) are read at streaming bandwidth instead of inside the per-frame selection CTA, whose
+// on-chip phases (radix select, scans, sort) would otherwise stall the loads.  Results go to a [F, ws_pitch] workspace
+// that select_kernel<T, true> reads back for the ~pre_k survivors only (L2 hits).
+// largest power-of-two vector width (in elements, <= 16 bytes) that the class planes of level l allow
 template <typename T>
-__global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const tscd_select_args args, int sort_cap) {
+__host__ __device__ inline int classmax_vw(const tscd_select_args& a, int l) {
+    const int nl = a.anchors.level_start[l + 1] - a.anchors.level_start[l];
+    int vw = 16 / (int)sizeof(T);
+    while (vw > 1 && ((a.cls.chan_stride[l] % vw) || (a.cls.frame_stride[l] % vw) || (nl % vw) ||
+                      (reinterpret_cast<uintptr_t>(a.cls.ptr[l]) % (vw * sizeof(T)))))
+        vw >>= 1;
+    return vw;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) classmax_kernel(const tscd_select_args args) {
+    constexpr int VMAX = 16 / sizeof(T);
+    const int frame = blockIdx.y;
+    const tscd_anchors& an = args.anchors;
+    const int C = args.num_classes;
+    static_assert(TSCD_MAX_LEVELS == 3, "level lookup below is written for three FPN levels");
+    const int vw0 = classmax_vw<T>(args, 0);
+    const int vw1 = an.num_levels > 1 ? classmax_vw<T>(args, 1) : 1;
+    const int vw2 = an.num_levels > 2 ? classmax_vw<T>(args, 2) : 1;
+    const int g1 = (an.level_start[1] - an.level_start[0]) / vw0;
+    const int g2 = g1 + (an.num_levels > 1 ? (an.level_start[2] - an.level_start[1]) / vw1 : 0);
+    const int g3 = g2 + (an.num_levels > 2 ? (an.level_start[3] - an.level_start[2]) / vw2 : 0);
+    T* wconf = reinterpret_cast<T*>(args.ws_conf) + (int64_t)frame * args.ws_pitch;
+    unsigned char* wcls = args.ws_cls + (int64_t)frame * args.ws_pitch;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= g3) return;
+    const int l = (g >= g1 ? 1 : 0) + (g >= g2 ? 1 : 0);
+    const int vw = l == 0 ? vw0 : (l == 1 ? vw1 : vw2);
+    const int a_lo = l == 0 ? an.level_start[0] : (l == 1 ? an.level_start[1] : an.level_start[2]);
+    const int a0 = (g - (l == 0 ? 0 : (l == 1 ? g1 : g2))) * vw;
+    const T* cp = reinterpret_cast<const T*>(args.cls.ptr[l]) + (int64_t)frame * args.cls.frame_stride[l] + a0;
+    const int64_t ccs = args.cls.chan_stride[l];
+    float best[VMAX];
+    int bi[VMAX];
+#pragma unroll
+    for (int v = 0; v < VMAX; ++v) { best[v] = -INFINITY; bi[v] = 0; }
+    for (int c0 = 0; c0 < C; c0 += 8) {
+        uint4 raw[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (c0 + u < C) {
+                const T* src = cp + (int64_t)(c0 + u) * ccs;
+                const int bytes = vw * (int)sizeof(T);
+                if (bytes == 16) raw[u] = __ldg(reinterpret_cast<const uint4*>(src));
+                else if (bytes == 8) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(src)); raw[u] = make_uint4(t.x, t.y, 0, 0); }
+                else if (bytes == 4) raw[u] = make_uint4(__ldg(reinterpret_cast<const uint32_t*>(src)), 0, 0, 0);
+                else raw[u] = make_uint4((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(src)), 0, 0, 0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (c0 + u < C) {
+                const T* e = reinterpret_cast<const T*>(&raw[u]);
+#pragma unroll
+                for (int v = 0; v < VMAX; ++v) {
+                    const float x = ldf_reg(e[v]);
+                    if (v < vw && x > best[v]) { best[v] = x; bi[v] = c0 + u; }     // first maximum wins (torch.max)
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < VMAX; ++v) {
+        if (v < vw) {
+            wconf[a_lo + a0 + v] = cvt_from_float<T>(best[v]);      // exact: the maximum is one of the T-typed inputs
+            wcls[a_lo + a0 + v] = (unsigned char)bi[v];
+        }
+    }
+}
+
+template <typename T, bool PRE>
+__global__ void __launch_bounds__(kSelThreads, PRE ? 3 : 2) select_kernel(const tscd_select_args args, int sort_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int frame = blockIdx.x;
     const tscd_anchors& an = args.anchors;
@@ -88,11 +167,15 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const tscd_selec
 
     const int A4 = (A + 3) & ~3;
     uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw);                     // [A] order-preserving selection key
-    float* conf_s = reinterpret_cast<float*>(keys + A4);                        // [A] class max (mode A: pre-sigmoid)
+    float* conf_s = reinterpret_cast<float*>(keys + A4);                        // [A] class max (mode A: pre-sigmoid); absent if PRE
     const int S4 = (min(A, args.cand_cap) + 3) & ~3;
-    int* sel = reinterpret_cast<int*>(conf_s + A4);                             // [min(A, cand_cap)] selected anchor ids
+    int* sel = reinterpret_cast<int*>(conf_s + (PRE ? 0 : A4));                 // [min(A, cand_cap)] selected anchor ids
     unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(sel + S4 + (S4 & 1 ? 1 : 0));  // [pow2(pre_k)], 8-byte aligned
-    unsigned char* cls_s = reinterpret_cast<unsigned char*>(sortbuf + sort_cap); // [A] class arg-max
+    unsigned char* cls_s = reinterpret_cast<unsigned char*>(sortbuf + sort_cap); // [A] class arg-max (absent if PRE)
+    // PRE + fp16 logits (mode A): 16-bit order-preserving keys of the raw objectness logits.  sigmoid is monotone, so the
+    // k-th largest logit locates the k-th largest score with a 2-pass radix select instead of 4 passes over fp32 keys.
+    constexpr bool K16 = PRE && sizeof(T) == 2;
+    unsigned short* k16 = reinterpret_cast<unsigned short*>(sortbuf + sort_cap);   // [A] (aliases cls_s, which PRE does not use)
     __shared__ SelSmem s;
 
     // ---- pass 1: stream objectness + class planes once; key / class max / arg-max per anchor ----------
@@ -133,7 +216,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const tscd_selec
 #pragma unroll
         for (int v = 0; v < VMAX; ++v) { best[v] = -INFINITY; bi[v] = 0; }
         // class planes in batches of 8 independent 16-byte loads (128 B in flight per thread)
-        for (int c0 = 0; c0 < C; c0 += 8) {
+        for (int c0 = 0; c0 < (PRE ? 0 : C); c0 += 8) {
             uint4 raw[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u)
@@ -167,8 +250,11 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const tscd_selec
                 n_ge += (key >= args.conf_thresh) ? 1 : 0;
             }
             keys[a] = f2ord(key);
-            conf_s[a] = b;
-            cls_s[a] = (unsigned char)bi[v];
+            if (!PRE) { conf_s[a] = b; cls_s[a] = (unsigned char)bi[v]; }
+            if (K16) {
+                const unsigned short hb = reinterpret_cast<const unsigned short*>(&oraw)[v];
+                k16[a] = (hb & 0x8000u) ? (unsigned short)~hb : (unsigned short)(hb | 0x8000u);
+            }
         }
     }
     for (int l = 0; l < an.num_levels; ++l) {
@@ -179,11 +265,16 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const tscd_selec
         const int nvec = nvec_l[l];
         for (int i = nvec * VMAX + threadIdx.x; i < nl; i += blockDim.x) {      // tail / non-planar layouts
             const int a = a_lo + i;
-            float o = ldf(op + (int64_t)i * args.obj.anchor_stride[l]);
+            const T oraw1 = __ldg(op + (int64_t)i * args.obj.anchor_stride[l]);
+            float o = ldf_reg(oraw1);
+            if (K16) {
+                const unsigned short hb = *reinterpret_cast<const unsigned short*>(&oraw1);
+                k16[a] = (hb & 0x8000u) ? (unsigned short)~hb : (unsigned short)(hb | 0x8000u);
+            }
             const T* c = cp + (int64_t)i * args.cls.anchor_stride[l];
             float b = ldf(c);
             int bidx = 0;
-            for (int k = 1; k < C; ++k) {
+            for (int k = 1; k < (PRE ? 0 : C); ++k) {
                 const float x = ldf(c + k * ccs);
                 if (x > b) { b = x; bidx = k; }
             }
@@ -195,8 +286,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const tscd_selec
                 n_ge += (key >= args.conf_thresh) ? 1 : 0;
             }
             keys[a] = f2ord(key);
-            conf_s[a] = b;
-            cls_s[a] = (unsigned char)bidx;
+            if (!PRE) { conf_s[a] = b; cls_s[a] = (unsigned char)bidx; }
         }
     }
     __syncthreads();
@@ -220,7 +310,23 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const tscd_selec
 
     uint32_t Tk = f2ord(args.conf_thresh);
     int r_eq = 0x7fffffff;  // threshold mode: every key == Tk is taken
-    if (take_k > 0) radix_select_kth(keys, A, take_k, &s, &Tk, &r_eq);
+    bool req_from_count = false;
+    if (take_k > 0) {
+        if (K16 && args.mode == 0) {
+            uint32_t x_k;
+            int dummy;
+            radix_select_kth<unsigned short>(k16, A, take_k, &s, &x_k, &dummy);
+            // score key of the k-th logit (every anchor with this logit has the same score); equal SCORES of different
+            // logits (sigmoid saturation) are resolved by the fp32 keys below: r_eq = k - #(score > T)
+            for (int a = threadIdx.x; a < A; a += blockDim.x)
+                if ((uint32_t)k16[a] == x_k) s.misc[2] = (int)keys[a];
+            __syncthreads();
+            Tk = (uint32_t)s.misc[2];
+            req_from_count = true;
+        } else {
+            radix_select_kth<uint32_t>(keys, A, take_k, &s, &Tk, &r_eq);
+        }
+    }
 
     // ---- stable compaction in ascending anchor order ---------------------------------------------------
     const int chunk = (A + blockDim.x - 1) / blockDim.x;
@@ -232,6 +338,11 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const tscd_selec
         n_eq += (u == Tk);
     }
     int tot_eq, tot_gt;
+    if (req_from_count) {
+        int tot_strict;
+        block_excl_scan(n_gt, s.scan, &tot_strict);
+        r_eq = take_k - tot_strict;
+    }
     int eq_before = block_excl_scan(n_eq, s.scan, &tot_eq);
     int take_eq = max(0, min(n_eq, r_eq - eq_before));  // lowest anchor ids among the ties
     int out_before = block_excl_scan(n_gt + take_eq, s.scan, &tot_gt);
@@ -270,7 +381,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const tscd_selec
         if (modeB) {
             score = ord2f(keys[a]);
         } else {
-            float conf = conf_s[a];
+            float conf = PRE ? ldf(reinterpret_cast<const T*>(args.ws_conf) + (int64_t)frame * args.ws_pitch + a) : conf_s[a];
             if (sig) conf = sigmoidf_ref(conf);
             score = __fmul_rn(ord2f(keys[a]), conf);                  // post_process.py:512  obj * class_conf
         }
@@ -278,7 +389,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const tscd_selec
         args.cand_idx[base + i] = a;
         reinterpret_cast<float4*>(args.cand_box)[base + i] = box;
         args.cand_score[base + i] = score;
-        args.cand_cls[base + i] = (int)cls_s[a];
+        args.cand_cls[base + i] = PRE ? (int)args.ws_cls[(int64_t)frame * args.ws_pitch + a] : (int)cls_s[a];
     }
     if (threadIdx.x == 0) args.cand_count[frame] = n_sel;
 }
@@ -300,21 +411,41 @@ extern "C" int tscd_select(const tscd_select_args* a, void* stream) {
     if (n64 > 16 * kSelThreads) return TSCD_ERR_CAPACITY;
     if (a->num_classes > 255) return TSCD_ERR_UNSUPPORTED;
     const int selcap = ((A < a->cand_cap ? A : a->cand_cap) + 3) & ~3;
-    size_t smem = (size_t)((A + 3) & ~3) * 8 + (size_t)selcap * 4 + 8 + (size_t)n64 * 8 + (size_t)((A + 15) & ~15);
-    if (smem > 200 * 1024) return TSCD_ERR_CAPACITY;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // mode A with a workspace and planar (anchor-contiguous) class planes: class max as a separate streaming kernel
+    bool pre = a->mode == 0 && a->ws_conf && a->ws_cls && a->ws_pitch >= A && (a->head_dtype == TSCD_F16 || a->head_dtype == TSCD_F32);
+    const int vmax = a->head_dtype == TSCD_F16 ? 8 : 4, esz = a->head_dtype == TSCD_F16 ? 2 : 4;
+    int groups = 0;
+    for (int l = 0; pre && l < a->anchors.num_levels; ++l) {
+        const int nl = a->anchors.level_start[l + 1] - a->anchors.level_start[l];
+        pre = a->cls.anchor_stride[l] == 1;                      // anchor-contiguous planes (NCHW conv outputs)
+        groups += nl / (a->head_dtype == TSCD_F16 ? classmax_vw<__half>(*a, l) : classmax_vw<float>(*a, l));
+    }
+    (void)vmax;
+    (void)esz;
+    const size_t smem = (size_t)((A + 3) & ~3) * (pre ? 4 : 8) + (size_t)selcap * 4 + 8 + (size_t)n64 * 8 + (pre ? (size_t)2 * ((A + 15) & ~15) : (size_t)((A + 15) & ~15));
+    if (smem > 200 * 1024) return TSCD_ERR_CAPACITY;
     cudaError_t e;
+    if (pre) {
+        const dim3 grid((groups + 255) / 256 > 0 ? (groups + 255) / 256 : 1, a->num_frames);
+        if (a->head_dtype == TSCD_F32) classmax_kernel<float><<<grid, 256, 0, st>>>(*a);
+        else classmax_kernel<__half><<<grid, 256, 0, st>>>(*a);
+        TSCD_CUDA_CHECK_LAUNCH();
+    }
+#define TSCD_LAUNCH_SELECT(TT, PP)                                                                                   \
+    do {                                                                                                             \
+        e = cudaFuncSetAttribute(select_kernel<TT, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        if (e != cudaSuccess) return TSCD_ERR_CUDA;                                                                  \
+        select_kernel<TT, PP><<<a->num_frames, kSelThreads, smem, st>>>(*a, n64);                                    \
+    } while (0)
     if (a->head_dtype == TSCD_F32) {
-        e = cudaFuncSetAttribute(select_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return TSCD_ERR_CUDA;
-        select_kernel<float><<<a->num_frames, kSelThreads, smem, st>>>(*a, n64);
+        if (pre) TSCD_LAUNCH_SELECT(float, true); else TSCD_LAUNCH_SELECT(float, false);
     } else if (a->head_dtype == TSCD_F16) {
-        e = cudaFuncSetAttribute(select_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return TSCD_ERR_CUDA;
-        select_kernel<__half><<<a->num_frames, kSelThreads, smem, st>>>(*a, n64);
+        if (pre) TSCD_LAUNCH_SELECT(__half, true); else TSCD_LAUNCH_SELECT(__half, false);
     } else {
         return TSCD_ERR_UNSUPPORTED;
     }
+#undef TSCD_LAUNCH_SELECT
     TSCD_CUDA_CHECK_LAUNCH();
     return TSCD_OK;
 }

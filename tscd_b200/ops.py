@@ -118,6 +118,13 @@ def select(head: HeadViews, mode: str, pre_k: int = 750, conf_thresh: float = 0.
     a.anchors, a.reg, a.obj, a.cls = head.anchors.to_c(), head.reg, head.obj, head.cls
     a.cand_idx, a.cand_box, a.cand_score = _p(out["idx"]), _p(out["box"]), _p(out["score"])
     a.cand_cls, a.cand_count = _p(out["cls"]), _p(out["count"])
+    if mode == "A":          # workspace of the streaming class-max kernel (K1 runs as two kernels for planar layouts)
+        pitch = (A + 15) // 16 * 16
+        ws_conf = torch.empty(Fn, pitch, dtype=head.dtype, device=dev)
+        ws_cls = torch.empty(Fn, pitch, dtype=torch.uint8, device=dev)
+        a.ws_conf, a.ws_cls, a.ws_pitch = _p(ws_conf), _p(ws_cls), pitch
+        out["_ws"] = (ws_conf, ws_cls)
+        L.launch_count += 1
     with L.timed("tscd_select"):
         L.check(L.lib().tscd_select(C.byref(a), _stream()), "tscd_select")
     return out

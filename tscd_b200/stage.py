@@ -92,12 +92,42 @@ class AggregationStage:
         self.cfg = cfg
         self.w = StageWeights(state_dict, cfg, device)
         self.device = device
-        self._side = None
+        self._side = {}
+        self._part_streams = []
 
     def _side_stream(self):
-        if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
-        return self._side
+        """Side stream of the classification branch, one per launching stream (concurrent sub-batches must not share it)."""
+        key = torch.cuda.current_stream().cuda_stream
+        if key not in self._side:
+            self._side[key] = torch.cuda.Stream(device=self.device)
+        return self._side[key]
+
+    # ------------------------------------------------------------------------------------------------------
+    def forward_concurrent(self, parts, feat_dtype, F: int, Lf: int):
+        """Run independent sub-batches of clips concurrently, each on its own stream (plus its own side stream).
+
+        Clips are independent units of work, and most kernels of the stage are latency-bound with modest grids (one
+        CTA per clip / frame), so two or more sub-batches in flight fill the SMs that a single launch sequence leaves
+        idle: the front end (select / NMS / gather) of one sub-batch overlaps the attention / CAFM tail of another.
+        parts: list of (head_views, feats, time_embedding, n_clips).  Returns the list of forward() outputs; all streams
+        are joined into the current stream before returning (CUDA-graph capturable)."""
+        main = torch.cuda.current_stream()
+        while len(self._part_streams) < len(parts):
+            self._part_streams.append(torch.cuda.Stream(device=self.device))
+        fork = torch.cuda.Event()
+        fork.record(main)
+        outs, joins = [], []
+        for i, (head, feats, te, nb) in enumerate(parts):
+            st = self._part_streams[i]
+            with torch.cuda.stream(st):
+                st.wait_event(fork)
+                outs.append(self.forward(head, feats, feat_dtype, te, nb, F, Lf))
+                ev = torch.cuda.Event()
+                ev.record(st)
+                joins.append(ev)
+        for ev in joins:
+            main.wait_event(ev)
+        return outs
 
     # ------------------------------------------------------------------------------------------------------
     def forward(self, head: ops.HeadViews, feats, feat_dtype, time_embedding: torch.Tensor, B: int, F: int, Lf: int,
@@ -239,6 +269,22 @@ class AggregationStage:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             out = self.forward(head, feats, feat_dtype, te, B, F, Lf, state=state, resume=resume)
+        return graph, out
+
+    # ------------------------------------------------------------------------------------------------------
+    def capture_fn(self, fn, warmup: int = 2):
+        """Capture an arbitrary launch sequence of this stage (e.g. forward_concurrent over fixed input buffers) into a
+        CUDA graph.  Returns (graph, value returned by fn during capture)."""
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                fn()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = fn()
         return graph, out
 
     # ------------------------------------------------------------------------------------------------------
