@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
                                                                 const __grid_constant__ CUtensorMap tmap_w,
                                                                 const GemmParams p) {
     using namespace tc;
+    constexpr int STAGES = BN == 256 ? 4 : 3;      // 128x256 tiles: 48 KB per stage, one CTA per SM, all 512 TMEM columns
     int M = p.M;
     if (p.m_dev) M = min(M, __ldg(p.m_dev));
     const int tiles_n = (p.N + BN - 1) / BN;
@@ -59,11 +60,11 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
     constexpr int kABytes = kGemmBM * kGemmBK * 2;
     constexpr int kWBytes = BN * kGemmBK * 2;
     unsigned char* sA = smem;
-    unsigned char* sW = smem + kGemmStages * kABytes;
-    unsigned char* sStage = sW + kGemmStages * kWBytes;      // 8 epilogue warps x (32 rows x 64 B)
+    unsigned char* sW = smem + STAGES * kABytes;
+    unsigned char* sStage = sW + STAGES * kWBytes;      // 8 epilogue warps x (32 rows x 64 B)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + 8 * 2048);
-    uint64_t* empty_bar = full_bar + kGemmStages;
-    uint64_t* tmem_full_bar = empty_bar + kGemmStages;
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
     uint64_t* tmem_empty_bar = tmem_full_bar + kAccStages;
     uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(tmem_empty_bar + kAccStages);
     if ((smem_u32(smem) & 1023u) != 0) __trap();             // alignment contract violated
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_w);
-        for (int s = 0; s < kGemmStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 8); }
         fence_barrier_init();
     }
@@ -91,8 +92,8 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 const int m0 = (t / tiles_n) * kGemmBM, n0 = (t % tiles_n) * BN;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % kGemmStages;
-                    const uint32_t ph = (it / kGemmStages) & 1;
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1, 100 + s);
                     mbar_expect_tx(&full_bar[s], kABytes + kWBytes);
                     tma_load_2d(sA + s * kABytes, &tmap_a, &full_bar[s], kb * kGemmBK, m0);
@@ -111,8 +112,8 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % kGemmStages;
-                    const uint32_t ph = (it / kGemmStages) & 1;
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&full_bar[s], ph, 110 + s);
                     tc_fence_after();
                     const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + s * kABytes));
@@ -279,7 +280,8 @@ int make_tmap_kmajor(CUtensorMap* m, const void* ptr, int is_bf16, int64_t rows,
 
 template <int BN, bool BF16>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
-    constexpr size_t smem = (size_t)kGemmStages * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + 8 * 2048 + 128;
+    constexpr int STAGES = BN == 256 ? 4 : 3;
+    constexpr size_t smem = (size_t)STAGES * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + 8 * 2048 + 128;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(gemm_tn_kernel<BN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -293,7 +295,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmP
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const int tiles = ((p.N + BN - 1) / BN) * ((p.M + kGemmBM - 1) / kGemmBM);
-    const int grid = tiles < 2 * num_sms ? tiles : 2 * num_sms;      // two resident CTAs per SM (97 KB smem, 2 x 2*BN TMEM columns)
+    const int ctas_per_sm = BN == 256 ? 1 : 2;                       // 113 KB smem and 2*BN TMEM columns per CTA (BN <= 128)
+    const int grid = tiles < ctas_per_sm * num_sms ? tiles : ctas_per_sm * num_sms;
     gemm_tn_kernel<BN, BF16><<<grid, kGemmThreads, smem, st>>>(ta, tw, p);
     return cudaGetLastError() == cudaSuccess ? TSCD_OK : TSCD_ERR_CUDA;
 }
@@ -306,7 +309,10 @@ extern "C" int tscd_linear(const tscd_linear_args* a, void* stream) {
     if (a->dtype != TSCD_F16 && a->dtype != TSCD_BF16) return TSCD_ERR_UNSUPPORTED;
     if (!a->out16 && !a->out32) return TSCD_ERR_INVALID_ARG;
     const int is_bf16 = a->dtype == TSCD_BF16;
-    const int BN = a->N <= 64 ? 64 : 128;
+    // 128x128 tiles need 128 B/clk of operand reads from shared memory (its full bandwidth), 128x256 tiles 96 B/clk:
+    // the wide tile is used where the main loop dominates (K >= 512); short-K GEMMs are epilogue-bound and keep two
+    // smaller CTAs (16 epilogue warps) per SM
+    const int BN = a->N <= 64 ? 64 : ((a->N % 256) == 0 && a->K >= 512 ? 256 : 128);
     CUtensorMap ta, tw;
     int rc = make_tmap_kmajor(&ta, a->x, is_bf16, a->M, a->K, a->ldx, kGemmBM);
     if (rc != TSCD_OK) return rc;
@@ -319,6 +325,6 @@ extern "C" int tscd_linear(const tscd_linear_args* a, void* stream) {
     p.ld16 = a->ld16; p.ld32 = a->ld32;
     p.is_bf16 = is_bf16;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (is_bf16) return BN == 64 ? launch_gemm<64, true>(ta, tw, p, st) : launch_gemm<128, true>(ta, tw, p, st);
-    return BN == 64 ? launch_gemm<64, false>(ta, tw, p, st) : launch_gemm<128, false>(ta, tw, p, st);
+    if (is_bf16) return BN == 64 ? launch_gemm<64, true>(ta, tw, p, st) : (BN == 128 ? launch_gemm<128, true>(ta, tw, p, st) : launch_gemm<256, true>(ta, tw, p, st));
+    return BN == 64 ? launch_gemm<64, false>(ta, tw, p, st) : (BN == 128 ? launch_gemm<128, false>(ta, tw, p, st) : launch_gemm<256, false>(ta, tw, p, st));
 }
