@@ -312,7 +312,7 @@ extern "C" int tscd_linear(const tscd_linear_args* a, void* stream) {
     // 128x128 tiles need 128 B/clk of operand reads from shared memory (its full bandwidth), 128x256 tiles 96 B/clk:
     // the wide tile is used where the main loop dominates (K >= 512); short-K GEMMs are epilogue-bound and keep two
     // smaller CTAs (16 epilogue warps) per SM
-    const int BN = a->N <= 64 ? 64 : ((a->N % 256) == 0 && a->K >= 512 ? 256 : 128);
+    const int BN = a->N <= 64 ? 64 : ((a->N % 256) == 0 && a->K >= 256 ? 256 : 128);
     CUtensorMap ta, tw;
     int rc = make_tmap_kmajor(&ta, a->x, is_bf16, a->M, a->K, a->ldx, kGemmBM);
     if (rc != TSCD_OK) return rc;
