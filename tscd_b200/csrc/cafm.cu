@@ -164,31 +164,44 @@ __global__ void __launch_bounds__(256) cafm_cost_kernel(const tscd_cafm_cost_arg
     const float* Cc = a.emb_cls + (int64_t)l0 * E;
     const int lane = threadIdx.x & 31, pr = threadIdx.x >> 5;   // pairs (pr + 8k, lane), k = 0..3
     float accR[4] = {0.f, 0.f, 0.f, 0.f}, accC[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int which = 0; which < 2; ++which) {
+    // slabs of 128 dims; each thread moves four float4 per matrix and slab (row = t / 32 + 8 k, 16-byte column t % 32);
+    // the next slab is fetched into registers while the current one is multiplied (one barrier pair per slab)
+    const int lr = threadIdx.x >> 5, lc4 = threadIdx.x & 31;
+    float4 pa[4], pb[4];
+    auto fetch = [&](int s) {
+        const int which = s >> 3, d0 = (s & 7) * 128;
         const float* P = which == 0 ? Rp : Cp;
         const float* Q = which == 0 ? Rc : Cc;
-        for (int d0 = 0; d0 < E; d0 += 128) {
-            __syncthreads();
-            for (int t = threadIdx.x; t < 32 * 128; t += 256) {
-                const int rr = t >> 7, dd = t & 127;
-                tileA[rr][dd] = (rb + rr < np) ? P[(int64_t)(rb + rr) * E + d0 + dd] : 0.f;
-                tileB[rr][dd] = (cb + rr < n) ? Q[(int64_t)(cb + rr) * E + d0 + dd] : 0.f;
-            }
-            __syncthreads();
-            float x[4] = {0.f, 0.f, 0.f, 0.f};
-            const float4* qrow = reinterpret_cast<const float4*>(tileB[lane]);
-#pragma unroll 4
-            for (int d4 = 0; d4 < 32; ++d4) {
-                const float4 q = qrow[d4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float4 p4 = reinterpret_cast<const float4*>(tileA[pr + 8 * k])[d4];   // broadcast
-                    x[k] = fmaf(p4.x, q.x, fmaf(p4.y, q.y, fmaf(p4.z, q.z, fmaf(p4.w, q.w, x[k]))));
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { if (which == 0) accR[k] += x[k]; else accC[k] += x[k]; }
+        for (int k = 0; k < 4; ++k) {
+            const int rr = lr + 8 * k;
+            pa[k] = (rb + rr < np) ? __ldg(reinterpret_cast<const float4*>(P + (int64_t)(rb + rr) * E + d0) + lc4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            pb[k] = (cb + rr < n) ? __ldg(reinterpret_cast<const float4*>(Q + (int64_t)(cb + rr) * E + d0) + lc4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+    };
+    fetch(0);
+    for (int s = 0; s < 16; ++s) {
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            *reinterpret_cast<float4*>(&tileA[lr + 8 * k][lc4 * 4]) = pa[k];
+            *reinterpret_cast<float4*>(&tileB[lr + 8 * k][lc4 * 4]) = pb[k];
+        }
+        __syncthreads();
+        if (s + 1 < 16) fetch(s + 1);
+        float x[4] = {0.f, 0.f, 0.f, 0.f};
+        const float4* qrow = reinterpret_cast<const float4*>(tileB[lane]);
+#pragma unroll 4
+        for (int d4 = 0; d4 < 32; ++d4) {
+            const float4 q = qrow[d4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float4 p4 = reinterpret_cast<const float4*>(tileA[pr + 8 * k])[d4];   // broadcast
+                x[k] = fmaf(p4.x, q.x, fmaf(p4.y, q.y, fmaf(p4.z, q.z, fmaf(p4.w, q.w, x[k]))));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { if (s < 8) accR[k] += x[k]; else accC[k] += x[k]; }
     }
     float* out = a.cost + (int64_t)lf * KM * KM;
 #pragma unroll

@@ -143,8 +143,9 @@ extern "C" int tscd_gather(const tscd_gather_args* a, void* stream) {
     count_scan_kernel<<<1, 1024, 0, st>>>(a->num_frames, a->use_keep, a->max_keep, a->cand_count, a->keep_count,
                                           a->sel_count, a->row_off);
     TSCD_CUDA_CHECK_LAUNCH();
-    int ysplit = a->max_keep > 64 ? (a->max_keep + 63) / 64 : 1;
-    if (ysplit > 8) ysplit = 8;
+    // one warp per kept row where possible (a row costs 3-4 dependent global round trips; rows are independent)
+    int ysplit = (a->max_keep + 7) / 8;
+    if (ysplit > 16) ysplit = 16;
     dim3 grid(a->num_frames, ysplit);
     int rc;
     switch (a->feat_dtype) {

@@ -283,7 +283,11 @@ class AggregationStage:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        # capture on a high-priority stream: the stage's own side streams (classification branch) have default priority,
+        # so whenever both have blocks pending the critical path (agg_iou -> CAFM -> TaskAligned) is scheduled first
+        hp = torch.cuda.Stream(device=self.device, priority=-1)
+        hp.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.graph(graph, stream=hp):
             out = fn()
         return graph, out
 
