@@ -238,6 +238,11 @@ typedef struct {
     float conf_sim_thresh;    /* 0.99 */
     void* out;                /* [loc_cap, ld_out] 256 columns */
     int32_t ld_out;
+    /* weight hand-over between the two launches of one module (both optional, [loc_cap, nk_pitch], lay.dtype):
+     * w_out (use_obj_mask = 0): store  sim_mask * exp(mean attention);  w_in (use_obj_mask = 1): reuse it -- the launch
+     * then only evaluates the reg-branch raw-v similarity (no score recomputation, no exponentials) */
+    void* w_out;
+    const void* w_in;
 } tscd_attn_round2_args;
 int tscd_attn_round2(const tscd_attn_round2_args* args, void* stream);
 

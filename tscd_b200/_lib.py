@@ -83,7 +83,8 @@ class AttnRound2Args(C.Structure):
     _fields_ = [("lay", AttnLayout), ("qn_cls", C.c_void_p), ("kn_cls", C.c_void_p), ("qn_reg", C.c_void_p),
                 ("kn_reg", C.c_void_p), ("vn_cls", C.c_void_p), ("vn_reg", C.c_void_p), ("vt", C.c_void_p),
                 ("row_frame", C.c_void_p), ("stats", C.c_void_p), ("use_obj_mask", C.c_int32),
-                ("sim_thresh", C.c_float), ("conf_sim_thresh", C.c_float), ("out", C.c_void_p), ("ld_out", C.c_int32)]
+                ("sim_thresh", C.c_float), ("conf_sim_thresh", C.c_float), ("out", C.c_void_p), ("ld_out", C.c_int32),
+                ("w_out", C.c_void_p), ("w_in", C.c_void_p)]
 
 
 class TransposeArgs(C.Structure):

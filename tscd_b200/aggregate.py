@@ -59,8 +59,10 @@ def mca_forward(lay: ops.AttnLayoutT, w: MCAWeights, bank_cls, bank_reg, bank_sc
     ops.attn_pv(lay, bufs, tmp_c[:, :256], tmp_r[:, :256], stats, need_reg=need_reg)
     cat_c = torch.empty(lay.loc_cap, 768, dtype=dt, device=dev)      # [round2 @ V | linear(x)]
     ops.linear(tmp_c, w.lin_w, w.lin_b, m_dev=n_loc_dev, out16=cat_c[:, 256:], want16=False)
+    # with a reg output to follow, the cls launch keeps its weights (sim_mask * exp(mean attention)) for the obj launch
+    w_keep = torch.empty(lay.loc_cap, lay.nk_pitch, dtype=dt, device=dev) if need_reg else None
     ops.attn_round2(lay, bufs, bufs["vt_cls"], stats, cat_c[:, :256], use_obj_mask=False, sim_thresh=sim_thresh,
-                    conf_sim_thresh=conf_sim_thresh)
+                    conf_sim_thresh=conf_sim_thresh, w_out=w_keep)
     trans_cls16, trans_cls32 = ops.linear(cat_c, w.out_w, w.out_b, m_dev=n_loc_dev, want16=cls_out[0], want32=cls_out[1])
     trans_obj16 = trans_obj32 = None
     cat_r = None
@@ -68,7 +70,7 @@ def mca_forward(lay: ops.AttnLayoutT, w: MCAWeights, bank_cls, bank_reg, bank_sc
         cat_r = torch.empty(lay.loc_cap, 768, dtype=dt, device=dev)
         ops.linear(tmp_r, w.linreg_w, w.linreg_b, m_dev=n_loc_dev, out16=cat_r[:, 256:], want16=False)
         ops.attn_round2(lay, bufs, bufs["vt_reg"], stats, cat_r[:, :256], use_obj_mask=True, sim_thresh=sim_thresh,
-                        conf_sim_thresh=conf_sim_thresh)
+                        conf_sim_thresh=conf_sim_thresh, w_in=w_keep)
         trans_obj16, trans_obj32 = ops.linear(cat_r, w.obj_w, w.obj_b, m_dev=n_loc_dev, want16=obj_out[0], want32=obj_out[1])
     if debug is not None:
         debug.update(qkv_c=qkv_c, qkv_r=qkv_r, bufs=bufs, tmp_c=tmp_c, tmp_r=tmp_r, stats=stats, cat_c=cat_c, cat_r=cat_r)

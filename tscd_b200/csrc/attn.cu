@@ -640,6 +640,10 @@ __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid
     const uint32_t tmem = bars.tmem_base;
     const int KT = (ci.n_clip + 63) / 64;
     const bool use_obj = a.use_obj_mask != 0;
+    // w_in: the cls-output launch of the same module already stored  sim_mask * exp(mean attention)  (its weights): this
+    // launch only needs the reg-branch raw-v similarity (obj mask) -- no score units, no exponentials
+    const bool reuse = a.w_in != nullptr;
+    const int atom0 = reuse ? 4 : 0;
     const int n_atoms = use_obj ? 8 : 4;
 
     if (warp == 8) {
@@ -653,7 +657,7 @@ __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid
                 return sRing + st * kR2StageBytes;
             };
             auto load_raw = [&](int kt) {
-                for (int x = 0; x < n_atoms; ++x, ++it) {
+                for (int x = atom0; x < n_atoms; ++x, ++it) {
                     const int br = x >> 2, at = x & 3;
                     unsigned char* d = acquire(24576);
                     uint64_t* fb = &bars.full[it % kR2Stages];
@@ -662,6 +666,7 @@ __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid
                 }
             };
             auto load_units = [&](int kt, int u0) {
+                if (reuse) return;
                 for (int u = u0; u < u0 + 4; ++u, ++it) {
                     const int h = u >> 1, br = u & 1;
                     unsigned char* d = acquire(24576);
@@ -702,7 +707,7 @@ __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid
             auto raw = [&](int kt) {          // raw-v similarities of tile kt (K = 256 as four 64-dim atoms per branch)
                 mbar_wait(&bars.r_empty, (kt & 1) ^ 1, 411);
                 tc_fence_after();
-                for (int x = 0; x < n_atoms; ++x, ++it) {
+                for (int x = atom0; x < n_atoms; ++x, ++it) {
                     const int br = x >> 2, at = x & 3;
                     unsigned char* d = wait_stage();
                     const uint64_t da = make_smem_desc_sw128(smem_u32(d)), db = make_smem_desc_sw128(smem_u32(d + 16384));
@@ -713,6 +718,7 @@ __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid
                 umma_commit(&bars.r_full);
             };
             auto units = [&](int u0) {
+                if (reuse) return;
                 for (int u = u0; u < u0 + 4; ++u, ++it, ++iu) {
                     const int su = iu & 1;
                     mbar_wait(&bars.s_empty[su], ((iu >> 1) & 1) ^ 1, 412);
@@ -785,14 +791,14 @@ __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid
             tc_fence_after();
             {
                 uint32_t rc[32], rr[32];
-                tmem_ld_32x32(lane_base + 256 + c0, rc);
+                if (!reuse) tmem_ld_32x32(lane_base + 256 + c0, rc);
                 if (use_obj) tmem_ld_32x32(lane_base + 320 + c0, rr);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int k = kbase + c0 + j;
                     bool ok = k < ci.n_clip && (k >= n_glob0 || (k >= lo && k < hi));
-                    ok = ok && (__uint_as_float(rc[j]) * 0.25f > a.sim_thresh);
+                    if (!reuse) ok = ok && (__uint_as_float(rc[j]) * 0.25f > a.sim_thresh);     // (already folded into w_in)
                     if (use_obj) ok = ok && (__uint_as_float(rr[j]) * 0.25f > a.conf_sim_thresh);
                     bits |= ok ? (1u << j) : 0u;
                 }
@@ -800,43 +806,71 @@ __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars.r_empty);
-            // ---- head-sum of the normalised attention over the 8 (head, branch) score units ----
-            float as[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) as[j] = 0.f;
-#pragma unroll
-            for (int u = 0; u < 8; ++u, ++iu) {
-                const int su = iu & 1;
-                mbar_wait(&bars.s_full[su], (iu >> 1) & 1, 421);
-                tc_fence_after();
-                uint32_t r[32];
-                tmem_ld_32x32(lane_base + 384 + su * 64 + c0, r);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars.s_empty[su]);      // the unit is in registers: release it before the math
-                const float m = mcl[u], sc = il[u];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) as[j] = fmaf(ex2_approx(fmaf(__uint_as_float(r[j]), kLog2e, -m)), sc, as[j]);
-            }
-            // ---- weights: mask * exp(mean attention) ----
             float w[32];
             float d0 = 0.f, d1 = 0.f;
+            if (!reuse) {
+                // ---- head-sum of the normalised attention over the 8 (head, branch) score units ----
+                float as[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-                w[j] = ((bits >> j) & 1u) ? ex2_approx(as[j] * (0.25f * kLog2e)) : 0.f;
-                w[j + 1] = ((bits >> (j + 1)) & 1u) ? ex2_approx(as[j + 1] * (0.25f * kLog2e)) : 0.f;
-                d0 += w[j]; d1 += w[j + 1];
+                for (int j = 0; j < 32; ++j) as[j] = 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u, ++iu) {
+                    const int su = iu & 1;
+                    mbar_wait(&bars.s_full[su], (iu >> 1) & 1, 421);
+                    tc_fence_after();
+                    uint32_t r[32];
+                    tmem_ld_32x32(lane_base + 384 + su * 64 + c0, r);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars.s_empty[su]);      // the unit is in registers: release it before the math
+                    const float m = mcl[u], sc = il[u];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) as[j] = fmaf(ex2_approx(fmaf(__uint_as_float(r[j]), kLog2e, -m)), sc, as[j]);
+                }
+                // ---- weights: mask * exp(mean attention) ----
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    w[j] = ((bits >> j) & 1u) ? ex2_approx(as[j] * (0.25f * kLog2e)) : 0.f;
+                    w[j + 1] = ((bits >> (j + 1)) & 1u) ? ex2_approx(as[j + 1] * (0.25f * kLog2e)) : 0.f;
+                }
+            } else {
+                // ---- weights of the cls launch (16-bit, sim mask applied) gated by the obj mask ----
+                const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.w_in) +
+                                                                  (int64_t)(ci.lbase + min(q, ci.n_loc - 1)) * lay.nk_pitch + kbase + c0);
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const uint4 raw = __ldg(src + cc);
+                    const uint32_t wd[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float lo16, hi16;
+                        if (BF16) {
+                            lo16 = __uint_as_float(wd[e] << 16); hi16 = __uint_as_float(wd[e] & 0xffff0000u);
+                        } else {
+                            const __half2 h2 = *reinterpret_cast<const __half2*>(&wd[e]);
+                            lo16 = __low2float(h2); hi16 = __high2float(h2);
+                        }
+                        const int j = cc * 8 + e * 2;
+                        w[j] = ((bits >> j) & 1u) ? lo16 : 0.f;
+                        w[j + 1] = ((bits >> (j + 1)) & 1u) ? hi16 : 0.f;
+                    }
+                }
             }
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) { d0 += w[j]; d1 += w[j + 1]; }
             den += d0 + d1;
             const int wb = kt & 1;
             mbar_wait(&bars.w_empty[wb], ((kt >> 1) & 1) ^ 1, 422);
             unsigned char* sWb = sW + wb * 16384;
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc)
-                *reinterpret_cast<uint4*>(sWb + sw128_off(row, (c0 >> 3) + cc)) =
-                    make_uint4(pack2<BF16>(w[cc * 8], w[cc * 8 + 1]), pack2<BF16>(w[cc * 8 + 2], w[cc * 8 + 3]),
-                               pack2<BF16>(w[cc * 8 + 4], w[cc * 8 + 5]), pack2<BF16>(w[cc * 8 + 6], w[cc * 8 + 7]));
+            for (int cc = 0; cc < 4; ++cc) {
+                const uint4 pk = make_uint4(pack2<BF16>(w[cc * 8], w[cc * 8 + 1]), pack2<BF16>(w[cc * 8 + 2], w[cc * 8 + 3]),
+                                            pack2<BF16>(w[cc * 8 + 4], w[cc * 8 + 5]), pack2<BF16>(w[cc * 8 + 6], w[cc * 8 + 7]));
+                *reinterpret_cast<uint4*>(sWb + sw128_off(row, (c0 >> 3) + cc)) = pk;
+                if (a.w_out && q_ok)     // keep the weights for the obj launch of the same module
+                    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.w_out) + (int64_t)(ci.lbase + q) * lay.nk_pitch + kbase + c0 + cc * 8) = pk;
+            }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars.w_full[wb]);

@@ -271,7 +271,7 @@ def attn_pv(lay: AttnLayoutT, bufs, x_cls, x_reg, stats, need_reg=True):
         L.check(L.lib().tscd_attn_pv(C.byref(a), _stream()), "tscd_attn_pv")
 
 
-def attn_round2(lay: AttnLayoutT, bufs, vt, stats, out, use_obj_mask, sim_thresh=0.75, conf_sim_thresh=0.99):
+def attn_round2(lay: AttnLayoutT, bufs, vt, stats, out, use_obj_mask, sim_thresh=0.75, conf_sim_thresh=0.99, w_out=None, w_in=None):
     a = L.AttnRound2Args()
     a.lay = lay.to_c()
     for n in ("qn_cls", "kn_cls", "qn_reg", "kn_reg", "vn_cls", "vn_reg", "row_frame"):
@@ -279,6 +279,9 @@ def attn_round2(lay: AttnLayoutT, bufs, vt, stats, out, use_obj_mask, sim_thresh
     a.vt, a.stats, a.use_obj_mask = _p(vt), _p(stats), int(use_obj_mask)
     a.sim_thresh, a.conf_sim_thresh = sim_thresh, conf_sim_thresh
     a.out, a.ld_out = _p(out), out.stride(0)
+    a.w_out, a.w_in = _p(w_out), _p(w_in)
+    for t in (w_out, w_in):
+        assert t is None or (t.dtype == lay.dtype and t.stride(0) == lay.nk_pitch and t.stride(1) == 1)
     with L.timed("tscd_attn_round2"):
         L.check(L.lib().tscd_attn_round2(C.byref(a), _stream()), "tscd_attn_round2")
 
