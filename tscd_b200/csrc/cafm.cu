@@ -131,7 +131,9 @@ struct ChainSmem {
 // ---------------------------------------------------------------------------------------------- matching costs
 // One CTA per (local frame, 32x32 tile): 128-dim slabs of the two 1024-dim embeddings staged in shared memory.
 __global__ void __launch_bounds__(256) cafm_cost_kernel(const tscd_cafm_cost_args a) {
-    __shared__ __align__(16) float tileA[32][132], tileB[32][132];   // 4-float skew: float4 row reads are conflict-free
+    __shared__ __align__(16) float tiles[2][32][132];                 // 4-float skew: float4 row reads are conflict-free
+    float (*tileA)[132] = tiles[0];
+    float (*tileB)[132] = tiles[1];
     const int lf = blockIdx.x, b = lf / a.L, f = lf - b * a.L;
     const int l0 = a.lrow_off[lf], n = a.lrow_off[lf + 1] - l0;
     if (n <= 0) {
@@ -162,8 +164,13 @@ __global__ void __launch_bounds__(256) cafm_cost_kernel(const tscd_cafm_cost_arg
     if (rb >= np || cb >= n || np > KM || n > KM) return;
     const float* Rc = a.emb_reg + (int64_t)l0 * E;
     const float* Cc = a.emb_cls + (int64_t)l0 * E;
-    const int lane = threadIdx.x & 31, pr = threadIdx.x >> 5;   // pairs (pr + 8k, lane), k = 0..3
-    float accR[4] = {0.f, 0.f, 0.f, 0.f}, accC[4] = {0.f, 0.f, 0.f, 0.f};
+    // Register tiling: the CTA's 4 groups of 64 threads each take 32 of a slab's 128 dims and ALL 32x32 pairs; a thread
+    // owns the 4x4 pairs (rows ty + 8i, columns tx + 8j), so one slab step costs 8 conflict-free 16-byte shared loads for
+    // 64 FMAs (the 1-output-column mapping it replaces was shared-memory-bandwidth bound at 5 loads per 16 FMAs).
+    const int grp = threadIdx.x >> 6, tg = threadIdx.x & 63, ty = tg & 7, tx = tg >> 3;
+    float accR[16], accC[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { accR[i] = 0.f; accC[i] = 0.f; }
     // slabs of 128 dims; each thread moves four float4 per matrix and slab (row = t / 32 + 8 k, 16-byte column t % 32);
     // the next slab is fetched into registers while the current one is multiplied (one barrier pair per slab)
     const int lr = threadIdx.x >> 5, lc4 = threadIdx.x & 31;
@@ -189,28 +196,50 @@ __global__ void __launch_bounds__(256) cafm_cost_kernel(const tscd_cafm_cost_arg
         }
         __syncthreads();
         if (s + 1 < 16) fetch(s + 1);
-        float x[4] = {0.f, 0.f, 0.f, 0.f};
-        const float4* qrow = reinterpret_cast<const float4*>(tileB[lane]);
-#pragma unroll 4
-        for (int d4 = 0; d4 < 32; ++d4) {
-            const float4 q = qrow[d4];
+        float x[16];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float4 p4 = reinterpret_cast<const float4*>(tileA[pr + 8 * k])[d4];   // broadcast
-                x[k] = fmaf(p4.x, q.x, fmaf(p4.y, q.y, fmaf(p4.z, q.z, fmaf(p4.w, q.w, x[k]))));
+        for (int i = 0; i < 16; ++i) x[i] = 0.f;
+#pragma unroll 2
+        for (int d4 = grp * 8; d4 < grp * 8 + 8; ++d4) {
+            float4 p4[4], q4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                p4[i] = reinterpret_cast<const float4*>(tileA[ty + 8 * i])[d4];
+                q4[i] = reinterpret_cast<const float4*>(tileB[tx + 8 * i])[d4];
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    x[i * 4 + j] = fmaf(p4[i].x, q4[j].x, fmaf(p4[i].y, q4[j].y, fmaf(p4[i].z, q4[j].z, fmaf(p4[i].w, q4[j].w, x[i * 4 + j]))));
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { if (s < 8) accR[k] += x[k]; else accC[k] += x[k]; }
+        for (int i = 0; i < 16; ++i) { if (s < 8) accR[i] += x[i]; else accC[i] += x[i]; }
     }
-    float* out = a.cost + (int64_t)lf * KM * KM;
+    // reduce the four dim-groups through shared memory (the tiles are free now): red[grp][which][row][col]
+    __syncthreads();
+    float* red = &tiles[0][0][0];
+    static_assert(sizeof(float) * 2 * 32 * 132 >= sizeof(float) * 4 * 2 * 32 * 32, "reduction scratch must fit in the two tiles");
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int r = rb + pr + 8 * k, c = cb + lane;
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = ty + 8 * i, c = tx + 8 * j;
+            red[((grp * 2 + 0) * 32 + r) * 32 + c] = accR[i * 4 + j];
+            red[((grp * 2 + 1) * 32 + r) * 32 + c] = accC[i * 4 + j];
+        }
+    __syncthreads();
+    float* out = a.cost + (int64_t)lf * KM * KM;
+    for (int t = threadIdx.x; t < 32 * 32; t += 256) {
+        const int rr = t >> 5, cc = t & 31;
+        const int r = rb + rr, c = cb + cc;
         if (r < np && c < n) {
-            const float cr = accR[k] / (nRp[r] * a.norm_reg[l0 + c]);
-            const float cc = accC[k] / (nCp[r] * a.norm_cls[l0 + c]);
-            float v = 1.f - (cr + cc) / 2.f;
+            float dr = 0.f, dc = 0.f;
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) { dr += red[((gq * 2 + 0) * 32 + rr) * 32 + cc]; dc += red[((gq * 2 + 1) * 32 + rr) * 32 + cc]; }
+            const float cr = dr / (nRp[r] * a.norm_reg[l0 + c]);
+            const float cq = dc / (nCp[r] * a.norm_cls[l0 + c]);
+            float v = 1.f - (cr + cq) / 2.f;
             if (v != v) v = 0.f;                    // tscd_matching.py:930 NaN -> 0
             out[(int64_t)r * KM + c] = v;
         }
