@@ -166,6 +166,78 @@ __device__ __forceinline__ void block_sort_desc64_dyn(unsigned long long* smem_k
     else block_sort_desc64<16>(smem_keys, n);
 }
 
+// ---- block radix select (k-th largest key), shared by K1 and K2 ---------------------------------------
+struct SelSmem {
+    int hist[256];
+    int scan[40];
+    int misc[8];
+};
+
+// k-th largest key among keys[0..n) (k >= 1, k <= n).  Returns the threshold key T and the number of
+// elements equal to T that belong to the top-k (r_eq); elements > T number k - r_eq.
+template <typename KT>
+__device__ void radix_select_kth(const KT* keys, int n, int k, SelSmem* s, uint32_t* T_out, int* req_out) {
+    uint32_t prefix = 0, mask = 0;
+    int remaining = k;
+    constexpr int kPasses = (int)sizeof(KT);       // 8-bit digits, most significant first
+    for (int pass = 0; pass < kPasses; ++pass) {
+        const int shift = 8 * (kPasses - 1 - pass);
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s->hist[i] = 0;
+        __syncthreads();
+        // histogram of the digit among the keys that still match the prefix.  Sigmoid scores share a few exponent
+        // digits, so a plain shared-memory atomic per key would serialise on one bin in the first pass: the lanes
+        // that agree with the first active lane's digit are counted with one ballot (leader adds the population),
+        // the others (few, spread over many bins in the later passes) add themselves.
+        for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+            const int i = i0 + threadIdx.x;
+            const uint32_t u = i < n ? (uint32_t)keys[i] : 0u;
+            const bool in = i < n && (u & mask) == prefix;
+            const unsigned act = __ballot_sync(0xffffffffu, in);
+            if (act == 0u) continue;
+            const uint32_t d = (u >> shift) & 255;
+            const int first = __ffs(act) - 1;
+            const uint32_t d0 = __shfl_sync(0xffffffffu, d, first);
+            const unsigned same = __ballot_sync(0xffffffffu, in && d == d0);
+            if ((int)(threadIdx.x & 31) == first) atomicAdd(&s->hist[d0], __popc(same));
+            else if (in && d != d0) atomicAdd(&s->hist[d], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            // warp 0: lane l owns digits [8l, 8l+8); suffix sums from the top digit down
+            const int lane = threadIdx.x;
+            int loc[8], tot = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { loc[j] = s->hist[255 - (lane * 8 + j)]; tot += loc[j]; }
+            int inc = warp_incl_scan(tot, lane);
+            int before = inc - tot;  // count of keys in strictly higher digit groups
+            if (before < remaining && remaining <= inc) {
+                int cum = before;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (cum < remaining && remaining <= cum + loc[j]) {
+                        s->misc[0] = 255 - (lane * 8 + j);
+                        s->misc[1] = remaining - cum;
+                    }
+                    cum += loc[j];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= (uint32_t)s->misc[0] << shift;
+        mask |= 255u << shift;
+        remaining = s->misc[1];
+        __syncthreads();
+    }
+    *T_out = prefix;
+    *req_out = remaining;
+}
+
+// Class max / arg-max of every anchor as its own streaming kernel (mode A, planar head layouts): thread = 8 anchors x all
+// class planes, 8 independent 16-byte loads in flight per batch, thousands of small CTAs -> the class planes (83 % of the
+// stage's mandatory HBM bytes) are read at streaming bandwidth instead of inside the per-frame selection CTA, whose
+// on-chip phases (radix select, scans, sort) would otherwise stall the loads.  Results go to a [F, ws_pitch] workspace
+// that select_kernel<T, true> reads back for the ~pre_k survivors only (L2 hits).
+
 // ---- anchor geometry ----------------------------------------------------------------------------------
 struct AnchorPos {
     int level;

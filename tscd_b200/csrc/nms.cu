@@ -9,10 +9,10 @@
 //
 // Algorithm (lazy greedy, no N^2 bitmask): candidates are sorted in shared memory (bitonic, 64-bit
 // composite keys = score bits | inverted position, which reproduces the stable order).  They are then
-// processed in chunks of 32: all threads build the 32x32 intra-chunk IoU bitmask, one warp resolves the
-// chunk serially from the bitmask (ballot/shuffle), then all threads apply the chunk's survivors to every
-// later candidate.  Work is O(kept * N) instead of O(N^2) and stops as soon as max_keep boxes are kept
-// (mode A only needs the first K=30 survivors of 750).
+// processed in chunks of 32: all threads test the chunk against the boxes kept so far (32 x kept IoUs) and build
+// the 32x32 intra-chunk IoU bitmask, one warp resolves the chunk serially from the bitmask (ballot/shuffle).
+// Later chunks are never touched before they are needed: work is O(kept * processed) instead of O(N^2) and stops
+// as soon as max_keep boxes are kept (mode A only needs the first K=30 survivors of 750).
 #include "common.cuh"
 
 namespace tscd {
@@ -244,33 +244,26 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const tscd_nms_args ar
         if (threadIdx.x == 0) args.keep_count[frame] = 0;
         return;
     }
-    int n64 = 1;
-    while (n64 < n) n64 <<= 1;
-
-    unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem_raw);      // [n64]
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem_raw);      // [smem_cap]
     float4* sbox = reinterpret_cast<float4*>(skey + smem_cap);                        // [n] sorted, offset boxes
     float* sarea = reinterpret_cast<float*>(sbox + smem_cap);                         // [n]
-    unsigned char* dead = reinterpret_cast<unsigned char*>(sarea + smem_cap);         // [n]
+    unsigned char* dead = reinterpret_cast<unsigned char*>(sarea + smem_cap);         // [n] ints: positions of the kept boxes
     __shared__ unsigned int cmask[32];
     __shared__ float red[kNmsThreads / 32];
-    __shared__ int s_kept_bits, s_nkept;
-    __shared__ int s_chunk_kept[32];
+    __shared__ int s_nkept;
+    __shared__ unsigned int s_deadbits;
+    __shared__ SelSmem rs;
 
     const int64_t base = (int64_t)frame * args.cand_cap;
     const float* gscore = args.score + base;
     const float4* gbox = reinterpret_cast<const float4*>(args.box) + base;
     const int32_t* gcls = args.cls + base;
 
-    // ---- sort keys + max coordinate -----------------------------------------------------------------
+    // ---- max coordinate (over ALL boxes: the coordinate-trick offset unit) --------------------------------
     float mx = -INFINITY;
-    for (int i = threadIdx.x; i < n64; i += blockDim.x) {
-        unsigned long long v = 0ull;
-        if (i < n) {
-            v = ((unsigned long long)f2ord(gscore[i]) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
-            float4 b = gbox[i];
-            mx = fmaxf(mx, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
-        }
-        skey[i] = v;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float4 b = gbox[i];
+        mx = fmaxf(mx, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
     }
     mx = warp_maxf(mx);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
@@ -279,83 +272,119 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const tscd_nms_args ar
 #pragma unroll
     for (int w = 1; w < kNmsThreads / 32; ++w) mx = fmaxf(mx, red[w]);
     const float off_unit = __fadd_rn(mx, 1.f);  // boxes.max() + 1
-
-    block_sort_desc64_dyn(skey, n, smem_cap);
-
-    for (int r = threadIdx.x; r < n; r += blockDim.x) {
-        int pos = (int)(0xffffffffu - (uint32_t)(skey[r] & 0xffffffffull));
-        float4 b = gbox[pos];
-        float off = __fmul_rn((float)gcls[pos], off_unit);
-        b.x = __fadd_rn(b.x, off); b.y = __fadd_rn(b.y, off);
-        b.z = __fadd_rn(b.z, off); b.w = __fadd_rn(b.w, off);
-        sbox[r] = b;
-        sarea[r] = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
-        dead[r] = 0;
-    }
-    if (threadIdx.x == 0) s_nkept = 0;
-    __syncthreads();
-
     const double thr = (double)args.iou_thresh;
     const int max_keep = args.max_keep;
     int32_t* keep = args.keep + (int64_t)frame * max_keep;
+    int* s_keptidx = reinterpret_cast<int*>(dead);     // sorted positions of the boxes kept so far (<= min(n, max_keep))
 
-    for (int c0 = 0; c0 < n; c0 += 32) {
-        const int cn = min(32, n - c0);
-        // (1) intra-chunk bitmask: bit j of cmask[l] set if earlier lane j suppresses lane l
-        if (threadIdx.x < 32) cmask[threadIdx.x] = 0u;
-        __syncthreads();
-        for (int pr = threadIdx.x; pr < 32 * 32; pr += blockDim.x) {
-            int l = pr >> 5, j = pr & 31;
-            if (j < l && l < cn) {
-                if (iou_gt(sbox[c0 + j], sarea[c0 + j], sbox[c0 + l], sarea[c0 + l], thr)) atomicOr(&cmask[l], 1u << j);
-            }
-        }
-        __syncthreads();
-        // (2) serial resolve by warp 0
-        if (threadIdx.x < 32) {
-            const int lane = threadIdx.x;
-            bool alive = (lane < cn) && !dead[c0 + lane];
-            unsigned alive_bits = __ballot_sync(0xffffffffu, alive);
-            unsigned my = cmask[lane];
-            unsigned kept = 0u;
-#pragma unroll
-            for (int l = 0; l < 32; ++l) {
-                unsigned m = __shfl_sync(0xffffffffu, my, l);
-                if (((alive_bits >> l) & 1u) && !(m & kept)) kept |= 1u << l;
-            }
-            int nk = s_nkept;
-            __syncwarp();
-            // truncate to max_keep
-            int rank = __popc(kept & ((1u << lane) - 1u));
-            bool mine = (kept >> lane) & 1u;
-            if (mine && nk + rank < max_keep) {
-                keep[nk + rank] = (int)(0xffffffffu - (uint32_t)(skey[c0 + lane] & 0xffffffffull));
-                s_chunk_kept[rank] = c0 + lane;
-            }
-            if (lane == 0) {
-                int add = min(__popc(kept), max_keep - nk);
-                s_kept_bits = add;  // number of newly kept boxes to apply
-                s_nkept = nk + add;
-            }
-        }
-        __syncthreads();
-        const int n_new = s_kept_bits;
-        if (s_nkept >= max_keep) break;
-        // (3) apply this chunk's survivors to all later candidates
-        if (n_new > 0) {
-            for (int j = c0 + 32 + threadIdx.x; j < n; j += blockDim.x) {
-                if (dead[j]) continue;
-                float4 bj = sbox[j];
-                float sj = sarea[j];
-                bool d = false;
-                for (int k = 0; k < n_new && !d; ++k) {
-                    int i = s_chunk_kept[k];
-                    d = iou_gt(sbox[i], sarea[i], bj, sj, thr);
+    // Top-K use (mode A keeps the first 30 survivors of 750): sorting all candidates is three quarters of this kernel.
+    // Attempt 0 takes only the candidates whose score reaches the kPartial-th largest one (block radix select; every
+    // tie at the threshold is included, so the subset is exactly a PREFIX of the fully sorted order), sorts those 256 at
+    // most and runs the same greedy loop; if that prefix is exhausted before max_keep boxes survive, attempt 1 redoes
+    // the frame with the full sort.
+    constexpr int kPartial = 128, kPartialCap = 256;
+    const bool try_partial = max_keep * 4 <= kPartial && n > kPartialCap;
+    for (int attempt = try_partial ? 0 : 1; attempt < 2; ++attempt) {
+        int n_work = n;                          // number of sorted candidates this attempt can look at
+        if (attempt == 0) {
+            uint32_t* k32 = reinterpret_cast<uint32_t*>(sarea);      // scratch: sarea is written later
+            for (int i = threadIdx.x; i < n; i += blockDim.x) k32[i] = f2ord(gscore[i]);
+            __syncthreads();
+            uint32_t T;
+            int req;
+            radix_select_kth<uint32_t>(k32, n, kPartial, &rs, &T, &req);
+            int cnt = 0;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) cnt += k32[i] >= T ? 1 : 0;
+            int tot;
+            block_excl_scan(cnt, rs.scan, &tot);
+            if (tot > kPartialCap) continue;                              // too many ties at the threshold: full path
+            // positions in ascending order (any order works: the sort key carries the position)
+            if (threadIdx.x == 0) rs.misc[3] = 0;
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                if (k32[i] >= T) {
+                    const int slot = atomicAdd(&rs.misc[3], 1);
+                    skey[slot] = ((unsigned long long)k32[i] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
                 }
-                if (d) dead[j] = 1;
             }
+            __syncthreads();
+            n_work = tot;
+            block_sort_desc64_dyn(skey, n_work, kPartialCap);
+        } else {
+            for (int i = threadIdx.x; i < n; i += blockDim.x)
+                skey[i] = ((unsigned long long)f2ord(gscore[i]) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+            __syncthreads();
+            block_sort_desc64_dyn(skey, n, smem_cap);
+        }
+
+        for (int r = threadIdx.x; r < n_work; r += blockDim.x) {
+            int pos = (int)(0xffffffffu - (uint32_t)(skey[r] & 0xffffffffull));
+            float4 b = gbox[pos];
+            float off = __fmul_rn((float)gcls[pos], off_unit);
+            b.x = __fadd_rn(b.x, off); b.y = __fadd_rn(b.y, off);
+            b.z = __fadd_rn(b.z, off); b.w = __fadd_rn(b.w, off);
+            sbox[r] = b;
+            sarea[r] = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+        }
+        if (threadIdx.x == 0) s_nkept = 0;
+        __syncthreads();
+
+        for (int c0 = 0; c0 < n_work; c0 += 32) {
+            const int cn = min(32, n_work - c0);
+            // (0) fully lazy: only THIS chunk is tested against the boxes kept so far (32 x kept IoUs); later chunks are
+            //     never touched if max_keep is reached first (mode A wants the first 30 survivors of 750)
+            if (threadIdx.x < 32) cmask[threadIdx.x] = 0u;
+            if (threadIdx.x == 0) s_deadbits = 0u;
+            __syncthreads();
+            const int nk0 = s_nkept;
+            {
+                unsigned mydead = 0u;
+                const int l = threadIdx.x & 31;
+                if (l < cn) {
+                    const float4 bl = sbox[c0 + l];
+                    const float sl = sarea[c0 + l];
+                    for (int k = threadIdx.x >> 5; k < nk0 && !mydead; k += kNmsThreads / 32) {
+                        const int i = s_keptidx[k];
+                        if (iou_gt(sbox[i], sarea[i], bl, sl, thr)) mydead = 1u << l;
+                    }
+                }
+                if (mydead) atomicOr(&s_deadbits, mydead);
+            }
+            // (1) intra-chunk bitmask: bit j of cmask[l] set if earlier lane j suppresses lane l
+            for (int pr = threadIdx.x; pr < 32 * 32; pr += blockDim.x) {
+                int l = pr >> 5, j = pr & 31;
+                if (j < l && l < cn) {
+                    if (iou_gt(sbox[c0 + j], sarea[c0 + j], sbox[c0 + l], sarea[c0 + l], thr)) atomicOr(&cmask[l], 1u << j);
+                }
+            }
+            __syncthreads();
+            // (2) serial resolve by warp 0
+            if (threadIdx.x < 32) {
+                const int lane = threadIdx.x;
+                bool alive = (lane < cn) && !((s_deadbits >> lane) & 1u);
+                unsigned alive_bits = __ballot_sync(0xffffffffu, alive);
+                unsigned my = cmask[lane];
+                unsigned kept = 0u;
+    #pragma unroll
+                for (int l = 0; l < 32; ++l) {
+                    unsigned m = __shfl_sync(0xffffffffu, my, l);
+                    if (((alive_bits >> l) & 1u) && !(m & kept)) kept |= 1u << l;
+                }
+                int nk = nk0;
+                // truncate to max_keep
+                int rank = __popc(kept & ((1u << lane) - 1u));
+                bool mine = (kept >> lane) & 1u;
+                if (mine && nk + rank < max_keep) {
+                    keep[nk + rank] = (int)(0xffffffffu - (uint32_t)(skey[c0 + lane] & 0xffffffffull));
+                    s_keptidx[nk + rank] = c0 + lane;
+                }
+                if (lane == 0) s_nkept = nk + min(__popc(kept), max_keep - nk);
+            }
+            __syncthreads();
+            if (s_nkept >= max_keep) break;
         }
         __syncthreads();
+        if (s_nkept >= max_keep || n_work == n) break;     // done; otherwise the prefix was too short: full sort
     }
     if (threadIdx.x == 0) args.keep_count[frame] = s_nkept;
 }
@@ -502,7 +531,7 @@ extern "C" int tscd_nms(const tscd_nms_args* a, void* stream) {
     int cap64 = 1;
     while (cap64 < cap) cap64 <<= 1;   // sort buffer must hold the padded power of two
     if (cap64 < kNmsMatThreads) cap64 = kNmsMatThreads;   // ... and E * blockDim.x keys of the block sort (either kernel)
-    size_t smem = (size_t)cap64 * (8 + 16 + 4 + 1) + 16;
+    size_t smem = (size_t)cap64 * (8 + 16 + 4 + 4) + 16;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (cap > 64 && cap <= kNmsMatCap && (int64_t)a->max_keep * 4 >= cap) {
         // most candidates survive: per-class decomposition / suppression-matrix kernel (the lazy kernel stops early and wins
