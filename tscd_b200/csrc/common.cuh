@@ -100,8 +100,8 @@ __device__ __forceinline__ int block_excl_scan(int v, int* scratch, int* total) 
 // Compare-exchange distances below E stay inside the thread, distances below 32 * E go through warp shuffles, only
 // the remaining ones use shared memory and a CTA barrier (10 of the 55 steps for 1024 keys on 512 threads).
 // `smem` must hold E * blockDim.x keys.  All threads must call.
-template <int E>
-__device__ __forceinline__ void bitonic_sort_regs_desc(unsigned long long (&v)[E], unsigned long long* smem) {
+template <int E, typename KT>
+__device__ __forceinline__ void bitonic_sort_regs_desc(KT (&v)[E], KT* smem) {
     const int tid = threadIdx.x;
     const int N = E * (int)blockDim.x;
     for (int k = 2; k <= N; k <<= 1) {
@@ -111,7 +111,7 @@ __device__ __forceinline__ void bitonic_sort_regs_desc(unsigned long long (&v)[E
                 for (int r = 0; r < E; ++r) {
                     if ((r & j) == 0 && r + j < E) {
                         const bool desc = (((tid * E + r) & k) == 0);
-                        const unsigned long long x = v[r], y = v[r + j < E ? r + j : r];
+                        const KT x = v[r], y = v[r + j < E ? r + j : r];
                         const bool sw = desc ? (x < y) : (x > y);
                         v[r] = sw ? y : x;
                         v[r + j < E ? r + j : r] = sw ? x : y;
@@ -121,7 +121,7 @@ __device__ __forceinline__ void bitonic_sort_regs_desc(unsigned long long (&v)[E
 #pragma unroll
                 for (int r = 0; r < E; ++r) {
                     const int idx = tid * E + r;
-                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[r], j / E);
+                    const KT o = __shfl_xor_sync(0xffffffffu, v[r], j / E);
                     const bool keep_max = (((idx & j) == 0) == ((idx & k) == 0));
                     v[r] = keep_max ? (v[r] > o ? v[r] : o) : (v[r] < o ? v[r] : o);
                 }
@@ -132,7 +132,7 @@ __device__ __forceinline__ void bitonic_sort_regs_desc(unsigned long long (&v)[E
 #pragma unroll
                 for (int r = 0; r < E; ++r) {
                     const int idx = tid * E + r;
-                    const unsigned long long o = smem[idx ^ j];
+                    const KT o = smem[idx ^ j];
                     const bool keep_max = (((idx & j) == 0) == ((idx & k) == 0));
                     v[r] = keep_max ? (v[r] > o ? v[r] : o) : (v[r] < o ? v[r] : o);
                 }
@@ -144,26 +144,27 @@ __device__ __forceinline__ void bitonic_sort_regs_desc(unsigned long long (&v)[E
 
 // Sort the first `n` (<= cap) keys of smem_keys[0..cap) descending in place; cap = E * blockDim.x exactly.
 // Entries at or beyond n are treated as 0 (they sort last).  Ends with the sorted keys visible to the whole CTA.
-template <int E>
-__device__ __forceinline__ void block_sort_desc64(unsigned long long* smem_keys, int n) {
-    unsigned long long v[E];
+template <int E, typename KT>
+__device__ __forceinline__ void block_sort_desc64(KT* smem_keys, int n) {
+    KT v[E];
     const int tid = threadIdx.x;
 #pragma unroll
-    for (int r = 0; r < E; ++r) { const int i = tid * E + r; v[r] = i < n ? smem_keys[i] : 0ull; }
+    for (int r = 0; r < E; ++r) { const int i = tid * E + r; v[r] = i < n ? smem_keys[i] : (KT)0; }
     __syncthreads();
-    bitonic_sort_regs_desc<E>(v, smem_keys);
+    bitonic_sort_regs_desc<E, KT>(v, smem_keys);
 #pragma unroll
     for (int r = 0; r < E; ++r) smem_keys[tid * E + r] = v[r];
     __syncthreads();
 }
-// run-time dispatch on cap / blockDim.x (a power of two between 1 and 16)
-__device__ __forceinline__ void block_sort_desc64_dyn(unsigned long long* smem_keys, int n, int cap) {
+// run-time dispatch on cap / blockDim.x (a power of two between 1 and 16); keys are 64- or 32-bit unsigned
+template <typename KT>
+__device__ __forceinline__ void block_sort_desc64_dyn(KT* smem_keys, int n, int cap) {
     const int e = cap / (int)blockDim.x;
-    if (e <= 1) block_sort_desc64<1>(smem_keys, n);
-    else if (e == 2) block_sort_desc64<2>(smem_keys, n);
-    else if (e == 4) block_sort_desc64<4>(smem_keys, n);
-    else if (e == 8) block_sort_desc64<8>(smem_keys, n);
-    else block_sort_desc64<16>(smem_keys, n);
+    if (e <= 1) block_sort_desc64<1, KT>(smem_keys, n);
+    else if (e == 2) block_sort_desc64<2, KT>(smem_keys, n);
+    else if (e == 4) block_sort_desc64<4, KT>(smem_keys, n);
+    else if (e == 8) block_sort_desc64<8, KT>(smem_keys, n);
+    else block_sort_desc64<16, KT>(smem_keys, n);
 }
 
 // ---- block radix select (k-th largest key), shared by K1 and K2 ---------------------------------------

@@ -309,12 +309,12 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const tscd_nms_args ar
             }
             __syncthreads();
             n_work = tot;
-            block_sort_desc64_dyn(skey, n_work, kPartialCap);
+            block_sort_desc64_dyn<unsigned long long>(skey, n_work, kPartialCap);
         } else {
             for (int i = threadIdx.x; i < n; i += blockDim.x)
                 skey[i] = ((unsigned long long)f2ord(gscore[i]) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
             __syncthreads();
-            block_sort_desc64_dyn(skey, n, smem_cap);
+            block_sort_desc64_dyn<unsigned long long>(skey, n, smem_cap);
         }
 
         for (int r = threadIdx.x; r < n_work; r += blockDim.x) {
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(kNmsMatThreads) nms_matrix_kernel(const tscd_n
     for (int w = 1; w < kNmsMatThreads / 32; ++w) mx = fmaxf(mx, red[w]);
     const float off_unit = __fadd_rn(mx, 1.f);  // boxes.max() + 1
 
-    block_sort_desc64_dyn(skey, n, smem_cap);
+    block_sort_desc64_dyn<unsigned long long>(skey, n, smem_cap);
 
     for (int r = threadIdx.x; r < n; r += blockDim.x) {
         int pos = (int)(0xffffffffu - (uint32_t)(skey[r] & 0xffffffffull));

@@ -291,14 +291,39 @@ __global__ void __launch_bounds__(kSelThreads, PRE ? 3 : 2) select_kernel(const 
 
     // ---- mode A: order by objectness, descending, ties lower anchor id first ---------------------------
     if (args.mode == 0) {
-        for (int i = threadIdx.x; i < n_sel; i += blockDim.x) {
-            const int a = sel[i];
-            sortbuf[i] = ((unsigned long long)keys[a] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)a);
+        bool sorted = false;
+        if (K16 && A <= 65536) {
+            // 32-bit keys (logit order | inverted anchor id): half the compare-exchange work of the 64-bit sort.  Valid
+            // unless two selected anchors with DIFFERENT logits share a score (sigmoid saturation): checked on the
+            // sorted list (such a pair is adjacent because sigmoid is monotone); then the 64-bit sort redoes the order.
+            uint32_t* sort32 = reinterpret_cast<uint32_t*>(sortbuf);
+            for (int i = threadIdx.x; i < n_sel; i += blockDim.x) {
+                const int a = sel[i];
+                sort32[i] = ((uint32_t)k16[a] << 16) | (0xffffu - (uint32_t)a);
+            }
+            __syncthreads();
+            block_sort_desc64_dyn<uint32_t>(sort32, n_sel, sort_cap);
+            int bad = 0;
+            for (int i = threadIdx.x; i + 1 < n_sel; i += blockDim.x) {
+                const int a0 = 0xffff - (int)(sort32[i] & 0xffffu), a1 = 0xffff - (int)(sort32[i + 1] & 0xffffu);
+                bad |= (k16[a0] != k16[a1] && keys[a0] == keys[a1]) ? 1 : 0;
+            }
+            if (!__syncthreads_or(bad)) {
+                for (int i = threadIdx.x; i < n_sel; i += blockDim.x) sel[i] = 0xffff - (int)(sort32[i] & 0xffffu);
+                sorted = true;
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        block_sort_desc64_dyn(sortbuf, n_sel, sort_cap);      // registers + shuffles; shared memory only for distances >= 32 * E
-        for (int i = threadIdx.x; i < n_sel; i += blockDim.x)
-            sel[i] = (int)(0xffffffffu - (uint32_t)(sortbuf[i] & 0xffffffffull));
+        if (!sorted) {
+            for (int i = threadIdx.x; i < n_sel; i += blockDim.x) {
+                const int a = sel[i];
+                sortbuf[i] = ((unsigned long long)keys[a] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)a);
+            }
+            __syncthreads();
+            block_sort_desc64_dyn<unsigned long long>(sortbuf, n_sel, sort_cap);      // registers + shuffles; smem only for distances >= 32 * E
+            for (int i = threadIdx.x; i < n_sel; i += blockDim.x)
+                sel[i] = (int)(0xffffffffu - (uint32_t)(sortbuf[i] & 0xffffffffull));
+        }
         __syncthreads();
     }
 
