@@ -285,3 +285,37 @@ def test_selection_seam_s1_raw_level_outputs(dt, mode):
         if got == want:
             torch.testing.assert_close(rows[f].cpu(), o_rows[f], rtol=1e-5, atol=1e-4)
     assert same / tot >= 0.995, (same, tot)
+
+
+def test_select_mode_a_sigmoid_saturation_ties():
+    """fp16 objectness logits >= 18 all map to sigmoid == 1.0f: different logits, equal scores.  The kernel ranks by the
+    16-bit logit first (2-pass radix select, 32-bit sort) and must fall back to the score keys so that ties are still
+    ordered by anchor id (topk tie-break, lower index first), not by logit."""
+    ops, _ = _stage_mods()
+    hw = [(72, 72), (36, 36), (18, 18)]
+    C, Fn = 25, 3
+    g = torch.Generator().manual_seed(77)
+    an = ops.AnchorSpec(hw)
+    A = an.num_anchors
+    reg, obj, cls = [], [], []
+    for (h, w) in hw:
+        reg.append(torch.cat([torch.rand(Fn, 2, h, w, generator=g), torch.randn(Fn, 2, h, w, generator=g) * 0.5], 1).half())
+        o = torch.randn(Fn, 1, h, w, generator=g) * 2 - 3
+        sat = torch.rand(Fn, 1, h, w, generator=g) < 0.045                       # ~300 saturated anchors per frame
+        vals = torch.tensor([18.0, 19.0, 20.0, 25.0])[torch.randint(0, 4, (Fn, 1, h, w), generator=g)]
+        obj.append(torch.where(sat, vals, o).half())
+        cls.append((torch.randn(Fn, C, h, w, generator=g) * 2 - 3).half())
+    head = ops.HeadViews.from_levels([t.cuda() for t in reg], [t.cuda() for t in obj], [t.cuda() for t in cls], an)
+    cand = ops.select(head, "A", pre_k=750)
+    torch.cuda.synchronize()
+    flat_obj = torch.cat([o.flatten(1) for o in obj], 1).float()                # [Fn, A], level-major anchor order
+    assert flat_obj.shape[1] == A
+    for f in range(Fn):
+        score = torch.sigmoid(flat_obj[f])
+        n_sat = int((score == 1.0).sum())
+        assert n_sat > 100
+        want = oracle.topk_lower_index_first(score, 750).tolist()
+        got = cand["idx"][f, :int(cand["count"][f])].cpu().tolist()
+        assert len(got) == 750
+        assert got[:n_sat] == want[:n_sat], f"frame {f}: saturated ties must come in anchor order"
+        assert len(set(got) & set(want)) >= 0.995 * 750
