@@ -214,7 +214,7 @@ struct PvTmaps {
 //   warps 0-3            softmax: thread == query row == TMEM lane; tcgen05.ld, visibility mask from the row's own
 //                        frame range (no shared-memory side table), exp2, fp16/bf16 probabilities written as the
 //                        swizzled K-major A operand of the P@V products (two P buffers).
-//   TMEM: pass A  2 x (S_cls 128 | S_reg 128);   pass B  2 x (S_cls 64 | S_reg 64) | O_cc O_rc O_cr O_rr (64 each).
+//   TMEM: pass A  2 x (S_cls 128 | S_reg 128);   pass B  2 x (S_cls 64 | S_reg 64) | O_cc O_cr O_rc O_rr (64 each).
 // -------------------------------------------------------------------------------------------------------
 constexpr int kPvThreads = 320;     // 8 softmax warps (2 per scheduler), TMA warp, MMA warp
 constexpr int kPvStages = 3;
@@ -415,6 +415,7 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
     } else if (warp == 9) {
         if (lane == 0) {
             const uint32_t idesc64 = make_idesc_f16(BF16, 128, 64);
+            const uint32_t idesc128b = make_idesc_f16(BF16, 128, 128);
             uint32_t it = itA;          // key-tile counter (ring stage / score buffer of tile `it`)
             uint32_t ip = 0;            // P@V counter (tile whose probabilities are consumed next)
             for (int h = 0; h < 4; ++h) {
@@ -447,14 +448,18 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                         const uint64_t dpr = make_smem_desc_sw128(smem_u32(sP + pb * 32768 + 16384));
                         const uint64_t dvc = make_smem_desc_sw128(smem_u32(sKV + st * 32768 + 16384));
                         const uint64_t dvr = make_smem_desc_sw128(smem_u32(sKV + st * 32768 + 24576));
+                        (void)dvr;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint32_t acc = (g > 1 || k) ? 1u : 0u;
-                            umma_f16(tmem + 256, dpc + 2 * k, dvc + 2 * k, idesc64, acc);   // O_cc
-                            umma_f16(tmem + 320, dpr + 2 * k, dvc + 2 * k, idesc64, acc);   // O_rc
                             if (need_reg) {
-                                umma_f16(tmem + 384, dpc + 2 * k, dvr + 2 * k, idesc64, acc);  // O_cr
-                                umma_f16(tmem + 448, dpr + 2 * k, dvr + 2 * k, idesc64, acc);  // O_rr
+                                // Vc^T and Vr^T tiles are adjacent in the stage: one N = 128 product per probability
+                                // matrix (the A operand is read from shared memory once instead of twice)
+                                umma_f16(tmem + 256, dpc + 2 * k, dvc + 2 * k, idesc128b, acc);   // O_cc | O_cr
+                                umma_f16(tmem + 384, dpr + 2 * k, dvc + 2 * k, idesc128b, acc);   // O_rc | O_rr
+                            } else {
+                                umma_f16(tmem + 256, dpc + 2 * k, dvc + 2 * k, idesc64, acc);     // O_cc
+                                umma_f16(tmem + 320, dpr + 2 * k, dvc + 2 * k, idesc64, acc);     // O_rc
                             }
                         }
                         umma_commit(&bars.kv_empty[st]);
@@ -538,8 +543,9 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                 uint16_t* dst = reinterpret_cast<uint16_t*>(br == 0 ? a.x_cls : a.x_reg);
                 const int c0 = half * 32;
                 uint32_t oc[32], orr[32];
-                tmem_ld_32x32(lane_base + 256 + br * 128 + c0, oc);
-                tmem_ld_32x32(lane_base + 320 + br * 128 + c0, orr);
+                // TMEM: need_reg  O_cc 256 | O_cr 320 | O_rc 384 | O_rr 448;   else  O_cc 256 | O_rc 320
+                tmem_ld_32x32(lane_base + (need_reg ? 256 + br * 64 : 256) + c0, oc);
+                tmem_ld_32x32(lane_base + (need_reg ? 384 + br * 64 : 320) + c0, orr);
                 tmem_ld_wait();
                 if (q_ok) {
                     uint32_t pk[16];

@@ -248,6 +248,55 @@ __global__ void __launch_bounds__(256) residual_ln2_kernel(const tscd_residual_l
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = min(a.rows_cap, a.n_rows ? __ldg(a.n_rows) : a.rows_cap);
     const int D = a.dim;
+    if (D == 1024) {
+        // TSCD-L width: the row lives in registers (8 float4 per lane, 16-byte loads), no shared memory
+        for (int r = blockIdx.x * 8 + warp; r < n; r += gridDim.x * 8) {
+            const float4* xp = reinterpret_cast<const float4*>(a.x + (int64_t)r * D);
+            const float4* rp = reinterpret_cast<const float4*>(a.r + (int64_t)r * D);
+            float4 v[8];
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 p = __ldg(xp + i * 32 + lane), q = __ldg(rp + i * 32 + lane);
+                v[i] = make_float4(p.x + q.x, p.y + q.y, p.z + q.z, p.w + q.w);
+                s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            }
+            float mean = warp_sumf(s) / D, var = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+                var = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, fmaf(dw, dw, var))));
+            }
+            float rstd = rsqrtf(warp_sumf(var) / D + 1e-5f);
+            s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(a.w_a) + i * 32 + lane), b = __ldg(reinterpret_cast<const float4*>(a.b_a) + i * 32 + lane);
+                v[i] = make_float4((v[i].x - mean) * rstd * w.x + b.x, (v[i].y - mean) * rstd * w.y + b.y,
+                                   (v[i].z - mean) * rstd * w.z + b.z, (v[i].w - mean) * rstd * w.w + b.w);
+                s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            }
+            mean = warp_sumf(s) / D; var = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+                var = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, fmaf(dw, dw, var))));
+            }
+            rstd = rsqrtf(warp_sumf(var) / D + 1e-5f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(a.w_b) + i * 32 + lane), b = __ldg(reinterpret_cast<const float4*>(a.b_b) + i * 32 + lane);
+                const float4 y = make_float4((v[i].x - mean) * rstd * w.x + b.x, (v[i].y - mean) * rstd * w.y + b.y,
+                                             (v[i].z - mean) * rstd * w.z + b.z, (v[i].w - mean) * rstd * w.w + b.w);
+                const int64_t o = (int64_t)r * D + (i * 32 + lane) * 4;
+                if (a.out16) {
+                    *reinterpret_cast<uint2*>(reinterpret_cast<T*>(a.out16) + o) = make_uint2(pack2<T>(y.x, y.y), pack2<T>(y.z, y.w));
+                }
+                if (a.out32) *reinterpret_cast<float4*>(a.out32 + o) = y;
+            }
+        }
+        return;
+    }
     float* buf = ln_smem + warp * D;
     for (int r = blockIdx.x * 8 + warp; r < n; r += gridDim.x * 8) {
         float s = 0.f;
