@@ -70,3 +70,44 @@ def test_cafm_chain_exact_assignments(counts_calls, kmax):
                 err = float((c32[lpos:lpos + nl].cpu() - want).abs().max() / want.abs().max())
                 assert err < (4e-3 if kmax <= 32 else 2e-3), f"call {call} clip {b}: {err}"
             lpos += nl
+
+
+@pytest.mark.parametrize("kmax", [32, 40])
+def test_lap_kernel_tie_rules_vs_scipy(kmax):
+    """tscd_cafm_lap against scipy.optimize.linear_sum_assignment on cost tables FULL of exact ties (small integers,
+    duplicated rows/columns), square and rectangular both ways.  kmax = 32 takes the register-resident solver, kmax = 40
+    (with frames above 32 rows) the shared-memory one; both must reproduce SciPy's assignment, not just its cost."""
+    from scipy.optimize import linear_sum_assignment
+    from tscd_b200 import _lib as L, ops
+    g = torch.Generator().manual_seed(5)
+    shapes = [(1, 1), (1, 7), (7, 1), (5, 5), (30, 30), (32, 32), (30, 17), (17, 30), (32, 3), (3, 32), (29, 31), (31, 29)]
+    if kmax > 32:
+        shapes += [(40, 40), (33, 20), (20, 33), (36, 40)]
+    shapes = shapes * 3
+    nf = len(shapes)
+    cost = torch.zeros(nf, kmax, kmax)
+    for f, (np_, n) in enumerate(shapes):
+        kind = f % 3
+        if kind == 0:
+            c = torch.randint(0, 3, (np_, n), generator=g).float()                 # heavy ties
+        elif kind == 1:
+            c = torch.randint(0, 4, (np_, 1), generator=g).float() + torch.randint(0, 4, (1, n), generator=g).float()   # rank-1: every assignment optimal
+        else:
+            c = (torch.rand(np_, n, generator=g) * 8).round() / 8                  # dyadic values, some ties
+        cost[f, :np_, :n] = c
+    lrow = torch.tensor([0] + list(torch.tensor([n for _, n in shapes]).cumsum(0)), dtype=torch.int32).cuda()
+    ref_n = torch.tensor([np_ for np_, _ in shapes], dtype=torch.int32).cuda()
+    lap_col = torch.full((nf, kmax), -7, dtype=torch.int32).cuda()
+    lap_row = torch.full((nf, kmax), -7, dtype=torch.int32).cuda()
+    ops.call("tscd_cafm_lap", L.CafmLapArgs, num_frames=nf, kmax=kmax, lrow_off=lrow, ref_n=ref_n, cost=cost.cuda().contiguous(),
+             lap_col=lap_col, lap_row=lap_row)
+    torch.cuda.synchronize()
+    for f, (np_, n) in enumerate(shapes):
+        ri, ci = linear_sum_assignment(cost[f, :np_, :n].double().numpy())
+        want_col = [-1] * np_
+        want_row = [-1] * n
+        for r, c in zip(ri.tolist(), ci.tolist()):
+            want_col[r] = c
+            want_row[c] = r
+        assert lap_col[f, :np_].cpu().tolist() == want_col, f"frame {f} shape {(np_, n)}"
+        assert lap_row[f, :n].cpu().tolist() == want_row, f"frame {f} shape {(np_, n)}"

@@ -314,6 +314,71 @@ __device__ void lap_warp(const float* C, int ldc, int n_prev, int n_cur, LapSmem
     }
 }
 
+// Same algorithm for problems with at most 32 rows and columns, with the whole solver state in REGISTERS: lane j owns
+// column j (v, shortest-path cost, predecessor, matched row, its position in SciPy's `remaining` list) and lane i owns
+// row i (u, matched column).  A Dijkstra step is one shared-memory load (the cost), a double-precision warp minimum and
+// one hardware integer reduction for the tie rule -- no shared-memory round trips, no __syncwarp.  Scan order and tie
+// rules are those of lap_warp / SciPy: among equal minima an unassigned column wins, the LAST such column in scan order,
+// otherwise the FIRST minimum; a removed column is replaced by the last one of the list.
+__device__ void lap_warp_fast(const float* C, int ldc, int n_prev, int n_cur, int lane, int* col4row_out, int* row4col_out) {
+    const bool tr = n_cur < n_prev;
+    const int nr = tr ? n_cur : n_prev, nc = tr ? n_prev : n_cur;
+    double v = 0.0, u = 0.0;
+    int row4col = -1, col4row = -1, path = -1;
+    for (int cur = 0; cur < nr; ++cur) {
+        double spc = INFINITY;
+        int pos = lane < nc ? nc - 1 - lane : -1;      // remaining[it] = nc - it - 1
+        bool SC = false, SR = false;
+        double min_val = 0.0;
+        int i = cur, num_rem = nc, sink = -1;
+        while (sink == -1) {
+            if (lane == i) SR = true;
+            const double ui = __shfl_sync(0xffffffffu, u, i);
+            if (pos >= 0) {
+                const double c = (double)(tr ? C[(int64_t)lane * ldc + i] : C[(int64_t)i * ldc + lane]);
+                const double r = min_val + c - ui - v;
+                if (r < spc) { path = i; spc = r; }
+            }
+            const double sj = pos >= 0 ? spc : INFINITY;
+            double m = sj;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (m == INFINITY) { sink = -2; break; }           // infeasible (cannot happen: finite costs)
+            const unsigned tb = (pos >= 0 && sj == m) ? (row4col == -1 ? (unsigned)(kChainMax - 1 - pos) : (0x10000u | (unsigned)pos)) : 0xffffffffu;
+            const unsigned best_tb = __reduce_min_sync(0xffffffffu, tb);
+            const int jwin = __ffs(__ballot_sync(0xffffffffu, tb == best_tb)) - 1;
+            min_val = m;
+            const int rw = __shfl_sync(0xffffffffu, row4col, jwin);
+            if (rw == -1) sink = jwin; else i = rw;
+            // remove jwin from the list: the last element takes its place
+            const int pwin = __shfl_sync(0xffffffffu, pos, jwin);
+            if (pos == num_rem - 1) pos = pwin;
+            if (lane == jwin) { SC = true; pos = -1; }
+            --num_rem;
+        }
+        if (sink < 0) break;
+        // dual updates
+        {
+            const double spc_of_match = __shfl_sync(0xffffffffu, spc, col4row < 0 ? 0 : col4row);
+            if (lane == cur) u += min_val;
+            else if (SR) u += min_val - spc_of_match;
+            if (SC) v -= min_val - spc;
+        }
+        // augment along the alternating path back to `cur`
+        int j = sink;
+        for (;;) {
+            const int r = __shfl_sync(0xffffffffu, path, j);
+            if (lane == j) row4col = r;
+            const int t = __shfl_sync(0xffffffffu, col4row, r);
+            if (lane == r) col4row = j;
+            j = t;
+            if (r == cur) break;
+        }
+    }
+    *col4row_out = col4row;
+    *row4col_out = row4col;
+}
+
 __global__ void __launch_bounds__(32) cafm_lap_kernel(const tscd_cafm_lap_args a) {
     extern __shared__ __align__(16) unsigned char lap_smem[];
     LapSmem& s = *reinterpret_cast<LapSmem*>(lap_smem);
@@ -330,11 +395,24 @@ __global__ void __launch_bounds__(32) cafm_lap_kernel(const tscd_cafm_lap_args a
         C = s.cost_s;
         ldc = n;
     }
-    lap_warp(C, ldc, np, n, s, lane);
-    __syncwarp();
-    const bool tr = n < np;       // lap_warp solves with rows = the smaller side
+    const bool tr = n < np;       // the solvers work with rows = the smaller side
     int32_t* col = a.lap_col + (int64_t)lf * KM;
     int32_t* row = a.lap_row + (int64_t)lf * KM;
+    if (np <= 32 && n <= 32) {
+        int c4r, r4c;
+        lap_warp_fast(C, ldc, np, n, lane, &c4r, &r4c);
+        // lane r holds col4row[r] of solver row r, lane c holds row4col[c] of solver column c
+        if (!tr) {
+            if (lane < np) col[lane] = c4r;
+            if (lane < n) row[lane] = r4c;
+        } else {                  // transposed problem: its rows are the current columns
+            if (lane < np) col[lane] = r4c;
+            if (lane < n) row[lane] = c4r;
+        }
+        return;
+    }
+    lap_warp(C, ldc, np, n, s, lane);
+    __syncwarp();
     if (!tr) {
         for (int r = lane; r < np; r += 32) col[r] = s.col4row[r];
         for (int c = lane; c < n; c += 32) row[c] = s.row4col[c];
