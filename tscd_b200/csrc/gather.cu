@@ -6,6 +6,8 @@
 // torch.max), lane 0 decodes the box, then the warp copies the three D-channel feature rows with 16-byte
 // vector loads when the plane is channel-contiguous (channels_last conv outputs), falling back to strided
 // element loads for NCHW planes.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace tscd {
@@ -115,6 +117,25 @@ __global__ void __launch_bounds__(256) rows_gather_kernel(const tscd_gather_args
             reinterpret_cast<float4*>(args.bank_box)[r] = box;
         }
         const int64_t r = (int64_t)(row0 + j) * args.feat_dim;
+        // fast path (TSCD-L: 256 channel-contiguous 16-bit features, same bank type): the three rows are fetched with
+        // three independent 16-byte loads per lane before anything is stored
+        if (std::is_same<TF, TB>::value && sizeof(TF) == 2 && args.feat_dim == 256 &&
+            args.feat_cls.chan_stride[p.level] == 1 && args.feat_reg.chan_stride[p.level] == 1 && args.feat_edge.chan_stride[p.level] == 1) {
+            const TF* s0 = view_ptr<TF>(args.feat_cls, p.level, frame, p.local) + lane * 8;
+            const TF* s1 = view_ptr<TF>(args.feat_reg, p.level, frame, p.local) + lane * 8;
+            const TF* s2 = view_ptr<TF>(args.feat_edge, p.level, frame, p.local) + lane * 8;
+            if (((reinterpret_cast<uintptr_t>(s0) | reinterpret_cast<uintptr_t>(s1) | reinterpret_cast<uintptr_t>(s2)) & 15) == 0) {
+                const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(s0));
+                const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(s1));
+                const uint4 v2 = __ldg(reinterpret_cast<const uint4*>(s2));
+                {                                      // identical 16-bit types: raw copy
+                    *reinterpret_cast<uint4*>(reinterpret_cast<TB*>(args.bank_cls) + r + lane * 8) = v0;
+                    *reinterpret_cast<uint4*>(reinterpret_cast<TB*>(args.bank_reg) + r + lane * 8) = v1;
+                    *reinterpret_cast<uint4*>(reinterpret_cast<TB*>(args.bank_edge) + r + lane * 8) = v2;
+                }
+                continue;
+            }
+        }
         copy_feature_row<TF, TB>(args.feat_cls, p.level, frame, p.local, args.feat_dim, reinterpret_cast<TB*>(args.bank_cls) + r, lane);
         copy_feature_row<TF, TB>(args.feat_reg, p.level, frame, p.local, args.feat_dim, reinterpret_cast<TB*>(args.bank_reg) + r, lane);
         copy_feature_row<TF, TB>(args.feat_edge, p.level, frame, p.local, args.feat_dim, reinterpret_cast<TB*>(args.bank_edge) + r, lane);
