@@ -999,11 +999,27 @@ __global__ void __launch_bounds__(kFastThreads, 1) cafm_chain_fast_kernel(const 
         float* st_cls = a.st_cls + (int64_t)b * KM * E;
         const float* Rc = a.emb_reg + (int64_t)last_l0 * E;
         const float* Cc = a.emb_cls + (int64_t)last_l0 * E;
-        for (int i = tid; i < n_prev * (E / 4); i += kFastThreads) {
-            const int r = i / (E / 4), c4 = i - r * (E / 4);
-            const int src = s.ord_prev[r];
-            reinterpret_cast<float4*>(st_reg)[(int64_t)r * (E / 4) + c4] = reinterpret_cast<const float4*>(Rc)[(int64_t)src * (E / 4) + c4];
-            reinterpret_cast<float4*>(st_cls)[(int64_t)r * (E / 4) + c4] = reinterpret_cast<const float4*>(Cc)[(int64_t)src * (E / 4) + c4];
+        // 2 x n_prev x 4 KB: batches of four independent 16-byte loads per matrix before the stores (latency-bound otherwise)
+        for (int i0 = 0; i0 < n_prev * (E / 4); i0 += 4 * kFastThreads) {
+            float4 vr[4], vc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kFastThreads + tid;
+                if (i < n_prev * (E / 4)) {
+                    const int r = i / (E / 4), c4 = i - r * (E / 4);
+                    const int src = s.ord_prev[r];
+                    vr[u] = __ldg(reinterpret_cast<const float4*>(Rc) + (int64_t)src * (E / 4) + c4);
+                    vc[u] = __ldg(reinterpret_cast<const float4*>(Cc) + (int64_t)src * (E / 4) + c4);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kFastThreads + tid;
+                if (i < n_prev * (E / 4)) {
+                    reinterpret_cast<float4*>(st_reg)[i] = vr[u];
+                    reinterpret_cast<float4*>(st_cls)[i] = vc[u];
+                }
+            }
         }
         for (int r = tid; r < n_prev; r += kFastThreads) {
             a.st_nreg[(int64_t)b * KM + r] = a.norm_reg[last_l0 + s.ord_prev[r]];
