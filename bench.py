@@ -367,6 +367,19 @@ def main():
     if work is not None:
         ach = work / (avg_ms / 1e3) / (1e9 if bound == "hbm" else 1e12)
         roof["achieved"], roof["frac"] = ach, ach / roof["peak"]
+    # DRAM traffic per launch of the dominant kernel from the committed `ncu` capture of the same workload
+    # (profiles/traffic_r1.json, made by tools/profile_step.py --clips 64 under ncu); null for other batch sizes
+    tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    if os.path.exists(tpath) and B == 64 and nsp == 1:
+        names = {"tscd_linear": "gemm_tn_kernel", "tscd_attn_round2": "attn_round2_kernel", "tscd_attn_pv": "attn_pv_kernel",
+                 "tscd_attn_prep": "attn_prep_kernel", "tscd_select": "select_kernel|classmax_kernel", "tscd_nms": "nms_",
+                 "tscd_gather": "rows_gather_kernel", "tscd_cafm_chain": "cafm_chain", "tscd_cafm_cost": "cafm_cost", "tscd_cafm_lap": "cafm_lap"}
+        pats = names.get(top, top).split("|")
+        tj = json.load(open(tpath))
+        sel = [v for k, v in tj.items() if any(p_ in k for p_ in pats)]
+        if sel:
+            roof["traffic"] = sum(v["dram_bytes_per_launch"] * v["launches"] for v in sel) / max(1, calls.get(top, 1))
+            roof["traffic_source"] = "profiles/traffic_r1.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, per C-ABI call)"
     line = {"metric": "clip-frames/sec of TSCD aggregation stage", "value": value, "unit": "clip-frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
