@@ -74,8 +74,10 @@ __device__ __forceinline__ float head_sumsq(const float (&v)[8]) {
 // One CTA per (64 keys, clip); one warp per bank row, lane = 8 consecutive channels (16-byte loads / stores), all four
 // heads of a row normalised at once (8 lanes per head).  The un-normalised v rows are staged in shared memory and
 // written out transposed (V^T: 64 consecutive keys = 128 bytes per channel row).
+constexpr int kPrepThreads = 384;     // 12 warps x 3 CTAs/SM (67.6 KB of staging each): 36 resident warps instead of 24
+
 template <typename T>
-__global__ void __launch_bounds__(256) attn_prep_kernel(const tscd_attn_prep_args a) {
+__global__ void __launch_bounds__(kPrepThreads) attn_prep_kernel(const tscd_attn_prep_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* tile_c = reinterpret_cast<T*>(smem_raw);        // [64 keys][kPrepRowPitch]
     T* tile_r = tile_c + 64 * kPrepRowPitch;
@@ -90,9 +92,10 @@ __global__ void __launch_bounds__(256) attn_prep_kernel(const tscd_attn_prep_arg
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = lane * 8;
 
+    constexpr int NW = kPrepThreads / 32;
 #pragma unroll 2
-    for (int i = 0; i < 8; ++i) {
-        const int r = k0 + warp + 8 * i;       // key index within the clip
+    for (int rr = warp; rr < 64; rr += NW) {
+        const int r = k0 + rr;                 // key index within the clip
         const int row = s0 + r;                // bank row
         const bool valid = r < n_clip;
         if (valid) {                           // frame of the row: lanes test one frame each
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(256) attn_prep_kernel(const tscd_attn_prep_arg
     }
     __syncthreads();
     // transposed store: channel ch -> 64 consecutive keys (128 bytes); lane = two consecutive keys
-    for (int ch = warp; ch < 256; ch += 8) {
+    for (int ch = warp; ch < 256; ch += NW) {
 #pragma unroll
         for (int br = 0; br < 2; ++br) {
             const uint16_t* tile = reinterpret_cast<const uint16_t*>(br == 0 ? tile_c : tile_r);
@@ -927,10 +930,10 @@ extern "C" int tscd_attn_prep(const tscd_attn_prep_args* a, void* stream) {
     const size_t smem = 2 * 64 * kPrepRowPitch * 2;
     if (a->lay.dtype == TSCD_F16) {
         if (cudaFuncSetAttribute(attn_prep_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
-        attn_prep_kernel<__half><<<grid, 256, smem, st>>>(*a);
+        attn_prep_kernel<__half><<<grid, kPrepThreads, smem, st>>>(*a);
     } else {
         if (cudaFuncSetAttribute(attn_prep_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
-        attn_prep_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(*a);
+        attn_prep_kernel<__nv_bfloat16><<<grid, kPrepThreads, smem, st>>>(*a);
     }
     TSCD_CUDA_CHECK_LAUNCH();
     return TSCD_OK;
