@@ -131,3 +131,13 @@ def test_stage_mode_a_topk_nms():
                     sel_kw=dict(pre_k=750, top_k=30, nms_thresh=0.75),
                     o_sel_kw=dict(nms_thre=0.75, pre_k=750, top_k=30), seeds=[7], calls=1)
     _check(rep)
+
+
+def test_stage_full_size_baseline_config():
+    """BASELINE.json configs[1] at full size: one 32-frame clip (8 local + 24 global) at 576x576 (6804 anchors), 25
+    classes, top-750 -> NMS 0.75 -> 30 proposals/frame, through every kernel of the stage (split K1, top-K NMS prefix
+    path, tcgen05 attention, smem/mma.sync CAFM chain, register LSAP, mma.sync TaskAligned, per-class final NMS)."""
+    rep = _run_case("A", B=1, F=32, Lf=8, hw=[(72, 72), (36, 36), (18, 18)], C=25,
+                    sel_kw=dict(pre_k=750, top_k=30, nms_thresh=0.75),
+                    o_sel_kw=dict(nms_thre=0.75, pre_k=750, top_k=30), seeds=[2024], calls=1)
+    _check(rep)
