@@ -150,6 +150,15 @@ typedef struct {
 } tscd_gather_args;
 int tscd_gather(const tscd_gather_args* args, void* stream);
 
+/* Offsets of the local rows (the first L frames of each clip; tscd_head.py:986-1005 concatenates them first):
+ * lrow_off[b*L + f] = sum of sel_count over the local frames before (b, f); lrow_off[B*L] = total. */
+typedef struct {
+    int32_t B, F, L;
+    const int32_t* sel_count;   /* [B*F] */
+    int32_t* lrow_off;          /* [B*L+1] */
+} tscd_local_offsets_args;
+int tscd_local_offsets(const tscd_local_offsets_args* args, void* stream);
+
 /* ---- Linear layer (tcgen05 GEMM) --------------------------------------------------------------------------
  * y[M,N] = x[M,K] * w[N,K]^T + bias.  Replaces every F.linear on the path (post_trans.py:613-618,687-689,
  * 1159-1161; tscd_matching.py:37-39,165-167,756; tscd_head.py:507,515-520).  x / w are fp16 or bf16 with K

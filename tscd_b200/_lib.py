@@ -118,6 +118,10 @@ class CafmLapArgs(C.Structure):
     _fields_ = _fields("num_frames:i kmax:i lrow_off:p ref_n:p cost:p lap_col:p lap_row:p")
 
 
+class LocalOffsetsArgs(C.Structure):
+    _fields_ = _fields("B:i F:i L:i sel_count:p lrow_off:p")
+
+
 class FrameAttentionArgs(C.Structure):
     _fields_ = _fields("num_frames:i heads:i head_dim:i in_dtype:i lrow_off:p q:p ldq:i k:p ldk:i v:p ldv:i out:p ldo:i")
 
@@ -147,6 +151,7 @@ SYMBOLS = [
     ("tscd_select", C.c_int, [C.POINTER(SelectArgs), C.c_void_p]),
     ("tscd_nms", C.c_int, [C.POINTER(NmsArgs), C.c_void_p]),
     ("tscd_gather", C.c_int, [C.POINTER(GatherArgs), C.c_void_p]),
+    ("tscd_local_offsets", C.c_int, [C.POINTER(LocalOffsetsArgs), C.c_void_p]),
     ("tscd_linear", C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
     ("tscd_attn_prep", C.c_int, [C.POINTER(AttnPrepArgs), C.c_void_p]),
     ("tscd_attn_pv", C.c_int, [C.POINTER(AttnPvArgs), C.c_void_p]),

@@ -35,12 +35,13 @@ class MCAWeights:
 def make_layout(sel_count: torch.Tensor, B: int, F: int, L: int, row_cap: int, loc_cap: int, nk_pitch: int,
                 dtype=torch.float16, row_off: Optional[torch.Tensor] = None) -> ops.AttnLayoutT:
     """Device-side prefix offsets from per-frame counts (torch ops on the current stream; no sync)."""
-    cnt = sel_count.view(B, F).to(torch.int32)
     if row_off is None:
+        cnt = sel_count.view(B, F).to(torch.int32)
         row_off = torch.zeros(B * F + 1, dtype=torch.int32, device=sel_count.device)
         row_off[1:] = torch.cumsum(cnt.reshape(-1), 0)
-    lrow_off = torch.zeros(B * L + 1, dtype=torch.int32, device=sel_count.device)
-    lrow_off[1:] = torch.cumsum(cnt[:, :L].reshape(-1), 0)
+    lrow_off = torch.empty(B * L + 1, dtype=torch.int32, device=sel_count.device)
+    assert sel_count.dtype == torch.int32 and sel_count.is_contiguous()
+    ops.call("tscd_local_offsets", ops.L.LocalOffsetsArgs, B=B, F=F, L=L, sel_count=sel_count, lrow_off=lrow_off)
     return ops.AttnLayoutT(B, F, L, row_off, lrow_off, row_cap, loc_cap, nk_pitch, dtype)
 
 

@@ -153,6 +153,29 @@ static int launch_gather_tb(const tscd_gather_args* a, dim3 grid, cudaStream_t s
     return TSCD_OK;
 }
 
+// Prefix offsets of the LOCAL rows (first L frames of every clip) from the per-frame counts: lrow_off[b*L + f].
+// One CTA; replaces a handful of tiny framework kernels (slice, cumsum, copy) on the critical path.
+__global__ void local_offsets_kernel(int B, int F, int L, const int32_t* sel_count, int32_t* lrow_off) {
+    __shared__ int scratch[40];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int n = B * L;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        int c = 0;
+        if (i < n) { const int b = i / L, f = i - b * L; c = sel_count[b * F + f]; }
+        int tot;
+        const int ex = block_excl_scan(c, scratch, &tot);
+        const int carry = carry_s;
+        if (i < n) lrow_off[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) lrow_off[n] = carry_s;
+}
+
 }  // namespace tscd
 
 extern "C" int tscd_gather(const tscd_gather_args* a, void* stream) {
@@ -176,6 +199,14 @@ extern "C" int tscd_gather(const tscd_gather_args* a, void* stream) {
         default: return TSCD_ERR_UNSUPPORTED;
     }
     if (rc != TSCD_OK) return rc;
+    TSCD_CUDA_CHECK_LAUNCH();
+    return TSCD_OK;
+}
+
+extern "C" int tscd_local_offsets(const tscd_local_offsets_args* a, void* stream) {
+    using namespace tscd;
+    if (!a || a->B <= 0 || a->F <= 0 || a->L <= 0 || a->L > a->F || !a->sel_count || !a->lrow_off) return TSCD_ERR_INVALID_ARG;
+    local_offsets_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a->B, a->F, a->L, a->sel_count, a->lrow_off);
     TSCD_CUDA_CHECK_LAUNCH();
     return TSCD_OK;
 }

@@ -94,6 +94,8 @@ class AggregationStage:
         self.device = device
         self._side = {}
         self._part_streams = []
+        self._default_state = {}
+        self._zero_resume = {}
 
     def _side_stream(self):
         """Side stream of the classification branch, one per launching stream (concurrent sub-batches must not share it)."""
@@ -275,18 +277,18 @@ class AggregationStage:
     def capture_fn(self, fn, warmup: int = 2):
         """Capture an arbitrary launch sequence of this stage (e.g. forward_concurrent over fixed input buffers) into a
         CUDA graph.  Returns (graph, value returned by fn during capture)."""
-        s = torch.cuda.Stream(device=self.device)
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            for _ in range(warmup):
-                fn()
-        torch.cuda.current_stream().wait_stream(s)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        # capture on a high-priority stream: the stage's own side streams (classification branch) have default priority,
-        # so whenever both have blocks pending the critical path (agg_iou -> CAFM -> TaskAligned) is scheduled first
+        # warm up and capture on the SAME high-priority stream (lazy per-stream state -- side streams, default CAFM memory --
+        # is then created before the capture starts).  High priority: the stage's own side streams (classification branch)
+        # have default priority, so whenever both have blocks pending the critical path (agg_iou -> CAFM -> TaskAligned)
+        # is scheduled first.
         hp = torch.cuda.Stream(device=self.device, priority=-1)
         hp.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(hp):
+            for _ in range(warmup):
+                fn()
+        torch.cuda.current_stream().wait_stream(hp)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=hp):
             out = fn()
         return graph, out
@@ -334,10 +336,17 @@ class AggregationStage:
                     t.record_stream(main)
 
         # ---- K5: CAFM --------------------------------------------------------------------------------
+        # Default memory: one CAFMState per (clips, kmax) owned by the stage object, like the reference keeps its memory on
+        # the module (tscd_matching.py:708-715).  With resume = 0 the chain never reads it, so nothing is cleared per call.
         if state is None:
-            state = CAFMState(B, kmax, D, dev)
+            key = (B, kmax, torch.cuda.current_stream().cuda_stream)     # one per launching stream (concurrent sub-batches)
+            if key not in self._default_state:
+                self._default_state[key] = CAFMState(B, kmax, D, dev)
+            state = self._default_state[key]
         if resume is None:
-            resume = torch.zeros(B, dtype=torch.int32, device=dev)
+            if B not in self._zero_resume:
+                self._zero_resume[B] = torch.zeros(B, dtype=torch.int32, device=dev)
+            resume = self._zero_resume[B]
         if before_cafm is not None:
             before_cafm(state)
         cafm16, cafm32, perm, te32 = self.run_cafm(lay, bank_reg, bank_edge, iou_reg32, iou_cls32, time_embedding, kmax,
