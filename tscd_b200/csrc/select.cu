@@ -333,10 +333,31 @@ __global__ void __launch_bounds__(kSelThreads, PRE ? 3 : 2) select_kernel(const 
         const int a = sel[i];
         AnchorPos p = anchor_pos(an, a);
         float score;
+        int cls_id = 0;
         if (modeB) {
             score = ord2f(keys[a]);
+            cls_id = (int)cls_s[a];
         } else {
-            float conf = PRE ? ldf(reinterpret_cast<const T*>(args.ws_conf) + (int64_t)frame * args.ws_pitch + a) : conf_s[a];
+            float conf;
+            if (!PRE) {
+                conf = conf_s[a];
+                cls_id = (int)cls_s[a];
+            } else if (args.ws_conf) {       // class max of every anchor was streamed by classmax_kernel
+                conf = ldf(reinterpret_cast<const T*>(args.ws_conf) + (int64_t)frame * args.ws_pitch + a);
+                cls_id = (int)args.ws_cls[(int64_t)frame * args.ws_pitch + a];
+            } else {                         // class-contiguous (channels_last) logits: max over the survivor's own row only
+                const T* c = view_ptr<T>(args.cls, p.level, frame, p.local);
+                const int64_t ccs = args.cls.chan_stride[p.level];
+                conf = -INFINITY;
+                for (int k0 = 0; k0 < C; k0 += 8) {                   // 8 independent loads in flight
+                    float x[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) x[u] = k0 + u < C ? ldf(c + (k0 + u) * ccs) : -INFINITY;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (x[u] > conf) { conf = x[u]; cls_id = k0 + u; }   // first maximum wins (torch.max)
+                }
+            }
             if (sig) conf = sigmoidf_ref(conf);
             score = __fmul_rn(ord2f(keys[a]), conf);                  // post_process.py:512  obj * class_conf
         }
@@ -344,7 +365,7 @@ __global__ void __launch_bounds__(kSelThreads, PRE ? 3 : 2) select_kernel(const 
         args.cand_idx[base + i] = a;
         reinterpret_cast<float4*>(args.cand_box)[base + i] = box;
         args.cand_score[base + i] = score;
-        args.cand_cls[base + i] = PRE ? (int)args.ws_cls[(int64_t)frame * args.ws_pitch + a] : (int)cls_s[a];
+        args.cand_cls[base + i] = cls_id;
     }
     if (threadIdx.x == 0) args.cand_count[frame] = n_sel;
 }
@@ -368,7 +389,12 @@ extern "C" int tscd_select(const tscd_select_args* a, void* stream) {
     const int selcap = ((A < a->cand_cap ? A : a->cand_cap) + 3) & ~3;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // mode A with a workspace and planar (anchor-contiguous) class planes: class max as a separate streaming kernel
-    bool pre = a->mode == 0 && a->ws_conf && a->ws_cls && a->ws_pitch >= A && (a->head_dtype == TSCD_F16 || a->head_dtype == TSCD_F32);
+    // mode A needs the class max of the ~pre_k survivors only.  Class-contiguous logits (channels_last conv outputs: an
+    // anchor's C logits are one 2C-byte row) are therefore read for the survivors alone -- 89 % of the class logits never
+    // leave HBM; anchor-contiguous (NCHW) planes cannot be gathered sector-efficiently and are streamed by classmax_kernel.
+    bool late = a->mode == 0;
+    for (int l = 0; late && l < a->anchors.num_levels; ++l) late = a->cls.chan_stride[l] == 1;
+    bool pre = !late && a->mode == 0 && a->ws_conf && a->ws_cls && a->ws_pitch >= A && (a->head_dtype == TSCD_F16 || a->head_dtype == TSCD_F32);
     const int vmax = a->head_dtype == TSCD_F16 ? 8 : 4, esz = a->head_dtype == TSCD_F16 ? 2 : 4;
     int groups = 0;
     for (int l = 0; pre && l < a->anchors.num_levels; ++l) {
@@ -378,7 +404,8 @@ extern "C" int tscd_select(const tscd_select_args* a, void* stream) {
     }
     (void)vmax;
     (void)esz;
-    const size_t smem = (size_t)((A + 3) & ~3) * (pre ? 4 : 8) + (size_t)selcap * 4 + 8 + (size_t)n64 * 8 + (pre ? (size_t)2 * ((A + 15) & ~15) : (size_t)((A + 15) & ~15));
+    const bool light = pre || late;          // select_kernel<T, true>: no class data in shared memory
+    const size_t smem = (size_t)((A + 3) & ~3) * (light ? 4 : 8) + (size_t)selcap * 4 + 8 + (size_t)n64 * 8 + (light ? (size_t)2 * ((A + 15) & ~15) : (size_t)((A + 15) & ~15));
     if (smem > 200 * 1024) return TSCD_ERR_CAPACITY;
     cudaError_t e;
     if (pre) {
@@ -393,10 +420,13 @@ extern "C" int tscd_select(const tscd_select_args* a, void* stream) {
         if (e != cudaSuccess) return TSCD_ERR_CUDA;                                                                  \
         select_kernel<TT, PP><<<a->num_frames, kSelThreads, smem, st>>>(*a, n64);                                    \
     } while (0)
+    tscd_select_args la = *a;                 // late path: no workspace reads
+    if (late) { la.ws_conf = nullptr; la.ws_cls = nullptr; }
+    a = &la;
     if (a->head_dtype == TSCD_F32) {
-        if (pre) TSCD_LAUNCH_SELECT(float, true); else TSCD_LAUNCH_SELECT(float, false);
+        if (light) TSCD_LAUNCH_SELECT(float, true); else TSCD_LAUNCH_SELECT(float, false);
     } else if (a->head_dtype == TSCD_F16) {
-        if (pre) TSCD_LAUNCH_SELECT(__half, true); else TSCD_LAUNCH_SELECT(__half, false);
+        if (light) TSCD_LAUNCH_SELECT(__half, true); else TSCD_LAUNCH_SELECT(__half, false);
     } else {
         return TSCD_ERR_UNSUPPORTED;
     }

@@ -118,7 +118,8 @@ def select(head: HeadViews, mode: str, pre_k: int = 750, conf_thresh: float = 0.
     a.anchors, a.reg, a.obj, a.cls = head.anchors.to_c(), head.reg, head.obj, head.cls
     a.cand_idx, a.cand_box, a.cand_score = _p(out["idx"]), _p(out["box"]), _p(out["score"])
     a.cand_cls, a.cand_count = _p(out["cls"]), _p(out["count"])
-    if mode == "A":          # workspace of the streaming class-max kernel (K1 runs as two kernels for planar layouts)
+    class_contiguous = all(head.cls.chan_stride[i] == 1 for i in range(len(head.anchors.hw)))
+    if mode == "A" and not class_contiguous:   # workspace of the streaming class-max kernel (K1 = two kernels for NCHW planes)
         pitch = (A + 15) // 16 * 16
         ws_conf = torch.empty(Fn, pitch, dtype=head.dtype, device=dev)
         ws_cls = torch.empty(Fn, pitch, dtype=torch.uint8, device=dev)

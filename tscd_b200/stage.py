@@ -175,9 +175,10 @@ class AggregationStage:
         if getattr(self, "_copy", None) is None:
             self._copy = torch.cuda.Stream(device=dev)
         cp = self._copy
-        key = (B, F, tuple(tuple(x) for x in hw), host["cls"][0].shape[1], host["cls"][0].dtype)
+        key = (B, F, tuple(tuple(x) for x in hw), host["cls"][0].shape[1], host["cls"][0].dtype, host["cls"][0].stride())
         if getattr(self, "_stage_key", None) != key:           # device staging for the head logits, reused across calls
-            self._stage_buf = {k: [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in host[k]] for k in ("reg", "obj", "cls")}
+            self._stage_buf = {k: [torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, device=dev) for t in host[k]]
+                               for k in ("reg", "obj", "cls")}      # same strides: the H2D copy is a plain memcpy
             self._stage_key = key
         dbuf = self._stage_buf
         te = time_embedding
