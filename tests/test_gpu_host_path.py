@@ -10,29 +10,31 @@ F, LF, C, D = 8, 3, 7, 256
 HW = [(24, 24), (12, 12), (6, 6)]
 
 
-def _synth(B, seed):
+def _synth(B, seed, logits_cl=False):
+    fmt = torch.channels_last if logits_cl else torch.contiguous_format
     g = torch.Generator(device="cuda").manual_seed(seed)
     n = B * F
     out = dict(reg=[], obj=[], cls=[], f_cls=[], f_reg=[], f_edge=[])
     for (h, w) in HW:
         xy = torch.rand(n, 2, h, w, generator=g, device="cuda") * 2 - 0.5
         wh = torch.randn(n, 2, h, w, generator=g, device="cuda") * 0.7 + 1.0
-        out["reg"].append(torch.cat([xy, wh], 1).half())
-        out["obj"].append((torch.randn(n, 1, h, w, generator=g, device="cuda") * 2 - 3).half())
-        out["cls"].append((torch.randn(n, C, h, w, generator=g, device="cuda") * 2 - 3).half())
+        out["reg"].append(torch.cat([xy, wh], 1).half().contiguous(memory_format=fmt))
+        out["obj"].append((torch.randn(n, 1, h, w, generator=g, device="cuda") * 2 - 3).half().contiguous(memory_format=fmt))
+        out["cls"].append((torch.randn(n, C, h, w, generator=g, device="cuda") * 2 - 3).half().contiguous(memory_format=fmt))
         for k in ("f_cls", "f_reg", "f_edge"):
             out[k].append(torch.randn(n, D, h, w, generator=g, device="cuda").half().contiguous(memory_format=torch.channels_last))
     return out
 
 
+@pytest.mark.parametrize("logits_cl", [False, True])
 @pytest.mark.parametrize("B,chunk", [(5, 2), (4, 4)])
-def test_forward_host_equals_forward(B, chunk):
+def test_forward_host_equals_forward(B, chunk, logits_cl):
     from tscd_b200 import ops, selection, stage, weights
     cfg = stage.StageConfig(num_classes=C, selection=selection.SelectionConfig(mode="A", pre_k=200, top_k=12, nms_thresh=0.75))
     st = stage.AggregationStage(cfg, weights.random_state_dict(C, D, seed=5))
-    dev = _synth(B, 31)
+    dev = _synth(B, 31, logits_cl)
     host = {k: [torch.empty(t.shape, dtype=t.dtype, pin_memory=True,
-                                memory_format=torch.channels_last if k.startswith("f_") else torch.contiguous_format).copy_(t) for t in v]
+                                memory_format=torch.channels_last if (k.startswith("f_") or logits_cl) else torch.contiguous_format).copy_(t) for t in v]
         for k, v in dev.items()}
     te = torch.cat([weights.timing_signal_1d(torch.arange(LF), 256)] * B, 0)
 
@@ -67,6 +69,14 @@ def test_forward_host_equals_forward(B, chunk):
         feat_bytes = sum(t.numel() * t.element_size() for k in ("f_cls", "f_reg", "f_edge") for t in host[k])
         assert head_bytes < h2d < head_bytes + feat_bytes // 4      # only the kept rows of the feature planes crossed PCIe
         assert d2h > 0
+    if logits_cl:
+        # optional mode: only the objectness plane is copied, K1 / K3 read the survivors' class / regression rows in place
+        res2, ori2, h2d_zc, _ = st.forward_host(host, HW, te.pin_memory(), B, F, LF, chunk_clips=chunk, zero_copy_logits=True)
+        assert h2d_zc < h2d
+        for gr, go, g2, o2 in zip(res, res_ori, res2, ori2):
+            assert (gr is None) == (g2 is None)
+            if gr is not None:
+                assert torch.equal(gr, g2) and torch.equal(go, o2)
 
 
 def test_forward_host_rejects_pageable_memory():

@@ -311,10 +311,26 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const tscd_nms_args ar
             n_work = tot;
             block_sort_desc64_dyn<unsigned long long>(skey, n_work, kPartialCap);
         } else {
-            for (int i = threadIdx.x; i < n; i += blockDim.x)
-                skey[i] = ((unsigned long long)f2ord(gscore[i]) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
-            __syncthreads();
-            block_sort_desc64_dyn<unsigned long long>(skey, n, smem_cap);
+            if (n <= 32) {
+                // tiny frames (the unrefined "ori" rows: <= 30 candidates): one warp sorts in registers
+                if (threadIdx.x < 32) {
+                    const int lane = threadIdx.x;
+                    unsigned long long v = lane < n ? (((unsigned long long)f2ord(gscore[lane]) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)lane)) : 0ull;
+                    for (int k = 2; k <= 32; k <<= 1)
+                        for (int j = k >> 1; j > 0; j >>= 1) {
+                            const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, j);
+                            const bool keep_max = (((lane & j) == 0) == ((lane & k) == 0));
+                            v = keep_max ? (v > o ? v : o) : (v < o ? v : o);
+                        }
+                    skey[lane] = v;
+                }
+                __syncthreads();
+            } else {
+                for (int i = threadIdx.x; i < n; i += blockDim.x)
+                    skey[i] = ((unsigned long long)f2ord(gscore[i]) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+                __syncthreads();
+                block_sort_desc64_dyn<unsigned long long>(skey, n, smem_cap);
+            }
         }
 
         for (int r = threadIdx.x; r < n_work; r += blockDim.x) {
