@@ -141,3 +141,17 @@ def test_stage_full_size_baseline_config():
                     sel_kw=dict(pre_k=750, top_k=30, nms_thresh=0.75),
                     o_sel_kw=dict(nms_thre=0.75, pre_k=750, top_k=30), seeds=[2024], calls=1)
     _check(rep)
+
+
+def test_stage_bf16_operands():
+    """StageConfig.dtype = bfloat16 (tensor-core operands bf16 instead of fp16): every kernel has a bf16 instantiation.
+    bf16 keeps 8 mantissa bits, so the float tolerance is 8x looser and near-threshold decisions (0.75 / 0.99 cosine masks,
+    Hungarian near-ties, 0.001 score filters) may flip: only a loose detection agreement is required."""
+    rep = _run_case("A", B=2, F=8, Lf=2, hw=[(40, 40), (20, 20), (10, 10)], C=25,
+                    sel_kw=dict(pre_k=750, top_k=30, nms_thresh=0.75),
+                    o_sel_kw=dict(nms_thre=0.75, pre_k=750, top_k=30), seeds=[7], calls=1, dtype=torch.bfloat16)
+    for call, b, errs, perm_ok, match, tot in rep:
+        print(f"bf16 call {call} clip {b}: perm_ok={perm_ok} dets {match}/{tot} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
+        for k, v in errs.items():
+            assert v < 5e-2, f"{k} rel err {v}"
+        assert tot == 0 or match / tot >= 0.85
