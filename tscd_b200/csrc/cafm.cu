@@ -35,25 +35,54 @@ __device__ __forceinline__ float se_gate(float a, float b, const float* w1, cons
     return a * s0 + b * s1;
 }
 
-// SE gate of 8 (a, b) pairs at once: the 32 hidden units' weights are read once per 8 elements (one LDS.128 each).
+// Packed fp32 arithmetic (Blackwell FFMA2 / FMUL2: two IEEE round-to-nearest fp32 operations per instruction).  The SE
+// gate is bound by the FMA pipe; pairing two elements per instruction halves its instruction count with bit-identical
+// results (each half is an ordinary fp32 fma / mul).
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// SE gate of 8 (a, b) pairs at once: the 32 hidden units' weights are read once per 8 elements (one LDS.128 each);
+// per hidden unit and element:  h = relu(w1b * b + w1a * a);  o0 += w2[0] * h;  o1 += w2[1] * h  (same order as se_gate)
 __device__ __forceinline__ void se_gate8(const float (&a)[8], const float (&b)[8], const float4* se, float (&out)[8]) {
-    float o0[8], o1[8];
+    unsigned long long A2[4], B2[4], o0[4], o1[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { o0[e] = 0.f; o1[e] = 0.f; }
+    for (int p = 0; p < 4; ++p) { A2[p] = pk2(a[2 * p], a[2 * p + 1]); B2[p] = pk2(b[2 * p], b[2 * p + 1]); o0[p] = 0ull; o1[p] = 0ull; }
 #pragma unroll 4
     for (int j = 0; j < 32; ++j) {
         const float4 w = se[j];
+        const unsigned long long wx = pk2(w.x, w.x), wy = pk2(w.y, w.y), wz = pk2(w.z, w.z), ww = pk2(w.w, w.w);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float h = fmaxf(0.f, fmaf(w.y, b[e], w.x * a[e]));
-            o0[e] = fmaf(w.z, h, o0[e]);
-            o1[e] = fmaf(w.w, h, o1[e]);
+        for (int p = 0; p < 4; ++p) {
+            float h0, h1;
+            upk2(fma2(wy, B2[p], mul2(wx, A2[p])), h0, h1);
+            const unsigned long long h = pk2(fmaxf(0.f, h0), fmaxf(0.f, h1));
+            o0[p] = fma2(wz, h, o0[p]);
+            o1[p] = fma2(ww, h, o1[p]);
         }
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const float s0 = 1.f / (1.f + expf(-o0[e])), s1 = 1.f / (1.f + expf(-o1[e]));
-        out[e] = a[e] * s0 + b[e] * s1;
+    for (int p = 0; p < 4; ++p) {
+        float x0, x1, y0, y1;
+        upk2(o0[p], x0, x1);
+        upk2(o1[p], y0, y1);
+        const float s00 = 1.f / (1.f + expf(-x0)), s01 = 1.f / (1.f + expf(-x1));
+        const float s10 = 1.f / (1.f + expf(-y0)), s11 = 1.f / (1.f + expf(-y1));
+        out[2 * p] = a[2 * p] * s00 + b[2 * p] * s10;
+        out[2 * p + 1] = a[2 * p + 1] * s01 + b[2 * p + 1] * s11;
     }
 }
 
