@@ -225,25 +225,30 @@ __global__ void __launch_bounds__(256) cafm_cost_kernel(const tscd_cafm_cost_arg
         }
         __syncthreads();
         if (s + 1 < 16) fetch(s + 1);
-        float x[16];
+        // packed fp32 FMAs (FFMA2): each accumulator pair holds the partial sums of the even / odd dims of its dot product
+        unsigned long long x2[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = 0.f;
+        for (int i = 0; i < 16; ++i) x2[i] = 0ull;
 #pragma unroll 2
         for (int d4 = grp * 8; d4 < grp * 8 + 8; ++d4) {
-            float4 p4[4], q4[4];
+            ulonglong2 p4[4], q4[4];          // a float4 viewed as two packed float pairs (x,y) (z,w)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                p4[i] = reinterpret_cast<const float4*>(tileA[ty + 8 * i])[d4];
-                q4[i] = reinterpret_cast<const float4*>(tileB[tx + 8 * i])[d4];
+                p4[i] = reinterpret_cast<const ulonglong2*>(tileA[ty + 8 * i])[d4];
+                q4[i] = reinterpret_cast<const ulonglong2*>(tileB[tx + 8 * i])[d4];
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    x[i * 4 + j] = fmaf(p4[i].x, q4[j].x, fmaf(p4[i].y, q4[j].y, fmaf(p4[i].z, q4[j].z, fmaf(p4[i].w, q4[j].w, x[i * 4 + j]))));
+                    x2[i * 4 + j] = fma2(p4[i].x, q4[j].x, fma2(p4[i].y, q4[j].y, x2[i * 4 + j]));
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { if (s < 8) accR[i] += x[i]; else accC[i] += x[i]; }
+        for (int i = 0; i < 16; ++i) {
+            float lo, hi;
+            upk2(x2[i], lo, hi);
+            if (s < 8) accR[i] += lo + hi; else accC[i] += lo + hi;
+        }
     }
     // reduce the four dim-groups through shared memory (the tiles are free now): red[grp][which][row][col]
     __syncthreads();
