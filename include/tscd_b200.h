@@ -223,6 +223,37 @@ typedef struct {
 } tscd_attn_prep_args;
 int tscd_attn_prep(const tscd_attn_prep_args* args, void* stream);
 
+/* Fused q|k|v projection of one branch (replaces tscd_linear + tscd_attn_prep for that branch): the tcgen05 GEMM
+ * x[rows,256] @ w[768,256]^T whose epilogue applies what tscd_attn_prep would do to its output -- per-head L2
+ * normalisation of q (query rows only), k (x scale [x key_score]) and v, the raw-v rows of the queries (x_ori) and the
+ * transposed raw v (V^T) -- straight from the fp32 accumulators; the [rows,768] q|k|v intermediate never exists.
+ * row_meta / row_frame come from tscd_attn_rowmeta, which also zero-fills the padding columns of V^T. */
+typedef struct {
+    tscd_attn_layout lay;
+    int32_t rows;             /* capacity rows of x (row_cap) */
+    const int32_t* m_dev;     /* device count of valid bank rows */
+    const void* x;            /* [rows, ldx] bank features (lay.dtype) */
+    int64_t ldx;
+    const void* w;            /* [768,256]: Wq | Wk | Wv */
+    const int32_t* row_meta;  /* [rows] (clip << 16) | key index */
+    const float* key_score;   /* [rows] or NULL (reg branch) */
+    float scale;              /* 25 */
+    void *qn, *kn, *vn;       /* [rows,256] */
+    void* vt;                 /* [B*256, nk_pitch] */
+    void* xori;               /* [loc_cap, ld_xori] or NULL */
+    int32_t ld_xori;
+} tscd_qkv_project_args;
+int tscd_qkv_project(const tscd_qkv_project_args* args, void* stream);
+
+typedef struct {
+    tscd_attn_layout lay;
+    int32_t* row_frame;       /* [row_cap] frame index (within its clip) of every bank row */
+    int32_t* row_meta;        /* [row_cap] (clip << 16) | key index within the clip */
+    void* vt_cls;             /* [B*256, nk_pitch]: columns [n_clip, round-up-128) of every clip are zero-filled */
+    void* vt_reg;             /* same, may be NULL */
+} tscd_attn_rowmeta_args;
+int tscd_attn_rowmeta(const tscd_attn_rowmeta_args* args, void* stream);
+
 typedef struct {
     tscd_attn_layout lay;
     const void *qn_cls, *kn_cls, *qn_reg, *kn_reg;

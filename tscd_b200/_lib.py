@@ -72,6 +72,18 @@ class AttnPrepArgs(C.Structure):
                 ("ld_xori", C.c_int32), ("row_frame", C.c_void_p)]
 
 
+class QkvProjectArgs(C.Structure):
+    _fields_ = [("lay", AttnLayout), ("rows", C.c_int32), ("m_dev", C.c_void_p), ("x", C.c_void_p), ("ldx", C.c_int64),
+                ("w", C.c_void_p), ("row_meta", C.c_void_p), ("key_score", C.c_void_p), ("scale", C.c_float),
+                ("qn", C.c_void_p), ("kn", C.c_void_p), ("vn", C.c_void_p), ("vt", C.c_void_p), ("xori", C.c_void_p),
+                ("ld_xori", C.c_int32)]
+
+
+class AttnRowmetaArgs(C.Structure):
+    _fields_ = [("lay", AttnLayout), ("row_frame", C.c_void_p), ("row_meta", C.c_void_p), ("vt_cls", C.c_void_p),
+                ("vt_reg", C.c_void_p)]
+
+
 class AttnPvArgs(C.Structure):
     _fields_ = [("lay", AttnLayout), ("qn_cls", C.c_void_p), ("kn_cls", C.c_void_p), ("qn_reg", C.c_void_p),
                 ("kn_reg", C.c_void_p), ("vt_cls", C.c_void_p), ("vt_reg", C.c_void_p), ("row_frame", C.c_void_p),
@@ -154,6 +166,8 @@ SYMBOLS = [
     ("tscd_local_offsets", C.c_int, [C.POINTER(LocalOffsetsArgs), C.c_void_p]),
     ("tscd_linear", C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
     ("tscd_attn_prep", C.c_int, [C.POINTER(AttnPrepArgs), C.c_void_p]),
+    ("tscd_qkv_project", C.c_int, [C.POINTER(QkvProjectArgs), C.c_void_p]),
+    ("tscd_attn_rowmeta", C.c_int, [C.POINTER(AttnRowmetaArgs), C.c_void_p]),
     ("tscd_attn_pv", C.c_int, [C.POINTER(AttnPvArgs), C.c_void_p]),
     ("tscd_attn_round2", C.c_int, [C.POINTER(AttnRound2Args), C.c_void_p]),
     ("tscd_transpose_clip", C.c_int, [C.POINTER(TransposeArgs), C.c_void_p]),

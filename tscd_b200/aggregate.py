@@ -11,6 +11,10 @@ import torch
 
 from . import ops
 
+# q|k|v projections with the normalise / scale / transpose step fused into the GEMM epilogue (tscd_qkv_project) instead of
+# tscd_linear + tscd_attn_prep; the unfused pair is kept for the MSA path and as a cross-check
+FUSED_QKV = True
+
 
 class MCAWeights:
     """16-bit device copies of one module's weights, q/kv fused as [Wq; Wkv] per branch."""
@@ -51,11 +55,16 @@ def mca_forward(lay: ops.AttnLayoutT, w: MCAWeights, bank_cls, bank_reg, bank_sc
     device scalars (total bank rows / total local rows).  Returns (trans_cls [loc_cap,1024], trans_obj or None), each a
     (16-bit, fp32) pair; cls_out / obj_out = (want16, want32) select which copies the output GEMMs write."""
     dev, dt = bank_cls.device, lay.dtype
-    qkv_c, _ = ops.linear(bank_cls, w.qkv_cls, m_dev=n_rows_dev)
-    qkv_r, _ = ops.linear(bank_reg, w.qkv_reg, m_dev=n_rows_dev)
     tmp_c = torch.empty(lay.loc_cap, 512, dtype=dt, device=dev)      # [attn@v | x_ori]
     tmp_r = torch.empty(lay.loc_cap, 512, dtype=dt, device=dev)
-    bufs = ops.attn_prep(lay, qkv_c, qkv_r, bank_score, xori_cls=tmp_c[:, 256:], xori_reg=tmp_r[:, 256:])
+    qkv_c = qkv_r = None
+    if FUSED_QKV:
+        bufs = ops.qkv_project_fused(lay, bank_cls, bank_reg, w.qkv_cls, w.qkv_reg, bank_score, n_rows_dev,
+                                     xori_cls=tmp_c[:, 256:], xori_reg=tmp_r[:, 256:])
+    else:
+        qkv_c, _ = ops.linear(bank_cls, w.qkv_cls, m_dev=n_rows_dev)
+        qkv_r, _ = ops.linear(bank_reg, w.qkv_reg, m_dev=n_rows_dev)
+        bufs = ops.attn_prep(lay, qkv_c, qkv_r, bank_score, xori_cls=tmp_c[:, 256:], xori_reg=tmp_r[:, 256:])
     stats = torch.empty(lay.loc_cap, 16, dtype=torch.float32, device=dev)
     ops.attn_pv(lay, bufs, tmp_c[:, :256], tmp_r[:, :256], stats, need_reg=need_reg)
     cat_c = torch.empty(lay.loc_cap, 768, dtype=dt, device=dev)      # [round2 @ V | linear(x)]

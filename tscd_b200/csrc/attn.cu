@@ -151,6 +151,36 @@ __global__ void __launch_bounds__(kPrepThreads) attn_prep_kernel(const tscd_attn
     }
 }
 
+// Row metadata for the fused q|k|v projection (tscd_qkv_project) and the attention kernels: frame of every bank row,
+// (clip, key index) of every bank row, and zero fill of the V^T padding columns [n_clip, round_up(n_clip, 128)) that
+// the P @ V / W @ V products read with zero weights.  grid (nk_pitch / 64, B), one thread per key.
+template <typename T>
+__global__ void __launch_bounds__(64) attn_rowmeta_kernel(const tscd_attn_rowmeta_args a) {
+    const tscd_attn_layout& lay = a.lay;
+    const int b = blockIdx.y, r = blockIdx.x * 64 + threadIdx.x;
+    const int s0 = lay.row_off[b * lay.F];
+    const int n_clip = lay.row_off[(b + 1) * lay.F] - s0;
+    const int n_pad = min((n_clip + 127) & ~127, lay.nk_pitch);
+    if (r >= n_pad) return;
+    if (r < n_clip) {
+        const int row = s0 + r;
+        int lo = 0, hi = lay.F;               // frame f with row_off[b*F+f] <= row < row_off[b*F+f+1] (last such f: empty frames)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (lay.row_off[b * lay.F + mid] <= row) lo = mid; else hi = mid;
+        }
+        a.row_frame[row] = lo;
+        a.row_meta[row] = (b << 16) | r;
+    } else {
+        T* vc = reinterpret_cast<T*>(a.vt_cls) + (int64_t)b * 256 * lay.nk_pitch + r;
+        T* vr = a.vt_reg ? reinterpret_cast<T*>(a.vt_reg) + (int64_t)b * 256 * lay.nk_pitch + r : nullptr;
+        for (int c = 0; c < 256; ++c) {
+            vc[(int64_t)c * lay.nk_pitch] = cvt_from_float<T>(0.f);
+            if (vr) vr[(int64_t)c * lay.nk_pitch] = cvt_from_float<T>(0.f);
+        }
+    }
+}
+
 // per-clip transpose (64 keys x 64 channels tiles through shared memory)
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_clip_kernel(const tscd_transpose_args a) {
@@ -1007,6 +1037,17 @@ extern "C" int tscd_attn_round2(const tscd_attn_round2_args* a, void* stream) {
         if (cudaFuncSetAttribute(attn_round2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
         attn_round2_kernel<false><<<grid, kR2Threads, smem, st>>>(tm, *a);
     }
+    TSCD_CUDA_CHECK_LAUNCH();
+    return TSCD_OK;
+}
+
+extern "C" int tscd_attn_rowmeta(const tscd_attn_rowmeta_args* a, void* stream) {
+    using namespace tscd;
+    if (!a || !layout_ok(a->lay) || !a->row_frame || !a->row_meta || !a->vt_cls || a->lay.B > 32767 || a->lay.nk_pitch > 65536) return TSCD_ERR_INVALID_ARG;
+    dim3 grid(a->lay.nk_pitch / 64, a->lay.B);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (a->lay.dtype == TSCD_F16) attn_rowmeta_kernel<__half><<<grid, 64, 0, st>>>(*a);
+    else attn_rowmeta_kernel<__nv_bfloat16><<<grid, 64, 0, st>>>(*a);
     TSCD_CUDA_CHECK_LAUNCH();
     return TSCD_OK;
 }

@@ -33,6 +33,15 @@ struct GemmParams {
     float* out32;         // optional fp32 output, pitch ld32 elements
     int ld16, ld32;
     int is_bf16;
+    // fused q|k|v epilogue (EPI = 1): per-head L2 normalisation, key scaling, V^T / x_ori scatter (see tscd_qkv_project)
+    const int32_t* row_meta;   // [rows] (clip << 16) | key index within the clip
+    const int32_t* row_off;    // [B*F+1]
+    const int32_t* lrow_off;   // [B*L+1]
+    int F, L, self_attn, nk_pitch;
+    const float* key_score;    // [rows] or NULL
+    float scale;
+    void *qn, *kn, *vn, *vt, *xori;
+    int ld_xori;
 };
 
 // Persistent, warp-specialised: every CTA walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...  (n fastest, so
@@ -40,7 +49,7 @@ struct GemmParams {
 // overlap the TMA/MMA main loop of tile i+1; the smem ring keeps filling across tile boundaries.
 constexpr int kAccStages = 2;
 
-template <int BN, bool BF16>
+template <int BN, bool BF16, int EPI = 0>
 __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                 const __grid_constant__ CUtensorMap tmap_w,
                                                                 const GemmParams p) {
@@ -148,6 +157,98 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
             const int row = row_base + lane;
             const bool row_ok = row < M;
             const uint32_t tsrc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
+            if constexpr (EPI == 1) {
+                // ---- fused q|k|v epilogue: this 256-column tile is the q (0), k (1) or v (2) projection of 128 bank rows;
+                //      the warp's 128 columns are two heads; thread == row holds a head's 64 values in registers ----
+                static_assert(BN == 256 || EPI == 0, "the fused epilogue works on 256-column tiles");
+                const int kind = n0 >> 8;
+                const int meta = row_ok ? __ldg(p.row_meta + row) : -1;
+                const bool valid = meta >= 0;
+                const int cb = valid ? (meta >> 16) : 0, kr = meta & 0xffff;
+                bool is_query = false;
+                int lb = 0;
+                if (valid) {
+                    const int s0 = __ldg(p.row_off + cb * p.F);
+                    const int n_loc = (p.self_attn ? __ldg(p.row_off + (cb + 1) * p.F) : __ldg(p.row_off + cb * p.F + p.L)) - s0;
+                    is_query = kr < n_loc;
+                    lb = __ldg(p.lrow_off + cb * p.L);
+                }
+                auto pk2h = [](float a, float b) -> uint32_t {
+                    if (BF16) { __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+                    __half2 h = __floats2half2_rn(a, b);
+                    return *reinterpret_cast<uint32_t*>(&h);
+                };
+#pragma unroll 1
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int head = half * 2 + hh;
+                    uint32_t r0[32], r1[32];
+                    tmem_ld_32x32(tsrc + (uint32_t)(hh * 64), r0);
+                    tmem_ld_32x32(tsrc + (uint32_t)(hh * 64 + 32), r1);
+                    tmem_ld_wait();
+                    float ss = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        ss = fmaf(__uint_as_float(r0[j]), __uint_as_float(r0[j]), ss);
+                        ss = fmaf(__uint_as_float(r1[j]), __uint_as_float(r1[j]), ss);
+                    }
+                    // 16-bit row-segment stores go through the warp's 32 x 64-byte staging tile (as in the plain epilogue):
+                    // one store instruction then writes 8 rows x 64 contiguous bytes instead of 32 scattered 16-byte pieces.
+                    // `dest` = destination row of this lane's bank row (-1: nothing to store), fetched per staged row by shuffle.
+                    auto staged_store = [&](const uint32_t (&w16)[16], uint16_t* base, int64_t dest, int ld, int col) {
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                                make_uint4(w16[4 * j], w16[4 * j + 1], w16[4 * j + 2], w16[4 * j + 3]);
+                        __syncwarp();
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int rr = 8 * k + (lane >> 2), ch = lane & 3;
+                            const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+                            const long long d = __shfl_sync(0xffffffffu, (long long)dest, rr);
+                            if (d >= 0) *reinterpret_cast<uint4*>(base + d * ld + col + ch * 8) = val;
+                        }
+                    };
+                    float sc = valid ? 1.f / sqrtf(ss) : 0.f;
+                    if (kind == 1 && valid) sc *= p.key_score ? p.scale * __ldg(p.key_score + row) : p.scale;
+                    uint16_t* nbase = reinterpret_cast<uint16_t*>(kind == 0 ? p.qn : (kind == 1 ? p.kn : p.vn));
+                    const int64_t ndest = (valid && (kind != 0 || is_query)) ? (int64_t)row : -1;     // q of the global rows is never read
+                    uint32_t w16[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) w16[j] = pk2h(__uint_as_float(r0[2 * j]) * sc, __uint_as_float(r0[2 * j + 1]) * sc);
+                    staged_store(w16, nbase, ndest, 256, head * 64);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) w16[j] = pk2h(__uint_as_float(r1[2 * j]) * sc, __uint_as_float(r1[2 * j + 1]) * sc);
+                    staged_store(w16, nbase, ndest, 256, head * 64 + 32);
+                    if (kind == 2) {
+                        // raw v: x_ori rows of the queries, and V^T (lanes are consecutive keys -> 64 contiguous bytes per channel)
+                        if (p.xori) {
+                            const int64_t xdest = (valid && is_query) ? (int64_t)(lb + kr) : -1;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) w16[j] = pk2h(__uint_as_float(r0[2 * j]), __uint_as_float(r0[2 * j + 1]));
+                            staged_store(w16, reinterpret_cast<uint16_t*>(p.xori), xdest, p.ld_xori, head * 64);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) w16[j] = pk2h(__uint_as_float(r1[2 * j]), __uint_as_float(r1[2 * j + 1]));
+                            staged_store(w16, reinterpret_cast<uint16_t*>(p.xori), xdest, p.ld_xori, head * 64 + 32);
+                        }
+                        if (valid) {
+                            uint16_t* vt = reinterpret_cast<uint16_t*>(p.vt) + ((int64_t)cb * 256 + head * 64) * p.nk_pitch + kr;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                vt[(int64_t)j * p.nk_pitch] = (uint16_t)(pk2h(__uint_as_float(r0[j]), 0.f) & 0xffffu);
+                                vt[(int64_t)(32 + j) * p.nk_pitch] = (uint16_t)(pk2h(__uint_as_float(r1[j]), 0.f) & 0xffffu);
+                            }
+                        }
+                    }
+                    {
+                    }   // valid
+                    __syncwarp();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                continue;
+            }
             uint32_t rbuf[2][32];
             tmem_ld_32x32(tsrc, rbuf[0]);
             tmem_ld_wait();
@@ -278,13 +379,13 @@ int make_tmap_kmajor(CUtensorMap* m, const void* ptr, int is_bf16, int64_t rows,
     return r == CUDA_SUCCESS ? TSCD_OK : TSCD_ERR_CUDA;
 }
 
-template <int BN, bool BF16>
+template <int BN, bool BF16, int EPI = 0>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
     constexpr int STAGES = BN == 256 ? 4 : 3;
     constexpr size_t smem = (size_t)STAGES * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + 8 * 2048 + 128;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(gemm_tn_kernel<BN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(gemm_tn_kernel<BN, BF16, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return TSCD_ERR_CUDA;
         attr_set = true;
     }
@@ -297,7 +398,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmP
     const int tiles = ((p.N + BN - 1) / BN) * ((p.M + kGemmBM - 1) / kGemmBM);
     const int ctas_per_sm = BN == 256 ? 1 : 2;                       // 113 KB smem and 2*BN TMEM columns per CTA (BN <= 128)
     const int grid = tiles < ctas_per_sm * num_sms ? tiles : ctas_per_sm * num_sms;
-    gemm_tn_kernel<BN, BF16><<<grid, kGemmThreads, smem, st>>>(ta, tw, p);
+    gemm_tn_kernel<BN, BF16, EPI><<<grid, kGemmThreads, smem, st>>>(ta, tw, p);
     return cudaGetLastError() == cudaSuccess ? TSCD_OK : TSCD_ERR_CUDA;
 }
 
@@ -318,7 +419,7 @@ extern "C" int tscd_linear(const tscd_linear_args* a, void* stream) {
     if (rc != TSCD_OK) return rc;
     rc = make_tmap_kmajor(&tw, a->w, is_bf16, a->N, a->K, a->ldw, BN);
     if (rc != TSCD_OK) return rc;
-    GemmParams p;
+    GemmParams p = {};
     p.M = a->M; p.N = a->N; p.K = a->K;
     p.m_dev = a->m_dev; p.bias = a->bias;
     p.out16 = a->out16; p.out32 = a->out32;
@@ -327,4 +428,28 @@ extern "C" int tscd_linear(const tscd_linear_args* a, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (is_bf16) return BN == 64 ? launch_gemm<64, true>(ta, tw, p, st) : (BN == 128 ? launch_gemm<128, true>(ta, tw, p, st) : launch_gemm<256, true>(ta, tw, p, st));
     return BN == 64 ? launch_gemm<64, false>(ta, tw, p, st) : (BN == 128 ? launch_gemm<128, false>(ta, tw, p, st) : launch_gemm<256, false>(ta, tw, p, st));
+}
+
+extern "C" int tscd_qkv_project(const tscd_qkv_project_args* a, void* stream) {
+    using namespace tscd;
+    if (!a || a->rows <= 0 || !a->x || !a->w || !a->row_meta || !a->qn || !a->kn || !a->vn || !a->vt) return TSCD_ERR_INVALID_ARG;
+    const tscd_attn_layout& l = a->lay;
+    if (l.dtype != TSCD_F16 && l.dtype != TSCD_BF16) return TSCD_ERR_UNSUPPORTED;
+    if (l.B <= 0 || l.F <= 0 || l.L <= 0 || l.L > l.F || !l.row_off || !l.lrow_off || (l.nk_pitch % 128) != 0 || l.nk_pitch > 65536) return TSCD_ERR_INVALID_ARG;
+    const int is_bf16 = l.dtype == TSCD_BF16;
+    CUtensorMap ta, tw;
+    int rc = make_tmap_kmajor(&ta, a->x, is_bf16, a->rows, 256, a->ldx, kGemmBM);
+    if (rc != TSCD_OK) return rc;
+    rc = make_tmap_kmajor(&tw, a->w, is_bf16, 768, 256, 256, 256);
+    if (rc != TSCD_OK) return rc;
+    GemmParams p = {};
+    p.M = a->rows; p.N = 768; p.K = 256;
+    p.m_dev = a->m_dev;
+    p.is_bf16 = is_bf16;
+    p.row_meta = a->row_meta; p.row_off = l.row_off; p.lrow_off = l.lrow_off;
+    p.F = l.F; p.L = l.L; p.self_attn = l.self_attn; p.nk_pitch = l.nk_pitch;
+    p.key_score = a->key_score; p.scale = a->scale;
+    p.qn = a->qn; p.kn = a->kn; p.vn = a->vn; p.vt = a->vt; p.xori = a->xori; p.ld_xori = a->ld_xori;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return is_bf16 ? launch_gemm<256, true, 1>(ta, tw, p, st) : launch_gemm<256, false, 1>(ta, tw, p, st);
 }

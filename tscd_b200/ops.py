@@ -261,6 +261,28 @@ def attn_prep(lay: AttnLayoutT, qkv_cls, qkv_reg, key_score, xori_cls=None, xori
     return bufs
 
 
+def qkv_project_fused(lay: AttnLayoutT, bank_cls, bank_reg, w_cls, w_reg, key_score, n_rows_dev, xori_cls=None, xori_reg=None,
+                      scale=25.0):
+    """tscd_attn_rowmeta + 2 x tscd_qkv_project: the q|k|v projections of both branches with the normalise / scale /
+    transpose step of tscd_attn_prep fused into the GEMM epilogue.  Returns the same operand dict as attn_prep."""
+    dev, dt = bank_cls.device, lay.dtype
+    bufs = {}
+    for n in ("qn_cls", "kn_cls", "vn_cls", "qn_reg", "kn_reg", "vn_reg"):
+        bufs[n] = torch.empty(lay.row_cap, 256, dtype=dt, device=dev)
+    for n in ("vt_cls", "vt_reg"):
+        bufs[n] = torch.empty(lay.B * 256, lay.nk_pitch, dtype=dt, device=dev)
+    bufs["row_frame"] = torch.empty(lay.row_cap, dtype=torch.int32, device=dev)
+    bufs["row_meta"] = torch.empty(lay.row_cap, dtype=torch.int32, device=dev)
+    call("tscd_attn_rowmeta", L.AttnRowmetaArgs, lay=lay.to_c(), row_frame=bufs["row_frame"], row_meta=bufs["row_meta"],
+         vt_cls=bufs["vt_cls"], vt_reg=bufs["vt_reg"])
+    for br, bank, w, ks, xo in (("cls", bank_cls, w_cls, key_score, xori_cls), ("reg", bank_reg, w_reg, None, xori_reg)):
+        assert bank.shape[0] >= lay.row_cap and bank.stride(1) == 1 and w.shape == (768, 256) and w.is_contiguous()
+        call("tscd_qkv_project", L.QkvProjectArgs, lay=lay.to_c(), rows=lay.row_cap, m_dev=n_rows_dev, x=bank, ldx=bank.stride(0),
+             w=w, row_meta=bufs["row_meta"], key_score=ks, scale=scale, qn=bufs["qn_" + br], kn=bufs["kn_" + br],
+             vn=bufs["vn_" + br], vt=bufs["vt_" + br], xori=xo, ld_xori=0 if xo is None else xo.stride(0))
+    return bufs
+
+
 def attn_pv(lay: AttnLayoutT, bufs, x_cls, x_reg, stats, need_reg=True):
     a = L.AttnPvArgs()
     a.lay = lay.to_c()
