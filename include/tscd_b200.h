@@ -65,7 +65,10 @@ typedef struct {
  * postpro_woclass (post_process.py:476-508, mode A).
  * Emits, per frame, a candidate list (anchor id, xyxy box, score = obj*class_conf, class id):
  *   mode A: the top-`pre_k` anchors by objectness, descending (ties: lower anchor id first);
- *   mode B: anchors with score >= conf_thresh subject to minimal/maximal limits, ascending anchor id. */
+ *   mode B: anchors with score >= conf_thresh subject to minimal/maximal limits, ascending anchor id.
+ * Mode A needs the class max of the survivors only: with class-contiguous logits (cls.chan_stride == 1, channels_last
+ * conv outputs) only the survivors' class rows are read; with anchor-contiguous planes (NCHW) and a workspace the class
+ * max of every anchor is streamed by a separate kernel (classmax_kernel); otherwise one fused kernel streams the planes. */
 typedef struct {
     int32_t mode;          /* 0 = A (postpro_woclass), 1 = B (postprocess_widx) */
     int32_t num_frames;    /* total frames in the batch (clips * frames per clip) */

@@ -232,7 +232,7 @@ __device__ bool nms_per_class(const tscd_nms_args& args, int frame, int n, const
     return true;
 }
 
-__global__ void __launch_bounds__(kNmsThreads) nms_kernel(const tscd_nms_args args, int smem_cap) {
+__global__ void __launch_bounds__(kNmsThreads, 4) nms_kernel(const tscd_nms_args args, int smem_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int frame = blockIdx.x;
     int n = args.count[frame];
