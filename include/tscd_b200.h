@@ -426,7 +426,7 @@ int tscd_cafm_chain(const tscd_cafm_chain_args* args, void* stream);
  * SAME frame.  q/k/v are the GEMM outputs of the projections (tscd_linear): fp32 for the generic kernel, 16-bit for the
  * mma.sync tensor-core kernel used when every frame holds <= 32 proposals.
  * tscd_residual_ln2: y = LN_b(LN_a(x + r))  -- CrossAttentionLayer.forward_post's norm followed by the
- * decoder_norm of TaskAligned (tscd_matching.py:421-433, 1133-1137). */
+ * decoder_norm of TaskAligned (tscd_matching.py:421-433, 1133-1137); optionally also the 1-output objectness head. */
 typedef struct {
     int32_t num_frames;          /* B*L local frames */
     int32_t heads, head_dim;
@@ -445,7 +445,10 @@ typedef struct {
     const float* x; const float* r;
     const float *w_a, *b_a, *w_b, *b_b;
     int32_t out_dtype;
-    void* out16; float* out32;
+    void* out16; float* out32;   /* either may be NULL */
+    /* optional fused single-output head (matcher_obj_pred, tscd_head.py:518): head_out[row] = <y_row, head_w> + head_b,
+     * y = the fp32 LayerNorm output (dim 1024 only); head_w fp32 [dim], head_b fp32 [1], head_out fp32 [rows_cap] */
+    const float* head_w; const float* head_b; float* head_out;
 } tscd_residual_ln2_args;
 int tscd_residual_ln2(const tscd_residual_ln2_args* args, void* stream);
 

@@ -139,7 +139,7 @@ class FrameAttentionArgs(C.Structure):
 
 
 class ResidualLn2Args(C.Structure):
-    _fields_ = _fields("rows_cap:i dim:i n_rows:p x:p r:p w_a:p b_a:p w_b:p b_b:p out_dtype:i out16:p out32:p")
+    _fields_ = _fields("rows_cap:i dim:i n_rows:p x:p r:p w_a:p b_a:p w_b:p b_b:p out_dtype:i out16:p out32:p head_w:p head_b:p head_out:p")
 
 
 class FinalExpandArgs(C.Structure):

@@ -283,16 +283,25 @@ __global__ void __launch_bounds__(256) residual_ln2_kernel(const tscd_residual_l
                 var = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, fmaf(dw, dw, var))));
             }
             rstd = rsqrtf(warp_sumf(var) / D + 1e-5f);
+            float hd = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float4 w = __ldg(reinterpret_cast<const float4*>(a.w_b) + i * 32 + lane), b = __ldg(reinterpret_cast<const float4*>(a.b_b) + i * 32 + lane);
                 const float4 y = make_float4((v[i].x - mean) * rstd * w.x + b.x, (v[i].y - mean) * rstd * w.y + b.y,
                                              (v[i].z - mean) * rstd * w.z + b.z, (v[i].w - mean) * rstd * w.w + b.w);
+                if (a.head_w) {
+                    const float4 hw = __ldg(reinterpret_cast<const float4*>(a.head_w) + i * 32 + lane);
+                    hd = fmaf(y.x, hw.x, fmaf(y.y, hw.y, fmaf(y.z, hw.z, fmaf(y.w, hw.w, hd))));
+                }
                 const int64_t o = (int64_t)r * D + (i * 32 + lane) * 4;
                 if (a.out16) {
                     *reinterpret_cast<uint2*>(reinterpret_cast<T*>(a.out16) + o) = make_uint2(pack2<T>(y.x, y.y), pack2<T>(y.z, y.w));
                 }
                 if (a.out32) *reinterpret_cast<float4*>(a.out32 + o) = y;
+            }
+            if (a.head_w) {
+                hd = warp_sumf(hd);
+                if (lane == 0) a.head_out[r] = hd + __ldg(a.head_b);
             }
         }
         return;
@@ -435,7 +444,8 @@ extern "C" int tscd_frame_attention(const tscd_frame_attention_args* a, void* st
 
 extern "C" int tscd_residual_ln2(const tscd_residual_ln2_args* a, void* stream) {
     using namespace tscd;
-    if (!a || a->rows_cap <= 0 || a->dim <= 0 || a->dim > 4096) return TSCD_ERR_INVALID_ARG;
+    if (!a || a->rows_cap <= 0 || a->dim <= 0 || a->dim > 4096 || (!a->out16 && !a->out32 && !a->head_w)) return TSCD_ERR_INVALID_ARG;
+    if (a->head_w && (a->dim != 1024 || !a->head_b || !a->head_out)) return TSCD_ERR_UNSUPPORTED;
     const size_t smem = (size_t)8 * a->dim * sizeof(float);
     int grid = (a->rows_cap + 7) / 8;
     if (grid > 148 * 8) grid = 148 * 8;

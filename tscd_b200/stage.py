@@ -67,6 +67,7 @@ class StageWeights:
         self.ta_dec_w, self.ta_dec_b = f32("task_aligned.decoder_norm.weight"), f32("task_aligned.decoder_norm.bias")
         self.cls_w, self.cls_b = w16("cls_pred.weight"), f32("cls_pred.bias")
         self.obj_w, self.obj_b = w16("matcher_obj_pred.weight"), f32("matcher_obj_pred.bias")
+        self.obj_w32 = self.obj_w.float().reshape(-1).contiguous()       # the 16-bit weight values, fp32 storage (fused head)
         self.reg_w, self.reg_b = w16("matcher_reg_pred.weight"), f32("matcher_reg_pred.bias")
 
 
@@ -382,11 +383,13 @@ class AggregationStage:
         ops.call("tscd_frame_attention", L.FrameAttentionArgs, num_frames=B * Lf, heads=8, head_dim=(4 * D) // 8,
                  in_dtype=dt if fast_ta else torch.float32, lrow_off=lay.lrow_off, q=tq, ldq=tq.stride(0), k=tkv, ldk=tkv.stride(0),
                  v=tkv[:, 4 * D:], ldv=tkv.stride(0), out=att, ldo=att.stride(0))
-        objref16 = torch.empty(loc_cap, 4 * D, dtype=dt, device=dev)
+        # LN(LN(x + attn)) with the 1-output objectness head (matcher_obj_pred) fused: the LayerNorm output row is in
+        # registers, so the refined features are only materialised for tracing
         objref32 = f32z(loc_cap, 4 * D) if trace is not None else None
+        obj_logits = f32z(loc_cap, 1)
         ops.call("tscd_residual_ln2", L.ResidualLn2Args, rows_cap=loc_cap, dim=4 * D, n_rows=n_loc_dev, x=iou_reg32, r=att,
-                 w_a=w.ta_ln_w, b_a=w.ta_ln_b, w_b=w.ta_dec_w, b_b=w.ta_dec_b, out_dtype=dt, out16=objref16, out32=objref32)
-        _, obj_logits = ops.linear(objref16, w.obj_w, w.obj_b, m_dev=n_loc_dev, want16=False, want32=True)
+                 w_a=w.ta_ln_w, b_a=w.ta_ln_b, w_b=w.ta_dec_w, b_b=w.ta_dec_b, out_dtype=dt, out16=None, out32=objref32,
+                 head_w=w.obj_w32, head_b=w.obj_b, head_out=obj_logits)
         main.wait_event(ev_join)                 # classification branch joins here
 
         # ---- final per-class expansion + NMS ---------------------------------------------------------------
