@@ -24,6 +24,8 @@ constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
 constexpr int kGemmStages = 3;
 constexpr int kGemmThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kGemmThreadsFused = 576;   // fused q|k|v epilogue: 16 epilogue warps, one head each (the epilogue is latency-bound)
+__host__ __device__ constexpr int gemm_epi_warps(int epi) { return epi ? 16 : 8; }
 
 struct GemmParams {
     int M, N, K;
@@ -50,7 +52,7 @@ struct GemmParams {
 constexpr int kAccStages = 2;
 
 template <int BN, bool BF16, int EPI = 0>
-__global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
+__global__ void __launch_bounds__(EPI ? kGemmThreadsFused : kGemmThreads) gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                 const __grid_constant__ CUtensorMap tmap_w,
                                                                 const GemmParams p) {
     using namespace tc;
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
     unsigned char* sA = smem;
     unsigned char* sW = smem + STAGES * kABytes;
     unsigned char* sStage = sW + STAGES * kWBytes;      // 8 epilogue warps x (32 rows x 64 B)
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + 8 * 2048);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + gemm_epi_warps(EPI) * 2048);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;
     uint64_t* tmem_empty_bar = tmem_full_bar + kAccStages;
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_w);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 8); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], gemm_epi_warps(EPI)); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<kAccStages * BN>(&tmem_base_smem);
@@ -151,39 +153,43 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
             const int m0 = (t / tiles_n) * kGemmBM, n0 = (t % tiles_n) * BN;
             const int acc = ti % kAccStages;
             const uint32_t aph = (ti / kAccStages) & 1;
-            mbar_wait(&tmem_full_bar[acc], aph, 120 + acc);
-            tc_fence_after();
             const int row_base = m0 + q * 32;
             const int row = row_base + lane;
             const bool row_ok = row < M;
+            // fused epilogue: the row metadata (three dependent L2 reads) is fetched BEFORE waiting for the accumulator
+            int meta = -1, lb = 0;
+            bool is_query = false;
+            if constexpr (EPI == 1) {
+                meta = row_ok ? __ldg(p.row_meta + row) : -1;
+                if (meta >= 0) {
+                    const int cb0 = meta >> 16;
+                    const int s0 = __ldg(p.row_off + cb0 * p.F);
+                    const int n_loc = (p.self_attn ? __ldg(p.row_off + (cb0 + 1) * p.F) : __ldg(p.row_off + cb0 * p.F + p.L)) - s0;
+                    is_query = (meta & 0xffff) < n_loc;
+                    lb = __ldg(p.lrow_off + cb0 * p.L);
+                }
+            }
+            mbar_wait(&tmem_full_bar[acc], aph, 120 + acc);
+            tc_fence_after();
             const uint32_t tsrc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
             if constexpr (EPI == 1) {
                 // ---- fused q|k|v epilogue: this 256-column tile is the q (0), k (1) or v (2) projection of 128 bank rows;
                 //      the warp's 128 columns are two heads; thread == row holds a head's 64 values in registers ----
                 static_assert(BN == 256 || EPI == 0, "the fused epilogue works on 256-column tiles");
                 const int kind = n0 >> 8;
-                const int meta = row_ok ? __ldg(p.row_meta + row) : -1;
                 const bool valid = meta >= 0;
                 const int cb = valid ? (meta >> 16) : 0, kr = meta & 0xffff;
-                bool is_query = false;
-                int lb = 0;
-                if (valid) {
-                    const int s0 = __ldg(p.row_off + cb * p.F);
-                    const int n_loc = (p.self_attn ? __ldg(p.row_off + (cb + 1) * p.F) : __ldg(p.row_off + cb * p.F + p.L)) - s0;
-                    is_query = kr < n_loc;
-                    lb = __ldg(p.lrow_off + cb * p.L);
-                }
                 auto pk2h = [](float a, float b) -> uint32_t {
                     if (BF16) { __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
                     __half2 h = __floats2half2_rn(a, b);
                     return *reinterpret_cast<uint32_t*>(&h);
                 };
-#pragma unroll 1
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int head = half * 2 + hh;
+                {
+                    const int head = (warp - 2) >> 2;              // 16 epilogue warps: lane quadrant x head
+                    const uint32_t tsrc_h = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + head * 64);
                     uint32_t r0[32], r1[32];
-                    tmem_ld_32x32(tsrc + (uint32_t)(hh * 64), r0);
-                    tmem_ld_32x32(tsrc + (uint32_t)(hh * 64 + 32), r1);
+                    tmem_ld_32x32(tsrc_h, r0);
+                    tmem_ld_32x32(tsrc_h + 32u, r1);
                     tmem_ld_wait();
                     float ss = 0.f;
 #pragma unroll
@@ -382,7 +388,7 @@ int make_tmap_kmajor(CUtensorMap* m, const void* ptr, int is_bf16, int64_t rows,
 template <int BN, bool BF16, int EPI = 0>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
     constexpr int STAGES = BN == 256 ? 4 : 3;
-    constexpr size_t smem = (size_t)STAGES * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + 8 * 2048 + 128;
+    constexpr size_t smem = (size_t)STAGES * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + gemm_epi_warps(EPI) * 2048 + 128;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(gemm_tn_kernel<BN, BF16, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -398,7 +404,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmP
     const int tiles = ((p.N + BN - 1) / BN) * ((p.M + kGemmBM - 1) / kGemmBM);
     const int ctas_per_sm = BN == 256 ? 1 : 2;                       // 113 KB smem and 2*BN TMEM columns per CTA (BN <= 128)
     const int grid = tiles < ctas_per_sm * num_sms ? tiles : ctas_per_sm * num_sms;
-    gemm_tn_kernel<BN, BF16, EPI><<<grid, kGemmThreads, smem, st>>>(ta, tw, p);
+    gemm_tn_kernel<BN, BF16, EPI><<<grid, EPI ? kGemmThreadsFused : kGemmThreads, smem, st>>>(ta, tw, p);
     return cudaGetLastError() == cudaSuccess ? TSCD_OK : TSCD_ERR_CUDA;
 }
 
