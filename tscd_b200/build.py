@@ -10,7 +10,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libtscd_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("TSCD_NVCC_EXTRA", "").split()
 
 
 def sources():

@@ -618,29 +618,83 @@ struct R2Tmaps {
     CUtensorMap q128c, q128r, k64c, k64r, vn128c, vn128r, vn64c, vn64r, vt;
 };
 
-// Warp-specialised like attn_pv.  All operands stream through ONE ring of 24 KB stages in a fixed order that the
-// TMA warp produces and the MMA warp consumes:
-//   per key tile kt (64 keys):  S units (h0c h0r h1c h1r) | raw-v atoms of tile kt+1 (cls x4 [, reg x4]) |
-//                               S units (h2c h2r h3c h3r) | V^T halves of tile kt-1 (2 x 128 dims)
-//   stage formats:  S unit  = Q head slice [128x64] 16K + K head slice [64x64] 8K
-//                   raw atom = Vn(query) [128x64] 16K + Vn(keys) [64x64] 8K          (one of the four 64-dim atoms)
-//                   V^T half = [128 dims x 64 keys] 16K
-// TMEM: U 256 | R_cls 64 | R_reg 64 | two score units of 64 columns.  The 8 softmax warps read the raw-v
-// similarities of a tile first (mask bits -> registers), then the 8 score units (head-sum of the normalised
-// attention, exact statistics from attn_pv), then write the round-2 weights as the A operand of W @ V^T.
-constexpr int kR2Threads = 320;
-constexpr int kR2Stages = 6;
-constexpr int kR2StageBytes = 24576;
+// Warp-specialised like attn_pv.  The kernel is bound by the latency of L2 -> shared-memory operand traffic, so the A
+// operands that every key tile re-uses stay RESIDENT in shared memory for the whole CTA (loaded once):
+//   cls launch (no w_in):  the 8 query head slices  Q[h][branch]  [128 x 64]   (8 x 16K = 128K)
+//   obj launch (w_in):     the 4 raw-v query atoms of the reg branch [128 x 64] (4 x 16K)
+// Everything else streams through ONE ring of 8 KB slots (10 / 16 of them) in a fixed order (r2_schedule) that the TMA
+// warp produces and the MMA warp consumes; an item takes 1..3 contiguous slots, one that would straddle the end
+// restarts at slot 0:
+//   S unit          = K head slice [64 x 64]                                   1 slot
+//   raw atom        = Vn(query) [128 x 64] 16K + Vn(keys) [64 x 64] 8K          3 slots  (cls launch)
+//                     Vn(keys) only, the query atom is resident                  1 slot   (obj launch)
+//   V^T half        = [128 dims x 64 keys]                                      2 slots
+// The schedule interleaves the item kinds (unit, raw atom of the next tile, unit, ... , V^T half of the previous tile)
+// so that the shallow ring never holds a burst of one kind while the softmax warps wait for another.
+// TMEM: U 256 | R_cls 64 | R_reg 64 | two score units of 64 columns (obj launch: the two R regions double-buffer the
+// reg-branch similarity).  The 8 softmax warps read the raw-v similarities of a tile first (mask bits -> registers),
+// then the 8 score units (head-sum of the normalised attention, exact statistics from attn_pv), then write the
+// round-2 weights as the A operand of W @ V^T.
+constexpr int kR2Threads = 576;      // 16 softmax warps + TMA warp + MMA warp
+constexpr int kR2MaxSlots = 16;
+constexpr int kR2SlotBytes = 8192;
+constexpr int kR2SmemBytes = 229376;      // resident operands + ring + weight buffers (mode-dependent split)
 
 struct R2Bars {
-    uint64_t full[kR2Stages], empty[kR2Stages];
-    uint64_t r_full, r_empty;
+    uint64_t full[kR2MaxSlots], empty[kR2MaxSlots];
+    uint64_t res_full;
+    uint64_t r_full[2], r_empty[2];
     uint64_t s_full[2], s_empty[2];
     uint64_t w_full[2], w_empty[2];
     uint64_t u_full;
     uint32_t tmem_base;
-    float xch[2][128];
+    float xch[4][128];
 };
+
+// f(kind, kt, i): kind 0 = score unit i of tile kt, 1 = raw atom i of tile kt, 2 = V^T half i of tile kt
+template <class F>
+__device__ __forceinline__ void r2_schedule(int KT, bool reuse, int n_atoms, F&& f) {
+    if (reuse) {
+        for (int x = 4; x < 8; ++x) f(1, 0, x);
+        for (int kt = 0; kt < KT; ++kt) {
+            if (kt + 1 < KT)
+                for (int x = 4; x < 8; ++x) f(1, kt + 1, x);
+            if (kt >= 1) { f(2, kt - 1, 0); f(2, kt - 1, 1); }
+        }
+        f(2, KT - 1, 0); f(2, KT - 1, 1);
+        return;
+    }
+    for (int x = 0; x < 4; ++x) { f(1, 0, x); if (n_atoms == 8) f(1, 0, x + 4); }
+    for (int kt = 0; kt < KT; ++kt) {
+        for (int i = 0; i < 4; ++i) {
+            f(0, kt, i);
+            if (kt + 1 < KT) { f(1, kt + 1, i); if (n_atoms == 8) f(1, kt + 1, i + 4); }
+        }
+        f(0, kt, 4);
+        if (kt >= 1) f(2, kt - 1, 0);
+        f(0, kt, 5);
+        if (kt >= 1) f(2, kt - 1, 1);
+        f(0, kt, 6);
+        f(0, kt, 7);
+    }
+    f(2, KT - 1, 0); f(2, KT - 1, 1);
+}
+
+// Debug build (-DTSCD_R2_PROF): clocks one lane per role of CTA (0,0) spends in each barrier wait, by wait-site tag.
+#ifdef TSCD_R2_PROF
+__device__ unsigned long long g_r2_wait[32];
+__device__ __forceinline__ void r2_wait_prof(uint64_t* bar, uint32_t parity, int tag) {
+    const long long t0 = clock64();
+    tc::mbar_wait(bar, parity, tag);
+    const long long dt = clock64() - t0;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x == 0 || threadIdx.x == 512 || threadIdx.x == 544))
+        atomicAdd(&g_r2_wait[tag - 400], (unsigned long long)dt);
+}
+#define R2_WAIT r2_wait_prof
+#else
+#define R2_WAIT mbar_wait
+#endif
+
 
 template <bool BF16>
 __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid_constant__ R2Tmaps tm,
@@ -650,153 +704,166 @@ __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid
     const int b = blockIdx.y;
     const ClipInfo ci = clip_info(lay, b, blockIdx.x);
     if (ci.q0 >= ci.n_loc) return;
+#ifdef TSCD_R2_PROF
+    const long long tk0 = clock64();
+#endif
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw;                       // no static shared memory: the window starts 1024-byte aligned
     if ((smem_u32(smem) & 1023u) != 0) __trap();
-    unsigned char* sRing = smem;                          // 6 x 24K
-    unsigned char* sW = smem + kR2Stages * kR2StageBytes; // 2 x 16K weights [128 x 64 keys]
-    R2Bars& bars = *reinterpret_cast<R2Bars*>(sW + 32768);
+    const bool use_obj = a.use_obj_mask != 0;
+    // w_in: the cls-output launch of the same module already stored  sim_mask * exp(mean attention)  (its weights): this
+    // launch only needs the reg-branch raw-v similarity (obj mask) -- no score units, no exponentials
+    const bool reuse = a.w_in != nullptr;
+    const int n_atoms = use_obj ? 8 : 4;
+    const int n_slots = reuse ? 16 : 10;
+    unsigned char* sRes = smem;                                   // resident A operands: 4 or 8 x 16K
+    unsigned char* sRing = smem + (reuse ? 65536 : 131072);       // 16 or 10 x 8K
+    unsigned char* sW = sRing + n_slots * kR2SlotBytes;           // 2 or 1 x 16K weights [128 x 64 keys]
+    R2Bars& bars = *reinterpret_cast<R2Bars*>(smem + kR2SmemBytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 256) {
+    if (threadIdx.x == 512) {
         tma_prefetch_desc(&tm.q128c); tma_prefetch_desc(&tm.q128r); tma_prefetch_desc(&tm.k64c); tma_prefetch_desc(&tm.k64r);
         tma_prefetch_desc(&tm.vn128c); tma_prefetch_desc(&tm.vn128r); tma_prefetch_desc(&tm.vn64c); tma_prefetch_desc(&tm.vn64r);
         tma_prefetch_desc(&tm.vt);
-        for (int i = 0; i < kR2Stages; ++i) { mbar_init(&bars.full[i], 1); mbar_init(&bars.empty[i], 1); }
-        mbar_init(&bars.r_full, 1); mbar_init(&bars.r_empty, 8);
+        for (int i = 0; i < kR2MaxSlots; ++i) { mbar_init(&bars.full[i], 1); mbar_init(&bars.empty[i], 1); }
+        mbar_init(&bars.res_full, 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&bars.s_full[i], 1); mbar_init(&bars.s_empty[i], 8);
-            mbar_init(&bars.w_full[i], 8); mbar_init(&bars.w_empty[i], 1);
+            mbar_init(&bars.r_full[i], 1); mbar_init(&bars.r_empty[i], 16);
+            mbar_init(&bars.s_full[i], 1); mbar_init(&bars.s_empty[i], 16);
+            mbar_init(&bars.w_full[i], 16); mbar_init(&bars.w_empty[i], 1);
         }
         mbar_init(&bars.u_full, 1);
         fence_barrier_init();
     }
-    if (warp == 9) tmem_alloc<512>(&bars.tmem_base);
+    if (warp == 17) tmem_alloc<512>(&bars.tmem_base);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars.tmem_base;
     const int KT = (ci.n_clip + 63) / 64;
-    const bool use_obj = a.use_obj_mask != 0;
-    // w_in: the cls-output launch of the same module already stored  sim_mask * exp(mean attention)  (its weights): this
-    // launch only needs the reg-branch raw-v similarity (obj mask) -- no score units, no exponentials
-    const bool reuse = a.w_in != nullptr;
-    const int atom0 = reuse ? 4 : 0;
-    const int n_atoms = use_obj ? 8 : 4;
-
-    if (warp == 8) {
+    if (warp == 16) {
         // ------------------------------------------------ TMA producer ------------------------------------------------
         if (lane == 0) {
-            uint32_t it = 0;
-            auto acquire = [&](uint32_t bytes) -> unsigned char* {
-                const int st = it % kR2Stages;
-                mbar_wait(&bars.empty[st], ((it / kR2Stages) & 1) ^ 1, 400);
-                mbar_expect_tx(&bars.full[st], bytes);
-                return sRing + st * kR2StageBytes;
-            };
-            auto load_raw = [&](int kt) {
-                for (int x = atom0; x < n_atoms; ++x, ++it) {
-                    const int br = x >> 2, at = x & 3;
-                    unsigned char* d = acquire(24576);
-                    uint64_t* fb = &bars.full[it % kR2Stages];
-                    tma_load_2d(d, br == 0 ? &tm.vn128c : &tm.vn128r, fb, at * 64, ci.s0 + ci.q0);
-                    tma_load_2d(d + 16384, br == 0 ? &tm.vn64c : &tm.vn64r, fb, at * 64, ci.s0 + kt * 64);
+            uint32_t pos = 0, eph = 0;     // next slot, per-slot parity of the empty barriers
+            auto acquire = [&](int n, uint32_t bytes, uint64_t*& fb) -> unsigned char* {
+                if (pos + n > n_slots) pos = 0;
+                for (int i = 0; i < n; ++i) {
+                    R2_WAIT(&bars.empty[pos + i], ((eph >> (pos + i)) & 1u) ^ 1u, 400);
+                    eph ^= 1u << (pos + i);
                 }
+                fb = &bars.full[pos];
+                mbar_expect_tx(fb, bytes);
+                unsigned char* d = sRing + pos * kR2SlotBytes;
+                pos += n;
+                return d;
             };
-            auto load_units = [&](int kt, int u0) {
-                if (reuse) return;
-                for (int u = u0; u < u0 + 4; ++u, ++it) {
-                    const int h = u >> 1, br = u & 1;
-                    unsigned char* d = acquire(24576);
-                    uint64_t* fb = &bars.full[it % kR2Stages];
-                    tma_load_2d(d, br == 0 ? &tm.q128c : &tm.q128r, fb, h * 64, ci.s0 + ci.q0);
-                    tma_load_2d(d + 16384, br == 0 ? &tm.k64c : &tm.k64r, fb, h * 64, ci.s0 + kt * 64);
-                }
-            };
-            auto load_vt = [&](int kt) {
-                for (int hf = 0; hf < 2; ++hf, ++it) {
-                    unsigned char* d = acquire(16384);
-                    uint64_t* fb = &bars.full[it % kR2Stages];
-                    tma_load_2d(d, &tm.vt, fb, kt * 64, b * 256 + hf * 128);
-                    tma_load_2d(d + 8192, &tm.vt, fb, kt * 64, b * 256 + hf * 128 + 64);
-                }
-            };
-            load_raw(0);
-            for (int kt = 0; kt < KT; ++kt) {
-                load_units(kt, 0);
-                if (kt + 1 < KT) load_raw(kt + 1);
-                load_units(kt, 4);
-                if (kt >= 1) load_vt(kt - 1);
+            // resident A operands
+            if (reuse) {
+                mbar_expect_tx(&bars.res_full, 4 * 16384);
+                for (int at = 0; at < 4; ++at) tma_load_2d(sRes + at * 16384, &tm.vn128r, &bars.res_full, at * 64, ci.s0 + ci.q0);
+            } else {
+                mbar_expect_tx(&bars.res_full, 8 * 16384);
+                for (int u = 0; u < 8; ++u)
+                    tma_load_2d(sRes + u * 16384, (u & 1) == 0 ? &tm.q128c : &tm.q128r, &bars.res_full, (u >> 1) * 64, ci.s0 + ci.q0);
             }
-            load_vt(KT - 1);
+            r2_schedule(KT, reuse, n_atoms, [&](int kind, int kt, int i) {
+                uint64_t* fb;
+                if (kind == 0) {
+                    unsigned char* d = acquire(1, 8192, fb);
+                    tma_load_2d(d, (i & 1) == 0 ? &tm.k64c : &tm.k64r, fb, (i >> 1) * 64, ci.s0 + kt * 64);
+                } else if (kind == 1) {
+                    const int br = i >> 2, at = i & 3;
+                    if (reuse) {
+                        unsigned char* d = acquire(1, 8192, fb);
+                        tma_load_2d(d, &tm.vn64r, fb, at * 64, ci.s0 + kt * 64);
+                    } else {
+                        unsigned char* d = acquire(3, 24576, fb);
+                        tma_load_2d(d, br == 0 ? &tm.vn128c : &tm.vn128r, fb, at * 64, ci.s0 + ci.q0);
+                        tma_load_2d(d + 16384, br == 0 ? &tm.vn64c : &tm.vn64r, fb, at * 64, ci.s0 + kt * 64);
+                    }
+                } else {
+                    unsigned char* d = acquire(2, 16384, fb);
+                    tma_load_2d(d, &tm.vt, fb, kt * 64, b * 256 + i * 128);
+                    tma_load_2d(d + 8192, &tm.vt, fb, kt * 64, b * 256 + i * 128 + 64);
+                }
+            });
         }
-    } else if (warp == 9) {
+    } else if (warp == 17) {
         // ------------------------------------------------ MMA issuer ------------------------------------------------
+        // (One consumer only: a second issuing warp that skips the other's ring items could run more than one barrier
+        // phase ahead of a slot, and a parity wait cannot tell phase k-1 from phase k+1.)
         if (lane == 0) {
             const uint32_t idesc64 = make_idesc_f16(BF16, 128, 64);
             const uint32_t idesc128 = make_idesc_f16(BF16, 128, 128);
-            uint32_t it = 0, iu = 0;     // ring stage counter, score-unit counter
-            auto wait_stage = [&]() -> unsigned char* {
-                const int st = it % kR2Stages;
-                mbar_wait(&bars.full[st], (it / kR2Stages) & 1, 410);
+            uint32_t pos = 0, fph = 0, iu = 0;     // next slot, per-slot parity of the full barriers, score-unit counter
+            auto wait_item = [&](int n, int& slot) -> unsigned char* {
+                if (pos + n > n_slots) pos = 0;
+                R2_WAIT(&bars.full[pos], (fph >> pos) & 1u, 410);
                 tc_fence_after();
-                return sRing + st * kR2StageBytes;
+                fph ^= 1u << pos;
+                slot = pos;
+                pos += n;
+                return sRing + slot * kR2SlotBytes;
             };
-            auto raw = [&](int kt) {          // raw-v similarities of tile kt (K = 256 as four 64-dim atoms per branch)
-                mbar_wait(&bars.r_empty, (kt & 1) ^ 1, 411);
-                tc_fence_after();
-                for (int x = atom0; x < n_atoms; ++x, ++it) {
-                    const int br = x >> 2, at = x & 3;
-                    unsigned char* d = wait_stage();
-                    const uint64_t da = make_smem_desc_sw128(smem_u32(d)), db = make_smem_desc_sw128(smem_u32(d + 16384));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(tmem + 256 + br * 64, da + 2 * k, db + 2 * k, idesc64, (at | k) ? 1u : 0u);
-                    umma_commit(&bars.empty[it % kR2Stages]);
-                }
-                umma_commit(&bars.r_full);
+            auto release = [&](int slot, int n) {
+                for (int i = 0; i < n; ++i) umma_commit(&bars.empty[slot + i]);
             };
-            auto units = [&](int u0) {
-                if (reuse) return;
-                for (int u = u0; u < u0 + 4; ++u, ++it, ++iu) {
+            R2_WAIT(&bars.res_full, 0, 414);
+            tc_fence_after();
+            r2_schedule(KT, reuse, n_atoms, [&](int kind, int kt, int i) {
+                int slot;
+                if (kind == 0) {                 // score unit i = 2 * head + branch
                     const int su = iu & 1;
-                    mbar_wait(&bars.s_empty[su], ((iu >> 1) & 1) ^ 1, 412);
-                    unsigned char* d = wait_stage();
-                    const uint64_t dq = make_smem_desc_sw128(smem_u32(d)), dk = make_smem_desc_sw128(smem_u32(d + 16384));
+                    R2_WAIT(&bars.s_empty[su], ((iu >> 1) & 1) ^ 1, 412);
+                    unsigned char* d = wait_item(1, slot);
+                    const uint64_t dq = make_smem_desc_sw128(smem_u32(sRes + i * 16384)), dk = make_smem_desc_sw128(smem_u32(d));
 #pragma unroll
                     for (int k = 0; k < 4; ++k) umma_f16(tmem + 384 + su * 64, dq + 2 * k, dk + 2 * k, idesc64, k ? 1u : 0u);
-                    umma_commit(&bars.empty[it % kR2Stages]);
+                    release(slot, 1);
                     umma_commit(&bars.s_full[su]);
-                }
-            };
-            auto wv = [&](int kt) {           // U += W(kt) @ V^T(kt), two 128-dim halves
-                const int wb = kt & 1;
-                mbar_wait(&bars.w_full[wb], (kt >> 1) & 1, 413);
-                tc_fence_after();
-                const uint64_t dw = make_smem_desc_sw128(smem_u32(sW + wb * 16384));
-                for (int hf = 0; hf < 2; ++hf, ++it) {
-                    unsigned char* d = wait_stage();
+                    ++iu;
+                } else if (kind == 1) {          // raw-v similarity atom (K = 256 as four 64-dim atoms per branch)
+                    const int br = i >> 2, at = i & 3;
+                    const int rb = reuse ? (kt & 1) : 0, use = reuse ? (kt >> 1) : kt;
+                    if (i == (reuse ? 4 : 0)) {
+                        R2_WAIT(&bars.r_empty[rb], (use & 1) ^ 1, 411);
+                        tc_fence_after();
+                    }
+                    const int n = reuse ? 1 : 3;
+                    unsigned char* d = wait_item(n, slot);
+                    const uint64_t da = make_smem_desc_sw128(smem_u32(reuse ? sRes + at * 16384 : d));
+                    const uint64_t db = make_smem_desc_sw128(smem_u32(reuse ? d : d + 16384));
+                    const uint32_t col = tmem + 256 + (reuse ? rb : br) * 64;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(col, da + 2 * k, db + 2 * k, idesc64, (at | k) ? 1u : 0u);
+                    release(slot, n);
+                    if (i == (reuse ? 7 : n_atoms - 1)) umma_commit(&bars.r_full[rb]);
+                } else {                         // U += W(kt) @ V^T(kt), 128-dim half i
+                    const int wb = reuse ? (kt & 1) : 0, use = reuse ? (kt >> 1) : kt;
+                    if (i == 0) {
+                        R2_WAIT(&bars.w_full[wb], use & 1, 413);
+                        tc_fence_after();
+                    }
+                    const uint64_t dw = make_smem_desc_sw128(smem_u32(sW + wb * 16384));
+                    unsigned char* d = wait_item(2, slot);
                     const uint64_t dv = make_smem_desc_sw128(smem_u32(d));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(tmem + hf * 128, dw + 2 * k, dv + 2 * k, idesc128, (kt | k) ? 1u : 0u);
-                    umma_commit(&bars.empty[it % kR2Stages]);
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem + i * 128, dw + 2 * k, dv + 2 * k, idesc128, (kt | k) ? 1u : 0u);
+                    release(slot, 2);
+                    if (i == 1) umma_commit(&bars.w_empty[wb]);
                 }
-                umma_commit(&bars.w_empty[wb]);
-            };
-            raw(0);
-            for (int kt = 0; kt < KT; ++kt) {
-                units(0);
-                if (kt + 1 < KT) raw(kt + 1);
-                units(4);
-                if (kt >= 1) wv(kt - 1);
-            }
-            wv(KT - 1);
+            });
             umma_commit(&bars.u_full);
         }
     } else {
         // ------------------------------------------------ softmax / weight warps ------------------------------------------------
+        // 16 warps: warp w owns TMEM lanes 32 * (w % 4) .. +31 (query rows) and column quarter w / 4 of every 64-key unit.
+        // (Four warps per scheduler: the per-unit chain  TMEM load -> ex2 -> accumulate  is latency-bound with two.)
+        constexpr int NC = 16;
         const int row = threadIdx.x & 127;
-        const int half = (threadIdx.x >> 7) & 1;
+        const int quarter = (threadIdx.x >> 7) & 3;
         const int q = ci.q0 + row;
         const bool q_ok = q < ci.n_loc;
         const bool self_attn = lay.self_attn != 0;
@@ -811,7 +878,7 @@ __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid
         float mcl[8], il[8];       // per unit u = 2*h + br: row max * log2e, 0.5 / row sum
 #pragma unroll
         for (int u = 0; u < 8; ++u) { mcl[u] = 0.f; il[u] = 0.f; }
-        if (q_ok) {
+        if (q_ok && !reuse) {
             const float* st = a.stats + (int64_t)(ci.lbase + q) * 16;
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
@@ -819,66 +886,69 @@ __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid
                 il[2 * h] = 0.5f / st[8 + h]; il[2 * h + 1] = 0.5f / st[12 + h];
             }
         }
-        const int c0 = half * 32;
+        const int c0 = quarter * NC;
+        // bits j of the NC columns starting at key `base` that fall into [k0, k1)
+        auto range_bits = [](int k0, int k1, int base) -> uint32_t {
+            const int x0 = min(max(k0 - base, 0), NC), x1 = min(max(k1 - base, 0), NC);
+            return x1 > x0 ? (((1u << x1) - 1u) & ~((1u << x0) - 1u)) : 0u;
+        };
         float den = 0.f;
         uint32_t iu = 0;
         for (int kt = 0; kt < KT; ++kt) {
             const int kbase = kt * 64;
             // ---- mask bits of this tile: visibility, head-mean raw-v cosine thresholds ----
-            uint32_t bits = 0;
-            mbar_wait(&bars.r_full, kt & 1, 420);
+            uint32_t bits = range_bits(n_glob0, ci.n_clip, kbase + c0) | range_bits(lo, min(hi, ci.n_clip), kbase + c0);
+            const int rb = reuse ? (kt & 1) : 0, ruse = reuse ? (kt >> 1) : kt;
+            R2_WAIT(&bars.r_full[rb], ruse & 1, 420);
             tc_fence_after();
             {
-                uint32_t rc[32], rr[32];
-                if (!reuse) tmem_ld_32x32(lane_base + 256 + c0, rc);
-                if (use_obj) tmem_ld_32x32(lane_base + 320 + c0, rr);
+                uint32_t rc[NC], rr[NC];
+                if (!reuse) tmem_ld_32x16(lane_base + 256 + c0, rc);
+                if (use_obj) tmem_ld_32x16(lane_base + (reuse ? 256 + rb * 64 : 320) + c0, rr);
                 tmem_ld_wait();
+                uint32_t pass = 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int k = kbase + c0 + j;
-                    bool ok = k < ci.n_clip && (k >= n_glob0 || (k >= lo && k < hi));
-                    if (!reuse) ok = ok && (__uint_as_float(rc[j]) * 0.25f > a.sim_thresh);     // (already folded into w_in)
+                for (int j = 0; j < NC; ++j) {
+                    bool ok = true;
+                    if (!reuse) ok = __uint_as_float(rc[j]) * 0.25f > a.sim_thresh;                    // (already folded into w_in)
                     if (use_obj) ok = ok && (__uint_as_float(rr[j]) * 0.25f > a.conf_sim_thresh);
-                    bits |= ok ? (1u << j) : 0u;
+                    pass |= ok ? (1u << j) : 0u;
                 }
+                bits &= pass;
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars.r_empty);
-            float w[32];
-            float d0 = 0.f, d1 = 0.f;
+            if (lane == 0) mbar_arrive(&bars.r_empty[rb]);
+            float w[NC];
             if (!reuse) {
                 // ---- head-sum of the normalised attention over the 8 (head, branch) score units ----
-                float as[32];
+                float as[NC];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) as[j] = 0.f;
+                for (int j = 0; j < NC; ++j) as[j] = 0.f;
 #pragma unroll
                 for (int u = 0; u < 8; ++u, ++iu) {
                     const int su = iu & 1;
-                    mbar_wait(&bars.s_full[su], (iu >> 1) & 1, 421);
+                    R2_WAIT(&bars.s_full[su], (iu >> 1) & 1, 421);
                     tc_fence_after();
-                    uint32_t r[32];
-                    tmem_ld_32x32(lane_base + 384 + su * 64 + c0, r);
+                    uint32_t r[NC];
+                    tmem_ld_32x16(lane_base + 384 + su * 64 + c0, r);
                     tmem_ld_wait();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars.s_empty[su]);      // the unit is in registers: release it before the math
                     const float m = mcl[u], sc = il[u];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) as[j] = fmaf(ex2_approx(fmaf(__uint_as_float(r[j]), kLog2e, -m)), sc, as[j]);
+                    for (int j = 0; j < NC; ++j) as[j] = fmaf(ex2_approx(fmaf(__uint_as_float(r[j]), kLog2e, -m)), sc, as[j]);
                 }
                 // ---- weights: mask * exp(mean attention) ----
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    w[j] = ((bits >> j) & 1u) ? ex2_approx(as[j] * (0.25f * kLog2e)) : 0.f;
-                    w[j + 1] = ((bits >> (j + 1)) & 1u) ? ex2_approx(as[j + 1] * (0.25f * kLog2e)) : 0.f;
-                }
+                for (int j = 0; j < NC; ++j) w[j] = ((bits >> j) & 1u) ? ex2_approx(as[j] * (0.25f * kLog2e)) : 0.f;
             } else {
                 // ---- weights of the cls launch (16-bit, sim mask applied) gated by the obj mask ----
                 const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.w_in) +
                                                                   (int64_t)(ci.lbase + min(q, ci.n_loc - 1)) * lay.nk_pitch + kbase + c0);
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
+                for (int cc = 0; cc < NC / 8; ++cc) {
                     const uint4 raw = __ldg(src + cc);
                     const uint32_t wd[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
@@ -896,14 +966,15 @@ __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid
                     }
                 }
             }
+            float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) { d0 += w[j]; d1 += w[j + 1]; }
+            for (int j = 0; j < NC; j += 2) { d0 += w[j]; d1 += w[j + 1]; }
             den += d0 + d1;
-            const int wb = kt & 1;
-            mbar_wait(&bars.w_empty[wb], ((kt >> 1) & 1) ^ 1, 422);
+            const int wb = reuse ? (kt & 1) : 0;
+            R2_WAIT(&bars.w_empty[wb], (ruse & 1) ^ 1, 422);
             unsigned char* sWb = sW + wb * 16384;
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int cc = 0; cc < NC / 8; ++cc) {
                 const uint4 pk = make_uint4(pack2<BF16>(w[cc * 8], w[cc * 8 + 1]), pack2<BF16>(w[cc * 8 + 2], w[cc * 8 + 3]),
                                             pack2<BF16>(w[cc * 8 + 4], w[cc * 8 + 5]), pack2<BF16>(w[cc * 8 + 6], w[cc * 8 + 7]));
                 *reinterpret_cast<uint4*>(sWb + sw128_off(row, (c0 >> 3) + cc)) = pk;
@@ -914,16 +985,16 @@ __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars.w_full[wb]);
         }
-        // ---- U / den: each column half of a row drains 128 of the 256 output columns ----
-        bars.xch[half][row] = den;
-        softmax_bar_sync();
-        den += bars.xch[half ^ 1][row];
-        mbar_wait(&bars.u_full, 0, 423);
+        // ---- U / den: each column quarter of a row drains 64 of the 256 output columns ----
+        bars.xch[quarter][row] = den;
+        asm volatile("bar.sync 1, 512;\n" ::: "memory");
+        den = (bars.xch[0][row] + bars.xch[1][row]) + (bars.xch[2][row] + bars.xch[3][row]);
+        R2_WAIT(&bars.u_full, 0, 423);
         tc_fence_after();
         const float inv = 1.f / den;
         uint16_t* dst = reinterpret_cast<uint16_t*>(a.out);
 #pragma unroll 1
-        for (int cb = half * 128; cb < half * 128 + 128; cb += 32) {
+        for (int cb = quarter * 64; cb < quarter * 64 + 64; cb += 32) {
             uint32_t u[32];
             tmem_ld_32x32(lane_base + cb, u);
             tmem_ld_wait();
@@ -937,9 +1008,12 @@ __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid
             }
         }
     }
+#ifdef TSCD_R2_PROF
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(&g_r2_wait[31], (unsigned long long)(clock64() - tk0));
+#endif
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == 17) {
         tc_fence_after();
         tmem_dealloc<512>(tmem);
     }
@@ -1013,6 +1087,7 @@ extern "C" int tscd_attn_pv(const tscd_attn_pv_args* a, void* stream) {
 extern "C" int tscd_attn_round2(const tscd_attn_round2_args* a, void* stream) {
     using namespace tscd;
     if (!a || !layout_ok(a->lay)) return TSCD_ERR_INVALID_ARG;
+    if (a->w_in && !a->use_obj_mask) return TSCD_ERR_INVALID_ARG;      // w_in is the cls launch's weights: only the obj launch re-uses them
     const tscd_attn_layout& l = a->lay;
     const int bf = l.dtype == TSCD_BF16;
     R2Tmaps tm;
@@ -1027,7 +1102,7 @@ extern "C" int tscd_attn_round2(const tscd_attn_round2_args* a, void* stream) {
     rc |= make_tmap_kmajor(&tm.vn64r, a->vn_reg, bf, l.row_cap, 256, 256, 64);
     rc |= make_tmap_kmajor(&tm.vt, a->vt, bf, (int64_t)l.B * 256, l.nk_pitch, l.nk_pitch, 64);
     if (rc) return TSCD_ERR_CUDA;
-    const size_t smem = kR2Stages * kR2StageBytes + 32768 + sizeof(R2Bars);
+    const size_t smem = kR2SmemBytes + sizeof(R2Bars);
     dim3 grid((l.nk_pitch + 127) / 128, l.B);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (bf) {
@@ -1040,6 +1115,16 @@ extern "C" int tscd_attn_round2(const tscd_attn_round2_args* a, void* stream) {
     TSCD_CUDA_CHECK_LAUNCH();
     return TSCD_OK;
 }
+
+#ifdef TSCD_R2_PROF
+extern "C" int tscd_debug_r2_waits(unsigned long long* out, int reset) {
+    if (reset) {
+        unsigned long long z[32] = {};
+        return cudaMemcpyToSymbol(tscd::g_r2_wait, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+    }
+    return cudaMemcpyFromSymbol(out, tscd::g_r2_wait, 32 * sizeof(unsigned long long)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" int tscd_attn_rowmeta(const tscd_attn_rowmeta_args* a, void* stream) {
     using namespace tscd;
