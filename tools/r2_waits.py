@@ -13,8 +13,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tscd_b200 import _lib as L, aggregate, weights  # noqa: E402
 
-TAGS = {0: "tma: ring slot empty", 10: "mma: ring item full", 11: "mma: R empty", 12: "mma: S empty", 13: "mma: W full",
-        14: "mma: resident full", 20: "softmax: R full", 21: "softmax: S full", 22: "softmax: W empty", 23: "softmax: U full",
+TAGS = {0: "tma-s: slot empty", 1: "tma-x: slot empty", 10: "mma-s: item full", 12: "mma-s: S empty", 15: "mma-x: item full",
+        11: "mma-x: R empty", 13: "mma-x: W full", 14: "mma: resident full", 20: "softmax: R full", 21: "softmax: S full", 22: "softmax: W empty", 23: "softmax: U full",
         31: "kernel total"}
 
 

@@ -618,27 +618,27 @@ struct R2Tmaps {
     CUtensorMap q128c, q128r, k64c, k64r, vn128c, vn128r, vn64c, vn64r, vt;
 };
 
-// Warp-specialised like attn_pv.  The kernel is bound by the latency of L2 -> shared-memory operand traffic, so the A
-// operands that every key tile re-uses stay RESIDENT in shared memory for the whole CTA (loaded once):
-//   cls launch (no w_in):  the 8 query head slices  Q[h][branch]  [128 x 64]   (8 x 16K = 128K)
-//   obj launch (w_in):     the 4 raw-v query atoms of the reg branch [128 x 64] (4 x 16K)
-// Everything else streams through ONE ring of 8 KB slots (10 / 16 of them) in a fixed order (r2_schedule) that the TMA
-// warp produces and the MMA warp consumes; an item takes 1..3 contiguous slots, one that would straddle the end
-// restarts at slot 0:
-//   S unit          = K head slice [64 x 64]                                   1 slot
-//   raw atom        = Vn(query) [128 x 64] 16K + Vn(keys) [64 x 64] 8K          3 slots  (cls launch)
-//                     Vn(keys) only, the query atom is resident                  1 slot   (obj launch)
-//   V^T half        = [128 dims x 64 keys]                                      2 slots
-// The schedule interleaves the item kinds (unit, raw atom of the next tile, unit, ... , V^T half of the previous tile)
-// so that the shallow ring never holds a burst of one kind while the softmax warps wait for another.
+// Warp-specialised like attn_pv.  The kernel is bound by the latency of L2 -> shared-memory operand traffic and of the
+// single-thread UMMA issue, so
+//  * the A operands that every key tile re-uses stay RESIDENT in shared memory for the whole CTA (loaded once):
+//      cls launch (no w_in):  the 8 query head slices  Q[h][branch]  [128 x 64]   (8 x 16K = 128K)
+//      obj launch (w_in):     the 4 raw-v query atoms of the reg branch [128 x 64] (4 x 16K)
+//  * the rest streams through TWO independent pipelines, each one TMA warp -> ring of 8 KB slots -> one MMA warp
+//    (single producer, single consumer per ring: every waiter sees every phase of its barriers):
+//      S pipeline (cls launch only, 4 slots):  the 8 score units of every tile; item = K head slice [64 x 64], 1 slot
+//      X pipeline (6 / 16 slots):  raw(0), then per tile kt:  W(kt-1) @ V^T halves | raw-v atoms of tile kt+1
+//          raw atom  = Vn(query) [128 x 64] 16K + Vn(keys) [64 x 64] 8K           3 slots  (cls launch)
+//                      Vn(keys) only, the query atom is resident                   1 slot   (obj launch)
+//          V^T half  = [128 dims x 64 keys]                                       2 slots
+//    An item takes contiguous slots; one that would straddle the end of its ring restarts at the ring's first slot.
 // TMEM: U 256 | R_cls 64 | R_reg 64 | two score units of 64 columns (obj launch: the two R regions double-buffer the
-// reg-branch similarity).  The 8 softmax warps read the raw-v similarities of a tile first (mask bits -> registers),
+// reg-branch similarity).  The 16 softmax warps read the raw-v similarities of a tile first (mask bits -> registers),
 // then the 8 score units (head-sum of the normalised attention, exact statistics from attn_pv), then write the
 // round-2 weights as the A operand of W @ V^T.
-constexpr int kR2Threads = 576;      // 16 softmax warps + TMA warp + MMA warp
+constexpr int kR2Threads = 640;      // 16 softmax warps + (TMA, MMA) of the S pipeline + (TMA, MMA) of the X pipeline
 constexpr int kR2MaxSlots = 16;
 constexpr int kR2SlotBytes = 8192;
-constexpr int kR2SmemBytes = 229376;      // resident operands + ring + weight buffers (mode-dependent split)
+constexpr int kR2SmemBytes = 229376;      // resident operands + rings + weight buffers (mode-dependent split)
 
 struct R2Bars {
     uint64_t full[kR2MaxSlots], empty[kR2MaxSlots];
@@ -651,31 +651,35 @@ struct R2Bars {
     float xch[4][128];
 };
 
-// f(kind, kt, i): kind 0 = score unit i of tile kt, 1 = raw atom i of tile kt, 2 = V^T half i of tile kt
-template <class F>
-__device__ __forceinline__ void r2_schedule(int KT, bool reuse, int n_atoms, F&& f) {
-    if (reuse) {
-        for (int x = 4; x < 8; ++x) f(1, 0, x);
-        for (int kt = 0; kt < KT; ++kt) {
-            if (kt + 1 < KT)
-                for (int x = 4; x < 8; ++x) f(1, kt + 1, x);
-            if (kt >= 1) { f(2, kt - 1, 0); f(2, kt - 1, 1); }
-        }
-        f(2, KT - 1, 0); f(2, KT - 1, 1);
-        return;
+// One side of a ring: slot cursor + per-slot barrier parities (the producer tracks `empty`, the consumer `full`).
+struct R2Ring {
+    int first, count;        // slots [first, first + count)
+    int pos;
+    uint32_t ph;
+    __device__ __forceinline__ R2Ring(int f, int c) : first(f), count(c), pos(f), ph(0) {}
+    // next(n): first slot of the next item of n slots.  parity(s): this side's phase bit of slot s, then flipped -- the
+    // producer calls it for every slot of an item (all `empty` barriers cycle), the consumer for the first only (`full`).
+    __device__ __forceinline__ int next(int n) {
+        if (pos + n > first + count) pos = first;
+        const int s = pos;
+        pos += n;
+        return s;
     }
-    for (int x = 0; x < 4; ++x) { f(1, 0, x); if (n_atoms == 8) f(1, 0, x + 4); }
+    __device__ __forceinline__ uint32_t parity(int s) {
+        const uint32_t p = (ph >> s) & 1u;
+        ph ^= 1u << s;
+        return p;
+    }
+};
+
+// X pipeline order.  f(kind, kt, i): kind 1 = raw atom i of tile kt, 2 = V^T half i of tile kt
+template <class F>
+__device__ __forceinline__ void r2_x_schedule(int KT, int atom0, int atom1, F&& f) {
+    for (int x = atom0; x < atom1; ++x) f(1, 0, x);
     for (int kt = 0; kt < KT; ++kt) {
-        for (int i = 0; i < 4; ++i) {
-            f(0, kt, i);
-            if (kt + 1 < KT) { f(1, kt + 1, i); if (n_atoms == 8) f(1, kt + 1, i + 4); }
-        }
-        f(0, kt, 4);
-        if (kt >= 1) f(2, kt - 1, 0);
-        f(0, kt, 5);
-        if (kt >= 1) f(2, kt - 1, 1);
-        f(0, kt, 6);
-        f(0, kt, 7);
+        if (kt >= 1) { f(2, kt - 1, 0); f(2, kt - 1, 1); }
+        if (kt + 1 < KT)
+            for (int x = atom0; x < atom1; ++x) f(1, kt + 1, x);
     }
     f(2, KT - 1, 0); f(2, KT - 1, 1);
 }
@@ -687,7 +691,7 @@ __device__ __forceinline__ void r2_wait_prof(uint64_t* bar, uint32_t parity, int
     const long long t0 = clock64();
     tc::mbar_wait(bar, parity, tag);
     const long long dt = clock64() - t0;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x == 0 || threadIdx.x == 512 || threadIdx.x == 544))
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x == 0 || (threadIdx.x >= 512 && (threadIdx.x & 31) == 0)))
         atomicAdd(&g_r2_wait[tag - 400], (unsigned long long)dt);
 }
 #define R2_WAIT r2_wait_prof
@@ -716,10 +720,11 @@ __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid
     // launch only needs the reg-branch raw-v similarity (obj mask) -- no score units, no exponentials
     const bool reuse = a.w_in != nullptr;
     const int n_atoms = use_obj ? 8 : 4;
-    const int n_slots = reuse ? 16 : 10;
+    const int n_s = reuse ? 0 : 4, n_x = reuse ? 16 : 6;          // ring slots of the S / X pipelines
+    const int atom0 = reuse ? 4 : 0, atom1 = reuse ? 8 : n_atoms;
     unsigned char* sRes = smem;                                   // resident A operands: 4 or 8 x 16K
     unsigned char* sRing = smem + (reuse ? 65536 : 131072);       // 16 or 10 x 8K
-    unsigned char* sW = sRing + n_slots * kR2SlotBytes;           // 2 or 1 x 16K weights [128 x 64 keys]
+    unsigned char* sW = sRing + (n_s + n_x) * kR2SlotBytes;       // 2 or 1 x 16K weights [128 x 64 keys]
     R2Bars& bars = *reinterpret_cast<R2Bars*>(smem + kR2SmemBytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -744,21 +749,8 @@ __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid
     const uint32_t tmem = bars.tmem_base;
     const int KT = (ci.n_clip + 63) / 64;
     if (warp == 16) {
-        // ------------------------------------------------ TMA producer ------------------------------------------------
+        // ------------------------------------------------ S pipeline: TMA producer ------------------------------------------------
         if (lane == 0) {
-            uint32_t pos = 0, eph = 0;     // next slot, per-slot parity of the empty barriers
-            auto acquire = [&](int n, uint32_t bytes, uint64_t*& fb) -> unsigned char* {
-                if (pos + n > n_slots) pos = 0;
-                for (int i = 0; i < n; ++i) {
-                    R2_WAIT(&bars.empty[pos + i], ((eph >> (pos + i)) & 1u) ^ 1u, 400);
-                    eph ^= 1u << (pos + i);
-                }
-                fb = &bars.full[pos];
-                mbar_expect_tx(fb, bytes);
-                unsigned char* d = sRing + pos * kR2SlotBytes;
-                pos += n;
-                return d;
-            };
             // resident A operands
             if (reuse) {
                 mbar_expect_tx(&bars.res_full, 4 * 16384);
@@ -767,91 +759,109 @@ __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid
                 mbar_expect_tx(&bars.res_full, 8 * 16384);
                 for (int u = 0; u < 8; ++u)
                     tma_load_2d(sRes + u * 16384, (u & 1) == 0 ? &tm.q128c : &tm.q128r, &bars.res_full, (u >> 1) * 64, ci.s0 + ci.q0);
+                R2Ring ring(0, n_s);
+                for (int kt = 0; kt < KT; ++kt)
+                    for (int u = 0; u < 8; ++u) {
+                        const int sl = ring.next(1);
+                        R2_WAIT(&bars.empty[sl], ring.parity(sl) ^ 1u, 400);
+                        mbar_expect_tx(&bars.full[sl], 8192);
+                        tma_load_2d(sRing + sl * kR2SlotBytes, (u & 1) == 0 ? &tm.k64c : &tm.k64r, &bars.full[sl], (u >> 1) * 64, ci.s0 + kt * 64);
+                    }
             }
-            r2_schedule(KT, reuse, n_atoms, [&](int kind, int kt, int i) {
-                uint64_t* fb;
-                if (kind == 0) {
-                    unsigned char* d = acquire(1, 8192, fb);
-                    tma_load_2d(d, (i & 1) == 0 ? &tm.k64c : &tm.k64r, fb, (i >> 1) * 64, ci.s0 + kt * 64);
-                } else if (kind == 1) {
+        }
+    } else if (warp == 18) {
+        // ------------------------------------------------ X pipeline: TMA producer ------------------------------------------------
+        if (lane == 0) {
+            R2Ring ring(n_s, n_x);
+            r2_x_schedule(KT, atom0, atom1, [&](int kind, int kt, int i) {
+                const int n = kind == 2 ? 2 : (reuse ? 1 : 3);
+                const int sl = ring.next(n);
+                for (int j = 0; j < n; ++j) R2_WAIT(&bars.empty[sl + j], ring.parity(sl + j) ^ 1u, 401);
+                uint64_t* fb = &bars.full[sl];
+                unsigned char* d = sRing + sl * kR2SlotBytes;
+                mbar_expect_tx(fb, n * 8192);
+                if (kind == 1) {
                     const int br = i >> 2, at = i & 3;
                     if (reuse) {
-                        unsigned char* d = acquire(1, 8192, fb);
                         tma_load_2d(d, &tm.vn64r, fb, at * 64, ci.s0 + kt * 64);
                     } else {
-                        unsigned char* d = acquire(3, 24576, fb);
                         tma_load_2d(d, br == 0 ? &tm.vn128c : &tm.vn128r, fb, at * 64, ci.s0 + ci.q0);
                         tma_load_2d(d + 16384, br == 0 ? &tm.vn64c : &tm.vn64r, fb, at * 64, ci.s0 + kt * 64);
                     }
                 } else {
-                    unsigned char* d = acquire(2, 16384, fb);
                     tma_load_2d(d, &tm.vt, fb, kt * 64, b * 256 + i * 128);
                     tma_load_2d(d + 8192, &tm.vt, fb, kt * 64, b * 256 + i * 128 + 64);
                 }
             });
         }
     } else if (warp == 17) {
-        // ------------------------------------------------ MMA issuer ------------------------------------------------
-        // (One consumer only: a second issuing warp that skips the other's ring items could run more than one barrier
-        // phase ahead of a slot, and a parity wait cannot tell phase k-1 from phase k+1.)
+        // ------------------------------------------------ S pipeline: MMA issuer (score units) ------------------------------------------------
+        if (lane == 0 && !reuse) {
+            const uint32_t idesc64 = make_idesc_f16(BF16, 128, 64);
+            R2Ring ring(0, n_s);
+            R2_WAIT(&bars.res_full, 0, 414);
+            tc_fence_after();
+            uint32_t iu = 0;
+            for (int kt = 0; kt < KT; ++kt)
+                for (int u = 0; u < 8; ++u, ++iu) {          // score unit u = 2 * head + branch
+                    const int su = iu & 1;
+                    R2_WAIT(&bars.s_empty[su], ((iu >> 1) & 1) ^ 1, 412);
+                    const int sl = ring.next(1);
+                    R2_WAIT(&bars.full[sl], ring.parity(sl), 410);
+                    tc_fence_after();
+                    const uint64_t dq = make_smem_desc_sw128(smem_u32(sRes + u * 16384));
+                    const uint64_t dk = make_smem_desc_sw128(smem_u32(sRing + sl * kR2SlotBytes));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem + 384 + su * 64, dq + 2 * k, dk + 2 * k, idesc64, k ? 1u : 0u);
+                    umma_commit(&bars.empty[sl]);
+                    umma_commit(&bars.s_full[su]);
+                }
+        }
+    } else if (warp == 19) {
+        // ------------------------------------------------ X pipeline: MMA issuer (raw-v similarity, W @ V^T) ------------------------------------------------
         if (lane == 0) {
             const uint32_t idesc64 = make_idesc_f16(BF16, 128, 64);
             const uint32_t idesc128 = make_idesc_f16(BF16, 128, 128);
-            uint32_t pos = 0, fph = 0, iu = 0;     // next slot, per-slot parity of the full barriers, score-unit counter
-            auto wait_item = [&](int n, int& slot) -> unsigned char* {
-                if (pos + n > n_slots) pos = 0;
-                R2_WAIT(&bars.full[pos], (fph >> pos) & 1u, 410);
+            R2Ring ring(n_s, n_x);
+            if (reuse) {
+                R2_WAIT(&bars.res_full, 0, 414);
                 tc_fence_after();
-                fph ^= 1u << pos;
-                slot = pos;
-                pos += n;
-                return sRing + slot * kR2SlotBytes;
-            };
-            auto release = [&](int slot, int n) {
-                for (int i = 0; i < n; ++i) umma_commit(&bars.empty[slot + i]);
-            };
-            R2_WAIT(&bars.res_full, 0, 414);
-            tc_fence_after();
-            r2_schedule(KT, reuse, n_atoms, [&](int kind, int kt, int i) {
-                int slot;
-                if (kind == 0) {                 // score unit i = 2 * head + branch
-                    const int su = iu & 1;
-                    R2_WAIT(&bars.s_empty[su], ((iu >> 1) & 1) ^ 1, 412);
-                    unsigned char* d = wait_item(1, slot);
-                    const uint64_t dq = make_smem_desc_sw128(smem_u32(sRes + i * 16384)), dk = make_smem_desc_sw128(smem_u32(d));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(tmem + 384 + su * 64, dq + 2 * k, dk + 2 * k, idesc64, k ? 1u : 0u);
-                    release(slot, 1);
-                    umma_commit(&bars.s_full[su]);
-                    ++iu;
-                } else if (kind == 1) {          // raw-v similarity atom (K = 256 as four 64-dim atoms per branch)
+            }
+            r2_x_schedule(KT, atom0, atom1, [&](int kind, int kt, int i) {
+                const int n = kind == 2 ? 2 : (reuse ? 1 : 3);
+                if (kind == 1) {                 // raw-v similarity atom (K = 256 as four 64-dim atoms per branch)
                     const int br = i >> 2, at = i & 3;
                     const int rb = reuse ? (kt & 1) : 0, use = reuse ? (kt >> 1) : kt;
-                    if (i == (reuse ? 4 : 0)) {
+                    if (i == atom0) {
                         R2_WAIT(&bars.r_empty[rb], (use & 1) ^ 1, 411);
                         tc_fence_after();
                     }
-                    const int n = reuse ? 1 : 3;
-                    unsigned char* d = wait_item(n, slot);
+                    const int sl = ring.next(n);
+                    R2_WAIT(&bars.full[sl], ring.parity(sl), 415);
+                    tc_fence_after();
+                    unsigned char* d = sRing + sl * kR2SlotBytes;
                     const uint64_t da = make_smem_desc_sw128(smem_u32(reuse ? sRes + at * 16384 : d));
                     const uint64_t db = make_smem_desc_sw128(smem_u32(reuse ? d : d + 16384));
                     const uint32_t col = tmem + 256 + (reuse ? rb : br) * 64;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) umma_f16(col, da + 2 * k, db + 2 * k, idesc64, (at | k) ? 1u : 0u);
-                    release(slot, n);
-                    if (i == (reuse ? 7 : n_atoms - 1)) umma_commit(&bars.r_full[rb]);
+                    for (int j = 0; j < n; ++j) umma_commit(&bars.empty[sl + j]);
+                    if (i == atom1 - 1) umma_commit(&bars.r_full[rb]);
                 } else {                         // U += W(kt) @ V^T(kt), 128-dim half i
                     const int wb = reuse ? (kt & 1) : 0, use = reuse ? (kt >> 1) : kt;
                     if (i == 0) {
                         R2_WAIT(&bars.w_full[wb], use & 1, 413);
                         tc_fence_after();
                     }
+                    const int sl = ring.next(2);
+                    R2_WAIT(&bars.full[sl], ring.parity(sl), 415);
+                    tc_fence_after();
                     const uint64_t dw = make_smem_desc_sw128(smem_u32(sW + wb * 16384));
-                    unsigned char* d = wait_item(2, slot);
-                    const uint64_t dv = make_smem_desc_sw128(smem_u32(d));
+                    const uint64_t dv = make_smem_desc_sw128(smem_u32(sRing + sl * kR2SlotBytes));
 #pragma unroll
                     for (int k = 0; k < 4; ++k) umma_f16(tmem + i * 128, dw + 2 * k, dv + 2 * k, idesc128, (kt | k) ? 1u : 0u);
-                    release(slot, 2);
+                    umma_commit(&bars.empty[sl]);
+                    umma_commit(&bars.empty[sl + 1]);
                     if (i == 1) umma_commit(&bars.w_empty[wb]);
                 }
             });
