@@ -240,16 +240,20 @@ struct PvTmaps {
 // -------------------------------------------------------------------------------------------------------
 // attn_pv: row max (pass A), exp/sum + P@V (pass B) -- warp-specialised, mbarrier-pipelined
 //
-//   warp 4 (one thread)  TMA producer: Q tiles (double-buffered per head) and a 3-stage ring of key tiles
+//   warp 16 (one thread) TMA producer: Q tiles (double-buffered per head) and a 3-stage ring of key tiles
 //                        (pass A: Kc|Kr of 128 keys; pass B: Kc|Kr|Vc^T|Vr^T of 64 keys), 32 KB per stage;
-//   warp 5 (one thread)  tcgen05.mma issuer: S = Q K^T of tile g+1 is issued before P(g) @ V(g), into one of two
-//                        TMEM score buffers, so the tensor pipe works while the softmax warps are busy;
-//   warps 0-3            softmax: thread == query row == TMEM lane; tcgen05.ld, visibility mask from the row's own
-//                        frame range (no shared-memory side table), exp2, fp16/bf16 probabilities written as the
-//                        swizzled K-major A operand of the P@V products (two P buffers).
+//   warp 17 (one thread) tcgen05.mma issuer of the scores S = Q K^T (two TMEM score buffers: tile g+1 is computed
+//                        while the softmax warps work on tile g);
+//   warp 18 (one thread) tcgen05.mma issuer of P(g) @ V(g) (pass B); its commit releases the ring stage -- the scores
+//                        of that stage were consumed before its probabilities existed.  (One issuing thread pays ~15
+//                        dependent instructions per UMMA; two issuers halve that serial chain.)
+//   warps 0-15           softmax: thread == query row == TMEM lane, warp w owns lanes 32 * (w % 4) and column quarter
+//                        w / 4 of every tile (four warps per scheduler hide the TMEM-load -> ex2 -> store chain);
+//                        visibility mask from the row's own frame range (no shared-memory side table), exp2, fp16/bf16
+//                        probabilities written as the swizzled K-major A operand of the P@V products (two P buffers).
 //   TMEM: pass A  2 x (S_cls 128 | S_reg 128);   pass B  2 x (S_cls 64 | S_reg 64) | O_cc O_cr O_rc O_rr (64 each).
 // -------------------------------------------------------------------------------------------------------
-constexpr int kPvThreads = 320;     // 8 softmax warps (2 per scheduler), TMA warp, MMA warp
+constexpr int kPvThreads = 608;     // 16 softmax warps (4 per scheduler), TMA warp, 2 MMA warps
 constexpr int kPvStages = 3;
 
 struct PvBars {
@@ -259,15 +263,18 @@ struct PvBars {
     uint64_t p_full[2], p_empty[2];
     uint64_t o_full, o_empty;
     uint32_t tmem_base;
-    float xch[2][128][2];      // partial row sums exchanged between the two column halves of a row (cls, reg)
+    float xch[4][128];         // partial row sums exchanged between the four column quarters of a row (cls, then reg:
+                               // the 227 KB window has no room for both at once)
 };
+
+static_assert(65536 + kPvStages * 32768 + 65536 + sizeof(PvBars) <= 232448, "attn_pv: over the 227 KB shared-memory window");
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+__device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
 
 template <bool BF16>
 __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_constant__ PvTmaps tm, const tscd_attn_pv_args a) {
@@ -286,19 +293,19 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
     PvBars& bars = *reinterpret_cast<PvBars*>(sP + 65536);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 256) {
+    if (threadIdx.x == 512) {
         tma_prefetch_desc(&tm.qc); tma_prefetch_desc(&tm.kc); tma_prefetch_desc(&tm.qr); tma_prefetch_desc(&tm.kr);
         tma_prefetch_desc(&tm.k64c); tma_prefetch_desc(&tm.k64r); tma_prefetch_desc(&tm.vtc); tma_prefetch_desc(&tm.vtr);
         for (int i = 0; i < kPvStages; ++i) { mbar_init(&bars.kv_full[i], 1); mbar_init(&bars.kv_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars.q_full[i], 1); mbar_init(&bars.q_empty[i], 1);
-            mbar_init(&bars.s_full[i], 1); mbar_init(&bars.s_empty[i], 8);
-            mbar_init(&bars.p_full[i], 8); mbar_init(&bars.p_empty[i], 1);
+            mbar_init(&bars.s_full[i], 1); mbar_init(&bars.s_empty[i], 16);
+            mbar_init(&bars.p_full[i], 16); mbar_init(&bars.p_empty[i], 1);
         }
-        mbar_init(&bars.o_full, 1); mbar_init(&bars.o_empty, 8);
+        mbar_init(&bars.o_full, 1); mbar_init(&bars.o_empty, 16);
         fence_barrier_init();
     }
-    if (warp == 9) tmem_alloc<512>(&bars.tmem_base);
+    if (warp == 17) tmem_alloc<512>(&bars.tmem_base);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -310,8 +317,8 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
 
     // softmax-thread state
     const int row = threadIdx.x & 127;
-    const int half = (threadIdx.x >> 7) & 1;     // softmax warps 0-3 own the lower column half of every tile, 4-7 the upper
-    const bool is_sm = warp < 8;
+    const int quarter = (threadIdx.x >> 7) & 3;  // softmax warps 4q .. 4q+3 own column quarter q of every tile
+    const bool is_sm = warp < 16;
     const int q = ci.q0 + row;
     const bool q_ok = is_sm && q < ci.n_loc;
     const bool self_attn = lay.self_attn != 0;
@@ -326,7 +333,7 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
     float mxc[4], mxr[4];
 
     // ======================================= pass A: row maxima =======================================
-    if (warp == 8) {
+    if (warp == 16) {
         if (lane == 0) {
             uint32_t it = 0;
             for (int h = 0; h < 4; ++h) {
@@ -344,7 +351,7 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 17) {
         if (lane == 0) {
             const uint32_t idesc128 = make_idesc_f16(BF16, 128, 128);
             uint32_t it = 0;
@@ -370,7 +377,7 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                 umma_commit(&bars.q_empty[qb]);
             }
         }
-    } else {
+    } else if (is_sm) {
         uint32_t it = 0;
         for (int h = 0; h < 4; ++h) {
             float mc = -INFINITY, mr = -INFINITY;
@@ -379,8 +386,8 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                 mbar_wait(&bars.s_full[sb], (it >> 1) & 1, 320);
                 tc_fence_after();
                 const bool all_vis = kbase >= n_glob0 && kbase + 128 <= ci.n_clip;
-#pragma unroll 1
-                for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
+                {
+                    const int c0 = quarter * 32;
                     uint32_t rc[32], rr[32];
                     tmem_ld_32x32(lane_base + sb * 256 + c0, rc);
                     tmem_ld_32x32(lane_base + sb * 256 + 128 + c0, rr);
@@ -406,8 +413,8 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars.s_empty[sb]);
             }
-            reinterpret_cast<float*>(sP)[(half * 128 + row) * 8 + h] = mc;      // sP is idle during pass A
-            reinterpret_cast<float*>(sP)[(half * 128 + row) * 8 + 4 + h] = mr;
+            reinterpret_cast<float*>(sP)[(quarter * 128 + row) * 8 + h] = mc;      // sP is idle during pass A
+            reinterpret_cast<float*>(sP)[(quarter * 128 + row) * 8 + 4 + h] = mr;
         }
     }
     __syncthreads();      // every pass-A score tile has been consumed: TMEM is re-partitioned for pass B
@@ -415,16 +422,15 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
             const float* x0 = reinterpret_cast<const float*>(sP) + row * 8;
-            const float* x1 = x0 + 128 * 8;
-            mxc[h] = fmaxf(x0[h], x1[h]);
-            mxr[h] = fmaxf(x0[4 + h], x1[4 + h]);
+            mxc[h] = fmaxf(fmaxf(x0[h], x0[1024 + h]), fmaxf(x0[2048 + h], x0[3072 + h]));
+            mxr[h] = fmaxf(fmaxf(x0[4 + h], x0[1024 + 4 + h]), fmaxf(x0[2048 + 4 + h], x0[3072 + 4 + h]));
         }
-        softmax_bar_sync();  // both halves have read the maxima before xch is reused for the row sums
+        softmax_bar_sync();  // every quarter has read the maxima before sP is written again
     }
 
     // ============================== pass B: exp / row sums / P @ V ================================
     const uint32_t itA = 4u * (uint32_t)GA;       // barrier use counters continue across the passes
-    if (warp == 8) {
+    if (warp == 16) {
         if (lane == 0) {
             uint32_t it = itA;
             for (int h = 0; h < 4; ++h) {
@@ -445,66 +451,67 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                 }
             }
         }
-    } else if (warp == 9) {
-        if (lane == 0) {
+    } else if (warp == 17) {
+        if (lane == 0) {        // scores of every tile
             const uint32_t idesc64 = make_idesc_f16(BF16, 128, 64);
-            const uint32_t idesc128b = make_idesc_f16(BF16, 128, 128);
             uint32_t it = itA;          // key-tile counter (ring stage / score buffer of tile `it`)
-            uint32_t ip = 0;            // P@V counter (tile whose probabilities are consumed next)
             for (int h = 0; h < 4; ++h) {
                 const int qb = h & 1, uq = 2 + (h >> 1);
                 mbar_wait(&bars.q_full[qb], uq & 1, 340);
                 const uint64_t dqc = make_smem_desc_sw128(smem_u32(sQ + qb * 32768));
                 const uint64_t dqr = make_smem_desc_sw128(smem_u32(sQ + qb * 32768 + 16384));
-                for (int g = 0; g <= GB; ++g) {
-                    if (g < GB) {       // scores of tile g
-                        const int st = it % kPvStages, sb = it & 1;
-                        mbar_wait(&bars.kv_full[st], (it / kPvStages) & 1, 341);
-                        mbar_wait(&bars.s_empty[sb], ((it >> 1) & 1) ^ 1, 342);
-                        tc_fence_after();
-                        const uint64_t dkc = make_smem_desc_sw128(smem_u32(sKV + st * 32768));
-                        const uint64_t dkr = make_smem_desc_sw128(smem_u32(sKV + st * 32768 + 8192));
+                for (int g = 0; g < GB; ++g, ++it) {
+                    const int st = it % kPvStages, sb = it & 1;
+                    mbar_wait(&bars.kv_full[st], (it / kPvStages) & 1, 341);
+                    mbar_wait(&bars.s_empty[sb], ((it >> 1) & 1) ^ 1, 342);
+                    tc_fence_after();
+                    const uint64_t dkc = make_smem_desc_sw128(smem_u32(sKV + st * 32768));
+                    const uint64_t dkr = make_smem_desc_sw128(smem_u32(sKV + st * 32768 + 8192));
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_f16(tmem + sb * 128, dqc + 2 * k, dkc + 2 * k, idesc64, k ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem + sb * 128, dqc + 2 * k, dkc + 2 * k, idesc64, k ? 1u : 0u);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_f16(tmem + sb * 128 + 64, dqr + 2 * k, dkr + 2 * k, idesc64, k ? 1u : 0u);
-                        umma_commit(&bars.s_full[sb]);
-                        ++it;
-                    }
-                    if (g >= 1) {       // P @ V of tile g-1
-                        const uint32_t itp = itA + ip;                 // global index of that tile
-                        const int st = itp % kPvStages, pb = ip & 1;
-                        mbar_wait(&bars.p_full[pb], (ip >> 1) & 1, 343);
-                        if (g == 1 && h > 0) mbar_wait(&bars.o_empty, (h - 1) & 1, 344);   // previous head's O has been read
-                        tc_fence_after();
-                        const uint64_t dpc = make_smem_desc_sw128(smem_u32(sP + pb * 32768));
-                        const uint64_t dpr = make_smem_desc_sw128(smem_u32(sP + pb * 32768 + 16384));
-                        const uint64_t dvc = make_smem_desc_sw128(smem_u32(sKV + st * 32768 + 16384));
-                        const uint64_t dvr = make_smem_desc_sw128(smem_u32(sKV + st * 32768 + 24576));
-                        (void)dvr;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint32_t acc = (g > 1 || k) ? 1u : 0u;
-                            if (need_reg) {
-                                // Vc^T and Vr^T tiles are adjacent in the stage: one N = 128 product per probability
-                                // matrix (the A operand is read from shared memory once instead of twice)
-                                umma_f16(tmem + 256, dpc + 2 * k, dvc + 2 * k, idesc128b, acc);   // O_cc | O_cr
-                                umma_f16(tmem + 384, dpr + 2 * k, dvc + 2 * k, idesc128b, acc);   // O_rc | O_rr
-                            } else {
-                                umma_f16(tmem + 256, dpc + 2 * k, dvc + 2 * k, idesc64, acc);     // O_cc
-                                umma_f16(tmem + 320, dpr + 2 * k, dvc + 2 * k, idesc64, acc);     // O_rc
-                            }
-                        }
-                        umma_commit(&bars.kv_empty[st]);
-                        umma_commit(&bars.p_empty[pb]);
-                        ++ip;
-                    }
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem + sb * 128 + 64, dqr + 2 * k, dkr + 2 * k, idesc64, k ? 1u : 0u);
+                    umma_commit(&bars.s_full[sb]);
                 }
-                umma_commit(&bars.o_full);
                 umma_commit(&bars.q_empty[qb]);
             }
         }
-    } else {
+    } else if (warp == 18) {
+        if (lane == 0) {        // P @ V of every tile; releases the ring stages
+            const uint32_t idesc64 = make_idesc_f16(BF16, 128, 64);
+            const uint32_t idesc128b = make_idesc_f16(BF16, 128, 128);
+            uint32_t ip = 0;            // P@V counter (tile whose probabilities are consumed next)
+            for (int h = 0; h < 4; ++h) {
+                for (int g = 0; g < GB; ++g, ++ip) {
+                    const uint32_t itp = itA + ip;                 // global index of that tile
+                    const int st = itp % kPvStages, pb = ip & 1;
+                    mbar_wait(&bars.kv_full[st], (itp / kPvStages) & 1, 345);          // (V^T half of the stage; passes at once)
+                    mbar_wait(&bars.p_full[pb], (ip >> 1) & 1, 343);
+                    if (g == 0 && h > 0) mbar_wait(&bars.o_empty, (h - 1) & 1, 344);   // previous head's O has been read
+                    tc_fence_after();
+                    const uint64_t dpc = make_smem_desc_sw128(smem_u32(sP + pb * 32768));
+                    const uint64_t dpr = make_smem_desc_sw128(smem_u32(sP + pb * 32768 + 16384));
+                    const uint64_t dvc = make_smem_desc_sw128(smem_u32(sKV + st * 32768 + 16384));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t acc = (g > 0 || k) ? 1u : 0u;
+                        if (need_reg) {
+                            // Vc^T and Vr^T tiles are adjacent in the stage: one N = 128 product per probability
+                            // matrix (the A operand is read from shared memory once instead of twice)
+                            umma_f16(tmem + 256, dpc + 2 * k, dvc + 2 * k, idesc128b, acc);   // O_cc | O_cr
+                            umma_f16(tmem + 384, dpr + 2 * k, dvc + 2 * k, idesc128b, acc);   // O_rc | O_rr
+                        } else {
+                            umma_f16(tmem + 256, dpc + 2 * k, dvc + 2 * k, idesc64, acc);     // O_cc
+                            umma_f16(tmem + 320, dpr + 2 * k, dvc + 2 * k, idesc64, acc);     // O_rc
+                        }
+                    }
+                    umma_commit(&bars.kv_empty[st]);
+                    umma_commit(&bars.p_empty[pb]);
+                }
+                umma_commit(&bars.o_full);
+            }
+        }
+    } else if (is_sm) {
         uint32_t it = itA, ip = 0;
         float lsum_c[4], lsum_r[4];
         for (int h = 0; h < 4; ++h) {
@@ -519,16 +526,16 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                 unsigned char* sPr = sPc + 16384;
                 const bool all_vis = kbase >= n_glob0 && kbase + 64 <= ci.n_clip;
                 {
-                    const int c0 = half * 32;
-                    uint32_t rc[32], rr[32];
-                    tmem_ld_32x32(lane_base + sb * 128 + c0, rc);
-                    tmem_ld_32x32(lane_base + sb * 128 + 64 + c0, rr);
+                    const int c0 = quarter * 16;
+                    uint32_t rc[16], rr[16];
+                    tmem_ld_32x16(lane_base + sb * 128 + c0, rc);
+                    tmem_ld_32x16(lane_base + sb * 128 + 64 + c0, rr);
                     tmem_ld_wait();
-                    float ec[32], er[32];
+                    float ec[16], er[16];
                     float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
                     if (all_vis) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
+                        for (int j = 0; j < 16; j += 2) {
                             ec[j] = ex2_approx(fmaf(__uint_as_float(rc[j]), kLog2e, -mc));
                             ec[j + 1] = ex2_approx(fmaf(__uint_as_float(rc[j + 1]), kLog2e, -mc));
                             er[j] = ex2_approx(fmaf(__uint_as_float(rr[j]), kLog2e, -mr));
@@ -537,7 +544,7 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
+                        for (int j = 0; j < 16; ++j) {
                             const int k = kbase + c0 + j;
                             const bool ok = k < ci.n_clip && (k >= n_glob0 || (k >= lo && k < hi));
                             ec[j] = ok ? ex2_approx(fmaf(__uint_as_float(rc[j]), kLog2e, -mc)) : 0.f;
@@ -547,7 +554,7 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                     }
                     lc += l0 + l1; lr += l2 + l3;
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
+                    for (int cc = 0; cc < 2; ++cc) {
                         const uint32_t off = sw128_off(row, (c0 >> 3) + cc);
                         *reinterpret_cast<uint4*>(sPc + off) =
                             make_uint4(pack2<BF16>(ec[cc * 8], ec[cc * 8 + 1]), pack2<BF16>(ec[cc * 8 + 2], ec[cc * 8 + 3]),
@@ -562,40 +569,44 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&bars.s_empty[sb]); mbar_arrive(&bars.p_full[pb]); }
             }
-            // the row's two column halves exchange their partial sums
-            bars.xch[half][row][0] = lc; bars.xch[half][row][1] = lr;
+            // the row's four column quarters exchange their partial sums
+            bars.xch[quarter][row] = lc;
             softmax_bar_sync();
-            lc += bars.xch[half ^ 1][row][0]; lr += bars.xch[half ^ 1][row][1];
+            lc = (bars.xch[0][row] + bars.xch[1][row]) + (bars.xch[2][row] + bars.xch[3][row]);
+            softmax_bar_sync();
+            bars.xch[quarter][row] = lr;
+            softmax_bar_sync();
+            lr = (bars.xch[0][row] + bars.xch[1][row]) + (bars.xch[2][row] + bars.xch[3][row]);
             softmax_bar_sync();
             lsum_c[h] = lc; lsum_r[h] = lr;
-            // head epilogue: x = (O_c / l_c + O_r / l_r) / 2; each half drains 32 of the head's 64 output columns
+            // head epilogue: x = (O_c / l_c + O_r / l_r) / 2; each quarter drains 16 of the head's 64 output columns
             mbar_wait(&bars.o_full, h & 1, 352);
             tc_fence_after();
             const float ic = 0.5f / lc, ir = 0.5f / lr;
             for (int br = 0; br < (need_reg ? 2 : 1); ++br) {
                 uint16_t* dst = reinterpret_cast<uint16_t*>(br == 0 ? a.x_cls : a.x_reg);
-                const int c0 = half * 32;
-                uint32_t oc[32], orr[32];
+                const int c0 = quarter * 16;
+                uint32_t oc[16], orr[16];
                 // TMEM: need_reg  O_cc 256 | O_cr 320 | O_rc 384 | O_rr 448;   else  O_cc 256 | O_rc 320
-                tmem_ld_32x32(lane_base + (need_reg ? 256 + br * 64 : 256) + c0, oc);
-                tmem_ld_32x32(lane_base + (need_reg ? 384 + br * 64 : 320) + c0, orr);
+                tmem_ld_32x16(lane_base + (need_reg ? 256 + br * 64 : 256) + c0, oc);
+                tmem_ld_32x16(lane_base + (need_reg ? 384 + br * 64 : 320) + c0, orr);
                 tmem_ld_wait();
                 if (q_ok) {
-                    uint32_t pk[16];
+                    uint32_t pk[8];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
+                    for (int j = 0; j < 8; ++j)
                         pk[j] = pack2<BF16>(__uint_as_float(oc[2 * j]) * ic + __uint_as_float(orr[2 * j]) * ir,
                                             __uint_as_float(oc[2 * j + 1]) * ic + __uint_as_float(orr[2 * j + 1]) * ir);
                     uint4* o = reinterpret_cast<uint4*>(dst + (int64_t)(ci.lbase + q) * a.ld_x + h * 64 + c0);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    for (int j = 0; j < 2; ++j) o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars.o_empty);
         }
-        if (q_ok && half == 0) {
+        if (q_ok && quarter == 0) {
             float4* st = reinterpret_cast<float4*>(a.stats + (int64_t)(ci.lbase + q) * 16);
             st[0] = make_float4(mxc[0], mxc[1], mxc[2], mxc[3]);
             st[1] = make_float4(mxr[0], mxr[1], mxr[2], mxr[3]);
@@ -605,7 +616,7 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == 17) {
         tc_fence_after();
         tmem_dealloc<512>(tmem);
     }
@@ -650,6 +661,8 @@ struct R2Bars {
     uint32_t tmem_base;
     float xch[4][128];
 };
+
+static_assert(kR2SmemBytes + sizeof(R2Bars) <= 232448, "attn_round2: over the 227 KB shared-memory window");
 
 // One side of a ring: slot cursor + per-slot barrier parities (the producer tracks `empty`, the consumer `full`).
 struct R2Ring {
