@@ -15,12 +15,16 @@ from tscd_b200 import _lib as L, aggregate, weights  # noqa: E402
 
 TAGS = {0: "tma-s: slot empty", 1: "tma-x: slot empty", 10: "mma-s: item full", 12: "mma-s: S empty", 15: "mma-x: item full",
         11: "mma-x: R empty", 13: "mma-x: W full", 14: "mma: resident full", 20: "softmax: R full", 21: "softmax: S full", 22: "softmax: W empty", 23: "softmax: U full",
-        31: "kernel total"}
+        63: "kernel total"}
+PV_TAGS = {0: "A tma: Q empty", 1: "A tma: kv empty", 10: "A mma: Q full", 11: "A mma: kv full", 12: "A mma: S empty", 20: "A softmax: S full",
+           30: "B tma: Q empty", 31: "B tma-k: K empty", 32: "B tma-v: V empty", 40: "B mma-s: Q full", 41: "B mma-s: K full", 42: "B mma-s: S empty",
+           45: "B mma-pv: V full", 43: "B mma-pv: P full", 44: "B mma-pv: O empty", 50: "B softmax: S full", 51: "B softmax: P empty",
+           52: "B softmax: O full", 62: "pass A total", 63: "kernel total"}
 
 
 def waits(fn):
     lib = L.lib()
-    buf = (ctypes.c_ulonglong * 32)()
+    buf = (ctypes.c_ulonglong * 128)()
     lib.tscd_debug_r2_waits(buf, 1)
     fn()
     torch.cuda.synchronize()
@@ -51,6 +55,9 @@ def main():
     print(f"{'wait site':28s} {'cls launch':>12s} {'obj launch (w_in)':>18s}   [clocks, CTA (0,0)]")
     for t, name in TAGS.items():
         print(f"{name:28s} {cls[t]:12d} {both[t] - cls[t]:18d}")
+    print(f"\n{'attn_pv wait site':28s} {'need_reg=0':>12s} {'need_reg=1':>12s}")
+    for t, name in PV_TAGS.items():
+        print(f"{name:28s} {cls[64 + t]:12d} {both[64 + t]:12d}")
 
 
 if __name__ == "__main__":

@@ -233,6 +233,25 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     }
 }
 
+// Debug build (-DTSCD_R2_PROF): clocks one lane per role of CTA (0,0) spends in each barrier wait, by wait-site tag
+// (attn_pv tags 300.., attn_round2 tags 400..); read back with tscd_debug_r2_waits (tools/r2_waits.py).
+#ifdef TSCD_R2_PROF
+__device__ unsigned long long g_r2_wait[64];
+__device__ unsigned long long g_pv_wait[64];
+__device__ __forceinline__ void wait_prof(unsigned long long* acc, uint64_t* bar, uint32_t parity, int tag, int base) {
+    const long long t0 = clock64();
+    tc::mbar_wait(bar, parity, tag);
+    const long long dt = clock64() - t0;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x == 0 || (threadIdx.x >= 512 && (threadIdx.x & 31) == 0)))
+        atomicAdd(&acc[tag - base], (unsigned long long)dt);
+}
+#define R2_WAIT(bar, parity, tag) wait_prof(g_r2_wait, bar, parity, tag, 400)
+#define PV_WAIT(bar, parity, tag) wait_prof(g_pv_wait, bar, parity, tag, 300)
+#else
+#define R2_WAIT mbar_wait
+#define PV_WAIT mbar_wait
+#endif
+
 struct PvTmaps {
     CUtensorMap qc, kc, qr, kr, k64c, k64r, vtc, vtr;
 };
@@ -241,23 +260,26 @@ struct PvTmaps {
 // attn_pv: row max (pass A), exp/sum + P@V (pass B) -- warp-specialised, mbarrier-pipelined
 //
 //   warp 16 (one thread) TMA producer: Q tiles (double-buffered per head) and a 3-stage ring of key tiles
-//                        (pass A: Kc|Kr of 128 keys; pass B: Kc|Kr|Vc^T|Vr^T of 64 keys), 32 KB per stage;
+//                        (pass A: Kc|Kr of 128 keys, 32 KB; pass B: Kc|Kr of 64 keys, the first 16 KB of a stage);
+//   warp 19 (one thread) TMA producer of the value tiles of pass B (Vc^T|Vr^T, the second 16 KB of a stage) -- its own
+//                        ring: a key tile is free again as soon as its scores exist, a value tile only after P@V, so
+//                        the key loads run up to three tiles ahead of the softmax instead of waiting for P@V;
 //   warp 17 (one thread) tcgen05.mma issuer of the scores S = Q K^T (two TMEM score buffers: tile g+1 is computed
 //                        while the softmax warps work on tile g);
-//   warp 18 (one thread) tcgen05.mma issuer of P(g) @ V(g) (pass B); its commit releases the ring stage -- the scores
-//                        of that stage were consumed before its probabilities existed.  (One issuing thread pays ~15
-//                        dependent instructions per UMMA; two issuers halve that serial chain.)
+//   warp 18 (one thread) tcgen05.mma issuer of P(g) @ V(g) (pass B).  (One issuing thread pays ~15 dependent
+//                        instructions per UMMA; two issuers halve that serial chain.)
 //   warps 0-15           softmax: thread == query row == TMEM lane, warp w owns lanes 32 * (w % 4) and column quarter
 //                        w / 4 of every tile (four warps per scheduler hide the TMEM-load -> ex2 -> store chain);
 //                        visibility mask from the row's own frame range (no shared-memory side table), exp2, fp16/bf16
 //                        probabilities written as the swizzled K-major A operand of the P@V products (two P buffers).
 //   TMEM: pass A  2 x (S_cls 128 | S_reg 128);   pass B  2 x (S_cls 64 | S_reg 64) | O_cc O_cr O_rc O_rr (64 each).
 // -------------------------------------------------------------------------------------------------------
-constexpr int kPvThreads = 608;     // 16 softmax warps (4 per scheduler), TMA warp, 2 MMA warps
+constexpr int kPvThreads = 640;     // 16 softmax warps (4 per scheduler), 2 TMA warps, 2 MMA warps
 constexpr int kPvStages = 3;
 
 struct PvBars {
-    uint64_t kv_full[kPvStages], kv_empty[kPvStages];
+    uint64_t k_full[kPvStages], k_empty[kPvStages];
+    uint64_t v_full[kPvStages], v_empty[kPvStages];
     uint64_t q_full[2], q_empty[2];
     uint64_t s_full[2], s_empty[2];
     uint64_t p_full[2], p_empty[2];
@@ -283,6 +305,9 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
     const int b = blockIdx.y;
     const ClipInfo ci = clip_info(lay, b, blockIdx.x);
     if (ci.q0 >= ci.n_loc) return;
+#ifdef TSCD_R2_PROF
+    const long long tk0 = clock64();
+#endif
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw;                      // no static shared memory: the window starts 1024-byte aligned
@@ -296,7 +321,10 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
     if (threadIdx.x == 512) {
         tma_prefetch_desc(&tm.qc); tma_prefetch_desc(&tm.kc); tma_prefetch_desc(&tm.qr); tma_prefetch_desc(&tm.kr);
         tma_prefetch_desc(&tm.k64c); tma_prefetch_desc(&tm.k64r); tma_prefetch_desc(&tm.vtc); tma_prefetch_desc(&tm.vtr);
-        for (int i = 0; i < kPvStages; ++i) { mbar_init(&bars.kv_full[i], 1); mbar_init(&bars.kv_empty[i], 1); }
+        for (int i = 0; i < kPvStages; ++i) {
+            mbar_init(&bars.k_full[i], 1); mbar_init(&bars.k_empty[i], 1);
+            mbar_init(&bars.v_full[i], 1); mbar_init(&bars.v_empty[i], 1);
+        }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars.q_full[i], 1); mbar_init(&bars.q_empty[i], 1);
             mbar_init(&bars.s_full[i], 1); mbar_init(&bars.s_empty[i], 16);
@@ -338,16 +366,16 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
             uint32_t it = 0;
             for (int h = 0; h < 4; ++h) {
                 const int qb = h & 1, uq = h >> 1;
-                mbar_wait(&bars.q_empty[qb], (uq & 1) ^ 1, 300);
+                PV_WAIT(&bars.q_empty[qb], (uq & 1) ^ 1, 300);
                 mbar_expect_tx(&bars.q_full[qb], 32768);
                 tma_load_2d(sQ + qb * 32768, &tm.qc, &bars.q_full[qb], h * 64, ci.s0 + ci.q0);
                 tma_load_2d(sQ + qb * 32768 + 16384, &tm.qr, &bars.q_full[qb], h * 64, ci.s0 + ci.q0);
                 for (int g = 0; g < GA; ++g, ++it) {
                     const int st = it % kPvStages;
-                    mbar_wait(&bars.kv_empty[st], ((it / kPvStages) & 1) ^ 1, 301);
-                    mbar_expect_tx(&bars.kv_full[st], 32768);
-                    tma_load_2d(sKV + st * 32768, &tm.kc, &bars.kv_full[st], h * 64, ci.s0 + g * 128);
-                    tma_load_2d(sKV + st * 32768 + 16384, &tm.kr, &bars.kv_full[st], h * 64, ci.s0 + g * 128);
+                    PV_WAIT(&bars.k_empty[st], ((it / kPvStages) & 1) ^ 1, 301);
+                    mbar_expect_tx(&bars.k_full[st], 32768);
+                    tma_load_2d(sKV + st * 32768, &tm.kc, &bars.k_full[st], h * 64, ci.s0 + g * 128);
+                    tma_load_2d(sKV + st * 32768 + 16384, &tm.kr, &bars.k_full[st], h * 64, ci.s0 + g * 128);
                 }
             }
         }
@@ -357,13 +385,13 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
             uint32_t it = 0;
             for (int h = 0; h < 4; ++h) {
                 const int qb = h & 1, uq = h >> 1;
-                mbar_wait(&bars.q_full[qb], uq & 1, 310);
+                PV_WAIT(&bars.q_full[qb], uq & 1, 310);
                 const uint64_t dqc = make_smem_desc_sw128(smem_u32(sQ + qb * 32768));
                 const uint64_t dqr = make_smem_desc_sw128(smem_u32(sQ + qb * 32768 + 16384));
                 for (int g = 0; g < GA; ++g, ++it) {
                     const int st = it % kPvStages, sb = it & 1;
-                    mbar_wait(&bars.kv_full[st], (it / kPvStages) & 1, 311);
-                    mbar_wait(&bars.s_empty[sb], ((it >> 1) & 1) ^ 1, 312);
+                    PV_WAIT(&bars.k_full[st], (it / kPvStages) & 1, 311);
+                    PV_WAIT(&bars.s_empty[sb], ((it >> 1) & 1) ^ 1, 312);
                     tc_fence_after();
                     const uint64_t dkc = make_smem_desc_sw128(smem_u32(sKV + st * 32768));
                     const uint64_t dkr = make_smem_desc_sw128(smem_u32(sKV + st * 32768 + 16384));
@@ -371,7 +399,7 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                     for (int k = 0; k < 4; ++k) umma_f16(tmem + sb * 256, dqc + 2 * k, dkc + 2 * k, idesc128, k ? 1u : 0u);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) umma_f16(tmem + sb * 256 + 128, dqr + 2 * k, dkr + 2 * k, idesc128, k ? 1u : 0u);
-                    umma_commit(&bars.kv_empty[st]);
+                    umma_commit(&bars.k_empty[st]);
                     umma_commit(&bars.s_full[sb]);
                 }
                 umma_commit(&bars.q_empty[qb]);
@@ -383,7 +411,7 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
             float mc = -INFINITY, mr = -INFINITY;
             for (int g = 0; g < GA; ++g, ++it) {
                 const int sb = it & 1, kbase = g * 128;
-                mbar_wait(&bars.s_full[sb], (it >> 1) & 1, 320);
+                PV_WAIT(&bars.s_full[sb], (it >> 1) & 1, 320);
                 tc_fence_after();
                 const bool all_vis = kbase >= n_glob0 && kbase + 128 <= ci.n_clip;
                 {
@@ -418,6 +446,9 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
         }
     }
     __syncthreads();      // every pass-A score tile has been consumed: TMEM is re-partitioned for pass B
+#ifdef TSCD_R2_PROF
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(&g_pv_wait[62], (unsigned long long)(clock64() - tk0));
+#endif
     if (is_sm) {
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
@@ -435,21 +466,32 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
             uint32_t it = itA;
             for (int h = 0; h < 4; ++h) {
                 const int qb = h & 1, uq = 2 + (h >> 1);
-                mbar_wait(&bars.q_empty[qb], (uq & 1) ^ 1, 330);
+                PV_WAIT(&bars.q_empty[qb], (uq & 1) ^ 1, 330);
                 mbar_expect_tx(&bars.q_full[qb], 32768);
                 tma_load_2d(sQ + qb * 32768, &tm.qc, &bars.q_full[qb], h * 64, ci.s0 + ci.q0);
                 tma_load_2d(sQ + qb * 32768 + 16384, &tm.qr, &bars.q_full[qb], h * 64, ci.s0 + ci.q0);
                 for (int g = 0; g < GB; ++g, ++it) {
                     const int st = it % kPvStages;
                     unsigned char* base = sKV + st * 32768;
-                    mbar_wait(&bars.kv_empty[st], ((it / kPvStages) & 1) ^ 1, 331);
-                    mbar_expect_tx(&bars.kv_full[st], need_reg ? 32768 : 24576);
-                    tma_load_2d(base, &tm.k64c, &bars.kv_full[st], h * 64, ci.s0 + g * 64);
-                    tma_load_2d(base + 8192, &tm.k64r, &bars.kv_full[st], h * 64, ci.s0 + g * 64);
-                    tma_load_2d(base + 16384, &tm.vtc, &bars.kv_full[st], g * 64, b * 256 + h * 64);
-                    if (need_reg) tma_load_2d(base + 24576, &tm.vtr, &bars.kv_full[st], g * 64, b * 256 + h * 64);
+                    PV_WAIT(&bars.k_empty[st], ((it / kPvStages) & 1) ^ 1, 331);
+                    mbar_expect_tx(&bars.k_full[st], 16384);
+                    tma_load_2d(base, &tm.k64c, &bars.k_full[st], h * 64, ci.s0 + g * 64);
+                    tma_load_2d(base + 8192, &tm.k64r, &bars.k_full[st], h * 64, ci.s0 + g * 64);
                 }
             }
+        }
+    } else if (warp == 19) {
+        if (lane == 0) {        // value tiles: their own ring (second half of every stage), counted from 0 in pass B
+            uint32_t iv = 0;
+            for (int h = 0; h < 4; ++h)
+                for (int g = 0; g < GB; ++g, ++iv) {
+                    const int st = iv % kPvStages;
+                    unsigned char* base = sKV + st * 32768 + 16384;
+                    PV_WAIT(&bars.v_empty[st], ((iv / kPvStages) & 1) ^ 1, 332);
+                    mbar_expect_tx(&bars.v_full[st], need_reg ? 16384 : 8192);
+                    tma_load_2d(base, &tm.vtc, &bars.v_full[st], g * 64, b * 256 + h * 64);
+                    if (need_reg) tma_load_2d(base + 8192, &tm.vtr, &bars.v_full[st], g * 64, b * 256 + h * 64);
+                }
         }
     } else if (warp == 17) {
         if (lane == 0) {        // scores of every tile
@@ -457,13 +499,13 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
             uint32_t it = itA;          // key-tile counter (ring stage / score buffer of tile `it`)
             for (int h = 0; h < 4; ++h) {
                 const int qb = h & 1, uq = 2 + (h >> 1);
-                mbar_wait(&bars.q_full[qb], uq & 1, 340);
+                PV_WAIT(&bars.q_full[qb], uq & 1, 340);
                 const uint64_t dqc = make_smem_desc_sw128(smem_u32(sQ + qb * 32768));
                 const uint64_t dqr = make_smem_desc_sw128(smem_u32(sQ + qb * 32768 + 16384));
                 for (int g = 0; g < GB; ++g, ++it) {
                     const int st = it % kPvStages, sb = it & 1;
-                    mbar_wait(&bars.kv_full[st], (it / kPvStages) & 1, 341);
-                    mbar_wait(&bars.s_empty[sb], ((it >> 1) & 1) ^ 1, 342);
+                    PV_WAIT(&bars.k_full[st], (it / kPvStages) & 1, 341);
+                    PV_WAIT(&bars.s_empty[sb], ((it >> 1) & 1) ^ 1, 342);
                     tc_fence_after();
                     const uint64_t dkc = make_smem_desc_sw128(smem_u32(sKV + st * 32768));
                     const uint64_t dkr = make_smem_desc_sw128(smem_u32(sKV + st * 32768 + 8192));
@@ -471,23 +513,23 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                     for (int k = 0; k < 4; ++k) umma_f16(tmem + sb * 128, dqc + 2 * k, dkc + 2 * k, idesc64, k ? 1u : 0u);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) umma_f16(tmem + sb * 128 + 64, dqr + 2 * k, dkr + 2 * k, idesc64, k ? 1u : 0u);
+                    umma_commit(&bars.k_empty[st]);
                     umma_commit(&bars.s_full[sb]);
                 }
                 umma_commit(&bars.q_empty[qb]);
             }
         }
     } else if (warp == 18) {
-        if (lane == 0) {        // P @ V of every tile; releases the ring stages
+        if (lane == 0) {        // P @ V of every tile
             const uint32_t idesc64 = make_idesc_f16(BF16, 128, 64);
             const uint32_t idesc128b = make_idesc_f16(BF16, 128, 128);
             uint32_t ip = 0;            // P@V counter (tile whose probabilities are consumed next)
             for (int h = 0; h < 4; ++h) {
                 for (int g = 0; g < GB; ++g, ++ip) {
-                    const uint32_t itp = itA + ip;                 // global index of that tile
-                    const int st = itp % kPvStages, pb = ip & 1;
-                    mbar_wait(&bars.kv_full[st], (itp / kPvStages) & 1, 345);          // (V^T half of the stage; passes at once)
-                    mbar_wait(&bars.p_full[pb], (ip >> 1) & 1, 343);
-                    if (g == 0 && h > 0) mbar_wait(&bars.o_empty, (h - 1) & 1, 344);   // previous head's O has been read
+                    const int st = ip % kPvStages, pb = ip & 1;
+                    PV_WAIT(&bars.v_full[st], (ip / kPvStages) & 1, 345);
+                    PV_WAIT(&bars.p_full[pb], (ip >> 1) & 1, 343);
+                    if (g == 0 && h > 0) PV_WAIT(&bars.o_empty, (h - 1) & 1, 344);   // previous head's O has been read
                     tc_fence_after();
                     const uint64_t dpc = make_smem_desc_sw128(smem_u32(sP + pb * 32768));
                     const uint64_t dpr = make_smem_desc_sw128(smem_u32(sP + pb * 32768 + 16384));
@@ -505,7 +547,7 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                             umma_f16(tmem + 320, dpr + 2 * k, dvc + 2 * k, idesc64, acc);     // O_rc
                         }
                     }
-                    umma_commit(&bars.kv_empty[st]);
+                    umma_commit(&bars.v_empty[st]);
                     umma_commit(&bars.p_empty[pb]);
                 }
                 umma_commit(&bars.o_full);
@@ -519,8 +561,8 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
             float lc = 0.f, lr = 0.f;
             for (int g = 0; g < GB; ++g, ++it, ++ip) {
                 const int sb = it & 1, pb = ip & 1, kbase = g * 64;
-                mbar_wait(&bars.s_full[sb], (it >> 1) & 1, 350);
-                mbar_wait(&bars.p_empty[pb], ((ip >> 1) & 1) ^ 1, 351);
+                PV_WAIT(&bars.s_full[sb], (it >> 1) & 1, 350);
+                PV_WAIT(&bars.p_empty[pb], ((ip >> 1) & 1) ^ 1, 351);
                 tc_fence_after();
                 unsigned char* sPc = sP + pb * 32768;
                 unsigned char* sPr = sPc + 16384;
@@ -580,7 +622,7 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
             softmax_bar_sync();
             lsum_c[h] = lc; lsum_r[h] = lr;
             // head epilogue: x = (O_c / l_c + O_r / l_r) / 2; each quarter drains 16 of the head's 64 output columns
-            mbar_wait(&bars.o_full, h & 1, 352);
+            PV_WAIT(&bars.o_full, h & 1, 352);
             tc_fence_after();
             const float ic = 0.5f / lc, ir = 0.5f / lr;
             for (int br = 0; br < (need_reg ? 2 : 1); ++br) {
@@ -614,6 +656,9 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
             st[3] = make_float4(lsum_r[0], lsum_r[1], lsum_r[2], lsum_r[3]);
         }
     }
+#ifdef TSCD_R2_PROF
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(&g_pv_wait[63], (unsigned long long)(clock64() - tk0));
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 17) {
@@ -696,22 +741,6 @@ __device__ __forceinline__ void r2_x_schedule(int KT, int atom0, int atom1, F&& 
     }
     f(2, KT - 1, 0); f(2, KT - 1, 1);
 }
-
-// Debug build (-DTSCD_R2_PROF): clocks one lane per role of CTA (0,0) spends in each barrier wait, by wait-site tag.
-#ifdef TSCD_R2_PROF
-__device__ unsigned long long g_r2_wait[32];
-__device__ __forceinline__ void r2_wait_prof(uint64_t* bar, uint32_t parity, int tag) {
-    const long long t0 = clock64();
-    tc::mbar_wait(bar, parity, tag);
-    const long long dt = clock64() - t0;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x == 0 || (threadIdx.x >= 512 && (threadIdx.x & 31) == 0)))
-        atomicAdd(&g_r2_wait[tag - 400], (unsigned long long)dt);
-}
-#define R2_WAIT r2_wait_prof
-#else
-#define R2_WAIT mbar_wait
-#endif
-
 
 template <bool BF16>
 __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid_constant__ R2Tmaps tm,
@@ -1032,7 +1061,7 @@ __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid
         }
     }
 #ifdef TSCD_R2_PROF
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(&g_r2_wait[31], (unsigned long long)(clock64() - tk0));
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(&g_r2_wait[63], (unsigned long long)(clock64() - tk0));
 #endif
     tc_fence_before();
     __syncthreads();
@@ -1140,12 +1169,13 @@ extern "C" int tscd_attn_round2(const tscd_attn_round2_args* a, void* stream) {
 }
 
 #ifdef TSCD_R2_PROF
-extern "C" int tscd_debug_r2_waits(unsigned long long* out, int reset) {
+extern "C" int tscd_debug_r2_waits(unsigned long long* out, int reset) {      // out[0..63] attn_round2, out[64..127] attn_pv
     if (reset) {
-        unsigned long long z[32] = {};
-        return cudaMemcpyToSymbol(tscd::g_r2_wait, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+        unsigned long long z[64] = {};
+        return cudaMemcpyToSymbol(tscd::g_r2_wait, z, sizeof(z)) == cudaSuccess && cudaMemcpyToSymbol(tscd::g_pv_wait, z, sizeof(z)) == cudaSuccess ? 0 : -1;
     }
-    return cudaMemcpyFromSymbol(out, tscd::g_r2_wait, 32 * sizeof(unsigned long long)) == cudaSuccess ? 0 : -1;
+    return cudaMemcpyFromSymbol(out, tscd::g_r2_wait, sizeof(unsigned long long) * 64) == cudaSuccess &&
+                   cudaMemcpyFromSymbol(out + 64, tscd::g_pv_wait, sizeof(unsigned long long) * 64) == cudaSuccess ? 0 : -1;
 }
 #endif
 
