@@ -49,6 +49,10 @@ struct GemmParams {
 // Persistent, warp-specialised: every CTA walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...  (n fastest, so
 // CTAs running at the same time share their A rows in L2).  Two TMEM accumulator stages let the epilogue of tile i
 // overlap the TMA/MMA main loop of tile i+1; the smem ring keeps filling across tile boundaries.
+// Resident weights: when the K loop has exactly as many blocks as the ring has stages (K = 256 with 128x256 tiles),
+// k-block kb of every tile lands in stage kb, so the weight half of a stage already holds the right block whenever two
+// consecutive tiles of a CTA share their column block -- tiles are then ordered m-fastest and the producer skips the
+// weight load (192 KB -> 64 KB of L2 -> shared-memory traffic per tile).
 constexpr int kAccStages = 2;
 
 template <int BN, bool BF16, int EPI = 0>
@@ -83,6 +87,11 @@ __global__ void __launch_bounds__(EPI ? kGemmThreadsFused : kGemmThreads) gemm_t
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_kb = (p.K + kGemmBK - 1) / kGemmBK;
+    const bool w_resident = num_kb == STAGES;
+    auto tile_origin = [&](int t, int& m0, int& n0) {
+        if (w_resident) { m0 = (t % tiles_m) * kGemmBM; n0 = (t / tiles_m) * BN; }
+        else { m0 = (t / tiles_n) * kGemmBM; n0 = (t % tiles_n) * BN; }
+    };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -100,16 +109,20 @@ __global__ void __launch_bounds__(EPI ? kGemmThreadsFused : kGemmThreads) gemm_t
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;   // running k-block counter across tiles -> ring stage / phase
+            int n_prev = -1;   // column block whose weights the stages hold (w_resident)
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int m0 = (t / tiles_n) * kGemmBM, n0 = (t % tiles_n) * BN;
+                int m0, n0;
+                tile_origin(t, m0, n0);
+                const bool load_w = !(w_resident && n0 == n_prev);
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1, 100 + s);
-                    mbar_expect_tx(&full_bar[s], kABytes + kWBytes);
+                    mbar_expect_tx(&full_bar[s], load_w ? kABytes + kWBytes : kABytes);
                     tma_load_2d(sA + s * kABytes, &tmap_a, &full_bar[s], kb * kGemmBK, m0);
-                    tma_load_2d(sW + s * kWBytes, &tmap_w, &full_bar[s], kb * kGemmBK, n0);
+                    if (load_w) tma_load_2d(sW + s * kWBytes, &tmap_w, &full_bar[s], kb * kGemmBK, n0);
                 }
+                n_prev = n0;
             }
         }
     } else if (warp == 1) {
@@ -150,7 +163,8 @@ __global__ void __launch_bounds__(EPI ? kGemmThreadsFused : kGemmThreads) gemm_t
         const bool al32 = p.out32 && (p.ld32 % 4) == 0 && (reinterpret_cast<uintptr_t>(p.out32) & 15) == 0;
         uint32_t ti = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
-            const int m0 = (t / tiles_n) * kGemmBM, n0 = (t % tiles_n) * BN;
+            int m0, n0;
+            tile_origin(t, m0, n0);
             const int acc = ti % kAccStages;
             const uint32_t aph = (ti / kAccStages) & 1;
             const int row_base = m0 + q * 32;
