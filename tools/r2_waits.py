@@ -25,10 +25,14 @@ PV_TAGS = {0: "A tma: Q empty", 1: "A tma: kv empty", 10: "A mma: Q full", 11: "
 def waits(fn):
     lib = L.lib()
     buf = (ctypes.c_ulonglong * 128)()
+    gbuf = (ctypes.c_ulonglong * 8)()
     lib.tscd_debug_r2_waits(buf, 1)
+    lib.tscd_debug_gemm_waits(gbuf, 1)
     fn()
     torch.cuda.synchronize()
     lib.tscd_debug_r2_waits(buf, 0)
+    lib.tscd_debug_gemm_waits(gbuf, 0)
+    waits.gemm = list(gbuf)
     return list(buf)
 
 
@@ -55,6 +59,11 @@ def main():
     print(f"{'wait site':28s} {'cls launch':>12s} {'obj launch (w_in)':>18s}   [clocks, CTA (0,0)]")
     for t, name in TAGS.items():
         print(f"{name:28s} {cls[t]:12d} {both[t] - cls[t]:18d}")
+    g = waits.gemm
+    print("\nfused q|k|v projection, CTA 0, both launches of the module summed [clocks]:")
+    for i, name in enumerate(["tma: stage empty", "mma: accumulator empty", "mma: stage full", "epilogue warp 2: accumulator full",
+                              "total tma warp", "total mma warp", "total epilogue warp 2"]):
+        print(f"{name:36s} {g[i]:12d}")
     print(f"\n{'attn_pv wait site':28s} {'need_reg=0':>12s} {'need_reg=1':>12s}")
     for t, name in PV_TAGS.items():
         print(f"{name:28s} {cls[64 + t]:12d} {both[64 + t]:12d}")

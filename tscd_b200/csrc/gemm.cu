@@ -46,6 +46,21 @@ struct GemmParams {
     int ld_xori;
 };
 
+// Debug build (-DTSCD_R2_PROF): clocks lane 0 of warps 0 (TMA), 1 (MMA) and 2 (epilogue) of CTA 0 of the FUSED projection
+// kernel spend in each barrier wait; read back with tscd_debug_gemm_waits (tools/r2_waits.py).
+#ifdef TSCD_R2_PROF
+__device__ unsigned long long g_gemm_wait[8];
+template <int EPI>
+__device__ __forceinline__ void gemm_wait_prof(uint64_t* bar, uint32_t parity, int tag, int slot) {
+    const long long t0 = clock64();
+    tc::mbar_wait(bar, parity, tag);
+    if (EPI == 1 && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && threadIdx.x < 96) atomicAdd(&g_gemm_wait[slot], (unsigned long long)(clock64() - t0));
+}
+#define GEMM_WAIT(bar, parity, tag, slot) gemm_wait_prof<EPI>(bar, parity, tag, slot)
+#else
+#define GEMM_WAIT(bar, parity, tag, slot) mbar_wait(bar, parity, tag)
+#endif
+
 // Persistent, warp-specialised: every CTA walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...  (n fastest, so
 // CTAs running at the same time share their A rows in L2).  Two TMEM accumulator stages let the epilogue of tile i
 // overlap the TMA/MMA main loop of tile i+1; the smem ring keeps filling across tile boundaries.
@@ -67,6 +82,9 @@ __global__ void __launch_bounds__(EPI ? kGemmThreadsFused : kGemmThreads) gemm_t
     const int tiles_m = (M + kGemmBM - 1) / kGemmBM;      // only tiles with valid rows exist
     const int num_tiles = tiles_m * tiles_n;
     if ((int)blockIdx.x >= num_tiles) return;             // uniform over the CTA, before any barrier / TMEM state exists
+#ifdef TSCD_R2_PROF
+    const long long tk0 = clock64();
+#endif
 
     // No static shared memory in this kernel: the dynamic window then starts at the CTA's shared base, which honours
     // the 1024-byte alignment the 128-byte swizzle needs (no over-allocation -> two CTAs fit in 227 KB).
@@ -117,7 +135,7 @@ __global__ void __launch_bounds__(EPI ? kGemmThreadsFused : kGemmThreads) gemm_t
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1, 100 + s);
+                    GEMM_WAIT(&empty_bar[s], ph ^ 1, 100 + s, 0);
                     mbar_expect_tx(&full_bar[s], load_w ? kABytes + kWBytes : kABytes);
                     tma_load_2d(sA + s * kABytes, &tmap_a, &full_bar[s], kb * kGemmBK, m0);
                     if (load_w) tma_load_2d(sW + s * kWBytes, &tmap_w, &full_bar[s], kb * kGemmBK, n0);
@@ -132,13 +150,13 @@ __global__ void __launch_bounds__(EPI ? kGemmThreadsFused : kGemmThreads) gemm_t
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
                 const int acc = ti % kAccStages;
                 const uint32_t aph = (ti / kAccStages) & 1;
-                mbar_wait(&tmem_empty_bar[acc], aph ^ 1, 130 + acc);     // epilogue has drained this accumulator
+                GEMM_WAIT(&tmem_empty_bar[acc], aph ^ 1, 130 + acc, 1);     // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&full_bar[s], ph, 110 + s);
+                    GEMM_WAIT(&full_bar[s], ph, 110 + s, 2);
                     tc_fence_after();
                     const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + s * kABytes));
                     const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sW + s * kWBytes));
@@ -183,7 +201,7 @@ __global__ void __launch_bounds__(EPI ? kGemmThreadsFused : kGemmThreads) gemm_t
                     lb = __ldg(p.lrow_off + cb0 * p.L);
                 }
             }
-            mbar_wait(&tmem_full_bar[acc], aph, 120 + acc);
+            GEMM_WAIT(&tmem_full_bar[acc], aph, 120 + acc, 3);
             tc_fence_after();
             const uint32_t tsrc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
             if constexpr (EPI == 1) {
@@ -359,6 +377,9 @@ __global__ void __launch_bounds__(EPI ? kGemmThreadsFused : kGemmThreads) gemm_t
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
     }
+#ifdef TSCD_R2_PROF
+    if (EPI == 1 && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && threadIdx.x < 96) atomicAdd(&g_gemm_wait[4 + warp], (unsigned long long)(clock64() - tk0));
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -473,3 +494,13 @@ extern "C" int tscd_qkv_project(const tscd_qkv_project_args* a, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     return is_bf16 ? launch_gemm<256, true, 1>(ta, tw, p, st) : launch_gemm<256, false, 1>(ta, tw, p, st);
 }
+
+#ifdef TSCD_R2_PROF
+extern "C" int tscd_debug_gemm_waits(unsigned long long* out, int reset) {
+    if (reset) {
+        unsigned long long z[8] = {};
+        return cudaMemcpyToSymbol(tscd::g_gemm_wait, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+    }
+    return cudaMemcpyFromSymbol(out, tscd::g_gemm_wait, sizeof(unsigned long long) * 8) == cudaSuccess ? 0 : -1;
+}
+#endif
