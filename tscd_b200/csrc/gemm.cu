@@ -278,8 +278,6 @@ __global__ void __launch_bounds__(EPI ? kGemmThreadsFused : kGemmThreads) gemm_t
                             }
                         }
                     }
-                    {
-                    }   // valid
                     __syncwarp();
                 }
                 tc_fence_before();
