@@ -154,3 +154,32 @@ def test_mca_ragged_clip_sizes_and_determinism(clustered):
         assert _rel(runs[0][0][lpos:lpos + nl], tc) < 1e-2, f"clip {b} cls"
         assert _rel(runs[0][1][lpos:lpos + nl], to) < 1e-2, f"clip {b} obj"
         lpos += nl
+
+
+def test_mca_long_clip_vs_oracle():
+    """One long clip (128 frames x 30 proposals = 3840 keys = 60 key tiles, 480 local rows = 4 query tiles): the
+    barrier phases of the pipelined attention kernels wrap many times; result within 1e-2 of the oracle."""
+    from tscd_b200 import aggregate
+    dtype = torch.float16
+    B, F, L = 1, 128, 16
+    counts = [30] * (B * F)
+    xc, xr, score = _make_case(B, F, L, counts, 23, False)
+    sd = oracle.init_stage_weights(25, dim=256, seed=6)
+    xc, xr = xc.to(dtype).float(), xr.to(dtype).float()
+    sd16 = {k: v.to(dtype).float() if v.dim() == 2 else v for k, v in sd.items()}
+    N = sum(counts)
+    row_cap = ((N + 127) // 128 + 1) * 128
+    cnt = torch.tensor(counts, dtype=torch.int32).cuda()
+    loc_total = sum(counts[:L])
+    lay = aggregate.make_layout(cnt, B, F, L, row_cap, ((loc_total + 127) // 128) * 128, ((N + 127) // 128) * 128, dtype)
+    bank_c = torch.zeros(row_cap, 256, dtype=dtype).cuda(); bank_c[:N] = xc.to(dtype).cuda()
+    bank_r = torch.zeros(row_cap, 256, dtype=dtype).cuda(); bank_r[:N] = xr.to(dtype).cuda()
+    bscore = torch.zeros(row_cap).cuda(); bscore[:N] = score.cuda()
+    n_dev = torch.tensor([N], dtype=torch.int32).cuda()
+    nl_dev = torch.tensor([loc_total], dtype=torch.int32).cuda()
+    w = aggregate.MCAWeights(sd, "agg_iou.", dtype)
+    (c16, c32), (o16, o32) = aggregate.mca_forward(lay, w, bank_c, bank_r, bscore, n_dev, nl_dev, need_reg=True)
+    torch.cuda.synchronize()
+    tc, to = oracle.mca_tscd_g2l_reg(sd16, "agg_iou.", xc.unsqueeze(0), xr.unsqueeze(0), score, counts, L)
+    assert _rel(c32[:loc_total], tc) < 1e-2
+    assert _rel(o32[:loc_total], to) < 1e-2
