@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Debug: where the round-2 attention kernel waits.  Needs a library built with TSCD_NVCC_EXTRA=-DTSCD_R2_PROF
-(python -m tscd_b200.build --force); prints, for CTA (0,0), the clocks one lane of each role spent in every barrier wait.
+"""Debug: where the warp-specialised kernels of one MCA module wait (attn_round2, attn_pv, the fused q|k|v projection).
+Needs a library built with TSCD_NVCC_EXTRA=-DTSCD_R2_PROF (python -m tscd_b200.build --force); prints, for CTA (0,0),
+the clocks one lane of each role (TMA producer, MMA issuer, softmax / epilogue warp) spent in every barrier wait and the
+kernel's total.  Rebuild without the flag afterwards: the counters cost ~20 % of the kernels' time.
 
   TSCD_NVCC_EXTRA=-DTSCD_R2_PROF python -m tscd_b200.build --force && python tools/r2_waits.py
 """
