@@ -94,14 +94,24 @@ typedef struct {
     void* ws_conf;           /* [num_frames, ws_pitch] head_dtype */
     unsigned char* ws_cls;   /* [num_frames, ws_pitch] */
     int32_t ws_pitch;        /* >= A, multiple of 16 */
+    /* optional [1] device flag: set to TSCD_ERR_CAPACITY when a frame selects more anchors than cand_cap (mode B without
+     * a maximal_limit: the reference's list is unbounded, postprocess_widx tscd_head.py:1591-1607; the candidate arrays
+     * are not).  The frame is truncated to its first cand_cap anchors and the caller must treat the batch as failed. */
+    int32_t* status;
 } tscd_select_args;
 int tscd_select(const tscd_select_args* args, void* stream);
 
 /* ---- K2: class-aware batched NMS ---------------------------------------------------------------------
  * Replaces torchvision.ops.batched_nms (coordinate trick + nms) at tscd_head.py:1630,
- * post_process.py:58,73,510.  One CTA per frame; keep lists are positions into the candidate arrays in
- * descending-score order (stable: ties keep the lower position first), truncated to max_keep.
- * n per frame must be <= 4096 (TSCD_ERR_CAPACITY is reported through `status`). */
+ * post_process.py:58,73,510.  Keep lists are positions into the candidate arrays in descending-score order
+ * (stable: ties keep the lower position first), truncated to max_keep.
+ *   cand_cap <= 4096: one CTA per frame, everything in shared memory;
+ *   4096 < cand_cap <= 16384 (the final per-class NMS of post_process.py:36-65 sees up to proposals x classes rows,
+ *   500 x 25 = 12 500 for the shipped OVIS-L limits): three kernels over a caller-provided workspace -- per-frame class
+ *   partition, one CTA per (frame, class) greedy NMS (exact whenever no cross-class pair of offset boxes exceeds the
+ *   threshold, which is tested explicitly), per-frame score-ordered merge; frames that fail the test take an exact general
+ *   path.  `ws` must then hold tscd_nms_workspace_bytes(num_frames, cand_cap) bytes.
+ * cand_cap > 16384 returns TSCD_ERR_CAPACITY from the call itself. */
 typedef struct {
     int32_t num_frames;
     int32_t cand_cap;     /* row pitch of the candidate arrays */
@@ -114,8 +124,14 @@ typedef struct {
     int32_t* keep;        /* [F,max_keep] */
     int32_t* keep_count;  /* [F] */
     int32_t* status;      /* [1] device flag: set to TSCD_ERR_CAPACITY if any frame exceeded the cap */
+    void* ws;             /* workspace for cand_cap > 4096 (NULL otherwise) */
+    int64_t ws_bytes;
+    int32_t strict_keep;  /* 1: a frame that keeps MORE than max_keep boxes is an error (status = TSCD_ERR_CAPACITY) instead
+                           * of a truncation -- mode B with pre-NMS, where max_keep is a buffer capacity and not the
+                           * reference's top-K (tscd_head.py:1629-1635 keeps everything) */
 } tscd_nms_args;
 int tscd_nms(const tscd_nms_args* args, void* stream);
+int64_t tscd_nms_workspace_bytes(int32_t num_frames, int32_t cand_cap);
 
 /* ---- K3: rows + feature gather into the clip bank -------------------------------------------------------
  * Replaces the row build (tscd_head.py:1581-1582, 1670-1684) and find_feature_score (:976-1006).

@@ -377,8 +377,9 @@ class CAFMState:
         self.last_edge = None
 
 
-def _double_match(ref_a, cur_a, ref_b, cur_b):
-    """double_match_embds, tscd_matching.py:912-937 (eps 1e-6 in the norms; NaN -> 0)."""
+def _double_match(ref_a, cur_a, ref_b, cur_b, lap_fn=None, ctx=None):
+    """double_match_embds, tscd_matching.py:912-937 (eps 1e-6 in the norms; NaN -> 0).
+    lap_fn(cost, ctx), if given, replaces the Hungarian solve (tests: force a measured near-tie the other way)."""
     def cos(r, c):
         r, c = r[:, 0, :], c[:, 0, :]
         r = r / (r.norm(dim=1)[:, None] + 1e-6)
@@ -386,11 +387,11 @@ def _double_match(ref_a, cur_a, ref_b, cur_b):
         return torch.mm(r, c.transpose(0, 1))
     C = 1 - ((cos(ref_a, cur_a) + cos(ref_b, cur_b)) / 2)
     C = torch.where(torch.isnan(C), torch.full_like(C, 0), C)
-    return lap(C.numpy()), C
+    return (lap(C.numpy()) if lap_fn is None else lap_fn(C.numpy(), ctx)), C
 
 
 def aware_position_reg_matcher(sd, prefix, features, features_reg, features_cls, features_edge, preds_per_frame,
-                               time_embedding, resume=False, state=None, num_heads=8, debug=None):
+                               time_embedding, resume=False, state=None, num_heads=8, debug=None, lap_fn=None):
     """AwarePositionRegMatcher.forward (CAFM), tscd_matching.py:722-888, decoder_layer_num=1.
 
     Returns ([Nloc, D] or None, state).  `debug`, if a dict, receives per-frame costs/permutations."""
@@ -408,20 +409,22 @@ def aware_position_reg_matcher(sd, prefix, features, features_reg, features_cls,
     te = F.linear(time_embedding, sd[prefix + "absolute_position_embedding.weight"],
                   sd[prefix + "absolute_position_embedding.bias"])[:, None, :]
     outputs, perms = [], []
+    prev_perm = None           # permutation of the previous non-empty frame of THIS call (ctx for lap_fn)
     for i, n in enumerate(preds_per_frame):
         if n == 0:
             if i == 0 and resume is False:
                 state = CAFMState()
             continue
+        ctx = dict(frame=i, prev_perm=prev_perm)
         E, R, Cc, Ed, T = fl[i], rl[i], cl[i], el[i], te[i].unsqueeze(0)
         if (i == 0 and resume is False) or state.last_output is None:      # :779-807
             state.last_embeds, state.last_reg, state.last_cls = E, R, Cc
-            (_, col), cost = _double_match(R, R, Cc, Cc)
+            (_, col), cost = _double_match(R, R, Cc, Cc, lap_fn, ctx)
             perm = col
             out = _referring_layer(sd, lp, E, E, E, T, T, Ed, Ed, num_heads)
             new_edge = Ed
         else:                                                              # :808-875
-            (row, col), cost = _double_match(state.last_reg, R, state.last_cls, Cc)
+            (row, col), cost = _double_match(state.last_reg, R, state.last_cls, Cc, lap_fn, ctx)
             n_prev = len(state.last_embeds)
             if n_prev < n:
                 no_match = [j for j in range(n) if j not in col]
@@ -444,6 +447,7 @@ def aware_position_reg_matcher(sd, prefix, features, features_reg, features_cls,
             debug.setdefault("perm", []).append(np.asarray(perm))
         outputs.append(out)
         perms.append(np.asarray(perm))
+        prev_perm = np.asarray(perm)
     if not outputs:
         return None, state
     outs = torch.cat([o[np.argsort(p)] for o, p in zip(outputs, perms)], dim=0)   # :881-884
@@ -492,12 +496,15 @@ def decode_reg_preds5(reg_preds, boxes, bbox_xform_clip=math.log(736.0 / 32)):
 
 
 # --------------------------------------------------------------------------- a12
-def postprocess(prediction, num_classes, fc_outputs, conf_output, reg_output, conf_thre=0.001, nms_thre=0.5):
+def postprocess(prediction, num_classes, fc_outputs, conf_output, reg_output, conf_thre=0.001, nms_thre=0.5, debug=None):
     """post_process.py:9-85 (cls_sig=True).  prediction: list of [n,7+C] (or None); returns
-    (output, output_ori) lists of [n_det,7] or None."""
+    (output, output_ori) lists of [n_det,7] or None.  `debug`, if a list, receives per frame the candidate rows fed to
+    batched_nms and the keep lists (None for skipped frames) -- used by the tests to measure decision margins."""
     output = [None] * len(prediction)
     output_ori = [None] * len(prediction)
     for i, det in enumerate(prediction):
+        if debug is not None:
+            debug.append(None)
         if det is None or det.shape[0] == 0:
             continue
         ori = det.clone()
@@ -521,15 +528,18 @@ def postprocess(prediction, num_classes, fc_outputs, conf_output, reg_output, co
         output[i] = new[keep]
         o7 = ori[:, :7]
         o7 = o7[o7[:, 4] * o7[:, 5] >= conf_thre]
-        keep = batched_nms(o7[:, :4], o7[:, 4] * o7[:, 5], o7[:, 6], nms_thre)
-        output_ori[i] = o7[keep]
+        keep_ori = batched_nms(o7[:, :4], o7[:, 4] * o7[:, 5], o7[:, 6], nms_thre)
+        output_ori[i] = o7[keep_ori]
+        if debug is not None:
+            debug[-1] = dict(cand=new, keep=keep, cand_ori=o7, keep_ori=keep_ori, all_scores=sc, obj=det[:, 4].clone(),
+                             box=det[:, :4].clone())
     return output, output_ori
 
 
 # --------------------------------------------------------------------------- a1
 def stage_tscd(sd, decoded, cls_feat, reg_feat, edge_feat, time_embedding, num_classes, lframe, gframe,
                selection="B", select_kwargs=None, nms_thresh=0.5, sim_thresh=0.75, conf_sim_thresh=0.99, heads=4,
-               resume=False, state=None, trace=None):
+               resume=False, state=None, trace=None, lap_fn=None):
     """TSCDHead.forward inference tail, tscd_head.py:374-733 (agg_type='mca', decouple_reg, reconf).
 
     decoded [F,A,5+C] (after decode_outputs), feature planes [F,A,D].  selection 'B' =
@@ -554,7 +564,7 @@ def stage_tscd(sd, decoded, cls_feat, reg_feat, edge_feat, time_embedding, num_c
     n_loc = sum(ppf[:lframe])
     dbg = {} if trace is not None else None
     matched, state = aware_position_reg_matcher(sd, "local_reg_matcher.", f_reg, iou_reg, iou_cls, f_edge, ppf[:lframe],
-                                                time_embedding[:lframe], resume=resume, state=state, debug=dbg)
+                                                time_embedding[:lframe], resume=resume, state=state, debug=dbg, lap_fn=lap_fn)
     if matched is None:
         matched = f_reg[:n_loc]
     matched = F.linear(matched, sd["fc_reg_matcher.weight"], sd["fc_reg_matcher.bias"])          # :507
@@ -575,8 +585,11 @@ def stage_tscd(sd, decoded, cls_feat, reg_feat, edge_feat, time_embedding, num_c
         trace.update(dict(rows=rows, idxs=idxs, bank=bank, agg_cls=agg_cls, iou_cls=iou_cls, iou_reg=iou_reg,
                           matched=matched, obj_ref=obj_ref, cls_preds=cls_preds, obj_preds=obj_preds,
                           reg_deltas=reg_deltas, reg_preds=reg_preds, cafm=dbg))
+    post_dbg = [] if trace is not None else None
     result, result_ori = postprocess([rows[i] for i in range(lframe)], num_classes, cls_pf, obj_pf, reg_pf,
-                                     nms_thre=nms_thresh)
+                                     nms_thre=nms_thresh, debug=post_dbg)
+    if trace is not None:
+        trace["post"] = post_dbg
     return result, result_ori, state
 
 
@@ -597,10 +610,10 @@ def stage_gen1(sd, decoded, cls_feat, reg_feat, num_classes, pre_k=750, top_k=30
 
 # --------------------------------------------------------------------------- synthetic workload
 def synth_head_outputs(num_frames, hw, num_classes, dim=256, seed=2024, clustered=False, dtype=torch.float32,
-                       obj_mean=-3.0):
+                       obj_mean=-3.0, n_obj=40, n_mem=12):
     """Synthetic boundary tensors at seam S2: pre-decode head outputs [F,A,5+C] with sigmoid applied
     (tscd_head.py:357-359,374-376) and three feature planes [F,A,dim].  obj/cls logits ~ N(-3,2^2),
-    dx,dy ~ U(-0.5,1.5), dw,dh ~ N(1.0,0.7^2); `clustered` duplicates 40 objects per frame with jitter;
+    dx,dy ~ U(-0.5,1.5), dw,dh ~ N(1.0,0.7^2); `clustered` duplicates n_obj (40) objects per frame over n_mem (12) anchors with jitter;
     `obj_mean` (scalar or per frame) shifts the objectness logits to vary how many anchors pass 0.001."""
     g = torch.Generator().manual_seed(seed)
     A = sum(h * w for h, w in hw)
@@ -620,7 +633,6 @@ def synth_head_outputs(num_frames, hw, num_classes, dim=256, seed=2024, clustere
             gx.append(xx.reshape(-1).float()); gy.append(yy.reshape(-1).float()); gs.append(torch.full((h * w,), float(s)))
         gx, gy, gs = torch.cat(gx), torch.cat(gy), torch.cat(gs)
         size = float(hw[0][1] * 8)
-        n_obj, n_mem = 40, 12
         for f in range(num_frames):
             for o in range(n_obj):
                 m = torch.randint(0, A, (n_mem,), generator=g)

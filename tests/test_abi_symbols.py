@@ -11,7 +11,7 @@ def test_library_exports_every_declared_symbol():
     build.build()
     handle = _lib.lib()
     header = open(os.path.join(ROOT, "include", "tscd_b200.h")).read()
-    declared = set(re.findall(r"^\s*(?:int|const char\*)\s+(tscd_\w+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^\s*(?:int|int64_t|const char\*)\s+(tscd_\w+)\s*\(", header, flags=re.M))
     assert declared, "no declarations parsed"
     bound = {name for name, _, _ in _lib.SYMBOLS}
     assert declared == bound, (declared ^ bound)

@@ -111,3 +111,46 @@ def test_lap_kernel_tie_rules_vs_scipy(kmax):
             want_row[c] = r
         assert lap_col[f, :np_].cpu().tolist() == want_col, f"frame {f} shape {(np_, n)}"
         assert lap_row[f, :n].cpu().tolist() == want_row, f"frame {f} shape {(np_, n)}"
+
+
+def test_lap_kernel_large_problems_vs_scipy():
+    """The shipped OVIS-L limits allow up to 500 proposals per frame (exps/TSCD_OVIS/ovis_tscd_large.py:45,49), i.e. LSAPs of
+    up to 500 x 500 (tscd_matching.py:929-935).  tscd_cafm_lap (shared-memory solver, one warp per frame) against
+    scipy.optimize.linear_sum_assignment on cosine-like fp32 costs and on a tie-heavy table: identical assignments."""
+    import time
+    from scipy.optimize import linear_sum_assignment
+    from tscd_b200 import _lib as L, ops
+    g = torch.Generator().manual_seed(8)
+    kmax = 512
+    shapes = [(100, 100), (250, 250), (500, 300), (300, 500), (512, 512), (500, 500), (100, 100), (1, 500), (500, 1)]
+    nf = len(shapes)
+    cost = torch.zeros(nf, kmax, kmax)
+    for f, (np_, n) in enumerate(shapes):
+        if f == 6:
+            c = torch.randint(0, 5, (np_, n), generator=g).float()                      # heavy exact ties
+        else:
+            a = torch.nn.functional.normalize(torch.randn(np_, 64, generator=g), dim=1)
+            b = torch.nn.functional.normalize(torch.randn(n, 64, generator=g), dim=1)
+            c = 1.0 - (a @ b.t() + torch.nn.functional.normalize(torch.randn(np_, 32, generator=g), dim=1)
+                       @ torch.nn.functional.normalize(torch.randn(n, 32, generator=g), dim=1).t()) / 2
+        cost[f, :np_, :n] = c
+    lrow = torch.tensor([0] + list(torch.tensor([n for _, n in shapes]).cumsum(0)), dtype=torch.int32).cuda()
+    ref_n = torch.tensor([np_ for np_, _ in shapes], dtype=torch.int32).cuda()
+    lap_col = torch.full((nf, kmax), -7, dtype=torch.int32).cuda()
+    lap_row = torch.full((nf, kmax), -7, dtype=torch.int32).cuda()
+    dcost = cost.cuda().contiguous()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ops.call("tscd_cafm_lap", L.CafmLapArgs, num_frames=nf, kmax=kmax, lrow_off=lrow, ref_n=ref_n, cost=dcost,
+             lap_col=lap_col, lap_row=lap_row)
+    torch.cuda.synchronize()
+    print(f"tscd_cafm_lap, {nf} problems up to 512x512: {(time.perf_counter() - t0) * 1e3:.2f} ms")
+    for f, (np_, n) in enumerate(shapes):
+        ri, ci = linear_sum_assignment(cost[f, :np_, :n].double().numpy())
+        want_col = [-1] * np_
+        want_row = [-1] * n
+        for r, c in zip(ri.tolist(), ci.tolist()):
+            want_col[r] = c
+            want_row[c] = r
+        assert lap_col[f, :np_].cpu().tolist() == want_col, f"frame {f} shape {(np_, n)}"
+        assert lap_row[f, :n].cpu().tolist() == want_row, f"frame {f} shape {(np_, n)}"

@@ -1,48 +1,72 @@
-"""GPU parity of the whole aggregation stage (K1..final NMS) through the C-ABI vs the oracle, on a batch of
-clips with ragged proposal counts, including the CAFM recurrence with resume across two consecutive calls.
+"""GPU parity of the whole aggregation stage (K1..final NMS) through the C-ABI vs the oracle, on batches of clips with
+ragged proposal counts, including the CAFM recurrence with resume across consecutive calls, at the shapes of every
+BASELINE.json configuration the stage ships for.
 
-Bars: selection ids exact; Hungarian permutations exact wherever the optimum is not a near-tie; float tensors max-normalised error <= 1e-2 (fp16
-tensor-core operands, fp32 accumulation vs the fp32 oracle fed the same 16-bit-rounded inputs/weights);
-final detections identical as (frame, class) multisets with boxes/scores within tolerance."""
+What "parity" asserts here (tests/parity.py states the tolerances):
+  * selection ids: exact;
+  * float tensors: max-normalised error <= 1e-3 and max relative error <= 1e-2 (fp16 tensor-core operands, fp32 accumulation,
+    vs the fp32 oracle fed the same 16-bit-rounded inputs / weights);
+  * Hungarian: the device assignment equals scipy's on the device's OWN cost table for every frame (exact), the device cost
+    table is within 2e-4 of the oracle's, and where the assignment still differs from the oracle's the cost gap of the two
+    assignments in the ORACLE's table is below 2 * (#differing pairs) * 2e-4 -- a measured near-tie; the oracle then continues
+    with the device's assignment (oracle `lap_fn` hook) so that the recurrence downstream stays comparable tensor by tensor;
+  * final detections: identical to the oracle's post-processing run on the device's own logits / deltas (exact discrete
+    stage), and identical to the all-fp32 oracle's detections except where the oracle's own margin (|score - 0.001|,
+    |IoU - thr|) is below the stated epsilon; such explained flips must stay below 1 % of the detections."""
 import numpy as np
 import pytest
 import torch
 
 import oracle
+import parity
 
 pytestmark = pytest.mark.gpu
-
-
-def _rel(a, b):
-    a, b = a.float().cpu(), b.float().cpu()
-    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-6))
 
 
 def _round_sd(sd, dtype):
     return {k: (v.to(dtype).float() if v.dim() == 2 and "CA.fc" not in k else v.clone()) for k, v in sd.items()}
 
 
-def _run_case(mode, B, F, Lf, hw, C, sel_kw, o_sel_kw, seeds, calls=1, dtype=torch.float16):
-    from tscd_b200 import ops, selection, stage
-    D = 256
-    sd = oracle.init_stage_weights(C, dim=D, seed=17)
+def _decisive_weights(C, D, seed=17):
+    sd = oracle.init_stage_weights(C, dim=D, seed=seed)
     # make the prediction heads decisive so the 0.001 filters / final NMS do real work
     sd["cls_pred.weight"] = sd["cls_pred.weight"] * 30.0
     sd["cls_pred.bias"] = sd["cls_pred.bias"] - 4.0
     sd["matcher_obj_pred.weight"] = sd["matcher_obj_pred.weight"] * 5.0
     sd["matcher_obj_pred.bias"] = sd["matcher_obj_pred.bias"] - 1.0
+    return sd
+
+
+def _compare_lists(got_list, want_list, label):
+    """Exact discrete stage: same detections in the same order; boxes / scores to fp32 rounding of exp / sigmoid."""
+    for f, (got, want) in enumerate(zip(got_list, want_list)):
+        if want is None or got is None:
+            assert want is None and got is None, f"{label} frame {f}: None mismatch"
+            continue
+        g, w = got.float().cpu(), want.float()
+        assert g.shape == w.shape, f"{label} frame {f}: {g.shape[0]} vs {w.shape[0]} detections"
+        assert torch.equal(g[:, 6], w[:, 6]), f"{label} frame {f}: class / order differs"
+        torch.testing.assert_close(g[:, :4], w[:, :4], rtol=1e-5, atol=2e-3)
+        torch.testing.assert_close(g[:, 4:6], w[:, 4:6], rtol=1e-5, atol=1e-7)
+
+
+def _run_case(mode, B, F, Lf, hw, C, sel_kw, o_sel_kw, seeds, calls=1, dtype=torch.float16, obj_means=None, synth_kw=None,
+              float_tol=(parity.TOL_NORM, parity.TOL_REL), strict=True):
+    from tscd_b200 import ops, selection, stage
+    D = 256
+    sd = _decisive_weights(C, D)
     sd16 = _round_sd(sd, dtype)
     cfg = stage.StageConfig(num_classes=C, selection=selection.SelectionConfig(mode=mode, **sel_kw), dtype=dtype)
     st = stage.AggregationStage(cfg, sd)
     an = ops.AnchorSpec(hw)
     state = None
     o_states = [None] * B
-    report = []
+    stats = dict(dets=0, explained=0, flips=0, frames=0, max_norm={}, max_rel={}, cost_delta=0.0)
     for call in range(calls):
         heads, planes = [], []
         for b in range(B):
-            h, f = oracle.synth_head_outputs(F, hw, C, dim=D, seed=seeds[call] + b, clustered=True,
-                                             obj_mean=[-7.5 + 0.6 * ((b + i) % 4) for i in range(F)])
+            om = obj_means(call, b) if obj_means else [-7.5 + 0.6 * ((b + i) % 4) for i in range(F)]
+            h, f = oracle.synth_head_outputs(F, hw, C, dim=D, seed=seeds[call] + b, clustered=True, obj_mean=om, **(synth_kw or {}))
             heads.append(oracle.decode_outputs(h, hw, [8, 16, 32]))
             planes.append([p.to(dtype).float() for p in f])
         decoded = torch.cat(heads, 0)
@@ -59,99 +83,232 @@ def _run_case(mode, B, F, Lf, hw, C, sel_kw, o_sel_kw, seeds, calls=1, dtype=tor
         res, res_ori = st.to_lists(out, B, Lf)
         lrow = out["layout"].lrow_off.cpu().tolist()
         perm = trace["perm"].cpu().numpy()
+        cost_dev = trace["cafm_cost"].cpu().numpy()
+        ref_n = trace["cafm_ref_n"].cpu().tolist()
+        lap_col = trace["cafm_lap_col"].cpu().numpy()
         te16 = te.to(dtype).float()
+        cnt = out["sel"]["sel_count"].cpu().tolist()
+        dev = {k: trace[k].float().cpu() for k in ("agg_cls", "iou_cls", "iou_reg", "matched", "obj_ref", "cls_logits", "obj_logits", "reg_deltas")}
         for b in range(B):
             otr = {}
+            ppf_dev = [cnt[b * F + f] for f in range(Lf)]
+
+            def lap_fn(Co, ctx, b=b):
+                """Runs inside the oracle's CAFM: checks the device's matching table and assignment of this frame against the
+                oracle's, and resolves a proven near-tie the device's way so that everything downstream stays comparable."""
+                f = ctx["frame"]
+                lf = b * Lf + f
+                nr, n = Co.shape
+                assert (nr, n) == (ref_n[lf], ppf_dev[f]), f"call {call} clip {b} frame {f}: table shape {(nr, n)} vs device {(ref_n[lf], ppf_dev[f])}"
+                assert parity.check_device_lap_exact(cost_dev[lf], nr, n, lap_col[lf]), \
+                    f"call {call} clip {b} frame {f}: device LSAP != scipy on the device's own cost table"
+                # device reference rows are in the previous frame's ORIGINAL order, the oracle's in matched order:
+                # oracle row r_o is the previous frame's row prev_perm[r_o]  (first frame / carried state: identity)
+                to_dev = np.arange(nr) if ctx["prev_perm"] is None else np.asarray(ctx["prev_perm"])
+                assert len(to_dev) == nr
+                row_map = np.empty(nr, dtype=np.int64)
+                row_map[to_dev] = np.arange(nr)                               # row_map[r_dev] = r_ora
+                delta = float(np.abs(cost_dev[lf][:nr, :n][to_dev] - Co).max())
+                stats["cost_delta"] = max(stats["cost_delta"], delta)
+                assert delta <= parity.COST_DELTA, f"call {call} clip {b} frame {f}: matching cost differs by {delta}"
+                ri, ci = oracle.lap(Co)
+                ora_pairs = {(int(r), int(c)) for r, c in zip(ri, ci)}
+                dev_pairs = {(int(row_map[r]), c) for r, c in parity.lap_pairs(lap_col[lf][:nr])}
+                stats["frames"] += 1
+                if dev_pairs != ora_pairs:
+                    kdiff = (len(dev_pairs ^ ora_pairs) + 1) // 2
+                    gap = sum(float(Co[r, c]) for r, c in dev_pairs) - sum(float(Co[r, c]) for r, c in ora_pairs)
+                    assert -1e-5 <= gap <= 2 * kdiff * parity.COST_DELTA, \
+                        f"call {call} clip {b} frame {f}: assignment differs with oracle cost gap {gap} over {kdiff} pairs"
+                    stats["flips"] += 1
+                    stats["max_gap"] = max(stats.get("max_gap", 0.0), gap)
+                pairs = sorted(dev_pairs)
+                return np.array([r for r, _ in pairs], dtype=np.int64), np.array([c for _, c in pairs], dtype=np.int64)
+
             o_res, o_ori, o_states[b] = oracle.stage_tscd(
                 sd16, heads[b], planes[b][0], planes[b][1], planes[b][2], te16[b * Lf:(b + 1) * Lf], C, Lf, F - Lf,
-                selection=mode, select_kwargs=o_sel_kw, nms_thresh=0.5, resume=(call > 0), state=o_states[b], trace=otr)
-            # selection: exact
-            cnt = out["sel"]["sel_count"].cpu().tolist()
+                selection=mode, select_kwargs=o_sel_kw, nms_thresh=0.5, resume=(call > 0), state=o_states[b], trace=otr, lap_fn=lap_fn)
+            label = f"call {call} clip {b}"
+            # ---- selection: exact ----
             for f in range(F):
                 n = cnt[b * F + f]
                 want = otr["idxs"][f]
-                assert out["sel"]["sel_idx"][b * F + f, :n].cpu().tolist() == (want.tolist() if want is not None else [])
+                assert out["sel"]["sel_idx"][b * F + f, :n].cpu().tolist() == (want.tolist() if want is not None else []), f"{label} frame {f}"
             l0, l1 = lrow[b * Lf], lrow[(b + 1) * Lf]
-            errs = dict(
-                agg_cls=_rel(trace["agg_cls"][l0:l1], otr["agg_cls"]),
-                iou_cls=_rel(trace["iou_cls"][l0:l1], otr["iou_cls"]),
-                iou_reg=_rel(trace["iou_reg"][l0:l1], otr["iou_reg"]),
-                matched=_rel(trace["matched"][l0:l1], otr["matched"]),
-                obj_ref=_rel(trace["obj_ref"][l0:l1], otr["obj_ref"]),
-                cls_logits=_rel(trace["cls_logits"][l0:l1, :C], otr["cls_preds"]),
-                obj_logits=_rel(trace["obj_logits"][l0:l1, :1], otr["obj_preds"]),
-                reg_deltas=_rel(trace["reg_deltas"][l0:l1, :4], otr["reg_deltas"]),
-            )
-            # Hungarian permutations: exact
+            ppf = ppf_dev
+            # ---- Hungarian: checked frame by frame inside lap_fn; with every near-tie resolved the device's way the
+            #      permutations must now be identical ----
             o_perm = np.concatenate(otr["cafm"]["perm"]) if otr["cafm"].get("perm") else np.zeros(0)
-            perm_ok = np.array_equal(perm[l0:l1], o_perm)
-            # detections
-            tot = match = 0
+            assert np.array_equal(perm[l0:l1], o_perm), f"{label}: permutations differ"
+
+            # ---- float tensors ----
+            pairs = [("agg_cls", otr["agg_cls"]), ("iou_cls", otr["iou_cls"]), ("iou_reg", otr["iou_reg"]),
+                     ("matched", otr["matched"]), ("obj_ref", otr["obj_ref"]), ("obj_logits", otr["obj_preds"]),
+                     ("reg_deltas", otr["reg_deltas"]), ("cls_logits", otr["cls_preds"])]
+            for name, want in pairs:
+                got = dev[name][l0:l1]
+                got = got[:, :want.shape[1]] if want.dim() == 2 else got
+                en, er = parity.float_err(got, want)
+                stats["max_norm"][name] = max(stats["max_norm"].get(name, 0.0), en)
+                stats["max_rel"][name] = max(stats["max_rel"].get(name, 0.0), er)
+                assert en <= float_tol[0], f"{label} {name}: max-normalised error {en}"
+                assert er <= float_tol[1], f"{label} {name}: max relative error {er}"
+
+            # ---- final detections: (a) exact on the device's own logits / deltas ----
+            rows_l = [otr["rows"][f] for f in range(Lf)]
+            ori_boxes = torch.cat([r[:, :4] for r in rows_l if r is not None], 0) if any(r is not None for r in rows_l) else torch.zeros(0, 4)
+            reg_dev = oracle.decode_reg_preds5(dev["reg_deltas"][l0:l1, :4], ori_boxes)
+            cls_pf, obj_pf, reg_pf, s = [], [], [], 0
             for f in range(Lf):
-                for got, want in ((res[b * Lf + f], o_res[f]), (res_ori[b * Lf + f], o_ori[f])):
-                    if want is None or got is None:
-                        assert want is None and got is None
+                n = ppf[f]
+                cls_pf.append(dev["cls_logits"][l0 + s:l0 + s + n, :C]); obj_pf.append(dev["obj_logits"][l0 + s:l0 + s + n, 0]); reg_pf.append(reg_dev[s:s + n])
+                s += n
+            own_dbg = []
+            own_res, own_ori = oracle.postprocess(rows_l, C, cls_pf, obj_pf, reg_pf, nms_thre=0.5, debug=own_dbg)
+            try:
+                _compare_lists(res[b * Lf:(b + 1) * Lf], own_res, label + " (own inputs)")
+            except AssertionError:
+                # sigmoid / exp are CUDA libm on the device and ATen-CPU in the oracle (1-ulp differences): saturated class scores
+                # give EXACT score ties whose order such an ulp decides.  Anything beyond a few ulp still fails here.
+                ulp = dict(eps_score=4e-6, eps_iou=2e-6, tol_box=2e-3, tol_score=4e-6) if strict else {}
+                for f in range(Lf):
+                    if own_dbg[f] is not None and res[b * Lf + f] is not None:
+                        _, ne = parity.explain_detection_diffs(own_dbg[f]["cand"], own_dbg[f]["keep"], res[b * Lf + f], 0.5,
+                                                               label=f"{label} frame {f} (own inputs)", **ulp)
+                        stats["ulp"] = stats.get("ulp", 0) + ne + 1
+            _compare_lists(res_ori[b * Lf:(b + 1) * Lf], o_ori, label + " (still)")       # unrefined rows: no float stage in between
+            # ---- (b) vs the all-fp32 oracle: identical up to measured near-ties ----
+            if True:
+                for f in range(Lf):
+                    dbg = otr["post"][f]
+                    got = res[b * Lf + f]
+                    if dbg is None or got is None:
+                        assert (o_res[f] is None) == (got is None), f"{label} frame {f}: None mismatch vs fp32 oracle"
                         continue
-                    g, w_ = got.cpu(), want
-                    tot += max(len(g), len(w_))
-                    used = set()
-                    for i in range(len(w_)):
-                        cand = [j for j in range(len(g)) if j not in used and g[j, 6] == w_[i, 6]
-                                and torch.allclose(g[j, :6], w_[i, :6], rtol=2e-2, atol=0.75)]
-                        if cand:
-                            used.add(cand[0]); match += 1
-            report.append((call, b, errs, perm_ok, match, tot))
-    return report
+                    common, expl = parity.explain_detection_diffs(dbg["cand"], dbg["keep"], got, 0.5, label=f"{label} frame {f}")
+                    stats["dets"] += common
+                    stats["explained"] += expl
+    return stats
 
 
-def _check(report):
-    for call, b, errs, perm_ok, match, tot in report:
-        print(f"call {call} clip {b}: perm_ok={perm_ok} dets {match}/{tot} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
-    # The matching costs come from fp16-operand GEMMs here, so a near-tie assignment may legitimately flip
-    # (exact assignment parity on exact costs is tests/test_gpu_cafm.py); require it for most clips.
-    assert sum(1 for r in report if r[3]) >= 0.6 * len(report)
-    for call, b, errs, perm_ok, match, tot in report:
-        for k, v in errs.items():
-            assert v < 1e-2, f"{k} rel err {v} (call {call}, clip {b})"
-        assert tot == 0 or match / tot >= 0.98, f"detections {match}/{tot}"
+def linear_sum(C):
+    from scipy.optimize import linear_sum_assignment
+    return linear_sum_assignment(C.astype(np.float64))
+
+
+def _report(stats, name, max_flip_frac=0.15):
+    print(f"\n[{name}] frames {stats['frames']} assignment near-tie flips {stats['flips']} (max oracle cost gap {stats.get('max_gap', 0.0):.2e}) | detections {stats['dets']} explained near-tie "
+          f"differences {stats['explained']} | max cost delta {stats['cost_delta']:.2e} | frames with ulp-level ties on own inputs {stats.get('ulp', 0)}")
+    print("   max-normalised: " + " ".join(f"{k}={v:.2e}" for k, v in stats["max_norm"].items()))
+    print("   max relative:   " + " ".join(f"{k}={v:.2e}" for k, v in stats["max_rel"].items()))
+    assert stats["dets"] > 0
+    assert stats["explained"] <= 0.01 * stats["dets"] + 1, "too many near-tie differences: not an isolated flip"
+    assert stats["flips"] <= max(1, max_flip_frac * stats["frames"])
 
 
 def test_stage_mode_b_ragged_with_resume():
     """What the shipped TSCD-L exps run: postprocess_widx limits, no pre-NMS; two consecutive clip batches."""
-    rep = _run_case("B", B=3, F=6, Lf=3, hw=[(16, 16), (8, 8), (4, 4)], C=5,
-                    sel_kw=dict(minimal_limit=12, maximal_limit=40, use_pre_nms=False),
-                    o_sel_kw=dict(nms_thre=0.75, minimal_limit=12, maximal_limit=40, use_pre_nms=False),
-                    seeds=[100, 200], calls=2)
-    _check(rep)
+    st = _run_case("B", B=3, F=6, Lf=3, hw=[(16, 16), (8, 8), (4, 4)], C=5,
+                   sel_kw=dict(minimal_limit=12, maximal_limit=40, use_pre_nms=False),
+                   o_sel_kw=dict(nms_thre=0.75, minimal_limit=12, maximal_limit=40, use_pre_nms=False),
+                   seeds=[100, 200], calls=2)
+    _report(st, "mode B ragged + resume")
 
 
 def test_stage_mode_a_topk_nms():
     """BASELINE config 2 selection: top-750 objectness -> class-aware NMS(0.75) -> first 30, then TSCD MCA/CAFM."""
-    rep = _run_case("A", B=2, F=8, Lf=2, hw=[(40, 40), (20, 20), (10, 10)], C=25,
-                    sel_kw=dict(pre_k=750, top_k=30, nms_thresh=0.75),
-                    o_sel_kw=dict(nms_thre=0.75, pre_k=750, top_k=30), seeds=[7], calls=1)
-    _check(rep)
+    st = _run_case("A", B=2, F=8, Lf=2, hw=[(40, 40), (20, 20), (10, 10)], C=25,
+                   sel_kw=dict(pre_k=750, top_k=30, nms_thresh=0.75),
+                   o_sel_kw=dict(nms_thre=0.75, pre_k=750, top_k=30), seeds=[7], calls=1)
+    _report(st, "mode A 750->30")
 
 
 def test_stage_full_size_baseline_config():
     """BASELINE.json configs[1] at full size: one 32-frame clip (8 local + 24 global) at 576x576 (6804 anchors), 25
     classes, top-750 -> NMS 0.75 -> 30 proposals/frame, through every kernel of the stage (split K1, top-K NMS prefix
     path, tcgen05 attention, smem/mma.sync CAFM chain, register LSAP, mma.sync TaskAligned, per-class final NMS)."""
-    rep = _run_case("A", B=1, F=32, Lf=8, hw=[(72, 72), (36, 36), (18, 18)], C=25,
-                    sel_kw=dict(pre_k=750, top_k=30, nms_thresh=0.75),
-                    o_sel_kw=dict(nms_thre=0.75, pre_k=750, top_k=30), seeds=[2024], calls=1)
-    _check(rep)
+    st = _run_case("A", B=1, F=32, Lf=8, hw=[(72, 72), (36, 36), (18, 18)], C=25,
+                   sel_kw=dict(pre_k=750, top_k=30, nms_thresh=0.75),
+                   o_sel_kw=dict(nms_thre=0.75, pre_k=750, top_k=30), seeds=[2024], calls=1)
+    _report(st, "configs[1] full size")
+
+
+def test_stage_config0_vid_l_full_size():
+    """BASELINE.json configs[0] at full size: TSCD-L VID, one 16-frame 576x576 clip (4 local + 12 global,
+    exps/TSCD_VID/vid_tscd_large.py:27-30), 30 classes, mode B with minimal_limit = 50, NO maximal_limit and no pre-NMS (:39-42):
+    frames below the 0.001 filter fall back to their top-50, the others keep every anchor above it (here 50 .. ~300), bounded
+    only by SelectionConfig.max_proposals = 512.  Generic CAFM chain (frames > 32 rows), shared-memory LSAP, fp32 TaskAligned
+    attention, workspace NMS (512 x 30 = 15 360-row candidate pitch)."""
+    means = [-13.0, -10.0, -10.2, -11.5, -10.4, -12.5, -9.9, -10.6, -11.0, -10.1, -13.0, -10.0, -9.8, -11.8, -10.4, -10.3]   # 50 .. 371 proposals per frame
+    st = _run_case("B", B=1, F=16, Lf=4, hw=[(72, 72), (36, 36), (18, 18)], C=30,
+                   sel_kw=dict(minimal_limit=50, maximal_limit=0, use_pre_nms=False),
+                   o_sel_kw=dict(nms_thre=0.75, minimal_limit=50, maximal_limit=0, use_pre_nms=False),
+                   seeds=[2024], calls=1, obj_means=lambda call, b: means, synth_kw=dict(n_obj=3, n_mem=10))
+    _report(st, "configs[0] VID-L full size", max_flip_frac=0.5)
+
+
+def test_stage_ovis_l_mode_b_ragged_full_size():
+    """The shipped OVIS TSCD-L limits at full size (exps/TSCD_OVIS/ovis_tscd_large.py:32-49): 32 frames (8 local + 24
+    global), 25 classes, mode B, minimal_limit 50 / maximal_limit 500, no pre-NMS, ragged 50 .. 500 proposals per frame
+    (up to ~12 000 keys per query, LSAPs up to 500 x 500, up to 12 500 final-NMS rows per frame)."""
+    def means(call, b):
+        return [[-13.5, -8.0, -10.2, -10.6, -9.7, -11.0, -13.0, -9.9][i % 8] for i in range(32)]     # 50 .. 500 proposals per frame
+    st = _run_case("B", B=1, F=32, Lf=8, hw=[(72, 72), (36, 36), (18, 18)], C=25,
+                   sel_kw=dict(minimal_limit=50, maximal_limit=500, use_pre_nms=False),
+                   o_sel_kw=dict(nms_thre=0.75, minimal_limit=50, maximal_limit=500, use_pre_nms=False),
+                   seeds=[77], calls=1, obj_means=means, synth_kw=dict(n_obj=4, n_mem=10))
+    _report(st, "OVIS-L mode B full size", max_flip_frac=0.5)
+
+
+@pytest.mark.parametrize("P,K", [(300, 100), (1500, 50), (1000, 75)])
+def test_stage_sweep_points(P, K):
+    """BASELINE.json configs[4] sweep corners: pre-NMS top-k P in 300 .. 1500, proposals per frame K in 30 .. 100 (K > 32 leaves
+    the shared-memory CAFM chain / mma.sync TaskAligned fast paths)."""
+    st = _run_case("A", B=2, F=6, Lf=2, hw=[(40, 40), (20, 20), (10, 10)], C=25,
+                   sel_kw=dict(pre_k=P, top_k=K, nms_thresh=0.75),
+                   o_sel_kw=dict(nms_thre=0.75, pre_k=P, top_k=K), seeds=[31], calls=1)
+    _report(st, f"sweep P={P} K={K}", max_flip_frac=0.5)
+
+
+def test_stage_capacity_overflow_is_loud():
+    """Mode B without a maximal_limit: a frame with more proposals than max_proposals must raise, never truncate silently."""
+    from tscd_b200 import ops, selection, stage
+    C, D, hw, F, Lf = 5, 256, [(16, 16), (8, 8), (4, 4)], 4, 2
+    sd = oracle.init_stage_weights(C, dim=D, seed=3)
+    cfg = stage.StageConfig(num_classes=C, selection=selection.SelectionConfig(mode="B", minimal_limit=10, use_pre_nms=False,
+                                                                              max_proposals=64))
+    st = stage.AggregationStage(cfg, sd)
+    h, f = oracle.synth_head_outputs(F, hw, C, dim=D, seed=5, obj_mean=[-2.0, -12.0, -12.0, -12.0])     # frame 0: hundreds above 0.001
+    decoded = oracle.decode_outputs(h, hw, [8, 16, 32])
+    an = ops.AnchorSpec(hw)
+    head = ops.HeadViews.from_fused(decoded.cuda(), an, apply_sigmoid=False, apply_decode=False)
+    views = tuple(ops.view_rowmajor(p.half().cuda().contiguous(), an) for p in f)
+    out = st.forward(head, views, torch.float16, oracle.timing_signal_1d(torch.arange(Lf), 256), 1, F, Lf)
+    with pytest.raises(RuntimeError, match="max_proposals"):
+        st.to_lists(out, 1, Lf)
+    # and a configuration that can never fit is rejected at construction
+    with pytest.raises(RuntimeError, match="max_proposals"):
+        stage.AggregationStage(stage.StageConfig(num_classes=C, selection=selection.SelectionConfig(mode="B", maximal_limit=600)), sd)
+    with pytest.raises(RuntimeError, match="NMS capacity"):
+        stage.AggregationStage(stage.StageConfig(num_classes=80, selection=selection.SelectionConfig(mode="B", maximal_limit=500)), sd)
 
 
 def test_stage_bf16_operands():
     """StageConfig.dtype = bfloat16 (tensor-core operands bf16 instead of fp16): every kernel has a bf16 instantiation.
-    bf16 keeps 8 mantissa bits, so the float tolerance is 8x looser and near-threshold decisions (0.75 / 0.99 cosine masks,
-    Hungarian near-ties, 0.001 score filters) may flip: only a loose detection agreement is required."""
-    rep = _run_case("A", B=2, F=8, Lf=2, hw=[(40, 40), (20, 20), (10, 10)], C=25,
-                    sel_kw=dict(pre_k=750, top_k=30, nms_thresh=0.75),
-                    o_sel_kw=dict(nms_thre=0.75, pre_k=750, top_k=30), seeds=[7], calls=1, dtype=torch.bfloat16)
-    for call, b, errs, perm_ok, match, tot in rep:
-        print(f"bf16 call {call} clip {b}: perm_ok={perm_ok} dets {match}/{tot} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
-        for k, v in errs.items():
-            assert v < 5e-2, f"{k} rel err {v}"
-        assert tot == 0 or match / tot >= 0.85
+    bf16 keeps 8 mantissa bits: float tolerance 8x looser (stated), the discrete checks are the same margin-based ones with
+    the cost delta scaled accordingly."""
+    old = parity.COST_DELTA, parity.EPS_SCORE, parity.EPS_IOU, parity.TOL_BOX_PX, parity.TOL_SCORE
+    parity.COST_DELTA, parity.EPS_SCORE, parity.EPS_IOU, parity.TOL_BOX_PX, parity.TOL_SCORE = 2e-3, 8e-2, 4e-2, 2.0, 8e-2
+    try:
+        st = _run_case("A", B=2, F=8, Lf=2, hw=[(40, 40), (20, 20), (10, 10)], C=25,
+                       sel_kw=dict(pre_k=750, top_k=30, nms_thresh=0.75),
+                       o_sel_kw=dict(nms_thre=0.75, pre_k=750, top_k=30), seeds=[7], calls=1, dtype=torch.bfloat16,
+                       float_tol=(8e-3, 8e-2), strict=False)
+    finally:
+        parity.COST_DELTA, parity.EPS_SCORE, parity.EPS_IOU, parity.TOL_BOX_PX, parity.TOL_SCORE = old
+    print(st)
+    assert stats_ok(st)
+
+
+def stats_ok(st):
+    return st["dets"] > 0 and st["explained"] <= 0.05 * st["dets"] + 2

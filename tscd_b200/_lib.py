@@ -30,13 +30,14 @@ class SelectArgs(C.Structure):
                 ("cand_cap", C.c_int32), ("anchors", Anchors), ("reg", View), ("obj", View), ("cls", View),
                 ("cand_idx", C.c_void_p), ("cand_box", C.c_void_p), ("cand_score", C.c_void_p),
                 ("cand_cls", C.c_void_p), ("cand_count", C.c_void_p),
-                ("ws_conf", C.c_void_p), ("ws_cls", C.c_void_p), ("ws_pitch", C.c_int32)]
+                ("ws_conf", C.c_void_p), ("ws_cls", C.c_void_p), ("ws_pitch", C.c_int32), ("status", C.c_void_p)]
 
 
 class NmsArgs(C.Structure):
     _fields_ = [("num_frames", C.c_int32), ("cand_cap", C.c_int32), ("max_keep", C.c_int32), ("iou_thresh", C.c_float),
                 ("box", C.c_void_p), ("score", C.c_void_p), ("cls", C.c_void_p), ("count", C.c_void_p),
-                ("keep", C.c_void_p), ("keep_count", C.c_void_p), ("status", C.c_void_p)]
+                ("keep", C.c_void_p), ("keep_count", C.c_void_p), ("status", C.c_void_p),
+                ("ws", C.c_void_p), ("ws_bytes", C.c_int64), ("strict_keep", C.c_int32)]
 
 
 class GatherArgs(C.Structure):
@@ -162,6 +163,7 @@ SYMBOLS = [
     ("tscd_last_cuda_error", C.c_char_p, []),
     ("tscd_select", C.c_int, [C.POINTER(SelectArgs), C.c_void_p]),
     ("tscd_nms", C.c_int, [C.POINTER(NmsArgs), C.c_void_p]),
+    ("tscd_nms_workspace_bytes", C.c_int64, [C.c_int32, C.c_int32]),
     ("tscd_gather", C.c_int, [C.POINTER(GatherArgs), C.c_void_p]),
     ("tscd_local_offsets", C.c_int, [C.POINTER(LocalOffsetsArgs), C.c_void_p]),
     ("tscd_linear", C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
@@ -202,7 +204,7 @@ def lib():
 
 # kernels launched per C-ABI call (for the bench's `gpu_launches` claim)
 _DEBUG_SYNC = os.environ.get("TSCD_DEBUG_SYNC", "0") == "1"
-KERNELS_PER_CALL = {"tscd_gather": 2}
+KERNELS_PER_CALL = {"tscd_gather": 2, "tscd_nms_large": 3}
 launch_count = 0
 # optional per-entry-point CUDA-event timing: {"names": set or None (= all), "events": {name: [(start, end), ...]}}
 profile = None

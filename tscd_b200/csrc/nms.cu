@@ -1,4 +1,5 @@
-// K2: class-aware batched NMS, one CTA per frame, bit-exact with torchvision's coordinate-trick path.
+// K2: class-aware batched NMS, one CTA per frame (up to 4096 candidates; larger frames: csrc/nms_large.cu), bit-exact with
+// torchvision's coordinate-trick path.
 //
 // Reference: torchvision.ops.batched_nms as called at yolox/models/tscd_head.py:1630 and
 // yolox/models/post_process.py:58,73,510  (boxes.py `_batched_nms_coordinate_trick`):
@@ -14,25 +15,11 @@
 // Later chunks are never touched before they are needed: work is O(kept * processed) instead of O(N^2) and stops
 // as soon as max_keep boxes are kept (mode A only needs the first K=30 survivors of 750).
 #include "common.cuh"
+#include "nms.cuh"
 
 namespace tscd {
 
 constexpr int kNmsThreads = 256;
-constexpr int kNmsCap = 4096;
-
-__device__ __forceinline__ bool iou_gt(const float4& a, float sa, const float4& b, float sb, double thr) {
-    float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
-    float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
-    // disjoint boxes (every pair of different classes after the coordinate-trick offset): inter = 0, and
-    // 0/u > thr is false for thr >= 0 (0/0 = NaN compares false too) -- skip the division
-    if (!(xx2 > xx1) || !(yy2 > yy1)) return false;
-    float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
-    float inter = __fmul_rn(w, h);
-    float uni = __fsub_rn(__fadd_rn(sa, sb), inter);
-    float ovr = __fdiv_rn(inter, uni);
-    return (double)ovr > thr;
-}
-
 
 // -------------------------------------------------------------------------------------------------------------
 // Per-class fast path, shared by both kernels.  After the coordinate-trick offset, boxes of different classes can
@@ -211,6 +198,7 @@ __device__ bool nms_per_class(const tscd_nms_args& args, int frame, int n, const
     // score-ordered compaction of the kept boxes, truncated to max_keep
     {
         const int max_keep = args.max_keep;
+        const int lim = max_keep + (args.strict_keep ? 1 : 0);     // strict: look one survivor further to detect the overflow
         int32_t* keep = args.keep + (int64_t)frame * max_keep;
         int* carry = &sc.misc[1];
         int* scan = sc.off;              // class offsets are no longer needed: reuse as scan scratch (>= 33 ints)
@@ -225,9 +213,12 @@ __device__ bool nms_per_class(const tscd_nms_args& args, int frame, int n, const
             __syncthreads();
             if (tid == 0) *carry = base + tot;
             __syncthreads();
-            if (*carry >= max_keep) break;
+            if (*carry >= lim) break;
         }
-        if (tid == 0) args.keep_count[frame] = min(*carry, max_keep);
+        if (tid == 0) {
+            args.keep_count[frame] = min(*carry, max_keep);
+            if (args.strict_keep && *carry > max_keep) atomicMin(args.status, TSCD_ERR_CAPACITY);
+        }
     }
     return true;
 }
@@ -274,6 +265,7 @@ __global__ void __launch_bounds__(kNmsThreads, 4) nms_kernel(const tscd_nms_args
     const float off_unit = __fadd_rn(mx, 1.f);  // boxes.max() + 1
     const double thr = (double)args.iou_thresh;
     const int max_keep = args.max_keep;
+    const int lim = max_keep + (args.strict_keep ? 1 : 0);         // strict: look one survivor further to detect the overflow
     int32_t* keep = args.keep + (int64_t)frame * max_keep;
     int* s_keptidx = reinterpret_cast<int*>(dead);     // sorted positions of the boxes kept so far (<= min(n, max_keep))
 
@@ -390,19 +382,22 @@ __global__ void __launch_bounds__(kNmsThreads, 4) nms_kernel(const tscd_nms_args
                 // truncate to max_keep
                 int rank = __popc(kept & ((1u << lane) - 1u));
                 bool mine = (kept >> lane) & 1u;
-                if (mine && nk + rank < max_keep) {
-                    keep[nk + rank] = (int)(0xffffffffu - (uint32_t)(skey[c0 + lane] & 0xffffffffull));
+                if (mine && nk + rank < lim) {
+                    if (nk + rank < max_keep) keep[nk + rank] = (int)(0xffffffffu - (uint32_t)(skey[c0 + lane] & 0xffffffffull));
                     s_keptidx[nk + rank] = c0 + lane;
                 }
-                if (lane == 0) s_nkept = nk + min(__popc(kept), max_keep - nk);
+                if (lane == 0) s_nkept = nk + min(__popc(kept), lim - nk);
             }
             __syncthreads();
-            if (s_nkept >= max_keep) break;
+            if (s_nkept >= lim) break;
         }
         __syncthreads();
-        if (s_nkept >= max_keep || n_work == n) break;     // done; otherwise the prefix was too short: full sort
+        if (s_nkept >= lim || n_work == n) break;     // done; otherwise the prefix was too short: full sort
     }
-    if (threadIdx.x == 0) args.keep_count[frame] = s_nkept;
+    if (threadIdx.x == 0) {
+        args.keep_count[frame] = min(s_nkept, max_keep);
+        if (args.strict_keep && s_nkept > max_keep) atomicMin(args.status, TSCD_ERR_CAPACITY);
+    }
 }
 
 // -------------------------------------------------------------------------------------------------------------
@@ -505,10 +500,11 @@ __global__ void __launch_bounds__(kNmsMatThreads) nms_matrix_kernel(const tscd_n
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
         const int max_keep = args.max_keep;
+        const int lim = max_keep + (args.strict_keep ? 1 : 0);
         int32_t* keep = args.keep + (int64_t)frame * max_keep;
         uint32_t removed = 0u;           // lane w < W: suppressed flags of boxes [32w, 32w+32)
         int nk = 0;
-        for (int w = 0; w < W && nk < max_keep; ++w) {
+        for (int w = 0; w < W && nk < lim; ++w) {
             const int i = (w << 5) + lane;
             const uint32_t rem_w = __shfl_sync(0xffffffffu, removed, w);
             const uint32_t diag = i < n ? smask[i * W + w] : 0u;          // boxes of this word that box i suppresses
@@ -521,9 +517,9 @@ __global__ void __launch_bounds__(kNmsMatThreads) nms_matrix_kernel(const tscd_n
                 if ((alive >> l) & 1u) { kept |= 1u << l; alive &= ~dl; }
             }
             // truncate to max_keep, emit, and apply the kept rows to the later words
-            const int room = max_keep - nk;
+            const int room = lim - nk;
             const int rank = __popc(kept & ((1u << lane) - 1u));
-            const bool mine = ((kept >> lane) & 1u) && rank < room;
+            const bool mine = ((kept >> lane) & 1u) && nk + rank < max_keep;
             if (mine) keep[nk + rank] = (int)(0xffffffffu - (uint32_t)(skey[i] & 0xffffffffull));
             uint32_t kk = kept;
             while (kk) {
@@ -533,7 +529,10 @@ __global__ void __launch_bounds__(kNmsMatThreads) nms_matrix_kernel(const tscd_n
             }
             nk += min(__popc(kept), room);
         }
-        if (lane == 0) args.keep_count[frame] = nk;
+        if (lane == 0) {
+            args.keep_count[frame] = min(nk, max_keep);
+            if (args.strict_keep && nk > max_keep) atomicMin(args.status, TSCD_ERR_CAPACITY);
+        }
     }
 }
 
@@ -543,7 +542,8 @@ extern "C" int tscd_nms(const tscd_nms_args* a, void* stream) {
     using namespace tscd;
     if (!a || a->num_frames < 0 || a->cand_cap <= 0 || a->max_keep <= 0 || !(a->iou_thresh >= 0.f)) return TSCD_ERR_INVALID_ARG;
     if (a->num_frames == 0) return TSCD_OK;
-    int cap = a->cand_cap < kNmsCap ? a->cand_cap : kNmsCap;
+    if (a->cand_cap > kNmsCap) return nms_large_launch(*a, reinterpret_cast<cudaStream_t>(stream));
+    int cap = a->cand_cap;
     int cap64 = 1;
     while (cap64 < cap) cap64 <<= 1;   // sort buffer must hold the padded power of two
     if (cap64 < kNmsMatThreads) cap64 = kNmsMatThreads;   // ... and E * blockDim.x keys of the block sort (either kernel)

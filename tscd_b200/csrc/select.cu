@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(kSelThreads, PRE ? 3 : 2) select_kernel(const 
     }
     __syncthreads();
     const int n_sel = min(n_sel_raw, args.cand_cap);
+    if (n_sel_raw > args.cand_cap && args.status && threadIdx.x == 0) atomicMin(args.status, TSCD_ERR_CAPACITY);
 
     // ---- mode A: order by objectness, descending, ties lower anchor id first ---------------------------
     if (args.mode == 0) {

@@ -95,10 +95,21 @@ class HeadViews:
                          cls[0].shape[0], cls[0].shape[1], True, True, (tuple(reg), tuple(obj), tuple(cls)))
 
 
+def _dev(head: "HeadViews"):
+    """Device of the head tensors (outputs are allocated next to their inputs, not on the current device).  Pinned host
+    tensors (forward_host's zero-copy views) fall back to the current CUDA device."""
+    for group in head._keep:
+        for t in (group if isinstance(group, (tuple, list)) else (group,)):
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                return t.device
+    return torch.device("cuda", torch.cuda.current_device())
+
+
 def select(head: HeadViews, mode: str, pre_k: int = 750, conf_thresh: float = 0.001, minimal_limit: int = 0,
-           maximal_limit: int = 0, cand_cap: Optional[int] = None):
-    """K1.  Returns dict(idx,box,score,cls,count) of device tensors [F,cap(,4)] / [F]."""
-    dev = torch.device("cuda")
+           maximal_limit: int = 0, cand_cap: Optional[int] = None, status: Optional[torch.Tensor] = None):
+    """K1.  Returns dict(idx,box,score,cls,count) of device tensors [F,cap(,4)] / [F].  `status` ([1] int32) receives
+    TSCD_ERR_CAPACITY when a mode-B frame selects more than cand_cap anchors."""
+    dev = _dev(head)
     Fn, A = head.num_frames, head.anchors.num_anchors
     if cand_cap is None:
         cand_cap = min(pre_k, A) if mode == "A" else (maximal_limit if maximal_limit else A)
@@ -118,6 +129,7 @@ def select(head: HeadViews, mode: str, pre_k: int = 750, conf_thresh: float = 0.
     a.anchors, a.reg, a.obj, a.cls = head.anchors.to_c(), head.reg, head.obj, head.cls
     a.cand_idx, a.cand_box, a.cand_score = _p(out["idx"]), _p(out["box"]), _p(out["score"])
     a.cand_cls, a.cand_count = _p(out["cls"]), _p(out["count"])
+    a.status = _p(status)
     class_contiguous = all(head.cls.chan_stride[i] == 1 for i in range(len(head.anchors.hw)))
     if mode == "A" and not class_contiguous:   # workspace of the streaming class-max kernel (K1 = two kernels for NCHW planes)
         pitch = (A + 15) // 16 * 16
@@ -131,10 +143,17 @@ def select(head: HeadViews, mode: str, pre_k: int = 750, conf_thresh: float = 0.
     return out
 
 
+NMS_SMEM_CAP = 4096       # csrc/nms.cuh kNmsCap: larger candidate lists take the workspace path (csrc/nms_large.cu)
+NMS_MAX_CAP = 16384       # kNmsLargeCap
+
+
 def nms(box: torch.Tensor, score: torch.Tensor, cls: torch.Tensor, count: torch.Tensor, iou_thresh: float,
-        max_keep: Optional[int] = None, status: Optional[torch.Tensor] = None):
-    """K2.  box [F,cap,4] f32, score [F,cap] f32, cls [F,cap] i32, count [F] i32 -> (keep [F,max_keep], keep_count [F])."""
+        max_keep: Optional[int] = None, status: Optional[torch.Tensor] = None, strict_keep: bool = False):
+    """K2.  box [F,cap,4] f32, score [F,cap] f32, cls [F,cap] i32, count [F] i32 -> (keep [F,max_keep], keep_count [F]).
+    strict_keep: more than max_keep survivors in a frame is a capacity error (status) instead of a truncation."""
     Fn, cap = score.shape
+    if cap > NMS_MAX_CAP:
+        raise RuntimeError(f"tscd_nms: {cap} candidates per frame exceed the kernel capacity of {NMS_MAX_CAP}")
     max_keep = cap if max_keep is None else max_keep
     keep = torch.empty(Fn, max_keep, dtype=torch.int32, device=score.device)
     keep_count = torch.empty(Fn, dtype=torch.int32, device=score.device)
@@ -144,15 +163,23 @@ def nms(box: torch.Tensor, score: torch.Tensor, cls: torch.Tensor, count: torch.
     a.num_frames, a.cand_cap, a.max_keep, a.iou_thresh = Fn, cap, max_keep, iou_thresh
     a.box, a.score, a.cls, a.count = _p(box), _p(score), _p(cls), _p(count)
     a.keep, a.keep_count, a.status = _p(keep), _p(keep_count), _p(status)
+    a.strict_keep = int(strict_keep)
+    ws = None
+    if cap > NMS_SMEM_CAP:
+        a.ws_bytes = L.lib().tscd_nms_workspace_bytes(Fn, cap)
+        ws = torch.empty(a.ws_bytes, dtype=torch.uint8, device=score.device)
+        a.ws = _p(ws)
     with L.timed("tscd_nms"):
-        L.check(L.lib().tscd_nms(C.byref(a), _stream()), "tscd_nms")
+        L.check(L.lib().tscd_nms(C.byref(a), _stream()), "tscd_nms_large" if ws is not None else "tscd_nms")
+    if ws is not None and not torch.cuda.is_current_stream_capturing():
+        ws.record_stream(torch.cuda.current_stream())
     return keep, keep_count, status
 
 
 def gather(head: HeadViews, feats, feat_dtype: torch.dtype, feat_dim: int, cand, keep=None, keep_count=None,
            max_keep: Optional[int] = None, bank_dtype: torch.dtype = torch.float16, bank_rows: Optional[int] = None):
     """K3.  feats = (view_cls, view_reg, view_edge).  Returns dict with sel_count,row_off,sel_idx,sel_rows,bank_*."""
-    dev = torch.device("cuda")
+    dev = cand["idx"].device
     Fn, Cn = head.num_frames, head.num_classes
     use_keep = keep is not None
     max_keep = (keep.shape[1] if use_keep else cand["cap"]) if max_keep is None else max_keep

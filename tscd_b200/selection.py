@@ -21,10 +21,42 @@ class SelectionConfig:
     minimal_limit: int = 0          # mode B
     maximal_limit: int = 0          # mode B
     use_pre_nms: bool = True        # mode B (False in both shipped -L exps)
+    # Mode B without a maximal_limit (VID TSCD-L, exps/TSCD_VID/vid_tscd_large.py:39-42) keeps EVERY anchor at or above
+    # conf_thresh: the reference's per-frame list is unbounded (up to all A = 6804 anchors), the kernels' buffers are not.
+    # max_proposals is the explicit per-frame capacity of the proposal list (bank pitch, CAFM state / cost tables);
+    # a frame that would keep more sets the stage's status flag and forward raises -- never a silent truncation.
+    max_proposals: int = 512        # the whole stage needs <= 512 (CAFM chain capacity, csrc/cafm.cu kChainMax); K1-K3 alone do not
+
+    def validate(self, chain_capacity: int = 512):
+        if self.mode not in ("A", "B"):
+            raise RuntimeError(f"selection mode {self.mode!r}: expected 'A' (postpro_woclass) or 'B' (postprocess_widx)")
+        if not 1 <= self.max_proposals <= chain_capacity:
+            raise RuntimeError(f"max_proposals = {self.max_proposals}: the CAFM chain holds at most {chain_capacity} proposals per frame")
+        if self.mode == "A":
+            if self.top_k > self.max_proposals:
+                raise RuntimeError(f"top_k = {self.top_k} exceeds max_proposals = {self.max_proposals}")
+            if self.pre_k > 8192:
+                raise RuntimeError(f"pre_k = {self.pre_k}: the selection kernel sorts at most 8192 survivors per frame")
+        else:
+            if max(self.maximal_limit, self.minimal_limit) > self.max_proposals:
+                raise RuntimeError(f"minimal_limit / maximal_limit = {self.minimal_limit} / {self.maximal_limit} exceed "
+                                   f"max_proposals = {self.max_proposals} (per-frame capacity of the aggregation kernels)")
 
     def max_keep(self, num_anchors: int) -> int:
+        """Per-frame capacity of the kept-proposal list (pitch of sel_rows / sel_idx, CAFM kmax)."""
         if self.mode == "A":
             return min(self.top_k, self.pre_k, num_anchors)
+        cap = self.maximal_limit if self.maximal_limit else num_anchors
+        if self.minimal_limit:
+            cap = max(cap, min(self.minimal_limit, num_anchors))
+        return min(cap, self.max_proposals)
+
+    def cand_cap(self, num_anchors: int) -> int:
+        """Per-frame capacity of the candidate list K1 emits (input of the pre-NMS when there is one)."""
+        if self.mode == "A":
+            return min(self.pre_k, num_anchors)
+        if not self.use_pre_nms:
+            return self.max_keep(num_anchors)          # the candidates ARE the proposals
         cap = self.maximal_limit if self.maximal_limit else num_anchors
         if self.minimal_limit:
             cap = max(cap, min(self.minimal_limit, num_anchors))
@@ -34,13 +66,21 @@ class SelectionConfig:
 def select_and_gather(head: ops.HeadViews, feats, feat_dtype, feat_dim, cfg: SelectionConfig,
                       bank_dtype=torch.float16, status: Optional[torch.Tensor] = None, bank_rows: Optional[int] = None):
     """Runs K1 (+K2) + K3.  Returns the dict of ops.gather plus the candidate dict under 'cand'."""
+    A = head.anchors.num_anchors
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=ops._dev(head))
+    cand_cap = cfg.cand_cap(A)
+    if cand_cap > ops.NMS_MAX_CAP:
+        raise RuntimeError(f"mode B pre-NMS over {cand_cap} candidates per frame exceeds the NMS capacity of {ops.NMS_MAX_CAP}; "
+                           "set maximal_limit or use_pre_nms=False")
     cand = ops.select(head, cfg.mode, pre_k=cfg.pre_k, conf_thresh=cfg.conf_thresh,
-                      minimal_limit=cfg.minimal_limit, maximal_limit=cfg.maximal_limit)
+                      minimal_limit=cfg.minimal_limit, maximal_limit=cfg.maximal_limit, cand_cap=cand_cap, status=status)
     keep = keep_count = None
-    max_keep = cfg.max_keep(head.anchors.num_anchors)
+    max_keep = cfg.max_keep(A)
     if cfg.mode == "A" or cfg.use_pre_nms:
+        # mode A: the first top_k survivors ARE the semantics; mode B: max_keep is a buffer capacity, overflow is an error
         keep, keep_count, status = ops.nms(cand["box"], cand["score"], cand["cls"], cand["count"], cfg.nms_thresh,
-                                           max_keep=max_keep, status=status)
+                                           max_keep=max_keep, status=status, strict_keep=cfg.mode == "B")
     out = ops.gather(head, feats, feat_dtype, feat_dim, cand, keep, keep_count, max_keep=max_keep,
                      bank_dtype=bank_dtype, bank_rows=bank_rows)
     out["cand"] = cand

@@ -35,6 +35,26 @@ class StageConfig:
     dtype: torch.dtype = torch.float16  # tensor-core operand type (fp16 = the reference's eval dtype; bf16 also supported)
 
 
+def validate_config(cfg: StageConfig):
+    """Capacity limits of the kernels, checked when the stage is CONSTRUCTED (not at the first forward): a configuration
+    that cannot fit is rejected here with the limit it breaks."""
+    sel = cfg.selection
+    sel.validate()
+    kmax = sel.top_k if sel.mode == "A" else sel.max_proposals
+    if sel.mode == "B" and sel.maximal_limit:
+        kmax = max(sel.maximal_limit, sel.minimal_limit)
+    if kmax * cfg.num_classes > ops.NMS_MAX_CAP:
+        raise RuntimeError(
+            f"final per-class NMS: up to {kmax} proposals x {cfg.num_classes} classes = {kmax * cfg.num_classes} candidate rows per "
+            f"frame (post_process.py:36-46) exceed the NMS capacity of {ops.NMS_MAX_CAP}; lower max_proposals / maximal_limit "
+            f"to <= {ops.NMS_MAX_CAP // cfg.num_classes}")
+    if cfg.num_classes > 255:
+        raise RuntimeError("more than 255 classes are not supported (8-bit class ids in the selection kernels)")
+
+
+MAX_KEYS_PER_CLIP = 65536     # attention kernels: keys of one clip (csrc/attn.cu, 16-bit key index in row_meta)
+
+
 class StageWeights:
     """Device copies of the aggregation-stage parameters (reference state_dict key names)."""
 
@@ -90,6 +110,7 @@ class AggregationStage:
         if cfg.dim != 256 or cfg.heads != 4:
             raise RuntimeError("tscd_b200 kernels are specialised for TSCD-L (dim 256, 4 heads)")
         L.lib()  # fail loudly if the CUDA library is missing
+        validate_config(cfg)
         self.cfg = cfg
         self.w = StageWeights(state_dict, cfg, device)
         self.device = device
@@ -141,6 +162,9 @@ class AggregationStage:
         assert head.num_frames == B * F and 1 <= Lf <= F
         A = head.anchors.num_anchors
         kmax = cfg.selection.max_keep(A)
+        if _r128(F * kmax) > MAX_KEYS_PER_CLIP:
+            raise RuntimeError(f"{F} frames x {kmax} proposals per frame = {F * kmax} keys per clip exceed the attention kernels' "
+                               f"capacity of {MAX_KEYS_PER_CLIP}; lower SelectionConfig.max_proposals")
         status = torch.zeros(1, dtype=torch.int32, device=dev)
 
         # ---- K1-K3: selection + bank (operand arrays are read in 128-row TMA boxes: capacity padded) ------
@@ -249,7 +273,8 @@ class AggregationStage:
     def _unpack_host(pk, nlf):
         st = int(pk["status"][0])
         if st != 0:
-            raise RuntimeError(f"tscd_b200 stage reported error {st} (capacity exceeded)")
+            raise RuntimeError(f"tscd_b200 stage reported error {st} (capacity exceeded: a frame holds more proposals than "
+                               "SelectionConfig.max_proposals)")
         pk["gathered_bytes"].append(int(pk["sel_count"].sum()) * pk["_row_bytes"])   # zero-copy reads of the feature rows
         if "cand_count" in pk:
             pk["gathered_bytes"].append((int(pk["cand_count"].sum()) + int(pk["sel_count"].sum())) * pk["_logit_row_bytes"])
@@ -367,7 +392,7 @@ class AggregationStage:
         if before_cafm is not None:
             before_cafm(state)
         cafm16, cafm32, perm, te32 = self.run_cafm(lay, bank_reg, bank_edge, iou_reg32, iou_cls32, time_embedding, kmax,
-                                                   state, resume, status, want_debug=trace is not None)
+                                                   state, resume, status, want_debug=trace is not None, debug=trace)
         if after_cafm is not None:
             after_cafm(state)
         f32z = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731  (fully written before read)
@@ -422,7 +447,7 @@ class AggregationStage:
 
     # ------------------------------------------------------------------------------------------------------
     def run_cafm(self, lay: ops.AttnLayoutT, bank_reg, bank_edge, emb_reg32, emb_cls32, time_embedding, kmax: int,
-                 state: CAFMState, resume: torch.Tensor, status: torch.Tensor, want_debug=False):
+                 state: CAFMState, resume: torch.Tensor, status: torch.Tensor, want_debug=False, debug: Optional[dict] = None):
         """CAFM (AwarePositionRegMatcher.forward, tscd_matching.py:722-888) for all clips of the batch.
         emb_reg32 / emb_cls32 [loc_cap,1024] are the agg_iou outputs used for matching only."""
         w, dev, dt, D = self.w, self.device, self.cfg.dtype, self.cfg.dim
@@ -468,6 +493,8 @@ class AggregationStage:
                  sc_qin=None if fast else f32z(B, kmax, D), sc_q=None if fast else f32z(B, kmax, D),
                  sc_k=None if fast else f32z(B, kmax, D), ref_n=ref_n, lap_col=lap_col, lap_row=lap_row,
                  out16=cafm16, out32=cafm32, perm=perm, status=status)
+        if debug is not None:        # matching tables of every local frame (tests: LSAP exactness on the device's own costs)
+            debug.update(cafm_cost=cost_full, cafm_ref_n=ref_n, cafm_lap_col=lap_col, cafm_lap_row=lap_row)
         return cafm16, cafm32, perm, te32
 
     # ------------------------------------------------------------------------------------------------------
@@ -477,8 +504,8 @@ class AggregationStage:
         (post_process.py:12-13,85): per local frame a fresh Tensor[n,7] or None."""
         st = int(out["status"].item())
         if st != 0:
-            raise RuntimeError(f"tscd_b200 stage reported error {st} (capacity exceeded: per-frame NMS candidates > 4096 "
-                               "or proposals > configured maximum)")
+            raise RuntimeError(f"tscd_b200 stage reported error {st} (capacity exceeded: a frame holds more proposals than "
+                               "SelectionConfig.max_proposals -- raise it (<= 512) or set maximal_limit)")
         det_n, ori_n = out["det_count"].cpu().tolist(), out["ori_count"].cpu().tolist()
         det_c = out["det_cand"].cpu().tolist()
         result, result_ori = [], []
