@@ -30,9 +30,23 @@ def test_dropin_head_state_dict_and_config():
     cfg = stage_config_from_head(mine)
     assert cfg.selection.mode == "B" and cfg.selection.minimal_limit == 50 and cfg.selection.maximal_limit == 500
     assert cfg.selection.use_pre_nms is False and cfg.conf_sim_thresh == 0.99 and cfg.num_classes == 25
-    bad = cls(25, 1.0, in_channels=[256, 512, 1024], heads=4, **dict(mg.MORE_ARGS, agg_type="localagg"))
-    with pytest.raises(RuntimeError):
-        stage_config_from_head(bad)
+    with pytest.raises(RuntimeError):        # unsupported configurations are rejected when the head is BUILT
+        cls(25, 1.0, in_channels=[256, 512, 1024], heads=4, **dict(mg.MORE_ARGS, agg_type="localagg"))
+    with pytest.raises(RuntimeError, match="max_proposals"):
+        cls(25, 1.0, in_channels=[256, 512, 1024], heads=4, **dict(mg.MORE_ARGS, maximal_limit=2000))
+    # VID TSCD-L: no maximal_limit -> explicit per-frame capacity instead of the anchor count (exps/TSCD_VID/vid_tscd_large.py:39-42)
+    vid_args = {k: v for k, v in mg.MORE_ARGS.items() if k not in ("maximal_limit", "conf_sim_thresh")}
+    vid = cls(30, 1.0, in_channels=[256, 512, 1024], heads=4, **vid_args)
+    vcfg = stage_config_from_head(vid)
+    assert vcfg.selection.maximal_limit == 0 and vcfg.selection.max_proposals == 512 and vcfg.selection.max_keep(6804) == 512
+    # the weight snapshot is invalidated by a PARENT module's load_state_dict and by .half() / .to()
+    import torch
+    mine._b200_stage = object()
+    torch.nn.Sequential(mine).load_state_dict({"0." + k: v for k, v in ref.state_dict().items()})
+    assert mine._b200_stage is None
+    mine._b200_stage = object()
+    mine.half()
+    assert mine._b200_stage is None
 
 
 def test_exp_file_swaps_head(monkeypatch):

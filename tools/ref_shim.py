@@ -1,10 +1,9 @@
-"""Import shim for the read-only reference checkout (golden generation only).
+"""Import shim for the reference package (golden generation, reference arm of bench.py, reference-vs-drop-in tests).
 
-This module is *tooling*: it is used by ``tools/make_goldens.py`` in the build
-container, where ``/root/reference`` exists, to run the reference's own PyTorch
-code on seeded inputs.  Nothing under ``tscd_b200/``, ``tests/`` (at run time),
-``bench.py`` or ``__graft_entry__.py`` imports it, and it never copies reference
-source: it only arranges for ``import yolox`` to succeed.
+This module is *tooling*: it arranges for ``import yolox`` to succeed against either the read-only checkout
+(``/root/reference``, build container) or the pip-installed copy under ``baseline/_ref`` (git-ignored; made by
+``baseline/install_reference.sh``; travels to the GPU box).  It contains no reference source and nothing under
+``tscd_b200/`` imports it.
 
 Recipe:
   1. permissive stub packages for the optional deps the reference imports at
@@ -24,7 +23,22 @@ import math
 import sys
 import types
 
+import os
+
 REFERENCE_ROOT = "/root/reference"
+INSTALLED_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+# The reference hard-codes .to('cuda') in its attention modules (post_trans.py:694-695 and siblings).  True: redirect
+# those moves to the CPU (CPU runs, also on a box that HAS a GPU); False: leave them alone (CUDA eager runs).
+CPU_REDIRECT = True
+
+
+def reference_root():
+    """The checkout if present, else the installed copy; None if neither exists."""
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, "yolox")):
+        return REFERENCE_ROOT
+    if os.path.isdir(os.path.join(INSTALLED_ROOT, "yolox")):
+        return INSTALLED_ROOT
+    return None
 _STUB_ROOTS = {"thop", "matplotlib", "pycocotools", "timm", "seaborn"}
 
 
@@ -87,29 +101,36 @@ def _install_pywt_stub():
 _installed = False
 
 
-def install(reference_root=REFERENCE_ROOT):
-    """Make ``import yolox`` work against the read-only reference checkout."""
-    global _installed
+def install(root=None, cpu_redirect=None):
+    """Make ``import yolox`` work.  cpu_redirect: initial value of CPU_REDIRECT (default: True iff no GPU is visible)."""
+    global _installed, CPU_REDIRECT
+    import torch
+    if cpu_redirect is None:
+        cpu_redirect = not torch.cuda.is_available()
+    CPU_REDIRECT = bool(cpu_redirect)
     if _installed:
         return
-    import torch
     import torchvision
 
+    root = root or reference_root()
+    if root is None:
+        raise RuntimeError("reference package not found: neither /root/reference nor baseline/_ref exists "
+                           "(run baseline/install_reference.sh where /root/reference is available)")
     sys.meta_path.insert(0, _StubFinder())
     _install_pywt_stub()
-    sys.path.insert(0, reference_root)
+    sys.path.insert(0, root)
 
-    if not torch.cuda.is_available():
-        _orig_to = torch.Tensor.to
+    _orig_to = torch.Tensor.to
 
-        def _to(self, *args, **kwargs):
+    def _to(self, *args, **kwargs):
+        if CPU_REDIRECT:
             if args and isinstance(args[0], str) and args[0].startswith("cuda"):
                 args = ("cpu",) + tuple(args[1:])
             if isinstance(kwargs.get("device"), str) and kwargs["device"].startswith("cuda"):
                 kwargs["device"] = "cpu"
-            return _orig_to(self, *args, **kwargs)
+        return _orig_to(self, *args, **kwargs)
 
-        torch.Tensor.to = _to
+    torch.Tensor.to = _to
 
     from torchvision.ops import boxes as _tvb
 

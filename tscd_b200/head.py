@@ -12,7 +12,7 @@ import torch
 
 from . import ops
 from .selection import SelectionConfig
-from .stage import AggregationStage, CAFMState, StageConfig
+from .stage import AggregationStage, CAFMState, StageConfig, validate_config
 from .weights import timing_signal_1d  # noqa: F401  (re-exported for callers that build time embeddings)
 
 _CONV_PREFIXES = ("stems", "cls_convs", "reg_convs", "edge_enhance", "cls_preds", "reg_preds", "obj_preds")
@@ -26,11 +26,17 @@ def stage_config_from_head(head) -> StageConfig:
         raise RuntimeError("TSCDHeadB200 supports the TSCD configuration only: agg_type='mca', decouple_reg, reconf, ota_mode")
     if kw.get("local_mask", False) or head.use_mask or not head.ave:
         raise RuntimeError("TSCDHeadB200: local_mask / use_mask / ave=False are not implemented (not used by the TSCD exps)")
+    # max_proposals: per-frame capacity of the proposal list.  The reference's list is unbounded when no maximal_limit is set
+    # (VID TSCD-L, exps/TSCD_VID/vid_tscd_large.py:39-42); the kernels hold at most 512 (fewer when 512 x classes would exceed
+    # the final NMS's 16384 candidate rows).  Overflow raises at forward time; kwargs['max_proposals'] overrides the default.
+    cap = min(512, ops.NMS_MAX_CAP // max(1, head.num_classes))
     sel = SelectionConfig(mode="B", nms_thresh=head.nms_thresh, conf_thresh=0.001,
                           minimal_limit=kw.get("minimal_limit", 0), maximal_limit=kw.get("maximal_limit", 0),
-                          use_pre_nms=kw.get("use_pre_nms", True))
-    return StageConfig(num_classes=head.num_classes, selection=sel, dim=head.width, heads=4, sim_thresh=head.sim_thresh,
-                       conf_sim_thresh=kw.get("conf_sim_thresh", 0.99))
+                          use_pre_nms=kw.get("use_pre_nms", True), max_proposals=int(kw.get("max_proposals", cap)))
+    cfg = StageConfig(num_classes=head.num_classes, selection=sel, dim=head.width, heads=4, sim_thresh=head.sim_thresh,
+                      conf_sim_thresh=kw.get("conf_sim_thresh", 0.99))
+    validate_config(cfg)             # capacity problems surface when the head is built, not at the first forward
+    return cfg
 
 
 def make_head_class():
@@ -42,16 +48,31 @@ def make_head_class():
             super().__init__(*args, **kwargs)
             self._b200_stage = None
             self._b200_state = None
+            self._b200_key = None
+            stage_config_from_head(self)      # reject unsupported / over-capacity configurations at construction
+            # model.load_state_dict(ckpt) recurses through _load_from_state_dict and never calls a child's load_state_dict:
+            # the post-hook fires for this module either way
+            self.register_load_state_dict_post_hook(lambda module, incompatible: module._b200_invalidate())
+
+        def _b200_invalidate(self):
+            self._b200_stage = None           # weights changed / moved: rebuild the 16-bit device copies lazily
+            self._b200_state = None
+
+        def _apply(self, fn, *a, **k):        # .half() / .to() / .cuda() / .float()
+            self._b200_invalidate()
+            return super()._apply(fn, *a, **k)
 
         def _stage(self):
-            if self._b200_stage is None:
+            # the snapshot is keyed on the parameters' identity and in-place version counters, so optimiser steps or manual
+            # edits of the weights are picked up as well
+            params = [p for n, p in self.named_parameters() if not n.startswith(_CONV_PREFIXES)]
+            key = (params[0].device, tuple((p.data_ptr(), p._version) for p in params))
+            if self._b200_stage is None or self._b200_key != key:
                 sd = {k: v for k, v in self.state_dict().items() if not k.startswith(_CONV_PREFIXES)}
-                self._b200_stage = AggregationStage(stage_config_from_head(self), sd, device=next(self.parameters()).device)
+                self._b200_stage = AggregationStage(stage_config_from_head(self), sd, device=params[0].device)
+                self._b200_key = key
+                self._b200_state = None
             return self._b200_stage
-
-        def load_state_dict(self, *a, **k):
-            self._b200_stage = None          # weights changed: rebuild the 16-bit device copies lazily
-            return super().load_state_dict(*a, **k)
 
         def forward(self, xin, labels=None, imgs=None, time_embedding=None, nms_thresh=0.5, lframe=0, gframe=32,
                     resume=False):
@@ -83,6 +104,9 @@ def make_head_class():
             out = st.forward(head, feats, f_cls[0].dtype, time_embedding[:lframe].float(), 1, F, lframe,
                              state=self._b200_state, resume=res)
             result, result_ori = st.to_lists(out, 1, lframe)
+            if int(out["sel"]["sel_count"].sum().item()) == 0:
+                # no proposal in any frame: the reference returns its F-length pred_result twice (tscd_head.py:439-440)
+                return [None] * F, [None] * F
             dt = xin[0].dtype
             return ([None if r is None else r.to(dt) for r in result], [None if r is None else r.to(dt) for r in result_ori])
 
