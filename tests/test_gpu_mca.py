@@ -183,3 +183,39 @@ def test_mca_long_clip_vs_oracle():
     tc, to = oracle.mca_tscd_g2l_reg(sd16, "agg_iou.", xc.unsqueeze(0), xr.unsqueeze(0), score, counts, L)
     assert _rel(c32[:loc_total], tc) < 1e-2
     assert _rel(o32[:loc_total], to) < 1e-2
+
+
+def test_gen1_stage_vs_oracle_full_size():
+    """BASELINE configs[1] as the gen-1 (YOLOV) pipeline the north_star items (1)-(4) describe: 32 frames at 576x576, top-750 ->
+    NMS 0.75 -> 30 proposals/frame -> MSA self-attention over all N = 960 proposals -> linear_pred; selection exact, refined
+    class logits within 1e-2 (max-normalised) of the oracle's stage_gen1."""
+    from tscd_b200 import gen1, ops, selection
+    dtype = torch.float16
+    C, F, B = 25, 32, 2
+    hw = [(72, 72), (36, 36), (18, 18)]
+    sd = oracle.init_stage_weights(C, dim=256, seed=6, gen1=True)
+    sd16 = {k: v.to(dtype).float() if v.dim() == 2 else v for k, v in sd.items()}
+    st = gen1.Gen1Stage(C, selection.SelectionConfig(mode="A", pre_k=750, top_k=30, nms_thresh=0.75), sd)
+    heads, planes = [], []
+    for b in range(B):
+        h, f = oracle.synth_head_outputs(F, hw, C, dim=256, seed=300 + b, clustered=True)
+        heads.append(oracle.decode_outputs(h, hw, [8, 16, 32]))
+        planes.append([p.to(dtype).float() for p in f])
+    an = ops.AnchorSpec(hw)
+    head = ops.HeadViews.from_fused(torch.cat(heads, 0).cuda(), an, apply_sigmoid=False, apply_decode=False)
+    dev_feats = [torch.cat([planes[b][k] for b in range(B)], 0).to(dtype).cuda().contiguous() for k in range(2)]
+    views = (ops.view_rowmajor(dev_feats[0], an), ops.view_rowmajor(dev_feats[1], an), ops.view_rowmajor(dev_feats[1], an))
+    out = st.forward(head, views, dtype, B, F)
+    torch.cuda.synchronize()
+    assert int(out["status"].item()) == 0
+    cnt = out["sel"]["sel_count"].cpu().tolist()
+    off = out["sel"]["row_off"].cpu().tolist()
+    for b in range(B):
+        rows, idxs, logits = oracle.stage_gen1(sd16, heads[b], planes[b][0], planes[b][1], C, pre_k=750, top_k=30)
+        for f in range(F):
+            assert out["sel"]["sel_idx"][b * F + f, :cnt[b * F + f]].cpu().tolist() == idxs[f].tolist()
+        got = out["logits"][off[b * F]:off[(b + 1) * F], :C + 1].cpu()
+        assert got.shape == logits.shape
+        err = _rel(got, logits)
+        print(f"gen-1 stage clip {b}: N = {got.shape[0]}, refined logits max-normalised error {err:.2e}")
+        assert err < 1e-2

@@ -105,8 +105,8 @@ def install(root=None, cpu_redirect=None):
     """Make ``import yolox`` work.  cpu_redirect: initial value of CPU_REDIRECT (default: True iff no GPU is visible)."""
     global _installed, CPU_REDIRECT
     import torch
-    if cpu_redirect is None:
-        cpu_redirect = not torch.cuda.is_available()
+    if cpu_redirect is None:          # keep the current setting once installed; first install: redirect iff no GPU is visible
+        cpu_redirect = CPU_REDIRECT if _installed else not torch.cuda.is_available()
     CPU_REDIRECT = bool(cpu_redirect)
     if _installed:
         return

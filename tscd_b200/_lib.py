@@ -227,9 +227,9 @@ def check(rc, what):
 class timed:
     """Context manager: brackets one C-ABI call with CUDA events on the current stream when profiling is on."""
 
-    def __init__(self, name):
-        self.name = name
+    def __init__(self, name, tag=None):
         self.on = profile is not None and (profile["names"] is None or name in profile["names"])
+        self.name = name if tag is None else f"{name}:{tag}"
 
     def __enter__(self):
         if self.on:

@@ -50,7 +50,8 @@ def make_layout(sel_count: torch.Tensor, B: int, F: int, L: int, row_cap: int, l
 
 
 def mca_forward(lay: ops.AttnLayoutT, w: MCAWeights, bank_cls, bank_reg, bank_score, n_rows_dev, n_loc_dev,
-                need_reg=True, sim_thresh=0.75, conf_sim_thresh=0.99, debug=None, cls_out=(True, True), obj_out=(True, True)):
+                need_reg=True, sim_thresh=0.75, conf_sim_thresh=0.99, debug=None, cls_out=(True, True), obj_out=(True, True),
+                tag="mca"):
     """One MCA module.  bank_* [row_cap,256] 16-bit, bank_score [row_cap] fp32; n_rows_dev / n_loc_dev are int32
     device scalars (total bank rows / total local rows).  Returns (trans_cls [loc_cap,1024], trans_obj or None), each a
     (16-bit, fp32) pair; cls_out / obj_out = (want16, want32) select which copies the output GEMMs write."""
@@ -60,28 +61,30 @@ def mca_forward(lay: ops.AttnLayoutT, w: MCAWeights, bank_cls, bank_reg, bank_sc
     qkv_c = qkv_r = None
     if FUSED_QKV:
         bufs = ops.qkv_project_fused(lay, bank_cls, bank_reg, w.qkv_cls, w.qkv_reg, bank_score, n_rows_dev,
-                                     xori_cls=tmp_c[:, 256:], xori_reg=tmp_r[:, 256:])
+                                     xori_cls=tmp_c[:, 256:], xori_reg=tmp_r[:, 256:], tag=tag)
     else:
         qkv_c, _ = ops.linear(bank_cls, w.qkv_cls, m_dev=n_rows_dev)
         qkv_r, _ = ops.linear(bank_reg, w.qkv_reg, m_dev=n_rows_dev)
         bufs = ops.attn_prep(lay, qkv_c, qkv_r, bank_score, xori_cls=tmp_c[:, 256:], xori_reg=tmp_r[:, 256:])
     stats = torch.empty(lay.loc_cap, 16, dtype=torch.float32, device=dev)
-    ops.attn_pv(lay, bufs, tmp_c[:, :256], tmp_r[:, :256], stats, need_reg=need_reg)
+    ops.attn_pv(lay, bufs, tmp_c[:, :256], tmp_r[:, :256], stats, need_reg=need_reg, tag=tag)
     cat_c = torch.empty(lay.loc_cap, 768, dtype=dt, device=dev)      # [round2 @ V | linear(x)]
-    ops.linear(tmp_c, w.lin_w, w.lin_b, m_dev=n_loc_dev, out16=cat_c[:, 256:], want16=False)
+    ops.linear(tmp_c, w.lin_w, w.lin_b, m_dev=n_loc_dev, out16=cat_c[:, 256:], want16=False, tag=tag + ".mca_linear")
     # with a reg output to follow, the cls launch keeps its weights (sim_mask * exp(mean attention)) for the obj launch
     w_keep = torch.empty(lay.loc_cap, lay.nk_pitch, dtype=dt, device=dev) if need_reg else None
     ops.attn_round2(lay, bufs, bufs["vt_cls"], stats, cat_c[:, :256], use_obj_mask=False, sim_thresh=sim_thresh,
-                    conf_sim_thresh=conf_sim_thresh, w_out=w_keep)
-    trans_cls16, trans_cls32 = ops.linear(cat_c, w.out_w, w.out_b, m_dev=n_loc_dev, want16=cls_out[0], want32=cls_out[1])
+                    conf_sim_thresh=conf_sim_thresh, w_out=w_keep, tag=tag + ".cls")
+    trans_cls16, trans_cls32 = ops.linear(cat_c, w.out_w, w.out_b, m_dev=n_loc_dev, want16=cls_out[0], want32=cls_out[1],
+                                          tag=tag + ".linear")
     trans_obj16 = trans_obj32 = None
     cat_r = None
     if need_reg:
         cat_r = torch.empty(lay.loc_cap, 768, dtype=dt, device=dev)
-        ops.linear(tmp_r, w.linreg_w, w.linreg_b, m_dev=n_loc_dev, out16=cat_r[:, 256:], want16=False)
+        ops.linear(tmp_r, w.linreg_w, w.linreg_b, m_dev=n_loc_dev, out16=cat_r[:, 256:], want16=False, tag=tag + ".mca_linear_reg")
         ops.attn_round2(lay, bufs, bufs["vt_reg"], stats, cat_r[:, :256], use_obj_mask=True, sim_thresh=sim_thresh,
-                        conf_sim_thresh=conf_sim_thresh, w_in=w_keep)
-        trans_obj16, trans_obj32 = ops.linear(cat_r, w.obj_w, w.obj_b, m_dev=n_loc_dev, want16=obj_out[0], want32=obj_out[1])
+                        conf_sim_thresh=conf_sim_thresh, w_in=w_keep, tag=tag + ".obj")
+        trans_obj16, trans_obj32 = ops.linear(cat_r, w.obj_w, w.obj_b, m_dev=n_loc_dev, want16=obj_out[0], want32=obj_out[1],
+                                              tag=tag + ".linear_obj")
     if debug is not None:
         debug.update(qkv_c=qkv_c, qkv_r=qkv_r, bufs=bufs, tmp_c=tmp_c, tmp_r=tmp_r, stats=stats, cat_c=cat_c, cat_r=cat_r)
     return (trans_cls16, trans_cls32), (trans_obj16, trans_obj32)
@@ -105,15 +108,15 @@ def msa_forward(lay: ops.AttnLayoutT, w: MSAWeights, bank_cls, bank_reg, bank_sc
     `lay` must be a self-attention layout (L == F, lrow_off is row_off).  Returns (out16, out32) [row_cap, 1024]."""
     assert lay.self_attn and lay.L == lay.F
     dev, dt, cap = bank_cls.device, lay.dtype, lay.row_cap
-    qkv_c, _ = ops.linear(bank_cls, w.qkv_cls, m_dev=n_rows_dev)
-    qkv_r, _ = ops.linear(bank_reg, w.qkv_reg, m_dev=n_rows_dev)
+    qkv_c, _ = ops.linear(bank_cls, w.qkv_cls, m_dev=n_rows_dev, tag="msa.qkv_cls")
+    qkv_r, _ = ops.linear(bank_reg, w.qkv_reg, m_dev=n_rows_dev, tag="msa.qkv_reg")
     tmp_c = torch.empty(cap, 512, dtype=dt, device=dev)                  # [attn@v | v]
     tmp_r = torch.empty(cap, 512, dtype=dt, device=dev)
     bufs = ops.attn_prep(lay, qkv_c, qkv_r, bank_score, xori_cls=tmp_c[:, 256:], xori_reg=tmp_r[:, 256:])
     stats = torch.empty(cap, 16, dtype=torch.float32, device=dev)
-    ops.attn_pv(lay, bufs, tmp_c[:, :256], tmp_r[:, :256], stats, need_reg=False)
+    ops.attn_pv(lay, bufs, tmp_c[:, :256], tmp_r[:, :256], stats, need_reg=False, tag="msa")
     cat = torch.empty(cap, 1024, dtype=dt, device=dev)                   # [round2 @ tc | tc]
-    ops.linear(tmp_c, w.l1_w, w.l1_b, m_dev=n_rows_dev, out16=cat[:, 512:], want16=False)
+    ops.linear(tmp_c, w.l1_w, w.l1_b, m_dev=n_rows_dev, out16=cat[:, 512:], want16=False, tag="msa.linear1")
     tct = torch.empty(lay.B * 512, lay.nk_pitch, dtype=dt, device=dev)
     ops.call("tscd_transpose_clip", ops.L.TransposeArgs, lay=lay.to_c(), width=512, x=cat[:, 512:], ld_x=cat.stride(0), xt=tct)
     # round 2 aggregates linear1's output, 256 columns per launch; V^T rows of clip b start at b*512 (+256)
@@ -121,5 +124,5 @@ def msa_forward(lay: ops.AttnLayoutT, w: MSAWeights, bank_cls, bank_reg, bank_sc
         vt = tct.view(lay.B, 512, lay.nk_pitch)[:, half * 256:(half + 1) * 256]
         vt = vt.contiguous().view(lay.B * 256, lay.nk_pitch)
         ops.attn_round2(lay, bufs, vt, stats, cat[:, half * 256:(half + 1) * 256], use_obj_mask=False,
-                        sim_thresh=sim_thresh, conf_sim_thresh=conf_sim_thresh)
-    return ops.linear(cat, w.l2_w, w.l2_b, m_dev=n_rows_dev, want16=True, want32=True)
+                        sim_thresh=sim_thresh, conf_sim_thresh=conf_sim_thresh, tag=f"msa.half{half}")
+    return ops.linear(cat, w.l2_w, w.l2_b, m_dev=n_rows_dev, want16=True, want32=True, tag="msa.linear2")

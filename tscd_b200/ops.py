@@ -148,7 +148,7 @@ NMS_MAX_CAP = 16384       # kNmsLargeCap
 
 
 def nms(box: torch.Tensor, score: torch.Tensor, cls: torch.Tensor, count: torch.Tensor, iou_thresh: float,
-        max_keep: Optional[int] = None, status: Optional[torch.Tensor] = None, strict_keep: bool = False):
+        max_keep: Optional[int] = None, status: Optional[torch.Tensor] = None, strict_keep: bool = False, tag=None):
     """K2.  box [F,cap,4] f32, score [F,cap] f32, cls [F,cap] i32, count [F] i32 -> (keep [F,max_keep], keep_count [F]).
     strict_keep: more than max_keep survivors in a frame is a capacity error (status) instead of a truncation."""
     Fn, cap = score.shape
@@ -169,7 +169,7 @@ def nms(box: torch.Tensor, score: torch.Tensor, cls: torch.Tensor, count: torch.
         a.ws_bytes = L.lib().tscd_nms_workspace_bytes(Fn, cap)
         ws = torch.empty(a.ws_bytes, dtype=torch.uint8, device=score.device)
         a.ws = _p(ws)
-    with L.timed("tscd_nms"):
+    with L.timed("tscd_nms", tag):
         L.check(L.lib().tscd_nms(C.byref(a), _stream()), "tscd_nms_large" if ws is not None else "tscd_nms")
     if ws is not None and not torch.cuda.is_current_stream_capturing():
         ws.record_stream(torch.cuda.current_stream())
@@ -213,7 +213,7 @@ def gather(head: HeadViews, feats, feat_dtype: torch.dtype, feat_dim: int, cand,
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, m_dev: Optional[torch.Tensor] = None,
-           out16: Optional[torch.Tensor] = None, out32: Optional[torch.Tensor] = None, want16=True, want32=False):
+           out16: Optional[torch.Tensor] = None, out32: Optional[torch.Tensor] = None, want16=True, want32=False, tag=None):
     """y = x @ w.T + bias on the tcgen05 GEMM.  x [M,K] (row pitch may exceed K), w [N,K]; both fp16 or bf16.
     Outputs may be column slices of wider buffers (stride(0) is the pitch)."""
     assert x.dtype == w.dtype and x.dtype in (torch.float16, torch.bfloat16)
@@ -234,8 +234,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous()
     if L.profile is not None:
-        L.profile.setdefault("linear", []).append((M, N, K, m_dev))
-    with L.timed("tscd_linear"):
+        L.profile.setdefault("linear", []).append((M, N, K, m_dev, tag, out16 is not None, out32 is not None))
+    with L.timed("tscd_linear", tag):
         L.check(L.lib().tscd_linear(C.byref(a), _stream()), "tscd_linear")
     return out16, out32
 
@@ -289,7 +289,7 @@ def attn_prep(lay: AttnLayoutT, qkv_cls, qkv_reg, key_score, xori_cls=None, xori
 
 
 def qkv_project_fused(lay: AttnLayoutT, bank_cls, bank_reg, w_cls, w_reg, key_score, n_rows_dev, xori_cls=None, xori_reg=None,
-                      scale=25.0):
+                      scale=25.0, tag=None):
     """tscd_attn_rowmeta + 2 x tscd_qkv_project: the q|k|v projections of both branches with the normalise / scale /
     transpose step of tscd_attn_prep fused into the GEMM epilogue.  Returns the same operand dict as attn_prep."""
     dev, dt = bank_cls.device, lay.dtype
@@ -304,24 +304,25 @@ def qkv_project_fused(lay: AttnLayoutT, bank_cls, bank_reg, w_cls, w_reg, key_sc
          vt_cls=bufs["vt_cls"], vt_reg=bufs["vt_reg"])
     for br, bank, w, ks, xo in (("cls", bank_cls, w_cls, key_score, xori_cls), ("reg", bank_reg, w_reg, None, xori_reg)):
         assert bank.shape[0] >= lay.row_cap and bank.stride(1) == 1 and w.shape == (768, 256) and w.is_contiguous()
-        call("tscd_qkv_project", L.QkvProjectArgs, lay=lay.to_c(), rows=lay.row_cap, m_dev=n_rows_dev, x=bank, ldx=bank.stride(0),
+        call("tscd_qkv_project", L.QkvProjectArgs, tag=None if tag is None else f"{tag}.{br}", lay=lay.to_c(), rows=lay.row_cap, m_dev=n_rows_dev, x=bank, ldx=bank.stride(0),
              w=w, row_meta=bufs["row_meta"], key_score=ks, scale=scale, qn=bufs["qn_" + br], kn=bufs["kn_" + br],
              vn=bufs["vn_" + br], vt=bufs["vt_" + br], xori=xo, ld_xori=0 if xo is None else xo.stride(0))
     return bufs
 
 
-def attn_pv(lay: AttnLayoutT, bufs, x_cls, x_reg, stats, need_reg=True):
+def attn_pv(lay: AttnLayoutT, bufs, x_cls, x_reg, stats, need_reg=True, tag=None):
     a = L.AttnPvArgs()
     a.lay = lay.to_c()
     for n in ("qn_cls", "kn_cls", "qn_reg", "kn_reg", "vt_cls", "vt_reg", "row_frame"):
         setattr(a, n, _p(bufs[n]))
     a.need_reg = int(need_reg)
     a.x_cls, a.x_reg, a.ld_x, a.stats = _p(x_cls), _p(x_reg), x_cls.stride(0), _p(stats)
-    with L.timed("tscd_attn_pv"):
+    with L.timed("tscd_attn_pv", tag):
         L.check(L.lib().tscd_attn_pv(C.byref(a), _stream()), "tscd_attn_pv")
 
 
-def attn_round2(lay: AttnLayoutT, bufs, vt, stats, out, use_obj_mask, sim_thresh=0.75, conf_sim_thresh=0.99, w_out=None, w_in=None):
+def attn_round2(lay: AttnLayoutT, bufs, vt, stats, out, use_obj_mask, sim_thresh=0.75, conf_sim_thresh=0.99, w_out=None, w_in=None,
+                tag=None):
     a = L.AttnRound2Args()
     a.lay = lay.to_c()
     for n in ("qn_cls", "kn_cls", "qn_reg", "kn_reg", "vn_cls", "vn_reg", "row_frame"):
@@ -332,12 +333,12 @@ def attn_round2(lay: AttnLayoutT, bufs, vt, stats, out, use_obj_mask, sim_thresh
     a.w_out, a.w_in = _p(w_out), _p(w_in)
     for t in (w_out, w_in):
         assert t is None or (t.dtype == lay.dtype and t.stride(0) == lay.nk_pitch and t.stride(1) == 1)
-    with L.timed("tscd_attn_round2"):
+    with L.timed("tscd_attn_round2", tag):
         L.check(L.lib().tscd_attn_round2(C.byref(a), _stream()), "tscd_attn_round2")
 
 
 # ----------------------------------------------------------------------------------------------- generic call helper
-def call(name: str, struct_cls, **kw):
+def call(name: str, struct_cls, tag=None, **kw):
     """Fill a ctypes argument struct from keyword arguments (tensors -> data_ptr) and call the C-ABI entry point."""
     a = struct_cls()
     for k, v in kw.items():
@@ -350,5 +351,5 @@ def call(name: str, struct_cls, **kw):
         setattr(a, k, v)
     missing = {f[0] for f in struct_cls._fields_} - set(kw)
     assert not missing, f"{name}: missing {missing}"
-    with L.timed(name):
+    with L.timed(name, tag):
         L.check(getattr(L.lib(), name)(C.byref(a), _stream()), name)

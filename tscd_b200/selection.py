@@ -80,7 +80,7 @@ def select_and_gather(head: ops.HeadViews, feats, feat_dtype, feat_dim, cfg: Sel
     if cfg.mode == "A" or cfg.use_pre_nms:
         # mode A: the first top_k survivors ARE the semantics; mode B: max_keep is a buffer capacity, overflow is an error
         keep, keep_count, status = ops.nms(cand["box"], cand["score"], cand["cls"], cand["count"], cfg.nms_thresh,
-                                           max_keep=max_keep, status=status, strict_keep=cfg.mode == "B")
+                                           max_keep=max_keep, status=status, strict_keep=cfg.mode == "B", tag="pre")
     out = ops.gather(head, feats, feat_dtype, feat_dim, cand, keep, keep_count, max_keep=max_keep,
                      bank_dtype=bank_dtype, bank_rows=bank_rows)
     out["cand"] = cand

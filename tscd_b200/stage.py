@@ -118,6 +118,7 @@ class AggregationStage:
         self._part_streams = []
         self._default_state = {}
         self._zero_resume = {}
+        self.serialize = False     # True: run the classification branch on the launching stream (per-kernel profiling passes)
 
     def _side_stream(self):
         """Side stream of the classification branch, one per launching stream (concurrent sub-batches must not share it)."""
@@ -357,10 +358,10 @@ class AggregationStage:
         #      + cls_pred on a side stream that starts when the recurrence does: the chain occupies one SM per clip,
         #      the independent classification branch fills the rest of the GPU --------------------------------
         main = torch.cuda.current_stream()
-        side = self._side_stream()
+        side = main if self.serialize else self._side_stream()
         (iou_cls16, iou_cls32), (iou_reg16, iou_reg32) = aggregate.mca_forward(
             lay, w.agg_iou, bank_cls, bank_reg, bank_score, n_rows_dev, n_loc_dev, need_reg=True,
-            sim_thresh=cfg.sim_thresh, conf_sim_thresh=cfg.conf_sim_thresh, cls_out=(False, True))   # cls: matching only (fp32)
+            sim_thresh=cfg.sim_thresh, conf_sim_thresh=cfg.conf_sim_thresh, cls_out=(False, True), tag="agg_iou")   # cls: matching only (fp32)
         ev_fork = torch.cuda.Event()
         ev_fork.record(main)
         with torch.cuda.stream(side):
@@ -368,8 +369,8 @@ class AggregationStage:
             (agg_cls16, agg_cls32), _ = aggregate.mca_forward(lay, w.agg, bank_cls, bank_reg, bank_score, n_rows_dev,
                                                               n_loc_dev, need_reg=False, sim_thresh=cfg.sim_thresh,
                                                               conf_sim_thresh=cfg.conf_sim_thresh,
-                                                              cls_out=(True, trace is not None))
-            _, cls_logits = ops.linear(agg_cls16, w.cls_w, w.cls_b, m_dev=n_loc_dev, want16=False, want32=True)
+                                                              cls_out=(True, trace is not None), tag="agg")
+            _, cls_logits = ops.linear(agg_cls16, w.cls_w, w.cls_b, m_dev=n_loc_dev, want16=False, want32=True, tag="cls_pred")
             ev_join = torch.cuda.Event()
             ev_join.record(side)
         if not torch.cuda.is_current_stream_capturing():
@@ -398,11 +399,11 @@ class AggregationStage:
         f32z = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731  (fully written before read)
 
         # ---- fc_reg_matcher, TaskAligned, prediction heads ---------------------------------------------
-        matched16, matched32 = ops.linear(cafm16, w.fc_w, w.fc_b, m_dev=n_loc_dev, want16=True, want32=trace is not None)
-        _, reg_deltas = ops.linear(matched16, w.reg_w, w.reg_b, m_dev=n_loc_dev, want16=False, want32=True)
+        matched16, matched32 = ops.linear(cafm16, w.fc_w, w.fc_b, m_dev=n_loc_dev, want16=True, want32=trace is not None, tag="fc_reg_matcher")
+        _, reg_deltas = ops.linear(matched16, w.reg_w, w.reg_b, m_dev=n_loc_dev, want16=False, want32=True, tag="reg_pred")
         fast_ta = kmax <= 32          # 16-bit q/k/v + mma.sync attention (csrc/tail.cu frame_attention16_kernel)
-        ta_q16, ta_q = ops.linear(iou_reg16, w.ta_wq, m_dev=n_loc_dev, want16=fast_ta, want32=not fast_ta)
-        ta_kv16, ta_kv = ops.linear(matched16, w.ta_wkv, m_dev=n_loc_dev, want16=fast_ta, want32=not fast_ta)
+        ta_q16, ta_q = ops.linear(iou_reg16, w.ta_wq, m_dev=n_loc_dev, want16=fast_ta, want32=not fast_ta, tag="ta_q")
+        ta_kv16, ta_kv = ops.linear(matched16, w.ta_wkv, m_dev=n_loc_dev, want16=fast_ta, want32=not fast_ta, tag="ta_kv")
         tq, tkv = (ta_q16, ta_kv16) if fast_ta else (ta_q, ta_kv)
         att = f32z(loc_cap, 4 * D)
         ops.call("tscd_frame_attention", L.FrameAttentionArgs, num_frames=B * Lf, heads=8, head_dim=(4 * D) // 8,
@@ -433,7 +434,8 @@ class AggregationStage:
                  o_box=o["box"], o_score=o["score"], o_cls=o["cls"], o_obj=o["obj"], o_cscore=o["cscore"], o_count=o["count"])
         out = {}
         for name, c, cap in (("det", r, rcap), ("ori", o, ocap)):
-            keep, kc, _ = ops.nms(c["box"], c["score"], c["cls"], c["count"], cfg.final_nms_thresh, max_keep=cap, status=status)
+            keep, kc, _ = ops.nms(c["box"], c["score"], c["cls"], c["count"], cfg.final_nms_thresh, max_keep=cap, status=status,
+                                  tag="final_" + name)
             rows = f32z(nlf, cap, 7)
             ops.call("tscd_final_rows", L.FinalRowsArgs, num_frames=nlf, cand_cap=cap, keep_cap=cap, box=c["box"],
                      obj=c["obj"], cscore=c["cscore"], cls=c["cls"], keep=keep, keep_count=kc, rows=rows)
@@ -456,7 +458,7 @@ class AggregationStage:
         te16 = time_embedding.to(device=dev, dtype=dt).contiguous()
         assert te16.shape == (B * Lf, 256)
         assert state.slots == B and state.kmax == kmax
-        _, te32 = ops.linear(te16, w.ape_w, w.ape_b, want16=False, want32=True)
+        _, te32 = ops.linear(te16, w.ape_w, w.ape_b, want16=False, want32=True, tag="time_emb")
         f32z = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731  (fully written before read)
         fast = kmax <= 32            # every frame's working set fits the shared-memory / mma.sync chain (csrc/cafm.cu)
         feat = edge = kin = None
@@ -469,8 +471,8 @@ class AggregationStage:
                  lrow_off=lay.lrow_off, bank_reg=bank_reg, bank_edge=bank_edge, time_emb=te32, se_w1=w.se_w1,
                  se_w2=w.se_w2, emb_reg=emb_reg32, emb_cls=emb_cls32, feat=feat, edge=edge, feat16=feat16,
                  kin16=kin16, kin=kin, norm_reg=norm_reg, norm_cls=norm_cls)
-        kproj16, kproj = ops.linear(kin16, w.cafm_wk, m_dev=n_loc_dev, want16=fast, want32=not fast)
-        vproj16, vproj = ops.linear(feat16, w.cafm_wv, m_dev=n_loc_dev, want16=fast, want32=not fast)
+        kproj16, kproj = ops.linear(kin16, w.cafm_wk, m_dev=n_loc_dev, want16=fast, want32=not fast, tag="cafm_k")
+        vproj16, vproj = ops.linear(feat16, w.cafm_wv, m_dev=n_loc_dev, want16=fast, want32=not fast, tag="cafm_v")
         cafm16 = torch.empty(loc_cap, D, dtype=dt, device=dev)
         cafm32 = f32z(loc_cap, D) if want_debug else None
         perm = torch.empty(loc_cap, dtype=torch.int32, device=dev) if want_debug else None

@@ -6,7 +6,8 @@ import math
 import torch
 
 
-def random_state_dict(num_classes: int, dim: int = 256, seed: int = 2024):
+def random_state_dict(num_classes: int, dim: int = 256, seed: int = 2024, gen1: bool = False):
+    """gen1=True: the gen-1 (YOLOV) MSA head instead -- trans.msa.qkv_*, trans.linear1/2, linear_pred (yolovp_msa.py)."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
 
@@ -21,6 +22,11 @@ def random_state_dict(num_classes: int, dim: int = 256, seed: int = 2024):
         sd[name + ".bias"] = torch.zeros(n)
 
     D = dim
+    if gen1:
+        lin("trans.msa.qkv_cls", 3 * D, D, False); lin("trans.msa.qkv_reg", 3 * D, D, False)
+        lin("trans.linear1", 2 * D, 2 * D); lin("trans.linear2", 4 * D, 4 * D)
+        lin("linear_pred", num_classes + 1, 4 * D)
+        return sd
     for m in ("agg.", "agg_iou."):
         lin(m + "mca.q_cls_local", D, D, False); lin(m + "mca.kv_cls", 2 * D, D, False)
         lin(m + "mca.q_reg_local", D, D, False); lin(m + "mca.kv_reg", 2 * D, D, False)
