@@ -499,6 +499,45 @@ typedef struct {
 } tscd_final_rows_args;
 int tscd_final_rows(const tscd_final_rows_args* args, void* stream);
 
+/* ---- long-clip mode: exchange of the global-frame bank rows between ranks ----------------------
+ * One clip sharded by frame: every rank runs K1-K3 on its own frames [n_local_frames local | n_global_frames global], then the
+ * ranks all-gather ONE packed buffer each (ncclAllGather, issued by the host) and every rank builds the virtual clip
+ * [own local frames | all ranks' global frames, rank-major] whose local rows it attends from.  Replaces nothing in the
+ * reference (single-GPU only); it is the exchange step BASELINE.json configs[3] names.
+ *   tscd_bank_pack_bytes  size of one rank's buffer: 1 KB header (per-frame counts, up to 256 global frames per rank) + n_global_frames * kmax rows of
+ *                         (cls 256 | reg 256 16-bit values | score fp32 + pad) = 1040 bytes;
+ *   tscd_bank_pack        bank rows of the rank's global frames -> send buffer (frames padded to kmax rows: static layout);
+ *   tscd_bank_unpack      gathered buffers [world, rank_bytes] + own bank -> per-frame counts, prefix offsets and the compacted
+ *                         16-bit bank of the virtual clip (two kernels, no host sync). */
+typedef struct {
+    int32_t n_local_frames, n_global_frames, kmax;
+    int32_t dtype;               /* TSCD_F16 / TSCD_BF16 bank element type */
+    const int32_t* sel_count;    /* [n_local_frames + n_global_frames] */
+    const int32_t* row_off;      /* [.. + 1] */
+    const void* bank_cls;        /* [rows, 256] */
+    const void* bank_reg;
+    const float* bank_score;     /* [rows] */
+    void* send;                  /* [tscd_bank_pack_bytes] */
+} tscd_bank_pack_args;
+int64_t tscd_bank_pack_bytes(int32_t n_global_frames, int32_t kmax);
+int tscd_bank_pack(const tscd_bank_pack_args* args, void* stream);
+
+typedef struct {
+    int32_t world, n_local_frames, n_global_frames, kmax;
+    int32_t dtype;
+    int64_t rank_bytes;          /* pitch of one rank's buffer inside recv */
+    const void* recv;            /* [world, rank_bytes] all-gathered buffers */
+    const int32_t* sel_count;    /* own selection (local frames are read) */
+    const int32_t* row_off;
+    const void* bank_cls; const void* bank_reg; const void* bank_edge; const float* bank_score;
+    int32_t* v_count;            /* out [n_local_frames + world * n_global_frames] */
+    int32_t* v_row_off;          /* out [.. + 1] */
+    void* v_bank_cls; void* v_bank_reg;   /* out [rows_cap, 256] */
+    void* v_bank_edge;           /* out, local rows only (may be NULL) */
+    float* v_bank_score;         /* out [rows_cap] */
+} tscd_bank_unpack_args;
+int tscd_bank_unpack(const tscd_bank_unpack_args* args, void* stream);
+
 /* Debug aid: cycles block 0 of the last tscd_cafm_chain launches spent per phase
  * (0 assignment re-index, 1 query input, 2 q projection, 3 normalise, 4 attention, 5 norms/state, 6 state carry). */
 int tscd_debug_chain_clocks(long long* host_out8, int reset);

@@ -32,7 +32,10 @@ def test_struct_sizes_match_header():
              ("tscd_attn_pv_args", _lib.AttnPvArgs), ("tscd_attn_round2_args", _lib.AttnRound2Args),
              ("tscd_transpose_args", _lib.TransposeArgs), ("tscd_cafm_prep_args", _lib.CafmPrepArgs), ("tscd_cafm_chain_args", _lib.CafmChainArgs), ("tscd_cafm_cost_args", _lib.CafmCostArgs), ("tscd_cafm_lap_args", _lib.CafmLapArgs),
              ("tscd_frame_attention_args", _lib.FrameAttentionArgs), ("tscd_residual_ln2_args", _lib.ResidualLn2Args),
-             ("tscd_final_expand_args", _lib.FinalExpandArgs), ("tscd_final_rows_args", _lib.FinalRowsArgs)]
+             ("tscd_final_expand_args", _lib.FinalExpandArgs), ("tscd_final_rows_args", _lib.FinalRowsArgs),
+             ("tscd_bank_pack_args", _lib.BankPackArgs), ("tscd_bank_unpack_args", _lib.BankUnpackArgs),
+             ("tscd_qkv_project_args", _lib.QkvProjectArgs), ("tscd_attn_rowmeta_args", _lib.AttnRowmetaArgs),
+             ("tscd_local_offsets_args", _lib.LocalOffsetsArgs)]
     body = "".join(f'printf("%zu\\n", sizeof({c}));' for c, _ in pairs)
     src = '#include <stdio.h>\n#include "tscd_b200.h"\nint main(){' + body + 'return 0;}'
     with tempfile.TemporaryDirectory() as d:

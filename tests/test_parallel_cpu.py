@@ -1,5 +1,5 @@
-"""CPU tests (gloo, world_size 2) of the multi-GPU host logic: clip sharding, the ragged all-gather of the global
-bank for the frame-sharded long clip, and the CAFM state hand-over between ranks."""
+"""CPU tests (gloo, world_size 2) of the multi-GPU host logic: clip sharding, frame ownership of the long clip, the single
+all-gather of the packed bank buffers and the one-message CAFM state hand-over between ranks."""
 import os
 import sys
 
@@ -19,25 +19,11 @@ def test_shard_clips_contiguous_and_complete():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
 
 
-def _make_rank_sel(rank, Lr, Gr, kmax, D=8):
-    g = torch.Generator().manual_seed(100 + rank)
-    counts = torch.randint(1, kmax + 1, (Lr + Gr,), generator=g).tolist()
-    n = sum(counts)
-    cap = ((Lr + Gr) * kmax + 127) // 128 * 128 + 128
-    sel = {}
-    for k in ("bank_cls", "bank_reg", "bank_edge"):
-        t = torch.zeros(cap, D)
-        t[:n] = torch.randn(n, D, generator=g) + 10 * rank
-        sel[k] = t
-    sc = torch.zeros(cap)
-    sc[:n] = torch.rand(n, generator=g)
-    sel["bank_score"] = sc
-    sel["sel_count"] = torch.tensor(counts, dtype=torch.int32)
-    ro = torch.zeros(Lr + Gr + 1, dtype=torch.int32)
-    ro[1:] = torch.cumsum(sel["sel_count"], 0)
-    sel["row_off"] = ro
-    sel["sel_rows"] = torch.zeros(Lr + Gr, kmax, 9)
-    return sel, counts
+class _FlatState:
+    """Stand-in with CAFMState's hand-over interface (one flat buffer) for the CPU test."""
+
+    def __init__(self, fill):
+        self.flat = torch.full((1000,), float(fill))
 
 
 def _worker(rank, world, port, ret):
@@ -46,35 +32,26 @@ def _worker(rank, world, port, ret):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from tscd_b200 import parallel
-        Lr, Gr, kmax = 2, 3, 5
-        sel, counts = _make_rank_sel(rank, Lr, Gr, kmax)
-        virt, F_virt = parallel.exchange_global_bank(sel, Lr, Gr, kmax)
-        # expected virtual clip, rebuilt from every rank's deterministic data
-        all_sel = [_make_rank_sel(r, Lr, Gr, kmax) for r in range(world)]
-        exp_counts = counts[:Lr] + [c for (_, cs) in all_sel for c in cs[Lr:]]
-        assert F_virt == Lr + world * Gr
-        assert virt["sel_count"].tolist() == exp_counts
-        assert virt["row_off"].tolist() == [0] + torch.cumsum(torch.tensor(exp_counts), 0).tolist()
-        n_loc = sum(counts[:Lr])
-        for k in ("bank_cls", "bank_reg", "bank_edge", "bank_score"):
-            parts = [sel[k][:n_loc]]
-            for (s_r, cs) in all_sel:
-                lo = sum(cs[:Lr])
-                parts.append(s_r[k][lo:lo + sum(cs[Lr:])])
-            exp = torch.cat(parts)
-            assert torch.equal(virt[k][:exp.shape[0]], exp), k
-        # CAFM state hand-over rank 0 -> rank 1
-        class St:
-            pass
-        st = St()
-        for i, f in enumerate(parallel._STATE_FIELDS):
-            setattr(st, f, torch.full((3, 4), float(i + 1) if rank == 0 else 0.0) if f != "n" else
-                    torch.tensor([7 if rank == 0 else 0], dtype=torch.int32))
+        # ONE all-gather of a packed byte buffer per rank (the long-clip exchange; the CUDA pack / unpack kernels around it are
+        # covered by tests/test_gpu_long_clip.py)
+        send = torch.full((4096,), rank + 1, dtype=torch.uint8)
+        recv = parallel.all_gather_bytes(send)
+        assert recv.shape == (world * 4096,)
+        for r in range(world):
+            assert bool((recv[r * 4096:(r + 1) * 4096] == r + 1).all())
+        # frame ownership: consecutive blocks, complete, in rank order
+        loc, glob = [], []
+        for r in range(world):
+            l_, g_ = parallel.frame_plan(8, 24, r, world)
+            loc += l_; glob += g_
+        assert loc == list(range(8)) and glob == list(range(8, 32))
+        # CAFM state hand-over rank 0 -> rank 1: one message
+        st = _FlatState(3.0 if rank == 0 else 0.0)
         if rank == 0:
             parallel.send_state(st, 1)
         else:
             parallel.recv_state(st, 0)
-            assert int(st.n.item()) == 7 and float(st.time[0, 0]) == float(len(parallel._STATE_FIELDS))
+            assert bool((st.flat == 3.0).all())
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()
@@ -87,3 +64,15 @@ def test_long_clip_exchange_world2_gloo():
     port = 29500 + os.getpid() % 2000
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def test_cafm_state_is_one_flat_buffer():
+    """Every field of CAFMState is a view of `flat` (so the rank-to-rank hand-over is a single message)."""
+    from tscd_b200.stage import CAFMState
+    st = CAFMState(2, 5, 8, device="cpu")
+    st.flat.fill_(1.0)
+    for f in ("out", "edge", "reg", "cls", "nreg", "ncls", "time"):
+        t = getattr(st, f)
+        assert bool((t == 1.0).all()) and t.untyped_storage().data_ptr() == st.flat.untyped_storage().data_ptr()
+    st.n.fill_(7)
+    assert st.flat[:2].view(torch.int32).tolist() == [7, 7] and st.out.shape == (2, 5, 8) and st.reg.shape == (2, 5, 32)

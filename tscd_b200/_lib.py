@@ -154,6 +154,18 @@ class FinalRowsArgs(C.Structure):
     _fields_ = _fields("num_frames:i cand_cap:i keep_cap:i box:p obj:p cscore:p cls:p keep:p keep_count:p rows:p")
 
 
+class BankPackArgs(C.Structure):
+    _fields_ = _fields("n_local_frames:i n_global_frames:i kmax:i dtype:i sel_count:p row_off:p bank_cls:p bank_reg:p bank_score:p send:p")
+
+
+class BankUnpackArgs(C.Structure):
+    _fields_ = [("world", C.c_int32), ("n_local_frames", C.c_int32), ("n_global_frames", C.c_int32), ("kmax", C.c_int32),
+                ("dtype", C.c_int32), ("rank_bytes", C.c_int64), ("recv", C.c_void_p), ("sel_count", C.c_void_p),
+                ("row_off", C.c_void_p), ("bank_cls", C.c_void_p), ("bank_reg", C.c_void_p), ("bank_edge", C.c_void_p),
+                ("bank_score", C.c_void_p), ("v_count", C.c_void_p), ("v_row_off", C.c_void_p), ("v_bank_cls", C.c_void_p),
+                ("v_bank_reg", C.c_void_p), ("v_bank_edge", C.c_void_p), ("v_bank_score", C.c_void_p)]
+
+
 _lib = None
 
 # every symbol include/tscd_b200.h declares: (name, restype, argtypes)
@@ -182,6 +194,9 @@ SYMBOLS = [
     ("tscd_residual_ln2", C.c_int, [C.POINTER(ResidualLn2Args), C.c_void_p]),
     ("tscd_final_expand", C.c_int, [C.POINTER(FinalExpandArgs), C.c_void_p]),
     ("tscd_final_rows", C.c_int, [C.POINTER(FinalRowsArgs), C.c_void_p]),
+    ("tscd_bank_pack_bytes", C.c_int64, [C.c_int32, C.c_int32]),
+    ("tscd_bank_pack", C.c_int, [C.POINTER(BankPackArgs), C.c_void_p]),
+    ("tscd_bank_unpack", C.c_int, [C.POINTER(BankUnpackArgs), C.c_void_p]),
 ]
 
 
@@ -204,7 +219,7 @@ def lib():
 
 # kernels launched per C-ABI call (for the bench's `gpu_launches` claim)
 _DEBUG_SYNC = os.environ.get("TSCD_DEBUG_SYNC", "0") == "1"
-KERNELS_PER_CALL = {"tscd_gather": 2, "tscd_nms_large": 3}
+KERNELS_PER_CALL = {"tscd_gather": 2, "tscd_nms_large": 3, "tscd_bank_unpack": 2}
 launch_count = 0
 # optional per-entry-point CUDA-event timing: {"names": set or None (= all), "events": {name: [(start, end), ...]}}
 profile = None

@@ -2,19 +2,24 @@
 
 * clip-parallel (configs 3, 5): clips are independent units -> `shard_clips` gives every rank a contiguous block; there
   is NO data-path collective (bench.py --gpus N).
-* one long clip sharded by frame (config 4): every rank selects / gathers ITS frames (K1-K3 are per frame), then the
-  packed bank rows of the GLOBAL frames are exchanged with ONE all-gather (counts first: the rows are ragged) so that
-  each rank holds [its own local rows | every global row].  Queries stay sharded, so the attention needs no reduction.
-  The CAFM recurrence is a chain over consecutive local frames: rank r receives the CAFM memory from rank r-1 before its
-  chain and sends it on afterwards (two tiny point-to-point messages per rank instead of gathering all local rows).
+* one long clip sharded by frame (config 4): every rank selects / gathers ITS frames (K1-K3 are per frame), packs the bank
+  rows of its GLOBAL frames into one buffer (tscd_bank_pack), the ranks exchange the buffers with ONE all-gather
+  (ncclAllGather over NVLink/NVSwitch via torch.distributed; 1040 bytes per row: 0.75 MB per rank at 24 global frames x 30
+  proposals), and tscd_bank_unpack builds the virtual clip [own local frames | every rank's global frames].  Queries stay
+  sharded, so the attention needs no reduction.  The CAFM recurrence is a chain over consecutive local frames: rank r
+  receives the CAFM memory from rank r-1 before its chain and sends it on afterwards -- ONE point-to-point message per hop
+  (CAFMState.flat) instead of gathering all local rows.
 
-The exchange helpers use torch ops only (device-agnostic, no host sync), so they are exercised with gloo on CPU in
-tests/test_parallel_cpu.py; on GPUs the backend is NCCL over NVLink/NVSwitch.
+`frame_plan`, `shard_clips`, `all_gather_bytes` and the state hand-over are device-agnostic and exercised with gloo on CPU
+(tests/test_parallel_cpu.py); pack / unpack are CUDA kernels (tests/test_gpu_long_clip.py emulates the ranks on one GPU).
 """
 from typing import Dict, Optional
 
 import torch
 import torch.distributed as dist
+
+from . import _lib as L
+from . import ops
 
 
 def shard_clips(num_clips: int, rank: int, world: int):
@@ -24,72 +29,67 @@ def shard_clips(num_clips: int, rank: int, world: int):
     return lo, min(lo + per, num_clips)
 
 
-def exchange_global_bank(sel: Dict[str, torch.Tensor], n_local_frames: int, n_global_frames: int, kmax: int,
-                         group=None):
-    """All-gather the packed bank rows of this rank's global frames.
+def frame_plan(n_local: int, n_global: int, rank: int, world: int):
+    """Frames of a long clip [n_local local | n_global global] owned by `rank`: consecutive blocks of the local frames in rank
+    order (the CAFM chain walks them in order) and of the global frames.  Returns (local frame ids, global frame ids)."""
+    if n_local % world or n_global % world:
+        raise RuntimeError(f"long-clip mode: {n_local} local / {n_global} global frames must divide over {world} ranks")
+    lr, gr = n_local // world, n_global // world
+    return list(range(rank * lr, (rank + 1) * lr)), list(range(n_local + rank * gr, n_local + (rank + 1) * gr))
 
-    sel: output of selection.select_and_gather for this rank's frames ordered [local frames | global frames]
-         (bank_* packed in that order, sel_count [Lr+Gr], row_off [Lr+Gr+1]).
-    Returns the `sel` dict of the VIRTUAL clip [own local frames | all ranks' global frames (rank-major)]:
-    bank_cls/reg/edge/score, sel_count [Lr + W*Gr], row_off, sel_rows (own frames' rows; only local ones are read).
-    Everything stays on the device; the number of valid rows is never read by the host."""
+
+def all_gather_bytes(send: torch.Tensor, group=None) -> torch.Tensor:
+    """ONE all-gather of a flat uint8 buffer per rank -> [world * nbytes]."""
     world = dist.get_world_size(group)
-    Lr, Gr = n_local_frames, n_global_frames
-    dev = sel["bank_cls"].device
-    cnt = sel["sel_count"].to(torch.int64)
-    row_off = sel["row_off"].to(torch.int64)
-    n_loc = row_off[Lr]                                   # device scalar: own local rows
-    cap_g = Gr * kmax                                     # padded rows per rank in the exchange
-    ar = torch.arange(cap_g, device=dev)
-    src = torch.clamp(n_loc + ar, max=sel["bank_cls"].shape[0] - 1)
+    recv = torch.empty(world * send.numel(), dtype=send.dtype, device=send.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    return recv
 
-    def gather_rows(t):
-        send = t.index_select(0, src).contiguous()        # own global rows, packed at the front of a padded block
-        recv = torch.empty((world * cap_g,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-        dist.all_gather_into_tensor(recv, send, group=group)
-        return recv
 
-    counts_all = torch.empty(world * Gr, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(counts_all, cnt[Lr:Lr + Gr].contiguous(), group=group)
-    n_g = counts_all.view(world, Gr).sum(1)               # valid global rows per rank
-    idx = torch.arange(world * cap_g, device=dev)
-    valid = (idx % cap_g) < n_g[idx // cap_g]
-    order = torch.argsort((~valid).to(torch.int8), stable=True)   # valid rows first, rank-major, original order
+def pack_global_bank(sel: Dict[str, torch.Tensor], n_local_frames: int, n_global_frames: int, kmax: int, dtype) -> torch.Tensor:
+    nbytes = L.lib().tscd_bank_pack_bytes(n_global_frames, kmax)
+    if nbytes < 0:
+        raise RuntimeError(f"long-clip mode: {n_global_frames} global frames per rank exceed the exchange header (256)")
+    send = torch.empty(nbytes, dtype=torch.uint8, device=sel["bank_cls"].device)
+    ops.call("tscd_bank_pack", L.BankPackArgs, n_local_frames=n_local_frames, n_global_frames=n_global_frames, kmax=kmax, dtype=dtype,
+             sel_count=sel["sel_count"], row_off=sel["row_off"], bank_cls=sel["bank_cls"], bank_reg=sel["bank_reg"],
+             bank_score=sel["bank_score"], send=send)
+    return send
 
-    F_virt = Lr + world * Gr
+
+def unpack_virtual_clip(sel: Dict[str, torch.Tensor], recv: torch.Tensor, world: int, n_local_frames: int, n_global_frames: int,
+                        kmax: int, dtype):
+    """Gathered buffers + own bank -> the `sel` dict of the virtual clip [own local frames | all ranks' global frames]."""
+    dev = recv.device
+    F_virt = n_local_frames + world * n_global_frames
     rows_cap = ((F_virt * kmax + 127) // 128) * 128 + 128
-    dest = torch.clamp(n_loc + torch.arange(world * cap_g, device=dev), max=rows_cap - 1)
-    out = {}
-    for k in ("bank_cls", "bank_reg", "bank_edge", "bank_score"):
-        t = sel[k]
-        g = gather_rows(t).index_select(0, order)
-        v = torch.zeros((rows_cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-        n_copy = min(Lr * kmax, t.shape[0], rows_cap)
-        v[:n_copy] = t[:n_copy]                           # own local rows sit at the front (plus junk that is overwritten / unused)
-        v.index_copy_(0, dest, g)                         # global rows start right after the local ones
-        out[k] = v
-    counts_virt = torch.cat([cnt[:Lr], counts_all]).to(torch.int32)
-    ro = torch.zeros(F_virt + 1, dtype=torch.int32, device=dev)
-    ro[1:] = torch.cumsum(counts_virt, 0)
-    out["sel_count"], out["row_off"] = counts_virt, ro
+    D = sel["bank_cls"].shape[1]
+    out = dict(sel_count=torch.empty(F_virt, dtype=torch.int32, device=dev), row_off=torch.empty(F_virt + 1, dtype=torch.int32, device=dev),
+               bank_cls=torch.empty(rows_cap, D, dtype=dtype, device=dev), bank_reg=torch.empty(rows_cap, D, dtype=dtype, device=dev),
+               bank_edge=torch.empty(rows_cap, D, dtype=dtype, device=dev), bank_score=torch.empty(rows_cap, dtype=torch.float32, device=dev))
+    ops.call("tscd_bank_unpack", L.BankUnpackArgs, world=world, n_local_frames=n_local_frames, n_global_frames=n_global_frames, kmax=kmax,
+             dtype=dtype, rank_bytes=recv.numel() // world, recv=recv, sel_count=sel["sel_count"], row_off=sel["row_off"],
+             bank_cls=sel["bank_cls"], bank_reg=sel["bank_reg"], bank_edge=sel["bank_edge"], bank_score=sel["bank_score"],
+             v_count=out["sel_count"], v_row_off=out["row_off"], v_bank_cls=out["bank_cls"], v_bank_reg=out["bank_reg"],
+             v_bank_edge=out["bank_edge"], v_bank_score=out["bank_score"])
     out["sel_rows"], out["sel_idx"] = sel["sel_rows"], sel.get("sel_idx")
     return out, F_virt
 
 
-_STATE_FIELDS = ("n", "out", "edge", "reg", "cls", "nreg", "ncls", "time")
+def exchange_global_bank(sel, n_local_frames: int, n_global_frames: int, kmax: int, dtype=torch.float16, group=None):
+    """pack -> ONE all-gather -> unpack.  Returns (virtual-clip sel dict, F_virt)."""
+    world = dist.get_world_size(group)
+    send = pack_global_bank(sel, n_local_frames, n_global_frames, kmax, dtype)
+    recv = all_gather_bytes(send, group)
+    return unpack_virtual_clip(sel, recv, world, n_local_frames, n_global_frames, kmax, dtype)
 
 
 def send_state(state, dst: int, group=None):
-    for f in _STATE_FIELDS:
-        dist.send(getattr(state, f).contiguous(), dst, group=group)
+    dist.send(state.flat, dst, group=group)              # one message: every field is a view of `flat`
 
 
 def recv_state(state, src: int, group=None):
-    for f in _STATE_FIELDS:
-        t = getattr(state, f)
-        buf = torch.empty_like(t)
-        dist.recv(buf, src, group=group)
-        t.copy_(buf)
+    dist.recv(state.flat, src, group=group)
 
 
 def long_clip_forward(stage, sel, n_local_frames: int, n_global_frames: int, kmax: int, time_embedding_local,
@@ -98,7 +98,7 @@ def long_clip_forward(stage, sel, n_local_frames: int, n_global_frames: int, kma
     ranks hold consecutive blocks of the clip's local frames in rank order.  Returns the stage output for this rank's
     local frames (use AggregationStage.to_lists(out, 1, n_local_frames))."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    virt, F_virt = exchange_global_bank(sel, n_local_frames, n_global_frames, kmax, group)
+    virt, F_virt = exchange_global_bank(sel, n_local_frames, n_global_frames, kmax, stage.cfg.dtype, group)
     dev = virt["bank_cls"].device
     resume = torch.tensor([1 if (rank > 0 or resume_first) else 0], dtype=torch.int32, device=dev)
 

@@ -92,15 +92,24 @@ class StageWeights:
 
 
 class CAFMState:
-    """Caller-owned CAFM memory (tscd_matching.py:708-715) for `slots` concurrent video streams."""
+    """Caller-owned CAFM memory (tscd_matching.py:708-715) for `slots` concurrent video streams.  All fields are views of ONE
+    flat fp32 buffer (`flat`; `n` is its first `slots` words viewed as int32), so handing the memory to another rank in the
+    long-clip mode is a single message."""
 
     def __init__(self, slots: int, kmax: int, dim: int = 256, device="cuda"):
-        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)  # noqa: E731
-        self.slots, self.kmax = slots, kmax
-        self.n = torch.zeros(slots, dtype=torch.int32, device=device)
-        self.out, self.edge = z(slots, kmax, dim), z(slots, kmax, dim)
-        self.reg, self.cls = z(slots, kmax, 4 * dim), z(slots, kmax, 4 * dim)
-        self.nreg, self.ncls, self.time = z(slots, kmax), z(slots, kmax), z(slots, dim)
+        self.slots, self.kmax, self.dim = slots, kmax, dim
+        sizes = [("n", slots), ("out", slots * kmax * dim), ("edge", slots * kmax * dim), ("reg", slots * kmax * 4 * dim),
+                 ("cls", slots * kmax * 4 * dim), ("nreg", slots * kmax), ("ncls", slots * kmax), ("time", slots * dim)]
+        total = sum(((n + 3) // 4) * 4 for _, n in sizes)            # every field 16-byte aligned
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        off, views = 0, {}
+        for name, n in sizes:
+            views[name] = self.flat[off:off + n]
+            off += ((n + 3) // 4) * 4
+        self.n = views["n"].view(torch.int32)
+        self.out, self.edge = views["out"].view(slots, kmax, dim), views["edge"].view(slots, kmax, dim)
+        self.reg, self.cls = views["reg"].view(slots, kmax, 4 * dim), views["cls"].view(slots, kmax, 4 * dim)
+        self.nreg, self.ncls, self.time = views["nreg"].view(slots, kmax), views["ncls"].view(slots, kmax), views["time"].view(slots, dim)
 
 
 class AggregationStage:
