@@ -55,7 +55,7 @@ A = sum(h * w for h, w in HW)
 METRIC = "clip-frames/sec of TSCD aggregation stage"
 
 CONFIGS = {
-    "ovis_a_k30": dict(C=25, F=32, L=8, mode="A", pre_k=750, top_k=30, clips=64, replays=64, obj_means=[-3.0],
+    "ovis_a_k30": dict(C=25, F=32, L=8, mode="A", pre_k=750, top_k=30, clips=148, replays=28, obj_means=[-3.0],
                        workload="TSCD-L OVIS 25cls, 32-frame clip (8 local + 24 global) @576x576 (6804 anchors), pre-NMS top-750 -> "
                                 "NMS0.75 -> 30 proposals/frame, agg+agg_iou MCA + CAFM + TaskAligned + final NMS0.5"),
     "ovis_l_modeB": dict(C=25, F=32, L=8, mode="B", minimal_limit=50, maximal_limit=500, clips=8, replays=8,
@@ -619,8 +619,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--config", default="ovis_a_k30", choices=list(CONFIGS) + ["sweep"])
     ap.add_argument("--mode", default="clips", choices=["clips", "long-clip"])
-    ap.add_argument("--clips", type=int, default=0, help="clips per GPU per graph replay (default: per config; 64 for the headline)")
-    ap.add_argument("--replays", type=int, default=0, help="graph replays per step (default: per config; 64 for the headline)")
+    ap.add_argument("--clips", type=int, default=0, help="clips per GPU per graph replay (default: per config; 148 = one per SM for the headline)")
+    ap.add_argument("--replays", type=int, default=0, help="graph replays per step (default: per config; 28 for the headline)")
     ap.add_argument("--sets", type=int, default=2, help="rotating input sets resident in HBM")
     ap.add_argument("--e2e-clips", type=int, default=0)
     ap.add_argument("--e2e-chunk", type=int, default=8, help="clips per pipelined chunk of the host-buffer path")

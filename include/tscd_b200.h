@@ -349,6 +349,8 @@ typedef struct {
     float* kin;                  /* out [loc_cap, D] fp32 copy (first-frame query input) */
     float* norm_reg;             /* out [loc_cap] |emb_reg| + 1e-6 */
     float* norm_cls;             /* out [loc_cap] */
+    int32_t emb_dtype;           /* TSCD_F32 (0): emb_* are fp32 and the norms are computed here; TSCD_F16 / TSCD_BF16: emb_* are not
+                                  * read, tscd_cafm_cost computes the norms from the 16-bit embeddings */
 } tscd_cafm_prep_args;
 int tscd_cafm_prep(const tscd_cafm_prep_args* args, void* stream);
 
@@ -365,6 +367,10 @@ typedef struct {
     const float* st_reg; const float* st_cls; const float* st_nreg; const float* st_ncls;
     float* cost;                 /* [B*L, kmax, kmax] */
     int32_t* ref_n;              /* [B*L] rows on the reference side of every frame's matching (0 for empty frames) */
+    /* TSCD_F32 (0): emb_* / norm_* as declared above (fp32 FMA kernel, any kmax <= 512).  TSCD_F16 / TSCD_BF16 (kmax <= 32): emb_reg /
+     * emb_cls point to 16-bit [loc_cap, 4D] embeddings (the GEMM outputs as the tensor cores produced them), the costs run on
+     * mma.sync with fp32 accumulation and norm_reg / norm_cls are OUTPUTS (written for the rows of every frame) */
+    int32_t emb_dtype;
 } tscd_cafm_cost_args;
 int tscd_cafm_cost(const tscd_cafm_cost_args* args, void* stream);
 
@@ -433,6 +439,7 @@ typedef struct {
     float* out32;                /* [loc_cap, D] same in fp32 (may be NULL) */
     int32_t* perm;               /* [loc_cap] matched column of every output row (debug / tests; may be NULL) */
     int32_t* status;
+    int32_t emb_dtype;           /* element type of emb_reg / emb_cls: TSCD_F32 (0), or 16-bit with the fast path (widened into the state) */
 } tscd_cafm_chain_args;
 int tscd_cafm_chain(const tscd_cafm_chain_args* args, void* stream);
 

@@ -46,6 +46,8 @@ def test_cafm_chain_exact_assignments(counts_calls, kmax):
         emb_c = torch.zeros(loc_cap, 4 * D)
         emb_r[:loc_total] = base[torch.randint(0, 12, (loc_total,), generator=g)] + 0.5 * torch.randn(loc_total, 4 * D, generator=g)
         emb_c[:loc_total] = base[torch.randint(0, 12, (loc_total,), generator=g)] + 0.5 * torch.randn(loc_total, 4 * D, generator=g)
+        if kmax <= 32:       # frames of <= 32 proposals match on the 16-bit GEMM outputs (tensor-core cost kernel): same values on both sides
+            emb_r, emb_c = emb_r.to(dtype).float(), emb_c.to(dtype).float()
         te = torch.cat([oracle.timing_signal_1d(torch.arange(call * Lf, (call + 1) * Lf), 256) for _ in range(B)], 0)
         bank_reg = torch.zeros(row_cap, D, dtype=dtype).cuda(); bank_reg[:N] = feat.cuda()
         bank_edge = torch.zeros(row_cap, D, dtype=dtype).cuda(); bank_edge[:N] = edge.cuda()

@@ -4,15 +4,15 @@
 On the GPU box (one step of the bench workload, bracketed by cudaProfilerStart/Stop in tools/profile_step.py):
 
   ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv \
-      --log-file gpurun_out/launches_r1.csv python tools/profile_step.py --clips 64
+      --log-file gpurun_out/launches_r2.csv python tools/profile_step.py --clips 64
   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,\
 sm__throughput.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,\
 sm__warps_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active,\
 launch__occupancy_limit_shared_mem,launch__occupancy_limit_registers,launch__registers_per_thread,\
 launch__shared_mem_per_block_dynamic --clock-control none --profile-from-start off -c 80 --csv \
-      --log-file gpurun_out/ncu_metrics_r1.csv python tools/profile_step.py --clips 64
+      --log-file gpurun_out/ncu_metrics_r2.csv python tools/profile_step.py --clips 64
 
-Here:  python tools/make_profiles.py   ->  profiles/launches_r1.csv, profiles/ncu_kernels_r1.csv, profiles/traffic_r1.json
+Here:  python tools/make_profiles.py   ->  profiles/launches_r2.csv, profiles/ncu_kernels_r2.csv, profiles/traffic_r2.json
 """
 import collections
 import csv
@@ -26,8 +26,8 @@ DST = os.path.join(ROOT, "profiles")
 
 
 def main():
-    shutil.copy(os.path.join(SRC, "launches_r1.csv"), os.path.join(DST, "launches_r1.csv"))
-    rows = [r for r in csv.reader(open(os.path.join(SRC, "ncu_metrics_r1.csv"))) if len(r) > 5]
+    shutil.copy(os.path.join(SRC, "launches_r2.csv"), os.path.join(DST, "launches_r2.csv"))
+    rows = [r for r in csv.reader(open(os.path.join(SRC, "ncu_metrics_r2.csv"))) if len(r) > 5]
     hdr = rows[0]
     ki, ii, mi, vi, ui, gi = (hdr.index(k) for k in ("Kernel Name", "ID", "Metric Name", "Metric Value", "Metric Unit", "Grid Size"))
     launches = collections.OrderedDict()
@@ -59,7 +59,7 @@ def main():
         a[0] += 1
         a[1] += t
         a[2] += rd + wr
-    csv.writer(open(os.path.join(DST, "ncu_kernels_r1.csv"), "w")).writerows(out)
+    csv.writer(open(os.path.join(DST, "ncu_kernels_r2.csv"), "w")).writerows(out)
     tot = sum(a[1] for a in agg.values())
     traffic = {}
     print(f"{'kernel':40s} {'n':>3s} {'us':>8s} {'share':>6s} {'MB/launch':>9s} {'GB/s':>7s}")
@@ -68,7 +68,7 @@ def main():
             print(f"{k[:40]:40s} {a[0]:3d} {a[1]:8.1f} {100 * a[1] / tot:5.1f}% {a[2] / a[0] / 1e6:9.1f} {a[2] / a[1] / 1e3:7.0f}")
         traffic[k] = {"launches": a[0], "dram_bytes_per_launch": a[2] / a[0], "time_us_total": a[1]}
     print(f"sum of kernel times {tot:.1f} us over {len(launches)} launches")
-    json.dump(traffic, open(os.path.join(DST, "traffic_r1.json"), "w"), indent=1)
+    json.dump(traffic, open(os.path.join(DST, "traffic_r2.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
-"""One profiled step of the bench workload (for ncu).  Two warm-up steps run outside the capture range; the
-third step is bracketed by cudaProfilerStart/Stop, so `ncu --profile-from-start off ...` sees exactly one step.
+"""One profiled replay of a bench configuration (for ncu).  Two warm-up passes run outside the capture range; the third is
+bracketed by cudaProfilerStart/Stop, so `ncu --profile-from-start off ...` sees exactly one pass of the stage (eager launches,
+classification branch serialised on the launching stream so that ncu's per-launch numbers are for kernels running alone).
 
-  python tools/profile_step.py [--clips 16]
+  python tools/profile_step.py [--config ovis_a_k30] [--clips 64]
 """
 import argparse
 import os
@@ -17,25 +18,27 @@ import bench  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--clips", type=int, default=16)
+    ap.add_argument("--config", default="ovis_a_k30", choices=list(bench.CONFIGS))
+    ap.add_argument("--clips", type=int, default=0)
     args = ap.parse_args()
-    from tscd_b200 import ops, selection, stage, weights
+    from tscd_b200 import ops, weights
+    cfg = bench.CONFIGS[args.config]
     dev = torch.device("cuda", 0)
-    B = args.clips
-    cfg = stage.StageConfig(num_classes=bench.C, selection=selection.SelectionConfig(mode="A", pre_k=bench.PRE_K, top_k=bench.TOP_K))
-    st = stage.AggregationStage(cfg, weights.random_state_dict(bench.C, bench.D, seed=2024), device=dev)
-    inp = bench.synth_s1(B, dev, seed=2024)
-    head, feats = bench.views_of(inp, ops)
-    te = torch.cat([weights.timing_signal_1d(torch.arange(bench.LF), 256)] * B, 0).to(dev)
+    B = args.clips or cfg["clips"]
+    st, run = bench.make_runner(cfg, dev)
+    st.serialize = True
+    inp = bench.synth_s1(cfg, B, dev, seed=2024)
+    views = bench.views_of(inp, ops)
+    te = torch.cat([weights.timing_signal_1d(torch.arange(cfg["L"]), 256)] * B, 0).to(dev)
     for _ in range(2):
-        out = st.forward(head, feats, torch.float16, te, B, bench.F, bench.LF)
+        out = run(views, B, te)
     torch.cuda.synchronize()
     torch.cuda.cudart().cudaProfilerStart()
-    out = st.forward(head, feats, torch.float16, te, B, bench.F, bench.LF)
+    out = run(views, B, te)
     torch.cuda.synchronize()
     torch.cuda.cudart().cudaProfilerStop()
-    res, _ = st.to_lists(out, B, bench.LF)
-    print("profiled one step:", B, "clips,", sum(0 if r is None else len(r) for r in res), "detections")
+    assert int(out["status"].item()) == 0
+    print("profiled one pass:", args.config, B, "clips")
 
 
 if __name__ == "__main__":

@@ -112,19 +112,19 @@ def _fields(spec):
 
 class CafmPrepArgs(C.Structure):
     _fields_ = _fields("B:i F:i L:i D:i bank_dtype:i row_off:p lrow_off:p bank_reg:p bank_edge:p time_emb:p se_w1:p "
-                       "se_w2:p emb_reg:p emb_cls:p feat:p edge:p feat16:p kin16:p kin:p norm_reg:p norm_cls:p")
+                       "se_w2:p emb_reg:p emb_cls:p feat:p edge:p feat16:p kin16:p kin:p norm_reg:p norm_cls:p emb_dtype:i")
 
 
 class CafmChainArgs(C.Structure):
     _fields_ = _fields("B:i F:i L:i D:i kmax:i out_dtype:i row_off:p lrow_off:p resume:p feat:p edge:p kin:p kproj:p "
                        "vproj:p kproj16:p vproj16:p wq16:p bank_reg:p bank_edge:p time_emb:p emb_reg:p emb_cls:p norm_reg:p norm_cls:p wq_t:p se_w1:p se_w2:p ln_w:p "
                        "ln_b:p dec_w:p dec_b:p st_n:p st_out:p st_edge:p st_reg:p st_cls:p st_nreg:p st_ncls:p "
-                       "st_time:p sc_qin:p sc_q:p sc_k:p ref_n:p lap_col:p lap_row:p out16:p out32:p perm:p status:p")
+                       "st_time:p sc_qin:p sc_q:p sc_k:p ref_n:p lap_col:p lap_row:p out16:p out32:p perm:p status:p emb_dtype:i")
 
 
 class CafmCostArgs(C.Structure):
     _fields_ = _fields("B:i L:i D:i kmax:i lrow_off:p resume:p st_n:p emb_reg:p emb_cls:p norm_reg:p norm_cls:p "
-                       "st_reg:p st_cls:p st_nreg:p st_ncls:p cost:p ref_n:p")
+                       "st_reg:p st_cls:p st_nreg:p st_ncls:p cost:p ref_n:p emb_dtype:i")
 
 
 class CafmLapArgs(C.Structure):

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(256) cafm_prep_kernel(const tscd_cafm_prep_arg
         uint4 kp;
         kp.x = pack2<T>(k[0], k[1]); kp.y = pack2<T>(k[2], k[3]); kp.z = pack2<T>(k[4], k[5]); kp.w = pack2<T>(k[6], k[7]);
         *reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.kin16) + o) = kp;
+        if (a.emb_dtype != TSCD_F32) continue;      // 16-bit matching embeddings: tscd_cafm_cost computes the norms itself
         float sr = 0.f, sc = 0.f;
         const float4* pr = reinterpret_cast<const float4*>(a.emb_reg + (int64_t)(l0 + j) * E);
         const float4* pc = reinterpret_cast<const float4*>(a.emb_cls + (int64_t)(l0 + j) * E);
@@ -278,6 +279,143 @@ __global__ void __launch_bounds__(256) cafm_cost_kernel(const tscd_cafm_cost_arg
             out[(int64_t)r * KM + c] = v;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------- matching costs, 16-bit
+// Frames of at most 32 proposals with 16-bit matching embeddings (the agg_iou GEMM outputs as the tensor cores produced
+// them): one CTA (4 warps) per local frame.  The two 1024-dim embeddings of the reference rows and of the current rows
+// stream through shared memory in 64-dim chunks (cp.async, double buffered, rows padded to 144 bytes so ldmatrix is
+// conflict-free); warp w owns embedding (w >> 1) and the 16 reference rows (w & 1): 4 n-tiles of mma.sync m16n8k16 per
+// k-step, fp32 accumulation.  Every thread also accumulates the squared norm of one (matrix, row) from the same chunks, so
+// the (|x| + 1e-6) norms of tscd_matching.py:914-927 come from exactly the values the dot products use and the 126 MB norm
+// pass over fp32 embeddings in tscd_cafm_prep disappears.  The current frame's norms are written out for the state carry.
+constexpr int kC16Pitch = 72;                 // halves per smem row: 64 + 8 pad
+constexpr int kC16Chunk = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(128) cafm_cost16_kernel(const tscd_cafm_cost_args a) {
+    __shared__ __align__(16) T tile[2][4][32][kC16Pitch];     // [stage][ref_reg, cur_reg, ref_cls, cur_cls][row][k]
+    __shared__ float nrm[4][32];
+    __shared__ float cosv[2][32][33];
+    const int lf = blockIdx.x, b = lf / a.L, f = lf - b * a.L;
+    const int l0 = a.lrow_off[lf], n = a.lrow_off[lf + 1] - l0;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (n <= 0) {
+        if (tid == 0) a.ref_n[lf] = 0;
+        return;
+    }
+    constexpr int E = 1024;
+    const int KM = a.kmax;
+    // reference side: previous non-empty local frame, else the carried state (resume), else the frame itself
+    const T *Rp = nullptr, *Cp = nullptr;
+    const float *sR = nullptr, *sC = nullptr;
+    int np = 0;
+    for (int p = f - 1; p >= 0 && np == 0; --p) {
+        const int pl0 = a.lrow_off[b * a.L + p], pn = a.lrow_off[b * a.L + p + 1] - pl0;
+        if (pn > 0) { np = pn; Rp = reinterpret_cast<const T*>(a.emb_reg) + (int64_t)pl0 * E; Cp = reinterpret_cast<const T*>(a.emb_cls) + (int64_t)pl0 * E; }
+    }
+    if (np == 0) {
+        const int sn = (a.resume && a.resume[b]) ? a.st_n[b] : 0;
+        if (sn > 0) { np = sn; sR = a.st_reg + (int64_t)b * KM * E; sC = a.st_cls + (int64_t)b * KM * E; }
+        else { np = n; Rp = reinterpret_cast<const T*>(a.emb_reg) + (int64_t)l0 * E; Cp = reinterpret_cast<const T*>(a.emb_cls) + (int64_t)l0 * E; }
+    }
+    if (np > KM || n > KM || np > 32 || n > 32) {          // the chain kernel reports the capacity error
+        if (tid == 0) a.ref_n[lf] = 0;
+        return;
+    }
+    if (tid == 0) a.ref_n[lf] = np;
+    const T* Rc = reinterpret_cast<const T*>(a.emb_reg) + (int64_t)l0 * E;
+    const T* Cc = reinterpret_cast<const T*>(a.emb_cls) + (int64_t)l0 * E;
+    // zero the rows no load will touch (both stages)
+    for (int i = tid; i < 2 * 4 * 32 * (kC16Pitch / 8); i += 128) {
+        const int st = i / (4 * 32 * (kC16Pitch / 8)), rem = i % (4 * 32 * (kC16Pitch / 8));
+        const int m = rem / (32 * (kC16Pitch / 8)), r = (rem / (kC16Pitch / 8)) % 32;
+        if (r >= ((m & 1) ? n : np)) reinterpret_cast<uint4*>(&tile[st][m][r][0])[rem % (kC16Pitch / 8)] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    auto load_chunk = [&](int st, int kc) {
+        // 4 matrices x 32 rows x 8 16-byte pieces = 1024 pieces, 8 per thread
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = u * 128 + tid;
+            const int m = i >> 8, r = (i >> 3) & 31, pc = i & 7;
+            const int rows = (m & 1) ? n : np;
+            if (r >= rows) continue;
+            T* dst = &tile[st][m][r][pc * 8];
+            if (m & 1) {
+                cp_async16(dst, (m == 1 ? Rc : Cc) + (int64_t)r * E + kc * kC16Chunk + pc * 8);
+            } else if (Rp) {
+                cp_async16(dst, (m == 0 ? Rp : Cp) + (int64_t)r * E + kc * kC16Chunk + pc * 8);
+            } else {                                        // carried state: fp32 copies of 16-bit values
+                const float* src = (m == 0 ? sR : sC) + (int64_t)r * E + kc * kC16Chunk + pc * 8;
+                const float4 x = __ldg(reinterpret_cast<const float4*>(src)), y = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                uint4 pk;
+                pk.x = pack2<T>(x.x, x.y); pk.y = pack2<T>(x.z, x.w); pk.z = pack2<T>(y.x, y.y); pk.w = pack2<T>(y.z, y.w);
+                *reinterpret_cast<uint4*>(dst) = pk;
+            }
+        }
+        cp_async_commit();
+    };
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float sq = 0.f;                                         // squared norm of (matrix tid >> 5, row tid & 31)
+    const int e = warp >> 1, mt = warp & 1;
+    __syncthreads();
+    load_chunk(0, 0);
+    constexpr int NCH = E / kC16Chunk;
+    for (int kc = 0; kc < NCH; ++kc) {
+        const int st = kc & 1;
+        if (kc + 1 < NCH) load_chunk(st ^ 1, kc + 1);
+        if (kc + 1 < NCH) asm volatile("cp.async.wait_group 1;\n" ::: "memory"); else cp_async_wait_all();
+        __syncthreads();
+        {   // norms
+            const uint4* row = reinterpret_cast<const uint4*>(&tile[st][warp][lane][0]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const uint4 raw = row[q];
+                const T* h = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) { const float x = ldf_reg(h[t]); sq = fmaf(x, x, sq); }
+            }
+        }
+#pragma unroll
+        for (int ks = 0; ks < kC16Chunk / 16; ++ks) {
+            uint32_t af[4], bf0[4], bf1[4];
+            // A: reference rows mt*16 .. +16, k ks*16 .. +16  (row-major): matrices (r0-7,k0-7) (r8-15,k0-7) (r0-7,k8-15) (r8-15,k8-15)
+            ldsm_x4(af, &tile[st][2 * e][mt * 16 + (lane & 15)][ks * 16 + (lane >> 4) * 8]);
+            // B: current rows as [n][k]: x4 = (n0-7,k0-7) (n0-7,k8-15) (n8-15,k0-7) (n8-15,k8-15)
+            ldsm_x4(bf0, &tile[st][2 * e + 1][(lane & 7) + ((lane >> 4) << 3)][ks * 16 + ((lane >> 3) & 1) * 8]);
+            ldsm_x4(bf1, &tile[st][2 * e + 1][16 + (lane & 7) + ((lane >> 4) << 3)][ks * 16 + ((lane >> 3) & 1) * 8]);
+            mma16816<T>(acc[0], af, bf0[0], bf0[1]);
+            mma16816<T>(acc[1], af, bf0[2], bf0[3]);
+            mma16816<T>(acc[2], af, bf1[0], bf1[1]);
+            mma16816<T>(acc[3], af, bf1[2], bf1[3]);
+        }
+        __syncthreads();
+    }
+    nrm[warp][lane] = sqrtf(sq) + 1e-6f;
+    __syncthreads();
+    // cos = dot / (|ref| |cur|); fragment layout of m16n8: rows lane/4 (+8), cols 2*(lane%4) (+1)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const int r = mt * 16 + (lane >> 2) + ((h >> 1) << 3), c = nt * 8 + 2 * (lane & 3) + (h & 1);
+            cosv[e][r][c] = acc[nt][h] / (nrm[2 * e][r] * nrm[2 * e + 1][c]);
+        }
+    __syncthreads();
+    float* out = a.cost + (int64_t)lf * KM * KM;
+    for (int t = tid; t < 32 * 32; t += 128) {
+        const int r = t >> 5, c = t & 31;
+        if (r < np && c < n) {
+            float v = 1.f - (cosv[0][r][c] + cosv[1][r][c]) / 2.f;
+            if (v != v) v = 0.f;                            // tscd_matching.py:930 NaN -> 0
+            out[(int64_t)r * KM + c] = v;
+        }
+    }
+    if (tid < n) { const_cast<float*>(a.norm_reg)[l0 + tid] = nrm[1][tid]; const_cast<float*>(a.norm_cls)[l0 + tid] = nrm[3][tid]; }
 }
 
 // Rectangular LSAP by warp 0.  C is the [n_prev x n_cur] cost (row-major, fp32).  Solves the problem with
@@ -1031,27 +1169,42 @@ __global__ void __launch_bounds__(kFastThreads, 1) cafm_chain_fast_kernel(const 
         for (int c = tid; c < 256; c += kFastThreads) a.st_time[(int64_t)b * 256 + c] = lastb.time[c];
         float* st_reg = a.st_reg + (int64_t)b * KM * E;
         float* st_cls = a.st_cls + (int64_t)b * KM * E;
-        const float* Rc = a.emb_reg + (int64_t)last_l0 * E;
-        const float* Cc = a.emb_cls + (int64_t)last_l0 * E;
-        // 2 x n_prev x 4 KB: batches of four independent 16-byte loads per matrix before the stores (latency-bound otherwise)
-        for (int i0 = 0; i0 < n_prev * (E / 4); i0 += 4 * kFastThreads) {
-            float4 vr[4], vc[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * kFastThreads + tid;
-                if (i < n_prev * (E / 4)) {
-                    const int r = i / (E / 4), c4 = i - r * (E / 4);
-                    const int src = s.ord_prev[r];
-                    vr[u] = __ldg(reinterpret_cast<const float4*>(Rc) + (int64_t)src * (E / 4) + c4);
-                    vc[u] = __ldg(reinterpret_cast<const float4*>(Cc) + (int64_t)src * (E / 4) + c4);
-                }
+        if (a.emb_dtype != TSCD_F32) {
+            // 16-bit matching embeddings: widened to fp32 in the state (exact), 8 values per 16-byte load
+            const T* Rc16 = reinterpret_cast<const T*>(a.emb_reg) + (int64_t)last_l0 * E;
+            const T* Cc16 = reinterpret_cast<const T*>(a.emb_cls) + (int64_t)last_l0 * E;
+            for (int i = tid; i < n_prev * (E / 8); i += kFastThreads) {
+                const int r = i / (E / 8), c8 = i - r * (E / 8);
+                const int src = s.ord_prev[r];
+                float vr[8], vc[8];
+                load8(Rc16 + (int64_t)src * E + c8 * 8, vr);
+                load8(Cc16 + (int64_t)src * E + c8 * 8, vc);
+                store8(st_reg + (int64_t)r * E + c8 * 8, vr);
+                store8(st_cls + (int64_t)r * E + c8 * 8, vc);
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * kFastThreads + tid;
-                if (i < n_prev * (E / 4)) {
-                    reinterpret_cast<float4*>(st_reg)[i] = vr[u];
-                    reinterpret_cast<float4*>(st_cls)[i] = vc[u];
+        } else {
+        const float* Rc = a.emb_reg + (int64_t)last_l0 * E;
+            const float* Cc = a.emb_cls + (int64_t)last_l0 * E;
+            // 2 x n_prev x 4 KB: batches of four independent 16-byte loads per matrix before the stores (latency-bound otherwise)
+            for (int i0 = 0; i0 < n_prev * (E / 4); i0 += 4 * kFastThreads) {
+                float4 vr[4], vc[4];
+    #pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * kFastThreads + tid;
+                    if (i < n_prev * (E / 4)) {
+                        const int r = i / (E / 4), c4 = i - r * (E / 4);
+                        const int src = s.ord_prev[r];
+                        vr[u] = __ldg(reinterpret_cast<const float4*>(Rc) + (int64_t)src * (E / 4) + c4);
+                        vc[u] = __ldg(reinterpret_cast<const float4*>(Cc) + (int64_t)src * (E / 4) + c4);
+                    }
+                }
+    #pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * kFastThreads + tid;
+                    if (i < n_prev * (E / 4)) {
+                        reinterpret_cast<float4*>(st_reg)[i] = vr[u];
+                        reinterpret_cast<float4*>(st_cls)[i] = vc[u];
+                    }
                 }
             }
         }
@@ -1082,6 +1235,14 @@ extern "C" int tscd_cafm_cost(const tscd_cafm_cost_args* a, void* stream) {
     using namespace tscd;
     if (!a || a->B <= 0 || a->L <= 0 || a->D != 256 || a->kmax <= 0 || a->kmax > kChainMax) return TSCD_ERR_INVALID_ARG;
     const int tiles = (a->kmax + 31) / 32;
+    if (a->emb_dtype != TSCD_F32) {                        // 16-bit matching embeddings: tensor-core kernel, frames <= 32 proposals
+        if (a->kmax > 32 || !a->norm_reg || !a->norm_cls || !a->ref_n) return TSCD_ERR_INVALID_ARG;
+        if (a->emb_dtype == TSCD_F16) cafm_cost16_kernel<__half><<<a->B * a->L, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+        else if (a->emb_dtype == TSCD_BF16) cafm_cost16_kernel<__nv_bfloat16><<<a->B * a->L, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+        else return TSCD_ERR_UNSUPPORTED;
+        TSCD_CUDA_CHECK_LAUNCH();
+        return TSCD_OK;
+    }
     cafm_cost_kernel<<<dim3(a->B * a->L, tiles, tiles), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
     TSCD_CUDA_CHECK_LAUNCH();
     return TSCD_OK;

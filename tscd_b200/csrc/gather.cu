@@ -86,10 +86,31 @@ __global__ void __launch_bounds__(256) rows_gather_kernel(const tscd_gather_args
         const int a = args.cand_idx[(int64_t)frame * args.cand_cap + pos];
         AnchorPos p = anchor_pos(an, a);
         float* row = args.sel_rows + ((int64_t)frame * args.max_keep + j) * W;
+        const int64_t r = (int64_t)(row0 + j) * args.feat_dim;
+        // fast path (TSCD-L: 256 channel-contiguous 16-bit features, same bank type): the three feature rows are requested FIRST
+        // (three independent 16-byte loads per lane), so their latency overlaps the dependent class / objectness / box loads below
+        bool fast = false;
+        uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0, v2 = v0;
+        if (std::is_same<TF, TB>::value && sizeof(TF) == 2 && args.feat_dim == 256 &&
+            args.feat_cls.chan_stride[p.level] == 1 && args.feat_reg.chan_stride[p.level] == 1 && args.feat_edge.chan_stride[p.level] == 1) {
+            const TF* s0 = view_ptr<TF>(args.feat_cls, p.level, frame, p.local) + lane * 8;
+            const TF* s1 = view_ptr<TF>(args.feat_reg, p.level, frame, p.local) + lane * 8;
+            const TF* s2 = view_ptr<TF>(args.feat_edge, p.level, frame, p.local) + lane * 8;
+            if (((reinterpret_cast<uintptr_t>(s0) | reinterpret_cast<uintptr_t>(s1) | reinterpret_cast<uintptr_t>(s2)) & 15) == 0) {
+                fast = true;
+                v0 = __ldg(reinterpret_cast<const uint4*>(s0));
+                v1 = __ldg(reinterpret_cast<const uint4*>(s1));
+                v2 = __ldg(reinterpret_cast<const uint4*>(s2));
+            }
+        }
         // class scores + arg-max (first maximum)
         const int64_t cbase = (int64_t)frame * args.cls.frame_stride[p.level] + (int64_t)p.local * args.cls.anchor_stride[p.level];
         float best = -INFINITY;
         int bi = 0x7fffffff;
+        float obj_raw = 0.f;
+        if (lane == 0)
+            obj_raw = ld_any(args.obj.ptr[p.level], hd,
+                             (int64_t)frame * args.obj.frame_stride[p.level] + (int64_t)p.local * args.obj.anchor_stride[p.level]);
         for (int c = lane; c < C; c += 32) {
             float v = ld_any(args.cls.ptr[p.level], hd, cbase + c * args.cls.chan_stride[p.level]);
             if (args.apply_sigmoid) v = sigmoidf_ref(v);
@@ -103,38 +124,23 @@ __global__ void __launch_bounds__(256) rows_gather_kernel(const tscd_gather_args
             if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
         }
         if (lane == 0) {
-            float obj = ld_any(args.obj.ptr[p.level], hd,
-                               (int64_t)frame * args.obj.frame_stride[p.level] + (int64_t)p.local * args.obj.anchor_stride[p.level]);
+            float obj = obj_raw;
             if (args.apply_sigmoid) obj = sigmoidf_ref(obj);
             float4 box = (hd == TSCD_F32) ? anchor_box<float>(args.reg, p, frame, args.apply_decode != 0)
                                           : anchor_box<__half>(args.reg, p, frame, args.apply_decode != 0);
             row[0] = box.x; row[1] = box.y; row[2] = box.z; row[3] = box.w;
             row[4] = obj; row[5] = best; row[6] = (float)bi;
             args.sel_idx[(int64_t)frame * args.max_keep + j] = a;
-            const int r = row0 + j;
-            args.bank_score[r] = best;
-            args.bank_fg[r] = obj;
-            reinterpret_cast<float4*>(args.bank_box)[r] = box;
+            const int rr = row0 + j;
+            args.bank_score[rr] = best;
+            args.bank_fg[rr] = obj;
+            reinterpret_cast<float4*>(args.bank_box)[rr] = box;
         }
-        const int64_t r = (int64_t)(row0 + j) * args.feat_dim;
-        // fast path (TSCD-L: 256 channel-contiguous 16-bit features, same bank type): the three rows are fetched with
-        // three independent 16-byte loads per lane before anything is stored
-        if (std::is_same<TF, TB>::value && sizeof(TF) == 2 && args.feat_dim == 256 &&
-            args.feat_cls.chan_stride[p.level] == 1 && args.feat_reg.chan_stride[p.level] == 1 && args.feat_edge.chan_stride[p.level] == 1) {
-            const TF* s0 = view_ptr<TF>(args.feat_cls, p.level, frame, p.local) + lane * 8;
-            const TF* s1 = view_ptr<TF>(args.feat_reg, p.level, frame, p.local) + lane * 8;
-            const TF* s2 = view_ptr<TF>(args.feat_edge, p.level, frame, p.local) + lane * 8;
-            if (((reinterpret_cast<uintptr_t>(s0) | reinterpret_cast<uintptr_t>(s1) | reinterpret_cast<uintptr_t>(s2)) & 15) == 0) {
-                const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(s0));
-                const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(s1));
-                const uint4 v2 = __ldg(reinterpret_cast<const uint4*>(s2));
-                {                                      // identical 16-bit types: raw copy
-                    *reinterpret_cast<uint4*>(reinterpret_cast<TB*>(args.bank_cls) + r + lane * 8) = v0;
-                    *reinterpret_cast<uint4*>(reinterpret_cast<TB*>(args.bank_reg) + r + lane * 8) = v1;
-                    *reinterpret_cast<uint4*>(reinterpret_cast<TB*>(args.bank_edge) + r + lane * 8) = v2;
-                }
-                continue;
-            }
+        if (fast) {                                    // identical 16-bit types: raw copy
+            *reinterpret_cast<uint4*>(reinterpret_cast<TB*>(args.bank_cls) + r + lane * 8) = v0;
+            *reinterpret_cast<uint4*>(reinterpret_cast<TB*>(args.bank_reg) + r + lane * 8) = v1;
+            *reinterpret_cast<uint4*>(reinterpret_cast<TB*>(args.bank_edge) + r + lane * 8) = v2;
+            continue;
         }
         copy_feature_row<TF, TB>(args.feat_cls, p.level, frame, p.local, args.feat_dim, reinterpret_cast<TB*>(args.bank_cls) + r, lane);
         copy_feature_row<TF, TB>(args.feat_reg, p.level, frame, p.local, args.feat_dim, reinterpret_cast<TB*>(args.bank_reg) + r, lane);

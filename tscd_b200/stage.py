@@ -368,9 +368,12 @@ class AggregationStage:
         #      the independent classification branch fills the rest of the GPU --------------------------------
         main = torch.cuda.current_stream()
         side = main if self.serialize else self._side_stream()
+        # agg_iou's cls output feeds the CAFM matching only.  Frames of <= 32 proposals match on the 16-bit GEMM outputs
+        # (tensor-core cost kernel, csrc/cafm.cu cafm_cost16_kernel): no fp32 copy is written at all
+        emb16 = kmax <= 32 and trace is None
         (iou_cls16, iou_cls32), (iou_reg16, iou_reg32) = aggregate.mca_forward(
             lay, w.agg_iou, bank_cls, bank_reg, bank_score, n_rows_dev, n_loc_dev, need_reg=True,
-            sim_thresh=cfg.sim_thresh, conf_sim_thresh=cfg.conf_sim_thresh, cls_out=(False, True), tag="agg_iou")   # cls: matching only (fp32)
+            sim_thresh=cfg.sim_thresh, conf_sim_thresh=cfg.conf_sim_thresh, cls_out=(kmax <= 32, not emb16), tag="agg_iou")
         ev_fork = torch.cuda.Event()
         ev_fork.record(main)
         with torch.cuda.stream(side):
@@ -401,7 +404,8 @@ class AggregationStage:
             resume = self._zero_resume[B]
         if before_cafm is not None:
             before_cafm(state)
-        cafm16, cafm32, perm, te32 = self.run_cafm(lay, bank_reg, bank_edge, iou_reg32, iou_cls32, time_embedding, kmax,
+        cafm16, cafm32, perm, te32 = self.run_cafm(lay, bank_reg, bank_edge, iou_reg16 if kmax <= 32 else iou_reg32,
+                                                   iou_cls16 if kmax <= 32 else iou_cls32, time_embedding, kmax,
                                                    state, resume, status, want_debug=trace is not None, debug=trace)
         if after_cafm is not None:
             after_cafm(state)
@@ -460,8 +464,13 @@ class AggregationStage:
     def run_cafm(self, lay: ops.AttnLayoutT, bank_reg, bank_edge, emb_reg32, emb_cls32, time_embedding, kmax: int,
                  state: CAFMState, resume: torch.Tensor, status: torch.Tensor, want_debug=False, debug: Optional[dict] = None):
         """CAFM (AwarePositionRegMatcher.forward, tscd_matching.py:722-888) for all clips of the batch.
-        emb_reg32 / emb_cls32 [loc_cap,1024] are the agg_iou outputs used for matching only."""
+        emb_reg32 / emb_cls32 [loc_cap,1024] are the agg_iou outputs used for matching only: fp32, or -- frames of <= 32
+        proposals -- the 16-bit GEMM outputs (fp32 tensors are rounded to the operand type then)."""
         w, dev, dt, D = self.w, self.device, self.cfg.dtype, self.cfg.dim
+        if kmax <= 32 and emb_reg32.dtype == torch.float32:
+            emb_reg32, emb_cls32 = emb_reg32.to(dt), emb_cls32.to(dt)
+        emb_dtype = emb_reg32.dtype
+        assert emb_cls32.dtype == emb_dtype and (emb_dtype == torch.float32 or kmax <= 32)
         B, F, Lf, loc_cap = lay.B, lay.F, lay.L, lay.loc_cap
         n_loc_dev = lay.lrow_off[-1:]
         te16 = time_embedding.to(device=dev, dtype=dt).contiguous()
@@ -479,7 +488,7 @@ class AggregationStage:
         ops.call("tscd_cafm_prep", L.CafmPrepArgs, B=B, F=F, L=Lf, D=D, bank_dtype=dt, row_off=lay.row_off,
                  lrow_off=lay.lrow_off, bank_reg=bank_reg, bank_edge=bank_edge, time_emb=te32, se_w1=w.se_w1,
                  se_w2=w.se_w2, emb_reg=emb_reg32, emb_cls=emb_cls32, feat=feat, edge=edge, feat16=feat16,
-                 kin16=kin16, kin=kin, norm_reg=norm_reg, norm_cls=norm_cls)
+                 kin16=kin16, kin=kin, norm_reg=norm_reg, norm_cls=norm_cls, emb_dtype=emb_dtype)
         kproj16, kproj = ops.linear(kin16, w.cafm_wk, m_dev=n_loc_dev, want16=fast, want32=not fast, tag="cafm_k")
         vproj16, vproj = ops.linear(feat16, w.cafm_wv, m_dev=n_loc_dev, want16=fast, want32=not fast, tag="cafm_v")
         cafm16 = torch.empty(loc_cap, D, dtype=dt, device=dev)
@@ -489,7 +498,8 @@ class AggregationStage:
         ref_n = torch.empty(B * Lf, dtype=torch.int32, device=dev)
         ops.call("tscd_cafm_cost", L.CafmCostArgs, B=B, L=Lf, D=D, kmax=kmax, lrow_off=lay.lrow_off, resume=resume,
                  st_n=state.n, emb_reg=emb_reg32, emb_cls=emb_cls32, norm_reg=norm_reg, norm_cls=norm_cls,
-                 st_reg=state.reg, st_cls=state.cls, st_nreg=state.nreg, st_ncls=state.ncls, cost=cost_full, ref_n=ref_n)
+                 st_reg=state.reg, st_cls=state.cls, st_nreg=state.nreg, st_ncls=state.ncls, cost=cost_full, ref_n=ref_n,
+                 emb_dtype=emb_dtype)
         lap_col = torch.empty(B * Lf, kmax, dtype=torch.int32, device=dev)
         lap_row = torch.empty(B * Lf, kmax, dtype=torch.int32, device=dev)
         ops.call("tscd_cafm_lap", L.CafmLapArgs, num_frames=B * Lf, kmax=kmax, lrow_off=lay.lrow_off, ref_n=ref_n, cost=cost_full,
@@ -503,7 +513,7 @@ class AggregationStage:
                  st_reg=state.reg, st_cls=state.cls, st_nreg=state.nreg, st_ncls=state.ncls, st_time=state.time,
                  sc_qin=None if fast else f32z(B, kmax, D), sc_q=None if fast else f32z(B, kmax, D),
                  sc_k=None if fast else f32z(B, kmax, D), ref_n=ref_n, lap_col=lap_col, lap_row=lap_row,
-                 out16=cafm16, out32=cafm32, perm=perm, status=status)
+                 out16=cafm16, out32=cafm32, perm=perm, status=status, emb_dtype=emb_dtype)
         if debug is not None:        # matching tables of every local frame (tests: LSAP exactness on the device's own costs)
             debug.update(cafm_cost=cost_full, cafm_ref_n=ref_n, cafm_lap_col=lap_col, cafm_lap_row=lap_row)
         return cafm16, cafm32, perm, te32
