@@ -506,6 +506,22 @@ typedef struct {
 } tscd_final_rows_args;
 int tscd_final_rows(const tscd_final_rows_args* args, void* stream);
 
+/* ---- evaluator / Predictor glue ---------------------------------------------------------------
+ * Replaces the per-frame .cpu() + per-box Python loops of OVISEvaluator.convert_to_coco_format
+ * (yolox/evaluators/ovis_evaluator_v2.py:233-289) and Predictor.to_repp_heavy (tools/val_to_imdb.py:193-218): all detections of
+ * all frames as ONE packed table (one device->host copy), already divided by the per-frame resize scale and converted to
+ * top-left + width / height:  packed row (12 floats) = [frame, x, y, w, h, obj * cls_score, class, obj, x2, y2, cls_score, 0];
+ * offsets[f] .. offsets[f+1] are frame f's rows (in NMS keep order). */
+typedef struct {
+    int32_t num_frames, cap;     /* frames; row pitch of `rows` per frame */
+    const float* rows;           /* [num_frames, cap, 7] stage output (x1,y1,x2,y2,obj,cls_score,cls) */
+    const int32_t* count;        /* [num_frames] */
+    const float* scale;          /* [num_frames] resize scale of every frame (boxes are DIVIDED by it), or NULL */
+    int32_t* offsets;            /* out [num_frames + 1] */
+    float* packed;               /* out [num_frames * cap, 12] */
+} tscd_pack_detections_args;
+int tscd_pack_detections(const tscd_pack_detections_args* args, void* stream);
+
 /* ---- long-clip mode: exchange of the global-frame bank rows between ranks ----------------------
  * One clip sharded by frame: every rank runs K1-K3 on its own frames [n_local_frames local | n_global_frames global], then the
  * ranks all-gather ONE packed buffer each (ncclAllGather, issued by the host) and every rank builds the virtual clip

@@ -413,7 +413,53 @@ __global__ void final_rows_kernel(const tscd_final_rows_args a) {
     }
 }
 
+// Evaluator / Predictor glue: every detection of every frame as ONE packed table, in the units the
+// reference's consumers compute per box in Python loops after a per-frame .cpu():
+//   OVISEvaluator.convert_to_coco_format (yolox/evaluators/ovis_evaluator_v2.py:233-289):  bboxes /= scale; xyxy2xywh;
+//   score = obj * cls_conf;   Predictor.to_repp_heavy (tools/val_to_imdb.py:193-218): output[:, :4] /= ratio, clipping to the image.
+// Row (12 floats) = [frame, x1/s, y1/s, (x2/s - x1/s), (y2/s - y1/s), obj * cls, class, obj, x2/s, y2/s, cls_score, 0]
+// (same operation order as the reference: divide, then subtract).
+__global__ void __launch_bounds__(1024) pack_offsets_kernel(int num_frames, int cap, const int32_t* count, int32_t* offsets) {
+    __shared__ int scan[40];
+    int carry = 0;
+    for (int f0 = 0; f0 < num_frames; f0 += blockDim.x) {
+        const int f = f0 + threadIdx.x;
+        const int c = f < num_frames ? min(count[f], cap) : 0;
+        int tot;
+        const int ex = block_excl_scan(c, scan, &tot);
+        if (f < num_frames) offsets[f] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) offsets[num_frames] = carry;
+}
+
+__global__ void pack_detections_kernel(const tscd_pack_detections_args a) {
+    const int f = blockIdx.x;
+    const int n = min(a.count[f], a.cap);
+    const int o = a.offsets[f];
+    const float s = a.scale ? a.scale[f] : 1.f;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const float* r = a.rows + ((int64_t)f * a.cap + j) * 7;
+        float* d = a.packed + (int64_t)(o + j) * 12;
+        const float x1 = __fdiv_rn(r[0], s), y1 = __fdiv_rn(r[1], s), x2 = __fdiv_rn(r[2], s), y2 = __fdiv_rn(r[3], s);
+        d[0] = (float)f; d[1] = x1; d[2] = y1; d[3] = __fsub_rn(x2, x1); d[4] = __fsub_rn(y2, y1);
+        d[5] = __fmul_rn(r[4], r[5]); d[6] = r[6]; d[7] = r[4];
+        d[8] = x2; d[9] = y2; d[10] = r[5]; d[11] = 0.f;
+    }
+}
+
 }  // namespace tscd
+
+extern "C" int tscd_pack_detections(const tscd_pack_detections_args* a, void* stream) {
+    using namespace tscd;
+    if (!a || a->num_frames <= 0 || a->cap <= 0 || !a->rows || !a->count || !a->offsets || !a->packed) return TSCD_ERR_INVALID_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    pack_offsets_kernel<<<1, 1024, 0, st>>>(a->num_frames, a->cap, a->count, a->offsets);
+    TSCD_CUDA_CHECK_LAUNCH();
+    pack_detections_kernel<<<a->num_frames, 128, 0, st>>>(*a);
+    TSCD_CUDA_CHECK_LAUNCH();
+    return TSCD_OK;
+}
 
 extern "C" int tscd_frame_attention(const tscd_frame_attention_args* a, void* stream) {
     using namespace tscd;
