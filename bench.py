@@ -73,6 +73,9 @@ CONFIGS = {
                      workload="gen-1 (YOLOV) 25cls, 32-frame clip @576x576, top-750 -> NMS0.75 -> 30 proposals/frame, MSA self-attention "
                               "over N=960 + linear_pred"),
 }
+SEAMS = {"rows": "S1 raw head logits in the drop-in head's fused layout (one 64 / 128-byte fp16 row [reg4|obj|cls C|pad] per anchor + "
+                  "dense objectness plane, tscd_pack_head) and channels_last fp16 feature planes",
+         "levels": "S1 raw per-level conv outputs, fp16, channels_last logits and features"}
 SWEEP_P, SWEEP_K = (300, 500, 750, 1000, 1500), (30, 50, 75, 100)
 
 
@@ -86,7 +89,7 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------- synthetic inputs
-def synth_s1(cfg, B, device, seed, pin=False, dtype=torch.float16, channels_last=True):
+def synth_s1(cfg, B, device, seed, pin=False, dtype=torch.float16, channels_last=True, layout="levels"):
     """Seam S1 tensors for B clips: per level reg [BF,4,H,W], obj [BF,1,H,W], cls [BF,C,H,W] logits and three feature planes
     [BF,256,H,W].  obj logits ~ N(obj_mean(frame), 2^2) (cfg['obj_means'] cycles over the frames of a clip: controls how many
     anchors pass the 0.001 filter in mode B), cls logits ~ N(-3, 2^2), dx,dy ~ U(-0.5,1.5), dw,dh ~ N(1, 0.7^2)."""
@@ -108,6 +111,14 @@ def synth_s1(cfg, B, device, seed, pin=False, dtype=torch.float16, channels_last
             for i in range(0, n, 64):       # chunked: bounds the fp32 temporary
                 t[i:i + 64] = torch.randn(min(64, n - i), D, h, w, generator=g, device=device).to(dtype)
             out[k].append(t)
+    if layout == "rows":       # the drop-in head's fused layout: one 64 / 128-byte row per anchor + dense objectness plane
+        from tscd_b200 import ops
+        packed = ops.pack_head(ops.HeadViews.from_levels(out["reg"], out["obj"], out["cls"], ops.AnchorSpec(HW)))
+        rows, objp = packed._keep
+        torch.cuda.synchronize()
+        for k in ("reg", "obj", "cls"):
+            del out[k]
+        out["rows"], out["objp"] = [rows], [objp]
     if pin:
         out = {k: [t.pin_memory() for t in v] for k, v in out.items()}
     return out
@@ -117,9 +128,12 @@ def nbytes(d):
     return sum(t.numel() * t.element_size() for v in d.values() for t in v)
 
 
-def views_of(inp, ops):
+def views_of(inp, ops, C=None):
     an = ops.AnchorSpec(HW)
-    head = ops.HeadViews.from_levels(inp["reg"], inp["obj"], inp["cls"], an)
+    if "rows" in inp:
+        head = ops.HeadViews.from_rows(inp["rows"][0], inp["objp"][0], an, C)
+    else:
+        head = ops.HeadViews.from_levels(inp["reg"], inp["obj"], inp["cls"], an)
     feats = tuple(ops.view_levels(inp[k]) for k in ("f_cls", "f_reg", "f_edge"))
     return head, feats
 
@@ -420,8 +434,8 @@ def run_ours(args, cfg, rank, world, local):
     nsets = max(2, args.sets)
     st, run = make_runner(cfg, dev)
     te = torch.cat([weights.timing_signal_1d(torch.arange(Lf), 256)] * B, 0).to(dev)
-    sets = [synth_s1(cfg, B, dev, seed=2024 + 100 * i + rank) for i in range(nsets)]
-    views = [views_of(s_, ops) for s_ in sets]
+    sets = [synth_s1(cfg, B, dev, seed=2024 + 100 * i + rank, layout=args.head_layout) for i in range(nsets)]
+    views = [views_of(s_, ops, C) for s_ in sets]
 
     def barrier():
         if world > 1:
@@ -530,7 +544,7 @@ def run_ours(args, cfg, rank, world, local):
             "config": {"workload": cfg["workload"], "name": args.config, "clips_per_gpu_per_step": clips_per_step,
                        "clips_per_graph_replay": B, "graph_replays_per_step": R, "input_sets": nsets,
                        "proposals_per_frame": {"min": min(counts), "mean": round(sum(counts) / len(counts), 1), "max": max(counts)},
-                       "seam": "S1 raw per-level conv outputs, fp16, channels_last logits and features (what the drop-in head's conv towers emit)",
+                       "seam": SEAMS[args.head_layout],
                        "l2": f"{nsets} rotating input sets of {inp_mib:.0f} MiB each (>> the 126 MB L2); no flush needed",
                        "parallelism": f"clip-parallel x{world}, no collective"},
             "clocks": clk, "gpu_launches": launches_per_replay * R * args.steps, "launch_mode": launch_mode,
@@ -560,8 +574,9 @@ def run_e2e(args, cfg, st, dev, rank, world, dist, barrier):
     from tscd_b200 import weights
     F, Lf = cfg["F"], cfg["L"]
     Be = args.e2e_clips or min(32, cfg["clips"])
-    dev_src = synth_s1(cfg, Be, dev, seed=99 + rank)
-    host = {k: [torch.empty(t.shape, dtype=t.dtype, pin_memory=True, memory_format=torch.channels_last).copy_(t) for t in v]
+    dev_src = synth_s1(cfg, Be, dev, seed=99 + rank, layout=args.head_layout)
+    host = {k: [(torch.empty(t.shape, dtype=t.dtype, pin_memory=True, memory_format=torch.channels_last) if t.dim() == 4 else
+                 torch.empty(t.shape, dtype=t.dtype, pin_memory=True)).copy_(t) for t in v]
             for k, v in dev_src.items()}
     del dev_src
     torch.cuda.empty_cache()
@@ -583,7 +598,19 @@ def run_e2e(args, cfg, st, dev, rank, world, dist, barrier):
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    # where a call spends its time: GPU time of the captured launch sequence (events around one replay) vs the whole call
+    gpu_ms = None
+    plans = getattr(st, "_host_plans", {})
+    if plans and list(plans.values())[-1]["graph"] is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record()
+        list(plans.values())[-1]["graph"].replay()
+        ev1.record()
+        torch.cuda.synchronize()
+        gpu_ms = ev0.elapsed_time(ev1)
     return {"value": world * Be * F * e2e_steps / e2e_s, "unit": "clip-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_call": 1e3 * e2e_s / e2e_steps, "gpu_ms_per_call": gpu_ms,
             "clips_per_gpu_per_step": Be, "chunk_clips": args.e2e_chunk, "steps": e2e_steps,
             "host_resident_input_bytes_per_step": nbytes(host),
             "note": "inputs are pinned HOST tensors; h2d counts the copied logits plus the rows read in place over PCIe"}
@@ -625,6 +652,8 @@ def main():
     ap.add_argument("--e2e-clips", type=int, default=0)
     ap.add_argument("--e2e-chunk", type=int, default=8, help="clips per pipelined chunk of the host-buffer path")
     ap.add_argument("--cpu-clips", type=int, default=6, help="clips timed for cpu_baseline (rank 0, N=1)")
+    ap.add_argument("--head-layout", default="rows", choices=["rows", "levels"],
+                    help="rows: fused 64-byte head rows + objectness plane (what the drop-in head emits); levels: per-level channels_last conv outputs")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / reference-gpu legs")

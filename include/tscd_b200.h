@@ -101,6 +101,32 @@ typedef struct {
 } tscd_select_args;
 int tscd_select(const tscd_select_args* args, void* stream);
 
+/* ---- head pack: the FUSED head layout (conv-tower seam) ---------------------------------------
+ * Replaces the flatten / cat / permute copies of tscd_head.py:374-376 (outputs -> [F, A, 5+C]) with ONE pass that
+ * writes, per anchor, a single aligned row  [reg 4 | obj 1 | cls C | zero pad]  of `row_pitch` fp16 elements (32 = 64
+ * bytes for C <= 27, 64 = 128 bytes for C <= 59) plus the objectness logits once more as a dense [F, obj_pitch] plane.
+ * tscd_select / tscd_gather recognise this layout from the views (reg.ptr + 5 == cls.ptr, anchor stride == row_pitch,
+ * chan stride 1) and take the row kernels of csrc/select_rows.cu: the selection streams only the 2-byte objectness plane
+ * and fetches the survivors' rows as whole 64-byte sectors (from device memory or, for forward_host, in place from
+ * pinned host memory). Values are copied bit-for-bit (logits stay logits; sigmoid / decode remain fused in K1 / K3). */
+typedef struct {
+    int32_t num_frames;
+    int32_t num_classes;
+    int32_t head_dtype;       /* TSCD_F16 */
+    int32_t row_pitch;        /* 32 or 64 elements */
+    int64_t obj_pitch;        /* elements per frame of obj_plane, >= A */
+    tscd_anchors anchors;
+    tscd_view reg, obj, cls;  /* inputs: 4, 1 and C channels, any strided layout */
+    void* rows;               /* out [num_frames, A, row_pitch] fp16, 16-byte aligned */
+    void* obj_plane;          /* out [num_frames, obj_pitch] fp16 */
+} tscd_pack_head_args;
+int tscd_pack_head(const tscd_pack_head_args* args, void* stream);
+
+/* Test hook: canonical 16-bit selection key (csrc/select_rows.cu canon_key16) and fp32 score of n fp16 bit patterns.
+ * tests/test_gpu_selection.py runs it over all 65536 patterns to prove that ordering by key == ordering by score. */
+int tscd_debug_select_keys(const unsigned short* half_bits, int n, int apply_sigmoid, unsigned short* key, float* score,
+                           void* stream);
+
 /* ---- K2: class-aware batched NMS ---------------------------------------------------------------------
  * Replaces torchvision.ops.batched_nms (coordinate trick + nms) at tscd_head.py:1630,
  * post_process.py:58,73,510.  Keep lists are positions into the candidate arrays in descending-score order
@@ -521,6 +547,18 @@ typedef struct {
     float* packed;               /* out [num_frames * cap, 12] */
 } tscd_pack_detections_args;
 int tscd_pack_detections(const tscd_pack_detections_args* args, void* stream);
+
+/* Raw variant for the host-buffer entry (AggregationStage.forward_host): the stage's padded [num_frames, cap, 7] detection rows
+ * compacted frame after frame into packed [sum n, 7] (+ offsets), so the host reads only the valid rows of ONE buffer and
+ * splits it into the reference's list[Tensor[n,7]] (post_process.py:12-13,85) without a per-frame copy. */
+typedef struct {
+    int32_t num_frames, cap;
+    const float* rows;           /* [num_frames, cap, 7] */
+    const int32_t* count;        /* [num_frames] */
+    int32_t* offsets;            /* out [num_frames + 1] */
+    float* packed;               /* out [num_frames * cap, 7] */
+} tscd_pack_rows_args;
+int tscd_pack_rows(const tscd_pack_rows_args* args, void* stream);
 
 /* ---- long-clip mode: exchange of the global-frame bank rows between ranks ----------------------
  * One clip sharded by frame: every rank runs K1-K3 on its own frames [n_local_frames local | n_global_frames global], then the

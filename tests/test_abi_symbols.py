@@ -26,7 +26,7 @@ def test_struct_sizes_match_header():
     import subprocess
     import tempfile
     from tscd_b200 import _lib
-    pairs = [("tscd_view", _lib.View), ("tscd_anchors", _lib.Anchors), ("tscd_select_args", _lib.SelectArgs),
+    pairs = [("tscd_view", _lib.View), ("tscd_anchors", _lib.Anchors), ("tscd_select_args", _lib.SelectArgs), ("tscd_pack_head_args", _lib.PackHeadArgs),
              ("tscd_nms_args", _lib.NmsArgs), ("tscd_gather_args", _lib.GatherArgs), ("tscd_linear_args", _lib.LinearArgs),
              ("tscd_attn_layout", _lib.AttnLayout), ("tscd_attn_prep_args", _lib.AttnPrepArgs),
              ("tscd_attn_pv_args", _lib.AttnPvArgs), ("tscd_attn_round2_args", _lib.AttnRound2Args),
@@ -35,7 +35,8 @@ def test_struct_sizes_match_header():
              ("tscd_final_expand_args", _lib.FinalExpandArgs), ("tscd_final_rows_args", _lib.FinalRowsArgs),
              ("tscd_bank_pack_args", _lib.BankPackArgs), ("tscd_bank_unpack_args", _lib.BankUnpackArgs),
              ("tscd_qkv_project_args", _lib.QkvProjectArgs), ("tscd_attn_rowmeta_args", _lib.AttnRowmetaArgs),
-             ("tscd_local_offsets_args", _lib.LocalOffsetsArgs)]
+             ("tscd_local_offsets_args", _lib.LocalOffsetsArgs), ("tscd_pack_rows_args", _lib.PackRowsArgs),
+             ("tscd_pack_detections_args", _lib.PackDetectionsArgs)]
     body = "".join(f'printf("%zu\\n", sizeof({c}));' for c, _ in pairs)
     src = '#include <stdio.h>\n#include "tscd_b200.h"\nint main(){' + body + 'return 0;}'
     with tempfile.TemporaryDirectory() as d:

@@ -26,16 +26,23 @@ def _synth(B, seed, logits_cl=False):
     return out
 
 
-@pytest.mark.parametrize("logits_cl", [False, True])
+@pytest.mark.parametrize("graph", [True, False])
+@pytest.mark.parametrize("logits_cl", [False, True, "rows"])
 @pytest.mark.parametrize("B,chunk", [(5, 2), (4, 4)])
-def test_forward_host_equals_forward(B, chunk, logits_cl):
+def test_forward_host_equals_forward(B, chunk, logits_cl, graph):
     from tscd_b200 import ops, selection, stage, weights
     cfg = stage.StageConfig(num_classes=C, selection=selection.SelectionConfig(mode="A", pre_k=200, top_k=12, nms_thresh=0.75))
     st = stage.AggregationStage(cfg, weights.random_state_dict(C, D, seed=5))
-    dev = _synth(B, 31, logits_cl)
+    dev = _synth(B, 31, logits_cl is True)
     host = {k: [torch.empty(t.shape, dtype=t.dtype, pin_memory=True,
-                                memory_format=torch.channels_last if (k.startswith("f_") or logits_cl) else torch.contiguous_format).copy_(t) for t in v]
+                                memory_format=torch.channels_last if (k.startswith("f_") or logits_cl is True) else torch.contiguous_format).copy_(t) for t in v]
         for k, v in dev.items()}
+    if logits_cl == "rows":          # the drop-in head's fused layout: rows read in place over PCIe, objectness plane copied
+        packed = ops.pack_head(ops.HeadViews.from_levels(dev["reg"], dev["obj"], dev["cls"], ops.AnchorSpec(HW)))
+        torch.cuda.synchronize()
+        for k in ("reg", "obj", "cls"):
+            del host[k]
+        host["rows"], host["objp"] = [packed._keep[0].cpu().pin_memory()], [packed._keep[1].cpu().pin_memory()]
     te = torch.cat([weights.timing_signal_1d(torch.arange(LF), 256)] * B, 0)
 
     an = ops.AnchorSpec(HW)
@@ -54,7 +61,7 @@ def test_forward_host_equals_forward(B, chunk, logits_cl):
     del head, feats
 
     for _ in range(2):       # twice: staging buffers are reused across calls
-        res, res_ori, h2d, d2h = st.forward_host(host, HW, te.pin_memory(), B, F, LF, chunk_clips=chunk)
+        res, res_ori, h2d, d2h = st.forward_host(host, HW, te.pin_memory(), B, F, LF, chunk_clips=chunk, graph=graph)
         assert len(res) == B * LF and len(res_ori) == B * LF
         n_det = 0
         for (wr, wo), gr, go in zip(want, res, res_ori):
@@ -65,13 +72,18 @@ def test_forward_host_equals_forward(B, chunk, logits_cl):
             assert torch.equal(gr, wr.cpu()) and torch.equal(go, wo.cpu())
             n_det += len(gr)
         assert n_det > 0
-        head_bytes = sum(t.numel() * t.element_size() for k in ("reg", "obj", "cls") for t in host[k])
         feat_bytes = sum(t.numel() * t.element_size() for k in ("f_cls", "f_reg", "f_edge") for t in host[k])
-        assert head_bytes < h2d < head_bytes + feat_bytes // 4      # only the kept rows of the feature planes crossed PCIe
+        if logits_cl == "rows":
+            head_bytes = sum(t.numel() * t.element_size() for t in host["objp"])
+            rows_bytes = sum(t.numel() * t.element_size() for t in host["rows"])
+            assert head_bytes < h2d < head_bytes + rows_bytes // 2 + feat_bytes // 4   # 200 of 756 rows + the kept feature rows
+        else:
+            head_bytes = sum(t.numel() * t.element_size() for k in ("reg", "obj", "cls") for t in host[k])
+            assert head_bytes < h2d < head_bytes + feat_bytes // 4      # only the kept rows of the feature planes crossed PCIe
         assert d2h > 0
-    if logits_cl:
+    if logits_cl is True:
         # optional mode: only the objectness plane is copied, K1 / K3 read the survivors' class / regression rows in place
-        res2, ori2, h2d_zc, _ = st.forward_host(host, HW, te.pin_memory(), B, F, LF, chunk_clips=chunk, zero_copy_logits=True)
+        res2, ori2, h2d_zc, _ = st.forward_host(host, HW, te.pin_memory(), B, F, LF, chunk_clips=chunk, zero_copy_logits=True, graph=graph)
         assert h2d_zc < h2d
         for gr, go, g2, o2 in zip(res, res_ori, res2, ori2):
             assert (gr is None) == (g2 is None)

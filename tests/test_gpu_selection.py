@@ -266,15 +266,17 @@ def test_empty_frames_and_small_anchor_sets():
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.float16])
 @pytest.mark.parametrize("mode", ["A", "B"])
-@pytest.mark.parametrize("logits_cl", [False, True])
+@pytest.mark.parametrize("logits_cl", [False, True, "rows"])
 def test_selection_seam_s1_raw_level_outputs(dt, mode, logits_cl):
     """Production seam S1: raw per-level logits; sigmoid + decode fused into the kernels.  The reference runs this stage on
     CUDA (tools/tscd_eval.py), where ATen evaluates sigmoid as 1 / (1 + exp(-x)) and exp with the CUDA math library -- the
     expressions the kernels use (csrc/common.cuh sigmoidf_ref, anchor_box).  The oracle is therefore fed sigmoid / exp values
     computed by torch ON THE GPU (everything else on the CPU as usual) and the selected ids and rows must be IDENTICAL."""
     ops, selection = _stage_mods()
+    if logits_cl == "rows" and dt != torch.float16:
+        pytest.skip("fused head rows are fp16")
     hw = [(72, 72), (36, 36), (18, 18)]
-    C, Fn = 25, 4
+    C, Fn = 25, 5                                    # odd frame count: the [F, A] objectness plane of odd frames is only 8-byte aligned
     g = torch.Generator().manual_seed(31)
     reg, obj, cls, fused = [], [], [], []
     for (h, w) in hw:
@@ -299,9 +301,21 @@ def test_selection_seam_s1_raw_level_outputs(dt, mode, logits_cl):
     an = ops.AnchorSpec(hw)
     # logits_cl: channels_last head outputs (class-contiguous: mode A computes the class max for the survivors only);
     # otherwise PyTorch's default NCHW planes (streaming class-max kernel in mode A)
-    fmt = torch.channels_last if logits_cl else torch.contiguous_format
+    fmt = torch.channels_last if logits_cl is True else torch.contiguous_format
     head = ops.HeadViews.from_levels([t.cuda().contiguous(memory_format=fmt) for t in reg], [t.cuda().contiguous(memory_format=fmt) for t in obj],
                                      [t.cuda().contiguous(memory_format=fmt) for t in cls], an)
+    if logits_cl == "rows":
+        # the fused layout of the drop-in head (tscd_pack_head): one 64-byte row per anchor + dense objectness plane; the
+        # candidate lists (all 750 in mode A) must equal the per-level path's bit for bit
+        packed = ops.pack_head(head, obj=torch.empty(Fn, an.num_anchors, dtype=torch.float16, device="cuda"))
+        kw = dict(pre_k=750) if mode == "A" else dict(minimal_limit=50, maximal_limit=500)
+        c0, c1 = ops.select(head, mode, **kw), ops.select(packed, mode, **kw)
+        assert torch.equal(c0["count"], c1["count"])
+        for f in range(Fn):
+            n = int(c0["count"][f])
+            for k in ("idx", "box", "score", "cls"):
+                assert torch.equal(c0[k][f, :n], c1[k][f, :n]), (f, k)
+        head = packed
     feats = [[torch.randn(Fn, 32, h, w).cuda() for (h, w) in hw] for _ in range(3)]
     sel = selection.select_and_gather(head, tuple(ops.view_levels(f) for f in feats), torch.float32, 32, cfg,
                                       bank_dtype=torch.float32)
@@ -310,6 +324,73 @@ def test_selection_seam_s1_raw_level_outputs(dt, mode, logits_cl):
     for f in range(Fn):
         assert idxs[f].cpu().tolist() == o_idx[f].tolist(), f"frame {f}"
         assert torch.equal(rows[f].cpu(), o_rows[f]), f"frame {f}: rows differ by {(rows[f].cpu() - o_rows[f]).abs().max()}"
+
+
+def test_selection_keys_order_like_scores_exhaustive():
+    """csrc/select_rows.cu ranks anchors by a canonical 16-bit key of the fp16 objectness logit instead of the fp32 sigmoid.
+    Exhaustive proof over every non-NaN fp16 value: the sigmoid the kernels use is monotone, and two values get the same key
+    exactly when they get the same fp32 score -- so ordering (and tie sets) by key == ordering by score."""
+    import ctypes
+    from tscd_b200 import _lib
+    bits = torch.arange(65536, dtype=torch.int32)
+    is_nan = ((bits & 0x7c00) == 0x7c00) & ((bits & 0x3ff) != 0)
+    bits = bits[~is_nan]
+    hb = bits.to(torch.int16).cuda()          # low 16 bits (two's complement wrap keeps the pattern)
+    n = hb.numel()
+    for sig in (1, 0):
+        key = torch.empty(n, dtype=torch.int16, device="cuda")
+        score = torch.empty(n, dtype=torch.float32, device="cuda")
+        _lib.check(_lib.lib().tscd_debug_select_keys(ctypes.c_void_p(hb.data_ptr()), n, sig, ctypes.c_void_p(key.data_ptr()),
+                                                      ctypes.c_void_p(score.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "tscd_debug_select_keys")
+        k = (key.cpu().to(torch.int32) & 0xffff).numpy()
+        sc = score.cpu().numpy().astype(np.float64)
+        vals = hb.cpu().view(torch.float16).float().numpy().astype(np.float64)
+        order = np.lexsort((k, vals))                      # ascending fp16 value
+        k, sc = k[order], sc[order]
+        assert np.all(np.diff(sc) >= 0), "the score function must be monotone in the fp16 input"
+        assert np.all(np.diff(k) >= 0), "keys must be monotone in the fp16 input"
+        same_k, same_s = np.diff(k) == 0, np.diff(sc) == 0
+        bad = np.nonzero(same_k != same_s)[0]
+        assert bad.size == 0, f"equal key <=> equal fp32 score violated at fp16 values {np.sort(vals)[bad[:8]]} (sig={sig})"
+        if sig:                                            # the device sigmoid is ATen-CUDA's (what the reference evaluates)
+            ref = torch.sigmoid(hb.view(torch.float16).float()).cpu().numpy().astype(np.float64)[order]
+            assert np.array_equal(ref, sc)
+            assert int(same_s.sum()) > 1000                # saturation plateaus exist and are handled
+
+
+@pytest.mark.parametrize("C", [25, 30])
+def test_select_fused_rows_saturation_and_wide_rows(C):
+    """Fused-row kernel: saturated objectness logits (equal fp32 scores of different logits -> anchor order), 128-byte rows
+    (30 classes), candidate lists identical to the per-level kernel's."""
+    ops, _ = _stage_mods()
+    hw = [(72, 72), (36, 36), (18, 18)]
+    Fn = 3
+    g = torch.Generator().manual_seed(78 + C)
+    an = ops.AnchorSpec(hw)
+    reg, obj, cls = [], [], []
+    for (h, w) in hw:
+        reg.append(torch.cat([torch.rand(Fn, 2, h, w, generator=g), torch.randn(Fn, 2, h, w, generator=g) * 0.5], 1).half())
+        o = torch.randn(Fn, 1, h, w, generator=g) * 2 - 3
+        sat = torch.rand(Fn, 1, h, w, generator=g) < 0.045
+        vals = torch.tensor([12.0, 17.0, 18.0, 19.0, 20.0, 25.0, 60000.0])[torch.randint(0, 7, (Fn, 1, h, w), generator=g)]
+        o = torch.where(sat, vals, o)
+        o[:, :, 0, :4] = torch.tensor([0.0, -0.0, 0.0, -0.0])              # +-0: equal scores, different bit patterns
+        obj.append(o.half())
+        cls.append((torch.randn(Fn, C, h, w, generator=g) * 2 - 3).half())
+    head = ops.HeadViews.from_levels([t.cuda() for t in reg], [t.cuda() for t in obj], [t.cuda() for t in cls], an)
+    packed = ops.pack_head(head)
+    assert packed.reg.anchor_stride[0] == (32 if C == 25 else 64)
+    for pre_k in (750, 300, 1500):
+        c0, c1 = ops.select(head, "A", pre_k=pre_k), ops.select(packed, "A", pre_k=pre_k)
+        torch.cuda.synchronize()
+        assert c1["count"].cpu().tolist() == [pre_k] * Fn
+        for k in ("idx", "box", "score", "cls"):
+            assert torch.equal(c0[k], c1[k]), (pre_k, k)
+    flat_obj = torch.cat([o.flatten(1) for o in obj], 1).float()
+    for f in range(Fn):
+        want = oracle.topk_lower_index_first(torch.sigmoid(flat_obj[f].cuda()).cpu(), 1500).tolist()
+        assert c1["idx"][f].cpu().tolist() == want
 
 
 def test_select_mode_a_sigmoid_saturation_ties():

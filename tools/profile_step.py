@@ -20,6 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="ovis_a_k30", choices=list(bench.CONFIGS))
     ap.add_argument("--clips", type=int, default=0)
+    ap.add_argument("--head-layout", default="rows", choices=["rows", "levels"])
     args = ap.parse_args()
     from tscd_b200 import ops, weights
     cfg = bench.CONFIGS[args.config]
@@ -27,8 +28,8 @@ def main():
     B = args.clips or cfg["clips"]
     st, run = bench.make_runner(cfg, dev)
     st.serialize = True
-    inp = bench.synth_s1(cfg, B, dev, seed=2024)
-    views = bench.views_of(inp, ops)
+    inp = bench.synth_s1(cfg, B, dev, seed=2024, layout=args.head_layout)
+    views = bench.views_of(inp, ops, cfg["C"])
     te = torch.cat([weights.timing_signal_1d(torch.arange(cfg["L"]), 256)] * B, 0).to(dev)
     for _ in range(2):
         out = run(views, B, te)

@@ -33,6 +33,12 @@ class SelectArgs(C.Structure):
                 ("ws_conf", C.c_void_p), ("ws_cls", C.c_void_p), ("ws_pitch", C.c_int32), ("status", C.c_void_p)]
 
 
+class PackHeadArgs(C.Structure):
+    _fields_ = [("num_frames", C.c_int32), ("num_classes", C.c_int32), ("head_dtype", C.c_int32), ("row_pitch", C.c_int32),
+                ("obj_pitch", C.c_int64), ("anchors", Anchors), ("reg", View), ("obj", View), ("cls", View),
+                ("rows", C.c_void_p), ("obj_plane", C.c_void_p)]
+
+
 class NmsArgs(C.Structure):
     _fields_ = [("num_frames", C.c_int32), ("cand_cap", C.c_int32), ("max_keep", C.c_int32), ("iou_thresh", C.c_float),
                 ("box", C.c_void_p), ("score", C.c_void_p), ("cls", C.c_void_p), ("count", C.c_void_p),
@@ -170,6 +176,10 @@ class PackDetectionsArgs(C.Structure):
     _fields_ = _fields("num_frames:i cap:i rows:p count:p scale:p offsets:p packed:p")
 
 
+class PackRowsArgs(C.Structure):
+    _fields_ = _fields("num_frames:i cap:i rows:p count:p offsets:p packed:p")
+
+
 _lib = None
 
 # every symbol include/tscd_b200.h declares: (name, restype, argtypes)
@@ -178,6 +188,8 @@ SYMBOLS = [
     ("tscd_device_ok", C.c_int, []),
     ("tscd_last_cuda_error", C.c_char_p, []),
     ("tscd_select", C.c_int, [C.POINTER(SelectArgs), C.c_void_p]),
+    ("tscd_pack_head", C.c_int, [C.POINTER(PackHeadArgs), C.c_void_p]),
+    ("tscd_debug_select_keys", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("tscd_nms", C.c_int, [C.POINTER(NmsArgs), C.c_void_p]),
     ("tscd_nms_workspace_bytes", C.c_int64, [C.c_int32, C.c_int32]),
     ("tscd_gather", C.c_int, [C.POINTER(GatherArgs), C.c_void_p]),
@@ -199,6 +211,7 @@ SYMBOLS = [
     ("tscd_final_expand", C.c_int, [C.POINTER(FinalExpandArgs), C.c_void_p]),
     ("tscd_final_rows", C.c_int, [C.POINTER(FinalRowsArgs), C.c_void_p]),
     ("tscd_pack_detections", C.c_int, [C.POINTER(PackDetectionsArgs), C.c_void_p]),
+    ("tscd_pack_rows", C.c_int, [C.POINTER(PackRowsArgs), C.c_void_p]),
     ("tscd_bank_pack_bytes", C.c_int64, [C.c_int32, C.c_int32]),
     ("tscd_bank_pack", C.c_int, [C.POINTER(BankPackArgs), C.c_void_p]),
     ("tscd_bank_unpack", C.c_int, [C.POINTER(BankUnpackArgs), C.c_void_p]),
@@ -224,7 +237,7 @@ def lib():
 
 # kernels launched per C-ABI call (for the bench's `gpu_launches` claim)
 _DEBUG_SYNC = os.environ.get("TSCD_DEBUG_SYNC", "0") == "1"
-KERNELS_PER_CALL = {"tscd_gather": 2, "tscd_nms_large": 3, "tscd_bank_unpack": 2, "tscd_pack_detections": 2}
+KERNELS_PER_CALL = {"tscd_gather": 2, "tscd_nms_large": 3, "tscd_bank_unpack": 2, "tscd_pack_detections": 2, "tscd_pack_rows": 2}
 launch_count = 0
 # optional per-entry-point CUDA-event timing: {"names": set or None (= all), "events": {name: [(start, end), ...]}}
 profile = None

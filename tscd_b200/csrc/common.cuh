@@ -269,11 +269,8 @@ __device__ __forceinline__ const T* view_ptr(const tscd_view& v, int level, int 
 
 // Box of one anchor as the reference computes it: decode_outputs (tscd_head.py:768-769) then
 // cxcywh->xyxy (tscd_head.py:1561-1566).  Explicit round-to-nearest ops: no FMA contraction.
-template <typename T>
-__device__ __forceinline__ float4 anchor_box(const tscd_view& reg, const AnchorPos& p, int frame, bool decode) {
-    const T* r = view_ptr<T>(reg, p.level, frame, p.local);
-    const int64_t cs = reg.chan_stride[p.level];
-    float cx = ldf(r), cy = ldf(r + cs), w = ldf(r + 2 * cs), h = ldf(r + 3 * cs);
+// cxcywh regression outputs of one anchor -> xyxy box, with explicit round-to-nearest ops (no FMA contraction)
+__device__ __forceinline__ float4 box_from_reg(float cx, float cy, float w, float h, const AnchorPos& p, bool decode) {
     if (decode) {
         cx = __fmul_rn(__fadd_rn(cx, p.gx), p.stride);
         cy = __fmul_rn(__fadd_rn(cy, p.gy), p.stride);
@@ -283,5 +280,17 @@ __device__ __forceinline__ float4 anchor_box(const tscd_view& reg, const AnchorP
     float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);  // w/2 is exact either way
     return make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
 }
+
+template <typename T>
+__device__ __forceinline__ float4 anchor_box(const tscd_view& reg, const AnchorPos& p, int frame, bool decode) {
+    const T* r = view_ptr<T>(reg, p.level, frame, p.local);
+    const int64_t cs = reg.chan_stride[p.level];
+    return box_from_reg(ldf(r), ldf(r + cs), ldf(r + 2 * cs), ldf(r + 3 * cs), p, decode);
+}
+
+// csrc/select_rows.cu: the fused [reg4|obj|cls C|pad] row layout (row pitch in elements, or 0) and its mode-A kernel
+int fused_rows_pitch(const tscd_anchors& an, const tscd_view& reg, const tscd_view& obj, const tscd_view& cls, int num_classes,
+                     int head_dtype, bool need_flat_obj);
+int select_rows_try(const tscd_select_args* a, cudaStream_t st);
 
 }  // namespace tscd

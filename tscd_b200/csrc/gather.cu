@@ -71,8 +71,9 @@ __device__ __forceinline__ void copy_feature_row(const tscd_view& v, int level, 
     }
 }
 
+// rp: row pitch (elements) of the fused head layout (csrc/select_rows.cu), 0 = generic strided views
 template <typename TF, typename TB>
-__global__ void __launch_bounds__(256) rows_gather_kernel(const tscd_gather_args args) {
+__global__ void __launch_bounds__(256) rows_gather_kernel(const tscd_gather_args args, int rp) {
     const int frame = blockIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int n = args.sel_count[frame];
@@ -104,18 +105,49 @@ __global__ void __launch_bounds__(256) rows_gather_kernel(const tscd_gather_args
             }
         }
         // class scores + arg-max (first maximum)
-        const int64_t cbase = (int64_t)frame * args.cls.frame_stride[p.level] + (int64_t)p.local * args.cls.anchor_stride[p.level];
         float best = -INFINITY;
         int bi = 0x7fffffff;
-        float obj_raw = 0.f;
-        if (lane == 0)
-            obj_raw = ld_any(args.obj.ptr[p.level], hd,
-                             (int64_t)frame * args.obj.frame_stride[p.level] + (int64_t)p.local * args.obj.anchor_stride[p.level]);
-        for (int c = lane; c < C; c += 32) {
-            float v = ld_any(args.cls.ptr[p.level], hd, cbase + c * args.cls.chan_stride[p.level]);
-            if (args.apply_sigmoid) v = sigmoidf_ref(v);
-            row[7 + c] = v;
-            if (v > best) { best = v; bi = c; }
+        float obj_raw = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+        if (rp) {
+            // fused layout: the anchor's whole head output is one aligned 64 / 128-byte row -> ONE coalesced load instruction
+            // (a single PCIe read when the rows live in pinned host memory), elements handed around with shuffles
+            const __half* rowp = reinterpret_cast<const __half*>(args.reg.ptr[p.level]) + (int64_t)frame * args.reg.frame_stride[p.level] +
+                                 (int64_t)p.local * rp;
+            float h0, h1 = 0.f;
+            if (rp == 32) {
+                h0 = __half2float(__ldg(rowp + lane));
+            } else {
+                const __half2 t = __ldg(reinterpret_cast<const __half2*>(rowp) + lane);
+                h0 = __low2float(t);
+                h1 = __high2float(t);
+            }
+            auto elem = [&](int e) -> float {                 // element e of the row (e may differ per lane)
+                if (rp == 32) return __shfl_sync(0xffffffffu, h0, e & 31);
+                const float a0 = __shfl_sync(0xffffffffu, h0, (e >> 1) & 31), a1 = __shfl_sync(0xffffffffu, h1, (e >> 1) & 31);
+                return (e & 1) ? a1 : a0;
+            };
+            r0 = elem(0); r1 = elem(1); r2 = elem(2); r3 = elem(3);
+            obj_raw = elem(4);
+            for (int c0 = 0; c0 < C; c0 += 32) {              // uniform trip count: the shuffles need the whole warp
+                const int c = c0 + lane;
+                float v = elem(5 + (c < C ? c : 0));
+                if (c < C) {
+                    if (args.apply_sigmoid) v = sigmoidf_ref(v);
+                    row[7 + c] = v;
+                    if (v > best) { best = v; bi = c; }
+                }
+            }
+        } else {
+            const int64_t cbase = (int64_t)frame * args.cls.frame_stride[p.level] + (int64_t)p.local * args.cls.anchor_stride[p.level];
+            if (lane == 0)
+                obj_raw = ld_any(args.obj.ptr[p.level], hd,
+                                 (int64_t)frame * args.obj.frame_stride[p.level] + (int64_t)p.local * args.obj.anchor_stride[p.level]);
+            for (int c = lane; c < C; c += 32) {
+                float v = ld_any(args.cls.ptr[p.level], hd, cbase + c * args.cls.chan_stride[p.level]);
+                if (args.apply_sigmoid) v = sigmoidf_ref(v);
+                row[7 + c] = v;
+                if (v > best) { best = v; bi = c; }
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -126,8 +158,9 @@ __global__ void __launch_bounds__(256) rows_gather_kernel(const tscd_gather_args
         if (lane == 0) {
             float obj = obj_raw;
             if (args.apply_sigmoid) obj = sigmoidf_ref(obj);
-            float4 box = (hd == TSCD_F32) ? anchor_box<float>(args.reg, p, frame, args.apply_decode != 0)
-                                          : anchor_box<__half>(args.reg, p, frame, args.apply_decode != 0);
+            float4 box = rp ? box_from_reg(r0, r1, r2, r3, p, args.apply_decode != 0)
+                            : ((hd == TSCD_F32) ? anchor_box<float>(args.reg, p, frame, args.apply_decode != 0)
+                                                : anchor_box<__half>(args.reg, p, frame, args.apply_decode != 0));
             row[0] = box.x; row[1] = box.y; row[2] = box.z; row[3] = box.w;
             row[4] = obj; row[5] = best; row[6] = (float)bi;
             args.sel_idx[(int64_t)frame * args.max_keep + j] = a;
@@ -150,10 +183,11 @@ __global__ void __launch_bounds__(256) rows_gather_kernel(const tscd_gather_args
 
 template <typename TF>
 static int launch_gather_tb(const tscd_gather_args* a, dim3 grid, cudaStream_t st) {
+    const int rp = fused_rows_pitch(a->anchors, a->reg, a->obj, a->cls, a->num_classes, a->head_dtype, false);
     switch (a->bank_dtype) {
-        case TSCD_F32: rows_gather_kernel<TF, float><<<grid, 256, 0, st>>>(*a); break;
-        case TSCD_F16: rows_gather_kernel<TF, __half><<<grid, 256, 0, st>>>(*a); break;
-        case TSCD_BF16: rows_gather_kernel<TF, __nv_bfloat16><<<grid, 256, 0, st>>>(*a); break;
+        case TSCD_F32: rows_gather_kernel<TF, float><<<grid, 256, 0, st>>>(*a, rp); break;
+        case TSCD_F16: rows_gather_kernel<TF, __half><<<grid, 256, 0, st>>>(*a, rp); break;
+        case TSCD_BF16: rows_gather_kernel<TF, __nv_bfloat16><<<grid, 256, 0, st>>>(*a, rp); break;
         default: return TSCD_ERR_UNSUPPORTED;
     }
     return TSCD_OK;

@@ -389,6 +389,10 @@ extern "C" int tscd_select(const tscd_select_args* a, void* stream) {
     if (a->num_classes > 255) return TSCD_ERR_UNSUPPORTED;
     const int selcap = ((A < a->cand_cap ? A : a->cand_cap) + 3) & ~3;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    {   // fused 64 / 128-byte rows + dense objectness plane (the drop-in head's layout): csrc/select_rows.cu
+        const int rc = select_rows_try(a, st);
+        if (rc != 0) return rc < 0 ? rc : TSCD_OK;
+    }
     // mode A with a workspace and planar (anchor-contiguous) class planes: class max as a separate streaming kernel
     // mode A needs the class max of the ~pre_k survivors only.  Class-contiguous logits (channels_last conv outputs: an
     // anchor's C logits are one 2C-byte row) are therefore read for the survivors alone -- 89 % of the class logits never

@@ -448,7 +448,27 @@ __global__ void pack_detections_kernel(const tscd_pack_detections_args a) {
     }
 }
 
+// raw variant: the [n,7] rows themselves, frame after frame (forward_host's single read-back)
+__global__ void pack_rows_kernel(const tscd_pack_rows_args a) {
+    const int f = blockIdx.x;
+    const int n = min(a.count[f], a.cap);
+    const float* src = a.rows + (int64_t)f * a.cap * 7;
+    float* dst = a.packed + (int64_t)a.offsets[f] * 7;
+    for (int j = threadIdx.x; j < n * 7; j += blockDim.x) dst[j] = src[j];
+}
+
 }  // namespace tscd
+
+extern "C" int tscd_pack_rows(const tscd_pack_rows_args* a, void* stream) {
+    using namespace tscd;
+    if (!a || a->num_frames <= 0 || a->cap <= 0 || !a->rows || !a->count || !a->offsets || !a->packed) return TSCD_ERR_INVALID_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    pack_offsets_kernel<<<1, 1024, 0, st>>>(a->num_frames, a->cap, a->count, a->offsets);
+    TSCD_CUDA_CHECK_LAUNCH();
+    pack_rows_kernel<<<a->num_frames, 256, 0, st>>>(*a);
+    TSCD_CUDA_CHECK_LAUNCH();
+    return TSCD_OK;
+}
 
 extern "C" int tscd_pack_detections(const tscd_pack_detections_args* a, void* stream) {
     using namespace tscd;

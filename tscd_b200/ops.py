@@ -89,6 +89,24 @@ class HeadViews:
                          apply_decode, (t,))
 
     @staticmethod
+    def from_rows(rows: torch.Tensor, obj: torch.Tensor, anchors: AnchorSpec, num_classes: int, apply_sigmoid: bool = True,
+                  apply_decode: bool = True):
+        """The FUSED head layout (include/tscd_b200.h tscd_pack_head): rows [F, A, 32|64] fp16 = [reg4|obj|cls C|pad] plus the
+        dense objectness plane obj [F, >=A].  Either tensor may live in pinned host memory (forward_host reads the rows
+        in place)."""
+        assert rows.dim() == 3 and rows.is_contiguous() and rows.dtype == torch.float16 and rows.shape[2] in (32, 64)
+        assert obj.dim() == 2 and obj.stride(1) == 1 and obj.dtype == torch.float16 and obj.shape[0] == rows.shape[0]
+        assert rows.shape[1] == anchors.num_anchors and obj.shape[1] >= anchors.num_anchors and 5 + num_classes <= rows.shape[2]
+        ov = L.View()
+        start = 0
+        for i, (h, w) in enumerate(anchors.hw):
+            ov.ptr[i] = obj.data_ptr() + start * 2
+            ov.frame_stride[i], ov.anchor_stride[i], ov.chan_stride[i] = obj.stride(0), 1, 1
+            start += h * w
+        return HeadViews(anchors, view_rowmajor(rows, anchors, 0), ov, view_rowmajor(rows, anchors, 5), rows.dtype,
+                         rows.shape[0], num_classes, apply_sigmoid, apply_decode, (rows, obj))
+
+    @staticmethod
     def from_levels(reg: List[torch.Tensor], obj: List[torch.Tensor], cls: List[torch.Tensor], anchors: AnchorSpec):
         """Seam S1: raw per-level conv outputs (logits), sigmoid + decode fused into the kernels."""
         return HeadViews(anchors, view_levels(reg), view_levels(obj), view_levels(cls), cls[0].dtype,
@@ -141,6 +159,32 @@ def select(head: HeadViews, mode: str, pre_k: int = 750, conf_thresh: float = 0.
     with L.timed("tscd_select"):
         L.check(L.lib().tscd_select(C.byref(a), _stream()), "tscd_select")
     return out
+
+
+def row_pitch(num_classes: int) -> int:
+    """Elements per fused head row: 32 (64 bytes) up to 27 classes, 64 (128 bytes) up to 59."""
+    if 5 + num_classes <= 32:
+        return 32
+    if 5 + num_classes <= 64:
+        return 64
+    raise RuntimeError(f"fused head rows hold at most 59 classes, got {num_classes}")
+
+
+def pack_head(head: HeadViews, rows: Optional[torch.Tensor] = None, obj: Optional[torch.Tensor] = None) -> HeadViews:
+    """tscd_pack_head: any strided fp16 head layout (per-level conv outputs) -> the fused-row layout, one pass."""
+    if head.dtype != torch.float16:
+        raise RuntimeError("tscd_pack_head: fp16 head outputs only (the fused rows are 16-bit)")
+    dev = _dev(head)
+    Fn, A = head.num_frames, head.anchors.num_anchors
+    rp = row_pitch(head.num_classes)
+    if rows is None:
+        rows = torch.empty(Fn, A, rp, dtype=torch.float16, device=dev)
+    if obj is None:
+        obj = torch.empty(Fn, (A + 7) // 8 * 8, dtype=torch.float16, device=dev)     # 16-byte aligned frames
+    call("tscd_pack_head", L.PackHeadArgs, num_frames=Fn, num_classes=head.num_classes, head_dtype=head.dtype, row_pitch=rp,
+         obj_pitch=obj.stride(0), anchors=head.anchors.to_c(), reg=head.reg, obj=head.obj, cls=head.cls, rows=rows,
+         obj_plane=obj)
+    return HeadViews.from_rows(rows, obj, head.anchors, head.num_classes, head.apply_sigmoid, head.apply_decode)
 
 
 NMS_SMEM_CAP = 4096       # csrc/nms.cuh kNmsCap: larger candidate lists take the workspace path (csrc/nms_large.cu)

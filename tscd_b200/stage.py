@@ -186,119 +186,195 @@ class AggregationStage:
 
     # ------------------------------------------------------------------------------------------------------
     def forward_host(self, host: dict, hw, time_embedding: torch.Tensor, B: int, F: int, Lf: int, chunk_clips: int = 8,
-                     strides=(8, 16, 32), zero_copy_logits: bool = False):
+                     strides=(8, 16, 32), zero_copy_logits: bool = False, graph: bool = True, lanes: int = 3):
         """The stage for callers whose boundary tensors live in (pinned) HOST memory -> detections on the host.
 
-        `host` = dict(reg, obj, cls, f_cls, f_reg, f_edge) of per-level lists of pinned CPU tensors (seam S1 layouts:
-        [B*F, ch, H, W], NCHW or channels_last).  Only what the kernels actually consume crosses PCIe:
-          * the head logits (reg/obj/cls planes, ~0.4 MB per frame) are copied host->device on a copy stream, one
-            chunk of clips ahead of the compute stream;
-          * the 256-channel feature planes (10.4 MB per frame) are NOT copied: K3 gathers the kept proposals' rows
-            straight out of the pinned host tensors (UVA zero-copy, 3 x 512 B per kept proposal), exactly the rows
-            find_feature_score (tscd_head.py:976-1006) indexes;
+        `host` holds per-level lists of pinned CPU tensors: the feature planes f_cls, f_reg, f_edge ([B*F, 256, H, W],
+        channels_last) and the head logits either in the fused layout the drop-in head emits -- rows [B*F, A, 32|64] +
+        objp [B*F, >=A] (include/tscd_b200.h tscd_pack_head) -- or per level (reg, obj, cls: [B*F, ch, H, W]).  Only what
+        the kernels consume crosses PCIe:
+          * fused layout, mode A: the 2-byte objectness plane is copied host->device on a copy stream (13.6 KB per frame),
+            one chunk of clips ahead of compute; K1 / K3 fetch the ~pre_k survivors' 64-byte rows IN PLACE from the pinned
+            tensor (cp.async / vector loads over PCIe; tools/zc_probe.cu measures 380 M rows/s = 24 GB/s for this pattern);
+            per-level layouts: the whole logits (~0.4 MB per frame) are copied;
+          * the 256-channel feature planes (10.4 MB per frame) are NOT copied: K3 gathers the kept proposals' rows straight
+            out of the pinned host tensors (3 x 512 B per kept proposal), exactly the rows find_feature_score
+            (tscd_head.py:976-1006) indexes;
           * detections come back as two padded tensors + counts in ONE device->host copy per chunk.
-        Returns (result, result_ori, h2d_bytes, d2h_bytes) with host tensors in the reference's list layout."""
-        dev = self.device
-        for k in ("reg", "obj", "cls", "f_cls", "f_reg", "f_edge"):
+        graph=True: the whole call (copies, every chunk's ~130 launches on two streams, read-backs) is captured ONCE per set
+        of host buffers into a CUDA graph and replayed afterwards -- callers that reuse their pinned staging buffers pay one
+        cudaGraphLaunch per call instead of ~1.4 ms of launch overhead per chunk.  (The graph reads the buffers at their
+        addresses: new tensors -> new capture; the four most recent plans are kept.)
+        Returns (result, result_ori, h2d_bytes, d2h_bytes) with fresh host tensors in the reference's list layout."""
+        fused = "rows" in host
+        head_keys = ("rows", "objp") if fused else ("reg", "obj", "cls")
+        for k in head_keys + ("f_cls", "f_reg", "f_edge"):
             for t in host[k]:
                 if t.device.type != "cpu" or not t.is_pinned():
                     raise RuntimeError(f"forward_host: host['{k}'] must be pinned CPU tensors (cudaHostAlloc) so the GPU can "
                                        "read them in place; there is no pageable-memory / CPU path")
-        an = ops.AnchorSpec(hw, strides)
-        feat_dtype = host["f_cls"][0].dtype
-        main = torch.cuda.current_stream()
-        if getattr(self, "_copy", None) is None:
-            self._copy = torch.cuda.Stream(device=dev)
-        cp = self._copy
-        key = (B, F, tuple(tuple(x) for x in hw), host["cls"][0].shape[1], host["cls"][0].dtype, host["cls"][0].stride())
-        if getattr(self, "_stage_key", None) != key:           # device staging for the head logits, reused across calls
-            self._stage_buf = {k: [torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, device=dev) for t in host[k]]
-                               for k in ("reg", "obj", "cls")}      # same strides: the H2D copy is a plain memcpy
-            self._stage_key = key
-        dbuf = self._stage_buf
-        # Mode A over class-contiguous (channels_last) logits only touches the objectness plane plus the class / regression
-        # rows of the ~pre_k survivors.  zero_copy_logits=True copies just `obj` and lets K1 / K3 read those rows in place
-        # from the pinned host tensors (4x fewer PCIe bytes).  Measured on B200: the ~2 million 64-byte PCIe reads per 32
-        # clips are slower (40 k clip-frames/s) than streaming all logits with the copy engine (93 k) -> off by default.
-        zc = zero_copy_logits and self.cfg.selection.mode == "A" and all(t.stride(1) == 1 for t in host["cls"]) \
-            and all(t.stride(1) == 1 for t in host["reg"])
-        copied = ("obj",) if zc else ("reg", "obj", "cls")
-        te = time_embedding
-        cp.wait_stream(main)                                   # previous call's kernels are done with the staging buffers
-        chunks = [(c0, min(chunk_clips, B - c0)) for c0 in range(0, B, chunk_clips)]
-        events, h2d = [], 0
-        with torch.cuda.stream(cp):
-            te_dev = te.to(dev, non_blocking=True)
-            h2d += te.numel() * te.element_size()
-            for (c0, nc) in chunks:
-                f0, f1 = c0 * F, (c0 + nc) * F
-                for k in copied:
-                    for l, t in enumerate(host[k]):
-                        dbuf[k][l][f0:f1].copy_(t[f0:f1], non_blocking=True)
-                        h2d += (f1 - f0) * t[0].numel() * t.element_size()
-                ev = torch.cuda.Event()
-                ev.record(cp)
-                events.append(ev)
-        pend = []
-        for (c0, nc), ev in zip(chunks, events):
-            f0, f1 = c0 * F, (c0 + nc) * F
-            main.wait_event(ev)
-            src = {k: (dbuf[k] if k in copied else host[k]) for k in ("reg", "obj", "cls")}
-            head = ops.HeadViews.from_levels([t[f0:f1] for t in src["reg"]], [t[f0:f1] for t in src["obj"]],
-                                             [t[f0:f1] for t in src["cls"]], an)
-            feats = tuple(ops.view_levels([t[f0:f1] for t in host[k]]) for k in ("f_cls", "f_reg", "f_edge"))
-            out = self.forward(head, feats, feat_dtype, te_dev[c0 * Lf:(c0 + nc) * Lf], nc, F, Lf)
-            pend.append((nc, self._pack_to_host(out, zc)))
+        key = (tuple((k, t.data_ptr(), tuple(t.shape), t.stride(), t.dtype) for k in head_keys + ("f_cls", "f_reg", "f_edge") for t in host[k]),
+               tuple(tuple(x) for x in hw), tuple(strides), B, F, Lf, chunk_clips, zero_copy_logits, graph, lanes,
+               tuple(time_embedding.shape))
+        plans = self.__dict__.setdefault("_host_plans", {})
+        plan = plans.pop(key, None)
+        if plan is None:
+            plan = self._build_host_plan(host, hw, time_embedding, B, F, Lf, chunk_clips, strides, zero_copy_logits, graph, fused, lanes)
+        plans[key] = plan                                      # most recently used last
+        while len(plans) > 4:
+            plans.pop(next(iter(plans)))
+        plan["te_pin"].copy_(time_embedding)
+        if plan["graph"] is not None:
+            plan["graph"].replay()
+        else:
+            plan["issue"]()
         torch.cuda.current_stream().synchronize()
         result, result_ori, d2h = [], [], 0
-        for nc, pk in pend:
-            r, o, nb = self._unpack_host(pk, nc * Lf)
+        h2d = plan["h2d"]
+        for nc, pk in plan["pend"]:
+            r, o, nb, zb = self._unpack_host(pk, nc * Lf)
             result += r
             result_ori += o
             d2h += nb
-        h2d += sum(int(x) for _, pk in pend for x in pk["gathered_bytes"])
+            h2d += zb
         return result, result_ori, h2d, d2h
 
+    def _build_host_plan(self, host, hw, time_embedding, B, F, Lf, chunk_clips, strides, zero_copy_logits, graph, fused, n_lanes):
+        """Staging buffers + the launch sequence of one forward_host call (optionally captured into a CUDA graph)."""
+        dev = self.device
+        an = ops.AnchorSpec(hw, strides)
+        feat_dtype = host["f_cls"][0].dtype
+        head_keys = ("rows", "objp") if fused else ("reg", "obj", "cls")
+        # Mode A only touches the objectness plane plus the class / regression rows of the ~pre_k survivors.
+        #  * fused layout: the objectness plane is copied and K1 / K3 read the survivors' 64-byte rows in place (measured,
+        #    profiles/zc_probe_r2.txt: 24 GB/s for 750-of-6804 row sets vs 55 GB/s for the copy engine moving all 435 KB);
+        #  * per-level layouts: zero_copy_logits=True copies just `obj` and reads the separate class / regression rows in
+        #    place.  Measured slower (40 k clip-frames/s vs 93 k): two unaligned bursts per survivor -> off by default.
+        zc = (not fused) and zero_copy_logits and self.cfg.selection.mode == "A" and all(t.stride(1) == 1 for t in host["cls"]) \
+            and all(t.stride(1) == 1 for t in host["reg"])
+        rows_in_place = fused and self.cfg.selection.mode == "A"
+        copied = (("objp",) if rows_in_place else ("objp", "rows")) if fused else (("obj",) if zc else ("reg", "obj", "cls"))
+        dbuf = {k: [torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, device=dev) for t in host[k]] for k in copied}
+        te_pin = torch.empty(time_embedding.shape, dtype=time_embedding.dtype, pin_memory=True)
+        te_pin.copy_(time_embedding)
+        cp = torch.cuda.Stream(device=dev)
+        aux = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(max(0, n_lanes - 1))]
+        chunks = [(c0, min(chunk_clips, B - c0)) for c0 in range(0, B, chunk_clips)]
+        plan = {"te_pin": te_pin, "graph": None, "pend": None, "h2d": 0, "_keep": (dbuf, host, cp, aux)}
+        fused_row_bytes = host["rows"][0].shape[2] * 2 if fused else None
+
+        def issue():
+            main = torch.cuda.current_stream()
+            cp.wait_stream(main)                               # earlier work on this stream is done with the staging buffers
+            events, h2d = [], 0
+            with torch.cuda.stream(cp):
+                te_dev = te_pin.to(dev, non_blocking=True)
+                h2d += te_pin.numel() * te_pin.element_size()
+                for (c0, nc) in chunks:
+                    f0, f1 = c0 * F, (c0 + nc) * F
+                    for k in copied:
+                        for l, t in enumerate(host[k]):
+                            dbuf[k][l][f0:f1].copy_(t[f0:f1], non_blocking=True)
+                            h2d += (f1 - f0) * t[0].numel() * t.element_size()
+                    ev = torch.cuda.Event()
+                    ev.record(cp)
+                    events.append(ev)
+            te_dev.record_stream(main)
+            # chunks alternate between two compute streams: K1 / K3 of one chunk wait on PCIe (rows and features are read in
+            # place) while the tensor-core tail of the previous chunk runs
+            lanes = ([main] + aux)[:max(1, len(chunks))]
+            for a_ in lanes[1:]:
+                a_.wait_stream(main)
+            pend = []
+            for ci, ((c0, nc), ev) in enumerate(zip(chunks, events)):
+                f0, f1 = c0 * F, (c0 + nc) * F
+                lane_s = lanes[ci % len(lanes)]
+                with torch.cuda.stream(lane_s):
+                    lane_s.wait_event(ev)
+                    if fused:
+                        rows_src = host["rows"][0] if rows_in_place else dbuf["rows"][0]
+                        head = ops.HeadViews.from_rows(rows_src[f0:f1], dbuf["objp"][0][f0:f1], an, self.cfg.num_classes)
+                    else:
+                        src = {k: (dbuf[k] if k in copied else host[k]) for k in ("reg", "obj", "cls")}
+                        head = ops.HeadViews.from_levels([t[f0:f1] for t in src["reg"]], [t[f0:f1] for t in src["obj"]],
+                                                         [t[f0:f1] for t in src["cls"]], an)
+                    feats = tuple(ops.view_levels([t[f0:f1] for t in host[k]]) for k in ("f_cls", "f_reg", "f_edge"))
+                    if lane_s is not main:
+                        te_dev.record_stream(lane_s)
+                    out = self.forward(head, feats, feat_dtype, te_dev[c0 * Lf:(c0 + nc) * Lf], nc, F, Lf)
+                    reuse = plan["pend"][len(pend)][1] if plan["pend"] is not None else None
+                    pend.append((nc, self._pack_to_host(out, zc or rows_in_place, fused_row_bytes, reuse)))
+            for a_ in lanes[1:]:
+                main.wait_stream(a_)
+            plan["pend"], plan["h2d"] = pend, h2d
+
+        plan["issue"] = issue
+        if graph:
+            # warm up (lazy module loading, per-stream stage state) and capture on one high-priority stream, like capture_fn
+            hp = torch.cuda.Stream(device=dev, priority=-1)
+            hp.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(hp):
+                issue()
+            torch.cuda.current_stream().wait_stream(hp)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=hp):
+                issue()
+            plan["graph"] = g
+        return plan
+
     @staticmethod
-    def _pack_to_host(out, zero_copy_logits=False):
-        """Asynchronous D2H of the padded detections + counts + status (one pinned buffer each)."""
+    def _pack_to_host(out, zero_copy_logits=False, fused_row_bytes=None, reuse=None):
+        """Device-side compaction of the padded detections (tscd_pack_rows: packed [sum n, 7] + offsets) and the asynchronous D2H
+        of tables, counts and status (one pinned buffer each; `reuse` = the dict a previous call returned: its pinned buffers
+        are written again -- no host allocation, as required under graph capture)."""
         pk = {}
+
+        def pinned(name, src):
+            h = reuse[name] if reuse is not None else torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+            h.copy_(src, non_blocking=True)
+            pk[name] = h
+
         if zero_copy_logits:         # bytes K1 / K3 read in place: survivors' class + regression rows, kept rows again
-            cc = torch.empty(out["sel"]["cand"]["count"].shape, dtype=torch.int32, pin_memory=True)
-            cc.copy_(out["sel"]["cand"]["count"], non_blocking=True)
-            pk["cand_count"] = cc
-            pk["_logit_row_bytes"] = (out["sel"]["sel_rows"].shape[2] - 7 + 4 + 1) * 2
-        for k in ("det_rows", "ori_rows", "det_count", "ori_count", "det_cand", "status"):
-            h = torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True)
-            h.copy_(out[k], non_blocking=True)
-            pk[k] = h
-        cnt = torch.empty(out["sel"]["sel_count"].shape, dtype=torch.int32, pin_memory=True)
-        cnt.copy_(out["sel"]["sel_count"], non_blocking=True)
-        pk["sel_count"] = cnt
-        pk["gathered_bytes"] = []
+            pinned("cand_count", out["sel"]["cand"]["count"])
+            pk["_logit_row_bytes"] = fused_row_bytes or (out["sel"]["sel_rows"].shape[2] - 7 + 4 + 1) * 2
+        for name in ("det", "ori"):
+            rows, cnt = out[name + "_rows"], out[name + "_count"]
+            nf, cap, _ = rows.shape
+            packed = torch.empty(nf * cap, 7, dtype=torch.float32, device=rows.device)
+            offsets = torch.empty(nf + 1, dtype=torch.int32, device=rows.device)
+            ops.call("tscd_pack_rows", L.PackRowsArgs, num_frames=nf, cap=cap, rows=rows, count=cnt, offsets=offsets, packed=packed)
+            pinned(name + "_packed", packed)
+            pinned(name + "_offsets", offsets)
+        for k in ("det_cand", "status"):
+            pinned(k, out[k])
+        pinned("sel_count", out["sel"]["sel_count"])
         pk["_row_bytes"] = 3 * out["sel"]["bank_cls"].shape[1] * 2
         return pk
 
     @staticmethod
     def _unpack_host(pk, nlf):
+        """Pinned read-back buffers of one chunk -> the reference's list layout.  The buffers belong to the plan (a graph
+        replay overwrites them), so the valid rows are copied out: ONE contiguous clone per output, split into per-frame views
+        (fresh tensors, as the callers mutate them in place -- ovis_evaluator_v2.py:268-271)."""
         st = int(pk["status"][0])
         if st != 0:
             raise RuntimeError(f"tscd_b200 stage reported error {st} (capacity exceeded: a frame holds more proposals than "
                                "SelectionConfig.max_proposals)")
-        pk["gathered_bytes"].append(int(pk["sel_count"].sum()) * pk["_row_bytes"])   # zero-copy reads of the feature rows
+        zc_bytes = int(pk["sel_count"].sum()) * pk["_row_bytes"]          # zero-copy reads of the feature rows
         if "cand_count" in pk:
-            pk["gathered_bytes"].append((int(pk["cand_count"].sum()) + int(pk["sel_count"].sum())) * pk["_logit_row_bytes"])
-        det_n, ori_n, det_c = pk["det_count"].tolist(), pk["ori_count"].tolist(), pk["det_cand"].tolist()
-        result, result_ori = [], []
-        for i in range(nlf):
-            if det_c[i] == 0:
-                result.append(None)
-                result_ori.append(None)
-                continue
-            result.append(pk["det_rows"][i, :det_n[i]])
-            result_ori.append(pk["ori_rows"][i, :ori_n[i]])
-        nb = sum(pk[k].numel() * pk[k].element_size() for k in ("det_rows", "ori_rows", "det_count", "ori_count", "det_cand", "status", "sel_count"))
-        return result, result_ori, nb
+            zc_bytes += (int(pk["cand_count"].sum()) + int(pk["sel_count"].sum())) * pk["_logit_row_bytes"]
+        det_c = pk["det_cand"][:nlf].tolist()
+        lists, nb = [], 0
+        for name in ("det", "ori"):
+            off = pk[name + "_offsets"][:nlf + 1].tolist()
+            table = pk[name + "_packed"][:off[-1]].clone()
+            parts = table.split([off[i + 1] - off[i] for i in range(nlf)])
+            lists.append([p_ if c else None for p_, c in zip(parts, det_c)])     # post_process.py:54-55: no candidates -> None
+            nb += pk[name + "_packed"].numel() * 4 + pk[name + "_offsets"].numel() * 4
+        result, result_ori = lists
+        nb += sum(pk[k].numel() * pk[k].element_size() for k in ("det_cand", "status", "sel_count"))
+        return result, result_ori, nb, zc_bytes
 
     # ------------------------------------------------------------------------------------------------------
     def capture(self, head: ops.HeadViews, feats, feat_dtype, time_embedding: torch.Tensor, B: int, F: int, Lf: int,
