@@ -98,6 +98,11 @@ typedef struct {
      * a maximal_limit: the reference's list is unbounded, postprocess_widx tscd_head.py:1591-1607; the candidate arrays
      * are not).  The frame is truncated to its first cand_cap anchors and the caller must treat the batch as failed. */
     int32_t* status;
+    /* optional (mode A, fused-row layout): when set, the objectness sort is SKIPPED -- candidates are emitted in ascending
+     * anchor order and cand_rank[f, i] = (16-bit objectness key << 16) | (0xffff - i) carries the order instead; pass it to
+     * tscd_nms as `rank` so that equal product scores keep the reference's tie order (topk order, post_process.py:506-517).
+     * The selected SET, the NMS keep list and everything downstream are identical; only the order of cand_* differs. */
+    uint32_t* cand_rank;
 } tscd_select_args;
 int tscd_select(const tscd_select_args* args, void* stream);
 
@@ -155,6 +160,10 @@ typedef struct {
     int32_t strict_keep;  /* 1: a frame that keeps MORE than max_keep boxes is an error (status = TSCD_ERR_CAPACITY) instead
                            * of a truncation -- mode B with pre-NMS, where max_keep is a buffer capacity and not the
                            * reference's top-K (tscd_head.py:1629-1635 keeps everything) */
+    const uint32_t* rank; /* optional [F,cap] tie-break keys written by tscd_select (cand_rank): candidates are then in ascending
+                           * anchor order and equal scores are ordered by DESCENDING rank (= the objectness order the reference's
+                           * topk would have put them in); the low 16 bits of a rank are 0xffff - position.  Top-K use only
+                           * (4 * max_keep < cand_cap <= 4096). */
 } tscd_nms_args;
 int tscd_nms(const tscd_nms_args* args, void* stream);
 int64_t tscd_nms_workspace_bytes(int32_t num_frames, int32_t cand_cap);

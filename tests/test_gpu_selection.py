@@ -393,6 +393,53 @@ def test_select_fused_rows_saturation_and_wide_rows(C):
         assert c1["idx"][f].cpu().tolist() == want
 
 
+def test_select_unsorted_rank_keeps_score_tie_order():
+    """Fused-row mode A without the objectness sort (cand_rank -> tscd_nms rank): engineered EQUAL product scores
+    (obj = s(a), cls = s(b) against obj = s(b), cls = s(a): the fp32 product commutes bit for bit) on disjoint boxes, so the first
+    30 survivors are decided by the tie order alone.  The keep list must equal the sorted path's and the oracle's
+    (topk order, post_process.py:506-517: higher objectness first, then lower anchor id)."""
+    ops, selection = _stage_mods()
+    hw = [(72, 72), (36, 36), (18, 18)]
+    C, Fn = 25, 3
+    an = ops.AnchorSpec(hw)
+    A = an.num_anchors
+    g = torch.Generator().manual_seed(5)
+    fused = torch.zeros(Fn, A, 5 + C)
+    grids, st = oracle.anchor_grid(hw, [8, 16, 32])
+    fused[..., 0:2] = 0.5                                   # box centres on the anchor grid, 2-pixel boxes: all disjoint
+    fused[..., 2:4] = torch.log(torch.tensor(2.0)) - torch.log(st)
+    fused[..., 4] = -9.0 + torch.rand(Fn, A, generator=g) * 0.01
+    fused[..., 5:] = -9.0
+    for f in range(Fn):
+        pick = torch.randperm(A, generator=g)[:900]
+        va, vb = 2.0 + 0.25 * f, -1.0 - 0.5 * f
+        fused[f, pick[:450], 4], fused[f, pick[:450], 5 + 3] = va, vb       # obj a, class 3 conf b
+        fused[f, pick[450:], 4], fused[f, pick[450:], 5 + 7] = vb, va       # obj b, class 7 conf a  -> same product
+    fused = fused.half()
+    rows = torch.zeros(Fn, A, 32, dtype=torch.float16)
+    rows[..., :5 + C] = fused
+    head = ops.HeadViews.from_rows(rows.cuda(), fused[..., 4].contiguous().cuda(), an, C)
+    cfg = selection.SelectionConfig(mode="A", pre_k=750, top_k=30)
+    c_sorted = ops.select(head, "A", pre_k=750)
+    k_sorted, n_sorted, _ = ops.nms(c_sorted["box"], c_sorted["score"], c_sorted["cls"], c_sorted["count"], 0.75, max_keep=30)
+    c_uns = ops.select(head, "A", pre_k=750, unsorted=True)
+    k_uns, n_uns, _ = ops.nms(c_uns["box"], c_uns["score"], c_uns["cls"], c_uns["count"], 0.75, max_keep=30, rank=c_uns["rank"])
+    torch.cuda.synchronize()
+    sig = fused.float().cuda()
+    sig[..., 4:] = torch.sigmoid(sig[..., 4:])
+    decoded = oracle.decode_outputs(sig.cpu(), hw, [8, 16, 32])
+    _, o_idx = oracle.select_mode_a(decoded, C, pre_k=750, top_k=30)
+    for f in range(Fn):
+        assert int(n_sorted[f]) == 30 and int(n_uns[f]) == 30
+        ids_sorted = c_sorted["idx"][f][k_sorted[f].long()].cpu().tolist()
+        ids_uns = c_uns["idx"][f][k_uns[f].long()].cpu().tolist()
+        assert c_uns["idx"][f].cpu().tolist() == sorted(c_uns["idx"][f].cpu().tolist()), "unsorted candidates come in anchor order"
+        assert ids_sorted == o_idx[f].tolist(), f
+        assert ids_uns == o_idx[f].tolist(), f
+        sc = c_sorted["score"][f][k_sorted[f].long()]
+        assert float(sc.max()) == float(sc.min()), "the kept boxes all tie on the score"
+
+
 def test_select_mode_a_sigmoid_saturation_ties():
     """fp16 objectness logits >= 18 all map to sigmoid == 1.0f: different logits, equal scores.  The kernel ranks by the
     16-bit logit first (2-pass radix select, 32-bit sort) and must fall back to the score keys so that ties are still

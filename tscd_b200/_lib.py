@@ -30,7 +30,8 @@ class SelectArgs(C.Structure):
                 ("cand_cap", C.c_int32), ("anchors", Anchors), ("reg", View), ("obj", View), ("cls", View),
                 ("cand_idx", C.c_void_p), ("cand_box", C.c_void_p), ("cand_score", C.c_void_p),
                 ("cand_cls", C.c_void_p), ("cand_count", C.c_void_p),
-                ("ws_conf", C.c_void_p), ("ws_cls", C.c_void_p), ("ws_pitch", C.c_int32), ("status", C.c_void_p)]
+                ("ws_conf", C.c_void_p), ("ws_cls", C.c_void_p), ("ws_pitch", C.c_int32), ("status", C.c_void_p),
+                ("cand_rank", C.c_void_p)]
 
 
 class PackHeadArgs(C.Structure):
@@ -43,7 +44,7 @@ class NmsArgs(C.Structure):
     _fields_ = [("num_frames", C.c_int32), ("cand_cap", C.c_int32), ("max_keep", C.c_int32), ("iou_thresh", C.c_float),
                 ("box", C.c_void_p), ("score", C.c_void_p), ("cls", C.c_void_p), ("count", C.c_void_p),
                 ("keep", C.c_void_p), ("keep_count", C.c_void_p), ("status", C.c_void_p),
-                ("ws", C.c_void_p), ("ws_bytes", C.c_int64), ("strict_keep", C.c_int32)]
+                ("ws", C.c_void_p), ("ws_bytes", C.c_int64), ("strict_keep", C.c_int32), ("rank", C.c_void_p)]
 
 
 class GatherArgs(C.Structure):

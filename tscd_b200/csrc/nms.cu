@@ -249,6 +249,14 @@ __global__ void __launch_bounds__(kNmsThreads, 4) nms_kernel(const tscd_nms_args
     const float* gscore = args.score + base;
     const float4* gbox = reinterpret_cast<const float4*>(args.box) + base;
     const int32_t* gcls = args.cls + base;
+    // optional tie-break keys (tscd_select's cand_rank: candidates in anchor order, rank = objectness key << 16 | 0xffff - position):
+    // equal scores are ordered by descending rank, the position is the rank's low half
+    const uint32_t* grank = args.rank ? args.rank + base : nullptr;
+    auto low_of = [&](int i) -> uint32_t { return grank ? grank[i] : 0xffffffffu - (uint32_t)i; };
+    auto pos_of = [&](unsigned long long key) -> int {
+        const uint32_t lo32 = (uint32_t)(key & 0xffffffffull);
+        return grank ? (int)(0xffffu - (lo32 & 0xffffu)) : (int)(0xffffffffu - lo32);
+    };
 
     // ---- max coordinate (over ALL boxes: the coordinate-trick offset unit) --------------------------------
     float mx = -INFINITY;
@@ -296,7 +304,7 @@ __global__ void __launch_bounds__(kNmsThreads, 4) nms_kernel(const tscd_nms_args
             for (int i = threadIdx.x; i < n; i += blockDim.x) {
                 if (k32[i] >= T) {
                     const int slot = atomicAdd(&rs.misc[3], 1);
-                    skey[slot] = ((unsigned long long)k32[i] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+                    skey[slot] = ((unsigned long long)k32[i] << 32) | (unsigned long long)low_of(i);
                 }
             }
             __syncthreads();
@@ -307,7 +315,7 @@ __global__ void __launch_bounds__(kNmsThreads, 4) nms_kernel(const tscd_nms_args
                 // tiny frames (the unrefined "ori" rows: <= 30 candidates): one warp sorts in registers
                 if (threadIdx.x < 32) {
                     const int lane = threadIdx.x;
-                    unsigned long long v = lane < n ? (((unsigned long long)f2ord(gscore[lane]) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)lane)) : 0ull;
+                    unsigned long long v = lane < n ? (((unsigned long long)f2ord(gscore[lane]) << 32) | (unsigned long long)low_of(lane)) : 0ull;
                     for (int k = 2; k <= 32; k <<= 1)
                         for (int j = k >> 1; j > 0; j >>= 1) {
                             const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, j);
@@ -319,14 +327,14 @@ __global__ void __launch_bounds__(kNmsThreads, 4) nms_kernel(const tscd_nms_args
                 __syncthreads();
             } else {
                 for (int i = threadIdx.x; i < n; i += blockDim.x)
-                    skey[i] = ((unsigned long long)f2ord(gscore[i]) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+                    skey[i] = ((unsigned long long)f2ord(gscore[i]) << 32) | (unsigned long long)low_of(i);
                 __syncthreads();
                 block_sort_desc64_dyn<unsigned long long>(skey, n, smem_cap);
             }
         }
 
         for (int r = threadIdx.x; r < n_work; r += blockDim.x) {
-            int pos = (int)(0xffffffffu - (uint32_t)(skey[r] & 0xffffffffull));
+            int pos = pos_of(skey[r]);
             float4 b = gbox[pos];
             float off = __fmul_rn((float)gcls[pos], off_unit);
             b.x = __fadd_rn(b.x, off); b.y = __fadd_rn(b.y, off);
@@ -383,7 +391,7 @@ __global__ void __launch_bounds__(kNmsThreads, 4) nms_kernel(const tscd_nms_args
                 int rank = __popc(kept & ((1u << lane) - 1u));
                 bool mine = (kept >> lane) & 1u;
                 if (mine && nk + rank < lim) {
-                    if (nk + rank < max_keep) keep[nk + rank] = (int)(0xffffffffu - (uint32_t)(skey[c0 + lane] & 0xffffffffull));
+                    if (nk + rank < max_keep) keep[nk + rank] = pos_of(skey[c0 + lane]);
                     s_keptidx[nk + rank] = c0 + lane;
                 }
                 if (lane == 0) s_nkept = nk + min(__popc(kept), lim - nk);
@@ -542,6 +550,7 @@ extern "C" int tscd_nms(const tscd_nms_args* a, void* stream) {
     using namespace tscd;
     if (!a || a->num_frames < 0 || a->cand_cap <= 0 || a->max_keep <= 0 || !(a->iou_thresh >= 0.f)) return TSCD_ERR_INVALID_ARG;
     if (a->num_frames == 0) return TSCD_OK;
+    if (a->rank && (a->cand_cap > 65535 || a->cand_cap <= 64 || (int64_t)a->max_keep * 4 >= a->cand_cap)) return TSCD_ERR_UNSUPPORTED;  // top-K kernel only
     if (a->cand_cap > kNmsCap) return nms_large_launch(*a, reinterpret_cast<cudaStream_t>(stream));
     int cap = a->cand_cap;
     int cap64 = 1;

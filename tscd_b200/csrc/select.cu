@@ -392,6 +392,7 @@ extern "C" int tscd_select(const tscd_select_args* a, void* stream) {
     {   // fused 64 / 128-byte rows + dense objectness plane (the drop-in head's layout): csrc/select_rows.cu
         const int rc = select_rows_try(a, st);
         if (rc != 0) return rc < 0 ? rc : TSCD_OK;
+        if (a->cand_rank) return TSCD_ERR_UNSUPPORTED;       // the unsorted / rank output exists for the fused-row kernel only
     }
     // mode A with a workspace and planar (anchor-contiguous) class planes: class max as a separate streaming kernel
     // mode A needs the class max of the ~pre_k survivors only.  Class-contiguous logits (channels_last conv outputs: an

@@ -162,8 +162,10 @@ select_rows_kernel(const tscd_select_args args, int sort_cap, int take_cap) {
         cp_async16(rows + idx, src + 8 * v);
     }
 
-    // ---- 4. order by objectness (descending; ties: lower anchor id == lower compaction position first) ----------------
-    block_sort_desc64_dyn<uint32_t>(sort32, n_sel, sort_cap);
+    // ---- 4. order by objectness (descending; ties: lower anchor id == lower compaction position first).  With cand_rank the
+    //         sort is skipped: candidates stay in anchor order and the key travels to K2 as the tie-break rank ----------------
+    const bool unsorted = args.cand_rank != nullptr;
+    if (!unsorted) block_sort_desc64_dyn<uint32_t>(sort32, n_sel, sort_cap);
     cp_async_wait_all();
     __syncthreads();
 
@@ -194,6 +196,7 @@ select_rows_kernel(const tscd_select_args args, int sort_cap, int take_cap) {
         reinterpret_cast<float4*>(args.cand_box)[base + j] = box;
         args.cand_score[base + j] = __fmul_rn(obj, conf);                  // post_process.py:512  obj * class_conf
         args.cand_cls[base + j] = cls_id;
+        if (unsorted) args.cand_rank[base + j] = sort32[j];
     }
     if (tid == 0) args.cand_count[frame] = n_sel;
 }

@@ -79,6 +79,7 @@ class HeadViews:
     apply_sigmoid: bool
     apply_decode: bool
     _keep: tuple = ()  # keeps the tensors alive
+    fused: bool = False  # the fused-row layout (from_rows): the row kernels of csrc/select_rows.cu apply
 
     @staticmethod
     def from_fused(t: torch.Tensor, anchors: AnchorSpec, apply_sigmoid: bool, apply_decode: bool):
@@ -104,7 +105,7 @@ class HeadViews:
             ov.frame_stride[i], ov.anchor_stride[i], ov.chan_stride[i] = obj.stride(0), 1, 1
             start += h * w
         return HeadViews(anchors, view_rowmajor(rows, anchors, 0), ov, view_rowmajor(rows, anchors, 5), rows.dtype,
-                         rows.shape[0], num_classes, apply_sigmoid, apply_decode, (rows, obj))
+                         rows.shape[0], num_classes, apply_sigmoid, apply_decode, (rows, obj), True)
 
     @staticmethod
     def from_levels(reg: List[torch.Tensor], obj: List[torch.Tensor], cls: List[torch.Tensor], anchors: AnchorSpec):
@@ -124,9 +125,11 @@ def _dev(head: "HeadViews"):
 
 
 def select(head: HeadViews, mode: str, pre_k: int = 750, conf_thresh: float = 0.001, minimal_limit: int = 0,
-           maximal_limit: int = 0, cand_cap: Optional[int] = None, status: Optional[torch.Tensor] = None):
+           maximal_limit: int = 0, cand_cap: Optional[int] = None, status: Optional[torch.Tensor] = None, unsorted: bool = False):
     """K1.  Returns dict(idx,box,score,cls,count) of device tensors [F,cap(,4)] / [F].  `status` ([1] int32) receives
-    TSCD_ERR_CAPACITY when a mode-B frame selects more than cand_cap anchors."""
+    TSCD_ERR_CAPACITY when a mode-B frame selects more than cand_cap anchors.
+    unsorted (mode A, fused-row layout only): skip the objectness sort -- candidates come in ascending anchor order and
+    out['rank'] carries the order for ops.nms(rank=...) (same keep list, see include/tscd_b200.h cand_rank)."""
     dev = _dev(head)
     Fn, A = head.num_frames, head.anchors.num_anchors
     if cand_cap is None:
@@ -148,6 +151,11 @@ def select(head: HeadViews, mode: str, pre_k: int = 750, conf_thresh: float = 0.
     a.cand_idx, a.cand_box, a.cand_score = _p(out["idx"]), _p(out["box"]), _p(out["score"])
     a.cand_cls, a.cand_count = _p(out["cls"]), _p(out["count"])
     a.status = _p(status)
+    if unsorted:
+        if not (mode == "A" and head.fused and Fn > 0):
+            raise RuntimeError("ops.select(unsorted=True) needs mode A over the fused-row head layout")
+        out["rank"] = torch.empty(Fn, cand_cap, dtype=torch.int32, device=dev)
+        a.cand_rank = _p(out["rank"])
     class_contiguous = all(head.cls.chan_stride[i] == 1 for i in range(len(head.anchors.hw)))
     if mode == "A" and not class_contiguous:   # workspace of the streaming class-max kernel (K1 = two kernels for NCHW planes)
         pitch = (A + 15) // 16 * 16
@@ -192,7 +200,8 @@ NMS_MAX_CAP = 16384       # kNmsLargeCap
 
 
 def nms(box: torch.Tensor, score: torch.Tensor, cls: torch.Tensor, count: torch.Tensor, iou_thresh: float,
-        max_keep: Optional[int] = None, status: Optional[torch.Tensor] = None, strict_keep: bool = False, tag=None):
+        max_keep: Optional[int] = None, status: Optional[torch.Tensor] = None, strict_keep: bool = False, tag=None,
+        rank: Optional[torch.Tensor] = None):
     """K2.  box [F,cap,4] f32, score [F,cap] f32, cls [F,cap] i32, count [F] i32 -> (keep [F,max_keep], keep_count [F]).
     strict_keep: more than max_keep survivors in a frame is a capacity error (status) instead of a truncation."""
     Fn, cap = score.shape
@@ -208,6 +217,7 @@ def nms(box: torch.Tensor, score: torch.Tensor, cls: torch.Tensor, count: torch.
     a.box, a.score, a.cls, a.count = _p(box), _p(score), _p(cls), _p(count)
     a.keep, a.keep_count, a.status = _p(keep), _p(keep_count), _p(status)
     a.strict_keep = int(strict_keep)
+    a.rank = _p(rank)
     ws = None
     if cap > NMS_SMEM_CAP:
         a.ws_bytes = L.lib().tscd_nms_workspace_bytes(Fn, cap)

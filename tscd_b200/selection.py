@@ -73,14 +73,20 @@ def select_and_gather(head: ops.HeadViews, feats, feat_dtype, feat_dim, cfg: Sel
     if cand_cap > ops.NMS_MAX_CAP:
         raise RuntimeError(f"mode B pre-NMS over {cand_cap} candidates per frame exceeds the NMS capacity of {ops.NMS_MAX_CAP}; "
                            "set maximal_limit or use_pre_nms=False")
-    cand = ops.select(head, cfg.mode, pre_k=cfg.pre_k, conf_thresh=cfg.conf_thresh,
-                      minimal_limit=cfg.minimal_limit, maximal_limit=cfg.maximal_limit, cand_cap=cand_cap, status=status)
-    keep = keep_count = None
     max_keep = cfg.max_keep(A)
+    # mode A over the fused-row layout: K1 skips its objectness sort (K2 orders by score anyway; the objectness order only
+    # breaks score ties and travels as a rank key) whenever K2 runs its top-K kernel
+    unsorted = cfg.mode == "A" and head.fused and head.num_frames > 0 and 64 < cand_cap <= ops.NMS_SMEM_CAP and 4 * max_keep < cand_cap \
+        and min(cfg.pre_k, A) <= cand_cap and A <= 65535
+    cand = ops.select(head, cfg.mode, pre_k=cfg.pre_k, conf_thresh=cfg.conf_thresh,
+                      minimal_limit=cfg.minimal_limit, maximal_limit=cfg.maximal_limit, cand_cap=cand_cap, status=status,
+                      unsorted=unsorted)
+    keep = keep_count = None
     if cfg.mode == "A" or cfg.use_pre_nms:
         # mode A: the first top_k survivors ARE the semantics; mode B: max_keep is a buffer capacity, overflow is an error
         keep, keep_count, status = ops.nms(cand["box"], cand["score"], cand["cls"], cand["count"], cfg.nms_thresh,
-                                           max_keep=max_keep, status=status, strict_keep=cfg.mode == "B", tag="pre")
+                                           max_keep=max_keep, status=status, strict_keep=cfg.mode == "B", tag="pre",
+                                           rank=cand.get("rank"))
     out = ops.gather(head, feats, feat_dtype, feat_dim, cand, keep, keep_count, max_keep=max_keep,
                      bank_dtype=bank_dtype, bank_rows=bank_rows)
     out["cand"] = cand
