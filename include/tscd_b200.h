@@ -569,6 +569,36 @@ typedef struct {
 } tscd_pack_rows_args;
 int tscd_pack_rows(const tscd_pack_rows_args* args, void* stream);
 
+/* ---- REPP detection linking -------------------------------------------------------------------
+ * Replaces REPP.get_video_pairs + solve_distances_def (tools/REPP.py:82-133) with the linking scores of distance_def /
+ * distance_logreg (:52-79) and the pair features of tools/repp_utils.py:34-109: for every pair of consecutive frames the
+ * n1 x n2 linking distances and the greedy minimum matching (global minimum first, ties in row-major order), as the list of
+ * (index in frame f, index in frame f+1) pairs IN EXTRACTION ORDER (the tubelet builder, REPP.py:138-190, depends on it).
+ * Detections of all frames are packed back to back; frame f owns [frame_off[f], frame_off[f+1]).  The one-hot class score
+ * vectors of REPP.__call__ (:248-254) are passed as (score, class).  The logistic model is given by its coefficients in the
+ * order (center_distances_corrected, height_rel, iou, width_rel) of tools/matching_model_logreg.pckl. */
+typedef struct {
+    int32_t num_frames;
+    int32_t max_det;          /* pitch of `pairs` per frame pair; >= detections of any frame, <= 4096 */
+    int32_t distance_func;    /* 0 = 'def', 1 = 'logreg' */
+    int32_t clf_mode;         /* 0 = 'dot', 1 = 'max', 2 = 'dot_plus', 3 = 'raw' */
+    double clf_thr;
+    double coef[4];
+    double intercept;
+    const int32_t* frame_off; /* [num_frames + 1] */
+    const float* bbox;        /* [N,4] x, y, width, height */
+    const float* center;      /* [N,2] normalised box centre (val_to_imdb.py:211-212) */
+    const double* score;      /* [N] obj * cls_score */
+    const int32_t* cls;       /* [N] */
+    int32_t* pairs;           /* out [num_frames - 1, max_det, 2] */
+    int32_t* pair_count;      /* out [num_frames - 1] */
+    double* ws_dist;          /* workspace [num_frames - 1, ws_pitch] candidate distances */
+    int32_t* ws_idx;          /* workspace [num_frames - 1, ws_pitch] */
+    int32_t ws_pitch;         /* >= number of finite distances of any frame pair (n1 * n2 always suffices) */
+    int32_t* status;          /* optional [1]: TSCD_ERR_CAPACITY when a frame exceeds max_det or ws_pitch */
+} tscd_repp_link_args;
+int tscd_repp_link(const tscd_repp_link_args* args, void* stream);
+
 /* ---- long-clip mode: exchange of the global-frame bank rows between ranks ----------------------
  * One clip sharded by frame: every rank runs K1-K3 on its own frames [n_local_frames local | n_global_frames global], then the
  * ranks all-gather ONE packed buffer each (ncclAllGather, issued by the host) and every rank builds the virtual clip

@@ -181,6 +181,14 @@ class PackRowsArgs(C.Structure):
     _fields_ = _fields("num_frames:i cap:i rows:p count:p offsets:p packed:p")
 
 
+class ReppLinkArgs(C.Structure):
+    _fields_ = [("num_frames", C.c_int32), ("max_det", C.c_int32), ("distance_func", C.c_int32), ("clf_mode", C.c_int32),
+                ("clf_thr", C.c_double), ("coef", C.c_double * 4), ("intercept", C.c_double),
+                ("frame_off", C.c_void_p), ("bbox", C.c_void_p), ("center", C.c_void_p), ("score", C.c_void_p), ("cls", C.c_void_p),
+                ("pairs", C.c_void_p), ("pair_count", C.c_void_p), ("ws_dist", C.c_void_p), ("ws_idx", C.c_void_p),
+                ("ws_pitch", C.c_int32), ("status", C.c_void_p)]
+
+
 _lib = None
 
 # every symbol include/tscd_b200.h declares: (name, restype, argtypes)
@@ -213,6 +221,7 @@ SYMBOLS = [
     ("tscd_final_rows", C.c_int, [C.POINTER(FinalRowsArgs), C.c_void_p]),
     ("tscd_pack_detections", C.c_int, [C.POINTER(PackDetectionsArgs), C.c_void_p]),
     ("tscd_pack_rows", C.c_int, [C.POINTER(PackRowsArgs), C.c_void_p]),
+    ("tscd_repp_link", C.c_int, [C.POINTER(ReppLinkArgs), C.c_void_p]),
     ("tscd_bank_pack_bytes", C.c_int64, [C.c_int32, C.c_int32]),
     ("tscd_bank_pack", C.c_int, [C.POINTER(BankPackArgs), C.c_void_p]),
     ("tscd_bank_unpack", C.c_int, [C.POINTER(BankUnpackArgs), C.c_void_p]),

@@ -93,6 +93,12 @@ def make_head_class():
             hw = [tuple(t.shape[-2:]) for t in cls_o]
             an = ops.AnchorSpec(hw, tuple(self.strides))
             head = ops.HeadViews.from_levels(reg_o, obj_o, cls_o, an)
+            if reg_o[0].dtype == torch.float16 and self.num_classes <= 59:
+                # conv-tower seam: instead of the reference's flatten / cat / permute copies into [F, A, 5+C]
+                # (tscd_head.py:374-376), ONE pass writes the fused layout -- a 64 / 128-byte row [reg4|obj|cls C] per anchor
+                # plus the dense objectness plane -- that the row kernels of K1 / K3 consume (csrc/select_rows.cu); sigmoid
+                # and decode stay fused in those kernels, values are copied bit for bit
+                head = ops.pack_head(head)
             feats = tuple(ops.view_levels(f) for f in (f_cls, f_reg, f_edge))
             st = self._stage()
             st.cfg.final_nms_thresh = nms_thresh

@@ -111,6 +111,23 @@ class CAFMState:
         self.reg, self.cls = views["reg"].view(slots, kmax, 4 * dim), views["cls"].view(slots, kmax, 4 * dim)
         self.nreg, self.ncls, self.time = views["nreg"].view(slots, kmax), views["ncls"].view(slots, kmax), views["time"].view(slots, dim)
 
+    _FIELDS = ("n", "out", "edge", "reg", "cls", "nreg", "ncls", "time")
+
+    def select(self, slot_ids) -> "CAFMState":
+        """Copy of the given slots as a dense state (batch position i <- slot slot_ids[i]): for batches that run only some of
+        the concurrent video streams (tscd_b200.clips.ClipScheduler near the end of a rank's work list)."""
+        sub = CAFMState(len(slot_ids), self.kmax, self.dim, self.flat.device)
+        idx = torch.as_tensor(list(slot_ids), dtype=torch.long, device=self.flat.device)
+        for f in self._FIELDS:
+            getattr(sub, f).copy_(getattr(self, f).index_select(0, idx))
+        return sub
+
+    def update_from(self, sub: "CAFMState", slot_ids):
+        """Write a dense sub-state back into its slots (inverse of select)."""
+        idx = torch.as_tensor(list(slot_ids), dtype=torch.long, device=self.flat.device)
+        for f in self._FIELDS:
+            getattr(self, f).index_copy_(0, idx, getattr(sub, f))
+
 
 class AggregationStage:
     """forward(): head outputs + feature planes of B clips x F frames -> refined detections of the B x L local frames."""
