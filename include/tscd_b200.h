@@ -478,6 +478,48 @@ typedef struct {
 } tscd_cafm_chain_args;
 int tscd_cafm_chain(const tscd_cafm_chain_args* args, void* stream);
 
+/* Wide CAFM chain for frames of MORE than 32 proposals (mode B: 50..500 per frame, the shipped TSCD-L configurations).  The
+ * recurrence over the local frames stays sequential, but every frame's step runs as batch-wide launches over all clips instead
+ * of inside one CTA per clip (see csrc/cafm.cu):  phase 0 once;  per frame f: phase 1 (permutation + 16-bit query input
+ * rows into qin16), then the CALLER runs tscd_linear (q = W_q qin16, rows [B*kmax]) and tscd_frame_flash (8 heads x 32, row
+ * ranges q_beg/q_end/kv_beg/kv_end, keys / values = the k_reg / v_reg projections) into `attn`, then phase 2 (identity +
+ * LayerNorms, outputs, state);  phase 3 once (matching embeddings into the carried state).  `base` is the argument block of
+ * tscd_cafm_chain: feat / edge / kin (fp32), lap_*, state and output fields are used; kproj*, vproj*, wq*, sc_* are not. */
+typedef struct {
+    tscd_cafm_chain_args base;
+    void* qin16;             /* out (phase 1) [B*kmax, D] 16-bit (out_dtype) */
+    const float* attn;       /* in  (phase 2) [B*kmax, D] attention output of the caller's tscd_frame_flash */
+    int32_t* q_beg;          /* out (phase 1) [B] row ranges for tscd_frame_flash */
+    int32_t* q_end;
+    int32_t* kv_beg;
+    int32_t* kv_end;
+    int32_t* ctl;            /* scratch [B,8] */
+    int32_t* perm_s;         /* scratch [B,kmax] */
+    int32_t* prow_s;         /* scratch [B,kmax] */
+    int32_t* ord_prev;       /* scratch [B,kmax] */
+    int32_t* n_prev;         /* scratch [B] */
+    int32_t* last_l0;        /* scratch [B] */
+} tscd_cafm_wide_args;
+int tscd_cafm_wide(const tscd_cafm_wide_args* args, int phase, int frame, void* stream);
+
+/* Cosine multi-head attention over ragged row sets (csrc/frame_flash.cu): for item i and every head,
+ * softmax(q^ k^T) v with q = rows [q_beg[i], q_end[i]) of `q`, k / v = rows [kv_beg[i], kv_end[i]) of `k` / `v`, q and k
+ * L2-normalised per head, no scale -- PositionMHAttention.forward (tscd_matching.py:31-60) and MHAttention.forward (:159-181)
+ * for frames of any size (mma.sync flash kernel; head_dim 32 or 128; 16-bit q / k / v, fp32 output written at the query rows). */
+typedef struct {
+    int32_t num_items;
+    int32_t heads, head_dim;
+    int32_t dtype;               /* TSCD_F16 / TSCD_BF16 */
+    int32_t max_q;               /* upper bound of q_end[i] - q_beg[i] (grid size) */
+    const int32_t* q_beg; const int32_t* q_end;      /* [num_items] device */
+    const int32_t* kv_beg; const int32_t* kv_end;
+    const void* q; int32_t ldq;  /* row pitches in elements, multiples of 8 */
+    const void* k; int32_t ldk;
+    const void* v; int32_t ldv;
+    float* out; int32_t ldo;
+} tscd_frame_flash_args;
+int tscd_frame_flash(const tscd_frame_flash_args* args, void* stream);
+
 /* ---- TaskAligned attention + LayerNorms ---------------------------------------------------------------------
  * tscd_frame_attention: MHAttention.forward (tscd_matching.py:159-181) for every local frame at once:
  * per frame and head, softmax(q^ k^T) v with L2-normalised q,k (no scale), queries/keys/values all from the

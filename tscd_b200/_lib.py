@@ -129,6 +129,16 @@ class CafmChainArgs(C.Structure):
                        "st_time:p sc_qin:p sc_q:p sc_k:p ref_n:p lap_col:p lap_row:p out16:p out32:p perm:p status:p emb_dtype:i")
 
 
+class CafmWideArgs(C.Structure):
+    _fields_ = [("base", CafmChainArgs)] + _fields("qin16:p attn:p q_beg:p q_end:p kv_beg:p kv_end:p ctl:p perm_s:p prow_s:p ord_prev:p "
+                                                   "n_prev:p last_l0:p")
+
+
+class FrameFlashArgs(C.Structure):
+    _fields_ = _fields("num_items:i heads:i head_dim:i dtype:i max_q:i q_beg:p q_end:p kv_beg:p kv_end:p q:p ldq:i k:p ldk:i v:p ldv:i "
+                       "out:p ldo:i")
+
+
 class CafmCostArgs(C.Structure):
     _fields_ = _fields("B:i L:i D:i kmax:i lrow_off:p resume:p st_n:p emb_reg:p emb_cls:p norm_reg:p norm_cls:p "
                        "st_reg:p st_cls:p st_nreg:p st_ncls:p cost:p ref_n:p emb_dtype:i")
@@ -215,6 +225,8 @@ SYMBOLS = [
     ("tscd_cafm_lap", C.c_int, [C.POINTER(CafmLapArgs), C.c_void_p]),
     ("tscd_debug_chain_clocks", C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
     ("tscd_cafm_chain", C.c_int, [C.POINTER(CafmChainArgs), C.c_void_p]),
+    ("tscd_cafm_wide", C.c_int, [C.POINTER(CafmWideArgs), C.c_int, C.c_int, C.c_void_p]),
+    ("tscd_frame_flash", C.c_int, [C.POINTER(FrameFlashArgs), C.c_void_p]),
     ("tscd_frame_attention", C.c_int, [C.POINTER(FrameAttentionArgs), C.c_void_p]),
     ("tscd_residual_ln2", C.c_int, [C.POINTER(ResidualLn2Args), C.c_void_p]),
     ("tscd_final_expand", C.c_int, [C.POINTER(FinalExpandArgs), C.c_void_p]),
@@ -247,7 +259,7 @@ def lib():
 
 # kernels launched per C-ABI call (for the bench's `gpu_launches` claim)
 _DEBUG_SYNC = os.environ.get("TSCD_DEBUG_SYNC", "0") == "1"
-KERNELS_PER_CALL = {"tscd_gather": 2, "tscd_nms_large": 3, "tscd_bank_unpack": 2, "tscd_pack_detections": 2, "tscd_pack_rows": 2}
+KERNELS_PER_CALL = {"tscd_gather": 2, "tscd_nms_large": 3, "tscd_bank_unpack": 2, "tscd_pack_detections": 2, "tscd_pack_rows": 2, "tscd_cafm_wide_p1": 2}
 launch_count = 0
 # optional per-entry-point CUDA-event timing: {"names": set or None (= all), "events": {name: [(start, end), ...]}}
 profile = None

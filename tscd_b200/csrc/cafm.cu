@@ -594,6 +594,38 @@ __global__ void __launch_bounds__(32) cafm_lap_kernel(const tscd_cafm_lap_args a
     }
 }
 
+// Frames of <= 32 proposals (kmax <= 32): 32 problems per CTA, one warp each, 4 KB of staged costs per warp.  A matching is a
+// latency-bound serial algorithm; as 1-warp CTAs with the general 37 KB scratch the B*L problems took two waves spread thinly
+// over every SM -- packed 32 to a CTA they run in ONE wave on a quarter of the SMs, and the rest of the GPU stays free for the
+// classification branch's tensor-core kernels on the side stream.
+constexpr int kLapPack = 32;
+__global__ void __launch_bounds__(kLapPack * 32) cafm_lap_small_kernel(const tscd_cafm_lap_args a) {
+    extern __shared__ __align__(16) unsigned char lap_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lf = blockIdx.x * kLapPack + warp;
+    if (lf >= a.num_frames) return;
+    const int n = a.lrow_off[lf + 1] - a.lrow_off[lf];
+    const int np = a.ref_n[lf];
+    if (n <= 0 || np <= 0) return;
+    const int KM = a.kmax;                           // <= 32
+    const float* C = a.cost + (int64_t)lf * KM * KM;
+    float* cost_s = reinterpret_cast<float*>(lap_smem) + warp * 1024;
+    for (int t = lane; t < np * n; t += 32) { const int r = t / n, c = t - r * n; cost_s[t] = C[(int64_t)r * KM + c]; }
+    __syncwarp();
+    const bool tr = n < np;
+    int32_t* col = a.lap_col + (int64_t)lf * KM;
+    int32_t* row = a.lap_row + (int64_t)lf * KM;
+    int c4r, r4c;
+    lap_warp_fast(cost_s, n, np, n, lane, &c4r, &r4c);
+    if (!tr) {
+        if (lane < np) col[lane] = c4r;
+        if (lane < n) row[lane] = r4c;
+    } else {
+        if (lane < np) col[lane] = r4c;
+        if (lane < n) row[lane] = c4r;
+    }
+}
+
 __device__ __forceinline__ void layer_norm_row(const float* x, const float* w, const float* b, float* y, int D, int lane) {
     float s = 0.f;
     for (int c = lane; c < D; c += 32) s += x[c];
@@ -1216,6 +1248,210 @@ __global__ void __launch_bounds__(kFastThreads, 1) cafm_chain_fast_kernel(const 
     if (tid == 0) a.st_n[b] = n_prev;
 }
 
+
+// ================================================================================================================
+// Wide chain (frames of MORE than 32 proposals: mode B, 50..500 per frame).  The recurrence is sequential over the local
+// frames of a clip, but one frame's step is a large parallel problem (SE gate on n x 256 elements, a 256 x 256
+// projection, an n x n attention over 8 heads, two LayerNorms): run by ONE CTA per clip it kept a handful of SMs busy
+// for ~1 ms per frame.  Here every step is a short sequence of batch-wide launches over ALL clips:
+//     tscd_cafm_wide(phase 0)            once: n_prev / ord_prev from the carried state
+//     for f in 0 .. L-1:
+//         tscd_cafm_wide(phase 1, f)     permutation of the frame (block scans) + query input rows (SE gate) -> 16-bit
+//         tscd_linear                    q = W_q qin                 (tcgen05 GEMM over B * kmax rows)
+//         tscd_frame_flash               softmax(q^ k^T) v           (mma.sync flash kernel, 8 heads x 32)
+//         tscd_cafm_wide(phase 2, f)     identity + LayerNorm -> new memory, decoder norm -> output rows, state update
+//     tscd_cafm_wide(phase 3)            once: matching embeddings of the last frame into the carried state
+// Same arithmetic as cafm_chain_kernel (tscd_matching.py:722-888) except that q / k / v enter the two products as 16-bit
+// operands, like the fast chain for small frames.
+// ================================================================================================================
+struct WideCtl { int n, np, first, l0, skip, pad0, pad1, pad2; };
+
+__global__ void cafm_wide_begin_kernel(const tscd_cafm_wide_args w) {
+    const tscd_cafm_chain_args& a = w.base;
+    const int b = blockIdx.x, KM = a.kmax;
+    const bool resume = a.resume ? (a.resume[b] != 0) : false;
+    for (int r = threadIdx.x; r < KM; r += blockDim.x) w.ord_prev[(int64_t)b * KM + r] = r;
+    if (threadIdx.x == 0) { w.n_prev[b] = resume ? a.st_n[b] : 0; w.last_l0[b] = -1; }
+}
+
+// one CTA (512 threads >= kmax) per clip: control block + perm / prow of frame f (tscd_matching.py:813-844)
+__global__ void __launch_bounds__(512) cafm_wide_perm_kernel(const tscd_cafm_wide_args w, int f) {
+    __shared__ int scan[40];
+    const tscd_cafm_chain_args& a = w.base;
+    const int b = blockIdx.x, KM = a.kmax, tid = threadIdx.x;
+    const int lf = b * a.L + f;
+    const int l0 = a.lrow_off[lf], n = a.lrow_off[lf + 1] - l0;
+    const bool resume = a.resume ? (a.resume[b] != 0) : false;
+    int n_prev = w.n_prev[b];
+    WideCtl* ctl = reinterpret_cast<WideCtl*>(w.ctl) + b;
+    int* perm = w.perm_s + (int64_t)b * KM;
+    int* prow = w.prow_s + (int64_t)b * KM;
+    const int* ord = w.ord_prev + (int64_t)b * KM;
+    __syncthreads();                                 // every thread has read n_prev before thread 0 may reset it
+    if (n == 0 || n > KM || n > kChainMax || n_prev > KM) {
+        if (tid == 0) {
+            if (n == 0) { if (f == 0 && !resume) w.n_prev[b] = 0; }
+            else atomicMin(a.status, TSCD_ERR_CAPACITY);
+            ctl->n = 0; ctl->skip = 1; ctl->l0 = l0; ctl->first = 0; ctl->np = 0;
+            w.q_beg[b] = b * KM; w.q_end[b] = b * KM; w.kv_beg[b] = l0; w.kv_end[b] = l0;
+        }
+        return;
+    }
+    const bool first = (f == 0 && !resume) || n_prev == 0;
+    const int np = first ? n : n_prev;
+    const int32_t* colo = a.lap_col + (int64_t)lf * KM;
+    const int32_t* rowo = a.lap_row + (int64_t)lf * KM;
+    if (np <= n) {
+        if (tid < np) { perm[tid] = colo[first ? tid : ord[tid]]; prow[tid] = tid; }
+        // unmatched current columns follow in ascending order
+        const int flag = (tid < n && rowo[tid] == -1) ? 1 : 0;
+        int tot;
+        const int ex = block_excl_scan(flag, scan, &tot);
+        if (flag && np + ex < n) { perm[np + ex] = tid; prow[np + ex] = -1 - tid; }
+    } else {
+        int c = -1;
+        if (tid < np) c = colo[ord[tid]];
+        const int flag = c >= 0 ? 1 : 0;
+        int tot;
+        const int ex = block_excl_scan(flag, scan, &tot);
+        if (flag && ex < n) { perm[ex] = c; prow[ex] = tid; }
+    }
+    if (tid == 0) {
+        ctl->n = n; ctl->np = np; ctl->first = first ? 1 : 0; ctl->l0 = l0; ctl->skip = 0;
+        w.q_beg[b] = b * KM; w.q_end[b] = b * KM + n; w.kv_beg[b] = l0; w.kv_end[b] = l0 + n;
+    }
+}
+
+// query input rows (ReferringCrossAttentionLayer: SE(tgt, query_edge) + query_pos), 8 rows per CTA, thread = channel
+template <typename T>
+__global__ void __launch_bounds__(256) cafm_wide_qin_kernel(const tscd_cafm_wide_args w) {
+    __shared__ float w1[64], w2[64];
+    const tscd_cafm_chain_args& a = w.base;
+    const int b = blockIdx.x, KM = a.kmax, D = a.D, c = threadIdx.x;
+    const WideCtl ctl = reinterpret_cast<const WideCtl*>(w.ctl)[b];
+    if (threadIdx.x < 64) { w1[threadIdx.x] = a.se_w1[threadIdx.x]; w2[threadIdx.x] = a.se_w2[threadIdx.x]; }
+    __syncthreads();
+    T* qin = reinterpret_cast<T*>(w.qin16) + (int64_t)b * KM * D;
+    const float* st_out = a.st_out + (int64_t)b * KM * D;
+    const float* st_edge = a.st_edge + (int64_t)b * KM * D;
+    const float tm = a.st_time[(int64_t)b * D + c];
+    const int* prow = w.prow_s + (int64_t)b * KM;
+    for (int r = blockIdx.y * 8; r < min(KM, blockIdx.y * 8 + 8); ++r) {
+        float v = 0.f;
+        if (!ctl.skip && r < ctl.n) {
+            if (ctl.first) {
+                v = a.kin[(int64_t)(ctl.l0 + r) * D + c];                  // SE(feat, edge) + time of this frame
+            } else {
+                const int p = prow[r];
+                const float tg = p >= 0 ? st_out[(int64_t)p * D + c] : a.feat[(int64_t)(ctl.l0 - 1 - p) * D + c];
+                const float ed = p >= 0 ? st_edge[(int64_t)p * D + c] : a.edge[(int64_t)(ctl.l0 - 1 - p) * D + c];
+                v = se_gate(tg, ed, w1, w2) + tm;
+            }
+        }
+        qin[(int64_t)r * D + c] = cvt_from_float<T>(v);
+    }
+}
+
+// identity + attention -> LayerNorm (new last_outputs) -> decoder norm (output rows); state update.  Warp per row.
+template <typename T>
+__global__ void __launch_bounds__(256) cafm_wide_finish_kernel(const tscd_cafm_wide_args w, int f) {
+    __shared__ float xs[8][256], ys[8][256];
+    const tscd_cafm_chain_args& a = w.base;
+    const int b = blockIdx.x, KM = a.kmax, D = a.D, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const WideCtl ctl = reinterpret_cast<const WideCtl*>(w.ctl)[b];
+    if (ctl.skip) return;
+    const int lf = b * a.L + f, n = ctl.n, l0 = ctl.l0;
+    const bool first = ctl.first != 0;
+    const int* perm = w.perm_s + (int64_t)b * KM;
+    float* st_out = a.st_out + (int64_t)b * KM * D;
+    float* st_edge = a.st_edge + (int64_t)b * KM * D;
+    const int r = blockIdx.y * 8 + warp;
+    if (r < n) {
+        const int pr = perm[r];
+        const int idr = first ? r : pr;
+        for (int c = lane; c < D; c += 32)
+            xs[warp][c] = a.feat[(int64_t)(l0 + idr) * D + c] + w.attn[((int64_t)b * KM + r) * D + c];
+        __syncwarp();
+        layer_norm_row(xs[warp], a.ln_w, a.ln_b, ys[warp], D, lane);
+        __syncwarp();
+        for (int c = lane; c < D; c += 32) st_out[(int64_t)r * D + c] = ys[warp][c];          // new last_outputs
+        layer_norm_row(ys[warp], a.dec_w, a.dec_b, xs[warp], D, lane);
+        __syncwarp();
+        const int dst = l0 + pr;
+        for (int c = lane; c < D; c += 32) {
+            reinterpret_cast<T*>(a.out16)[(int64_t)dst * D + c] = cvt_from_float<T>(xs[warp][c]);
+            if (a.out32) a.out32[(int64_t)dst * D + c] = xs[warp][c];
+            st_edge[(int64_t)r * D + c] = a.edge[(int64_t)(l0 + idr) * D + c];
+        }
+        if (lane == 0) {
+            if (a.perm) a.perm[l0 + r] = pr;
+            w.ord_prev[(int64_t)b * KM + r] = idr;
+        }
+    }
+    if (blockIdx.y == 0) {
+        for (int c = threadIdx.x; c < D; c += blockDim.x) a.st_time[(int64_t)b * D + c] = a.time_emb[(int64_t)lf * D + c];
+        if (threadIdx.x == 0) { w.n_prev[b] = n; w.last_l0[b] = l0; }
+    }
+}
+
+// carry the last frame's matching embeddings (in matched order) to the next call
+__global__ void __launch_bounds__(256) cafm_wide_end_kernel(const tscd_cafm_wide_args w) {
+    const tscd_cafm_chain_args& a = w.base;
+    const int b = blockIdx.x, KM = a.kmax, E = 4 * a.D, tid = threadIdx.x;
+    const int n_prev = w.n_prev[b], last_l0 = w.last_l0[b];
+    const int* ord = w.ord_prev + (int64_t)b * KM;
+    if (last_l0 >= 0) {
+        float* st_reg = a.st_reg + (int64_t)b * KM * E;
+        float* st_cls = a.st_cls + (int64_t)b * KM * E;
+        const float* Rc = a.emb_reg + (int64_t)last_l0 * E;
+        const float* Cc = a.emb_cls + (int64_t)last_l0 * E;
+        for (int t = tid; t < n_prev * (E / 4); t += blockDim.x) {
+            const int r = t / (E / 4), c4 = t - r * (E / 4);
+            const int src = ord[r];
+            reinterpret_cast<float4*>(st_reg)[(int64_t)r * (E / 4) + c4] = reinterpret_cast<const float4*>(Rc)[(int64_t)src * (E / 4) + c4];
+            reinterpret_cast<float4*>(st_cls)[(int64_t)r * (E / 4) + c4] = reinterpret_cast<const float4*>(Cc)[(int64_t)src * (E / 4) + c4];
+        }
+        for (int r = tid; r < n_prev; r += blockDim.x) {
+            a.st_nreg[(int64_t)b * KM + r] = a.norm_reg[last_l0 + ord[r]];
+            a.st_ncls[(int64_t)b * KM + r] = a.norm_cls[last_l0 + ord[r]];
+        }
+    }
+    if (tid == 0) a.st_n[b] = n_prev;
+}
+
+}  // namespace tscd
+
+extern "C" int tscd_cafm_wide(const tscd_cafm_wide_args* w, int phase, int frame, void* stream) {
+    using namespace tscd;
+    if (!w) return TSCD_ERR_INVALID_ARG;
+    const tscd_cafm_chain_args& a = w->base;
+    if (a.B <= 0 || a.L <= 0 || a.D != 256 || a.kmax <= 0 || a.kmax > kChainMax || frame < 0 || frame >= a.L) return TSCD_ERR_INVALID_ARG;
+    if (a.emb_dtype != TSCD_F32 || !w->ctl || !w->perm_s || !w->prow_s || !w->ord_prev || !w->n_prev || !w->last_l0 || !w->q_beg ||
+        !w->q_end || !w->kv_beg || !w->kv_end || !w->qin16 || !w->attn)
+        return TSCD_ERR_INVALID_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const dim3 rows(a.B, (a.kmax + 7) / 8);
+    switch (phase) {
+        case 0: cafm_wide_begin_kernel<<<a.B, 256, 0, st>>>(*w); break;
+        case 1:
+            cafm_wide_perm_kernel<<<a.B, 512, 0, st>>>(*w, frame);
+            if (a.out_dtype == TSCD_F16) cafm_wide_qin_kernel<__half><<<rows, 256, 0, st>>>(*w);
+            else if (a.out_dtype == TSCD_BF16) cafm_wide_qin_kernel<__nv_bfloat16><<<rows, 256, 0, st>>>(*w);
+            else return TSCD_ERR_UNSUPPORTED;
+            break;
+        case 2:
+            if (a.out_dtype == TSCD_F16) cafm_wide_finish_kernel<__half><<<rows, 256, 0, st>>>(*w, frame);
+            else if (a.out_dtype == TSCD_BF16) cafm_wide_finish_kernel<__nv_bfloat16><<<rows, 256, 0, st>>>(*w, frame);
+            else return TSCD_ERR_UNSUPPORTED;
+            break;
+        case 3: cafm_wide_end_kernel<<<a.B, 256, 0, st>>>(*w); break;
+        default: return TSCD_ERR_INVALID_ARG;
+    }
+    TSCD_CUDA_CHECK_LAUNCH();
+    return TSCD_OK;
+}
+
+namespace tscd {
 }  // namespace tscd
 
 extern "C" int tscd_cafm_prep(const tscd_cafm_prep_args* a, void* stream) {
@@ -1251,6 +1487,13 @@ extern "C" int tscd_cafm_cost(const tscd_cafm_cost_args* a, void* stream) {
 extern "C" int tscd_cafm_lap(const tscd_cafm_lap_args* a, void* stream) {
     using namespace tscd;
     if (!a || a->num_frames <= 0 || a->kmax <= 0 || a->kmax > kChainMax) return TSCD_ERR_INVALID_ARG;
+    if (a->kmax <= 32) {
+        const size_t sm = (size_t)kLapPack * 1024 * sizeof(float);
+        if (cudaFuncSetAttribute(cafm_lap_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return TSCD_ERR_CUDA;
+        cafm_lap_small_kernel<<<(a->num_frames + kLapPack - 1) / kLapPack, kLapPack * 32, sm, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+        TSCD_CUDA_CHECK_LAUNCH();
+        return TSCD_OK;
+    }
     const size_t smem = sizeof(LapSmem);
     if (cudaFuncSetAttribute(cafm_lap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TSCD_ERR_CUDA;
     cafm_lap_kernel<<<a->num_frames, 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*a);

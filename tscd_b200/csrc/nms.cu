@@ -56,6 +56,53 @@ __device__ inline ClsScratch carve_cls_scratch(unsigned char* p, int cap) {
     return c;
 }
 
+// per-class greedy: lane j owns members j, j+32, ... (S slots, <= 32 * S members); the class leader walks the score order.
+// S = 1 when every class holds at most 32 boxes (always the case for the stage's final NMS with <= 32 proposals per frame: a
+// proposal contributes one row per class, post_process.py:36-46) -- a third of the IoU tests and no slot selection.
+template <int S>
+__device__ __forceinline__ void per_class_greedy(const tscd_nms_args& args, int ncl, const float4* sbox, const float* sarea, ClsScratch sc,
+                                                 int warp, int lane, int nw) {
+    const double thr = (double)args.iou_thresh;
+    for (int ci = warp; ci < ncl; ci += nw) {
+        const int c = sc.ids[ci];
+        const int o0 = sc.off[c], cnt = sc.off[c + 1] - o0;
+        float4 b[S];
+        float ar[S];
+        unsigned dead = 0;
+#pragma unroll
+        for (int q = 0; q < S; ++q) {
+            const int k = q * 32 + lane;
+            if (k < cnt) { const int r = sc.list[o0 + k]; b[q] = sbox[r]; ar[q] = sarea[r]; }
+            else { b[q] = make_float4(0.f, 0.f, 0.f, 0.f); ar[q] = 0.f; dead |= 1u << q; }
+        }
+        for (int k = 0; k < cnt; ++k) {
+            const int q0 = k >> 5, l0 = k & 31;
+            // is member k still alive?  (owner lane l0, slot q0)
+            const unsigned dk = __shfl_sync(0xffffffffu, dead, l0);
+            if ((dk >> q0) & 1u) continue;
+            float4 bk;
+            float ak;
+            {
+                const float4 src = (S == 1 || q0 == 0) ? b[0] : (q0 == 1 ? b[S > 1 ? 1 : 0] : b[S - 1]);
+                const float sa = (S == 1 || q0 == 0) ? ar[0] : (q0 == 1 ? ar[S > 1 ? 1 : 0] : ar[S - 1]);
+                bk.x = __shfl_sync(0xffffffffu, src.x, l0); bk.y = __shfl_sync(0xffffffffu, src.y, l0);
+                bk.z = __shfl_sync(0xffffffffu, src.z, l0); bk.w = __shfl_sync(0xffffffffu, src.w, l0);
+                ak = __shfl_sync(0xffffffffu, sa, l0);
+            }
+#pragma unroll
+            for (int q = 0; q < S; ++q) {
+                const int m = q * 32 + lane;
+                if (m > k && m < cnt && !((dead >> q) & 1u) && iou_gt(bk, ak, b[q], ar[q], thr)) dead |= 1u << q;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < S; ++q) {
+            const int k = q * 32 + lane;
+            if (k < cnt) sc.flag[sc.list[o0 + k]] = ((dead >> q) & 1u) ? 0 : 1;
+        }
+    }
+}
+
 // skey: sorted keys (low 32 bits = inverted original position); sbox/sarea: sorted offset boxes.
 __device__ bool nms_per_class(const tscd_nms_args& args, int frame, int n, const unsigned long long* skey, const float4* sbox,
                               const float* sarea, const int32_t* gcls, ClsScratch sc) {
@@ -85,6 +132,14 @@ __device__ bool nms_per_class(const tscd_nms_args& args, int frame, int n, const
         for (int j = 0; j < 8; ++j) { run += loc[j]; sc.off[1 + lane * 8 + j] = run; }
         __syncwarp();
         if (__any_sync(0xffffffffu, big) && lane == 0) sc.misc[0] = 1;
+        {
+            int mxc = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mxc = max(mxc, loc[j]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mxc = max(mxc, __shfl_xor_sync(0xffffffffu, mxc, o));
+            if (lane == 0) sc.misc[3] = mxc;
+        }
         // compact list of the non-empty classes (ascending ids), kept in sc.ids
         int ncl = 0;
 #pragma unroll
@@ -153,47 +208,8 @@ __device__ bool nms_per_class(const tscd_nms_args& args, int frame, int n, const
     __syncthreads();
     if (sc.misc[0]) return false;
 
-    // per-class greedy: lane j owns members j, j+32, j+64 (<= kClsMaxMembers); the class leader walks the score order
-    const double thr = (double)args.iou_thresh;
-    for (int ci = warp; ci < ncl; ci += nw) {
-        const int c = sc.ids[ci];
-        const int o0 = sc.off[c], cnt = sc.off[c + 1] - o0;
-        constexpr int S = kClsMaxMembers / 32;
-        float4 b[S];
-        float ar[S];
-        unsigned dead = 0;
-#pragma unroll
-        for (int q = 0; q < S; ++q) {
-            const int k = q * 32 + lane;
-            if (k < cnt) { const int r = sc.list[o0 + k]; b[q] = sbox[r]; ar[q] = sarea[r]; }
-            else { b[q] = make_float4(0.f, 0.f, 0.f, 0.f); ar[q] = 0.f; dead |= 1u << q; }
-        }
-        for (int k = 0; k < cnt; ++k) {
-            const int q0 = k >> 5, l0 = k & 31;
-            // is member k still alive?  (owner lane l0, slot q0)
-            const unsigned dk = __shfl_sync(0xffffffffu, dead, l0);
-            if ((dk >> q0) & 1u) continue;
-            float4 bk;
-            float ak;
-            {
-                const float4 src = q0 == 0 ? b[0] : (q0 == 1 ? b[1] : b[S - 1]);
-                const float sa = q0 == 0 ? ar[0] : (q0 == 1 ? ar[1] : ar[S - 1]);
-                bk.x = __shfl_sync(0xffffffffu, src.x, l0); bk.y = __shfl_sync(0xffffffffu, src.y, l0);
-                bk.z = __shfl_sync(0xffffffffu, src.z, l0); bk.w = __shfl_sync(0xffffffffu, src.w, l0);
-                ak = __shfl_sync(0xffffffffu, sa, l0);
-            }
-#pragma unroll
-            for (int q = 0; q < S; ++q) {
-                const int m = q * 32 + lane;
-                if (m > k && m < cnt && !((dead >> q) & 1u) && iou_gt(bk, ak, b[q], ar[q], thr)) dead |= 1u << q;
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < S; ++q) {
-            const int k = q * 32 + lane;
-            if (k < cnt) sc.flag[sc.list[o0 + k]] = ((dead >> q) & 1u) ? 0 : 1;
-        }
-    }
+    if (sc.misc[3] <= 32) per_class_greedy<1>(args, ncl, sbox, sarea, sc, warp, lane, nw);
+    else per_class_greedy<kClsMaxMembers / 32>(args, ncl, sbox, sarea, sc, warp, lane, nw);
     __syncthreads();
     // score-ordered compaction of the kept boxes, truncated to max_keep
     {

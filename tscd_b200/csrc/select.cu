@@ -86,8 +86,9 @@ __global__ void __launch_bounds__(256) classmax_kernel(const tscd_select_args ar
     }
 }
 
+// rp: row pitch (elements) of the fused head layout (csrc/select_rows.cu; fp16 only), 0 = generic strided views
 template <typename T, bool PRE>
-__global__ void __launch_bounds__(kSelThreads, PRE ? 3 : 2) select_kernel(const tscd_select_args args, int sort_cap) {
+__global__ void __launch_bounds__(kSelThreads, PRE ? 3 : 2) select_kernel(const tscd_select_args args, int sort_cap, int rp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int frame = blockIdx.x;
     const tscd_anchors& an = args.anchors;
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(kSelThreads, PRE ? 3 : 2) select_kernel(const 
                                 ((reinterpret_cast<uintptr_t>(op) | reinterpret_cast<uintptr_t>(cp)) & 15) == 0 &&
                                 (args.cls.chan_stride[l] % VMAX) == 0 && (args.obj.frame_stride[l] % VMAX) == 0 &&
                                 (args.cls.frame_stride[l] % VMAX) == 0;
-            nvec_l[l] = planar ? nl / VMAX : 0;
+            nvec_l[l] = (planar && !(rp && !PRE)) ? nl / VMAX : 0;
         }
         goff[l + 1] = goff[l] + nvec_l[l];
     }
@@ -187,7 +188,42 @@ __global__ void __launch_bounds__(kSelThreads, PRE ? 3 : 2) select_kernel(const 
             }
         }
     }
-    for (int l = 0; l < an.num_levels; ++l) {
+    // fused 64 / 128-byte rows [reg4|obj|cls C|pad] (mode B streams every anchor's row): one thread per anchor, the row as
+    // 16-byte vector loads -- consecutive lanes read consecutive rows, so the four loads of a warp cover whole sectors
+    if (rp && sizeof(T) == 2 && !PRE) {
+        for (int l = 0; l < an.num_levels; ++l) {
+            const int a_lo = an.level_start[l], nl = an.level_start[l + 1] - a_lo;
+            const uint4* rowp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(args.reg.ptr[l]) + (int64_t)frame * args.reg.frame_stride[l]);
+            const int rpv = rp / 8;
+            for (int i = threadIdx.x; i < nl; i += blockDim.x) {
+                float b = -INFINITY, o = 0.f;
+                int bidx = 0;
+                for (int v = 0; v < rpv; ++v) {
+                    const uint4 q = __ldg(rowp + (int64_t)i * rpv + v);
+                    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const int e = v * 8 + t;
+                        const float x = __half2float(__ushort_as_half((unsigned short)((w[t >> 1] >> (16 * (t & 1))) & 0xffffu)));
+                        if (e == 4) o = x;
+                        else if (e >= 5 && e - 5 < C && x > b) { b = x; bidx = e - 5; }   // first maximum wins (torch.max)
+                    }
+                }
+                if (sig) o = sigmoidf_ref(o);
+                float key = o;
+                if (modeB) {
+                    if (sig) b = sigmoidf_ref(b);
+                    key = __fmul_rn(o, b);
+                    n_ge += (key >= args.conf_thresh) ? 1 : 0;
+                }
+                const int a = a_lo + i;
+                keys[a] = f2ord(key);
+                conf_s[a] = b;
+                cls_s[a] = (unsigned char)bidx;
+            }
+        }
+    }
+    for (int l = 0; l < (rp && sizeof(T) == 2 && !PRE ? 0 : an.num_levels); ++l) {
         const int a_lo = an.level_start[l], nl = an.level_start[l + 1] - a_lo;
         const T* op = reinterpret_cast<const T*>(args.obj.ptr[l]) + (int64_t)frame * args.obj.frame_stride[l];
         const T* cp = reinterpret_cast<const T*>(args.cls.ptr[l]) + (int64_t)frame * args.cls.frame_stride[l];
@@ -424,8 +460,9 @@ extern "C" int tscd_select(const tscd_select_args* a, void* stream) {
     do {                                                                                                             \
         e = cudaFuncSetAttribute(select_kernel<TT, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
         if (e != cudaSuccess) return TSCD_ERR_CUDA;                                                                  \
-        select_kernel<TT, PP><<<a->num_frames, kSelThreads, smem, st>>>(*a, n64);                                    \
+        select_kernel<TT, PP><<<a->num_frames, kSelThreads, smem, st>>>(*a, n64, rows_rp);                           \
     } while (0)
+    const int rows_rp = fused_rows_pitch(a->anchors, a->reg, a->obj, a->cls, a->num_classes, a->head_dtype, false);
     tscd_select_args la = *a;                 // late path: no workspace reads
     if (late) { la.ws_conf = nullptr; la.ws_cls = nullptr; }
     a = &la;

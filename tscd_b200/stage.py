@@ -507,14 +507,19 @@ class AggregationStage:
         # ---- fc_reg_matcher, TaskAligned, prediction heads ---------------------------------------------
         matched16, matched32 = ops.linear(cafm16, w.fc_w, w.fc_b, m_dev=n_loc_dev, want16=True, want32=trace is not None, tag="fc_reg_matcher")
         _, reg_deltas = ops.linear(matched16, w.reg_w, w.reg_b, m_dev=n_loc_dev, want16=False, want32=True, tag="reg_pred")
-        fast_ta = kmax <= 32          # 16-bit q/k/v + mma.sync attention (csrc/tail.cu frame_attention16_kernel)
-        ta_q16, ta_q = ops.linear(iou_reg16, w.ta_wq, m_dev=n_loc_dev, want16=fast_ta, want32=not fast_ta, tag="ta_q")
-        ta_kv16, ta_kv = ops.linear(matched16, w.ta_wkv, m_dev=n_loc_dev, want16=fast_ta, want32=not fast_ta, tag="ta_kv")
-        tq, tkv = (ta_q16, ta_kv16) if fast_ta else (ta_q, ta_kv)
+        # TaskAligned attention on 16-bit q/k/v: frames of <= 32 rows in one mma.sync tile (csrc/tail.cu frame_attention16_kernel),
+        # larger frames on the flash kernel (csrc/frame_flash.cu)
+        tq, _ = ops.linear(iou_reg16, w.ta_wq, m_dev=n_loc_dev, want16=True, want32=False, tag="ta_q")
+        tkv, _ = ops.linear(matched16, w.ta_wkv, m_dev=n_loc_dev, want16=True, want32=False, tag="ta_kv")
         att = f32z(loc_cap, 4 * D)
-        ops.call("tscd_frame_attention", L.FrameAttentionArgs, num_frames=B * Lf, heads=8, head_dim=(4 * D) // 8,
-                 in_dtype=dt if fast_ta else torch.float32, lrow_off=lay.lrow_off, q=tq, ldq=tq.stride(0), k=tkv, ldk=tkv.stride(0),
-                 v=tkv[:, 4 * D:], ldv=tkv.stride(0), out=att, ldo=att.stride(0))
+        if kmax <= 32:
+            ops.call("tscd_frame_attention", L.FrameAttentionArgs, num_frames=B * Lf, heads=8, head_dim=(4 * D) // 8,
+                     in_dtype=dt, lrow_off=lay.lrow_off, q=tq, ldq=tq.stride(0), k=tkv, ldk=tkv.stride(0),
+                     v=tkv[:, 4 * D:], ldv=tkv.stride(0), out=att, ldo=att.stride(0))
+        else:
+            ops.call("tscd_frame_flash", L.FrameFlashArgs, tag="task_aligned", num_items=B * Lf, heads=8, head_dim=(4 * D) // 8, dtype=dt,
+                     max_q=kmax, q_beg=lay.lrow_off, q_end=lay.lrow_off[1:], kv_beg=lay.lrow_off, kv_end=lay.lrow_off[1:],
+                     q=tq, ldq=tq.stride(0), k=tkv, ldk=tkv.stride(0), v=tkv[:, 4 * D:], ldv=tkv.stride(0), out=att, ldo=att.stride(0))
         # LN(LN(x + attn)) with the 1-output objectness head (matcher_obj_pred) fused: the LayerNorm output row is in
         # registers, so the refined features are only materialised for tracing
         objref32 = f32z(loc_cap, 4 * D) if trace is not None else None
@@ -582,8 +587,8 @@ class AggregationStage:
                  lrow_off=lay.lrow_off, bank_reg=bank_reg, bank_edge=bank_edge, time_emb=te32, se_w1=w.se_w1,
                  se_w2=w.se_w2, emb_reg=emb_reg32, emb_cls=emb_cls32, feat=feat, edge=edge, feat16=feat16,
                  kin16=kin16, kin=kin, norm_reg=norm_reg, norm_cls=norm_cls, emb_dtype=emb_dtype)
-        kproj16, kproj = ops.linear(kin16, w.cafm_wk, m_dev=n_loc_dev, want16=fast, want32=not fast, tag="cafm_k")
-        vproj16, vproj = ops.linear(feat16, w.cafm_wv, m_dev=n_loc_dev, want16=fast, want32=not fast, tag="cafm_v")
+        kproj16, kproj = ops.linear(kin16, w.cafm_wk, m_dev=n_loc_dev, want16=True, want32=False, tag="cafm_k")
+        vproj16, vproj = ops.linear(feat16, w.cafm_wv, m_dev=n_loc_dev, want16=True, want32=False, tag="cafm_v")
         cafm16 = torch.empty(loc_cap, D, dtype=dt, device=dev)
         cafm32 = f32z(loc_cap, D) if want_debug else None
         perm = torch.empty(loc_cap, dtype=torch.int32, device=dev) if want_debug else None
@@ -597,19 +602,64 @@ class AggregationStage:
         lap_row = torch.empty(B * Lf, kmax, dtype=torch.int32, device=dev)
         ops.call("tscd_cafm_lap", L.CafmLapArgs, num_frames=B * Lf, kmax=kmax, lrow_off=lay.lrow_off, ref_n=ref_n, cost=cost_full,
                  lap_col=lap_col, lap_row=lap_row)
-        ops.call("tscd_cafm_chain", L.CafmChainArgs, B=B, F=F, L=Lf, D=D, kmax=kmax, out_dtype=dt, row_off=lay.row_off,
-                 lrow_off=lay.lrow_off, resume=resume, feat=feat, edge=edge, kin=kin, kproj=kproj, vproj=vproj,
-                 kproj16=kproj16, vproj16=vproj16, wq16=w.cafm_wq16 if fast else None,
-                 bank_reg=bank_reg if fast else None, bank_edge=bank_edge if fast else None, time_emb=te32, emb_reg=emb_reg32, emb_cls=emb_cls32, norm_reg=norm_reg, norm_cls=norm_cls,
-                 wq_t=w.cafm_wq_t, se_w1=w.se_w1, se_w2=w.se_w2, ln_w=w.cafm_ln_w, ln_b=w.cafm_ln_b,
-                 dec_w=w.cafm_dec_w, dec_b=w.cafm_dec_b, st_n=state.n, st_out=state.out, st_edge=state.edge,
-                 st_reg=state.reg, st_cls=state.cls, st_nreg=state.nreg, st_ncls=state.ncls, st_time=state.time,
-                 sc_qin=None if fast else f32z(B, kmax, D), sc_q=None if fast else f32z(B, kmax, D),
-                 sc_k=None if fast else f32z(B, kmax, D), ref_n=ref_n, lap_col=lap_col, lap_row=lap_row,
-                 out16=cafm16, out32=cafm32, perm=perm, status=status, emb_dtype=emb_dtype)
+        chain_kw = dict(B=B, F=F, L=Lf, D=D, kmax=kmax, out_dtype=dt, row_off=lay.row_off,
+                        lrow_off=lay.lrow_off, resume=resume, feat=feat, edge=edge, kin=kin, kproj=None, vproj=None,
+                        kproj16=kproj16 if fast else None, vproj16=vproj16 if fast else None, wq16=w.cafm_wq16 if fast else None,
+                        bank_reg=bank_reg if fast else None, bank_edge=bank_edge if fast else None, time_emb=te32, emb_reg=emb_reg32,
+                        emb_cls=emb_cls32, norm_reg=norm_reg, norm_cls=norm_cls,
+                        wq_t=None, se_w1=w.se_w1, se_w2=w.se_w2, ln_w=w.cafm_ln_w, ln_b=w.cafm_ln_b,
+                        dec_w=w.cafm_dec_w, dec_b=w.cafm_dec_b, st_n=state.n, st_out=state.out, st_edge=state.edge,
+                        st_reg=state.reg, st_cls=state.cls, st_nreg=state.nreg, st_ncls=state.ncls, st_time=state.time,
+                        sc_qin=None, sc_q=None, sc_k=None, ref_n=ref_n, lap_col=lap_col, lap_row=lap_row,
+                        out16=cafm16, out32=cafm32, perm=perm, status=status, emb_dtype=emb_dtype)
+        if fast:
+            ops.call("tscd_cafm_chain", L.CafmChainArgs, **chain_kw)
+        else:
+            self._cafm_wide(chain_kw, kproj16, vproj16, B, Lf, kmax, D)
         if debug is not None:        # matching tables of every local frame (tests: LSAP exactness on the device's own costs)
             debug.update(cafm_cost=cost_full, cafm_ref_n=ref_n, cafm_lap_col=lap_col, cafm_lap_row=lap_row)
         return cafm16, cafm32, perm, te32
+
+    # ------------------------------------------------------------------------------------------------------
+    def _cafm_wide(self, chain_kw, kproj16, vproj16, B: int, Lf: int, kmax: int, D: int):
+        """CAFM recurrence for frames of more than 32 proposals (mode B: 50..500 per frame): per local frame a short sequence
+        of batch-wide launches over all clips -- permutation + SE-gated query rows, q projection on the tcgen05 GEMM, the
+        n x n cosine attention on the mma.sync flash kernel, LayerNorms + state update (csrc/cafm.cu "wide chain")."""
+        import ctypes as C
+        w, dev, dt = self.w, self.device, self.cfg.dtype
+        base = L.CafmChainArgs()
+        for k_, v_ in chain_kw.items():
+            if isinstance(v_, torch.Tensor) or v_ is None:
+                v_ = ops._p(v_)
+            elif isinstance(v_, torch.dtype):
+                v_ = ops._DT[v_]
+            setattr(base, k_, v_)
+        rows = _r128(B * kmax)
+        i32 = lambda *s_: torch.empty(*s_, dtype=torch.int32, device=dev)  # noqa: E731
+        qin16 = torch.empty(rows, D, dtype=dt, device=dev)
+        attn = torch.empty(rows, D, dtype=torch.float32, device=dev)
+        rng = [i32(B) for _ in range(4)]
+        scratch = dict(ctl=i32(B, 8), perm_s=i32(B, kmax), prow_s=i32(B, kmax), ord_prev=i32(B, kmax), n_prev=i32(B), last_l0=i32(B))
+        wa = L.CafmWideArgs()
+        wa.base = base
+        wa.qin16, wa.attn = ops._p(qin16), ops._p(attn)
+        wa.q_beg, wa.q_end, wa.kv_beg, wa.kv_end = (ops._p(t) for t in rng)
+        for k_, v_ in scratch.items():
+            setattr(wa, k_, ops._p(v_))
+
+        def phase(p_, f_):
+            with L.timed("tscd_cafm_wide", f"phase{p_}"):
+                L.check(L.lib().tscd_cafm_wide(C.byref(wa), p_, f_, ops._stream()), "tscd_cafm_wide_p1" if p_ == 1 else "tscd_cafm_wide")
+
+        phase(0, 0)
+        for f in range(Lf):
+            phase(1, f)
+            q16, _ = ops.linear(qin16, w.cafm_wq16, want16=True, want32=False, tag="cafm_q")
+            ops.call("tscd_frame_flash", L.FrameFlashArgs, tag="cafm", num_items=B, heads=8, head_dim=D // 8, dtype=dt, max_q=kmax,
+                     q_beg=rng[0], q_end=rng[1], kv_beg=rng[2], kv_end=rng[3], q=q16, ldq=q16.stride(0), k=kproj16,
+                     ldk=kproj16.stride(0), v=vproj16, ldv=vproj16.stride(0), out=attn, ldo=attn.stride(0))
+            phase(2, f)
+        phase(3, 0)
 
     # ------------------------------------------------------------------------------------------------------
     @staticmethod
