@@ -58,7 +58,7 @@ CONFIGS = {
     "ovis_a_k30": dict(C=25, F=32, L=8, mode="A", pre_k=750, top_k=30, clips=148, replays=28, obj_means=[-3.0],
                        workload="TSCD-L OVIS 25cls, 32-frame clip (8 local + 24 global) @576x576 (6804 anchors), pre-NMS top-750 -> "
                                 "NMS0.75 -> 30 proposals/frame, agg+agg_iou MCA + CAFM + TaskAligned + final NMS0.5"),
-    "ovis_l_modeB": dict(C=25, F=32, L=8, mode="B", minimal_limit=50, maximal_limit=500, clips=8, replays=8,
+    "ovis_l_modeB": dict(C=25, F=32, L=8, mode="B", minimal_limit=50, maximal_limit=500, clips=64, replays=4,
                          obj_means=[-13.5, -8.0, -10.2, -10.6, -9.7, -11.0, -13.0, -9.9],
                          workload="TSCD-L OVIS 25cls (exps/TSCD_OVIS/ovis_tscd_large.py), 32-frame clip (8 local + 24 global) @576x576, "
                                   "postprocess_widx min 50 / max 500, no pre-NMS, ragged 50..500 proposals/frame, full TSCD tail"),

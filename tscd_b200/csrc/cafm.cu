@@ -1397,7 +1397,8 @@ __global__ void __launch_bounds__(256) cafm_wide_finish_kernel(const tscd_cafm_w
 // carry the last frame's matching embeddings (in matched order) to the next call
 __global__ void __launch_bounds__(256) cafm_wide_end_kernel(const tscd_cafm_wide_args w) {
     const tscd_cafm_chain_args& a = w.base;
-    const int b = blockIdx.x, KM = a.kmax, E = 4 * a.D, tid = threadIdx.x;
+    const int b = blockIdx.x, KM = a.kmax, E = 4 * a.D, tid = blockIdx.y * blockDim.x + threadIdx.x;
+    const int nthreads = gridDim.y * blockDim.x;
     const int n_prev = w.n_prev[b], last_l0 = w.last_l0[b];
     const int* ord = w.ord_prev + (int64_t)b * KM;
     if (last_l0 >= 0) {
@@ -1405,13 +1406,13 @@ __global__ void __launch_bounds__(256) cafm_wide_end_kernel(const tscd_cafm_wide
         float* st_cls = a.st_cls + (int64_t)b * KM * E;
         const float* Rc = a.emb_reg + (int64_t)last_l0 * E;
         const float* Cc = a.emb_cls + (int64_t)last_l0 * E;
-        for (int t = tid; t < n_prev * (E / 4); t += blockDim.x) {
+        for (int t = tid; t < n_prev * (E / 4); t += nthreads) {
             const int r = t / (E / 4), c4 = t - r * (E / 4);
             const int src = ord[r];
             reinterpret_cast<float4*>(st_reg)[(int64_t)r * (E / 4) + c4] = reinterpret_cast<const float4*>(Rc)[(int64_t)src * (E / 4) + c4];
             reinterpret_cast<float4*>(st_cls)[(int64_t)r * (E / 4) + c4] = reinterpret_cast<const float4*>(Cc)[(int64_t)src * (E / 4) + c4];
         }
-        for (int r = tid; r < n_prev; r += blockDim.x) {
+        for (int r = tid; r < n_prev; r += nthreads) {
             a.st_nreg[(int64_t)b * KM + r] = a.norm_reg[last_l0 + ord[r]];
             a.st_ncls[(int64_t)b * KM + r] = a.norm_cls[last_l0 + ord[r]];
         }
@@ -1444,7 +1445,7 @@ extern "C" int tscd_cafm_wide(const tscd_cafm_wide_args* w, int phase, int frame
             else if (a.out_dtype == TSCD_BF16) cafm_wide_finish_kernel<__nv_bfloat16><<<rows, 256, 0, st>>>(*w, frame);
             else return TSCD_ERR_UNSUPPORTED;
             break;
-        case 3: cafm_wide_end_kernel<<<a.B, 256, 0, st>>>(*w); break;
+        case 3: cafm_wide_end_kernel<<<dim3(a.B, 32), 256, 0, st>>>(*w); break;
         default: return TSCD_ERR_INVALID_ARG;
     }
     TSCD_CUDA_CHECK_LAUNCH();

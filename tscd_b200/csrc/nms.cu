@@ -30,7 +30,7 @@ constexpr int kNmsThreads = 256;
 // Returns false (nothing written) when the frame does not qualify: class ids outside [0, 256), a class with more
 // than kClsMaxMembers boxes, or a cross-class pair above the IoU threshold; the caller then runs its general algorithm.
 // -------------------------------------------------------------------------------------------------------------
-constexpr int kClsMaxMembers = 96;
+constexpr int kClsMaxMembers = 128;
 
 struct ClsScratch {          // carved from dynamic shared memory by the caller
     unsigned short* list;    // [n] sorted indices grouped by class (score order inside a class)
@@ -83,8 +83,11 @@ __device__ __forceinline__ void per_class_greedy(const tscd_nms_args& args, int 
             float4 bk;
             float ak;
             {
-                const float4 src = (S == 1 || q0 == 0) ? b[0] : (q0 == 1 ? b[S > 1 ? 1 : 0] : b[S - 1]);
-                const float sa = (S == 1 || q0 == 0) ? ar[0] : (q0 == 1 ? ar[S > 1 ? 1 : 0] : ar[S - 1]);
+                float4 src = b[0];
+                float sa = ar[0];
+#pragma unroll
+                for (int q = 1; q < S; ++q)
+                    if (q0 == q) { src = b[q]; sa = ar[q]; }
                 bk.x = __shfl_sync(0xffffffffu, src.x, l0); bk.y = __shfl_sync(0xffffffffu, src.y, l0);
                 bk.z = __shfl_sync(0xffffffffu, src.z, l0); bk.w = __shfl_sync(0xffffffffu, src.w, l0);
                 ak = __shfl_sync(0xffffffffu, sa, l0);
@@ -209,6 +212,7 @@ __device__ bool nms_per_class(const tscd_nms_args& args, int frame, int n, const
     if (sc.misc[0]) return false;
 
     if (sc.misc[3] <= 32) per_class_greedy<1>(args, ncl, sbox, sarea, sc, warp, lane, nw);
+    else if (sc.misc[3] <= 64) per_class_greedy<2>(args, ncl, sbox, sarea, sc, warp, lane, nw);
     else per_class_greedy<kClsMaxMembers / 32>(args, ncl, sbox, sarea, sc, warp, lane, nw);
     __syncthreads();
     // score-ordered compaction of the kept boxes, truncated to max_keep
@@ -239,9 +243,12 @@ __device__ bool nms_per_class(const tscd_nms_args& args, int frame, int n, const
     return true;
 }
 
-__global__ void __launch_bounds__(kNmsThreads, 4) nms_kernel(const tscd_nms_args args, int smem_cap) {
+// only_redo: second launch after nms_matrix_kernel -- only the frames it marked with keep_count == -1 (per-class decomposition
+// not applicable, too large for the suppression matrix) are processed
+__global__ void __launch_bounds__(kNmsThreads, 4) nms_kernel(const tscd_nms_args args, int smem_cap, int only_redo) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int frame = blockIdx.x;
+    if (only_redo && args.keep_count[frame] != -1) return;
     int n = args.count[frame];
     if (n > smem_cap) {
         if (threadIdx.x == 0) { atomicMin(args.status, TSCD_ERR_CAPACITY); args.keep_count[frame] = 0; }
@@ -435,11 +442,11 @@ __global__ void __launch_bounds__(kNmsThreads, 4) nms_kernel(const tscd_nms_args
 constexpr int kNmsMatThreads = 512;
 constexpr int kNmsMatCap = 768;      // 768 x 24 words = 72 KB
 
-__global__ void __launch_bounds__(kNmsMatThreads) nms_matrix_kernel(const tscd_nms_args args, int smem_cap) {
+__global__ void __launch_bounds__(kNmsMatThreads) nms_matrix_kernel(const tscd_nms_args args, int smem_cap, int has_matrix) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int frame = blockIdx.x;
     int n = args.count[frame];
-    if (n > smem_cap || n > kNmsMatCap) {
+    if (n > smem_cap) {
         if (threadIdx.x == 0) { atomicMin(args.status, TSCD_ERR_CAPACITY); args.keep_count[frame] = 0; }
         return;
     }
@@ -493,6 +500,10 @@ __global__ void __launch_bounds__(kNmsMatThreads) nms_matrix_kernel(const tscd_n
     // the suppression-matrix area doubles as scratch of the per-class fast path
     if (nms_per_class(args, frame, n, skey, sbox, sarea, gcls, carve_cls_scratch(reinterpret_cast<unsigned char*>(smask), smem_cap)))
         return;
+    if (!has_matrix) {                  // no room for the suppression matrix: hand the frame to the lazy kernel (second launch)
+        if (threadIdx.x == 0) args.keep_count[frame] = -1;
+        return;
+    }
 
     const double thr = (double)args.iou_thresh;
     const int W = (n + 31) >> 5;
@@ -574,21 +585,24 @@ extern "C" int tscd_nms(const tscd_nms_args* a, void* stream) {
     if (cap64 < kNmsMatThreads) cap64 = kNmsMatThreads;   // ... and E * blockDim.x keys of the block sort (either kernel)
     size_t smem = (size_t)cap64 * (8 + 16 + 4 + 4) + 16;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (cap > 64 && cap <= kNmsMatCap && (int64_t)a->max_keep * 4 >= cap) {
-        // most candidates survive: per-class decomposition / suppression-matrix kernel (the lazy kernel stops early and wins
-        // when only the first few survivors are wanted, and for tiny frames)
-        size_t smem_m = (size_t)cap * ((cap + 31) / 32) * 4;
+    int only_redo = 0;
+    if (cap > 64 && (int64_t)a->max_keep * 4 >= cap && !a->rank) {
+        // most candidates survive: per-class decomposition, then (cap <= 768) the suppression-matrix algorithm in the same
+        // kernel or (larger caps) the lazy kernel for the frames the decomposition does not cover.  (The lazy kernel stops
+        // early and wins when only the first few survivors are wanted, and for tiny frames.)
+        size_t smem_m = cap <= kNmsMatCap ? (size_t)cap * ((cap + 31) / 32) * 4 : 0;
         if (smem_m < cls_scratch_bytes(cap64)) smem_m = cls_scratch_bytes(cap64);
         smem_m += (size_t)cap64 * (8 + 16 + 4) + 16;
         if (cudaFuncSetAttribute(nms_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m) != cudaSuccess)
             return TSCD_ERR_CUDA;
-        nms_matrix_kernel<<<a->num_frames, kNmsMatThreads, smem_m, st>>>(*a, cap64);
+        nms_matrix_kernel<<<a->num_frames, kNmsMatThreads, smem_m, st>>>(*a, cap64, cap <= kNmsMatCap ? 1 : 0);
         TSCD_CUDA_CHECK_LAUNCH();
-        return TSCD_OK;
+        if (cap <= kNmsMatCap) return TSCD_OK;
+        only_redo = 1;
     }
     if (cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return TSCD_ERR_CUDA;
-    nms_kernel<<<a->num_frames, kNmsThreads, smem, st>>>(*a, cap64);
+    nms_kernel<<<a->num_frames, kNmsThreads, smem, st>>>(*a, cap64, only_redo);
     TSCD_CUDA_CHECK_LAUNCH();
     return TSCD_OK;
 }
