@@ -406,6 +406,13 @@ typedef struct {
      * emb_cls point to 16-bit [loc_cap, 4D] embeddings (the GEMM outputs as the tensor cores produced them), the costs run on
      * mma.sync with fp32 accumulation and norm_reg / norm_cls are OUTPUTS (written for the rows of every frame) */
     int32_t emb_dtype;
+    /* optional, with emb_dtype == TSCD_F32 and kmax > 32: 16-bit copies of emb_reg / emb_cls ([loc_cap, 4D], the same GEMM's
+     * 16-bit output).  When both are set the costs of the wide frames run on mma.sync tensor cores (128 x 64 tiles, fp32
+     * accumulation, fp32 norms from tscd_cafm_prep; a carried fp32 state is converted while it is staged) instead of the
+     * fp32 FMA kernel. */
+    const void* emb_reg16;
+    const void* emb_cls16;
+    int32_t emb16_dtype;         /* TSCD_F16 / TSCD_BF16 */
 } tscd_cafm_cost_args;
 int tscd_cafm_cost(const tscd_cafm_cost_args* args, void* stream);
 

@@ -141,7 +141,7 @@ class FrameFlashArgs(C.Structure):
 
 class CafmCostArgs(C.Structure):
     _fields_ = _fields("B:i L:i D:i kmax:i lrow_off:p resume:p st_n:p emb_reg:p emb_cls:p norm_reg:p norm_cls:p "
-                       "st_reg:p st_cls:p st_nreg:p st_ncls:p cost:p ref_n:p emb_dtype:i")
+                       "st_reg:p st_cls:p st_nreg:p st_ncls:p cost:p ref_n:p emb_dtype:i emb_reg16:p emb_cls16:p emb16_dtype:i")
 
 
 class CafmLapArgs(C.Structure):

@@ -139,6 +139,136 @@ __global__ void __launch_bounds__(256) cafm_prep_kernel(const tscd_cafm_prep_arg
     }
 }
 
+// ---------------------------------------------------------------------------------------------- matching costs, wide frames
+// Frames of more than 32 proposals with 16-bit copies of the matching embeddings: one CTA (8 warps) per (local frame,
+// 128 reference rows, 64 current rows).  Both 1024-dim embeddings stream through shared memory in 64-dim chunks (cp.async,
+// double buffered, 144-byte rows: ldmatrix conflict-free); warp w owns reference rows [16w, 16w+16) x all 64 columns:
+// 8 n-tiles of mma.sync m16n8k16 per k-step, fp32 accumulation, the two cosines kept in separate accumulators.  Norms are the
+// fp32 ones of tscd_cafm_prep (or of the carried state, whose fp32 embeddings are converted while they are staged).
+constexpr int kCwRows = 128, kCwCols = 64, kCwPitch = 72, kCwThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kCwThreads) cafm_cost_wide16_kernel(const tscd_cafm_cost_args a) {
+    extern __shared__ __align__(16) unsigned char cw_smem[];
+    T* sA = reinterpret_cast<T*>(cw_smem);                        // [2][128][72]
+    T* sB = sA + 2 * kCwRows * kCwPitch;                          // [2][64][72]
+    const int lf = blockIdx.x, b = lf / a.L, f = lf - b * a.L;
+    const int l0 = a.lrow_off[lf], n = a.lrow_off[lf + 1] - l0;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    if (n <= 0) {
+        if (a.ref_n && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) a.ref_n[lf] = 0;
+        return;
+    }
+    constexpr int E = 1024;
+    const int KM = a.kmax;
+    // reference side: previous non-empty local frame, else the carried state (resume), else the frame itself
+    const T *Rp = nullptr, *Cp = nullptr;
+    const float *sR = nullptr, *sC = nullptr, *nRp = nullptr, *nCp = nullptr;
+    int np = 0;
+    for (int p = f - 1; p >= 0 && np == 0; --p) {
+        const int pl0 = a.lrow_off[b * a.L + p], pn = a.lrow_off[b * a.L + p + 1] - pl0;
+        if (pn > 0) {
+            np = pn;
+            Rp = reinterpret_cast<const T*>(a.emb_reg16) + (int64_t)pl0 * E; Cp = reinterpret_cast<const T*>(a.emb_cls16) + (int64_t)pl0 * E;
+            nRp = a.norm_reg + pl0; nCp = a.norm_cls + pl0;
+        }
+    }
+    if (np == 0) {
+        const int sn = (a.resume && a.resume[b]) ? a.st_n[b] : 0;
+        if (sn > 0) {
+            np = sn;
+            sR = a.st_reg + (int64_t)b * KM * E; sC = a.st_cls + (int64_t)b * KM * E;
+            nRp = a.st_nreg + (int64_t)b * KM; nCp = a.st_ncls + (int64_t)b * KM;
+        } else {
+            np = n;
+            Rp = reinterpret_cast<const T*>(a.emb_reg16) + (int64_t)l0 * E; Cp = reinterpret_cast<const T*>(a.emb_cls16) + (int64_t)l0 * E;
+            nRp = a.norm_reg + l0; nCp = a.norm_cls + l0;
+        }
+    }
+    if (a.ref_n && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) a.ref_n[lf] = (np > KM || n > KM) ? 0 : np;
+    const int rb = blockIdx.y * kCwRows, cb = blockIdx.z * kCwCols;
+    if (rb >= np || cb >= n || np > KM || n > KM) return;
+    const T* Rc = reinterpret_cast<const T*>(a.emb_reg16) + (int64_t)l0 * E;
+    const T* Cc = reinterpret_cast<const T*>(a.emb_cls16) + (int64_t)l0 * E;
+
+    auto stage = [&](int s, int buf) {                  // chunk s: embedding s >> 4, dims [(s & 15) * 64, +64)
+        const int which = s >> 4, d0 = (s & 15) * 64;
+        T* dA = sA + buf * kCwRows * kCwPitch;
+        T* dB = sB + buf * kCwCols * kCwPitch;
+        const T* P16 = which == 0 ? Rp : Cp;
+        const float* P32 = which == 0 ? sR : sC;
+        for (int i = tid; i < kCwRows * 8; i += kCwThreads) {
+            const int r = i >> 3, c = (i & 7) * 8;
+            T* dst = dA + r * kCwPitch + c;
+            if (rb + r >= np) { *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0); continue; }
+            if (P16) {
+                cp_async16(dst, P16 + (int64_t)(rb + r) * E + d0 + c);
+            } else {                                    // carried fp32 state: convert while staging
+                const float4 u = *reinterpret_cast<const float4*>(P32 + (int64_t)(rb + r) * E + d0 + c);
+                const float4 v = *reinterpret_cast<const float4*>(P32 + (int64_t)(rb + r) * E + d0 + c + 4);
+                uint4 o;
+                o.x = pack2<T>(u.x, u.y); o.y = pack2<T>(u.z, u.w); o.z = pack2<T>(v.x, v.y); o.w = pack2<T>(v.z, v.w);
+                *reinterpret_cast<uint4*>(dst) = o;
+            }
+        }
+        const T* Q16 = which == 0 ? Rc : Cc;
+        for (int i = tid; i < kCwCols * 8; i += kCwThreads) {
+            const int r = i >> 3, c = (i & 7) * 8;
+            T* dst = dB + r * kCwPitch + c;
+            if (cb + r < n) cp_async16(dst, Q16 + (int64_t)(cb + r) * E + d0 + c);
+            else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+        }
+        cp_async_commit();
+    };
+
+    float acc[2][8][4];
+#pragma unroll
+    for (int w = 0; w < 2; ++w)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) acc[w][nt][0] = acc[w][nt][1] = acc[w][nt][2] = acc[w][nt][3] = 0.f;
+    stage(0, 0);
+#pragma unroll 1
+    for (int s = 0; s < 32; ++s) {
+        const int buf = s & 1;
+        cp_async_wait_all();
+        __syncthreads();                                 // chunk s landed; every warp is done with the other buffer
+        if (s + 1 < 32) stage(s + 1, buf ^ 1);
+        const T* tA = sA + buf * kCwRows * kCwPitch;
+        const T* tB = sB + buf * kCwCols * kCwPitch;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t fa[4];
+            ldsm_x4(fa, tA + (warp * 16 + (lane & 15)) * kCwPitch + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+            for (int ntp = 0; ntp < 4; ++ntp) {
+                uint32_t fb[4];
+                ldsm_x4(fb, tB + (ntp * 16 + (lane & 7) + ((lane >> 4) & 1) * 8) * kCwPitch + ks * 16 + ((lane >> 3) & 1) * 8);
+                if (s < 16) { mma16816<T>(acc[0][2 * ntp], fa, fb[0], fb[1]); mma16816<T>(acc[0][2 * ntp + 1], fa, fb[2], fb[3]); }
+                else { mma16816<T>(acc[1][2 * ntp], fa, fb[0], fb[1]); mma16816<T>(acc[1][2 * ntp + 1], fa, fb[2], fb[3]); }
+            }
+        }
+    }
+    float* out = a.cost + (int64_t)lf * KM * KM;
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+        const int r = rb + warp * 16 + g + hr * 8;
+        if (r >= np) continue;
+        const float nr = nRp[r], nc = nCp[r];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = cb + nt * 8 + 2 * t4 + e;
+                if (c >= n) continue;
+                const float cr = acc[0][nt][hr * 2 + e] / (nr * a.norm_reg[l0 + c]);
+                const float cq = acc[1][nt][hr * 2 + e] / (nc * a.norm_cls[l0 + c]);
+                float v = 1.f - (cr + cq) / 2.f;
+                if (v != v) v = 0.f;                     // tscd_matching.py:930 NaN -> 0
+                out[(int64_t)r * KM + c] = v;
+            }
+    }
+}
+
 constexpr int kSmall = 32;   // frames with <= kSmall proposals keep their whole working set in shared memory
 
 struct LapSmem {
@@ -1477,6 +1607,22 @@ extern "C" int tscd_cafm_cost(const tscd_cafm_cost_args* a, void* stream) {
         if (a->emb_dtype == TSCD_F16) cafm_cost16_kernel<__half><<<a->B * a->L, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
         else if (a->emb_dtype == TSCD_BF16) cafm_cost16_kernel<__nv_bfloat16><<<a->B * a->L, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
         else return TSCD_ERR_UNSUPPORTED;
+        TSCD_CUDA_CHECK_LAUNCH();
+        return TSCD_OK;
+    }
+    if (a->emb_reg16 && a->emb_cls16 && a->kmax > 32) {      // wide frames, 16-bit copies available: tensor-core kernel
+        const size_t sm = (size_t)2 * (kCwRows + kCwCols) * kCwPitch * 2;
+        const dim3 grid(a->B * a->L, (a->kmax + kCwRows - 1) / kCwRows, (a->kmax + kCwCols - 1) / kCwCols);
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        if (a->emb16_dtype == TSCD_F16) {
+            if (cudaFuncSetAttribute(cafm_cost_wide16_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return TSCD_ERR_CUDA;
+            cafm_cost_wide16_kernel<__half><<<grid, kCwThreads, sm, st>>>(*a);
+        } else if (a->emb16_dtype == TSCD_BF16) {
+            if (cudaFuncSetAttribute(cafm_cost_wide16_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return TSCD_ERR_CUDA;
+            cafm_cost_wide16_kernel<__nv_bfloat16><<<grid, kCwThreads, sm, st>>>(*a);
+        } else {
+            return TSCD_ERR_UNSUPPORTED;
+        }
         TSCD_CUDA_CHECK_LAUNCH();
         return TSCD_OK;
     }

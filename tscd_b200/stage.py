@@ -466,7 +466,7 @@ class AggregationStage:
         emb16 = kmax <= 32 and trace is None
         (iou_cls16, iou_cls32), (iou_reg16, iou_reg32) = aggregate.mca_forward(
             lay, w.agg_iou, bank_cls, bank_reg, bank_score, n_rows_dev, n_loc_dev, need_reg=True,
-            sim_thresh=cfg.sim_thresh, conf_sim_thresh=cfg.conf_sim_thresh, cls_out=(kmax <= 32, not emb16), tag="agg_iou")
+            sim_thresh=cfg.sim_thresh, conf_sim_thresh=cfg.conf_sim_thresh, cls_out=(True, not emb16), tag="agg_iou")
         ev_fork = torch.cuda.Event()
         ev_fork.record(main)
         with torch.cuda.stream(side):
@@ -499,7 +499,8 @@ class AggregationStage:
             before_cafm(state)
         cafm16, cafm32, perm, te32 = self.run_cafm(lay, bank_reg, bank_edge, iou_reg16 if kmax <= 32 else iou_reg32,
                                                    iou_cls16 if kmax <= 32 else iou_cls32, time_embedding, kmax,
-                                                   state, resume, status, want_debug=trace is not None, debug=trace)
+                                                   state, resume, status, want_debug=trace is not None, debug=trace,
+                                                   emb16=None if kmax <= 32 else (iou_reg16, iou_cls16))
         if after_cafm is not None:
             after_cafm(state)
         f32z = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731  (fully written before read)
@@ -560,8 +561,10 @@ class AggregationStage:
 
     # ------------------------------------------------------------------------------------------------------
     def run_cafm(self, lay: ops.AttnLayoutT, bank_reg, bank_edge, emb_reg32, emb_cls32, time_embedding, kmax: int,
-                 state: CAFMState, resume: torch.Tensor, status: torch.Tensor, want_debug=False, debug: Optional[dict] = None):
+                 state: CAFMState, resume: torch.Tensor, status: torch.Tensor, want_debug=False, debug: Optional[dict] = None,
+                 emb16=None):
         """CAFM (AwarePositionRegMatcher.forward, tscd_matching.py:722-888) for all clips of the batch.
+        emb16 (wide frames): 16-bit copies of the fp32 matching embeddings -> tensor-core cost kernel.
         emb_reg32 / emb_cls32 [loc_cap,1024] are the agg_iou outputs used for matching only: fp32, or -- frames of <= 32
         proposals -- the 16-bit GEMM outputs (fp32 tensors are rounded to the operand type then)."""
         w, dev, dt, D = self.w, self.device, self.cfg.dtype, self.cfg.dim
@@ -597,7 +600,8 @@ class AggregationStage:
         ops.call("tscd_cafm_cost", L.CafmCostArgs, B=B, L=Lf, D=D, kmax=kmax, lrow_off=lay.lrow_off, resume=resume,
                  st_n=state.n, emb_reg=emb_reg32, emb_cls=emb_cls32, norm_reg=norm_reg, norm_cls=norm_cls,
                  st_reg=state.reg, st_cls=state.cls, st_nreg=state.nreg, st_ncls=state.ncls, cost=cost_full, ref_n=ref_n,
-                 emb_dtype=emb_dtype)
+                 emb_dtype=emb_dtype, emb_reg16=None if emb16 is None else emb16[0], emb_cls16=None if emb16 is None else emb16[1],
+                 emb16_dtype=dt)
         lap_col = torch.empty(B * Lf, kmax, dtype=torch.int32, device=dev)
         lap_row = torch.empty(B * Lf, kmax, dtype=torch.int32, device=dev)
         ops.call("tscd_cafm_lap", L.CafmLapArgs, num_frames=B * Lf, kmax=kmax, lrow_off=lay.lrow_off, ref_n=ref_n, cost=cost_full,
