@@ -316,11 +316,14 @@ def reference_gpu_eager(cfg, dev, reps=3):
 
 
 # ------------------------------------------------------------------------------------------------- per-kernel roofline
-KERNEL_OF = {"tscd_select": "select_kernel (+ classmax_kernel for NCHW planes)", "tscd_nms": "nms_kernel / nms_matrix_kernel / nmsl_*",
+KERNEL_OF = {"tscd_select": "select_rows_kernel (fused rows, mode A) / select_kernel (+ classmax_kernel for NCHW planes)",
+             "tscd_nms": "nms_kernel / nms_matrix_kernel / nmsl_*", "tscd_cafm_wide": "cafm_wide_{begin,perm,qin,finish,end}_kernel",
+             "tscd_frame_flash": "frame_flash_kernel",
              "tscd_gather": "rows_gather_kernel (+ offsets)", "tscd_local_offsets": "local_offsets_kernel", "tscd_attn_rowmeta": "attn_rowmeta_kernel",
              "tscd_qkv_project": "gemm_tn_kernel<256,.,EPI=1>", "tscd_linear": "gemm_tn_kernel", "tscd_attn_pv": "attn_pv_kernel",
              "tscd_attn_round2": "attn_round2_kernel", "tscd_attn_prep": "attn_prep_kernel", "tscd_transpose_clip": "transpose_clip_kernel",
-             "tscd_cafm_prep": "cafm_prep_kernel", "tscd_cafm_cost": "cafm_cost_kernel", "tscd_cafm_lap": "cafm_lap_kernel",
+             "tscd_cafm_prep": "cafm_prep_kernel", "tscd_cafm_cost": "cafm_cost16_kernel / cafm_cost_wide16_kernel / cafm_cost_kernel",
+             "tscd_cafm_lap": "cafm_lap_small_kernel / cafm_lap_kernel",
              "tscd_cafm_chain": "cafm_chain_fast_kernel / cafm_chain_kernel", "tscd_frame_attention": "frame_attention16_kernel / frame_attention_kernel",
              "tscd_residual_ln2": "residual_ln2_kernel", "tscd_final_expand": "final_expand_kernel", "tscd_final_rows": "final_rows_kernel"}
 
@@ -411,8 +414,9 @@ def load_traffic():
     """{kernel key: DRAM bytes per launch} from the committed ncu capture of the headline step (tools/make_profiles.py)."""
     p = os.path.join(ROOT, "profiles", "traffic_r2.json")
     if os.path.exists(p):
-        return json.load(open(p)).get("by_bench_key", {})
-    return {}
+        j = json.load(open(p))
+        return j.get("by_bench_key", {}), j.get("clips_per_replay")
+    return {}, None
 
 
 # ------------------------------------------------------------------------------------------------- main arm
@@ -524,7 +528,9 @@ def run_ours(args, cfg, rank, world, local):
             dist.destroy_process_group()
         return None
     pk = peaks()
-    rows = kernel_rows(cfg, events, linear_info, counts, cand_counts, B, pk, load_traffic() if (args.config == "ovis_a_k30" and B == 64) else {})
+    traffic, traffic_clips = load_traffic()
+    rows = kernel_rows(cfg, events, linear_info, counts, cand_counts, B, pk,
+                       traffic if (args.config == "ovis_a_k30" and B == traffic_clips and args.head_layout == "rows") else {})
     serial_ms = sum(r["avg_launch_ms"] * r["launches_per_step"] for r in rows)
     for r in rows:
         r["share_of_serialised_step"] = round(r["avg_launch_ms"] * r["launches_per_step"] / serial_ms, 4)

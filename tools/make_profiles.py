@@ -68,7 +68,20 @@ def main():
             print(f"{k[:40]:40s} {a[0]:3d} {a[1]:8.1f} {100 * a[1] / tot:5.1f}% {a[2] / a[0] / 1e6:9.1f} {a[2] / a[1] / 1e3:7.0f}")
         traffic[k] = {"launches": a[0], "dram_bytes_per_launch": a[2] / a[0], "time_us_total": a[1]}
     print(f"sum of kernel times {tot:.1f} us over {len(launches)} launches")
-    json.dump(traffic, open(os.path.join(DST, "traffic_r2.json"), "w"), indent=1)
+    # DRAM bytes per launch keyed like bench.py's kernel rows (launch order of the serialised pass: agg_iou first, then agg)
+    per_kernel = collections.OrderedDict()
+    for i, d in launches.items():
+        name = d["name"].split("(")[0].replace("void ", "").replace("tscd::", "")
+        per_kernel.setdefault(name.split("<")[0], []).append(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0))
+    rules = {"tscd_select": ("select_rows_kernel", 0), "tscd_gather": ("rows_gather_kernel", 0), "tscd_attn_pv:agg_iou": ("attn_pv_kernel", 0),
+             "tscd_attn_pv:agg": ("attn_pv_kernel", 1), "tscd_attn_round2:agg_iou.cls": ("attn_round2_kernel", 0),
+             "tscd_attn_round2:agg_iou.obj": ("attn_round2_kernel", 1), "tscd_attn_round2:agg.cls": ("attn_round2_kernel", 2),
+             "tscd_cafm_chain": ("cafm_chain_fast_kernel", 0), "tscd_cafm_prep": ("cafm_prep_kernel", 0), "tscd_cafm_cost": ("cafm_cost16_kernel", 0),
+             "tscd_frame_attention": ("frame_attention16_kernel", 0), "tscd_residual_ln2": ("residual_ln2_kernel", 0),
+             "tscd_nms:pre": ("nms_kernel", 0), "tscd_nms:final_det": ("nms_matrix_kernel", 0)}
+    by_key = {k: per_kernel[n][j] for k, (n, j) in rules.items() if n in per_kernel and j < len(per_kernel[n])}
+    clips = int(os.environ.get("TSCD_PROFILE_CLIPS", "148"))
+    json.dump({"clips_per_replay": clips, "by_bench_key": by_key, "by_cuda_kernel": traffic}, open(os.path.join(DST, "traffic_r2.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":

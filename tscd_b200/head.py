@@ -81,19 +81,33 @@ def make_head_class():
             if imgs.shape[0] == 1:
                 return super().forward(xin, labels, imgs, time_embedding, nms_thresh, lframe, gframe, resume)
             # ---- conv towers: the reference's own modules, channels_last so an anchor's 256 channels are contiguous ----
-            reg_o, obj_o, cls_o, f_cls, f_reg, f_edge = [], [], [], [], [], []
+            # kwargs['b200_pred_gemm'] (fp16 only): the 1x1 prediction convs run as tcgen05 GEMMs that write the fused layout
+            # directly (ops.pred_heads) instead of cuDNN convs + tscd_pack_head; logits then differ from cuDNN's in the last bits
+            pred_gemm = bool(self.kwargs.get("b200_pred_gemm", False)) and xin[0].dtype == torch.float16 and self.num_classes <= 59
+            reg_o, obj_o, cls_o, f_cls, f_reg, f_edge, reg_f, cls_f = [], [], [], [], [], [], [], []
             for k, x in enumerate(xin):
                 x = self.stems[k](x.contiguous(memory_format=torch.channels_last))
                 reg_feat, cls_feat = self.reg_convs[k](x), self.cls_convs[k](x)
                 vid_cls = self.cls_convs2[k](x) if self.kwargs.get("vid_cls", True) else cls_feat
                 vid_reg = self.reg_convs2[k](x) if self.kwargs.get("vid_reg", True) else reg_feat
-                reg_o.append(self.reg_preds[k](reg_feat)); obj_o.append(self.obj_preds[k](reg_feat))
-                cls_o.append(self.cls_preds[k](cls_feat))
+                if pred_gemm:
+                    reg_f.append(reg_feat.contiguous(memory_format=torch.channels_last))
+                    cls_f.append(cls_feat.contiguous(memory_format=torch.channels_last))
+                else:
+                    reg_o.append(self.reg_preds[k](reg_feat)); obj_o.append(self.obj_preds[k](reg_feat))
+                    cls_o.append(self.cls_preds[k](cls_feat))
                 f_cls.append(vid_cls); f_reg.append(vid_reg); f_edge.append(self.edge_enhance_reg[k](vid_reg))
-            hw = [tuple(t.shape[-2:]) for t in cls_o]
+            hw = [tuple(t.shape[-2:]) for t in f_cls]
             an = ops.AnchorSpec(hw, tuple(self.strides))
-            head = ops.HeadViews.from_levels(reg_o, obj_o, cls_o, an)
-            if reg_o[0].dtype == torch.float16 and self.num_classes <= 59:
+            if pred_gemm:
+                wro = [torch.cat([self.reg_preds[k].weight, self.obj_preds[k].weight], 0).flatten(1).contiguous() for k in range(len(xin))]
+                bro = [torch.cat([self.reg_preds[k].bias, self.obj_preds[k].bias], 0).float().contiguous() for k in range(len(xin))]
+                wc = [self.cls_preds[k].weight.flatten(1).contiguous() for k in range(len(xin))]
+                bc = [self.cls_preds[k].bias.float().contiguous() for k in range(len(xin))]
+                head = ops.pred_heads(reg_f, cls_f, wro, bro, wc, bc, an, self.num_classes)
+            else:
+                head = ops.HeadViews.from_levels(reg_o, obj_o, cls_o, an)
+            if not pred_gemm and reg_o[0].dtype == torch.float16 and self.num_classes <= 59:
                 # conv-tower seam: instead of the reference's flatten / cat / permute copies into [F, A, 5+C]
                 # (tscd_head.py:374-376), ONE pass writes the fused layout -- a 64 / 128-byte row [reg4|obj|cls C] per anchor
                 # plus the dense objectness plane -- that the row kernels of K1 / K3 consume (csrc/select_rows.cu); sigmoid

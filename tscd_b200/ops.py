@@ -108,6 +108,24 @@ class HeadViews:
                          rows.shape[0], num_classes, apply_sigmoid, apply_decode, (rows, obj), True)
 
     @staticmethod
+    def from_level_rows(rows: List[torch.Tensor], obj: torch.Tensor, anchors: AnchorSpec, num_classes: int, apply_sigmoid: bool = True,
+                        apply_decode: bool = True):
+        """Fused rows kept per FPN level: rows[l] is [F, H_l*W_l, 32|64] (what pred_heads writes), obj the dense [F, >=A] plane."""
+        ov, rv, cv = L.View(), L.View(), L.View()
+        start = 0
+        for i, ((h, w), t) in enumerate(zip(anchors.hw, rows)):
+            assert t.dim() == 3 and t.is_contiguous() and t.dtype == torch.float16 and t.shape[1] == h * w and t.shape[2] in (32, 64)
+            rp = t.shape[2]
+            ov.ptr[i] = obj.data_ptr() + start * 2
+            ov.frame_stride[i], ov.anchor_stride[i], ov.chan_stride[i] = obj.stride(0), 1, 1
+            rv.ptr[i], cv.ptr[i] = t.data_ptr(), t.data_ptr() + 5 * 2
+            for v in (rv, cv):
+                v.frame_stride[i], v.anchor_stride[i], v.chan_stride[i] = h * w * rp, rp, 1
+            start += h * w
+        return HeadViews(anchors, rv, ov, cv, torch.float16, rows[0].shape[0], num_classes, apply_sigmoid, apply_decode,
+                         (tuple(rows), obj), True)
+
+    @staticmethod
     def from_levels(reg: List[torch.Tensor], obj: List[torch.Tensor], cls: List[torch.Tensor], anchors: AnchorSpec):
         """Seam S1: raw per-level conv outputs (logits), sigmoid + decode fused into the kernels."""
         return HeadViews(anchors, view_levels(reg), view_levels(obj), view_levels(cls), cls[0].dtype,
@@ -193,6 +211,34 @@ def pack_head(head: HeadViews, rows: Optional[torch.Tensor] = None, obj: Optiona
          obj_pitch=obj.stride(0), anchors=head.anchors.to_c(), reg=head.reg, obj=head.obj, cls=head.cls, rows=rows,
          obj_plane=obj)
     return HeadViews.from_rows(rows, obj, head.anchors, head.num_classes, head.apply_sigmoid, head.apply_decode)
+
+
+def pred_heads(reg_feats: List[torch.Tensor], cls_feats: List[torch.Tensor], w_regobj: List[torch.Tensor], b_regobj: List[torch.Tensor],
+               w_cls: List[torch.Tensor], b_cls: List[torch.Tensor], anchors: AnchorSpec, num_classes: int) -> HeadViews:
+    """The 1x1 prediction convolutions of the decoupled head (reg_preds / obj_preds on reg_feat, cls_preds on cls_feat,
+    tscd_head.py:327-329) as tcgen05 GEMMs that write the FUSED head layout directly (the pred convs folded into the
+    seam): per level  rows[:, 0:5] = reg_feat @ [W_reg; W_obj]^T + b,  rows[:, 5:5+C] = cls_feat @ W_cls^T + b  over the
+    channels_last feature maps viewed as [F*H*W, 256] matrices, then the objectness column into the dense plane.
+    reg_feats / cls_feats: per level [F, 256, H, W] fp16 channels_last; w_regobj[l] [5, 256] / w_cls[l] [C, 256] fp16; biases fp32."""
+    Fn = reg_feats[0].shape[0]
+    dev = reg_feats[0].device
+    rp = row_pitch(num_classes)
+    A = anchors.num_anchors
+    objp = torch.empty(Fn, (A + 7) // 8 * 8, dtype=torch.float16, device=dev)
+    rows, start = [], 0
+    for l, ((h, w), rf, cf) in enumerate(zip(anchors.hw, reg_feats, cls_feats)):
+        assert rf.dtype == torch.float16 and rf.is_contiguous(memory_format=torch.channels_last) and cf.is_contiguous(memory_format=torch.channels_last)
+        K = rf.shape[1]
+        xr = rf.permute(0, 2, 3, 1).reshape(Fn * h * w, K)          # views: channels_last memory is [F, H, W, C]
+        xc = cf.permute(0, 2, 3, 1).reshape(Fn * h * w, K)
+        r = torch.zeros(Fn * h * w, rp, dtype=torch.float16, device=dev)
+        linear(xr, w_regobj[l], b_regobj[l], out16=r[:, 0:5], want32=False, tag="pred_regobj")
+        linear(xc, w_cls[l], b_cls[l], out16=r[:, 5:5 + num_classes], want32=False, tag="pred_cls")
+        r = r.view(Fn, h * w, rp)
+        objp[:, start:start + h * w].copy_(r[:, :, 4])
+        rows.append(r)
+        start += h * w
+    return HeadViews.from_level_rows(rows, objp, anchors, num_classes)
 
 
 NMS_SMEM_CAP = 4096       # csrc/nms.cuh kNmsCap: larger candidate lists take the workspace path (csrc/nms_large.cu)
