@@ -579,7 +579,7 @@ def run_e2e(args, cfg, st, dev, rank, world, dist, barrier):
     proposals' feature rows out of the pinned feature planes, one D2H of the padded detections per chunk."""
     from tscd_b200 import weights
     F, Lf = cfg["F"], cfg["L"]
-    Be = args.e2e_clips or min(32, cfg["clips"])
+    Be = args.e2e_clips or min(64, cfg["clips"])
     dev_src = synth_s1(cfg, Be, dev, seed=99 + rank, layout=args.head_layout)
     host = {k: [(torch.empty(t.shape, dtype=t.dtype, pin_memory=True, memory_format=torch.channels_last) if t.dim() == 4 else
                  torch.empty(t.shape, dtype=t.dtype, pin_memory=True)).copy_(t) for t in v]

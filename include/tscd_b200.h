@@ -318,6 +318,9 @@ typedef struct {
     void* x_reg;
     int32_t ld_x;
     float* stats;             /* [loc_cap,16]: row max (cls h0-3, reg h0-3), row sum (cls h0-3, reg h0-3) */
+    float max_logit;          /* > 0 with BF16 operands: single-pass mode -- an upper bound of every logit (the key scale, 25:
+                               * |q^ . k^| <= 1 and the class scores are <= 1) replaces the row maxima of pass A (BF16 probabilities keep
+                               * their exponent range) and stats[0..7] = max_logit.  0, or fp16 operands: exact two-pass statistics */
 } tscd_attn_pv_args;
 int tscd_attn_pv(const tscd_attn_pv_args* args, void* stream);
 

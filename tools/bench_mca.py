@@ -20,9 +20,10 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--need-reg", type=int, default=1)
     ap.add_argument("--k", type=int, default=30)
+    ap.add_argument("--bf16", action="store_true")
     args = ap.parse_args()
     B, F, Lf, K, D = args.clips, 32, 8, args.k, 256
-    dt = torch.float16
+    dt = torch.bfloat16 if args.bf16 else torch.float16
     g = torch.Generator(device="cuda").manual_seed(1)
     N = B * F * K
     row_cap = (N + 127) // 128 * 128 + 128

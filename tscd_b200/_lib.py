@@ -96,7 +96,7 @@ class AttnPvArgs(C.Structure):
     _fields_ = [("lay", AttnLayout), ("qn_cls", C.c_void_p), ("kn_cls", C.c_void_p), ("qn_reg", C.c_void_p),
                 ("kn_reg", C.c_void_p), ("vt_cls", C.c_void_p), ("vt_reg", C.c_void_p), ("row_frame", C.c_void_p),
                 ("need_reg", C.c_int32), ("x_cls", C.c_void_p), ("x_reg", C.c_void_p), ("ld_x", C.c_int32),
-                ("stats", C.c_void_p)]
+                ("stats", C.c_void_p), ("max_logit", C.c_float)]
 
 
 class AttnRound2Args(C.Structure):

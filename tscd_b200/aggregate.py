@@ -9,6 +9,12 @@ from typing import Dict, Optional
 
 import torch
 
+import os
+
+# attn_pv statistics with BF16 operands: single pass with this upper bound of the logits (scale 25 x cosine <= 1 x class score <= 1)
+# instead of a first pass for the row maxima (include/tscd_b200.h tscd_attn_pv_args.max_logit; fp16 operands always run two passes)
+SINGLE_PASS_MAX_LOGIT = float(os.environ.get("TSCD_ATTN_MAX_LOGIT", "25.0"))
+
 from . import ops
 
 # q|k|v projections with the normalise / scale / transpose step fused into the GEMM epilogue (tscd_qkv_project) instead of
@@ -67,7 +73,7 @@ def mca_forward(lay: ops.AttnLayoutT, w: MCAWeights, bank_cls, bank_reg, bank_sc
         qkv_r, _ = ops.linear(bank_reg, w.qkv_reg, m_dev=n_rows_dev)
         bufs = ops.attn_prep(lay, qkv_c, qkv_r, bank_score, xori_cls=tmp_c[:, 256:], xori_reg=tmp_r[:, 256:])
     stats = torch.empty(lay.loc_cap, 16, dtype=torch.float32, device=dev)
-    ops.attn_pv(lay, bufs, tmp_c[:, :256], tmp_r[:, :256], stats, need_reg=need_reg, tag=tag)
+    ops.attn_pv(lay, bufs, tmp_c[:, :256], tmp_r[:, :256], stats, need_reg=need_reg, tag=tag, max_logit=SINGLE_PASS_MAX_LOGIT)
     cat_c = torch.empty(lay.loc_cap, 768, dtype=dt, device=dev)      # [round2 @ V | linear(x)]
     ops.linear(tmp_c, w.lin_w, w.lin_b, m_dev=n_loc_dev, out16=cat_c[:, 256:], want16=False, tag=tag + ".mca_linear")
     # with a reg output to follow, the cls launch keeps its weights (sim_mask * exp(mean attention)) for the obj launch
@@ -114,7 +120,7 @@ def msa_forward(lay: ops.AttnLayoutT, w: MSAWeights, bank_cls, bank_reg, bank_sc
     tmp_r = torch.empty(cap, 512, dtype=dt, device=dev)
     bufs = ops.attn_prep(lay, qkv_c, qkv_r, bank_score, xori_cls=tmp_c[:, 256:], xori_reg=tmp_r[:, 256:])
     stats = torch.empty(cap, 16, dtype=torch.float32, device=dev)
-    ops.attn_pv(lay, bufs, tmp_c[:, :256], tmp_r[:, :256], stats, need_reg=False, tag="msa")
+    ops.attn_pv(lay, bufs, tmp_c[:, :256], tmp_r[:, :256], stats, need_reg=False, tag="msa", max_logit=SINGLE_PASS_MAX_LOGIT)
     cat = torch.empty(cap, 1024, dtype=dt, device=dev)                   # [round2 @ tc | tc]
     ops.linear(tmp_c, w.l1_w, w.l1_b, m_dev=n_rows_dev, out16=cat[:, 512:], want16=False, tag="msa.linear1")
     tct = torch.empty(lay.B * 512, lay.nk_pitch, dtype=dt, device=dev)

@@ -339,7 +339,14 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
     tc_fence_after();
     const uint32_t tmem = bars.tmem_base;
 
-    const int GA = (ci.n_clip + 127) / 128;       // key tiles of pass A
+    // Single-pass mode (a.max_logit > 0, BF16 operands only): the logits are bounded (|q^ . k^| <= 1 times the key scale), so
+    // exp(s - max_logit) needs no row maximum -- IF the probabilities keep their exponent range, which BF16's 8-bit exponent
+    // does and fp16's does not (a row whose true maximum lies 20 below the bound would underflow).  Pass A (every score read
+    // out of TMEM a second time at 64 B/clk -- the kernel's bound) disappears; the row sums and the statistics handed to
+    // attn_round2 (m = max_logit, l) stay exact in fp32.  fp16 operands keep the exact two-pass statistics: a BF16 P
+    // against an fp16 V in one tcgen05.mma (mixed a/b formats) is an illegal instruction on sm_100a (tried).
+    const bool single = BF16 && a.max_logit > 0.f;
+    const int GA = single ? 0 : (ci.n_clip + 127) / 128;       // key tiles of pass A
     const int GB = (ci.n_clip + 63) / 64;         // key tiles of pass B
     const bool need_reg = a.need_reg != 0;
 
@@ -361,10 +368,11 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
     float mxc[4], mxr[4];
 
     // ======================================= pass A: row maxima =======================================
+    const int HA = single ? 0 : 4;                 // heads visited by pass A
     if (warp == 16) {
         if (lane == 0) {
             uint32_t it = 0;
-            for (int h = 0; h < 4; ++h) {
+            for (int h = 0; h < HA; ++h) {
                 const int qb = h & 1, uq = h >> 1;
                 PV_WAIT(&bars.q_empty[qb], (uq & 1) ^ 1, 300);
                 mbar_expect_tx(&bars.q_full[qb], 32768);
@@ -383,7 +391,7 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
         if (lane == 0) {
             const uint32_t idesc128 = make_idesc_f16(BF16, 128, 128);
             uint32_t it = 0;
-            for (int h = 0; h < 4; ++h) {
+            for (int h = 0; h < HA; ++h) {
                 const int qb = h & 1, uq = h >> 1;
                 PV_WAIT(&bars.q_full[qb], uq & 1, 310);
                 const uint64_t dqc = make_smem_desc_sw128(smem_u32(sQ + qb * 32768));
@@ -407,7 +415,7 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
         }
     } else if (is_sm) {
         uint32_t it = 0;
-        for (int h = 0; h < 4; ++h) {
+        for (int h = 0; h < HA; ++h) {
             float mc = -INFINITY, mr = -INFINITY;
             for (int g = 0; g < GA; ++g, ++it) {
                 const int sb = it & 1, kbase = g * 128;
@@ -455,6 +463,7 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
             const float* x0 = reinterpret_cast<const float*>(sP) + row * 8;
             mxc[h] = fmaxf(fmaxf(x0[h], x0[1024 + h]), fmaxf(x0[2048 + h], x0[3072 + h]));
             mxr[h] = fmaxf(fmaxf(x0[4 + h], x0[1024 + 4 + h]), fmaxf(x0[2048 + 4 + h], x0[3072 + 4 + h]));
+            if (single) { mxc[h] = a.max_logit; mxr[h] = a.max_logit; }
         }
         softmax_bar_sync();  // every quarter has read the maxima before sP is written again
     }
@@ -465,7 +474,7 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
         if (lane == 0) {
             uint32_t it = itA;
             for (int h = 0; h < 4; ++h) {
-                const int qb = h & 1, uq = 2 + (h >> 1);
+                const int qb = h & 1, uq = (single ? 0 : 2) + (h >> 1);
                 PV_WAIT(&bars.q_empty[qb], (uq & 1) ^ 1, 330);
                 mbar_expect_tx(&bars.q_full[qb], 32768);
                 tma_load_2d(sQ + qb * 32768, &tm.qc, &bars.q_full[qb], h * 64, ci.s0 + ci.q0);
@@ -498,7 +507,7 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
             const uint32_t idesc64 = make_idesc_f16(BF16, 128, 64);
             uint32_t it = itA;          // key-tile counter (ring stage / score buffer of tile `it`)
             for (int h = 0; h < 4; ++h) {
-                const int qb = h & 1, uq = 2 + (h >> 1);
+                const int qb = h & 1, uq = (single ? 0 : 2) + (h >> 1);
                 PV_WAIT(&bars.q_full[qb], uq & 1, 340);
                 const uint64_t dqc = make_smem_desc_sw128(smem_u32(sQ + qb * 32768));
                 const uint64_t dqr = make_smem_desc_sw128(smem_u32(sQ + qb * 32768 + 16384));

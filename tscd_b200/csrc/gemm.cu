@@ -422,18 +422,18 @@ template <int BN, bool BF16, int EPI = 0>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
     constexpr int STAGES = BN == 256 ? 4 : 3;
     constexpr size_t smem = (size_t)STAGES * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + gemm_epi_warps(EPI) * 2048 + 128;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // per-DEVICE caches (the attribute is per device; a process may drive several GPUs)
+    static bool attr_set[64] = {};
+    static int num_sms_dev[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return TSCD_ERR_CUDA;
+    if (!attr_set[dev]) {
         if (cudaFuncSetAttribute(gemm_tn_kernel<BN, BF16, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return TSCD_ERR_CUDA;
-        attr_set = true;
+        if (cudaDeviceGetAttribute(&num_sms_dev[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return TSCD_ERR_CUDA;
+        attr_set[dev] = true;
     }
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int num_sms = num_sms_dev[dev];
     const int tiles = ((p.N + BN - 1) / BN) * ((p.M + kGemmBM - 1) / kGemmBM);
     const int ctas_per_sm = BN == 256 ? 1 : 2;                       // 113 KB smem and 2*BN TMEM columns per CTA (BN <= 128)
     const int grid = tiles < ctas_per_sm * num_sms ? tiles : ctas_per_sm * num_sms;

@@ -410,8 +410,10 @@ def qkv_project_fused(lay: AttnLayoutT, bank_cls, bank_reg, w_cls, w_reg, key_sc
     return bufs
 
 
-def attn_pv(lay: AttnLayoutT, bufs, x_cls, x_reg, stats, need_reg=True, tag=None):
+def attn_pv(lay: AttnLayoutT, bufs, x_cls, x_reg, stats, need_reg=True, tag=None, max_logit: float = 0.0):
+    """max_logit > 0: single-pass mode (include/tscd_b200.h tscd_attn_pv_args.max_logit)."""
     a = L.AttnPvArgs()
+    a.max_logit = max_logit
     a.lay = lay.to_c()
     for n in ("qn_cls", "kn_cls", "qn_reg", "kn_reg", "vt_cls", "vt_reg", "row_frame"):
         setattr(a, n, _p(bufs[n]))
