@@ -9,8 +9,21 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace tscd {
+
+// 1-D bulk copies of the TMA engine (cp.async.bulk): global / pinned host -> shared with mbarrier completion, shared -> global.
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(tc::smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(tc::smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(tc::smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 
 __global__ void count_scan_kernel(int num_frames, int use_keep, int max_keep, const int32_t* cand_count,
                                   const int32_t* keep_count, int32_t* sel_count, int32_t* row_off) {
@@ -72,19 +85,73 @@ __device__ __forceinline__ void copy_feature_row(const tscd_view& v, int level, 
 }
 
 // rp: row pitch (elements) of the fused head layout (csrc/select_rows.cu), 0 = generic strided views
+// bulk: TSCD-L fast layout (256 channel-contiguous 16-bit features, bank of the same type): the three feature rows of every
+//       kept proposal are staged through shared memory by the TMA engine -- one lane issues three 512-byte cp.async.bulk loads
+//       per row (device memory or, for forward_host, pinned host memory), and since the kept rows of a frame are CONSECUTIVE in
+//       the packed bank, each plane leaves as ONE bulk store of n x 512 bytes; the warps meanwhile build the reference rows
+//       (class scores, box) of the same proposals.  No feature byte passes through a register.
+constexpr int kGatherBulkRows = 32;          // rows staged per batch: 3 planes x 32 x 512 B = 48 KB (16-row batches measured slower)
+constexpr int kGatherMaxRows = 512;          // kept rows per frame whose anchor ids are staged in shared memory
+
 template <typename TF, typename TB>
-__global__ void __launch_bounds__(256) rows_gather_kernel(const tscd_gather_args args, int rp) {
+__global__ void __launch_bounds__(256) rows_gather_kernel(const tscd_gather_args args, int rp, int bulk) {
+    extern __shared__ __align__(128) unsigned char gsm[];
+    __shared__ __align__(8) uint64_t gbar;
     const int frame = blockIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int n = args.sel_count[frame];
     const int row0 = args.row_off[frame];
+    // kept position -> anchor id of every row of the frame, resolved once by the whole CTA (two dependent loads) instead of by every
+    // warp in front of its own row loads
+    __shared__ int s_anchor[kGatherMaxRows];
+    const bool staged = gridDim.y == 1 && n <= kGatherMaxRows;
+    if (staged)
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            const int pos = args.use_keep ? args.keep[(int64_t)frame * args.max_keep + j] : j;
+            s_anchor[j] = args.cand_idx[(int64_t)frame * args.cand_cap + pos];
+        }
+    if (bulk && threadIdx.x == 0) { tc::mbar_init(&gbar, 1); tc::fence_barrier_init(); }
+    if (bulk || staged) __syncthreads();
     const int C = args.num_classes;
     const int W = 7 + C;
     const tscd_anchors& an = args.anchors;
     const int hd = args.head_dtype;
+    if (bulk && wid == 0) {
+        TB* const banks[3] = {reinterpret_cast<TB*>(args.bank_cls), reinterpret_cast<TB*>(args.bank_reg), reinterpret_cast<TB*>(args.bank_edge)};
+        for (int b0 = 0; b0 < n; b0 += kGatherBulkRows) {
+            const int nb = min(kGatherBulkRows, n - b0);
+            if (lane == 0) tc::mbar_expect_tx(&gbar, (uint32_t)nb * 3u * 512u);
+            __syncwarp();
+            if (lane < nb) {
+                const int j = b0 + lane;
+                int a;
+                if (staged) a = s_anchor[j];
+                else {
+                    const int pos = args.use_keep ? args.keep[(int64_t)frame * args.max_keep + j] : j;
+                    a = args.cand_idx[(int64_t)frame * args.cand_cap + pos];
+                }
+                const AnchorPos p = anchor_pos(args.anchors, a);
+                bulk_load(gsm + (0 * kGatherBulkRows + lane) * 512, view_ptr<TF>(args.feat_cls, p.level, frame, p.local), 512, &gbar);
+                bulk_load(gsm + (1 * kGatherBulkRows + lane) * 512, view_ptr<TF>(args.feat_reg, p.level, frame, p.local), 512, &gbar);
+                bulk_load(gsm + (2 * kGatherBulkRows + lane) * 512, view_ptr<TF>(args.feat_edge, p.level, frame, p.local), 512, &gbar);
+            }
+            tc::mbar_wait(&gbar, (uint32_t)((b0 / kGatherBulkRows) & 1), 700);
+            tc::fence_proxy_async();
+            if (lane < 3) {          // the batch's rows are consecutive in the packed bank: one store per plane
+                bulk_store(banks[lane] + (int64_t)(row0 + b0) * 256, gsm + lane * kGatherBulkRows * 512, (uint32_t)nb * 512u);
+                bulk_commit();
+                bulk_wait_read();    // the staging buffer may be overwritten by the next batch
+            }
+            __syncwarp();
+        }
+    }
     for (int j = wid + blockIdx.y * nw; j < n; j += nw * gridDim.y) {
-        const int pos = args.use_keep ? args.keep[(int64_t)frame * args.max_keep + j] : j;
-        const int a = args.cand_idx[(int64_t)frame * args.cand_cap + pos];
+        int a;
+        if (staged) a = s_anchor[j];
+        else {
+            const int pos = args.use_keep ? args.keep[(int64_t)frame * args.max_keep + j] : j;
+            a = args.cand_idx[(int64_t)frame * args.cand_cap + pos];
+        }
         AnchorPos p = anchor_pos(an, a);
         float* row = args.sel_rows + ((int64_t)frame * args.max_keep + j) * W;
         const int64_t r = (int64_t)(row0 + j) * args.feat_dim;
@@ -92,7 +159,7 @@ __global__ void __launch_bounds__(256) rows_gather_kernel(const tscd_gather_args
         // (three independent 16-byte loads per lane), so their latency overlaps the dependent class / objectness / box loads below
         bool fast = false;
         uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0, v2 = v0;
-        if (std::is_same<TF, TB>::value && sizeof(TF) == 2 && args.feat_dim == 256 &&
+        if (!bulk && std::is_same<TF, TB>::value && sizeof(TF) == 2 && args.feat_dim == 256 &&
             args.feat_cls.chan_stride[p.level] == 1 && args.feat_reg.chan_stride[p.level] == 1 && args.feat_edge.chan_stride[p.level] == 1) {
             const TF* s0 = view_ptr<TF>(args.feat_cls, p.level, frame, p.local) + lane * 8;
             const TF* s1 = view_ptr<TF>(args.feat_reg, p.level, frame, p.local) + lane * 8;
@@ -169,6 +236,7 @@ __global__ void __launch_bounds__(256) rows_gather_kernel(const tscd_gather_args
             args.bank_fg[rr] = obj;
             reinterpret_cast<float4*>(args.bank_box)[rr] = box;
         }
+        if (bulk) continue;                            // features travel through the TMA engine (below)
         if (fast) {                                    // identical 16-bit types: raw copy
             *reinterpret_cast<uint4*>(reinterpret_cast<TB*>(args.bank_cls) + r + lane * 8) = v0;
             *reinterpret_cast<uint4*>(reinterpret_cast<TB*>(args.bank_reg) + r + lane * 8) = v1;
@@ -181,13 +249,40 @@ __global__ void __launch_bounds__(256) rows_gather_kernel(const tscd_gather_args
     }
 }
 
+// the TMA-bulk path needs 512-byte channel-contiguous 16-bit feature rows, 16-byte aligned, and a bank of the same type
+static bool gather_bulk_ok(const tscd_gather_args* a) {
+    if (a->feat_dim != 256 || a->feat_dtype != a->bank_dtype || (a->feat_dtype != TSCD_F16 && a->feat_dtype != TSCD_BF16)) return false;
+    const tscd_view* vs[3] = {&a->feat_cls, &a->feat_reg, &a->feat_edge};
+    for (int v = 0; v < 3; ++v)
+        for (int l = 0; l < a->anchors.num_levels; ++l) {
+            if (vs[v]->chan_stride[l] != 1 || (reinterpret_cast<uintptr_t>(vs[v]->ptr[l]) & 15)) return false;
+            if ((vs[v]->frame_stride[l] % 8) || (vs[v]->anchor_stride[l] % 8)) return false;
+        }
+    const void* bs[3] = {a->bank_cls, a->bank_reg, a->bank_edge};
+    for (int v = 0; v < 3; ++v)
+        if (reinterpret_cast<uintptr_t>(bs[v]) & 15) return false;
+    return true;
+}
+
+template <typename TF, typename TB>
+static int launch_gather_kernel(const tscd_gather_args* a, dim3 grid, int rp, int bulk, cudaStream_t st) {
+    const size_t sm = bulk ? (size_t)3 * kGatherBulkRows * 512 : 0;
+    if (bulk) {
+        if (cudaFuncSetAttribute(rows_gather_kernel<TF, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return TSCD_ERR_CUDA;
+        grid.y = 1;              // one CTA per frame: warp 0 drives the TMA engine, all eight warps build the reference rows
+    }
+    rows_gather_kernel<TF, TB><<<grid, 256, sm, st>>>(*a, rp, bulk);
+    return TSCD_OK;
+}
+
 template <typename TF>
 static int launch_gather_tb(const tscd_gather_args* a, dim3 grid, cudaStream_t st) {
     const int rp = fused_rows_pitch(a->anchors, a->reg, a->obj, a->cls, a->num_classes, a->head_dtype, false);
+    const int bulk = gather_bulk_ok(a) ? 1 : 0;
     switch (a->bank_dtype) {
-        case TSCD_F32: rows_gather_kernel<TF, float><<<grid, 256, 0, st>>>(*a, rp); break;
-        case TSCD_F16: rows_gather_kernel<TF, __half><<<grid, 256, 0, st>>>(*a, rp); break;
-        case TSCD_BF16: rows_gather_kernel<TF, __nv_bfloat16><<<grid, 256, 0, st>>>(*a, rp); break;
+        case TSCD_F32: return launch_gather_kernel<TF, float>(a, grid, rp, 0, st);
+        case TSCD_F16: return launch_gather_kernel<TF, __half>(a, grid, rp, bulk, st);
+        case TSCD_BF16: return launch_gather_kernel<TF, __nv_bfloat16>(a, grid, rp, bulk, st);
         default: return TSCD_ERR_UNSUPPORTED;
     }
     return TSCD_OK;
