@@ -185,7 +185,8 @@ typedef struct {
     int32_t bank_dtype;     /* TSCD_F16 / TSCD_BF16 / TSCD_F32 */
     tscd_anchors anchors;
     tscd_view reg, obj, cls;
-    tscd_view feat_cls, feat_reg, feat_edge; /* D channels each */
+    tscd_view feat_cls, feat_reg, feat_edge; /* D channels each; feat_edge.ptr[0] == NULL: no edge plane (bank_edge untouched,
+                                              * filled by tscd_edge_patches / tscd_edge_combine instead) */
     const int32_t* cand_idx;
     const int32_t* cand_count;
     const int32_t* keep;
@@ -529,6 +530,49 @@ typedef struct {
     float* out; int32_t ldo;
 } tscd_frame_flash_args;
 int tscd_frame_flash(const tscd_frame_flash_args* args, void* stream);
+
+/* ---- WaveletsHFBlock at the selected anchors only ------------------------------------------------
+ * Replaces the dense edge_enhance_reg[k](vid_feat_reg) of the head (tscd_head.py:367; surrounding_extraction.py:215-267)
+ * followed by the row lookup of find_feature_score (tscd_head.py:991): the block's output is evaluated only at the kept
+ * proposals.  tscd_gather is called with a null feat_edge view (it then leaves bank_edge alone) and
+ *   tscd_edge_patches   writes, per kept proposal, the zero-padded 3x3 patch [9*256] (tap-major: (ky,kx), channel) and the Haar
+ *                       high-pass sub-bands [LH|HL|HH] (3*256) of its 2x2 block as 16-bit rows.  Every pyramid level has its
+ *                       own conv weights, so rows are grouped by level: level l owns slots [seg_base[l], seg_base[l]+seg_cap[l])
+ *                       and level_count[l] (device) says how many are filled; slot[bank row] = 4*slot + 2*(y&1) + (x&1);
+ *   tscd_linear         per level: content = patches x W3^T + b3 (filter2, weight [256, 9*256] tap-major) and
+ *                       hf_out = hf x W1^T + b1 (filter1, weight [768,768]), m_dev = &level_count[l];
+ *   tscd_edge_combine   bank_edge[row] = ReLU(content) * 1/2 (s_lh ReLU(LH') + s_hl ReLU(HL') + s_hh ReLU(HH')) (inverse Haar with
+ *                       LL = 0; s_lh = -1 on odd rows, s_hl = -1 on odd columns, s_hh = s_lh * s_hl).
+ * Feature maps need even height and width (the reference's stride-2 transform has no same-size inverse otherwise). */
+typedef struct {
+    int32_t num_frames, max_keep;
+    int32_t feat_dtype;                   /* TSCD_F32 / TSCD_F16 / TSCD_BF16: type of feat_reg */
+    int32_t op_dtype;                     /* TSCD_F16 / TSCD_BF16: type of patches / hf */
+    tscd_anchors anchors;
+    tscd_view feat_reg;                   /* 256 channels per anchor */
+    const int32_t* sel_idx;               /* [num_frames, max_keep] anchor ids (tscd_gather) */
+    const int32_t* sel_count;             /* [num_frames] */
+    const int32_t* row_off;               /* [num_frames+1] */
+    int32_t seg_base[TSCD_MAX_LEVELS];
+    int32_t seg_cap[TSCD_MAX_LEVELS];
+    int32_t* level_count;                 /* [TSCD_MAX_LEVELS] out (zeroed by the call) */
+    int32_t* slot;                        /* [bank rows] out */
+    void* patches;                        /* [slots, 2304] out */
+    void* hf;                             /* [slots, 768] out */
+    int32_t* status;                      /* TSCD_ERR_CAPACITY if a level's segment overflowed, or NULL */
+} tscd_edge_patches_args;
+int tscd_edge_patches(const tscd_edge_patches_args* args, void* stream);
+
+typedef struct {
+    int32_t rows_cap;                     /* bank row capacity (grid size) */
+    int32_t op_dtype;                     /* TSCD_F16 / TSCD_BF16: type of content / hf_out / bank_edge */
+    const int32_t* total_rows;            /* device: number of bank rows (= row_off[num_frames]) */
+    const int32_t* slot;                  /* [bank rows] from tscd_edge_patches */
+    const void* content;                  /* [slots, 256] pre-ReLU filter2 output */
+    const void* hf_out;                   /* [slots, 768] pre-ReLU filter1 output */
+    void* bank_edge;                      /* [bank rows, 256] out */
+} tscd_edge_combine_args;
+int tscd_edge_combine(const tscd_edge_combine_args* args, void* stream);
 
 /* ---- TaskAligned attention + LayerNorms ---------------------------------------------------------------------
  * tscd_frame_attention: MHAttention.forward (tscd_matching.py:159-181) for every local frame at once:

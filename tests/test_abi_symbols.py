@@ -37,7 +37,8 @@ def test_struct_sizes_match_header():
              ("tscd_qkv_project_args", _lib.QkvProjectArgs), ("tscd_attn_rowmeta_args", _lib.AttnRowmetaArgs),
              ("tscd_local_offsets_args", _lib.LocalOffsetsArgs), ("tscd_pack_rows_args", _lib.PackRowsArgs),
              ("tscd_pack_detections_args", _lib.PackDetectionsArgs), ("tscd_repp_link_args", _lib.ReppLinkArgs),
-             ("tscd_cafm_wide_args", _lib.CafmWideArgs), ("tscd_frame_flash_args", _lib.FrameFlashArgs)]
+             ("tscd_cafm_wide_args", _lib.CafmWideArgs), ("tscd_frame_flash_args", _lib.FrameFlashArgs),
+             ("tscd_edge_patches_args", _lib.EdgePatchesArgs), ("tscd_edge_combine_args", _lib.EdgeCombineArgs)]
     body = "".join(f'printf("%zu\\n", sizeof({c}));' for c, _ in pairs)
     src = '#include <stdio.h>\n#include "tscd_b200.h"\nint main(){' + body + 'return 0;}'
     with tempfile.TemporaryDirectory() as d:

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Generate the host-side goldens (tests/golden/clips.json, tests/golden/repp.json) by RUNNING the reference's own code.
+"""Generate the host-side goldens (tests/golden/clips.json, repp.json, edge.npz) by RUNNING the reference's own code.
 
 Build container only (needs /root/reference):  python tools/make_goldens_host.py
 No reference source is copied: the functions are imported (or, for the clip loop that tscd_demo.py has inline in
@@ -11,7 +11,8 @@ clips.json   OVIS.photo_to_sequence (yolox/data/datasets/vid.py:601-683), VIDDat
 repp.json    tools/REPP.py REPP.__call__ on seeded synthetic detections of a 14-frame video (moving objects, detections typed like
              Predictor.to_repp_heavy's: numpy float32 scalars), for the shipped configuration (tools/yolo_repp_cfg.json: logreg /
              dot, re-coordination) and variants (def distance, add_unmatched, no re-coordination); plus the coefficients of the
-             linking model (tools/matching_model_logreg.pckl)."""
+             linking model (tools/matching_model_logreg.pckl).
+edge.npz     yolox/models/surrounding_extraction.py WaveletsHFBlock.forward on seeded inputs and weights (fp32, CPU)."""
 import copy
 import json
 import os
@@ -142,8 +143,26 @@ def gen_repp():
     json.dump(dict(logreg=logreg, cases=cases), open(os.path.join(OUT, "repp.json"), "w"))
 
 
+def gen_edge():
+    """WaveletsHFBlock (yolox/models/surrounding_extraction.py:215-267): seeded inputs / weights -> the module's output (fp32, CPU)."""
+    import torch
+    from yolox.models.surrounding_extraction import WaveletsHFBlock
+    out = {}
+    for i, (C, H, W, B) in enumerate(((8, 6, 10, 2), (16, 4, 4, 3), (4, 12, 2, 1))):
+        torch.manual_seed(40 + i)
+        m = WaveletsHFBlock(C).eval()
+        x = torch.randn(B, C, H, W)
+        with torch.no_grad():
+            y = m(x)
+        out.update({f"x{i}": x.numpy(), f"y{i}": y.numpy(), f"w1_{i}": m.filter1[0].weight.detach().numpy(),
+                    f"b1_{i}": m.filter1[0].bias.detach().numpy(), f"w3_{i}": m.filter2[0].weight.detach().numpy(),
+                    f"b3_{i}": m.filter2[0].bias.detach().numpy()})
+    np.savez_compressed(os.path.join(OUT, "edge.npz"), **out)
+
+
 if __name__ == "__main__":
     gen_clips()
     gen_repp()
-    for f in ("clips.json", "repp.json"):
+    gen_edge()
+    for f in ("clips.json", "repp.json", "edge.npz"):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

@@ -139,6 +139,17 @@ class FrameFlashArgs(C.Structure):
                        "out:p ldo:i")
 
 
+class EdgePatchesArgs(C.Structure):
+    _fields_ = [("num_frames", C.c_int32), ("max_keep", C.c_int32), ("feat_dtype", C.c_int32), ("op_dtype", C.c_int32),
+                ("anchors", Anchors), ("feat_reg", View), ("sel_idx", C.c_void_p), ("sel_count", C.c_void_p), ("row_off", C.c_void_p),
+                ("seg_base", C.c_int32 * MAX_LEVELS), ("seg_cap", C.c_int32 * MAX_LEVELS), ("level_count", C.c_void_p),
+                ("slot", C.c_void_p), ("patches", C.c_void_p), ("hf", C.c_void_p), ("status", C.c_void_p)]
+
+
+class EdgeCombineArgs(C.Structure):
+    _fields_ = _fields("rows_cap:i op_dtype:i total_rows:p slot:p content:p hf_out:p bank_edge:p")
+
+
 class CafmCostArgs(C.Structure):
     _fields_ = _fields("B:i L:i D:i kmax:i lrow_off:p resume:p st_n:p emb_reg:p emb_cls:p norm_reg:p norm_cls:p "
                        "st_reg:p st_cls:p st_nreg:p st_ncls:p cost:p ref_n:p emb_dtype:i emb_reg16:p emb_cls16:p emb16_dtype:i")
@@ -227,6 +238,8 @@ SYMBOLS = [
     ("tscd_cafm_chain", C.c_int, [C.POINTER(CafmChainArgs), C.c_void_p]),
     ("tscd_cafm_wide", C.c_int, [C.POINTER(CafmWideArgs), C.c_int, C.c_int, C.c_void_p]),
     ("tscd_frame_flash", C.c_int, [C.POINTER(FrameFlashArgs), C.c_void_p]),
+    ("tscd_edge_patches", C.c_int, [C.POINTER(EdgePatchesArgs), C.c_void_p]),
+    ("tscd_edge_combine", C.c_int, [C.POINTER(EdgeCombineArgs), C.c_void_p]),
     ("tscd_frame_attention", C.c_int, [C.POINTER(FrameAttentionArgs), C.c_void_p]),
     ("tscd_residual_ln2", C.c_int, [C.POINTER(ResidualLn2Args), C.c_void_p]),
     ("tscd_final_expand", C.c_int, [C.POINTER(FinalExpandArgs), C.c_void_p]),

@@ -116,11 +116,13 @@ __global__ void __launch_bounds__(256) rows_gather_kernel(const tscd_gather_args
     const int W = 7 + C;
     const tscd_anchors& an = args.anchors;
     const int hd = args.head_dtype;
+    // a null edge view: the edge rows are computed from the regression features afterwards (csrc/edge.cu), bank_edge is left alone
+    const int np = args.feat_edge.ptr[0] ? 3 : 2;
     if (bulk && wid == 0) {
         TB* const banks[3] = {reinterpret_cast<TB*>(args.bank_cls), reinterpret_cast<TB*>(args.bank_reg), reinterpret_cast<TB*>(args.bank_edge)};
         for (int b0 = 0; b0 < n; b0 += kGatherBulkRows) {
             const int nb = min(kGatherBulkRows, n - b0);
-            if (lane == 0) tc::mbar_expect_tx(&gbar, (uint32_t)nb * 3u * 512u);
+            if (lane == 0) tc::mbar_expect_tx(&gbar, (uint32_t)(nb * np) * 512u);
             __syncwarp();
             if (lane < nb) {
                 const int j = b0 + lane;
@@ -133,11 +135,11 @@ __global__ void __launch_bounds__(256) rows_gather_kernel(const tscd_gather_args
                 const AnchorPos p = anchor_pos(args.anchors, a);
                 bulk_load(gsm + (0 * kGatherBulkRows + lane) * 512, view_ptr<TF>(args.feat_cls, p.level, frame, p.local), 512, &gbar);
                 bulk_load(gsm + (1 * kGatherBulkRows + lane) * 512, view_ptr<TF>(args.feat_reg, p.level, frame, p.local), 512, &gbar);
-                bulk_load(gsm + (2 * kGatherBulkRows + lane) * 512, view_ptr<TF>(args.feat_edge, p.level, frame, p.local), 512, &gbar);
+                if (np == 3) bulk_load(gsm + (2 * kGatherBulkRows + lane) * 512, view_ptr<TF>(args.feat_edge, p.level, frame, p.local), 512, &gbar);
             }
             tc::mbar_wait(&gbar, (uint32_t)((b0 / kGatherBulkRows) & 1), 700);
             tc::fence_proxy_async();
-            if (lane < 3) {          // the batch's rows are consecutive in the packed bank: one store per plane
+            if (lane < np) {         // the batch's rows are consecutive in the packed bank: one store per plane
                 bulk_store(banks[lane] + (int64_t)(row0 + b0) * 256, gsm + lane * kGatherBulkRows * 512, (uint32_t)nb * 512u);
                 bulk_commit();
                 bulk_wait_read();    // the staging buffer may be overwritten by the next batch
@@ -160,15 +162,15 @@ __global__ void __launch_bounds__(256) rows_gather_kernel(const tscd_gather_args
         bool fast = false;
         uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0, v2 = v0;
         if (!bulk && std::is_same<TF, TB>::value && sizeof(TF) == 2 && args.feat_dim == 256 &&
-            args.feat_cls.chan_stride[p.level] == 1 && args.feat_reg.chan_stride[p.level] == 1 && args.feat_edge.chan_stride[p.level] == 1) {
+            args.feat_cls.chan_stride[p.level] == 1 && args.feat_reg.chan_stride[p.level] == 1 && (np == 2 || args.feat_edge.chan_stride[p.level] == 1)) {
             const TF* s0 = view_ptr<TF>(args.feat_cls, p.level, frame, p.local) + lane * 8;
             const TF* s1 = view_ptr<TF>(args.feat_reg, p.level, frame, p.local) + lane * 8;
-            const TF* s2 = view_ptr<TF>(args.feat_edge, p.level, frame, p.local) + lane * 8;
+            const TF* s2 = np == 3 ? view_ptr<TF>(args.feat_edge, p.level, frame, p.local) + lane * 8 : s1;
             if (((reinterpret_cast<uintptr_t>(s0) | reinterpret_cast<uintptr_t>(s1) | reinterpret_cast<uintptr_t>(s2)) & 15) == 0) {
                 fast = true;
                 v0 = __ldg(reinterpret_cast<const uint4*>(s0));
                 v1 = __ldg(reinterpret_cast<const uint4*>(s1));
-                v2 = __ldg(reinterpret_cast<const uint4*>(s2));
+                if (np == 3) v2 = __ldg(reinterpret_cast<const uint4*>(s2));
             }
         }
         // class scores + arg-max (first maximum)
@@ -240,12 +242,12 @@ __global__ void __launch_bounds__(256) rows_gather_kernel(const tscd_gather_args
         if (fast) {                                    // identical 16-bit types: raw copy
             *reinterpret_cast<uint4*>(reinterpret_cast<TB*>(args.bank_cls) + r + lane * 8) = v0;
             *reinterpret_cast<uint4*>(reinterpret_cast<TB*>(args.bank_reg) + r + lane * 8) = v1;
-            *reinterpret_cast<uint4*>(reinterpret_cast<TB*>(args.bank_edge) + r + lane * 8) = v2;
+            if (np == 3) *reinterpret_cast<uint4*>(reinterpret_cast<TB*>(args.bank_edge) + r + lane * 8) = v2;
             continue;
         }
         copy_feature_row<TF, TB>(args.feat_cls, p.level, frame, p.local, args.feat_dim, reinterpret_cast<TB*>(args.bank_cls) + r, lane);
         copy_feature_row<TF, TB>(args.feat_reg, p.level, frame, p.local, args.feat_dim, reinterpret_cast<TB*>(args.bank_reg) + r, lane);
-        copy_feature_row<TF, TB>(args.feat_edge, p.level, frame, p.local, args.feat_dim, reinterpret_cast<TB*>(args.bank_edge) + r, lane);
+        if (np == 3) copy_feature_row<TF, TB>(args.feat_edge, p.level, frame, p.local, args.feat_dim, reinterpret_cast<TB*>(args.bank_edge) + r, lane);
     }
 }
 
@@ -253,7 +255,8 @@ __global__ void __launch_bounds__(256) rows_gather_kernel(const tscd_gather_args
 static bool gather_bulk_ok(const tscd_gather_args* a) {
     if (a->feat_dim != 256 || a->feat_dtype != a->bank_dtype || (a->feat_dtype != TSCD_F16 && a->feat_dtype != TSCD_BF16)) return false;
     const tscd_view* vs[3] = {&a->feat_cls, &a->feat_reg, &a->feat_edge};
-    for (int v = 0; v < 3; ++v)
+    const int np = a->feat_edge.ptr[0] ? 3 : 2;
+    for (int v = 0; v < np; ++v)
         for (int l = 0; l < a->anchors.num_levels; ++l) {
             if (vs[v]->chan_stride[l] != 1 || (reinterpret_cast<uintptr_t>(vs[v]->ptr[l]) & 15)) return false;
             if ((vs[v]->frame_stride[l] % 8) || (vs[v]->anchor_stride[l] % 8)) return false;

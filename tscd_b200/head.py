@@ -57,6 +57,7 @@ def make_head_class():
         def _b200_invalidate(self):
             self._b200_stage = None           # weights changed / moved: rebuild the 16-bit device copies lazily
             self._b200_state = None
+            self._b200_edge = None
 
         def _apply(self, fn, *a, **k):        # .half() / .to() / .cuda() / .float()
             self._b200_invalidate()
@@ -74,6 +75,14 @@ def make_head_class():
                 self._b200_state = None
             return self._b200_stage
 
+        def _edge_block(self, dtype):
+            """16-bit copies of the per-level WaveletsHFBlock weights for the selected-anchor evaluation (ops.EdgeBlock)."""
+            params = list(self.edge_enhance_reg.parameters())
+            key = (params[0].device, dtype, tuple((p.data_ptr(), p._version) for p in params))
+            if getattr(self, "_b200_edge", None) is None or self._b200_edge[0] != key:
+                self._b200_edge = (key, ops.EdgeBlock.from_modules(self.edge_enhance_reg, dtype=dtype, device=params[0].device))
+            return self._b200_edge[1]
+
         def forward(self, xin, labels=None, imgs=None, time_embedding=None, nms_thresh=0.5, lframe=0, gframe=32,
                     resume=False):
             if self.training:
@@ -84,6 +93,9 @@ def make_head_class():
             # kwargs['b200_pred_gemm'] (fp16 only): the 1x1 prediction convs run as tcgen05 GEMMs that write the fused layout
             # directly (ops.pred_heads) instead of cuDNN convs + tscd_pack_head; logits then differ from cuDNN's in the last bits
             pred_gemm = bool(self.kwargs.get("b200_pred_gemm", False)) and xin[0].dtype == torch.float16 and self.num_classes <= 59
+            # the wavelet edge block (edge_enhance_reg, tscd_head.py:367) is evaluated at the kept proposals only
+            # (csrc/edge.cu) instead of densely over every level; kwargs['b200_dense_edge'] keeps the reference's dense modules
+            dense_edge = bool(self.kwargs.get("b200_dense_edge", False))
             reg_o, obj_o, cls_o, f_cls, f_reg, f_edge, reg_f, cls_f = [], [], [], [], [], [], [], []
             for k, x in enumerate(xin):
                 x = self.stems[k](x.contiguous(memory_format=torch.channels_last))
@@ -96,7 +108,9 @@ def make_head_class():
                 else:
                     reg_o.append(self.reg_preds[k](reg_feat)); obj_o.append(self.obj_preds[k](reg_feat))
                     cls_o.append(self.cls_preds[k](cls_feat))
-                f_cls.append(vid_cls); f_reg.append(vid_reg); f_edge.append(self.edge_enhance_reg[k](vid_reg))
+                f_cls.append(vid_cls); f_reg.append(vid_reg)
+                if dense_edge:
+                    f_edge.append(self.edge_enhance_reg[k](vid_reg))
             hw = [tuple(t.shape[-2:]) for t in f_cls]
             an = ops.AnchorSpec(hw, tuple(self.strides))
             if pred_gemm:
@@ -113,8 +127,9 @@ def make_head_class():
                 # plus the dense objectness plane -- that the row kernels of K1 / K3 consume (csrc/select_rows.cu); sigmoid
                 # and decode stay fused in those kernels, values are copied bit for bit
                 head = ops.pack_head(head)
-            feats = tuple(ops.view_levels(f) for f in (f_cls, f_reg, f_edge))
             st = self._stage()
+            feats = (ops.view_levels(f_cls), ops.view_levels(f_reg),
+                     ops.view_levels(f_edge) if dense_edge else self._edge_block(st.cfg.dtype))
             st.cfg.final_nms_thresh = nms_thresh
             F = imgs.shape[0]
             kmax = st.cfg.selection.max_keep(an.num_anchors)

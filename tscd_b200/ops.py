@@ -301,7 +301,8 @@ def gather(head: HeadViews, feats, feat_dtype: torch.dtype, feat_dim: int, cand,
     a.cand_cap, a.max_keep, a.use_keep = cand["cap"], max_keep, int(use_keep)
     a.feat_dim, a.feat_dtype, a.bank_dtype = feat_dim, _DT[feat_dtype], _DT[bank_dtype]
     a.anchors, a.reg, a.obj, a.cls = head.anchors.to_c(), head.reg, head.obj, head.cls
-    a.feat_cls, a.feat_reg, a.feat_edge = feats
+    a.feat_cls, a.feat_reg = feats[0], feats[1]
+    a.feat_edge = feats[2] if isinstance(feats[2], L.View) else L.View()   # EdgeBlock: rows computed afterwards (edge_rows)
     a.cand_idx, a.cand_count = _p(cand["idx"]), _p(cand["count"])
     a.keep, a.keep_count = _p(keep), _p(keep_count)
     for k in ("sel_count", "row_off", "sel_idx", "sel_rows", "bank_cls", "bank_reg", "bank_edge", "bank_score",
@@ -310,6 +311,77 @@ def gather(head: HeadViews, feats, feat_dtype: torch.dtype, feat_dim: int, cand,
     with L.timed("tscd_gather"):
         L.check(L.lib().tscd_gather(C.byref(a), _stream()), "tscd_gather")
     return out
+
+
+class EdgeBlock:
+    """Weights of the head's per-level WaveletsHFBlock modules (edge_enhance_reg, tscd_head.py:206; surrounding_extraction.py:
+    215-233) laid out for the selected-anchor evaluation (csrc/edge.cu): pass it as the third element of `feats` instead of a
+    view of densely computed edge maps.  w3[l] [256, 9*256] is filter2's 3x3 kernel tap-major ((ky, kx), input channel), w1[l]
+    [768, 768] filter1's 1x1 kernel; 16-bit operands in the stage's operand dtype, fp32 biases."""
+
+    def __init__(self, w3: List[torch.Tensor], b3: List[torch.Tensor], w1: List[torch.Tensor], b1: List[torch.Tensor],
+                 dtype: torch.dtype = torch.float16, device="cuda"):
+        assert dtype in (torch.float16, torch.bfloat16)
+        self.dtype = dtype
+        self.w3, self.b3, self.w1, self.b1 = [], [], [], []
+        for k in range(len(w3)):
+            co, ci, kh, kw = w3[k].shape
+            if (co, ci, kh, kw) != (256, 256, 3, 3) or tuple(w1[k].shape[:2]) != (768, 768):
+                raise RuntimeError("EdgeBlock: the kernels are specialised for WaveletsHFBlock(256)")
+            self.w3.append(w3[k].detach().permute(0, 2, 3, 1).reshape(co, kh * kw * ci).to(device=device, dtype=dtype).contiguous())
+            self.w1.append(w1[k].detach().reshape(768, 768).to(device=device, dtype=dtype).contiguous())
+            self.b3.append(b3[k].detach().to(device=device, dtype=torch.float32).contiguous())
+            self.b1.append(b1[k].detach().to(device=device, dtype=torch.float32).contiguous())
+
+    @staticmethod
+    def from_modules(blocks, dtype: torch.dtype = torch.float16, device="cuda") -> "EdgeBlock":
+        """blocks: the head's nn.ModuleList edge_enhance_reg (filter1 = Conv2d(768,768,1)+ReLU, filter2 = Conv2d(256,256,3,p=1)+ReLU)."""
+        blocks = [b if hasattr(b, "filter2") else b[0] for b in blocks]      # the head wraps each block in nn.Sequential (:206-212)
+        return EdgeBlock([b.filter2[0].weight for b in blocks], [b.filter2[0].bias for b in blocks],
+                         [b.filter1[0].weight for b in blocks], [b.filter1[0].bias for b in blocks], dtype, device)
+
+
+def edge_rows(block: EdgeBlock, feat_reg: L.View, feat_dtype: torch.dtype, anchors: AnchorSpec, gathered: dict, num_frames: int,
+              status: Optional[torch.Tensor] = None):
+    """Fills gathered['bank_edge'] with WaveletsHFBlock(feat_reg) at the kept proposals: patch / Haar rows per level
+    (tscd_edge_patches), two tcgen05 GEMMs per level with the device-side row count, combine (tscd_edge_combine)."""
+    bank = gathered["bank_edge"]
+    dev, dt = bank.device, bank.dtype
+    if dt != block.dtype:
+        raise RuntimeError(f"EdgeBlock weights are {block.dtype}, the bank is {dt}")
+    if len(block.w3) != len(anchors.hw):
+        raise RuntimeError("EdgeBlock: one weight set per pyramid level expected")
+    max_keep = gathered["max_keep"]
+    rows = num_frames * max_keep
+    seg_cap = [((min(rows, num_frames * h * w) + 127) // 128) * 128 for h, w in anchors.hw]
+    seg_base = [sum(seg_cap[:l]) for l in range(len(seg_cap))]
+    slots = sum(seg_cap)
+    patches = torch.empty(slots, 9 * 256, dtype=dt, device=dev)
+    hf = torch.empty(slots, 3 * 256, dtype=dt, device=dev)
+    content = torch.empty(slots, 256, dtype=dt, device=dev)
+    hf_out = torch.empty(slots, 3 * 256, dtype=dt, device=dev)
+    level_count = torch.empty(L.MAX_LEVELS, dtype=torch.int32, device=dev)
+    slot = torch.empty(bank.shape[0], dtype=torch.int32, device=dev)
+    a = L.EdgePatchesArgs()
+    a.num_frames, a.max_keep, a.feat_dtype, a.op_dtype = num_frames, max_keep, _DT[feat_dtype], _DT[dt]
+    a.anchors, a.feat_reg = anchors.to_c(), feat_reg
+    a.sel_idx, a.sel_count, a.row_off = _p(gathered["sel_idx"]), _p(gathered["sel_count"]), _p(gathered["row_off"])
+    for l in range(len(seg_cap)):
+        a.seg_base[l], a.seg_cap[l] = seg_base[l], seg_cap[l]
+    a.level_count, a.slot, a.patches, a.hf, a.status = _p(level_count), _p(slot), _p(patches), _p(hf), _p(status)
+    with L.timed("tscd_edge_patches"):
+        L.check(L.lib().tscd_edge_patches(C.byref(a), _stream()), "tscd_edge_patches")
+    for l in range(len(seg_cap)):
+        s0, s1 = seg_base[l], seg_base[l] + seg_cap[l]
+        linear(patches[s0:s1], block.w3[l], block.b3[l], m_dev=level_count[l:l + 1], out16=content[s0:s1], tag="edge_f2")
+        linear(hf[s0:s1], block.w1[l], block.b1[l], m_dev=level_count[l:l + 1], out16=hf_out[s0:s1], tag="edge_f1")
+    c = L.EdgeCombineArgs()
+    c.rows_cap, c.op_dtype = bank.shape[0], _DT[dt]
+    c.total_rows, c.slot = _p(gathered["row_off"][num_frames:]), _p(slot)
+    c.content, c.hf_out, c.bank_edge = _p(content), _p(hf_out), _p(bank)
+    with L.timed("tscd_edge_combine"):
+        L.check(L.lib().tscd_edge_combine(C.byref(c), _stream()), "tscd_edge_combine")
+    return bank
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, m_dev: Optional[torch.Tensor] = None,

@@ -89,6 +89,9 @@ def select_and_gather(head: ops.HeadViews, feats, feat_dtype, feat_dim, cfg: Sel
                                            rank=cand.get("rank"))
     out = ops.gather(head, feats, feat_dtype, feat_dim, cand, keep, keep_count, max_keep=max_keep,
                      bank_dtype=bank_dtype, bank_rows=bank_rows)
+    if isinstance(feats[2], ops.EdgeBlock):
+        # the wavelet edge block is evaluated at the kept proposals only (the dense maps are never built)
+        ops.edge_rows(feats[2], feats[1], feat_dtype, head.anchors, out, head.num_frames, status=status)
     out["cand"] = cand
     out["status"] = status
     return out
