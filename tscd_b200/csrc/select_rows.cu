@@ -80,69 +80,137 @@ select_rows_kernel(const tscd_select_args args, int sort_cap, int take_cap) {
     const bool sig = args.apply_sigmoid != 0;
     const int A8 = (A + 15) & ~7;                                          // room for the alignment shift of the keys
 
+    // the row staging area doubles as the per-warp digit histograms of the first radix pass (never less than NW * 512 bytes)
+    const size_t rows_bytes = max((size_t)take_cap * RPV * 16, (size_t)NW * 512);
     uint4* rows = reinterpret_cast<uint4*>(smem_raw);                      // [take_cap][RPV] staged survivor rows
-    uint32_t* sort32 = reinterpret_cast<uint32_t*>(rows + (size_t)take_cap * RPV);   // [sort_cap] (key << 16 | 0xffff - position)
+    uint32_t* sort32 = reinterpret_cast<uint32_t*>(smem_raw + rows_bytes); // [sort_cap] (key << 16 | 0xffff - position)
     unsigned short* k16_base = reinterpret_cast<unsigned short*>(sort32 + sort_cap); // [A8] keys
     unsigned short* sel16 = k16_base + A8;                                 // [take_cap] anchor id of compaction position i
     __shared__ SelSmem s;
-    __shared__ int warp_gt[NW], warp_eq[NW];
 
-    // ---- 1. objectness plane -> keys --------------------------------------------------------------------------
+    // ---- 1. objectness plane -> keys, and the histogram of their high bytes --------------------------------------
+    // Sigmoid logits share a few exponent bytes, so one shared histogram would serialise the whole CTA on a handful of bins:
+    // every warp counts into its OWN 256 x 16-bit histogram (two bins per word, plain shared atomics, no cross-warp
+    // contention; a warp sees < 65536 keys), merged once afterwards.
+    uint32_t* whist = reinterpret_cast<uint32_t*>(smem_raw) + wid * 128;
+    for (int i = tid; i < NW * 128; i += NT) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0u;
+    __syncthreads();
     const __half* op = reinterpret_cast<const __half*>(args.obj.ptr[0]) + (int64_t)frame * args.obj.frame_stride[0];
     const int head = min(A, (int)(((16u - (uint32_t)(reinterpret_cast<uintptr_t>(op) & 15u)) & 15u) >> 1));   // elements before 16-byte alignment
-    unsigned short* k16 = k16_base + ((8 - head) & 7);                     // k16[head + 8 g] is 16-byte aligned in shared memory
+    const int sh = (8 - head) & 7;
+    unsigned short* k16 = k16_base + sh;                                   // k16[head + 8 g] is 16-byte aligned in shared memory
     const int nvec = (A - head) >> 3;
+    auto count_hi = [&](uint32_t key) { atomicAdd(&whist[key >> 9], 1u << ((key >> 4) & 16u)); };   // bin = key >> 8: word bin / 2, half bin & 1
     for (int g = tid; g < nvec; g += NT) {
         const uint4 raw = __ldg(reinterpret_cast<const uint4*>(op + head) + g);
         const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
         uint32_t o[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) o[q] = canon_key16(w[q] & 0xffffu, sig) | (canon_key16(w[q] >> 16, sig) << 16);
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t k0 = canon_key16(w[q] & 0xffffu, sig), k1 = canon_key16(w[q] >> 16, sig);
+            count_hi(k0);
+            count_hi(k1);
+            o[q] = k0 | (k1 << 16);
+        }
         *reinterpret_cast<uint4*>(k16 + head + 8 * g) = make_uint4(o[0], o[1], o[2], o[3]);
     }
     for (int i = tid; i < head + (A - head - 8 * nvec); i += NT) {         // unaligned head + tail
         const int a = i < head ? i : 8 * nvec + i;
-        k16[a] = (unsigned short)canon_key16(__half_as_ushort(__ldg(op + a)), sig);
+        const uint32_t k = canon_key16(__half_as_ushort(__ldg(op + a)), sig);
+        count_hi(k);
+        k16[a] = (unsigned short)k;
     }
     __syncthreads();
 
-    // ---- 2. P-th largest key, stable compaction in ascending anchor order ------------------------------------------
+    // ---- 2. P-th largest key (two 8-bit digits), stable compaction in ascending anchor order --------------------------
     const int take_k = min(min(args.pre_k, A), take_cap);
-    uint32_t Tk;
-    int r_eq;
-    radix_select_kth<unsigned short>(k16, A, take_k, &s, &Tk, &r_eq);
-    const int per_warp = (((A + NW - 1) / NW) + 31) & ~31;                 // contiguous anchor range of a warp, whole 32-lane steps
-    const int w_lo = min(A, wid * per_warp), w_hi = min(A, w_lo + per_warp);
-    int n_gt = 0, n_eq = 0;
-    for (int a0 = w_lo; a0 < w_hi; a0 += 32) {
-        const int a = a0 + lane;
-        const uint32_t u = a < w_hi ? (uint32_t)k16[a] : 0u;
-        n_gt += __popc(__ballot_sync(0xffffffffu, a < w_hi && u > Tk));
-        n_eq += __popc(__ballot_sync(0xffffffffu, a < w_hi && u == Tk));
-    }
-    if (lane == 0) { warp_gt[wid] = n_gt; warp_eq[wid] = n_eq; }
-    __syncthreads();
-    int eq_before = 0, out_before = 0;
-    for (int w = 0; w < wid; ++w) {
-        const int e = warp_eq[w];
-        out_before += warp_gt[w] + max(0, min(e, r_eq - eq_before));
-        eq_before += e;
-    }
-    const unsigned lt_mask = (1u << lane) - 1u;
-    for (int a0 = w_lo; a0 < w_hi; a0 += 32) {
-        const int a = a0 + lane;
-        const uint32_t u = a < w_hi ? (uint32_t)k16[a] : 0u;
-        const unsigned m_eq = __ballot_sync(0xffffffffu, a < w_hi && u == Tk);
-        const int my_eq = eq_before + __popc(m_eq & lt_mask);
-        const bool take = a < w_hi && (u > Tk || (u == Tk && my_eq < r_eq));
-        const unsigned m_take = __ballot_sync(0xffffffffu, take);
-        if (take) {
-            const int i = out_before + __popc(m_take & lt_mask);
-            sort32[i] = (u << 16) | (0xffffu - (uint32_t)i);
-            sel16[i] = (unsigned short)a;
+    // suffix sums over the 256 bins from the top digit down (warp 0: lane l owns digits [8l, 8l+8)): the digit holding the
+    // `remaining`-th largest key -> s.misc[0], its rank inside that digit -> s.misc[1]
+    auto find_digit = [&](int remaining) {
+        if (tid < 32) {
+            int loc[8], tot = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { loc[j] = s.hist[255 - (lane * 8 + j)]; tot += loc[j]; }
+            const int inc = warp_incl_scan(tot, lane);
+            int cum = inc - tot;
+            if (cum < remaining && remaining <= inc) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (cum < remaining && remaining <= cum + loc[j]) { s.misc[0] = 255 - (lane * 8 + j); s.misc[1] = remaining - cum; }
+                    cum += loc[j];
+                }
+            }
         }
-        out_before += __popc(m_take);
-        eq_before += __popc(m_eq);
+    };
+    if (tid < 256) {                                                       // merge the per-warp histograms
+        const uint32_t* h = reinterpret_cast<const uint32_t*>(smem_raw) + (tid >> 1);
+        const int hs = 16 * (tid & 1);
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) tot += (int)((h[w * 128] >> hs) & 0xffffu);
+        s.hist[tid] = tot;
+    }
+    __syncthreads();
+    find_digit(take_k);
+    __syncthreads();
+    const uint32_t d_hi = (uint32_t)s.misc[0];
+    const int rem_hi = s.misc[1];
+    __syncthreads();
+    if (tid < 256) s.hist[tid] = 0;
+    __syncthreads();
+    // low byte among the keys of the threshold's high byte (a few hundred keys spread over 256 bins)
+    for (int g = tid; g < nvec; g += NT) {
+        const uint4 kv = *reinterpret_cast<const uint4*>(k16 + head + 8 * g);
+        const uint32_t w[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (((w[q] >> 8) & 255u) == d_hi) atomicAdd(&s.hist[w[q] & 255u], 1);
+            if ((w[q] >> 24) == d_hi) atomicAdd(&s.hist[(w[q] >> 16) & 255u], 1);
+        }
+    }
+    for (int i = tid; i < head + (A - head - 8 * nvec); i += NT) {
+        const uint32_t k = k16[i < head ? i : 8 * nvec + i];
+        if ((k >> 8) == d_hi) atomicAdd(&s.hist[k & 255u], 1);
+    }
+    __syncthreads();
+    find_digit(rem_hi);
+    __syncthreads();
+    const uint32_t Tk = (d_hi << 8) | (uint32_t)s.misc[0];
+    const int r_eq = s.misc[1];                                            // keys equal to Tk that belong to the top take_k
+    // compaction: a thread owns a CONTIGUOUS run of keys (whole aligned 16-byte vectors of the shifted key array), counts its
+    // keys above / equal to the threshold, one block scan of the packed counts gives its first output position
+    const int V = (A + sh + 7) >> 3, VPT = (V + NT - 1) / NT;
+    const int v_lo = min(V, tid * VPT), v_hi = min(V, v_lo + VPT);
+    uint32_t cnt = 0;                                                      // keys > Tk | keys == Tk << 16
+    for (int v = v_lo; v < v_hi; ++v) {
+        const uint4 kv = *reinterpret_cast<const uint4*>(k16_base + 8 * v);
+        const uint32_t w[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const uint32_t u = (w[e >> 1] >> (16 * (e & 1))) & 0xffffu;
+            if ((unsigned)(8 * v + e - sh) < (unsigned)A) cnt += (u > Tk ? 1u : 0u) + (u == Tk ? 0x10000u : 0u);
+        }
+    }
+    int tot_unused;
+    const uint32_t before = (uint32_t)block_excl_scan((int)cnt, s.scan, &tot_unused);
+    int eq_idx = (int)(before >> 16);
+    int out = (int)(before & 0xffffu) + min(eq_idx, r_eq);
+    for (int v = v_lo; v < v_hi; ++v) {
+        const uint4 kv = *reinterpret_cast<const uint4*>(k16_base + 8 * v);
+        const uint32_t w[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const uint32_t u = (w[e >> 1] >> (16 * (e & 1))) & 0xffffu;
+            const int a = 8 * v + e - sh;
+            if ((unsigned)a >= (unsigned)A) continue;
+            const bool eq = u == Tk;
+            if (u > Tk || (eq && eq_idx < r_eq)) {
+                sort32[out] = (u << 16) | (0xffffu - (uint32_t)out);
+                sel16[out] = (unsigned short)a;
+                ++out;
+            }
+            eq_idx += eq ? 1 : 0;
+        }
     }
     const int n_sel = take_k;                                              // exactly take_k anchors are selected
     for (int i = n_sel + tid; i < sort_cap; i += NT) sort32[i] = 0u;
@@ -265,7 +333,9 @@ int select_rows_try(const tscd_select_args* a, cudaStream_t st) {
     int sort_cap = kRowsThreads;
     while (sort_cap < take_cap) sort_cap <<= 1;
     if (sort_cap > 16 * kRowsThreads) return 0;
-    const size_t smem = (size_t)take_cap * rp * 2 + (size_t)sort_cap * 4 + (size_t)((A + 15) & ~7) * 2 + (size_t)take_cap * 2 + 16;
+    size_t rows_bytes = (size_t)take_cap * rp * 2;
+    if (rows_bytes < (size_t)(kRowsThreads / 32) * 512) rows_bytes = (size_t)(kRowsThreads / 32) * 512;   // per-warp histograms alias the rows
+    const size_t smem = rows_bytes + (size_t)sort_cap * 4 + (size_t)((A + 15) & ~7) * 2 + (size_t)take_cap * 2 + 16;
     if (smem > 200 * 1024) return 0;
     cudaError_t e;
     if (rp == 32) {
