@@ -100,3 +100,36 @@ def test_forward_host_rejects_pageable_memory():
     te = weights.timing_signal_1d(torch.arange(LF), 256)
     with pytest.raises(RuntimeError):
         st.forward_host(host, HW, te, 1, F, LF)
+
+
+@pytest.mark.parametrize("graph", [True, False])
+def test_forward_host_two_calls_in_flight(graph):
+    """forward_host_submit / forward_host_collect: two calls in flight on two slots (different input sets, separate buffers and
+    graphs) return exactly what the synchronous calls return; a busy slot cannot be resubmitted."""
+    from tscd_b200 import ops, selection, stage, weights
+    B, chunk = 4, 2
+    cfg = stage.StageConfig(num_classes=C, selection=selection.SelectionConfig(mode="A", pre_k=200, top_k=12, nms_thresh=0.75))
+    st = stage.AggregationStage(cfg, weights.random_state_dict(C, D, seed=5))
+    te = torch.cat([weights.timing_signal_1d(torch.arange(LF), 256)] * B, 0).pin_memory()
+    hosts = []
+    for seed in (31, 47):
+        dev = _synth(B, seed)
+        packed = ops.pack_head(ops.HeadViews.from_levels(dev["reg"], dev["obj"], dev["cls"], ops.AnchorSpec(HW)))
+        torch.cuda.synchronize()
+        h = {k: [torch.empty(t.shape, dtype=t.dtype, pin_memory=True, memory_format=torch.channels_last).copy_(t) for t in dev[k]]
+             for k in ("f_cls", "f_reg", "f_edge")}
+        h["rows"], h["objp"] = [packed._keep[0].cpu().pin_memory()], [packed._keep[1].cpu().pin_memory()]
+        hosts.append(h)
+    want = [st.forward_host(h, HW, te, B, F, LF, chunk_clips=chunk, graph=graph) for h in hosts]
+    assert sum(len(r) for r in want[0][0] if r is not None) > 0
+    for rounds in range(3):
+        t0 = st.forward_host_submit(hosts[0], HW, te, B, F, LF, chunk_clips=chunk, graph=graph, slot=0)
+        t1 = st.forward_host_submit(hosts[1], HW, te, B, F, LF, chunk_clips=chunk, graph=graph, slot=1)
+        with pytest.raises(RuntimeError):
+            st.forward_host_submit(hosts[0], HW, te, B, F, LF, chunk_clips=chunk, graph=graph, slot=0)
+        for ticket, w in ((t0, want[0]), (t1, want[1])):
+            res, ori, _, _ = st.forward_host_collect(ticket)
+            for gr, go, wr, wo in zip(res, ori, w[0], w[1]):
+                assert (gr is None) == (wr is None)
+                if gr is not None:
+                    assert torch.equal(gr, wr) and torch.equal(go, wo)

@@ -22,9 +22,13 @@ def main():
     ap.add_argument("--clips", type=int, default=32)
     ap.add_argument("--chunk", type=int, default=8)
     ap.add_argument("--config", default="ovis_a_k30")
+    ap.add_argument("--phases-only", action="store_true")
+    ap.add_argument("--pre-k", type=int, default=0, help="override the configuration's pre_k (what-if timing only)")
     args = ap.parse_args()
     from tscd_b200 import ops, selection, weights
-    cfg = bench.CONFIGS[args.config]
+    cfg = dict(bench.CONFIGS[args.config])
+    if args.pre_k:
+        cfg["pre_k"] = args.pre_k
     dev = torch.device("cuda", 0)
     F, Lf, C = cfg["F"], cfg["L"], cfg["C"]
     Be = args.clips
@@ -43,7 +47,7 @@ def main():
         torch.cuda.synchronize()
         return 1e3 * (time.perf_counter() - t0) / n
 
-    for graph, lanes, chunk in [(True, 2, 8), (True, 1, 8), (True, 3, 8), (True, 4, 8), (True, 2, 4), (True, 4, 4), (True, 2, 16), (True, 1, 32),
+    for graph, lanes, chunk in [] if args.phases_only else [(True, 2, 8), (True, 1, 8), (True, 3, 8), (True, 4, 8), (True, 2, 4), (True, 4, 4), (True, 2, 16), (True, 1, 32),
                                 (False, 2, 8), (False, 2, 16)]:
         ms = timed(lambda: st.forward_host(host, bench.HW, te, Be, F, Lf, chunk_clips=chunk, graph=graph, lanes=lanes))
         plan = list(st._host_plans.values())[-1]

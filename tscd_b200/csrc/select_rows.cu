@@ -19,6 +19,8 @@
 //      position is known; the copies are in flight while the CTA sorts the (key, position) pairs.
 //   4. block bitonic sort on 32-bit keys in registers, then one thread per survivor builds the record from the staged row:
 //      class max / arg-max, the two sigmoids, box decode.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace tscd {
@@ -337,15 +339,17 @@ int select_rows_try(const tscd_select_args* a, cudaStream_t st) {
     if (rows_bytes < (size_t)(kRowsThreads / 32) * 512) rows_bytes = (size_t)(kRowsThreads / 32) * 512;   // per-warp histograms alias the rows
     const size_t smem = rows_bytes + (size_t)sort_cap * 4 + (size_t)((A + 15) & ~7) * 2 + (size_t)take_cap * 2 + 16;
     if (smem > 200 * 1024) return 0;
+    size_t smem_launch = smem;
+    if (const char* pad = getenv("TSCD_K1_PAD_SMEM")) { const size_t v = (size_t)atoi(pad); if (v > smem_launch && v <= 200 * 1024) smem_launch = v; }
     cudaError_t e;
     if (rp == 32) {
-        e = cudaFuncSetAttribute(select_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(select_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_launch);
         if (e != cudaSuccess) return TSCD_ERR_CUDA;
-        select_rows_kernel<4><<<a->num_frames, kRowsThreads, smem, st>>>(*a, sort_cap, take_cap);
+        select_rows_kernel<4><<<a->num_frames, kRowsThreads, smem_launch, st>>>(*a, sort_cap, take_cap);
     } else {
-        e = cudaFuncSetAttribute(select_rows_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(select_rows_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_launch);
         if (e != cudaSuccess) return TSCD_ERR_CUDA;
-        select_rows_kernel<8><<<a->num_frames, kRowsThreads, smem, st>>>(*a, sort_cap, take_cap);
+        select_rows_kernel<8><<<a->num_frames, kRowsThreads, smem_launch, st>>>(*a, sort_cap, take_cap);
     }
     TSCD_CUDA_CHECK_LAUNCH();
     return 1;

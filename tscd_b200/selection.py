@@ -66,6 +66,13 @@ class SelectionConfig:
 def select_and_gather(head: ops.HeadViews, feats, feat_dtype, feat_dim, cfg: SelectionConfig,
                       bank_dtype=torch.float16, status: Optional[torch.Tensor] = None, bank_rows: Optional[int] = None):
     """Runs K1 (+K2) + K3.  Returns the dict of ops.gather plus the candidate dict under 'cand'."""
+    picked = select_candidates(head, cfg, status)
+    return gather_bank(head, feats, feat_dtype, feat_dim, cfg, picked, bank_dtype=bank_dtype, bank_rows=bank_rows)
+
+
+def select_candidates(head: ops.HeadViews, cfg: SelectionConfig, status: Optional[torch.Tensor] = None):
+    """K1 (+K2): candidate lists and, where the configuration has a pre-NMS, the kept positions.  Returns (cand, keep, keep_count,
+    status, max_keep) for gather_bank (forward_host runs the two halves on different lanes)."""
     A = head.anchors.num_anchors
     if status is None:
         status = torch.zeros(1, dtype=torch.int32, device=ops._dev(head))
@@ -87,6 +94,13 @@ def select_and_gather(head: ops.HeadViews, feats, feat_dtype, feat_dim, cfg: Sel
         keep, keep_count, status = ops.nms(cand["box"], cand["score"], cand["cls"], cand["count"], cfg.nms_thresh,
                                            max_keep=max_keep, status=status, strict_keep=cfg.mode == "B", tag="pre",
                                            rank=cand.get("rank"))
+    return cand, keep, keep_count, status, max_keep
+
+
+def gather_bank(head: ops.HeadViews, feats, feat_dtype, feat_dim, cfg: SelectionConfig, picked, bank_dtype=torch.float16,
+                bank_rows: Optional[int] = None):
+    """K3 (+ the selected-anchor edge block) on the output of select_candidates."""
+    cand, keep, keep_count, status, max_keep = picked
     out = ops.gather(head, feats, feat_dtype, feat_dim, cand, keep, keep_count, max_keep=max_keep,
                      bank_dtype=bank_dtype, bank_rows=bank_rows)
     if isinstance(feats[2], ops.EdgeBlock):

@@ -203,7 +203,7 @@ class AggregationStage:
 
     # ------------------------------------------------------------------------------------------------------
     def forward_host(self, host: dict, hw, time_embedding: torch.Tensor, B: int, F: int, Lf: int, chunk_clips: int = 8,
-                     strides=(8, 16, 32), zero_copy_logits: bool = False, graph: bool = True, lanes: int = 3):
+                     strides=(8, 16, 32), zero_copy_logits: bool = False, graph: bool = True, lanes: int = 4):
         """The stage for callers whose boundary tensors live in (pinned) HOST memory -> detections on the host.
 
         `host` holds per-level lists of pinned CPU tensors: the feature planes f_cls, f_reg, f_edge ([B*F, 256, H, W],
@@ -222,7 +222,17 @@ class AggregationStage:
         of host buffers into a CUDA graph and replayed afterwards -- callers that reuse their pinned staging buffers pay one
         cudaGraphLaunch per call instead of ~1.4 ms of launch overhead per chunk.  (The graph reads the buffers at their
         addresses: new tensors -> new capture; the four most recent plans are kept.)
+        forward_host = forward_host_submit + forward_host_collect; callers that stream clips keep two calls in flight (two
+        `slot`s: separate staging / output buffers and graphs) so that the PCIe phases of one call overlap the compute tail and the
+        host-side unpacking of the previous one.
         Returns (result, result_ori, h2d_bytes, d2h_bytes) with fresh host tensors in the reference's list layout."""
+        return self.forward_host_collect(self.forward_host_submit(host, hw, time_embedding, B, F, Lf, chunk_clips, strides,
+                                                                  zero_copy_logits, graph, lanes))
+
+    def forward_host_submit(self, host: dict, hw, time_embedding: torch.Tensor, B: int, F: int, Lf: int, chunk_clips: int = 8,
+                            strides=(8, 16, 32), zero_copy_logits: bool = False, graph: bool = True, lanes: int = 4, slot: int = 0):
+        """Launches one forward_host call without waiting for it; returns the ticket for forward_host_collect.  Calls submitted with
+        different `slot`s own separate buffers and may be in flight together; a slot must be collected before it is reused."""
         fused = "rows" in host
         head_keys = ("rows", "objp") if fused else ("reg", "obj", "cls")
         for k in head_keys + ("f_cls", "f_reg", "f_edge"):
@@ -232,24 +242,38 @@ class AggregationStage:
                                        "read them in place; there is no pageable-memory / CPU path")
         key = (tuple((k, t.data_ptr(), tuple(t.shape), t.stride(), t.dtype) for k in head_keys + ("f_cls", "f_reg", "f_edge") for t in host[k]),
                tuple(tuple(x) for x in hw), tuple(strides), B, F, Lf, chunk_clips, zero_copy_logits, graph, lanes,
-               tuple(time_embedding.shape))
+               tuple(time_embedding.shape), slot)
         plans = self.__dict__.setdefault("_host_plans", {})
         plan = plans.pop(key, None)
         if plan is None:
             plan = self._build_host_plan(host, hw, time_embedding, B, F, Lf, chunk_clips, strides, zero_copy_logits, graph, fused, lanes)
         plans[key] = plan                                      # most recently used last
         while len(plans) > 4:
-            plans.pop(next(iter(plans)))
+            idle = next((k for k, v in plans.items() if not v.get("busy") and v is not plan), None)
+            if idle is None:
+                break
+            plans.pop(idle)
+        if plan.get("busy"):
+            raise RuntimeError("forward_host_submit: this slot still has a call in flight (collect it first or use another slot)")
         plan["te_pin"].copy_(time_embedding)
         if plan["graph"] is not None:
-            plan["graph"].replay()
+            with torch.cuda.stream(plan["launch"]):            # one launch stream per plan: calls of different slots run concurrently
+                plan["graph"].replay()
+                plan["done"].record()
         else:
             plan["issue"]()
-        torch.cuda.current_stream().synchronize()
+            plan["done"].record()
+        plan["busy"] = True
+        return plan
+
+    def forward_host_collect(self, plan):
+        """Waits for a submitted call and returns (result, result_ori, h2d_bytes, d2h_bytes)."""
+        plan["done"].synchronize()
+        plan["busy"] = False
         result, result_ori, d2h = [], [], 0
         h2d = plan["h2d"]
         for nc, pk in plan["pend"]:
-            r, o, nb, zb = self._unpack_host(pk, nc * Lf)
+            r, o, nb, zb = self._unpack_host(pk, nc * plan["Lf"])
             result += r
             result_ori += o
             d2h += nb
@@ -275,9 +299,11 @@ class AggregationStage:
         te_pin = torch.empty(time_embedding.shape, dtype=time_embedding.dtype, pin_memory=True)
         te_pin.copy_(time_embedding)
         cp = torch.cuda.Stream(device=dev)
+        io = torch.cuda.Stream(device=dev, priority=-1)
         aux = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(max(0, n_lanes - 1))]
         chunks = [(c0, min(chunk_clips, B - c0)) for c0 in range(0, B, chunk_clips)]
-        plan = {"te_pin": te_pin, "graph": None, "pend": None, "h2d": 0, "_keep": (dbuf, host, cp, aux)}
+        plan = {"te_pin": te_pin, "graph": None, "pend": None, "h2d": 0, "_keep": (dbuf, host, cp, aux, io), "Lf": Lf, "busy": False,
+                "done": torch.cuda.Event(), "launch": torch.cuda.Stream(device=dev, priority=-1)}
         fused_row_bytes = host["rows"][0].shape[2] * 2 if fused else None
 
         def issue():
@@ -297,17 +323,23 @@ class AggregationStage:
                     ev.record(cp)
                     events.append(ev)
             te_dev.record_stream(main)
-            # chunks alternate between two compute streams: K1 / K3 of one chunk wait on PCIe (rows and features are read in
-            # place) while the tensor-core tail of the previous chunk runs
-            lanes = ([main] + aux)[:max(1, len(chunks))]
+            # Software pipeline over chunks of clips: ONE i/o lane runs K1 -> K2 -> K3 of every chunk back to back -- these are
+            # the PCIe-bound kernels (survivor rows and kept feature rows are read in place), so the link never idles --
+            # while the tensor-core / latency-bound tail of the previous chunks runs on the compute lanes.  (Chunks that walk
+            # through all phases in lockstep on parallel lanes leave the link idle during every compute phase.)
+            cfg_sel = self.cfg.selection
+            kmax = cfg_sel.max_keep(an.num_anchors)
+            if _r128(F * kmax) > MAX_KEYS_PER_CLIP:
+                raise RuntimeError(f"{F} frames x {kmax} proposals per frame exceed the attention kernels' capacity of {MAX_KEYS_PER_CLIP} keys per clip")
+            lanes = ([main] + aux)[:max(1, min(len(chunks), n_lanes))]
+            io.wait_stream(main)
             for a_ in lanes[1:]:
                 a_.wait_stream(main)
-            pend = []
-            for ci, ((c0, nc), ev) in enumerate(zip(chunks, events)):
-                f0, f1 = c0 * F, (c0 + nc) * F
-                lane_s = lanes[ci % len(lanes)]
-                with torch.cuda.stream(lane_s):
-                    lane_s.wait_event(ev)
+            banks = []
+            with torch.cuda.stream(io):
+                for (c0, nc), ev in zip(chunks, events):
+                    f0, f1 = c0 * F, (c0 + nc) * F
+                    io.wait_event(ev)
                     if fused:
                         rows_src = host["rows"][0] if rows_in_place else dbuf["rows"][0]
                         head = ops.HeadViews.from_rows(rows_src[f0:f1], dbuf["objp"][0][f0:f1], an, self.cfg.num_classes)
@@ -316,13 +348,27 @@ class AggregationStage:
                         head = ops.HeadViews.from_levels([t[f0:f1] for t in src["reg"]], [t[f0:f1] for t in src["obj"]],
                                                          [t[f0:f1] for t in src["cls"]], an)
                     feats = tuple(ops.view_levels([t[f0:f1] for t in host[k]]) for k in ("f_cls", "f_reg", "f_edge"))
+                    status = torch.zeros(1, dtype=torch.int32, device=dev)
+                    sel = _selection.select_and_gather(head, feats, feat_dtype, self.cfg.dim, cfg_sel, bank_dtype=self.cfg.dtype,
+                                                       status=status, bank_rows=_r128(nc * F * kmax) + 128)
+                    evb = torch.cuda.Event()
+                    evb.record(io)
+                    banks.append((sel, status, evb))
+            pend = []
+            for ci, ((c0, nc), (sel, status, evb)) in enumerate(zip(chunks, banks)):
+                lane_s = lanes[ci % len(lanes)]
+                with torch.cuda.stream(lane_s):
+                    lane_s.wait_event(evb)
                     if lane_s is not main:
                         te_dev.record_stream(lane_s)
-                    out = self.forward(head, feats, feat_dtype, te_dev[c0 * Lf:(c0 + nc) * Lf], nc, F, Lf)
+                    out = self.forward_from_bank(sel, nc, F, Lf, kmax, te_dev[c0 * Lf:(c0 + nc) * Lf], status=status)
                     reuse = plan["pend"][len(pend)][1] if plan["pend"] is not None else None
                     pend.append((nc, self._pack_to_host(out, zc or rows_in_place, fused_row_bytes, reuse)))
+            main.wait_stream(io)
             for a_ in lanes[1:]:
                 main.wait_stream(a_)
+            # the banks were allocated on the i/o lane and are read on the compute lanes: keep them until the call has synchronised
+            plan["_banks"] = banks
             plan["pend"], plan["h2d"] = pend, h2d
 
         plan["issue"] = issue
