@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=8)
     ap.add_argument("--config", default="ovis_a_k30")
     ap.add_argument("--phases-only", action="store_true")
+    ap.add_argument("--pipeline-only", action="store_true")
     ap.add_argument("--pre-k", type=int, default=0, help="override the configuration's pre_k (what-if timing only)")
     args = ap.parse_args()
     from tscd_b200 import ops, selection, weights
@@ -47,7 +48,7 @@ def main():
         torch.cuda.synchronize()
         return 1e3 * (time.perf_counter() - t0) / n
 
-    for graph, lanes, chunk in [] if args.phases_only else [(True, 2, 8), (True, 1, 8), (True, 3, 8), (True, 4, 8), (True, 2, 4), (True, 4, 4), (True, 2, 16), (True, 1, 32),
+    for graph, lanes, chunk in [] if (args.phases_only or args.pipeline_only) else [(True, 2, 8), (True, 1, 8), (True, 3, 8), (True, 4, 8), (True, 2, 4), (True, 4, 4), (True, 2, 16), (True, 1, 32),
                                 (False, 2, 8), (False, 2, 16)]:
         ms = timed(lambda: st.forward_host(host, bench.HW, te, Be, F, Lf, chunk_clips=chunk, graph=graph, lanes=lanes))
         plan = list(st._host_plans.values())[-1]
@@ -61,6 +62,26 @@ def main():
             torch.cuda.synchronize()
             gpu = f" (GPU {e0.elapsed_time(e1):.2f} ms)"
         print(f"forward_host graph={graph} lanes={lanes} chunk={chunk}: {ms:.2f} ms/call{gpu} -> {Be * F / ms * 1e3:.0f} clip-frames/s")
+    # pipelined throughput: `depth` calls in flight on separate slots
+    for depth, lanes, chunk in [] if args.phases_only else [(2, 4, 8), (3, 4, 8), (3, 6, 4), (4, 4, 8), (3, 4, 4), (4, 6, 4), (3, 8, 4), (3, 8, 2)]:
+        def submit(i):
+            return st.forward_host_submit(host, bench.HW, te, Be, F, Lf, chunk_clips=chunk, lanes=lanes, slot=i % depth)
+        for i in range(2 * depth):
+            st.forward_host_collect(submit(i))
+        n, infl = 12 * depth, []
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(n):
+            infl.append(submit(i))
+            if len(infl) == depth:
+                st.forward_host_collect(infl.pop(0))
+        while infl:
+            st.forward_host_collect(infl.pop(0))
+        ms = 1e3 * (time.perf_counter() - t0) / n
+        print(f"pipelined depth={depth} lanes={lanes} chunk={chunk}: {ms:.2f} ms/call -> {Be * F / ms * 1e3:.0f} clip-frames/s")
+        st._host_plans.clear()
+    if args.pipeline_only:
+        return
     # phases of the graph path
     st.forward_host(host, bench.HW, te, Be, F, Lf, chunk_clips=args.chunk, graph=True)
     plan = list(st._host_plans.values())[-1]
