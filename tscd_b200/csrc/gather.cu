@@ -8,8 +8,6 @@
 // element loads for NCHW planes.
 #include <type_traits>
 
-#include <cstdlib>
-
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -283,8 +281,7 @@ static int launch_gather_kernel(const tscd_gather_args* a, dim3 grid, int rp, in
 template <typename TF>
 static int launch_gather_tb(const tscd_gather_args* a, dim3 grid, cudaStream_t st) {
     const int rp = fused_rows_pitch(a->anchors, a->reg, a->obj, a->cls, a->num_classes, a->head_dtype, false);
-    int bulk = gather_bulk_ok(a) ? 1 : 0;
-    if (const char* e = getenv("TSCD_GATHER_BULK")) { if (e[0] == '0') bulk = 0; }
+    const int bulk = gather_bulk_ok(a) ? 1 : 0;
     switch (a->bank_dtype) {
         case TSCD_F32: return launch_gather_kernel<TF, float>(a, grid, rp, 0, st);
         case TSCD_F16: return launch_gather_kernel<TF, __half>(a, grid, rp, bulk, st);

@@ -14,13 +14,14 @@
 //      x > 9 or x < -80, and |x| < 2^-9 where fp16 steps are finer than the fp32 score's); those keys are replaced by the lowest key of their plateau (binary search on the
 //      same sigmoid the scores use), which makes "order by key" identical to "order by score" -- no fp32 score of the 6804
 //      anchors is ever computed.  tests/test_gpu_selection.py checks the equivalence exhaustively over all 65536 fp16 values.
-//   2. two-pass radix select of the P-th largest key; warp-cooperative stable compaction (ballots, no bank conflicts).
-//   3. every survivor's row is requested with cp.async (16-byte global -> shared copies, 4 or 8 per row) as soon as its
-//      position is known; the copies are in flight while the CTA sorts the (key, position) pairs.
-//   4. block bitonic sort on 32-bit keys in registers, then one thread per survivor builds the record from the staged row:
-//      class max / arg-max, the two sigmoids, box decode.
-#include <cstdlib>
-
+//   2. two-digit radix select of the P-th largest key: the high-byte histogram is built WHILE the keys are produced, into
+//      per-warp private 16-bit histograms (sigmoid logits share a few exponent bytes: a shared histogram serialises the CTA on a
+//      handful of bins); the low-byte pass only touches the few hundred keys of the threshold's high byte.  Stable compaction:
+//      every thread owns a contiguous run of keys, counts (> T, == T) locally, ONE block scan of the packed counts places them.
+//   3. every survivor's row is requested with cp.async (16-byte global -> shared copies, 4 or 8 adjacent lanes per row = one
+//      coalesced 64 / 128-byte request) as soon as its position is known.
+//   4. (only without cand_rank) block bitonic sort on 32-bit keys; then one thread per survivor builds the record from the
+//      staged row: class max / arg-max, the two sigmoids, box decode.
 #include "common.cuh"
 
 namespace tscd {
@@ -339,17 +340,15 @@ int select_rows_try(const tscd_select_args* a, cudaStream_t st) {
     if (rows_bytes < (size_t)(kRowsThreads / 32) * 512) rows_bytes = (size_t)(kRowsThreads / 32) * 512;   // per-warp histograms alias the rows
     const size_t smem = rows_bytes + (size_t)sort_cap * 4 + (size_t)((A + 15) & ~7) * 2 + (size_t)take_cap * 2 + 16;
     if (smem > 200 * 1024) return 0;
-    size_t smem_launch = smem;
-    if (const char* pad = getenv("TSCD_K1_PAD_SMEM")) { const size_t v = (size_t)atoi(pad); if (v > smem_launch && v <= 200 * 1024) smem_launch = v; }
     cudaError_t e;
     if (rp == 32) {
-        e = cudaFuncSetAttribute(select_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_launch);
+        e = cudaFuncSetAttribute(select_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return TSCD_ERR_CUDA;
-        select_rows_kernel<4><<<a->num_frames, kRowsThreads, smem_launch, st>>>(*a, sort_cap, take_cap);
+        select_rows_kernel<4><<<a->num_frames, kRowsThreads, smem, st>>>(*a, sort_cap, take_cap);
     } else {
-        e = cudaFuncSetAttribute(select_rows_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_launch);
+        e = cudaFuncSetAttribute(select_rows_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return TSCD_ERR_CUDA;
-        select_rows_kernel<8><<<a->num_frames, kRowsThreads, smem_launch, st>>>(*a, sort_cap, take_cap);
+        select_rows_kernel<8><<<a->num_frames, kRowsThreads, smem, st>>>(*a, sort_cap, take_cap);
     }
     TSCD_CUDA_CHECK_LAUNCH();
     return 1;
