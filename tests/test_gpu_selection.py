@@ -473,3 +473,47 @@ def test_select_mode_a_sigmoid_saturation_ties():
         assert got[:n_sat] == want[:n_sat], f"frame {f}: saturated ties must come in anchor order"
         want_gpu = oracle.topk_lower_index_first(torch.sigmoid(flat_obj[f].cuda()).cpu(), 750).tolist()    # ATen-CUDA sigmoid: identical
         assert got == want_gpu
+
+
+@pytest.mark.parametrize("hw", [[(5, 7), (3, 3), (1, 2)], [(9, 9), (5, 4), (2, 3)], [(40, 40), (20, 20), (10, 10)]])
+@pytest.mark.parametrize("C", [3, 30])
+def test_select_fused_rows_small_shapes_and_threshold_ties(hw, C):
+    """Fused-row K1 (per-warp digit histograms, thread-contiguous compaction) on odd shapes: anchor counts that are not multiples
+    of 8, an odd frame count (objectness rows only 2-byte aligned from frame to frame), pre_k from 1 to beyond the anchor count,
+    and objectness logits quantised to steps of 0.5 so that MANY anchors tie on the threshold key -- the selected ids must be the
+    stable top-k (equal scores: lower anchor id first), sorted and unsorted (anchor-order) variants alike."""
+    ops, _ = _stage_mods()
+    Fn = 5
+    an = ops.AnchorSpec(hw)
+    A = an.num_anchors
+    g = torch.Generator().manual_seed(1000 + A + C)
+    rp = ops.row_pitch(C)
+    rows = torch.zeros(Fn, A, rp, dtype=torch.float16)
+    rows[..., 0:2] = torch.rand(Fn, A, 2, generator=g).half()
+    rows[..., 2:4] = (torch.randn(Fn, A, 2, generator=g) * 0.5).half()
+    obj = (torch.randn(Fn, A, generator=g) * 2 - 3).mul(2).round().div(2).half()       # steps of 0.5: heavy ties
+    obj[0, : min(A, 20)] = 30.0                                                         # saturated block (score 1.0f) in frame 0
+    rows[..., 4] = obj
+    rows[..., 5:5 + C] = (torch.randn(Fn, A, C, generator=g) * 2 - 3).half()
+    objp_dev = torch.zeros(Fn, (A + 7) // 8 * 8 + 1, dtype=torch.float16, device="cuda")   # odd pitch: misaligned frame rows
+    objp_dev[:, :A] = obj.cuda()
+    head = ops.HeadViews.from_rows(rows.cuda(), objp_dev[:, :A], an, C)
+    score = torch.sigmoid(obj.float().cuda()).cpu()
+    for pre_k in sorted({1, 8, 33, 64, max(1, A - 1), A, A + 50}):
+        cand = ops.select(head, "A", pre_k=pre_k)
+        torch.cuda.synchronize()
+        k = min(pre_k, A)
+        assert cand["count"].cpu().tolist() == [k] * Fn
+        for f in range(Fn):
+            want = oracle.topk_lower_index_first(score[f], k).tolist()
+            assert cand["idx"][f, :k].cpu().tolist() == want, (pre_k, f)
+        if 64 < k <= 1024 and k < A:          # (larger lists may exceed the row staging area: the generic kernel takes over, sorted only)
+            uns = ops.select(head, "A", pre_k=pre_k, unsorted=True)
+            torch.cuda.synchronize()
+            for f in range(Fn):
+                assert uns["idx"][f, :k].cpu().tolist() == sorted(cand["idx"][f, :k].cpu().tolist()), (pre_k, f)
+                # the rank's high half orders like the score, its low half is 0xffff - position
+                r = uns["rank"][f, :k].cpu().to(torch.int64) & 0xffffffff
+                assert ((r & 0xffff) == 0xffff - torch.arange(k)).all()
+                order = torch.sort(r, descending=True, stable=True).indices
+                assert uns["idx"][f, :k].cpu()[order].tolist() == cand["idx"][f, :k].cpu().tolist(), (pre_k, f)
