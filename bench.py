@@ -25,7 +25,7 @@ is >= 100 ms of GPU work, 20 steps are seconds, and the sustained peaks of MEASU
 
 value : whole-job clip-frames/s with the step's inputs resident in HBM.
 e2e   : same metric through AggregationStage.forward_host_submit / forward_host_collect with HOST (pinned) inputs: H2D of what
-        the kernels consume and D2H of the detections inside the timed region; `--e2e-depth` (3) calls are kept in flight the
+        the kernels consume and D2H of the detections inside the timed region; `--e2e-depth` (4) calls are kept in flight the
         way a streaming caller double-buffers (e2e.sync_call_ms is the latency of a lone synchronous call).
 roofline : the dominant kernel (largest time per step among single kernels, launches of identical shape averaged), measured live
         with CUDA events in this process; `kernels` lists EVERY kernel of the step the same way.
@@ -675,7 +675,7 @@ def main():
     ap.add_argument("--sets", type=int, default=2, help="rotating input sets resident in HBM")
     ap.add_argument("--e2e-clips", type=int, default=0)
     ap.add_argument("--e2e-chunk", type=int, default=8, help="clips per pipelined chunk of the host-buffer path")
-    ap.add_argument("--e2e-depth", type=int, default=3, help="forward_host calls kept in flight by the e2e loop (1 = synchronous calls)")
+    ap.add_argument("--e2e-depth", type=int, default=4, help="forward_host calls kept in flight by the e2e loop (1 = synchronous calls)")
     ap.add_argument("--cpu-clips", type=int, default=6, help="clips timed for cpu_baseline (rank 0, N=1)")
     ap.add_argument("--head-layout", default="rows", choices=["rows", "levels"],
                     help="rows: fused 64-byte head rows + objectness plane (what the drop-in head emits); levels: per-level channels_last conv outputs")

@@ -221,7 +221,7 @@ class AggregationStage:
         graph=True: the whole call (copies, every chunk's ~130 launches on two streams, read-backs) is captured ONCE per set
         of host buffers into a CUDA graph and replayed afterwards -- callers that reuse their pinned staging buffers pay one
         cudaGraphLaunch per call instead of ~1.4 ms of launch overhead per chunk.  (The graph reads the buffers at their
-        addresses: new tensors -> new capture; the four most recent plans are kept.)
+        addresses: new tensors -> new capture; the eight most recent plans are kept.)
         forward_host = forward_host_submit + forward_host_collect; callers that stream clips keep two calls in flight (two
         `slot`s: separate staging / output buffers and graphs) so that the PCIe phases of one call overlap the compute tail and the
         host-side unpacking of the previous one.
@@ -248,7 +248,7 @@ class AggregationStage:
         if plan is None:
             plan = self._build_host_plan(host, hw, time_embedding, B, F, Lf, chunk_clips, strides, zero_copy_logits, graph, fused, lanes)
         plans[key] = plan                                      # most recently used last
-        while len(plans) > 4:
+        while len(plans) > 8:
             idle = next((k for k, v in plans.items() if not v.get("busy") and v is not plan), None)
             if idle is None:
                 break
