@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
             }
         }
     } else if (warp == 17) {
-        if (lane == 0) {
+        {   // the whole warp walks the loop (warp-uniform operands stay in uniform registers); one elected lane issues
             const uint32_t idesc128 = make_idesc_f16(BF16, 128, 128);
             uint32_t it = 0;
             for (int h = 0; h < HA; ++h) {
@@ -403,14 +403,18 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                     tc_fence_after();
                     const uint64_t dkc = make_smem_desc_sw128(smem_u32(sKV + st * 32768));
                     const uint64_t dkr = make_smem_desc_sw128(smem_u32(sKV + st * 32768 + 16384));
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(tmem + sb * 256, dqc + 2 * k, dkc + 2 * k, idesc128, k ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k) umma_f16(tmem + sb * 256, dqc + 2 * k, dkc + 2 * k, idesc128, k ? 1u : 0u);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(tmem + sb * 256 + 128, dqr + 2 * k, dkr + 2 * k, idesc128, k ? 1u : 0u);
-                    umma_commit(&bars.k_empty[st]);
-                    umma_commit(&bars.s_full[sb]);
+                        for (int k = 0; k < 4; ++k) umma_f16(tmem + sb * 256 + 128, dqr + 2 * k, dkr + 2 * k, idesc128, k ? 1u : 0u);
+                        umma_commit(&bars.k_empty[st]);
+                        umma_commit(&bars.s_full[sb]);
+                    }
+                    __syncwarp();
                 }
-                umma_commit(&bars.q_empty[qb]);
+                if (elect_one()) umma_commit(&bars.q_empty[qb]);
+                __syncwarp();
             }
         }
     } else if (is_sm) {
@@ -503,7 +507,7 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                 }
         }
     } else if (warp == 17) {
-        if (lane == 0) {        // scores of every tile
+        {                       // scores of every tile (whole warp walks the loop, one elected lane issues: uniform operands)
             const uint32_t idesc64 = make_idesc_f16(BF16, 128, 64);
             uint32_t it = itA;          // key-tile counter (ring stage / score buffer of tile `it`)
             for (int h = 0; h < 4; ++h) {
@@ -518,18 +522,22 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                     tc_fence_after();
                     const uint64_t dkc = make_smem_desc_sw128(smem_u32(sKV + st * 32768));
                     const uint64_t dkr = make_smem_desc_sw128(smem_u32(sKV + st * 32768 + 8192));
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(tmem + sb * 128, dqc + 2 * k, dkc + 2 * k, idesc64, k ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k) umma_f16(tmem + sb * 128, dqc + 2 * k, dkc + 2 * k, idesc64, k ? 1u : 0u);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(tmem + sb * 128 + 64, dqr + 2 * k, dkr + 2 * k, idesc64, k ? 1u : 0u);
-                    umma_commit(&bars.k_empty[st]);
-                    umma_commit(&bars.s_full[sb]);
+                        for (int k = 0; k < 4; ++k) umma_f16(tmem + sb * 128 + 64, dqr + 2 * k, dkr + 2 * k, idesc64, k ? 1u : 0u);
+                        umma_commit(&bars.k_empty[st]);
+                        umma_commit(&bars.s_full[sb]);
+                    }
+                    __syncwarp();
                 }
-                umma_commit(&bars.q_empty[qb]);
+                if (elect_one()) umma_commit(&bars.q_empty[qb]);
+                __syncwarp();
             }
         }
     } else if (warp == 18) {
-        if (lane == 0) {        // P @ V of every tile
+        {                       // P @ V of every tile
             const uint32_t idesc64 = make_idesc_f16(BF16, 128, 64);
             const uint32_t idesc128b = make_idesc_f16(BF16, 128, 128);
             uint32_t ip = 0;            // P@V counter (tile whose probabilities are consumed next)
@@ -543,23 +551,27 @@ __global__ void __launch_bounds__(kPvThreads, 1) attn_pv_kernel(const __grid_con
                     const uint64_t dpc = make_smem_desc_sw128(smem_u32(sP + pb * 32768));
                     const uint64_t dpr = make_smem_desc_sw128(smem_u32(sP + pb * 32768 + 16384));
                     const uint64_t dvc = make_smem_desc_sw128(smem_u32(sKV + st * 32768 + 16384));
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t acc = (g > 0 || k) ? 1u : 0u;
-                        if (need_reg) {
-                            // Vc^T and Vr^T tiles are adjacent in the stage: one N = 128 product per probability
-                            // matrix (the A operand is read from shared memory once instead of twice)
-                            umma_f16(tmem + 256, dpc + 2 * k, dvc + 2 * k, idesc128b, acc);   // O_cc | O_cr
-                            umma_f16(tmem + 384, dpr + 2 * k, dvc + 2 * k, idesc128b, acc);   // O_rc | O_rr
-                        } else {
-                            umma_f16(tmem + 256, dpc + 2 * k, dvc + 2 * k, idesc64, acc);     // O_cc
-                            umma_f16(tmem + 320, dpr + 2 * k, dvc + 2 * k, idesc64, acc);     // O_rc
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t acc = (g > 0 || k) ? 1u : 0u;
+                            if (need_reg) {
+                                // Vc^T and Vr^T tiles are adjacent in the stage: one N = 128 product per probability
+                                // matrix (the A operand is read from shared memory once instead of twice)
+                                umma_f16(tmem + 256, dpc + 2 * k, dvc + 2 * k, idesc128b, acc);   // O_cc | O_cr
+                                umma_f16(tmem + 384, dpr + 2 * k, dvc + 2 * k, idesc128b, acc);   // O_rc | O_rr
+                            } else {
+                                umma_f16(tmem + 256, dpc + 2 * k, dvc + 2 * k, idesc64, acc);     // O_cc
+                                umma_f16(tmem + 320, dpr + 2 * k, dvc + 2 * k, idesc64, acc);     // O_rc
+                            }
                         }
+                        umma_commit(&bars.v_empty[st]);
+                        umma_commit(&bars.p_empty[pb]);
                     }
-                    umma_commit(&bars.v_empty[st]);
-                    umma_commit(&bars.p_empty[pb]);
+                    __syncwarp();
                 }
-                umma_commit(&bars.o_full);
+                if (elect_one()) umma_commit(&bars.o_full);
+                __syncwarp();
             }
         }
     } else if (is_sm) {
@@ -847,7 +859,7 @@ __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid
         }
     } else if (warp == 17) {
         // ------------------------------------------------ S pipeline: MMA issuer (score units) ------------------------------------------------
-        if (lane == 0 && !reuse) {
+        if (!reuse) {             // whole warp walks the loop (uniform operands), one elected lane issues
             const uint32_t idesc64 = make_idesc_f16(BF16, 128, 64);
             R2Ring ring(0, n_s);
             R2_WAIT(&bars.res_full, 0, 414);
@@ -862,15 +874,18 @@ __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid
                     tc_fence_after();
                     const uint64_t dq = make_smem_desc_sw128(smem_u32(sRes + u * 16384));
                     const uint64_t dk = make_smem_desc_sw128(smem_u32(sRing + sl * kR2SlotBytes));
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(tmem + 384 + su * 64, dq + 2 * k, dk + 2 * k, idesc64, k ? 1u : 0u);
-                    umma_commit(&bars.empty[sl]);
-                    umma_commit(&bars.s_full[su]);
+                        for (int k = 0; k < 4; ++k) umma_f16(tmem + 384 + su * 64, dq + 2 * k, dk + 2 * k, idesc64, k ? 1u : 0u);
+                        umma_commit(&bars.empty[sl]);
+                        umma_commit(&bars.s_full[su]);
+                    }
+                    __syncwarp();
                 }
         }
     } else if (warp == 19) {
         // ------------------------------------------------ X pipeline: MMA issuer (raw-v similarity, W @ V^T) ------------------------------------------------
-        if (lane == 0) {
+        {
             const uint32_t idesc64 = make_idesc_f16(BF16, 128, 64);
             const uint32_t idesc128 = make_idesc_f16(BF16, 128, 128);
             R2Ring ring(n_s, n_x);
@@ -894,10 +909,13 @@ __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid
                     const uint64_t da = make_smem_desc_sw128(smem_u32(reuse ? sRes + at * 16384 : d));
                     const uint64_t db = make_smem_desc_sw128(smem_u32(reuse ? d : d + 16384));
                     const uint32_t col = tmem + 256 + (reuse ? rb : br) * 64;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(col, da + 2 * k, db + 2 * k, idesc64, (at | k) ? 1u : 0u);
-                    for (int j = 0; j < n; ++j) umma_commit(&bars.empty[sl + j]);
-                    if (i == atom1 - 1) umma_commit(&bars.r_full[rb]);
+                        for (int k = 0; k < 4; ++k) umma_f16(col, da + 2 * k, db + 2 * k, idesc64, (at | k) ? 1u : 0u);
+                        for (int j = 0; j < n; ++j) umma_commit(&bars.empty[sl + j]);
+                        if (i == atom1 - 1) umma_commit(&bars.r_full[rb]);
+                    }
+                    __syncwarp();
                 } else {                         // U += W(kt) @ V^T(kt), 128-dim half i
                     const int wb = reuse ? (kt & 1) : 0, use = reuse ? (kt >> 1) : kt;
                     if (i == 0) {
@@ -909,14 +927,18 @@ __global__ void __launch_bounds__(kR2Threads, 1) attn_round2_kernel(const __grid
                     tc_fence_after();
                     const uint64_t dw = make_smem_desc_sw128(smem_u32(sW + wb * 16384));
                     const uint64_t dv = make_smem_desc_sw128(smem_u32(sRing + sl * kR2SlotBytes));
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(tmem + i * 128, dw + 2 * k, dv + 2 * k, idesc128, (kt | k) ? 1u : 0u);
-                    umma_commit(&bars.empty[sl]);
-                    umma_commit(&bars.empty[sl + 1]);
-                    if (i == 1) umma_commit(&bars.w_empty[wb]);
+                        for (int k = 0; k < 4; ++k) umma_f16(tmem + i * 128, dw + 2 * k, dv + 2 * k, idesc128, (kt | k) ? 1u : 0u);
+                        umma_commit(&bars.empty[sl]);
+                        umma_commit(&bars.empty[sl + 1]);
+                        if (i == 1) umma_commit(&bars.w_empty[wb]);
+                    }
+                    __syncwarp();
                 }
             });
-            umma_commit(&bars.u_full);
+            if (elect_one()) umma_commit(&bars.u_full);
+            __syncwarp();
         }
     } else {
         // ------------------------------------------------ softmax / weight warps ------------------------------------------------

@@ -144,7 +144,8 @@ __global__ void __launch_bounds__(EPI ? kGemmThreadsFused : kGemmThreads) gemm_t
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // the whole warp walks the tile loop (warp-uniform operands stay in uniform registers: no per-instruction broadcast
+            // loop in front of every tcgen05.mma), one elected lane issues
             const uint32_t idesc = make_idesc_f16(BF16, kGemmBM, BN);
             uint32_t it = 0, ti = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
@@ -160,14 +161,18 @@ __global__ void __launch_bounds__(EPI ? kGemmThreadsFused : kGemmThreads) gemm_t
                     tc_fence_after();
                     const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + s * kABytes));
                     const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sW + s * kWBytes));
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < kGemmBK / 16; ++k) {
-                        // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
-                        umma_f16(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                        for (int k = 0; k < kGemmBK / 16; ++k) {
+                            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
+                            umma_f16(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                        }
+                        umma_commit(&empty_bar[s]);
                     }
-                    umma_commit(&empty_bar[s]);
+                    __syncwarp();
                 }
-                umma_commit(&tmem_full_bar[acc]);
+                if (elect_one()) umma_commit(&tmem_full_bar[acc]);
+                __syncwarp();
             }
         }
     } else {
