@@ -245,7 +245,7 @@ __device__ bool nms_per_class(const tscd_nms_args& args, int frame, int n, const
 
 // only_redo: second launch after nms_matrix_kernel -- only the frames it marked with keep_count == -1 (per-class decomposition
 // not applicable, too large for the suppression matrix) are processed
-__global__ void __launch_bounds__(kNmsThreads, 4) nms_kernel(const tscd_nms_args args, int smem_cap, int only_redo) {
+__global__ void __launch_bounds__(kNmsThreads, 6) nms_kernel(const tscd_nms_args args, int smem_cap, int only_redo) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int frame = blockIdx.x;
     if (only_redo && args.keep_count[frame] != -1) return;
@@ -441,8 +441,9 @@ __global__ void __launch_bounds__(kNmsThreads, 4) nms_kernel(const tscd_nms_args
 // -------------------------------------------------------------------------------------------------------------
 constexpr int kNmsMatThreads = 512;
 constexpr int kNmsMatCap = 768;      // 768 x 24 words = 72 KB
+constexpr int kNmsMatInline = 256;   // the matrix shares the per-class kernel only up to 256 rows (8 KB)
 
-__global__ void __launch_bounds__(kNmsMatThreads) nms_matrix_kernel(const tscd_nms_args args, int smem_cap, int has_matrix) {
+__global__ void __launch_bounds__(kNmsMatThreads, 3) nms_matrix_kernel(const tscd_nms_args args, int smem_cap, int has_matrix) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int frame = blockIdx.x;
     int n = args.count[frame];
@@ -590,14 +591,18 @@ extern "C" int tscd_nms(const tscd_nms_args* a, void* stream) {
         // most candidates survive: per-class decomposition, then (cap <= 768) the suppression-matrix algorithm in the same
         // kernel or (larger caps) the lazy kernel for the frames the decomposition does not cover.  (The lazy kernel stops
         // early and wins when only the first few survivors are wanted, and for tiny frames.)
-        size_t smem_m = cap <= kNmsMatCap ? (size_t)cap * ((cap + 31) / 32) * 4 : 0;
+        // The suppression matrix (frames the per-class decomposition does not cover: cross-class overlaps, which the coordinate
+        // trick's class offsets make rare) stays in this kernel only while it is small: 72 KB of it for 750 rows would cap the
+        // kernel at two CTAs per SM for every frame -- larger frames mark themselves and take the second launch instead.
+        const bool inline_matrix = cap <= kNmsMatInline;
+        size_t smem_m = inline_matrix ? (size_t)cap * ((cap + 31) / 32) * 4 : 0;
         if (smem_m < cls_scratch_bytes(cap64)) smem_m = cls_scratch_bytes(cap64);
         smem_m += (size_t)cap64 * (8 + 16 + 4) + 16;
         if (cudaFuncSetAttribute(nms_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m) != cudaSuccess)
             return TSCD_ERR_CUDA;
-        nms_matrix_kernel<<<a->num_frames, kNmsMatThreads, smem_m, st>>>(*a, cap64, cap <= kNmsMatCap ? 1 : 0);
+        nms_matrix_kernel<<<a->num_frames, kNmsMatThreads, smem_m, st>>>(*a, cap64, inline_matrix ? 1 : 0);
         TSCD_CUDA_CHECK_LAUNCH();
-        if (cap <= kNmsMatCap) return TSCD_OK;
+        if (inline_matrix) return TSCD_OK;
         only_redo = 1;
     }
     if (cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
