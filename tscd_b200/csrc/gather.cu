@@ -118,7 +118,30 @@ __global__ void __launch_bounds__(256) rows_gather_kernel(const tscd_gather_args
     const int hd = args.head_dtype;
     // a null edge view: the edge rows are computed from the regression features afterwards (csrc/edge.cu), bank_edge is left alone
     const int np = args.feat_edge.ptr[0] ? 3 : 2;
-    if (bulk && wid == 0) {
+    if (bulk && n <= kGatherBulkRows) {
+        // Frames of <= 32 kept rows (mode A: 30): ONE batch whose bulk loads are issued by ALL eight warps, four rows each --
+        // cp.async.bulk is a uniform-datapath instruction, so the lanes of a warp issue theirs one after the other (~100 clk
+        // each); 90 loads from one warp were a third of the CTA's lifetime.  Warp 0 then waits for the bytes and stores the planes.
+        TB* const banks[3] = {reinterpret_cast<TB*>(args.bank_cls), reinterpret_cast<TB*>(args.bank_reg), reinterpret_cast<TB*>(args.bank_edge)};
+        if (threadIdx.x == 0) tc::mbar_expect_tx(&gbar, (uint32_t)(n * np) * 512u);
+        const int j = wid * 4 + lane;
+        if (lane < 4 && j < n) {
+            const AnchorPos p = anchor_pos(args.anchors, s_anchor[j]);
+            bulk_load(gsm + (0 * kGatherBulkRows + j) * 512, view_ptr<TF>(args.feat_cls, p.level, frame, p.local), 512, &gbar);
+            bulk_load(gsm + (1 * kGatherBulkRows + j) * 512, view_ptr<TF>(args.feat_reg, p.level, frame, p.local), 512, &gbar);
+            if (np == 3) bulk_load(gsm + (2 * kGatherBulkRows + j) * 512, view_ptr<TF>(args.feat_edge, p.level, frame, p.local), 512, &gbar);
+        }
+        if (wid == 0 && n > 0) {
+            tc::mbar_wait(&gbar, 0u, 700);
+            tc::fence_proxy_async();
+            if (lane < np) {
+                bulk_store(banks[lane] + (int64_t)row0 * 256, gsm + lane * kGatherBulkRows * 512, (uint32_t)n * 512u);
+                bulk_commit();
+                bulk_wait_read();
+            }
+            __syncwarp();
+        }
+    } else if (bulk && wid == 0) {
         TB* const banks[3] = {reinterpret_cast<TB*>(args.bank_cls), reinterpret_cast<TB*>(args.bank_reg), reinterpret_cast<TB*>(args.bank_edge)};
         for (int b0 = 0; b0 < n; b0 += kGatherBulkRows) {
             const int nb = min(kGatherBulkRows, n - b0);
