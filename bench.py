@@ -597,11 +597,15 @@ def run_e2e(args, cfg, st, dev, rank, world, dist, barrier):
     for i in range(2 * depth):             # warm-up: builds / captures every slot's plan
         res, res_ori, h2d, d2h = st.forward_host_collect(submit(i))
     # latency of one synchronous call (submit + collect, nothing else in flight)
-    call_ms = []
+    call_ms, call_split = [], []
     for i in range(3):
         tc0 = time.perf_counter()
-        st.forward_host_collect(submit(i))
+        ticket = submit(i)
+        tc1 = time.perf_counter()
+        tm = {}
+        st.forward_host_collect(ticket, timing=tm)
         call_ms.append(round(1e3 * (time.perf_counter() - tc0), 3))
+        call_split.append({"submit": round(1e3 * (tc1 - tc0), 3), "wait": round(tm["wait"], 3), "unpack": round(tm["unpack"], 3)})
     import gc
     gc.collect()                       # the main arm left graphs / input sets behind: collect before, not inside, the timed region
     barrier()
@@ -634,7 +638,7 @@ def run_e2e(args, cfg, st, dev, rank, world, dist, barrier):
         torch.cuda.synchronize()
         gpu_ms = ev0.elapsed_time(ev1)
     return {"value": world * Be * F * e2e_steps / e2e_s, "unit": "clip-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "ms_per_call": 1e3 * e2e_s / e2e_steps, "gpu_ms_per_call": gpu_ms, "sync_call_ms": call_ms,
+            "ms_per_call": 1e3 * e2e_s / e2e_steps, "gpu_ms_per_call": gpu_ms, "sync_call_ms": call_ms, "sync_call_split_ms": call_split, "plans_built": getattr(st, "host_plan_builds", None),
             "clips_per_gpu_per_step": Be, "chunk_clips": args.e2e_chunk, "steps": e2e_steps, "calls_in_flight": depth,
             "host_resident_input_bytes_per_step": nbytes(host),
             "note": "inputs are pinned HOST tensors; h2d counts the copied logits plus the rows read in place over PCIe"}

@@ -247,6 +247,7 @@ class AggregationStage:
         plan = plans.pop(key, None)
         if plan is None:
             plan = self._build_host_plan(host, hw, time_embedding, B, F, Lf, chunk_clips, strides, zero_copy_logits, graph, fused, lanes)
+            self.host_plan_builds = getattr(self, "host_plan_builds", 0) + 1      # diagnostics: a caller that keeps missing the plan cache pays a capture per call
         plans[key] = plan                                      # most recently used last
         while len(plans) > 8:
             idle = next((k for k, v in plans.items() if not v.get("busy") and v is not plan), None)
@@ -266,9 +267,13 @@ class AggregationStage:
         plan["busy"] = True
         return plan
 
-    def forward_host_collect(self, plan):
-        """Waits for a submitted call and returns (result, result_ori, h2d_bytes, d2h_bytes)."""
+    def forward_host_collect(self, plan, timing: Optional[dict] = None):
+        """Waits for a submitted call and returns (result, result_ori, h2d_bytes, d2h_bytes).  `timing` (optional dict) receives
+        the host-side split of this call in ms: 'wait' (event synchronise) and 'unpack' (detections -> reference list layout)."""
+        import time as _time
+        t0 = _time.perf_counter()
         plan["done"].synchronize()
+        t1 = _time.perf_counter()
         plan["busy"] = False
         result, result_ori, d2h = [], [], 0
         h2d = plan["h2d"]
@@ -278,6 +283,9 @@ class AggregationStage:
             result_ori += o
             d2h += nb
             h2d += zb
+        if timing is not None:
+            timing["wait"] = 1e3 * (t1 - t0)
+            timing["unpack"] = 1e3 * (_time.perf_counter() - t1)
         return result, result_ori, h2d, d2h
 
     def _build_host_plan(self, host, hw, time_embedding, B, F, Lf, chunk_clips, strides, zero_copy_logits, graph, fused, n_lanes):
