@@ -172,13 +172,16 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, extra="", period_ms=100):
+        self.index, self.rows, self.proc, self.period_ms = index, [], None, period_ms
+        if extra:                       # e.g. the PCIe link state for the host-buffer path
+            self.Q = self.Q + "," + extra
+        self.extra = [x for x in extra.split(",") if x]
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -196,8 +199,11 @@ class ClockSampler:
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": reasons, "samples": len(sm)}
+        for k, name in enumerate(self.extra):            # extra columns: the distinct values seen
+            out[name] = sorted({r[6 + k] for r in self.rows if len(r) > 6 + k})
+        return out
 
 
 # ------------------------------------------------------------------------------------------------- reference arms
@@ -594,8 +600,13 @@ def run_e2e(args, cfg, st, dev, rank, world, dist, barrier):
     def submit(i):
         return st.forward_host_submit(host, HW, te_e, Be, F, Lf, chunk_clips=args.e2e_chunk, slot=i % depth)
 
-    for i in range(2 * depth):             # warm-up: builds / captures every slot's plan
+    for i in range(2 * depth):                                        # warm-up: builds / captures every slot's plan ...
         res, res_ori, h2d, d2h = st.forward_host_collect(submit(i))
+    tw0, i = time.perf_counter(), 2 * depth
+    while time.perf_counter() - tw0 < 0.5:                            # ... then keeps the GPU and the PCIe link busy for half a second
+        res, res_ori, h2d, d2h = st.forward_host_collect(submit(i))   # (the pinned allocation above left them idle for seconds:
+        i += 1                                                        # P-state / link speed ramp up)
+    warm_calls = i
     # latency of one synchronous call (submit + collect, nothing else in flight)
     call_ms, call_split = [], []
     for i in range(3):
@@ -609,6 +620,8 @@ def run_e2e(args, cfg, st, dev, rank, world, dist, barrier):
     import gc
     gc.collect()                       # the main arm left graphs / input sets behind: collect before, not inside, the timed region
     barrier()
+    link = ClockSampler(torch.cuda.current_device(), extra="pstate,pcie.link.gen.current,pcie.link.width.current", period_ms=25)
+    link.start()
     t0 = time.perf_counter()
     e2e_steps = max(3, min(args.steps, 10)) * depth
     # throughput: `depth` calls in flight (double buffering): the PCIe phases of step i+1 overlap the compute tail and the host-side
@@ -622,6 +635,7 @@ def run_e2e(args, cfg, st, dev, rank, world, dist, barrier):
         res, res_ori, h2d, d2h = st.forward_host_collect(inflight.pop(0))
     barrier()
     e2e_s = time.perf_counter() - t0
+    link_state = link.stop()
     if world > 1:
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -638,7 +652,7 @@ def run_e2e(args, cfg, st, dev, rank, world, dist, barrier):
         torch.cuda.synchronize()
         gpu_ms = ev0.elapsed_time(ev1)
     return {"value": world * Be * F * e2e_steps / e2e_s, "unit": "clip-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "ms_per_call": 1e3 * e2e_s / e2e_steps, "gpu_ms_per_call": gpu_ms, "sync_call_ms": call_ms, "sync_call_split_ms": call_split, "plans_built": getattr(st, "host_plan_builds", None),
+            "ms_per_call": 1e3 * e2e_s / e2e_steps, "gpu_ms_per_call": gpu_ms, "sync_call_ms": call_ms, "sync_call_split_ms": call_split, "plans_built": getattr(st, "host_plan_builds", None), "warmup_calls": warm_calls, "gpu_state": link_state,
             "clips_per_gpu_per_step": Be, "chunk_clips": args.e2e_chunk, "steps": e2e_steps, "calls_in_flight": depth,
             "host_resident_input_bytes_per_step": nbytes(host),
             "note": "inputs are pinned HOST tensors; h2d counts the copied logits plus the rows read in place over PCIe"}
