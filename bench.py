@@ -581,6 +581,18 @@ def _capture(fn, dev):
     return g, out
 
 
+def _host_info():
+    """CPU budget of this container (the host-buffer path has a host part: one thread)."""
+    info = {"cpu_count": os.cpu_count(), "torch_threads": torch.get_num_threads()}
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            info["cgroup_cpu"] = open(path).read().strip()
+            break
+        except OSError:
+            pass
+    return info
+
+
 def run_e2e(args, cfg, st, dev, rank, world, dist, barrier):
     """Every step: H2D of what the kernels consume (copy stream, chunk-pipelined with compute), zero-copy gather of the kept
     proposals' feature rows out of the pinned feature planes, one D2H of the padded detections per chunk."""
@@ -652,7 +664,7 @@ def run_e2e(args, cfg, st, dev, rank, world, dist, barrier):
         torch.cuda.synchronize()
         gpu_ms = ev0.elapsed_time(ev1)
     return {"value": world * Be * F * e2e_steps / e2e_s, "unit": "clip-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "ms_per_call": 1e3 * e2e_s / e2e_steps, "gpu_ms_per_call": gpu_ms, "sync_call_ms": call_ms, "sync_call_split_ms": call_split, "plans_built": getattr(st, "host_plan_builds", None), "warmup_calls": warm_calls, "gpu_state": link_state,
+            "ms_per_call": 1e3 * e2e_s / e2e_steps, "gpu_ms_per_call": gpu_ms, "sync_call_ms": call_ms, "sync_call_split_ms": call_split, "plans_built": getattr(st, "host_plan_builds", None), "host": _host_info(), "warmup_calls": warm_calls, "gpu_state": link_state,
             "clips_per_gpu_per_step": Be, "chunk_clips": args.e2e_chunk, "steps": e2e_steps, "calls_in_flight": depth,
             "host_resident_input_bytes_per_step": nbytes(host),
             "note": "inputs are pinned HOST tensors; h2d counts the copied logits plus the rows read in place over PCIe"}

@@ -10,6 +10,7 @@ import math
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
+import numpy as np
 import torch
 
 from . import _lib as L
@@ -256,7 +257,10 @@ class AggregationStage:
             plans.pop(idle)
         if plan.get("busy"):
             raise RuntimeError("forward_host_submit: this slot still has a call in flight (collect it first or use another slot)")
-        plan["te_pin"].copy_(time_embedding)
+        # plain single-threaded memcpy: torch's copy_ / clone of more than 32 K elements open an OpenMP region, and waking (then
+        # spinning) the whole intra-op pool once per call starves this thread on CPU-quota-limited containers (measured: 8 ms here
+        # and 28 ms in the unpack instead of 0.2 / 0.5 ms, intermittently, depending on the box)
+        np.copyto(plan["te_pin"].numpy(), time_embedding.detach().cpu().numpy())
         if plan["graph"] is not None:
             with torch.cuda.stream(plan["launch"]):            # one launch stream per plan: calls of different slots run concurrently
                 plan["graph"].replay()
@@ -439,7 +443,7 @@ class AggregationStage:
         lists, nb = [], 0
         for name in ("det", "ori"):
             off = pk[name + "_offsets"][:nlf + 1].tolist()
-            table = pk[name + "_packed"][:off[-1]].clone()
+            table = torch.from_numpy(pk[name + "_packed"][:off[-1]].numpy().copy())     # single-threaded copy (see forward_host_submit)
             parts = table.split([off[i + 1] - off[i] for i in range(nlf)])
             lists.append([p_ if c else None for p_, c in zip(parts, det_c)])     # post_process.py:54-55: no candidates -> None
             nb += pk[name + "_packed"].numel() * 4 + pk[name + "_offsets"].numel() * 4
