@@ -146,3 +146,24 @@ def test_selected_edge_rows_vs_reference_module_on_cuda():
     want = want.float()
     scale = float(want.abs().max())
     assert scale > 0 and float((got - want).abs().max()) <= 3e-3 * scale, (float((got - want).abs().max()), scale)
+
+
+def test_selected_edge_rows_reject_odd_maps():
+    """The reference's stride-2 Haar transform has no same-size inverse on odd feature maps (its product of x_content and x_idwt
+    fails there too): the C-ABI reports the configuration as unsupported instead of producing rows."""
+    from tscd_b200 import ops, selection
+    hw = [(5, 6), (4, 4), (2, 2)]
+    Fn, C = 2, 3
+    g = torch.Generator().manual_seed(3)
+    feats = [[torch.randn(Fn, 256, h, w, generator=g).half().cuda().contiguous(memory_format=torch.channels_last) for h, w in hw] for _ in range(2)]
+    w3, b3, w1, b1 = _weights(5)
+    block = ops.EdgeBlock(w3, b3, w1, b1, dtype=torch.float16)
+    head, _ = oracle.synth_head_outputs(Fn, hw, C, dim=8, seed=4, obj_mean=2.0)
+    decoded = oracle.decode_outputs(head, hw, [8, 16, 32])
+    an = ops.AnchorSpec(hw)
+    hv = ops.HeadViews.from_fused(decoded.cuda(), an, apply_sigmoid=False, apply_decode=False)
+    cfg = selection.SelectionConfig(mode="B", use_pre_nms=False, minimal_limit=4, maximal_limit=8, max_proposals=an.num_anchors)
+    with pytest.raises(RuntimeError, match="unsupported"):
+        selection.select_and_gather(hv, (ops.view_levels(feats[0]), ops.view_levels(feats[1]), block), torch.float16, 256, cfg,
+                                    bank_dtype=torch.float16)
+    torch.cuda.synchronize()
